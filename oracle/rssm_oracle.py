@@ -1,0 +1,308 @@
+"""CPU oracle for the RSSM imagine / observe / lambda-return path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` may be imported by the
+product package (``world-model-rl_b200/wmrl``).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs use it, and there only as the checker / the CPU arm.
+
+What it is
+----------
+A functional restatement (explicit weight dicts, pre-drawn noise, no hidden RNG)
+of the reference algorithm in ``/root/reference/src/reflect``; every function
+cites the reference ``file:line`` it follows.  The arithmetic itself lives in
+PyTorch ATen (third-party, not vendored by the reference and not pinned in its
+``pyproject.toml:18-25``); the effective pin is this image's torch 2.11.0+cu128
+CPU kernels, so the oracle calls the same ATen ops (``F.linear``,
+``F.layer_norm``, ``F.elu``, ``F.softplus``, ``softmax``) in the same order.
+
+Parity pin
+----------
+The reference's own tests hold no numeric vectors for this path (SURVEY.md §8c:
+shapes / truthiness only), so the oracle is pinned against OUTPUTS OF THE
+REFERENCE ITSELF: ``oracle/gen_golden.py`` imports the unmodified reference
+modules in the build container, injects the noise by patching
+``torch.randn_like`` / ``torch.multinomial``, and stores weights, inputs, noise,
+outputs and actor gradients in ``tests/golden/*.npz``.  ``tests/test_oracle_golden.py``
+checks this file against those vectors (bit-for-bit on CPU where the op
+sequence is identical).
+
+Noise contract
+------------------------------
+continuous: ``eps[t]`` replaces ``torch.randn_like(mean)`` (``rssm.py:181``).
+discrete:   ``q[t] ~ Exp(1)`` replaces the noise drawn inside
+``torch.multinomial(p, 1, True)`` whose single-draw path is ``argmax(p / q)``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Weights = Dict[str, torch.Tensor]
+
+
+# --------------------------------------------------------------------------
+# Actor  (components/models/actor.py)
+# --------------------------------------------------------------------------
+def actor_num_layers(aw: Weights) -> int:
+    """Number of [Linear, LayerNorm, ELU] blocks (actor.py:22-37)."""
+    n = 0
+    while f"layers.{3 * n}.weight" in aw:
+        n += 1
+    return n
+
+
+def actor_hidden(aw: Weights, x: torch.Tensor) -> torch.Tensor:
+    """[Linear, LayerNorm(eps=1e-5), ELU] x La  (actor.py:23-37, 48)."""
+    for l in range(actor_num_layers(aw)):
+        w, b = aw[f"layers.{3 * l}.weight"], aw[f"layers.{3 * l}.bias"]
+        g, be = aw[f"layers.{3 * l + 1}.weight"], aw[f"layers.{3 * l + 1}.bias"]
+        x = F.linear(x, w, b)
+        x = F.layer_norm(x, (w.shape[0],), g, be, 1e-5)
+        x = F.elu(x)
+    return x
+
+
+def actor_mu(aw: Weights, x: torch.Tensor, action_scale: float, bound: torch.Tensor) -> torch.Tensor:
+    """deterministic action: tanh(mu / action_scale) * bound  (actor.py:48-52)."""
+    hid = actor_hidden(aw, x)
+    mu = F.linear(hid, aw["mu.weight"], aw["mu.bias"])
+    return torch.tanh(mu / action_scale) * bound
+
+
+def actor_dist(aw: Weights, x: torch.Tensor, action_scale: float, bound: torch.Tensor):
+    """(mu, std) of the Normal head: std = 1.0*sigmoid(.) + 0.01  (actor.py:54-59)."""
+    hid = actor_hidden(aw, x)
+    mu = torch.tanh(F.linear(hid, aw["mu.weight"], aw["mu.bias"]) / action_scale) * bound
+    std = 1.0 * torch.sigmoid(F.linear(hid, aw["stddev.weight"], aw["stddev.bias"])) + 0.01
+    return mu, std
+
+
+# --------------------------------------------------------------------------
+# Stochastic heads
+# --------------------------------------------------------------------------
+def gen_stoch_continuous(out: torch.Tensor, S: int, eps: torch.Tensor):
+    """mean,raw = split; std = softplus(raw)+0.1; stoch = mean + std*eps (rssm.py:179-181)."""
+    mean, raw = torch.split(out, S, dim=-1)
+    std = F.softplus(raw) + 0.1
+    stoch = mean + std * eps
+    return stoch, mean, std
+
+
+def categorical_probs(logits: torch.Tensor) -> torch.Tensor:
+    """torch.distributions.Categorical(logits=l).probs: normalise by logsumexp,
+    then softmax (state/discrete.py:27-29 -> OneHotCategoricalStraightThrough)."""
+    ln = logits - logits.logsumexp(dim=-1, keepdim=True)
+    return F.softmax(ln, dim=-1)
+
+
+def gen_stoch_discrete(out: torch.Tensor, C: int, S: int, q: torch.Tensor):
+    """logits = out.reshape(B, num_categories, stoch_size) (rssm.py:223) - the
+    categorical axis is the LAST one (size ``stoch_size``).  sample =
+    one_hot(argmax(p/q)) + (p - p.detach())  (state/discrete.py:27-32,
+    torch multinomial single-draw path)."""
+    logits = out.reshape(-1, C, S)
+    p = categorical_probs(logits)
+    idx = torch.argmax(p.detach() / q.reshape(-1, C, S), dim=-1)
+    onehot = F.one_hot(idx, S).to(p.dtype)
+    stoch = onehot + (p - p.detach())
+    return stoch.reshape(-1, C * S), logits, idx
+
+
+# --------------------------------------------------------------------------
+# RSSM single steps (rssm.py:53-91)
+# --------------------------------------------------------------------------
+def gru_cell(w: Weights, x: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
+    """torch.nn.GRUCell, gate order r,z,n; b_hn inside r*(.) (rssm.py:28,66)."""
+    gi = F.linear(x, w["rnn.weight_ih"], w["rnn.bias_ih"])
+    gh = F.linear(h, w["rnn.weight_hh"], w["rnn.bias_hh"])
+    i_r, i_z, i_n = gi.chunk(3, -1)
+    h_r, h_z, h_n = gh.chunk(3, -1)
+    r = torch.sigmoid(i_r + h_r)
+    z = torch.sigmoid(i_z + h_z)
+    n = torch.tanh(i_n + r * h_n)
+    return (1.0 - z) * n + z * h
+
+
+def prior_deter(w: Weights, stoch: torch.Tensor, action: torch.Tensor, deter: torch.Tensor):
+    """cat(stoch, a) -> Linear -> ELU -> GRUCell -> prior head (rssm.py:64-67)."""
+    sa = torch.cat([stoch, action], dim=-1)
+    x = F.elu(F.linear(sa, w["fc_state_action_embed.weight"], w["fc_state_action_embed.bias"]))
+    h = gru_cell(w, x, deter)
+    hid = F.elu(F.linear(h, w["state_prior.0.weight"], w["state_prior.0.bias"]))
+    out = F.linear(hid, w["state_prior.2.weight"], w["state_prior.2.bias"])
+    return h, out
+
+
+def posterior_out(w: Weights, deter: torch.Tensor, obs_embed: torch.Tensor) -> torch.Tensor:
+    """cat(deter, obs_embed) -> Linear -> ELU -> Linear (rssm.py:80-81)."""
+    hcat = torch.cat([deter, obs_embed], dim=-1)
+    hid = F.elu(F.linear(hcat, w["state_posterior.0.weight"], w["state_posterior.0.bias"]))
+    return F.linear(hid, w["state_posterior.2.weight"], w["state_posterior.2.bias"])
+
+
+# --------------------------------------------------------------------------
+# Rollouts
+# --------------------------------------------------------------------------
+def imagine_rollout(
+    variant: str,
+    w: Weights,
+    aw: Weights,
+    deter0: torch.Tensor,
+    stoch0: torch.Tensor,
+    noise: torch.Tensor,
+    n_steps: int,
+    S: int,
+    C: int = 1,
+    action_scale: float = 5.0,
+    bound: Optional[torch.Tensor] = None,
+):
+    """RSSMBase.imagine_rollout (rssm.py:123-140).
+
+    Per step: features.detach() -> actor(deterministic=True) -> prior.  Returns
+    per-step lists stacked on dim 1 WITHOUT the index-0 slot (the caller owns
+    the initial state): deter[B,H,D], stoch[B,H,S_in], dist (mean,std) or
+    logits[B,H,C,S], actions[B,H,A], idx[B,H,C] (discrete only).
+    noise: continuous eps[H,B,S]; discrete q[H,B,C,S].
+    """
+    if bound is None:
+        bound = torch.tensor(1.0, dtype=deter0.dtype)
+    deter, stoch = deter0, stoch0
+    o_deter, o_stoch, o_a, o_d1, o_d2, o_idx = [], [], [], [], [], []
+    for t in range(n_steps):
+        feat = torch.cat([deter, stoch], dim=-1).detach()          # rssm.py:135
+        action = actor_mu(aw, feat, action_scale, bound)            # rssm.py:136
+        deter, out = prior_deter(w, stoch, action, deter)           # rssm.py:137
+        if variant == "continuous":
+            stoch, mean, std = gen_stoch_continuous(out, S, noise[t])
+            o_d1.append(mean)
+            o_d2.append(std)
+        else:
+            stoch, logits, idx = gen_stoch_discrete(out, C, S, noise[t])
+            o_d1.append(logits)
+            o_idx.append(idx)
+        o_deter.append(deter)
+        o_stoch.append(stoch)
+        o_a.append(action)
+    res = {
+        "deter": torch.stack(o_deter, 1),
+        "stoch": torch.stack(o_stoch, 1),
+        "actions": torch.stack(o_a, 1),
+    }
+    if variant == "continuous":
+        res["mean"] = torch.stack(o_d1, 1)
+        res["std"] = torch.stack(o_d2, 1)
+    else:
+        res["logits"] = torch.stack(o_d1, 1)
+        res["idx"] = torch.stack(o_idx, 1)
+    return res
+
+
+def observe_rollout(
+    variant: str,
+    w: Weights,
+    obs_embeds: torch.Tensor,
+    actions: torch.Tensor,
+    noise_prior: torch.Tensor,
+    noise_post: torch.Tensor,
+    S: int,
+    C: int = 1,
+):
+    """RSSMBase.observe_rollout (rssm.py:93-121) from the zero initial state
+    (rssm.py:166-172 / 215-220).  For t in 0..T-2: prior_{t+1} = prior(a_t, post_t);
+    post_{t+1} = posterior(e_{t+1}, prior_{t+1}).  Two draws per step (prior
+    first, then posterior).  Returns dicts for the prior and posterior
+    sequences WITHOUT the index-0 slot, fields [B,T-1,...]."""
+    Bn, T = obs_embeds.shape[:2]
+    D = w["rnn.weight_hh"].shape[1]
+    S_in = S if variant == "continuous" else C * S
+    deter = torch.zeros(Bn, D, dtype=obs_embeds.dtype)
+    stoch = torch.zeros(Bn, S_in, dtype=obs_embeds.dtype)
+    pri: Dict[str, List[torch.Tensor]] = {k: [] for k in ("deter", "stoch", "d1", "d2", "idx")}
+    pos: Dict[str, List[torch.Tensor]] = {k: [] for k in ("deter", "stoch", "d1", "d2", "idx")}
+    for t in range(T - 1):
+        h, out = prior_deter(w, stoch, actions[:, t], deter)       # rssm.py:90 via :112
+        pout = posterior_out(w, h, obs_embeds[:, t + 1])           # rssm.py:91
+        if variant == "continuous":
+            ps, pm, pstd = gen_stoch_continuous(out, S, noise_prior[t])
+            qs, qm, qstd = gen_stoch_continuous(pout, S, noise_post[t])
+            pri["d1"].append(pm); pri["d2"].append(pstd)
+            pos["d1"].append(qm); pos["d2"].append(qstd)
+        else:
+            ps, pl, pi = gen_stoch_discrete(out, C, S, noise_prior[t])
+            qs, ql, qi = gen_stoch_discrete(pout, C, S, noise_post[t])
+            pri["d1"].append(pl); pri["idx"].append(pi)
+            pos["d1"].append(ql); pos["idx"].append(qi)
+        pri["deter"].append(h); pri["stoch"].append(ps)
+        pos["deter"].append(h); pos["stoch"].append(qs)
+        deter, stoch = h, qs                                        # rssm.py:120
+    names = ("mean", "std") if variant == "continuous" else ("logits", None)
+
+    def pack(d):
+        r = {"deter": torch.stack(d["deter"], 1), "stoch": torch.stack(d["stoch"], 1),
+             names[0]: torch.stack(d["d1"], 1)}
+        if variant == "continuous":
+            r["std"] = torch.stack(d["d2"], 1)
+        else:
+            r["idx"] = torch.stack(d["idx"], 1)
+        return r
+
+    return pack(pri), pack(pos)
+
+
+# --------------------------------------------------------------------------
+# lambda-return (trainers/value/value_trainer.py)
+# --------------------------------------------------------------------------
+def done_preprocess(dones: torch.Tensor) -> torch.Tensor:
+    """shift right by one, threshold at 0.5, running max (value_trainer.py:148-149)."""
+    d = torch.cat([torch.zeros_like(dones[:, [0]]), dones[:, :-1]], dim=1)
+    d, _ = (d > 0.5).float().cummax(dim=1)
+    return d
+
+
+def _rollout_value(V, r, d, gam, k):
+    """compute_rollout_value (value_trainer.py:62-86) on a slice."""
+    big_h = V.shape[1]
+    h = min(k, big_h - 1)
+    R = gam[:h][None, :, None] * r[:, :h] * (1 - d[:, :h])
+    final = gam[h] * V[:, [h]] * (1 - d[:, [h]])
+    return R.sum(1) + final[:, 0, :]
+
+
+def lambda_return_loops(V, r, d, gamma: float = 0.99, lam: float = 0.95):
+    """value_loss's target loop (value_trainer.py:126-134) over
+    compute_value_target (:88-113).  gamma table is built once, as an fp32 tensor
+    of length H (:71-74).  V,r,d: [B,H,1] -> targets [B,H,1]."""
+    H = V.shape[1]
+    gam = torch.tensor([gamma ** i for i in range(H)]).to(V.dtype)
+    outs = []
+    for i in range(H):
+        Vi, ri, di = V[:, i:], r[:, i:], d[:, i:]
+        big_h = Vi.shape[1]
+        val_sum = 0
+        for k in range(1, big_h - 1):
+            val_sum = val_sum + lam ** (k - 1) * _rollout_value(Vi, ri, di, gam, k)
+        final_val = _rollout_value(Vi, ri, di, gam, big_h)
+        outs.append((1 - lam) * val_sum + lam ** (big_h - 1) * final_val)
+    return torch.stack(outs, dim=1)
+
+
+def lambda_return_scan(V, r, d, gamma: float = 0.99, lam: float = 0.95):
+    """O(H) restatement of the loops above, exact in real
+    arithmetic: r'=r(1-d), V'=V(1-d); Std/M/T at H-1 = V'_{H-1}; for i<H-1:
+    Std_i = r'_i + g((1-l)V'_{i+1} + l Std_{i+1}); M_i = r'_i + g M_{i+1};
+    T_i = Std_i - (l^{n-2} - l^{n-1}) M_i, n = H-i (the reference's weights do
+    not sum to one; n=2 gives l*G_1)."""
+    H = V.shape[1]
+    rp, Vp = r * (1 - d), V * (1 - d)
+    out = [None] * H
+    Std = Vp[:, H - 1]
+    M = Vp[:, H - 1]
+    out[H - 1] = Vp[:, H - 1]
+    for i in range(H - 2, -1, -1):
+        n = H - i
+        Std = rp[:, i] + gamma * ((1 - lam) * Vp[:, i + 1] + lam * Std)
+        M = rp[:, i] + gamma * M
+        out[i] = Std - (lam ** (n - 2) - lam ** (n - 1)) * M
+    return torch.stack(out, dim=1)
