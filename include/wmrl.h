@@ -1,0 +1,207 @@
+/*
+ * wmrl.h - C ABI of the B200-native RSSM latent-imagination path.
+ *
+ * One shared object (libwmrl.so, sm_100a) replaces the ATen op chains that the
+ * reference (mauicv/world-model-rl, package `reflect`) executes in
+ *   - RSSMBase.imagine_rollout   src/reflect/components/rssm_world_model/rssm.py:123-140
+ *   - RSSMBase.observe_rollout   src/reflect/components/rssm_world_model/rssm.py:93-121
+ *   - Actor.forward(det.)        src/reflect/components/models/actor.py:47-52
+ *   - ValueGradTrainer lambda-return loops
+ *                                src/reflect/components/trainers/value/value_trainer.py:62-134
+ * The reference has no FFI of its own (pure Python over torch); the binding a
+ * maintainer adds is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a BORROWED CUDA device pointer that
+ *     outlives the call; nothing is allocated or freed inside;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, non-zero on error with the text in wmrl_last_error();
+ *   - all tensors are contiguous fp32 unless stated; weights are in torch
+ *     nn.Linear / nn.GRUCell layout, i.e. weight[out][in] row-major, GRU gate
+ *     order r,z,n (rssm.py:28-42);
+ *   - symbols: B rows, D deter_size, S stoch_size, C num_categories (1 for the
+ *     continuous variant), S_in = S (continuous) or C*S (discrete), P = 2S or
+ *     C*S, Hd hidden_size, E obs_embed_size, A action dim, Ha/La actor hidden
+ *     width / number of [Linear,LayerNorm,ELU] blocks, F = D + S_in.
+ *   - one host thread per device context; not re-entrant.
+ */
+#ifndef WMRL_H_
+#define WMRL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WMRL_ABI_VERSION 1
+#if defined(__GNUC__)
+#define WMRL_API __attribute__((visibility("default")))
+#else
+#define WMRL_API
+#endif
+#define WMRL_MAX_ACTOR_LAYERS 8
+
+enum { WMRL_CONTINUOUS = 0, WMRL_DISCRETE = 1 };
+enum { WMRL_FP32 = 0, WMRL_BF16 = 1 };
+/* dims.flags */
+enum {
+  WMRL_FLAG_WM_WGRAD = 1,   /* imagine_bwd: also produce RSSM weight grads (WM not frozen) */
+  WMRL_FLAG_SAVE_FOR_BWD = 2 /* imagine_fwd / observe_fwd: fill `saved` for a later *_bwd   */
+};
+
+typedef struct wmrl_dims {
+  int32_t variant;      /* WMRL_CONTINUOUS | WMRL_DISCRETE                               */
+  int32_t precision;    /* WMRL_FP32 (SIMT validation mode) | WMRL_BF16 (tcgen05 path)    */
+  int32_t B;            /* rows: start states (imagine) or sequences (observe)            */
+  int32_t T;            /* imagine: n_steps H.  observe: sequence length T (T-1 steps)    */
+  int32_t D, S, C, A, Hd, E;
+  int32_t Ha, La;       /* actor hidden width / blocks (ignored by observe)               */
+  float   action_scale; /* Actor.action_scale, actor.py:14                                */
+  int32_t flags;
+} wmrl_dims;
+
+/* RSSMBase.__init__ parameters, rssm.py:27-42.  state_dict names in comments. */
+typedef struct wmrl_rssm_params {
+  const float* embed_w;   /* fc_state_action_embed.weight [D, S_in+A] */
+  const float* embed_b;   /* fc_state_action_embed.bias   [D]         */
+  const float* w_ih;      /* rnn.weight_ih [3D, D]                    */
+  const float* w_hh;      /* rnn.weight_hh [3D, D]                    */
+  const float* b_ih;      /* rnn.bias_ih   [3D]                       */
+  const float* b_hh;      /* rnn.bias_hh   [3D]                       */
+  const float* prior0_w;  /* state_prior.0.weight [Hd, D]             */
+  const float* prior0_b;  /* state_prior.0.bias   [Hd]                */
+  const float* prior2_w;  /* state_prior.2.weight [P, Hd]             */
+  const float* prior2_b;  /* state_prior.2.bias   [P]                 */
+  const float* post0_w;   /* state_posterior.0.weight [Hd, D+E]       */
+  const float* post0_b;   /* state_posterior.0.bias   [Hd]            */
+  const float* post2_w;   /* state_posterior.2.weight [P, Hd]         */
+  const float* post2_b;   /* state_posterior.2.bias   [P]             */
+} wmrl_rssm_params;
+
+/* Same fields, writable: gradients are ACCUMULATED (+=) into them; the caller
+ * zero-fills.  Any pointer may be NULL (that gradient is skipped). */
+typedef struct wmrl_rssm_grads {
+  float *embed_w, *embed_b, *w_ih, *w_hh, *b_ih, *b_hh, *prior0_w, *prior0_b, *prior2_w,
+      *prior2_b, *post0_w, *post0_b, *post2_w, *post2_b;
+} wmrl_rssm_grads;
+
+/* Actor parameters, actor.py:22-39.  lin_* / ln_* index l is block l:
+ * layers.{3l}.weight [Ha, F or Ha], layers.{3l}.bias, layers.{3l+1}.weight/bias. */
+typedef struct wmrl_actor_params {
+  const float* lin_w[WMRL_MAX_ACTOR_LAYERS];
+  const float* lin_b[WMRL_MAX_ACTOR_LAYERS];
+  const float* ln_g[WMRL_MAX_ACTOR_LAYERS];
+  const float* ln_b[WMRL_MAX_ACTOR_LAYERS];
+  const float* mu_w;    /* mu.weight [A, Ha] */
+  const float* mu_b;    /* mu.bias   [A]     */
+  const float* bound;   /* Actor.bound broadcast to [A] (actor.py:20) */
+} wmrl_actor_params;
+
+typedef struct wmrl_actor_grads {
+  float* lin_w[WMRL_MAX_ACTOR_LAYERS];
+  float* lin_b[WMRL_MAX_ACTOR_LAYERS];
+  float* ln_g[WMRL_MAX_ACTOR_LAYERS];
+  float* ln_b[WMRL_MAX_ACTOR_LAYERS];
+  float* mu_w;
+  float* mu_b;
+} wmrl_actor_grads;
+
+WMRL_API int wmrl_abi_version(void);
+WMRL_API const char* wmrl_last_error(void);
+
+/* 1 if the running device can execute the sm_100a tcgen05 path, else 0. */
+WMRL_API int wmrl_device_supports_bf16(void);
+
+/* Buffer sizes the caller must provide.  op: 0 imagine, 1 observe. */
+WMRL_API size_t wmrl_saved_bytes(const wmrl_dims* d, int op);
+WMRL_API size_t wmrl_workspace_bytes(const wmrl_dims* d, int op);
+/* Bytes of the packed bf16 weight image used by the WMRL_BF16 path (0 if the
+ * shape is not supported by the tcgen05 kernel). */
+WMRL_API size_t wmrl_packed_bytes(const wmrl_dims* d);
+/* fp32 torch-layout params -> bf16 MMA-panel image (refreshed by the host
+ * wrapper whenever a parameter's version counter changes). */
+WMRL_API int wmrl_pack_weights(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
+                      void* packed, void* stream);
+
+/*
+ * RSSMBase.imagine_rollout (rssm.py:123-140): H steps of
+ *   a_t = Actor(cat(h_t, s_t).detach(), deterministic=True)     actor.py:47-52
+ *   h_{t+1}, out = prior(a_t, (h_t, s_t))                       rssm.py:64-67
+ *   s_{t+1} = sample(out, noise[t])                             rssm.py:179-181 / 223-227
+ * noise: continuous eps[H][B][S] ~ N(0,1); discrete q[H][B][C][S] ~ Exp(1)
+ *        (index = argmax(p/q), torch.multinomial's single-draw rule).
+ * Outputs (index 0 of deter_seq/stoch_seq is filled from deter0/stoch0; index 0
+ * of dist_a/dist_b is left to the caller, which owns the initial state):
+ *   deter_seq[B][H+1][D], stoch_seq[B][H+1][S_in],
+ *   dist_a = means[B][H+1][S] | logits[B][H+1][C][S], dist_b = stds[B][H+1][S] | NULL,
+ *   actions[B][H][A], idx[B][H][C] int32 (discrete, else NULL).
+ */
+WMRL_API int wmrl_imagine_fwd(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
+                     const void* packed, const float* deter0, const float* stoch0,
+                     const float* noise, float* deter_seq, float* stoch_seq, float* dist_a,
+                     float* dist_b, float* actions, int32_t* idx, void* saved, size_t saved_bytes,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * Hand-written BPTT of the above.  Actor input is detached (rssm.py:135): actor
+ * weights get gradient only through a_t -> dynamics.  g_* inputs are the
+ * upstream gradients of the forward outputs (same shapes; index 0 slots of
+ * g_deter_seq / g_stoch_seq flow straight to g_deter0 / g_stoch0).  Any g_*
+ * input may be NULL (treated as zero).  gw may be NULL unless
+ * WMRL_FLAG_WM_WGRAD is set.
+ */
+WMRL_API int wmrl_imagine_bwd(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
+                     const void* packed, const float* noise, const float* deter_seq,
+                     const float* stoch_seq, const float* dist_a, const float* dist_b,
+                     const float* actions, const void* saved, const float* g_deter_seq,
+                     const float* g_stoch_seq, const float* g_dist_a, const float* g_dist_b,
+                     const wmrl_actor_grads* gaw, const wmrl_rssm_grads* gw, float* g_deter0,
+                     float* g_stoch0, void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * RSSMBase.observe_rollout (rssm.py:93-121) from the zero initial state:
+ * for t in 0..T-2: prior_{t+1} = prior(a_t, post_t); post_{t+1} =
+ * posterior(e_{t+1}, prior_{t+1}) (rssm.py:84-91).  obs_embeds[B][T][E],
+ * actions[B][T][A]; noise_prior / noise_post [T-1][B][S] or [T-1][B][C][S].
+ * Outputs are the two sequences, fields [B][T][...]; index 0 is zero-filled
+ * for deter/stoch and left to the caller for the dist fields
+ * (rssm.py:166-172 / 215-220: discrete initial logits are torch.randn).
+ */
+WMRL_API int wmrl_observe_fwd(const wmrl_dims* d, const wmrl_rssm_params* w, const float* obs_embeds,
+                     const float* actions, const float* noise_prior, const float* noise_post,
+                     float* pri_deter, float* pri_stoch, float* pri_dist_a, float* pri_dist_b,
+                     float* post_deter, float* post_stoch, float* post_dist_a, float* post_dist_b,
+                     void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, void* stream);
+
+/* Full backward (weight grads + d obs_embeds + d actions) of observe_fwd, as
+ * needed by WorldModel.update (world_model.py:120-163). */
+WMRL_API int wmrl_observe_bwd(const wmrl_dims* d, const wmrl_rssm_params* w, const float* obs_embeds,
+                     const float* actions, const float* noise_prior, const float* noise_post,
+                     const float* pri_deter, const float* pri_stoch, const float* pri_dist_a,
+                     const float* pri_dist_b, const float* post_deter, const float* post_stoch,
+                     const float* post_dist_a, const float* post_dist_b, const void* saved,
+                     const float* g_pri_deter, const float* g_pri_stoch, const float* g_pri_dist_a,
+                     const float* g_pri_dist_b, const float* g_post_deter, const float* g_post_stoch,
+                     const float* g_post_dist_a, const float* g_post_dist_b,
+                     const wmrl_rssm_grads* gw, float* g_obs_embeds, float* g_actions, void* ws,
+                     size_t ws_bytes, void* stream);
+
+/*
+ * lambda-return targets of ValueGradTrainer.value_loss (value_trainer.py:126-134
+ * over :62-113) as one O(H) scan per row; V, r, d, out: [B][H] (the trailing
+ * singleton of the reference's [B,H,1] dropped).  d is the pre-processed 0/1
+ * done mask (value_trainer.py:148-149, see wmrl_done_mask).
+ */
+WMRL_API int wmrl_lambda_return_fwd(const float* V, const float* r, const float* d, float gamma, float lam,
+                           int32_t B, int32_t H, float* out, void* stream);
+WMRL_API int wmrl_lambda_return_bwd(const float* g_out, const float* d, float gamma, float lam, int32_t B,
+                           int32_t H, float* g_V, float* g_r, void* stream);
+/* shift right by one, threshold 0.5, running max (value_trainer.py:148-149). */
+WMRL_API int wmrl_done_mask(const float* dones, int32_t B, int32_t H, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WMRL_H_ */

@@ -1,0 +1,130 @@
+"""CPU-side checks: library loads and exports every symbol include/wmrl.h
+declares, host-side module API mirrors the reference, error paths are loud."""
+import os
+import re
+
+import pytest
+import torch
+
+import wmrl
+from wmrl import _lib
+from wmrl.parallel import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "wmrl.h")).read()
+    declared = set(re.findall(r"WMRL_API\s+[\w\s\*]+?\b(wmrl_\w+)\s*\(", header))
+    assert declared, "no prototypes found in include/wmrl.h"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.wmrl_abi_version() == _lib.ABI_VERSION
+
+
+def test_dims_struct_matches_header_order():
+    header = open(os.path.join(ROOT, "include", "wmrl.h")).read()
+    body = header.split("typedef struct wmrl_dims {")[1].split("} wmrl_dims;")[0]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
+    assert names == [f[0] for f in _lib.Dims._fields_]
+
+
+def test_size_queries_and_argument_errors_without_gpu():
+    import ctypes as C
+    lib = _lib.load()
+    d = _lib.Dims(variant=0, precision=0, B=8, T=5, D=32, S=8, C=1, A=2, Hd=32, E=16, Ha=64, La=2,
+                  action_scale=5.0, flags=0)
+    assert lib.wmrl_saved_bytes(C.byref(d), 0) == 4 * 5 * 8 * (2 * (2 * 64 + 1) + 2 + 5 * 32 + 32)
+    assert lib.wmrl_workspace_bytes(C.byref(d), 0) > 0
+    bad = _lib.Dims(variant=7, precision=0, B=8, T=5, D=32, S=8, C=1, A=2, Hd=32, E=16, Ha=64, La=2,
+                    action_scale=5.0, flags=0)
+    rc = lib.wmrl_imagine_fwd(C.byref(bad), None, None, *([None] * 11), 0, None, 0, None)
+    assert rc != 0 and b"variant" in lib.wmrl_last_error()
+    rc = lib.wmrl_lambda_return_fwd(None, None, None, 0.99, 0.95, 4, 0, None, None)
+    assert rc != 0
+
+
+def test_state_dict_keys_match_reference():
+    r = wmrl.DiscreteRSSM(32, 32, 8, 4, 64, 1)
+    assert list(r.state_dict()) == [
+        "rnn.weight_ih", "rnn.weight_hh", "rnn.bias_ih", "rnn.bias_hh", "fc_state_action_embed.weight",
+        "fc_state_action_embed.bias", "state_prior.0.weight", "state_prior.0.bias", "state_prior.2.weight",
+        "state_prior.2.bias", "state_posterior.0.weight", "state_posterior.0.bias", "state_posterior.2.weight",
+        "state_posterior.2.bias"]
+    assert r.state_dict()["fc_state_action_embed.weight"].shape == (32, 33)
+    a = wmrl.Actor(64, 1, 1, 3, 64)
+    assert list(a.state_dict()) == [f"layers.{i}.{k}" for i in (0, 1, 3, 4, 6, 7) for k in ("weight", "bias")] + \
+        ["mu.weight", "mu.bias", "stddev.weight", "stddev.bias"]
+    c = wmrl.ValueCritic(20, 3, 16)
+    assert "layers.9.weight" in c.state_dict()
+
+
+def test_no_cpu_fallback():
+    r, a = wmrl.ContinuousRSSM(16, 16, 4, 8, 1), wmrl.Actor(20, 1, 1.0, 1, 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        r.imagine_rollout(r.initial_state(2), a, 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        r.observe_rollout(torch.zeros(2, 3, 8), torch.zeros(2, 3, 1))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        wmrl.functional.lambda_return(torch.zeros(2, 3, 1), torch.zeros(2, 3, 1), torch.zeros(2, 3, 1), 0.9, 0.9)
+
+
+def test_eager_single_step_api():
+    """prior/posterior/observe_step stay callable at B=1 (memory_actor.py:34-57)."""
+    torch.manual_seed(0)
+    for rssm in (wmrl.ContinuousRSSM(16, 16, 4, 8, 2), wmrl.DiscreteRSSM(16, 16, 4, 3, 8, 2)):
+        s = rssm.initial_state(1)
+        pri, post = rssm.observe_step(torch.randn(1, 8), torch.randn(1, 2), s)
+        assert pri.deter_state.shape == (1, 16) and torch.equal(pri.deter_state, post.deter_state)
+        assert post.get_features().shape == (1, 16 + rssm.flat_stoch_size)
+    actor = wmrl.Actor(20, 2, [1.0, 2.0], 2, 16)
+    wm = wmrl.WorldModel(torch.nn.Linear(5, 8), torch.nn.Linear(20, 5), wmrl.DenseModel(1, 20, 8, 1),
+                         wmrl.DenseModel(1, 20, 8, 1), wmrl.ContinuousRSSM(16, 16, 4, 8, 2))
+    pol = wmrl.WorldModelActor(wm, actor)
+    pol.reset()
+    a = pol(torch.randn(1, 5))
+    assert a.shape == (1, 2) and float(a[0, 1].abs()) <= 2.0
+
+
+def test_state_containers_follow_reference_contracts():
+    """shape contracts of rssm_world_model/tests/test_continuous_states.py / test_discrete_states.py"""
+    s = wmrl.InternalStateContinuous(torch.zeros(3, 5), torch.zeros(3, 2), torch.zeros(3, 2), torch.ones(3, 2))
+    seq = s.to_sequence()
+    assert seq.shapes == ((3, 1, 5), (3, 1, 2), (3, 1, 2), (3, 1, 2))
+    assert seq.get_features().shape == (3, 0, 7)
+    seq.append_(s); seq.append_(s)
+    assert seq.get_features().shape == (3, 2, 7) and seq[1].mean.shape == (3, 2)
+    assert seq.flatten_batch_time().deter_state.shape == (6, 5)
+    assert seq.get_dist().sample().shape == (3, 2, 2)
+    assert seq.get_last().get_features().shape == (3, 7)
+    d = wmrl.InternalStateDiscrete.from_logits(torch.zeros(3, 5), torch.randn(3, 4, 6))
+    assert d.stoch_state.shape == (3, 24) and set(d.stoch_state.unique().tolist()) <= {0.0, 1.0}
+    dseq = d.to_sequence(); dseq.append_(d)
+    assert dseq.get_dist().sample().shape == (3, 1, 4, 6)
+    moved = dseq.detach(); assert moved is not dseq and moved.logits.shape == (3, 2, 4, 6)
+    assert wmrl.InternalStateContinuous.from_mean_std(torch.zeros(2, 3), torch.zeros(2, 2), torch.ones(2, 2)).stoch_state.shape == (2, 2)
+
+
+def test_freeze_parameters_restores_flags():
+    m = torch.nn.Linear(2, 2)
+    m.bias.requires_grad_(False)
+    with wmrl.FreezeParameters([m]):
+        assert not m.weight.requires_grad and not m.training
+    assert m.weight.requires_grad and not m.bias.requires_grad and m.training
+
+
+def test_shard_range_partitions():
+    for n, w in ((10, 4), (65536, 8), (3, 8), (0, 2)):
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1

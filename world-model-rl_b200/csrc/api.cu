@@ -1,0 +1,190 @@
+// C ABI of libwmrl (include/wmrl.h): argument checking and dispatch between the
+// fp32 SIMT path (f32_path.cu) and the bf16 tcgen05 path (tc_imagine.cu).
+#include <mutex>
+
+#include "common.cuh"
+
+namespace wmrl {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int check_dims(const wmrl_dims* d, int op) {
+  WMRL_REQUIRE(d != nullptr, "dims is NULL");
+  WMRL_REQUIRE(d->variant == WMRL_CONTINUOUS || d->variant == WMRL_DISCRETE, "bad variant");
+  WMRL_REQUIRE(d->precision == WMRL_FP32 || d->precision == WMRL_BF16, "bad precision");
+  WMRL_REQUIRE(d->B >= 0 && d->T >= 0, "negative B/T");
+  WMRL_REQUIRE(d->D > 0 && d->S > 0 && d->A > 0 && d->Hd > 0, "D,S,A,Hd must be positive");
+  if (d->variant == WMRL_DISCRETE) WMRL_REQUIRE(d->C > 0, "discrete variant needs C > 0");
+  if (op == 0) {
+    WMRL_REQUIRE(d->Ha > 0 && d->La > 0 && d->La <= WMRL_MAX_ACTOR_LAYERS, "bad actor shape");
+    WMRL_REQUIRE(d->action_scale != 0.f, "action_scale must be non-zero");
+  } else {
+    WMRL_REQUIRE(d->E > 0, "observe needs E > 0");
+  }
+  return 0;
+}
+
+static int require_device() {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error(std::string("wmrl: no CUDA device: ") + cudaGetErrorString(e));
+    return 3;
+  }
+  return 0;
+}
+
+}  // namespace wmrl
+
+using namespace wmrl;
+
+extern "C" {
+
+int wmrl_abi_version(void) { return WMRL_ABI_VERSION; }
+const char* wmrl_last_error(void) { return g_last_error.c_str(); }
+
+int wmrl_device_supports_bf16(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+  return p.major == 10 ? 1 : 0;
+}
+
+size_t wmrl_saved_bytes(const wmrl_dims* d, int op) {
+  if (check_dims(d, op)) return 0;
+  Dims dd(*d);
+  return f32_saved_bytes(dd, op);
+}
+
+size_t wmrl_workspace_bytes(const wmrl_dims* d, int op) {
+  if (check_dims(d, op)) return 0;
+  Dims dd(*d);
+  size_t a = f32_workspace_bytes(dd, op);
+  if (d->precision == WMRL_BF16 && op == 0) {
+    size_t b = tc_workspace_bytes(dd);
+    if (b > a) a = b;
+  }
+  return a;
+}
+
+size_t wmrl_packed_bytes(const wmrl_dims* d) {
+  if (check_dims(d, 0)) return 0;
+  Dims dd(*d);
+  if (!tc_supported(dd)) return 0;
+  return tc_packed_bytes(dd);
+}
+
+int wmrl_pack_weights(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
+                      void* packed, void* stream) {
+  if (int r = check_dims(d, 0)) return r;
+  WMRL_REQUIRE(w && aw && packed, "pack_weights: NULL argument");
+  Dims dd(*d);
+  WMRL_REQUIRE(tc_supported(dd), "pack_weights: shape not supported by the tcgen05 path");
+  if (int r = require_device()) return r;
+  return tc_pack_weights(dd, w, aw, packed, (cudaStream_t)stream);
+}
+
+int wmrl_imagine_fwd(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
+                     const void* packed, const float* deter0, const float* stoch0,
+                     const float* noise, float* deter_seq, float* stoch_seq, float* dist_a,
+                     float* dist_b, float* actions, int32_t* idx, void* saved, size_t saved_bytes,
+                     void* ws, size_t ws_bytes, void* stream) {
+  if (int r = check_dims(d, 0)) return r;
+  WMRL_REQUIRE(w && aw, "imagine_fwd: NULL weights");
+  Dims dd(*d);
+  if (dd.B == 0 || dd.T == 0) return 0;
+  WMRL_REQUIRE(deter0 && stoch0 && noise && deter_seq && stoch_seq && dist_a && actions,
+               "imagine_fwd: NULL tensor");
+  WMRL_REQUIRE(dd.variant == WMRL_DISCRETE || dist_b, "imagine_fwd: continuous needs dist_b (stds)");
+  WMRL_REQUIRE(ws && ws_bytes >= wmrl_workspace_bytes(d, 0), "imagine_fwd: workspace too small");
+  if (int r = require_device()) return r;
+  const bool save = (d->flags & WMRL_FLAG_SAVE_FOR_BWD) != 0;
+  if (save)
+    WMRL_REQUIRE(saved && saved_bytes >= f32_saved_bytes(dd, 0), "imagine_fwd: saved buffer too small");
+  if (d->precision == WMRL_BF16) {
+    WMRL_REQUIRE(tc_supported(dd), "imagine_fwd: shape not supported by the bf16 tcgen05 path");
+    WMRL_REQUIRE(packed, "imagine_fwd: bf16 path needs the packed weight image");
+    WMRL_REQUIRE(wmrl_device_supports_bf16(), "imagine_fwd: bf16 path needs an sm_100 device");
+    WMRL_REQUIRE(!save, "imagine_fwd: bf16 path does not record activations; the backward "
+                        "recomputes them (call the fp32 forward with SAVE_FOR_BWD)");
+    return tc_imagine_fwd(dd, w, aw, packed, deter0, stoch0, noise, deter_seq, stoch_seq, dist_a,
+                          dist_b, actions, idx, ws, (cudaStream_t)stream);
+  }
+  return f32_imagine_fwd(dd, w, aw, deter0, stoch0, noise, deter_seq, stoch_seq, dist_a, dist_b,
+                         actions, idx, save ? (float*)saved : nullptr, (float*)ws,
+                         (cudaStream_t)stream);
+}
+
+int wmrl_imagine_bwd(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
+                     const void* packed, const float* noise, const float* deter_seq,
+                     const float* stoch_seq, const float* dist_a, const float* dist_b,
+                     const float* actions, const void* saved, const float* g_deter_seq,
+                     const float* g_stoch_seq, const float* g_dist_a, const float* g_dist_b,
+                     const wmrl_actor_grads* gaw, const wmrl_rssm_grads* gw, float* g_deter0,
+                     float* g_stoch0, void* ws, size_t ws_bytes, void* stream) {
+  (void)packed;
+  if (int r = check_dims(d, 0)) return r;
+  WMRL_REQUIRE(w && aw && gaw, "imagine_bwd: NULL weights / grads");
+  Dims dd(*d);
+  if (dd.B == 0 || dd.T == 0) return 0;
+  WMRL_REQUIRE(noise && deter_seq && stoch_seq && dist_a && actions && saved, "imagine_bwd: NULL tensor");
+  WMRL_REQUIRE(!(d->flags & WMRL_FLAG_WM_WGRAD) || gw, "imagine_bwd: WM_WGRAD needs gw");
+  WMRL_REQUIRE(ws && ws_bytes >= wmrl_workspace_bytes(d, 0), "imagine_bwd: workspace too small");
+  if (int r = require_device()) return r;
+  return f32_imagine_bwd(dd, w, aw, noise, deter_seq, stoch_seq, dist_a, dist_b, actions,
+                         (const float*)saved, g_deter_seq, g_stoch_seq, g_dist_a, g_dist_b, gaw, gw,
+                         g_deter0, g_stoch0, (float*)ws, (cudaStream_t)stream);
+}
+
+int wmrl_observe_fwd(const wmrl_dims* d, const wmrl_rssm_params* w, const float* obs_embeds,
+                     const float* actions, const float* noise_prior, const float* noise_post,
+                     float* pri_deter, float* pri_stoch, float* pri_dist_a, float* pri_dist_b,
+                     float* post_deter, float* post_stoch, float* post_dist_a, float* post_dist_b,
+                     void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, void* stream) {
+  if (int r = check_dims(d, 1)) return r;
+  WMRL_REQUIRE(w, "observe_fwd: NULL weights");
+  Dims dd(*d);
+  if (dd.B == 0 || dd.T == 0) return 0;
+  WMRL_REQUIRE(pri_deter && pri_stoch && pri_dist_a && post_deter && post_stoch && post_dist_a,
+               "observe_fwd: NULL output");
+  WMRL_REQUIRE(dd.T == 1 || (obs_embeds && actions && noise_prior && noise_post), "observe_fwd: NULL input");
+  WMRL_REQUIRE(dd.variant == WMRL_DISCRETE || (pri_dist_b && post_dist_b), "observe_fwd: continuous needs stds");
+  WMRL_REQUIRE(ws && ws_bytes >= wmrl_workspace_bytes(d, 1), "observe_fwd: workspace too small");
+  const bool save = (d->flags & WMRL_FLAG_SAVE_FOR_BWD) != 0;
+  if (save && dd.T > 1)
+    WMRL_REQUIRE(saved && saved_bytes >= f32_saved_bytes(dd, 1), "observe_fwd: saved buffer too small");
+  if (int r = require_device()) return r;
+  return f32_observe_fwd(dd, w, obs_embeds, actions, noise_prior, noise_post, pri_deter, pri_stoch,
+                         pri_dist_a, pri_dist_b, post_deter, post_stoch, post_dist_a, post_dist_b,
+                         save ? (float*)saved : nullptr, (float*)ws, (cudaStream_t)stream);
+}
+
+int wmrl_observe_bwd(const wmrl_dims* d, const wmrl_rssm_params* w, const float* obs_embeds,
+                     const float* actions, const float* noise_prior, const float* noise_post,
+                     const float* pri_deter, const float* pri_stoch, const float* pri_dist_a,
+                     const float* pri_dist_b, const float* post_deter, const float* post_stoch,
+                     const float* post_dist_a, const float* post_dist_b, const void* saved,
+                     const float* g_pri_deter, const float* g_pri_stoch, const float* g_pri_dist_a,
+                     const float* g_pri_dist_b, const float* g_post_deter, const float* g_post_stoch,
+                     const float* g_post_dist_a, const float* g_post_dist_b,
+                     const wmrl_rssm_grads* gw, float* g_obs_embeds, float* g_actions, void* ws,
+                     size_t ws_bytes, void* stream) {
+  if (int r = check_dims(d, 1)) return r;
+  WMRL_REQUIRE(w && gw, "observe_bwd: NULL weights / grads");
+  Dims dd(*d);
+  if (dd.B == 0 || dd.T <= 1) return 0;
+  WMRL_REQUIRE(obs_embeds && actions && noise_prior && noise_post && pri_deter && pri_dist_a &&
+                   post_deter && post_stoch && post_dist_a && saved,
+               "observe_bwd: NULL tensor");
+  WMRL_REQUIRE(ws && ws_bytes >= wmrl_workspace_bytes(d, 1), "observe_bwd: workspace too small");
+  if (int r = require_device()) return r;
+  return f32_observe_bwd(dd, w, obs_embeds, actions, noise_prior, noise_post, pri_deter, pri_stoch,
+                         pri_dist_a, pri_dist_b, post_deter, post_stoch, post_dist_a, post_dist_b,
+                         (const float*)saved, g_pri_deter, g_pri_stoch, g_pri_dist_a, g_pri_dist_b,
+                         g_post_deter, g_post_stoch, g_post_dist_a, g_post_dist_b, gw, g_obs_embeds,
+                         g_actions, (float*)ws, (cudaStream_t)stream);
+}
+
+}  // extern "C"

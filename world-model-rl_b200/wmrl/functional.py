@@ -1,0 +1,426 @@
+"""torch.autograd bindings of the libwmrl C ABI.
+
+Three custom Functions - imagine rollout (forward + hand-written actor BPTT),
+observe rollout (forward + full backward) and the lambda-return scan - each a
+thin marshalling layer: allocate outputs / workspace with torch, pass raw device
+pointers and the current CUDA stream to the C ABI, never compute on the host.
+There is no fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+# parameter order used for the flat lists handed to the autograd Functions
+RSSM_ORDER = _lib.RSSM_FIELDS
+
+
+@dataclass(frozen=True)
+class PathConfig:
+    """Static shape/config of one call (mirrors wmrl_dims)."""
+    variant: int
+    D: int
+    S: int
+    C: int
+    A: int
+    Hd: int
+    E: int
+    Ha: int = 0
+    La: int = 0
+    action_scale: float = 5.0
+    precision: int = _lib.FP32
+
+    @property
+    def S_in(self) -> int:
+        return self.S * (self.C if self.variant == _lib.DISCRETE else 1)
+
+    @property
+    def dist_width(self) -> int:
+        return self.S_in if self.variant == _lib.DISCRETE else self.S
+
+    def dims(self, B: int, T: int, flags: int = 0, precision: Optional[int] = None) -> _lib.Dims:
+        return _lib.Dims(variant=self.variant, precision=self.precision if precision is None else precision,
+                         B=B, T=T, D=self.D, S=self.S, C=self.C if self.variant == _lib.DISCRETE else 1,
+                         A=self.A, Hd=self.Hd, E=self.E, Ha=self.Ha, La=self.La,
+                         action_scale=self.action_scale, flags=flags)
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("wmrl: the RSSM path runs only on CUDA tensors (no CPU fallback); "
+                               "move the modules and inputs to a B200 device")
+        dev = dev or t.device
+        if t.device != dev:
+            raise RuntimeError(f"wmrl: tensors on different devices ({t.device} vs {dev})")
+    return dev
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _stream_ptr(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _rssm_ptrs(params: Sequence[Optional[torch.Tensor]]) -> _lib.RssmPtrs:
+    s = _lib.RssmPtrs()
+    for name, t in zip(RSSM_ORDER, params):
+        setattr(s, name, _lib.ptr(t))
+    return s
+
+
+def _actor_layout(La: int) -> List[str]:
+    """flat order of actor tensors: per block (lin_w, lin_b, ln_g, ln_b), then mu_w, mu_b."""
+    names = []
+    for l in range(La):
+        names += [f"lin_w{l}", f"lin_b{l}", f"ln_g{l}", f"ln_b{l}"]
+    return names + ["mu_w", "mu_b"]
+
+
+def _actor_ptrs(params: Sequence[Optional[torch.Tensor]], La: int, bound: Optional[torch.Tensor], grads=False):
+    s = _lib.ActorGradPtrs() if grads else _lib.ActorPtrs()
+    for l in range(La):
+        s.lin_w[l] = _lib.ptr(params[4 * l + 0])
+        s.lin_b[l] = _lib.ptr(params[4 * l + 1])
+        s.ln_g[l] = _lib.ptr(params[4 * l + 2])
+        s.ln_b[l] = _lib.ptr(params[4 * l + 3])
+    s.mu_w = _lib.ptr(params[4 * La])
+    s.mu_b = _lib.ptr(params[4 * La + 1])
+    if not grads:
+        s.bound = _lib.ptr(bound)
+    return s
+
+
+def _bytes(n: int, dev) -> torch.Tensor:
+    return torch.empty(max(int(n), 16), dtype=torch.uint8, device=dev)
+
+
+# ----------------------------------------------------------------------------
+# packed bf16 weight image cache (refreshed when a parameter's version changes)
+# ----------------------------------------------------------------------------
+class PackedWeights:
+    def __init__(self):
+        self.key = None
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, cfg: PathConfig, rssm_p: Sequence[torch.Tensor], actor_p: Sequence[torch.Tensor],
+            bound: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        key = (cfg, tuple((p.data_ptr(), p._version) for p in list(rssm_p) + list(actor_p)))
+        if self.key == key and self.buf is not None:
+            return self.buf
+        dev = rssm_p[0].device
+        d = cfg.dims(0, 0, precision=_lib.BF16)
+        n = lib.wmrl_packed_bytes(C.byref(d))
+        if n == 0:
+            raise RuntimeError("wmrl: this shape is not supported by the bf16 tcgen05 path; use precision='fp32'")
+        buf = _bytes(n, dev)
+        r32 = [_f32c(p) for p in rssm_p]
+        a32 = [_f32c(p) for p in actor_p]
+        w, aw = _rssm_ptrs(r32), _actor_ptrs(a32, cfg.La, bound)
+        _lib.check(lib.wmrl_pack_weights(C.byref(d), C.byref(w), C.byref(aw), buf.data_ptr(), _stream_ptr(dev)),
+                   "wmrl_pack_weights")
+        self.key, self.buf = key, buf
+        return buf
+
+
+# ----------------------------------------------------------------------------
+# imagine
+# ----------------------------------------------------------------------------
+class ImagineRollout(torch.autograd.Function):
+    """outputs: deter_seq[B,H+1,D], stoch_seq[B,H+1,S_in], dist_a, dist_b, actions[B,H,A], idx.
+
+    inputs after the static ones: deter0, stoch0, init_da, init_db (initial
+    mean/std or logits -> index 0 of the dist outputs), noise, bound, then the
+    actor tensors (``_actor_layout``) and the 14 RSSM tensors (``RSSM_ORDER``).
+    """
+
+    @staticmethod
+    def forward(ctx, cfg: PathConfig, H: int, packed, deter0, stoch0, init_da, init_db, noise, bound, *params):
+        lib = _lib.load()
+        n_actor = 4 * cfg.La + 2
+        actor_p, rssm_p = params[:n_actor], params[n_actor:]
+        dev = _require_cuda(deter0, stoch0, noise, bound, *params)
+        B = deter0.shape[0]
+        disc = cfg.variant == _lib.DISCRETE
+        need_bwd = any(ctx.needs_input_grad)
+        a32 = [_f32c(p) for p in actor_p]
+        r32 = [_f32c(p) for p in rssm_p]
+        d0, s0, nz, bd = _f32c(deter0), _f32c(stoch0), _f32c(noise), _f32c(bound)
+        T1 = H + 1
+        deter_seq = torch.empty(B, T1, cfg.D, device=dev)
+        stoch_seq = torch.empty(B, T1, cfg.S_in, device=dev)
+        if disc:
+            dist_a = torch.empty(B, T1, cfg.C, cfg.S, device=dev)
+            dist_b = None
+            idx = torch.empty(B, H, cfg.C, dtype=torch.int32, device=dev)
+        else:
+            dist_a = torch.empty(B, T1, cfg.S, device=dev)
+            dist_b = torch.empty(B, T1, cfg.S, device=dev)
+            idx = None
+        actions = torch.empty(B, H, cfg.A, device=dev)
+        # the tcgen05 kernel does not record activations; when a backward will
+        # follow, the fp32 chain runs (and records) instead - see DESIGN.md
+        precision = cfg.precision
+        if need_bwd and precision == _lib.BF16:
+            precision = _lib.FP32
+        flags = _lib.FLAG_SAVE_FOR_BWD if need_bwd else 0
+        d = cfg.dims(B, H, flags, precision)
+        saved_n = lib.wmrl_saved_bytes(C.byref(d), _lib.OP_IMAGINE) if need_bwd else 0
+        saved = _bytes(saved_n, dev) if need_bwd else None
+        ws_n = lib.wmrl_workspace_bytes(C.byref(d), _lib.OP_IMAGINE)
+        ws = _bytes(ws_n, dev)
+        w, aw = _rssm_ptrs(r32), _actor_ptrs(a32, cfg.La, bd)
+        if B > 0 and H > 0:
+            _lib.check(lib.wmrl_imagine_fwd(
+                C.byref(d), C.byref(w), C.byref(aw), _lib.ptr(packed) if precision == _lib.BF16 else None,
+                d0.data_ptr(), s0.data_ptr(), nz.data_ptr(), deter_seq.data_ptr(), stoch_seq.data_ptr(),
+                dist_a.data_ptr(), _lib.ptr(dist_b), actions.data_ptr(), _lib.ptr(idx), _lib.ptr(saved),
+                saved_n, ws.data_ptr(), ws_n, _stream_ptr(dev)), "wmrl_imagine_fwd")
+        else:
+            deter_seq[:, 0], stoch_seq[:, 0] = d0, s0
+        dist_a[:, 0] = init_da.detach()
+        if dist_b is not None:
+            dist_b[:, 0] = init_db.detach()
+        ctx.cfg, ctx.H, ctx.n_actor = cfg, H, n_actor
+        ctx.has_b = dist_b is not None
+        if need_bwd:
+            ctx.save_for_backward(nz, bd, deter_seq, stoch_seq, dist_a,
+                                  dist_b if dist_b is not None else torch.empty(0, device=dev),
+                                  actions, saved, *a32, *r32)
+        outs = (deter_seq, stoch_seq, dist_a)
+        if dist_b is not None:
+            outs += (dist_b,)
+        ctx.mark_non_differentiable(actions)
+        if idx is not None:
+            ctx.mark_non_differentiable(idx)
+            return outs + (actions, idx)
+        return outs + (actions,)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        lib = _lib.load()
+        cfg, H, n_actor = ctx.cfg, ctx.H, ctx.n_actor
+        nz, bd, deter_seq, stoch_seq, dist_a, dist_b, actions, saved, *rest = ctx.saved_tensors
+        a32, r32 = rest[:n_actor], rest[n_actor:]
+        dev = deter_seq.device
+        B = deter_seq.shape[0]
+        g_deter, g_stoch, g_da = gouts[0], gouts[1], gouts[2]
+        g_db = gouts[3] if ctx.has_b else None
+
+        def prep(g):
+            return None if g is None else g.to(torch.float32).contiguous()
+
+        g_deter, g_stoch, g_da, g_db = prep(g_deter), prep(g_stoch), prep(g_da), prep(g_db)
+        # which inputs need gradients (inputs: cfg,H,packed,deter0,stoch0,init_da,init_db,noise,bound,*params)
+        need = ctx.needs_input_grad
+        base = 9
+        need_rssm = any(need[base + n_actor:])
+        flags = _lib.FLAG_SAVE_FOR_BWD | (_lib.FLAG_WM_WGRAD if need_rssm else 0)
+        d = cfg.dims(B, H, flags, _lib.FP32)
+        ga = [torch.zeros_like(p) for p in a32]
+        gr = [torch.zeros_like(p) for p in r32] if need_rssm else [None] * len(r32)
+        g_d0 = torch.zeros(B, cfg.D, device=dev)
+        g_s0 = torch.zeros(B, cfg.S_in, device=dev)
+        ws_n = lib.wmrl_workspace_bytes(C.byref(d), _lib.OP_IMAGINE)
+        ws = _bytes(ws_n, dev)
+        w, aw = _rssm_ptrs(r32), _actor_ptrs(a32, cfg.La, bd)
+        gaw = _actor_ptrs(ga, cfg.La, None, grads=True)
+        gw = _rssm_ptrs(gr)
+        if B > 0 and H > 0:
+            _lib.check(lib.wmrl_imagine_bwd(
+                C.byref(d), C.byref(w), C.byref(aw), None, nz.data_ptr(), deter_seq.data_ptr(),
+                stoch_seq.data_ptr(), dist_a.data_ptr(), _lib.ptr(dist_b if ctx.has_b else None),
+                actions.data_ptr(), saved.data_ptr(), _lib.ptr(g_deter), _lib.ptr(g_stoch), _lib.ptr(g_da),
+                _lib.ptr(g_db), C.byref(gaw), C.byref(gw) if need_rssm else None, g_d0.data_ptr(),
+                g_s0.data_ptr(), ws.data_ptr(), ws_n, _stream_ptr(dev)), "wmrl_imagine_bwd")
+        else:
+            if g_deter is not None:
+                g_d0 = g_deter[:, 0].clone()
+            if g_stoch is not None:
+                g_s0 = g_stoch[:, 0].clone()
+        g_init_da = g_da[:, 0] if (g_da is not None and need[5]) else None
+        g_init_db = g_db[:, 0] if (g_db is not None and need[6]) else None
+        grads = [None, None, None, g_d0 if need[3] else None, g_s0 if need[4] else None, g_init_da, g_init_db,
+                 None, None]
+        for i, g in enumerate(ga):
+            grads.append(g if need[base + i] else None)
+        for i, g in enumerate(gr):
+            grads.append(g if (g is not None and need[base + n_actor + i]) else None)
+        return tuple(grads)
+
+
+# ----------------------------------------------------------------------------
+# observe
+# ----------------------------------------------------------------------------
+class ObserveRollout(torch.autograd.Function):
+    """inputs: cfg, obs_embeds[B,T,E], actions[B,T,A], noise_prior, noise_post, init_da, init_db
+    (index-0 dist slots of both sequences), 14 RSSM tensors.
+    outputs: (pri_deter, pri_stoch, pri_da[, pri_db], post_deter, post_stoch, post_da[, post_db])."""
+
+    @staticmethod
+    def forward(ctx, cfg: PathConfig, obs, act, noise_pri, noise_post, init_pri_da, init_pri_db, init_post_da,
+                init_post_db, *rssm_p):
+        lib = _lib.load()
+        dev = _require_cuda(obs, act, *rssm_p)
+        B, T = obs.shape[0], obs.shape[1]
+        disc = cfg.variant == _lib.DISCRETE
+        need_bwd = any(ctx.needs_input_grad)
+        r32 = [_f32c(p) for p in rssm_p]
+        ob, ac = _f32c(obs), _f32c(act)
+        n1 = _f32c(noise_pri) if noise_pri is not None else None
+        n2 = _f32c(noise_post) if noise_post is not None else None
+
+        def seq_bufs():
+            de = torch.empty(B, T, cfg.D, device=dev)
+            st = torch.empty(B, T, cfg.S_in, device=dev)
+            if disc:
+                return de, st, torch.empty(B, T, cfg.C, cfg.S, device=dev), None
+            return de, st, torch.empty(B, T, cfg.S, device=dev), torch.empty(B, T, cfg.S, device=dev)
+
+        pri, post = seq_bufs(), seq_bufs()
+        flags = _lib.FLAG_SAVE_FOR_BWD if need_bwd else 0
+        d = cfg.dims(B, T, flags, _lib.FP32)
+        saved_n = lib.wmrl_saved_bytes(C.byref(d), _lib.OP_OBSERVE) if need_bwd else 0
+        saved = _bytes(saved_n, dev) if need_bwd else None
+        ws_n = lib.wmrl_workspace_bytes(C.byref(d), _lib.OP_OBSERVE)
+        ws = _bytes(ws_n, dev)
+        w = _rssm_ptrs(r32)
+        if B > 0 and T > 0:
+            _lib.check(lib.wmrl_observe_fwd(
+                C.byref(d), C.byref(w), ob.data_ptr(), ac.data_ptr(), _lib.ptr(n1), _lib.ptr(n2),
+                pri[0].data_ptr(), pri[1].data_ptr(), pri[2].data_ptr(), _lib.ptr(pri[3]),
+                post[0].data_ptr(), post[1].data_ptr(), post[2].data_ptr(), _lib.ptr(post[3]),
+                _lib.ptr(saved), saved_n, ws.data_ptr(), ws_n, _stream_ptr(dev)), "wmrl_observe_fwd")
+        if T > 0:
+            pri[2][:, 0] = init_pri_da.detach()
+            post[2][:, 0] = init_post_da.detach()
+            if not disc:
+                pri[3][:, 0] = init_pri_db.detach()
+                post[3][:, 0] = init_post_db.detach()
+        ctx.cfg, ctx.disc = cfg, disc
+        if need_bwd:
+            empty = torch.empty(0, device=dev)
+            ctx.save_for_backward(ob, ac, n1 if n1 is not None else empty, n2 if n2 is not None else empty,
+                                  pri[0], pri[1], pri[2], pri[3] if pri[3] is not None else empty,
+                                  post[0], post[1], post[2], post[3] if post[3] is not None else empty,
+                                  saved, *r32)
+        if disc:
+            return pri[0], pri[1], pri[2], post[0], post[1], post[2]
+        return pri + post
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        lib = _lib.load()
+        cfg, disc = ctx.cfg, ctx.disc
+        (ob, ac, n1, n2, p_de, p_st, p_da, p_db, q_de, q_st, q_da, q_db, saved, *r32) = ctx.saved_tensors
+        dev = ob.device
+        B, T = ob.shape[0], ob.shape[1]
+
+        def prep(g):
+            return None if g is None else g.to(torch.float32).contiguous()
+
+        if disc:
+            g = [prep(x) for x in gouts]
+            gp = (g[0], g[1], g[2], None)
+            gq = (g[3], g[4], g[5], None)
+        else:
+            g = [prep(x) for x in gouts]
+            gp, gq = tuple(g[0:4]), tuple(g[4:8])
+        d = cfg.dims(B, T, _lib.FLAG_SAVE_FOR_BWD, _lib.FP32)
+        gr = [torch.zeros_like(p) for p in r32]
+        g_obs = torch.zeros_like(ob)
+        g_act = torch.zeros_like(ac)
+        ws_n = lib.wmrl_workspace_bytes(C.byref(d), _lib.OP_OBSERVE)
+        ws = _bytes(ws_n, dev)
+        w, gw = _rssm_ptrs(r32), _rssm_ptrs(gr)
+        if B > 0 and T > 1:
+            _lib.check(lib.wmrl_observe_bwd(
+                C.byref(d), C.byref(w), ob.data_ptr(), ac.data_ptr(), n1.data_ptr(), n2.data_ptr(),
+                p_de.data_ptr(), p_st.data_ptr(), p_da.data_ptr(), None if disc else p_db.data_ptr(),
+                q_de.data_ptr(), q_st.data_ptr(), q_da.data_ptr(), None if disc else q_db.data_ptr(),
+                saved.data_ptr(),
+                _lib.ptr(gp[0]), _lib.ptr(gp[1]), _lib.ptr(gp[2]), _lib.ptr(gp[3]),
+                _lib.ptr(gq[0]), _lib.ptr(gq[1]), _lib.ptr(gq[2]), _lib.ptr(gq[3]),
+                C.byref(gw), g_obs.data_ptr(), g_act.data_ptr(), ws.data_ptr(), ws_n, _stream_ptr(dev)),
+                "wmrl_observe_bwd")
+        need = ctx.needs_input_grad
+
+        def first(gseq):
+            return None if gseq is None else gseq[:, 0]
+
+        grads = [None, g_obs if need[1] else None, g_act if need[2] else None, None, None,
+                 first(gp[2]) if need[5] else None, first(gp[3]) if need[6] else None,
+                 first(gq[2]) if need[7] else None, first(gq[3]) if need[8] else None]
+        for i, gt in enumerate(gr):
+            grads.append(gt if need[9 + i] else None)
+        return tuple(grads)
+
+
+# ----------------------------------------------------------------------------
+# lambda-return
+# ----------------------------------------------------------------------------
+class LambdaReturn(torch.autograd.Function):
+    """targets[B,H] from V, r, d [B,H] (value_trainer.py:62-134 as one scan).
+    Linear in (V, r) for a given mask d, so the backward is the transposed scan;
+    no gradient flows through d (value_trainer.py:149 thresholds it)."""
+
+    @staticmethod
+    def forward(ctx, V, r, d, gamma: float, lam: float):
+        lib = _lib.load()
+        dev = _require_cuda(V, r, d)
+        B, H = V.shape
+        v32, r32, d32 = _f32c(V), _f32c(r), _f32c(d)
+        out = torch.empty(B, H, device=dev)
+        if B > 0:
+            _lib.check(lib.wmrl_lambda_return_fwd(v32.data_ptr(), r32.data_ptr(), d32.data_ptr(), gamma, lam,
+                                                  B, H, out.data_ptr(), _stream_ptr(dev)), "wmrl_lambda_return_fwd")
+        ctx.save_for_backward(d32)
+        ctx.gamma, ctx.lam = gamma, lam
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        (d32,) = ctx.saved_tensors
+        B, H = d32.shape
+        g = g_out.to(torch.float32).contiguous()
+        g_V, g_r = torch.empty_like(g), torch.empty_like(g)
+        if B > 0:
+            _lib.check(lib.wmrl_lambda_return_bwd(g.data_ptr(), d32.data_ptr(), ctx.gamma, ctx.lam, B, H,
+                                                  g_V.data_ptr(), g_r.data_ptr(), _stream_ptr(g.device)),
+                       "wmrl_lambda_return_bwd")
+        return g_V, g_r, None, None, None
+
+
+def lambda_return(V: torch.Tensor, r: torch.Tensor, d: torch.Tensor, gamma: float, lam: float) -> torch.Tensor:
+    """V, r, d: [B,H,1] (or [B,H]) -> targets of the same shape."""
+    shape = V.shape
+    if V.dim() == 3:
+        V, r, d = V[..., 0], r[..., 0], d[..., 0]
+    if V.shape[1] < 1:
+        raise ValueError("lambda_return needs H >= 1")
+    return LambdaReturn.apply(V, r, d, float(gamma), float(lam)).reshape(shape)
+
+
+def done_mask(dones: torch.Tensor) -> torch.Tensor:
+    """shift right, threshold at 0.5, running max (value_trainer.py:148-149)."""
+    lib = _lib.load()
+    dev = _require_cuda(dones)
+    shape = dones.shape
+    d2 = _f32c(dones.reshape(shape[0], shape[1]))
+    out = torch.empty_like(d2)
+    if d2.shape[0] > 0:
+        _lib.check(lib.wmrl_done_mask(d2.data_ptr(), d2.shape[0], d2.shape[1], out.data_ptr(), _stream_ptr(dev)),
+                   "wmrl_done_mask")
+    return out.reshape(shape)

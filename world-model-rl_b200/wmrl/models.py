@@ -1,0 +1,41 @@
+"""Adjacent MLP heads kept in plain torch (cuBLAS): ``DenseModel`` (reward /
+done / state enc-dec heads, rssm_world_model/models.py:3-37) and ``ValueCritic``
+(trainers/value/critic.py:4-29).  They consume the ``features[B,H,F]`` the
+native rollout returns; fusing them onto it is SURVEY.md §8(f) rank 1."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+
+def _mlp(in_dim, hidden, depth, out_dim, act, layernorm=True):
+    layers, width = [], in_dim
+    for _ in range(depth):
+        layers.append(nn.Linear(width, hidden))
+        if layernorm:
+            layers.append(nn.LayerNorm(hidden))
+        layers.append(act())
+        width = hidden
+    layers.append(nn.Linear(width, out_dim))
+    return nn.Sequential(*layers)
+
+
+class DenseModel(nn.Module):
+    def __init__(self, depth: int = 3, input_dim: int = 230, hidden_dim: int = 256, output_dim: int = 1,
+                 hidden_act=nn.SiLU, output_act=nn.Identity, use_layernorm: bool = True):
+        super().__init__()
+        self.fc = _mlp(input_dim, hidden_dim, depth, output_dim, hidden_act, use_layernorm)
+        self.output_act = output_act()
+
+    def forward(self, z: torch.Tensor) -> torch.Tensor:
+        return self.output_act(self.fc(z))
+
+
+class ValueCritic(nn.Module):
+    def __init__(self, state_dim, num_layers=3, hidden_dim=512):
+        super().__init__()
+        self.state_dim, self.num_layers, self.hidden_dim = state_dim, num_layers, hidden_dim
+        self.layers = _mlp(state_dim, hidden_dim, num_layers, 1, nn.ReLU, True)
+
+    def forward(self, x):
+        return self.layers(x)

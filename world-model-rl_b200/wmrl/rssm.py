@@ -1,0 +1,264 @@
+"""Drop-in RSSM modules: same constructor arguments, attributes, state_dict keys
+and method names as ``reflect.components.rssm_world_model.rssm`` (rssm.py:13-227),
+with ``imagine_rollout`` / ``observe_rollout`` executed by libwmrl kernels.
+
+* ``imagine_rollout(initial_states, actor, n_steps)`` -> one ``wmrl_imagine_fwd``
+  call (all H steps; the actor MLP, GRU, prior head and sampling fused in the
+  native path) registered as an autograd Function whose backward is the
+  hand-written BPTT ``wmrl_imagine_bwd``.
+* ``observe_rollout(obs_embeds, action_embs)`` -> ``wmrl_observe_fwd`` / ``_bwd``.
+* ``prior`` / ``posterior`` / ``observe_step`` stay eager torch: they are the
+  B=1 online-acting API (memory_actor.py:34-57), not the hot path.
+
+Extras over the reference signature are keyword-only: ``noise=`` (pre-drawn
+tensors, see ``draw_imagine_noise``), ``generator=``, ``return_actions=``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import _lib
+from .functional import ImagineRollout, ObserveRollout, PackedWeights, PathConfig
+from .state import (InternalStateContinuous, InternalStateContinuousSequence, InternalStateDiscrete,
+                    InternalStateDiscreteSequence)
+
+_PRECISIONS = {"fp32": _lib.FP32, "bf16": _lib.BF16}
+
+
+def _actor_tensors(actor: nn.Module):
+    """(La, Ha, flat tensor list in functional._actor_layout order) from an
+    Actor-shaped module (reference Actor or wmrl.actor.Actor)."""
+    try:
+        La, layers, mu = int(actor.num_layers), actor.layers, actor.mu
+    except AttributeError as e:  # pragma: no cover - defensive
+        raise TypeError("imagine_rollout needs an Actor-shaped module (layers/mu/num_layers/bound)") from e
+    flat = []
+    for l in range(La):
+        lin, ln = layers[3 * l], layers[3 * l + 1]
+        flat += [lin.weight, lin.bias, ln.weight, ln.bias]
+    flat += [mu.weight, mu.bias]
+    return La, int(actor.hidden_dim), flat
+
+
+class RSSMBase(nn.Module):
+    """Owns the weights of rssm.py:14-42 under identical names."""
+
+    variant = _lib.CONTINUOUS
+
+    def __init__(self, hidden_size: int, deter_size: int, stoch_size: int, obs_embed_size: int,
+                 parameterized_stoch_size: int, state_action_embed_input_size: int,
+                 precision: str = "fp32"):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.deter_size = deter_size
+        self.stoch_size = stoch_size
+        self.obs_embed_size = obs_embed_size
+        self.act = nn.ELU()
+        self.rnn = nn.GRUCell(deter_size, deter_size)
+        self.fc_state_action_embed = nn.Linear(state_action_embed_input_size, deter_size)
+        self.state_prior = nn.Sequential(
+            nn.Linear(deter_size, hidden_size), nn.ELU(), nn.Linear(hidden_size, parameterized_stoch_size))
+        self.state_posterior = nn.Sequential(
+            nn.Linear(deter_size + obs_embed_size, hidden_size), nn.ELU(),
+            nn.Linear(hidden_size, parameterized_stoch_size))
+        self.set_precision(precision)
+        self._packed = PackedWeights()
+
+    # ------------------------------------------------------------------ config
+    def set_precision(self, precision: str) -> "RSSMBase":
+        """'fp32' = SIMT validation mode, 'bf16' = tcgen05 tensor-core path."""
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        self.precision = precision
+        return self
+
+    @property
+    def num_groups(self) -> int:
+        return getattr(self, "num_categories", 1)
+
+    @property
+    def flat_stoch_size(self) -> int:
+        return self.stoch_size * (self.num_groups if self.variant == _lib.DISCRETE else 1)
+
+    def _rssm_tensors(self):
+        sd = dict(self.named_parameters())
+        return [sd[_lib.RSSM_KEYS[f]] for f in _lib.RSSM_FIELDS]
+
+    def _config(self, action_size: int, Ha: int = 0, La: int = 0, action_scale: float = 5.0) -> PathConfig:
+        return PathConfig(variant=self.variant, D=self.deter_size, S=self.stoch_size, C=self.num_groups,
+                          A=action_size, Hd=self.hidden_size, E=self.obs_embed_size, Ha=Ha, La=La,
+                          action_scale=float(action_scale), precision=_PRECISIONS[self.precision])
+
+    # --------------------------------------------------- eager single-step API
+    def initial_state_sequence(self, batch_size):
+        raise NotImplementedError
+
+    def initial_state(self, batch_size):
+        raise NotImplementedError
+
+    def generate_stoch_state(self, deter_state, dist: torch.Tensor):
+        raise NotImplementedError
+
+    def prior(self, action_emb: torch.Tensor, state):
+        """h_t = f(s_{t-1}, a_{t-1}, h_{t-1}); p(s_t | h_t)   (rssm.py:53-68)"""
+        x = self.act(self.fc_state_action_embed(torch.cat((state.stoch_state, action_emb), dim=-1)))
+        deter = self.rnn(x, state.deter_state)
+        return self.generate_stoch_state(deter, self.state_prior(deter))
+
+    def posterior(self, obs_embed: torch.Tensor, state):
+        """p(s_t | h_t, o_t)   (rssm.py:70-82)"""
+        out = self.state_posterior(torch.cat((state.deter_state, obs_embed), dim=-1))
+        return self.generate_stoch_state(state.deter_state, out)
+
+    def observe_step(self, obs_embed, action_emb, state):
+        prior_state = self.prior(action_emb, state)
+        return prior_state, self.posterior(obs_embed, prior_state)
+
+    # ------------------------------------------------------------ noise helpers
+    def draw_imagine_noise(self, n_steps: int, batch: int, device, generator: Optional[torch.Generator] = None):
+        """eps ~ N(0,1) [H,B,S] (continuous) or q ~ Exp(1) [H,B,C,S] (discrete):
+        the draws the reference makes inside generate_stoch_state."""
+        if self.variant == _lib.DISCRETE:
+            q = torch.empty(n_steps, batch, self.num_groups, self.stoch_size, device=device)
+            return q.exponential_(1.0, generator=generator)
+        return torch.randn(n_steps, batch, self.stoch_size, device=device, generator=generator)
+
+    # ------------------------------------------------------------- native paths
+    def imagine_rollout(self, initial_states, actor: nn.Module, n_steps: int, *, noise: Optional[torch.Tensor] = None,
+                        generator: Optional[torch.Generator] = None, return_actions: bool = False):
+        """rssm.py:123-140.  Returns the reference's Sequence type with fields
+        [B, n_steps+1, .] (index 0 = ``initial_states``)."""
+        device = next(actor.parameters()).device
+        La, Ha, actor_p = _actor_tensors(actor)
+        A = actor.mu.weight.shape[0]
+        cfg = self._config(A, Ha, La, getattr(actor, "action_scale", 5.0))
+        deter0 = initial_states.deter_state.to(device)
+        stoch0 = initial_states.stoch_state.to(device)
+        B = deter0.shape[0]
+        if deter0.shape[1] != self.deter_size or stoch0.shape[1] != self.flat_stoch_size:
+            raise ValueError(f"initial state shapes {tuple(deter0.shape)}, {tuple(stoch0.shape)} do not match "
+                             f"deter_size={self.deter_size}, flat stoch={self.flat_stoch_size}")
+        if actor.layers[0].weight.shape[1] != self.deter_size + self.flat_stoch_size:
+            raise ValueError("actor input_dim must equal deter_size + flat stoch size")
+        if noise is None:
+            noise = self.draw_imagine_noise(n_steps, B, device, generator)
+        noise = noise.to(device)
+        want = (n_steps, B, self.num_groups, self.stoch_size) if self.variant == _lib.DISCRETE else \
+            (n_steps, B, self.stoch_size)
+        if tuple(noise.shape) != want:
+            raise ValueError(f"noise must have shape {want}, got {tuple(noise.shape)}")
+        bound = torch.as_tensor(actor.bound, dtype=torch.float32, device=device).reshape(-1)
+        bound = bound.expand(A).contiguous() if bound.numel() == 1 else bound
+        if bound.numel() != A:
+            raise ValueError("actor.bound must be a scalar or have one entry per action dim")
+        rssm_p = self._rssm_tensors()
+        packed = None
+        if cfg.precision == _lib.BF16:
+            packed = self._packed.get(cfg, rssm_p, actor_p, bound)
+        if self.variant == _lib.DISCRETE:
+            init_da, init_db = initial_states.logits.to(device), None
+        else:
+            init_da, init_db = initial_states.mean.to(device), initial_states.std.to(device)
+        outs = ImagineRollout.apply(cfg, int(n_steps), packed, deter0, stoch0, init_da, init_db, noise, bound,
+                                    *actor_p, *rssm_p)
+        if self.variant == _lib.DISCRETE:
+            deter_seq, stoch_seq, logits, actions, _idx = outs
+            seq = InternalStateDiscreteSequence(deter_states=deter_seq, stoch_states=stoch_seq, logits=logits)
+        else:
+            deter_seq, stoch_seq, means, stds, actions = outs
+            seq = InternalStateContinuousSequence(deter_states=deter_seq, stoch_states=stoch_seq, means=means,
+                                                  stds=stds)
+        return (seq, actions) if return_actions else seq
+
+    def observe_rollout(self, obs_embeds: torch.Tensor, action_embs: torch.Tensor, *,
+                        noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                        generator: Optional[torch.Generator] = None):
+        """rssm.py:93-121.  Returns (prior_sequence, posterior_sequence), fields
+        [B, T, .]; index 0 is the zero initial state (discrete initial logits are
+        drawn with torch.randn as in rssm.py:219)."""
+        device = obs_embeds.device
+        B, T = obs_embeds.shape[0], obs_embeds.shape[1]
+        A = action_embs.shape[-1]
+        cfg = self._config(A)
+        steps = max(T - 1, 0)
+        if noise is None:
+            noise = (self.draw_imagine_noise(steps, B, device, generator),
+                     self.draw_imagine_noise(steps, B, device, generator))
+        n_pri, n_post = (n.to(device) for n in noise)
+        init_pri = self.initial_state(B)
+        init_pri.to(device)
+        init_post = self.initial_state(B)
+        init_post.to(device)
+        if self.variant == _lib.DISCRETE:
+            inits = (init_pri.logits, None, init_post.logits, None)
+        else:
+            inits = (init_pri.mean, init_pri.std, init_post.mean, init_post.std)
+        outs = ObserveRollout.apply(cfg, obs_embeds, action_embs.to(device), n_pri, n_post, *inits,
+                                    *self._rssm_tensors())
+        if self.variant == _lib.DISCRETE:
+            pri = InternalStateDiscreteSequence(deter_states=outs[0], stoch_states=outs[1], logits=outs[2])
+            post = InternalStateDiscreteSequence(deter_states=outs[3], stoch_states=outs[4], logits=outs[5])
+        else:
+            pri = InternalStateContinuousSequence(deter_states=outs[0], stoch_states=outs[1], means=outs[2],
+                                                  stds=outs[3])
+            post = InternalStateContinuousSequence(deter_states=outs[4], stoch_states=outs[5], means=outs[6],
+                                                   stds=outs[7])
+        return pri, post
+
+
+class ContinuousRSSM(RSSMBase):
+    """Gaussian latent (rssm.py:143-187)."""
+    variant = _lib.CONTINUOUS
+
+    def __init__(self, hidden_size: int, deter_size: int, stoch_size: int, obs_embed_size: int, action_size: int,
+                 precision: str = "fp32"):
+        super().__init__(hidden_size=hidden_size, deter_size=deter_size, stoch_size=stoch_size,
+                         obs_embed_size=obs_embed_size, parameterized_stoch_size=2 * stoch_size,
+                         state_action_embed_input_size=stoch_size + action_size, precision=precision)
+        self.action_size = action_size
+
+    def initial_state(self, batch_size):
+        z = lambda n: torch.zeros(batch_size, n)  # noqa: E731
+        return InternalStateContinuous(deter_state=z(self.deter_size), stoch_state=z(self.stoch_size),
+                                       mean=z(self.stoch_size), std=z(self.stoch_size))
+
+    def initial_state_sequence(self, batch_size):
+        return InternalStateContinuousSequence.from_init(self.initial_state(batch_size))
+
+    def generate_stoch_state(self, deter_state, dist: torch.Tensor):
+        mean, raw = dist.split(self.stoch_size, dim=-1)
+        std = nn.functional.softplus(raw) + 0.1
+        return InternalStateContinuous(deter_state=deter_state, stoch_state=mean + std * torch.randn_like(mean),
+                                       mean=mean, std=std)
+
+
+class DiscreteRSSM(RSSMBase):
+    """Categorical straight-through latent: ``num_categories`` independent groups,
+    each a categorical over ``stoch_size`` classes (rssm.py:190-227; the axis
+    naming follows the reference, rssm.py:223)."""
+    variant = _lib.DISCRETE
+
+    def __init__(self, hidden_size: int, deter_size: int, stoch_size: int, num_categories: int,
+                 obs_embed_size: int, action_size: int, precision: str = "fp32"):
+        super().__init__(hidden_size=hidden_size, deter_size=deter_size, stoch_size=stoch_size,
+                         obs_embed_size=obs_embed_size, parameterized_stoch_size=num_categories * stoch_size,
+                         state_action_embed_input_size=num_categories * stoch_size + action_size,
+                         precision=precision)
+        self.num_categories = num_categories
+        self.action_size = action_size
+
+    def initial_state(self, batch_size):
+        return InternalStateDiscrete(
+            deter_state=torch.zeros(batch_size, self.deter_size),
+            stoch_state=torch.zeros(batch_size, self.stoch_size * self.num_categories),
+            logits=torch.randn(batch_size, self.num_categories, self.stoch_size))
+
+    def initial_state_sequence(self, batch_size):
+        return InternalStateDiscreteSequence.from_init(self.initial_state(batch_size))
+
+    def generate_stoch_state(self, deter_state, dist: torch.Tensor):
+        logits = dist.reshape(-1, self.num_categories, self.stoch_size)
+        return InternalStateDiscrete.from_logits(deter_state=deter_state, logits=logits)
