@@ -1,9 +1,749 @@
-// placeholder - replaced by the tcgen05 kernel
+// bf16 tensor-core path of RSSMBase.imagine_rollout (rssm.py:123-140), continuous
+// latent: ONE persistent kernel walks all H steps of a 128-row batch tile.
+//
+//   * the tile's latent state and every intermediate activation stay in shared
+//     memory as bf16 MMA A-operand panels ([k/8][128 rows][8] = tcgen05 K-major
+//     no-swizzle core-matrix layout); the fp32 master copy of h lives in the
+//     output tensor itself (L2-resident, one row per thread);
+//   * the ~9 dependent GEMMs of a step (actor x4, embed, GRU ih/hh, prior x2)
+//     are tcgen05.mma M=128 tiles with fp32 accumulators in TMEM; weights are
+//     pre-packed once into the exact per-stage operand panels and streamed
+//     L2 -> smem by the TMA engine (cp.async.bulk + mbarrier tx-count) through a
+//     ring, in the fixed order the MMA warp consumes them;
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread)
+//     and TMEM owner, warps 2-5 = epilogue (one TMEM lane = one batch row per
+//     thread, so LayerNorm statistics need no cross-thread reduction);
+//   * bias, LayerNorm+ELU, GRU gates, tanh squash, softplus and the
+//     reparameterised sample are fused into the TMEM->register epilogues, which
+//     write the next GEMM's A panel (bf16, smem) and the fp32 sequence outputs.
+//
+// The work is described by two host-built tables (same for every step): STAGES
+// (what the producer loads and the MMA thread issues) and JOBS (what the
+// epilogue warps do once a job's accumulator is complete).
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
+#include "tc_ptx.cuh"
+
 namespace wmrl {
-bool tc_supported(const Dims&) { return false; }
-size_t tc_packed_bytes(const Dims&) { return 0; }
-size_t tc_workspace_bytes(const Dims&) { return 0; }
-int tc_pack_weights(const Dims&, const wmrl_rssm_params*, const wmrl_actor_params*, void*, cudaStream_t) { set_error("tc path not built"); return 9; }
-int tc_imagine_fwd(const Dims&, const wmrl_rssm_params*, const wmrl_actor_params*, const void*, const float*, const float*, const float*, float*, float*, float*, float*, float*, int32_t*, void*, cudaStream_t) { set_error("tc path not built"); return 9; }
+
+// --------------------------------------------------------------------------
+// tables
+// --------------------------------------------------------------------------
+constexpr int kTileM = 128;
+constexpr int kSlotBytes = 16384;       // ring slot (one weight stage)
+constexpr int kMaxSmem = 232448;        // 227 KB opt-in limit on sm_100
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+
+enum : uint8_t { ST_FIRST_ACC = 1, ST_LAST_OF_JOB = 2, ST_FIRST_OF_JOB = 4, ST_DBUF = 8 };
+struct __align__(16) StageDesc {
+  uint32_t w_off16;   // byte offset / 16 of this stage in the packed stage area
+  uint16_t bytes16;   // stage bytes / 16
+  uint8_t nk16;       // number of K=16 MMAs in the stage
+  uint8_t flags;      // ST_*
+  uint16_t a_off16;   // smem byte offset / 16 of the A panel at the stage's first K step
+  uint16_t n;         // MMA N
+  uint16_t tmem_col;  // accumulator column (plus (job&1)*256 when ST_DBUF)
+  uint8_t dep;        // first stage of a job: wait for the epilogue of job (j - dep); 0 = none
+  uint8_t pad;
+};
+static_assert(sizeof(StageDesc) == 16, "StageDesc must be 16 bytes");
+
+enum : uint8_t { JOB_ACTOR_LN = 1, JOB_MU, JOB_DENSE_ELU, JOB_GRU, JOB_PRIOR2_CONT };
+struct __align__(16) JobDesc {
+  uint8_t type;
+  uint8_t dbuf;        // accumulator lives in the (job&1) half of TMEM
+  uint16_t n;          // padded accumulator width handled by the epilogue
+  uint16_t tmem_col;
+  uint16_t col0;       // GRU: first state column of the chunk
+  uint32_t dst_off;    // smem byte offset of the destination A panel (column 0 of it)
+  uint32_t p_off;      // float offset of this job's epilogue parameters
+  uint32_t aux;
+  uint32_t pad[3];
+};
+static_assert(sizeof(JobDesc) == 32, "JobDesc must be 32 bytes");
+
+struct PackOp {
+  const float* src;
+  int ld;
+  int row0_a, valid_a, pad_a, row0_b, valid_b, pad_b;
+  int k0, kvalid, nk8;
+  unsigned long long dst_off;
+};
+struct VecOp {
+  const float* src1;
+  const float* src2;
+  int off, valid, pad;
+  unsigned long long dst;   // float offset
+};
+
+struct TcParams {
+  const uint8_t* stage_data;
+  const StageDesc* stages;
+  const JobDesc* jobs;
+  const float* eparams;
+  const float* deter0;
+  const float* stoch0;
+  const float* noise;
+  float* deter_seq;
+  float* stoch_seq;
+  float* mean_seq;
+  float* std_seq;
+  float* actions;
+  int nstages, njobs;
+  int B, H, D, S, A, Dp, Sp, Ap, Ha, Hdp;
+  float inv_action_scale;
+  uint32_t off_h, off_s, off_a, off_x, off_h2;   // smem byte offsets of the A panels
+  uint32_t ring_off, bar_off;
+  int nslots, ntiles;
+};
+
+static inline int ceil16(int x) { return (x + 15) / 16 * 16; }
+
+struct Plan {
+  int Dp, Sp, Ap, Ha, Hdp, h2c, XW;
+  uint32_t off_h, off_s, off_a, off_x, off_h2, panels_bytes, ring_off, bar_off, smem_bytes;
+  int nslots;
+  std::vector<StageDesc> stages;
+  std::vector<JobDesc> jobs;
+  std::vector<PackOp> pack_ops;
+  std::vector<VecOp> vec_ops;
+  size_t eparams_floats = 0, data_bytes = 0;
+  size_t off_stage_tab, off_job_tab, off_packops, off_eparams, off_data, total_bytes;
+  bool ok = false;
+};
+
+struct RowSpec { int row0_a, valid_a, pad_a, row0_b, valid_b, pad_b; };
+struct Seg { uint32_t a_off; int kpad; const float* src; int ld; int k0; int kvalid; };
+
+static void add_acc_group(Plan& pl, const RowSpec& rs, const std::vector<Seg>& segs, int tmem_col,
+                          bool dbuf, bool first_of_job, int dep, bool last_of_job) {
+  const int N = rs.pad_a + rs.pad_b;
+  int per = kSlotBytes / (N * 32);
+  if (per < 1) per = 1;
+  if (per > 64) per = 64;
+  bool first_acc = true;
+  for (size_t si = 0; si < segs.size(); ++si) {
+    const Seg& sg = segs[si];
+    const int total = sg.kpad / 16;
+    for (int done = 0; done < total;) {
+      const int nk = std::min(per, total - done);
+      StageDesc st{};
+      st.w_off16 = (uint32_t)(pl.data_bytes / 16);
+      st.bytes16 = (uint16_t)(nk * N * 32 / 16);
+      st.nk16 = (uint8_t)nk;
+      st.flags = 0;
+      if (first_acc) st.flags |= ST_FIRST_ACC;
+      if (first_of_job && first_acc) { st.flags |= ST_FIRST_OF_JOB; st.dep = (uint8_t)dep; }
+      if (dbuf) st.flags |= ST_DBUF;
+      const bool last = (si + 1 == segs.size()) && (done + nk == total);
+      if (last && last_of_job) st.flags |= ST_LAST_OF_JOB;
+      st.a_off16 = (uint16_t)((sg.a_off + (uint32_t)done * 4096u) / 16);
+      st.n = (uint16_t)N;
+      st.tmem_col = (uint16_t)tmem_col;
+      pl.stages.push_back(st);
+      PackOp op{};
+      op.src = sg.src; op.ld = sg.ld;
+      op.row0_a = rs.row0_a; op.valid_a = rs.valid_a; op.pad_a = rs.pad_a;
+      op.row0_b = rs.row0_b; op.valid_b = rs.valid_b; op.pad_b = rs.pad_b;
+      op.k0 = sg.k0 + done * 16;
+      op.kvalid = std::max(0, sg.kvalid - done * 16);
+      op.nk8 = nk * 2;
+      op.dst_off = pl.data_bytes;
+      pl.pack_ops.push_back(op);
+      pl.data_bytes += (size_t)nk * N * 32;
+      done += nk;
+      first_acc = false;
+    }
+  }
 }
+
+static uint32_t add_vec(Plan& pl, const float* s1, const float* s2, int off, int valid, int pad) {
+  VecOp v{s1, s2, off, valid, pad, (unsigned long long)pl.eparams_floats};
+  pl.vec_ops.push_back(v);
+  const uint32_t at = (uint32_t)pl.eparams_floats;
+  pl.eparams_floats += pad;
+  return at;
+}
+
+// Build the per-step tables.  Weight pointers may be null (size / launch queries).
+static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw) {
+  Plan pl;
+  if (d.variant != WMRL_CONTINUOUS) return pl;
+  if (d.Ha % 32 != 0 || d.Ha > 512 || d.Ha < 32 || d.A > 16 || d.S > 128 || d.La < 1) return pl;
+  pl.Dp = ceil16(d.D); pl.Sp = ceil16(d.S); pl.Ap = 16; pl.Ha = d.Ha; pl.Hdp = ceil16(d.Hd);
+  if (pl.Hdp > 512 || pl.Dp > 4096) return pl;
+  pl.h2c = std::max(pl.Dp, pl.Hdp);
+  pl.XW = std::max(d.Ha, pl.h2c + pl.Dp);
+  pl.off_h = 0;
+  pl.off_s = pl.off_h + pl.Dp / 8 * 2048;
+  pl.off_a = pl.off_s + pl.Sp / 8 * 2048;
+  pl.off_x = pl.off_a + pl.Ap / 8 * 2048;
+  pl.off_h2 = pl.off_x + pl.h2c / 8 * 2048;
+  pl.panels_bytes = pl.off_x + pl.XW / 8 * 2048;
+  pl.ring_off = pl.panels_bytes;
+  const int avail = kMaxSmem - (int)pl.panels_bytes - 256;
+  pl.nslots = avail / kSlotBytes;
+  if (pl.nslots < 2) return pl;
+  if (pl.nslots > 8) pl.nslots = 8;
+  pl.bar_off = pl.ring_off + pl.nslots * kSlotBytes;
+  pl.smem_bytes = pl.bar_off + 256;
+  if (pl.panels_bytes / 16 > 65535) return pl;
+
+  const float* nul = nullptr;
+  auto W = [&](const float* const* p) { return p ? *p : nul; };
+  (void)W;
+  const int Ke = d.S_in + d.A;
+  // ---- actor blocks
+  for (int l = 0; l < d.La; ++l) {
+    JobDesc jb{};
+    jb.type = JOB_ACTOR_LN; jb.n = (uint16_t)d.Ha; jb.tmem_col = 0; jb.dst_off = pl.off_x;
+    const float* lw = aw ? aw->lin_w[l] : nul;
+    const uint32_t pb = add_vec(pl, aw ? aw->lin_b[l] : nul, nul, 0, d.Ha, d.Ha);
+    add_vec(pl, aw ? aw->ln_g[l] : nul, nul, 0, d.Ha, d.Ha);
+    add_vec(pl, aw ? aw->ln_b[l] : nul, nul, 0, d.Ha, d.Ha);
+    jb.p_off = pb;
+    pl.jobs.push_back(jb);
+    const int nchunks = (d.Ha + 255) / 256;
+    for (int nc = 0; nc < nchunks; ++nc) {
+      const int rows = std::min(256, d.Ha - nc * 256);
+      RowSpec rs{nc * 256, rows, rows, 0, 0, 0};
+      std::vector<Seg> segs;
+      if (l == 0) {
+        // A = [P_h | P_s]: contiguous panels, source columns [0,D) and [D,D+S)
+        segs.push_back({pl.off_h, pl.Dp, lw, d.F, 0, d.D});
+        segs.push_back({pl.off_s, pl.Sp, lw, d.F, d.D, d.S_in});
+      } else {
+        segs.push_back({pl.off_x, d.Ha, lw, d.Ha, 0, d.Ha});
+      }
+      add_acc_group(pl, rs, segs, nc * 256, false, nc == 0, 1, nc == nchunks - 1);
+    }
+  }
+  // ---- mu head
+  {
+    JobDesc jb{};
+    jb.type = JOB_MU; jb.n = 16; jb.tmem_col = 0; jb.dst_off = pl.off_a;
+    jb.p_off = add_vec(pl, aw ? aw->mu_b : nul, nul, 0, d.A, 16);
+    add_vec(pl, aw ? aw->bound : nul, nul, 0, d.A, 16);
+    pl.jobs.push_back(jb);
+    RowSpec rs{0, d.A, 16, 0, 0, 0};
+    add_acc_group(pl, rs, {{pl.off_x, d.Ha, aw ? aw->mu_w : nul, d.Ha, 0, d.Ha}}, 0, false, true, 1, true);
+  }
+  // ---- state-action embed: A = [P_s | P_a]
+  {
+    JobDesc jb{};
+    jb.type = JOB_DENSE_ELU; jb.n = (uint16_t)pl.Dp; jb.tmem_col = 0; jb.dst_off = pl.off_x;
+    jb.p_off = add_vec(pl, w ? w->embed_b : nul, nul, 0, d.D, pl.Dp);
+    pl.jobs.push_back(jb);
+    const float* ew = w ? w->embed_w : nul;
+    // N = Dp may exceed 256 -> chunks of 256 accumulator columns
+    const int nchunks = (pl.Dp + 255) / 256;
+    if (pl.Dp > 512) return pl;
+    for (int nc = 0; nc < nchunks; ++nc) {
+      const int padr = std::min(256, pl.Dp - nc * 256);
+      const int valid = std::max(0, std::min(padr, d.D - nc * 256));
+      RowSpec rs{nc * 256, valid, padr, 0, 0, 0};
+      add_acc_group(pl, rs, {{pl.off_s, pl.Sp, ew, Ke, 0, d.S_in}, {pl.off_a, pl.Ap, ew, Ke, d.S_in, d.A}},
+                    nc * 256, false, nc == 0, 1, nc == nchunks - 1);
+    }
+  }
+  // ---- GRU, chunks of 64 state columns: TMEM [r | z | i_n | h_n], double buffered
+  {
+    const uint32_t pb = add_vec(pl, w ? w->b_ih : nul, w ? w->b_hh : nul, 0, d.D, pl.Dp);       // b_r
+    add_vec(pl, w ? w->b_ih : nul, w ? w->b_hh : nul, d.D, d.D, pl.Dp);                         // b_z
+    add_vec(pl, w ? w->b_ih : nul, nul, 2 * d.D, d.D, pl.Dp);                                    // b_in
+    add_vec(pl, w ? w->b_hh : nul, nul, 2 * d.D, d.D, pl.Dp);                                    // b_hn
+    const int nchunks = (pl.Dp + 63) / 64;
+    for (int c = 0; c < nchunks; ++c) {
+      const int cw = std::min(64, pl.Dp - c * 64);
+      const int valid = std::max(0, std::min(cw, d.D - c * 64));
+      JobDesc jb{};
+      jb.type = JOB_GRU; jb.dbuf = 1; jb.n = (uint16_t)cw; jb.tmem_col = 0; jb.col0 = (uint16_t)(c * 64);
+      jb.dst_off = pl.off_h2; jb.p_off = pb;
+      pl.jobs.push_back(jb);
+      const float* wih = w ? w->w_ih : nul;
+      const float* whh = w ? w->w_hh : nul;
+      const int dep = (c < 2) ? (c + 1) : 2;   // chunk 0/1 wait for the embed epilogue, later ones for chunk c-2
+      RowSpec rz{c * 64, valid, cw, d.D + c * 64, valid, cw};
+      add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}, {pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 0, true,
+                    true, dep, false);
+      RowSpec rn{2 * d.D + c * 64, valid, cw, 0, 0, 0};
+      add_acc_group(pl, rn, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, 2 * cw, true, false, 0, false);
+      add_acc_group(pl, rn, {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 3 * cw, true, false, 0, true);
+    }
+  }
+  // ---- prior head
+  {
+    JobDesc jb{};
+    jb.type = JOB_DENSE_ELU; jb.n = (uint16_t)pl.Hdp; jb.tmem_col = 0; jb.dst_off = pl.off_x;
+    jb.p_off = add_vec(pl, w ? w->prior0_b : nul, nul, 0, d.Hd, pl.Hdp);
+    pl.jobs.push_back(jb);
+    const int nchunks = (pl.Hdp + 255) / 256;
+    for (int nc = 0; nc < nchunks; ++nc) {
+      const int padr = std::min(256, pl.Hdp - nc * 256);
+      const int valid = std::max(0, std::min(padr, d.Hd - nc * 256));
+      RowSpec rs{nc * 256, valid, padr, 0, 0, 0};
+      add_acc_group(pl, rs, {{pl.off_h2, pl.Dp, w ? w->prior0_w : nul, d.D, 0, d.D}}, nc * 256, false, nc == 0, 1,
+                    nc == nchunks - 1);
+    }
+  }
+  {
+    JobDesc jb{};
+    jb.type = JOB_PRIOR2_CONT; jb.n = (uint16_t)(2 * pl.Sp); jb.tmem_col = 0; jb.dst_off = pl.off_s;
+    jb.p_off = add_vec(pl, w ? w->prior2_b : nul, nul, 0, d.S, pl.Sp);
+    add_vec(pl, w ? w->prior2_b : nul, nul, d.S, d.S, pl.Sp);
+    pl.jobs.push_back(jb);
+    RowSpec rs{0, d.S, pl.Sp, d.S, d.S, pl.Sp};   // mean rows -> cols [0,Sp), raw rows -> [Sp,2Sp)
+    add_acc_group(pl, rs, {{pl.off_x, pl.Hdp, w ? w->prior2_w : nul, d.Hd, 0, d.Hd}}, 0, false, true, 1, true);
+  }
+  for (const StageDesc& st : pl.stages)
+    if ((int)st.bytes16 * 16 > kSlotBytes) return pl;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  pl.off_stage_tab = 256;
+  pl.off_job_tab = al(pl.off_stage_tab + pl.stages.size() * sizeof(StageDesc));
+  pl.off_packops = al(pl.off_job_tab + pl.jobs.size() * sizeof(JobDesc));
+  pl.off_eparams = al(pl.off_packops + pl.pack_ops.size() * sizeof(PackOp) + pl.vec_ops.size() * sizeof(VecOp));
+  pl.off_data = al(pl.off_eparams + pl.eparams_floats * sizeof(float));
+  pl.total_bytes = al(pl.off_data + pl.data_bytes);
+  pl.ok = true;
+  return pl;
+}
+
+bool tc_supported(const Dims& d) { return make_plan(d, nullptr, nullptr).ok; }
+size_t tc_packed_bytes(const Dims& d) {
+  Plan pl = make_plan(d, nullptr, nullptr);
+  return pl.ok ? pl.total_bytes : 0;
+}
+size_t tc_workspace_bytes(const Dims&) { return 256; }
+
+// --------------------------------------------------------------------------
+// weight packing kernels
+// --------------------------------------------------------------------------
+__global__ void pack_stage_kernel(const PackOp* __restrict__ ops, uint8_t* __restrict__ data) {
+  const PackOp op = ops[blockIdx.x];
+  const int N = op.pad_a + op.pad_b;
+  const int total = op.nk8 * N;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int kc = i / N, n = i % N;
+    int row = -1;
+    if (n < op.pad_a) {
+      if (n < op.valid_a) row = op.row0_a + n;
+    } else {
+      const int m = n - op.pad_a;
+      if (m < op.valid_b) row = op.row0_b + m;
+    }
+    __align__(16) __nv_bfloat16 out[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * 8 + e;
+      float v = 0.f;
+      if (row >= 0 && k < op.kvalid) v = op.src[(size_t)row * op.ld + op.k0 + k];
+      out[e] = __float2bfloat16_rn(v);
+    }
+    *reinterpret_cast<uint4*>(data + op.dst_off + (size_t)i * 16) = *reinterpret_cast<const uint4*>(out);
+  }
+}
+__global__ void pack_vec_kernel(const VecOp* __restrict__ ops, float* __restrict__ dst) {
+  const VecOp op = ops[blockIdx.x];
+  for (int i = threadIdx.x; i < op.pad; i += blockDim.x) {
+    float v = 0.f;
+    if (i < op.valid) {
+      v = op.src1[op.off + i];
+      if (op.src2) v += op.src2[op.off + i];
+    }
+    dst[op.dst + i] = v;
+  }
+}
+
+int tc_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
+                    void* packed, cudaStream_t st) {
+  Plan pl = make_plan(d, w, aw);
+  WMRL_REQUIRE(pl.ok, "pack_weights: unsupported shape");
+  uint8_t* base = (uint8_t*)packed;
+  // tables travel host -> device inside the packed image (synchronous for pageable memory)
+  WMRL_CUDA_OK(cudaMemcpyAsync(base + pl.off_stage_tab, pl.stages.data(), pl.stages.size() * sizeof(StageDesc),
+                               cudaMemcpyHostToDevice, st));
+  WMRL_CUDA_OK(cudaMemcpyAsync(base + pl.off_job_tab, pl.jobs.data(), pl.jobs.size() * sizeof(JobDesc),
+                               cudaMemcpyHostToDevice, st));
+  uint8_t* ops_dev = base + pl.off_packops;
+  WMRL_CUDA_OK(cudaMemcpyAsync(ops_dev, pl.pack_ops.data(), pl.pack_ops.size() * sizeof(PackOp),
+                               cudaMemcpyHostToDevice, st));
+  uint8_t* vops_dev = ops_dev + pl.pack_ops.size() * sizeof(PackOp);
+  WMRL_CUDA_OK(cudaMemcpyAsync(vops_dev, pl.vec_ops.data(), pl.vec_ops.size() * sizeof(VecOp),
+                               cudaMemcpyHostToDevice, st));
+  pack_stage_kernel<<<(unsigned)pl.pack_ops.size(), 256, 0, st>>>((const PackOp*)ops_dev, base + pl.off_data);
+  WMRL_CUDA_OK(cudaGetLastError());
+  pack_vec_kernel<<<(unsigned)pl.vec_ops.size(), 128, 0, st>>>((const VecOp*)vops_dev,
+                                                                (float*)(base + pl.off_eparams));
+  WMRL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// --------------------------------------------------------------------------
+// the fused kernel
+// --------------------------------------------------------------------------
+using namespace ptx;
+
+struct EpiCtx {
+  const TcParams* p;
+  uint32_t smem_base, tmem_lane;   // tmem base with this warp's lane quarter folded in
+  int row;                         // row within the tile == TMEM lane
+  long long b;                     // global row
+  bool valid;
+  int t;
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// tile start: deter0 / stoch0 -> index 0 of the outputs and the bf16 panels
+__device__ void epi_init(const EpiCtx& c) {
+  const TcParams& p = *c.p;
+  const long long T1 = p.H + 1;
+  for (int k8 = 0; k8 < p.Dp / 8; ++k8) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = k8 * 8 + e;
+      v[e] = (c.valid && col < p.D) ? p.deter0[c.b * p.D + col] : 0.f;
+      if (c.valid && col < p.D) p.deter_seq[(c.b * T1) * p.D + col] = v[e];
+    }
+    st_chunk(c.smem_base + p.off_h + k8 * 2048 + c.row * 16, v);
+  }
+  for (int k8 = 0; k8 < p.Sp / 8; ++k8) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = k8 * 8 + e;
+      v[e] = (c.valid && col < p.S) ? p.stoch0[c.b * p.S + col] : 0.f;
+      if (c.valid && col < p.S) p.stoch_seq[(c.b * T1) * p.S + col] = v[e];
+    }
+    st_chunk(c.smem_base + p.off_s + k8 * 2048 + c.row * 16, v);
+  }
+  const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k8 = 0; k8 < p.Ap / 8; ++k8) st_chunk(c.smem_base + p.off_a + k8 * 2048 + c.row * 16, z);
+}
+
+// Linear -> LayerNorm(eps 1e-5) -> ELU (actor.py:23-36); row statistics are thread-local
+__device__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb) {
+  const TcParams& p = *c.p;
+  const float* bias = p.eparams + jb.p_off;
+  const float* gam = bias + p.Ha;
+  const float* bet = gam + p.Ha;
+  const int ngrp = p.Ha / 32;
+  float sum = 0.f, sq = 0.f;
+  for (int g = 0; g < ngrp; ++g) {
+    float v[32];
+    tmem_ld32(c.tmem_lane + jb.tmem_col + g * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = ldg4(bias + g * 32 + i);
+      const float x0 = v[i] + b4.x, x1 = v[i + 1] + b4.y, x2 = v[i + 2] + b4.z, x3 = v[i + 3] + b4.w;
+      sum += (x0 + x1) + (x2 + x3);
+      sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+    }
+  }
+  const float inv = 1.f / (float)p.Ha;
+  const float mean = sum * inv;
+  const float var = fmaxf(sq * inv - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  for (int g = 0; g < ngrp; ++g) {
+    float v[32];
+    tmem_ld32(c.tmem_lane + jb.tmem_col + g * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = ldg4(bias + g * 32 + i);
+      const float4 g4 = ldg4(gam + g * 32 + i);
+      const float4 e4 = ldg4(bet + g * 32 + i);
+      v[i] = elu_fast(fmaf((v[i] + b4.x - mean) * rstd, g4.x, e4.x));
+      v[i + 1] = elu_fast(fmaf((v[i + 1] + b4.y - mean) * rstd, g4.y, e4.y));
+      v[i + 2] = elu_fast(fmaf((v[i + 2] + b4.z - mean) * rstd, g4.z, e4.z));
+      v[i + 3] = elu_fast(fmaf((v[i + 3] + b4.w - mean) * rstd, g4.w, e4.w));
+    }
+    const uint32_t dst = c.smem_base + jb.dst_off + (g * 4) * 2048 + c.row * 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) st_chunk(dst + k * 2048, v + k * 8);
+  }
+}
+
+// bias + ELU -> bf16 panel (embed rssm.py:65, prior hidden rssm.py:33-35)
+__device__ void epi_dense_elu(const EpiCtx& c, const JobDesc& jb) {
+  const TcParams& p = *c.p;
+  const float* bias = p.eparams + jb.p_off;
+  for (int g = 0; g < jb.n / 16; ++g) {
+    float v[16];
+    tmem_ld16(c.tmem_lane + jb.tmem_col + g * 16, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 b4 = ldg4(bias + g * 16 + i);
+      v[i] = elu_fast(v[i] + b4.x); v[i + 1] = elu_fast(v[i + 1] + b4.y);
+      v[i + 2] = elu_fast(v[i + 2] + b4.z); v[i + 3] = elu_fast(v[i + 3] + b4.w);
+    }
+    const uint32_t dst = c.smem_base + jb.dst_off + (g * 2) * 2048 + c.row * 16;
+    st_chunk(dst, v);
+    st_chunk(dst + 2048, v + 8);
+  }
+}
+
+// a = tanh(mu / action_scale) * bound  (actor.py:49-50) -> actions[B,H,A] + P_a panel
+__device__ void epi_mu(const EpiCtx& c, const JobDesc& jb) {
+  const TcParams& p = *c.p;
+  const float* bias = p.eparams + jb.p_off;
+  const float* bound = bias + 16;
+  float v[16];
+  tmem_ld16(c.tmem_lane + jb.tmem_col, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float a = tanh_fast((v[i] + __ldg(bias + i)) * p.inv_action_scale) * __ldg(bound + i);
+    v[i] = (i < p.A) ? a : 0.f;
+    if (c.valid && i < p.A) p.actions[(c.b * p.H + c.t) * p.A + i] = v[i];
+  }
+  const uint32_t dst = c.smem_base + jb.dst_off + c.row * 16;
+  st_chunk(dst, v);
+  st_chunk(dst + 2048, v + 8);
+}
+
+// GRUCell gates for one chunk of state columns (rssm.py:66); h_prev is the fp32
+// master copy in deter_seq[:, t] (written by this same thread one step earlier)
+__device__ void epi_gru(const EpiCtx& c, const JobDesc& jb, uint32_t tmem) {
+  const TcParams& p = *c.p;
+  const int cw = jb.n;
+  const float* b_r = p.eparams + jb.p_off;
+  const float* b_z = b_r + p.Dp;
+  const float* b_in = b_z + p.Dp;
+  const float* b_hn = b_in + p.Dp;
+  const long long T1 = p.H + 1;
+  const float* hprev = p.deter_seq + (c.b * T1 + c.t) * p.D;
+  float* hnext = p.deter_seq + (c.b * T1 + c.t + 1) * p.D;
+  for (int g = 0; g < cw / 16; ++g) {
+    const int col = jb.col0 + g * 16;
+    float hp[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) hp[i] = (c.valid && col + i < p.D) ? hprev[col + i] : 0.f;
+    float r[16], z[16], gi[16], gh[16];
+    tmem_ld16(tmem + g * 16, r);
+    tmem_ld16(tmem + cw + g * 16, z);
+    tmem_ld16(tmem + 2 * cw + g * 16, gi);
+    tmem_ld16(tmem + 3 * cw + g * 16, gh);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float rr = sigmoid_fast(r[i] + __ldg(b_r + col + i));
+      const float zz = sigmoid_fast(z[i] + __ldg(b_z + col + i));
+      const float nn = tanh_fast(gi[i] + __ldg(b_in + col + i) + rr * (gh[i] + __ldg(b_hn + col + i)));
+      const float h = fmaf(zz, hp[i] - nn, nn);   // (1-z)*n + z*h
+      r[i] = h;
+      if (c.valid && col + i < p.D) hnext[col + i] = h;
+    }
+    const uint32_t dst = c.smem_base + jb.dst_off + (col / 8) * 2048 + c.row * 16;
+    st_chunk(dst, r);
+    st_chunk(dst + 2048, r + 8);
+  }
+}
+
+// Gaussian head (rssm.py:179-181) + end-of-step hand-over of h' into the P_h panel
+__device__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& jb) {
+  const TcParams& p = *c.p;
+  const float* b_m = p.eparams + jb.p_off;
+  const float* b_s = b_m + p.Sp;
+  const long long T1 = p.H + 1;
+  const long long o = (c.b * T1 + c.t + 1) * p.S;
+  const float* eps = p.noise + ((long long)c.t * p.B + c.b) * p.S;
+  for (int g = 0; g < p.Sp / 16; ++g) {
+    float m[16], s[16];
+    tmem_ld16(c.tmem_lane + jb.tmem_col + g * 16, m);
+    tmem_ld16(c.tmem_lane + jb.tmem_col + p.Sp + g * 16, s);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int col = g * 16 + i;
+      const bool ok = c.valid && col < p.S;
+      const float mean = m[i] + __ldg(b_m + col);
+      const float raw = s[i] + __ldg(b_s + col);
+      const float sd = (raw > 20.f ? raw : __logf(1.f + __expf(raw))) + 0.1f;
+      const float e = ok ? eps[col] : 0.f;
+      const float st = fmaf(sd, e, mean);
+      m[i] = (col < p.S) ? st : 0.f;
+      if (ok) {
+        p.mean_seq[o + col] = mean;
+        p.std_seq[o + col] = sd;
+        p.stoch_seq[o + col] = st;
+      }
+    }
+    const uint32_t dst = c.smem_base + jb.dst_off + (g * 2) * 2048 + c.row * 16;
+    st_chunk(dst, m);
+    st_chunk(dst + 2048, m + 8);
+  }
+  // h' (X[h2..]) -> P_h: every MMA that read the old P_h has completed (this job's
+  // accumulator barrier is committed after them)
+  for (int k8 = 0; k8 < p.Dp / 8; ++k8) {
+    uint32_t a, b, cc, d;
+    const uint32_t src = c.smem_base + p.off_h2 + k8 * 2048 + c.row * 16;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(cc), "=r"(d) : "r"(src) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(c.smem_base + p.off_h + k8 * 2048 + c.row * 16),
+                 "r"(a), "r"(b), "r"(cc), "r"(d)
+                 : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring = smem_base + p.ring_off;
+  const uint32_t bars = smem_base + p.bar_off;
+  // barrier map (8 B each): full[0..8) | empty[8..16) | acc_full[16..18) | acc_empty[18..20) | tmem ptr @ +192
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };
+  auto accf_bar = [&](uint32_t j) { return bars + 128u + 8u * (j & 1u); };
+  auto acce_bar = [&](uint32_t j) { return bars + 144u + 8u * (j & 1u); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 192);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nslots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (uint32_t j = 0; j < 2; ++j) { mbar_init(accf_bar(j), 1); mbar_init(acce_bar(j), kEpiThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: stream weight stages in consumption order
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+        for (int t = 0; t < p.H; ++t)
+          for (int s = 0; s < p.nstages; ++s) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.stages + s));
+            const uint32_t bytes = (raw.y & 0xFFFFu) * 16u;
+            mbar_wait(empty_bar(slot), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(slot), bytes);
+            bulk_g2s(ring + slot * kSlotBytes, p.stage_data + (size_t)raw.x * 16u, bytes, full_bar(slot));
+            if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+          }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0, job = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        mbar_arrive(accf_bar(job));   // INIT job has no MMA
+        ++job;
+        for (int t = 0; t < p.H; ++t)
+          for (int s = 0; s < p.nstages; ++s) {
+            const StageDesc st = p.stages[s];
+            if ((st.flags & ST_FIRST_OF_JOB) && st.dep) {
+              const uint32_t dj = job - st.dep;
+              mbar_wait(acce_bar(dj), (dj >> 1) & 1u);
+            }
+            mbar_wait(full_bar(slot), phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base + (uint32_t)st.a_off16 * 16u;
+            const uint32_t b_addr = ring + slot * kSlotBytes;
+            const uint32_t tm = tmem_base + st.tmem_col + ((st.flags & ST_DBUF) ? (job & 1u) * 256u : 0u);
+            const uint32_t idesc = make_idesc_bf16(kTileM, st.n);
+            const uint32_t n = st.n;
+            for (uint32_t i = 0; i < st.nk16; ++i) {
+              const uint64_t ad = make_smem_desc(a_addr + i * 4096u, 2048u, 128u);
+              const uint64_t bd = make_smem_desc(b_addr + i * n * 32u, n * 16u, 128u);
+              mma_bf16_ss(tm, ad, bd, idesc, ((st.flags & ST_FIRST_ACC) && i == 0) ? 0u : 1u);
+            }
+            tc_commit(empty_bar(slot));
+            if (st.flags & ST_LAST_OF_JOB) {
+              tc_commit(accf_bar(job));
+              ++job;
+            }
+            if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+          }
+      }
+    }
+  } else {
+    // ===================== epilogue warps: one batch row (TMEM lane) per thread
+    EpiCtx c;
+    c.p = &p;
+    c.smem_base = smem_base;
+    c.row = (warp & 3) * 32 + lane;
+    c.tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t job = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      c.b = (long long)tile * kTileM + c.row;
+      c.valid = c.b < p.B;
+      c.t = 0;
+      mbar_wait(accf_bar(job), (job >> 1) & 1u);
+      epi_init(c);
+      fence_proxy_async_smem();
+      mbar_arrive(acce_bar(job));
+      ++job;
+      for (int t = 0; t < p.H; ++t) {
+        c.t = t;
+        for (int jb_i = 0; jb_i < p.njobs; ++jb_i) {
+          const JobDesc jb = p.jobs[jb_i];
+          mbar_wait(accf_bar(job), (job >> 1) & 1u);
+          tc_fence_after();
+          switch (jb.type) {
+            case JOB_ACTOR_LN: epi_actor_ln(c, jb); break;
+            case JOB_MU: epi_mu(c, jb); break;
+            case JOB_DENSE_ELU: epi_dense_elu(c, jb); break;
+            case JOB_GRU: epi_gru(c, jb, c.tmem_lane + (job & 1u) * 256u); break;
+            case JOB_PRIOR2_CONT: epi_prior2_cont(c, jb); break;
+            default: break;
+          }
+          tc_fence_before();
+          fence_proxy_async_smem();
+          mbar_arrive(acce_bar(job));
+          ++job;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
+                   const void* packed, const float* deter0, const float* stoch0,
+                   const float* noise, float* deter_seq, float* stoch_seq, float* dist_a,
+                   float* dist_b, float* actions, int32_t* idx, void* ws, cudaStream_t st) {
+  (void)w; (void)aw; (void)idx; (void)ws;
+  Plan pl = make_plan(d, nullptr, nullptr);
+  WMRL_REQUIRE(pl.ok, "tc_imagine_fwd: unsupported shape");
+  const uint8_t* base = (const uint8_t*)packed;
+  TcParams p{};
+  p.stage_data = base + pl.off_data;
+  p.stages = (const StageDesc*)(base + pl.off_stage_tab);
+  p.jobs = (const JobDesc*)(base + pl.off_job_tab);
+  p.eparams = (const float*)(base + pl.off_eparams);
+  p.deter0 = deter0; p.stoch0 = stoch0; p.noise = noise;
+  p.deter_seq = deter_seq; p.stoch_seq = stoch_seq; p.mean_seq = dist_a; p.std_seq = dist_b;
+  p.actions = actions;
+  p.nstages = (int)pl.stages.size(); p.njobs = (int)pl.jobs.size();
+  p.B = d.B; p.H = d.T; p.D = d.D; p.S = d.S; p.A = d.A;
+  p.Dp = pl.Dp; p.Sp = pl.Sp; p.Ap = pl.Ap; p.Ha = d.Ha; p.Hdp = pl.Hdp;
+  p.inv_action_scale = 1.f / d.action_scale;
+  p.off_h = pl.off_h; p.off_s = pl.off_s; p.off_a = pl.off_a; p.off_x = pl.off_x; p.off_h2 = pl.off_h2;
+  p.ring_off = pl.ring_off; p.bar_off = pl.bar_off; p.nslots = pl.nslots;
+  p.ntiles = (d.B + kTileM - 1) / kTileM;
+  int dev = 0, sms = 148;
+  WMRL_CUDA_OK(cudaGetDevice(&dev));
+  WMRL_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)pl.smem_bytes));
+  const int grid = std::min(p.ntiles, sms);
+  tc_imagine_kernel<<<grid, kThreads, pl.smem_bytes, st>>>(p);
+  WMRL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace wmrl

@@ -9,6 +9,7 @@ There is no fallback: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -34,6 +35,7 @@ class PathConfig:
     La: int = 0
     action_scale: float = 5.0
     precision: int = _lib.FP32
+    record: bool = True   # autograd is recording (torch.is_grad_enabled() at the call site)
 
     @property
     def S_in(self) -> int:
@@ -116,7 +118,8 @@ class PackedWeights:
     def get(self, cfg: PathConfig, rssm_p: Sequence[torch.Tensor], actor_p: Sequence[torch.Tensor],
             bound: torch.Tensor) -> torch.Tensor:
         lib = _lib.load()
-        key = (cfg, tuple((p.data_ptr(), p._version) for p in list(rssm_p) + list(actor_p)))
+        key = (dataclasses.replace(cfg, record=True), bound.data_ptr(),
+               tuple((p.data_ptr(), p._version) for p in list(rssm_p) + list(actor_p)))
         if self.key == key and self.buf is not None:
             return self.buf
         dev = rssm_p[0].device
@@ -153,7 +156,7 @@ class ImagineRollout(torch.autograd.Function):
         dev = _require_cuda(deter0, stoch0, noise, bound, *params)
         B = deter0.shape[0]
         disc = cfg.variant == _lib.DISCRETE
-        need_bwd = any(ctx.needs_input_grad)
+        need_bwd = cfg.record and any(ctx.needs_input_grad)
         a32 = [_f32c(p) for p in actor_p]
         r32 = [_f32c(p) for p in rssm_p]
         d0, s0, nz, bd = _f32c(deter0), _f32c(stoch0), _f32c(noise), _f32c(bound)
@@ -275,7 +278,7 @@ class ObserveRollout(torch.autograd.Function):
         dev = _require_cuda(obs, act, *rssm_p)
         B, T = obs.shape[0], obs.shape[1]
         disc = cfg.variant == _lib.DISCRETE
-        need_bwd = any(ctx.needs_input_grad)
+        need_bwd = cfg.record and any(ctx.needs_input_grad)
         r32 = [_f32c(p) for p in rssm_p]
         ob, ac = _f32c(obs), _f32c(act)
         n1 = _f32c(noise_pri) if noise_pri is not None else None

@@ -90,7 +90,8 @@ class RSSMBase(nn.Module):
     def _config(self, action_size: int, Ha: int = 0, La: int = 0, action_scale: float = 5.0) -> PathConfig:
         return PathConfig(variant=self.variant, D=self.deter_size, S=self.stoch_size, C=self.num_groups,
                           A=action_size, Hd=self.hidden_size, E=self.obs_embed_size, Ha=Ha, La=La,
-                          action_scale=float(action_scale), precision=_PRECISIONS[self.precision])
+                          action_scale=float(action_scale), precision=_PRECISIONS[self.precision],
+                          record=torch.is_grad_enabled())
 
     # --------------------------------------------------- eager single-step API
     def initial_state_sequence(self, batch_size):
