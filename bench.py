@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the RSSM latent-imagination path (BASELINE.json metric:
+imagined latent-steps/sec = start states x horizon / time).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[3] at its largest point, the
+one the north-star target is quoted on - continuous RSSM (deter 200, stoch 30
+Gaussian, hidden 200, action 6, Actor 3x512), 65,536 start states PER GPU x
+horizon 15, forward imagination through the bf16 tcgen05 kernel.  One "step" is
+one `RSSM.imagine_rollout` call over that batch (one persistent kernel launch).
+Weak scaling: every rank owns its own 65,536 start states; no data-path
+collective (rollouts are independent), timing is max-over-ranks.
+
+`--impl reference`: the reference's CPU implementation of the same path.  The
+reference is pure Python/torch and is not present on the GPU box, so this arm
+times its restatement (oracle/rssm_oracle.py, checked against golden vectors of
+the real reference) on all host cores, on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "world-model-rl_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "imagined latent-steps/sec"
+UNIT = "latent-steps/s"
+# workload dims
+CFG = dict(variant="continuous", B=65536, H=15, D=200, S=30, C=1, Hd=200, E=1024, A=6, Ha=512, La=3)
+
+
+def flops_per_latent_step(c) -> int:
+    """ALGORITHMIC forward FLOPs per latent step: 2 x MACs of every
+    nn.Linear on the path, padding excluded."""
+    S_in = c["S"] * (c["C"] if c["variant"] == "discrete" else 1)
+    P = S_in if c["variant"] == "discrete" else 2 * c["S"]
+    F = c["D"] + S_in
+    mac_actor = F * c["Ha"] + (c["La"] - 1) * c["Ha"] ** 2 + c["Ha"] * c["A"]
+    mac_dyn = (S_in + c["A"]) * c["D"] + 6 * c["D"] ** 2 + c["D"] * c["Hd"] + c["Hd"] * P
+    return 2 * (mac_actor + mac_dyn)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return d, "measured"
+    # /opt/skills/guides/B200_PROFILING.md fallback
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n_, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n_)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_problem(c, device, seed=0, precision="bf16"):
+    """Synthetic weights / start states / noise: default torch inits under a fixed
+    seed, deter = tanh(N(0,1)), stoch ~ N(0,1), eps ~ N(0,1)."""
+    import wmrl
+    torch.manual_seed(seed)
+    rssm = wmrl.ContinuousRSSM(c["Hd"], c["D"], c["S"], c["E"], c["A"], precision=precision)
+    actor = wmrl.Actor(c["D"] + c["S"], c["A"], 1.0, c["La"], c["Ha"])
+    return rssm.to(device), actor.to(device)
+
+
+def host_inputs(c, B, seed, pin):
+    g = torch.Generator().manual_seed(seed)
+    deter0 = torch.tanh(torch.randn(B, c["D"], generator=g))
+    stoch0 = torch.randn(B, c["S"], generator=g)
+    noise = torch.randn(c["H"], B, c["S"], generator=g)
+    if pin:
+        deter0, stoch0, noise = deter0.pin_memory(), stoch0.pin_memory(), noise.pin_memory()
+    return deter0, stoch0, noise
+
+
+def cpu_reference_rate(c, rssm, actor, sample_rows, repeats, threads):
+    """oracle (reference restatement) on the host cores; returns (latent-steps/s, seconds per pass)."""
+    from oracle import rssm_oracle as O
+    torch.set_num_threads(threads)
+    w = {k: v.detach().cpu() for k, v in rssm.state_dict().items()}
+    aw = {k: v.detach().cpu() for k, v in actor.state_dict().items()}
+    d0, s0, nz = host_inputs(c, sample_rows, 11, pin=False)
+    best = None
+    with torch.no_grad():
+        for i in range(repeats + 1):           # first pass is the warm-up
+            t0 = time.perf_counter()
+            O.imagine_rollout_reference_like(c["variant"], w, aw, d0, s0, c["H"], c["S"], c["C"])
+            dt = time.perf_counter() - t0
+            if i > 0:
+                best = dt if best is None else min(best, dt)
+    return sample_rows * c["H"] / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    c = dict(CFG)
+    threads = os.cpu_count() or 1
+    torch.manual_seed(0)
+    import wmrl
+    rssm = wmrl.ContinuousRSSM(c["Hd"], c["D"], c["S"], c["E"], c["A"])
+    actor = wmrl.Actor(c["D"] + c["S"], c["A"], 1.0, c["La"], c["Ha"])
+    from oracle import rssm_oracle as O
+    torch.set_num_threads(threads)
+    w = {k: v.detach() for k, v in rssm.state_dict().items()}
+    aw = {k: v.detach() for k, v in actor.state_dict().items()}
+    rows = 4096     # bounded sample of the 65,536-row workload; CPU rate is flat in B beyond a few thousand rows
+    d0, s0, _ = host_inputs(c, rows, 11, pin=False)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            O.imagine_rollout_reference_like(c["variant"], w, aw, d0, s0, c["H"], c["S"], c["C"])
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = rows * c["H"] * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(c, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{rows} of 65536 start states x H=15 per step, fp32, torch CPU, "
+                                   f"oracle/rssm_oracle.py::imagine_rollout_reference_like"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(c, n_gpus):
+    return {"workload": "continuous-RSSM imagine forward (BASELINE configs[3] top point): deter 200, stoch 30 "
+                        "Gaussian, hidden 200, action 6, Actor 3x512; 65536 start states per GPU x horizon 15",
+            "start_states_per_gpu": c["B"], "horizon": c["H"], "global_start_states": c["B"] * n_gpus,
+            "parallelism": f"dp{n_gpus} (batch-sharded, no data-path collective)",
+            "l2_policy": "per-step inputs (178 MB) and outputs (1.24 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import wmrl
+    from wmrl import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    c = dict(CFG)
+    B, H = c["B"], c["H"]
+    rssm, actor = build_problem(c, dev)
+    deter0_h, stoch0_h, noise_h = host_inputs(c, B, 100 + rank, pin=True)
+    deter0, stoch0, noise = deter0_h.to(dev), stoch0_h.to(dev), noise_h.to(dev)
+    init = wmrl.InternalStateContinuous(deter0, stoch0, stoch0.clone(), torch.ones_like(stoch0))
+    lib = _lib.load()
+    if not lib.wmrl_device_supports_bf16():
+        raise SystemExit("bench.py: the tcgen05 path needs an sm_100 device")
+
+    def step():
+        with torch.no_grad():
+            return rssm.imagine_rollout(init, actor, H, noise=noise)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        seq = step()
+    # ---- device-resident timing: K steps bracketed by barrier + synchronize, CUDA events on the
+    # launching (current) stream, plus one event pair per launch for the roofline figure
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_beg.record()
+    for i in range(args.steps):
+        ev[i][0].record()
+        seq = step()
+        ev[i][1].record()
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = t_beg.elapsed_time(t_end)
+    launch_ms = [a.elapsed_time(b) for a, b in ev]
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * B * H * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end: host (pinned) inputs -> H2D -> rollout -> scalar result -> D2H, every step.
+    # The next step's inputs are prefetched on a copy stream while the current step computes.
+    copy_stream = torch.cuda.Stream(dev)
+    bufs = [[torch.empty_like(deter0), torch.empty_like(stoch0), torch.empty_like(noise)] for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    result_h = torch.empty(1, dtype=torch.float32).pin_memory()
+    h2d_bytes = sum(t.numel() * 4 for t in (deter0_h, stoch0_h, noise_h))
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            for dst, src in zip(bufs[slot], (deter0_h, stoch0_h, noise_h)):
+                dst.copy_(src, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_run(n):
+        for e in consumed:
+            e.record()
+        upload(0)
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                upload(slot ^ 1)
+            torch.cuda.current_stream().wait_event(ready[slot])
+            d0, s0, nz = bufs[slot]
+            st = wmrl.InternalStateContinuous(d0, s0, s0, s0)
+            with torch.no_grad():
+                sq = rssm.imagine_rollout(st, actor, H, noise=nz)
+                res = sq.deter_states[:, -1].mean() + sq.stoch_states[:, -1].mean()
+            consumed[slot].record()
+            result_h.copy_(res.reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()     # the caller reads the step's result on the host
+
+    e2e_run(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(args.steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * H * args.steps / e2e_s
+
+    if rank == 0:
+        peaks, peaks_src = measured_peaks()
+        fl = flops_per_latent_step(c)
+        avg_launch_s = statistics.mean(launch_ms) * 1e-3
+        achieved_tf = fl * B * H / avg_launch_s / 1e12
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("tc_imagine_kernel_dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(c, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "note": "pinned host start states + noise -> H2D (prefetched on a copy stream) -> "
+                            "RSSM.imagine_rollout -> scalar summary -> D2H + host sync, every step"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": traffic, "kernel": "tc_imagine_kernel",
+                         "flops_per_latent_step": fl, "latent_steps_per_launch": B * H,
+                         "avg_launch_ms": avg_launch_s * 1e3,
+                         "peak_source": f"{peaks_src} bf16_tflops_sustained (MEASURED_PEAKS.json)",
+                         "frac_of_burst": achieved_tf / float(peaks.get("bf16_tflops", peak_tf))},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rows = 4096
+            rate, secs = cpu_reference_rate(c, rssm, actor, rows, repeats=3, threads=threads)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{rows} of {B} start states x H={H}, best of 3 passes "
+                                              f"({secs:.2f} s each), fp32 torch CPU, oracle restatement of "
+                                              f"rssm.py:123-140"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -306,3 +306,36 @@ def lambda_return_scan(V, r, d, gamma: float = 0.99, lam: float = 0.95):
         M = rp[:, i] + gamma * M
         out[i] = Std - (lam ** (n - 2) - lam ** (n - 1)) * M
     return torch.stack(out, dim=1)
+
+
+def imagine_rollout_reference_like(variant, w, aw, deter0, stoch0, n_steps, S, C=1, action_scale=5.0, bound=None):
+    """CPU-baseline twin of ``imagine_rollout``: the same arithmetic, but executed the
+    way the reference's CPU path executes it - noise drawn internally
+    (``torch.randn_like`` rssm.py:181 / ``OneHotCategoricalStraightThrough.rsample``
+    state/discrete.py:27-30) and the ``[B,t,.]`` buffers re-grown with ``torch.cat``
+    every step (``Sequence.append_``, state/continuous.py:56-60, state/discrete.py:56-59).
+    Used only for timing (bench.py cpu_baseline / --impl reference)."""
+    import torch.distributions as Dist
+    if bound is None:
+        bound = torch.tensor(1.0, dtype=deter0.dtype)
+    deter, stoch = deter0, stoch0
+    seq = [deter0.unsqueeze(1), stoch0.unsqueeze(1)]
+    extra = None
+    for _ in range(n_steps):
+        feat = torch.cat([deter, stoch], dim=-1).detach()
+        action = actor_mu(aw, feat, action_scale, bound)
+        deter, out = prior_deter(w, stoch, action, deter)
+        if variant == "continuous":
+            mean, raw = torch.split(out, S, dim=-1)
+            std = F.softplus(raw) + 0.1
+            stoch = mean + std * torch.randn_like(mean)
+            new = [mean.unsqueeze(1), std.unsqueeze(1)]
+        else:
+            logits = out.reshape(-1, C, S)
+            dist = Dist.Independent(Dist.OneHotCategoricalStraightThrough(logits=logits), 1)
+            stoch = dist.rsample().reshape(-1, C * S)
+            new = [logits.unsqueeze(1)]
+        seq[0] = torch.cat([seq[0], deter.unsqueeze(1)], dim=1)
+        seq[1] = torch.cat([seq[1], stoch.unsqueeze(1)], dim=1)
+        extra = new if extra is None else [torch.cat([e, n_], dim=1) for e, n_ in zip(extra, new)]
+    return seq + (extra or [])

@@ -21,6 +21,7 @@
 // (what the producer loads and the MMA thread issues) and JOBS (what the
 // epilogue warps do once a job's accumulator is complete).
 #include <algorithm>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -101,6 +102,15 @@ struct TcParams {
 };
 
 static inline int ceil16(int x) { return (x + 15) / 16 * 16; }
+
+// With 227 KB of shared memory carved out the L1D is ~1 KB, so any global load
+// in the inner loops is a full L2 round trip.  The per-step tables and the
+// epilogue parameters (biases, LayerNorm affine, bound) are therefore served
+// from the constant cache: every access is warp-uniform.
+constexpr int kMaxStages = 512, kMaxJobs = 32, kMaxEparams = 12032;
+__constant__ uint4 c_stages[kMaxStages];
+__constant__ JobDesc c_jobs[kMaxJobs];
+__constant__ __align__(16) float c_eparams[kMaxEparams];
 
 struct Plan {
   int Dp, Sp, Ap, Ha, Hdp, h2c, XW;
@@ -300,6 +310,9 @@ static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor
   }
   for (const StageDesc& st : pl.stages)
     if ((int)st.bytes16 * 16 > kSlotBytes) return pl;
+  if ((int)pl.stages.size() > kMaxStages || (int)pl.jobs.size() > kMaxJobs ||
+      (int)pl.eparams_floats > kMaxEparams)
+    return pl;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   pl.off_stage_tab = 256;
   pl.off_job_tab = al(pl.off_stage_tab + pl.stages.size() * sizeof(StageDesc));
@@ -357,10 +370,20 @@ __global__ void pack_vec_kernel(const VecOp* __restrict__ ops, float* __restrict
   }
 }
 
+// which packed image currently sits in constant memory (single host thread per device, see wmrl.h)
+static const void* g_const_src = nullptr;
+static unsigned long long g_const_gen = 0, g_pack_counter = 0;
+static std::unordered_map<const void*, unsigned long long> g_pack_gen;
+static unsigned long long pack_generation(const void* packed) {
+  auto it = g_pack_gen.find(packed);
+  return it == g_pack_gen.end() ? 0ull : it->second;
+}
+
 int tc_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
                     void* packed, cudaStream_t st) {
   Plan pl = make_plan(d, w, aw);
   WMRL_REQUIRE(pl.ok, "pack_weights: unsupported shape");
+  g_pack_gen[packed] = ++g_pack_counter;
   uint8_t* base = (uint8_t*)packed;
   // tables travel host -> device inside the packed image (synchronous for pageable memory)
   WMRL_CUDA_OK(cudaMemcpyAsync(base + pl.off_stage_tab, pl.stages.data(), pl.stages.size() * sizeof(StageDesc),
@@ -395,7 +418,7 @@ struct EpiCtx {
   int t;
 };
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldc4(uint32_t off) { return *reinterpret_cast<const float4*>(&c_eparams[off]); }
 
 // tile start: deter0 / stoch0 -> index 0 of the outputs and the bf16 panels
 __device__ void epi_init(const EpiCtx& c) {
@@ -428,9 +451,7 @@ __device__ void epi_init(const EpiCtx& c) {
 // Linear -> LayerNorm(eps 1e-5) -> ELU (actor.py:23-36); row statistics are thread-local
 __device__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb) {
   const TcParams& p = *c.p;
-  const float* bias = p.eparams + jb.p_off;
-  const float* gam = bias + p.Ha;
-  const float* bet = gam + p.Ha;
+  const uint32_t bias = jb.p_off, gam = bias + p.Ha, bet = gam + p.Ha;
   const int ngrp = p.Ha / 32;
   float sum = 0.f, sq = 0.f;
   for (int g = 0; g < ngrp; ++g) {
@@ -439,7 +460,7 @@ __device__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb) {
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b4 = ldg4(bias + g * 32 + i);
+      const float4 b4 = ldc4(bias + g * 32 + i);
       const float x0 = v[i] + b4.x, x1 = v[i + 1] + b4.y, x2 = v[i + 2] + b4.z, x3 = v[i + 3] + b4.w;
       sum += (x0 + x1) + (x2 + x3);
       sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
@@ -455,9 +476,9 @@ __device__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb) {
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b4 = ldg4(bias + g * 32 + i);
-      const float4 g4 = ldg4(gam + g * 32 + i);
-      const float4 e4 = ldg4(bet + g * 32 + i);
+      const float4 b4 = ldc4(bias + g * 32 + i);
+      const float4 g4 = ldc4(gam + g * 32 + i);
+      const float4 e4 = ldc4(bet + g * 32 + i);
       v[i] = elu_fast(fmaf((v[i] + b4.x - mean) * rstd, g4.x, e4.x));
       v[i + 1] = elu_fast(fmaf((v[i + 1] + b4.y - mean) * rstd, g4.y, e4.y));
       v[i + 2] = elu_fast(fmaf((v[i + 2] + b4.z - mean) * rstd, g4.z, e4.z));
@@ -472,14 +493,14 @@ __device__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb) {
 // bias + ELU -> bf16 panel (embed rssm.py:65, prior hidden rssm.py:33-35)
 __device__ void epi_dense_elu(const EpiCtx& c, const JobDesc& jb) {
   const TcParams& p = *c.p;
-  const float* bias = p.eparams + jb.p_off;
+  const uint32_t bias = jb.p_off;
   for (int g = 0; g < jb.n / 16; ++g) {
     float v[16];
     tmem_ld16(c.tmem_lane + jb.tmem_col + g * 16, v);
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
-      const float4 b4 = ldg4(bias + g * 16 + i);
+      const float4 b4 = ldc4(bias + g * 16 + i);
       v[i] = elu_fast(v[i] + b4.x); v[i + 1] = elu_fast(v[i + 1] + b4.y);
       v[i + 2] = elu_fast(v[i + 2] + b4.z); v[i + 3] = elu_fast(v[i + 3] + b4.w);
     }
@@ -492,14 +513,13 @@ __device__ void epi_dense_elu(const EpiCtx& c, const JobDesc& jb) {
 // a = tanh(mu / action_scale) * bound  (actor.py:49-50) -> actions[B,H,A] + P_a panel
 __device__ void epi_mu(const EpiCtx& c, const JobDesc& jb) {
   const TcParams& p = *c.p;
-  const float* bias = p.eparams + jb.p_off;
-  const float* bound = bias + 16;
+  const uint32_t bias = jb.p_off, bound = bias + 16;
   float v[16];
   tmem_ld16(c.tmem_lane + jb.tmem_col, v);
   tmem_ld_wait();
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float a = tanh_fast((v[i] + __ldg(bias + i)) * p.inv_action_scale) * __ldg(bound + i);
+    const float a = tanh_fast((v[i] + c_eparams[bias + i]) * p.inv_action_scale) * c_eparams[bound + i];
     v[i] = (i < p.A) ? a : 0.f;
     if (c.valid && i < p.A) p.actions[(c.b * p.H + c.t) * p.A + i] = v[i];
   }
@@ -509,48 +529,62 @@ __device__ void epi_mu(const EpiCtx& c, const JobDesc& jb) {
 }
 
 // GRUCell gates for one chunk of state columns (rssm.py:66); h_prev is the fp32
-// master copy in deter_seq[:, t] (written by this same thread one step earlier)
-__device__ void epi_gru(const EpiCtx& c, const JobDesc& jb, uint32_t tmem) {
+// master copy in deter_seq[:, t] (written by this same thread one step earlier).
+// It is fetched BEFORE the accumulator barrier so the L2 round trip overlaps the MMAs.
+struct GruPrefetch { float hp[64]; };
+__device__ __forceinline__ void gru_prefetch(const EpiCtx& c, const JobDesc& jb, GruPrefetch& pf) {
   const TcParams& p = *c.p;
-  const int cw = jb.n;
-  const float* b_r = p.eparams + jb.p_off;
-  const float* b_z = b_r + p.Dp;
-  const float* b_in = b_z + p.Dp;
-  const float* b_hn = b_in + p.Dp;
   const long long T1 = p.H + 1;
   const float* hprev = p.deter_seq + (c.b * T1 + c.t) * p.D;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    const int col = jb.col0 + i;
+    pf.hp[i] = (c.valid && i < jb.n && col < p.D) ? hprev[col] : 0.f;
+  }
+}
+__device__ __forceinline__ void epi_gru(const EpiCtx& c, const JobDesc& jb, uint32_t tmem, const GruPrefetch& pf) {
+  const TcParams& p = *c.p;
+  const int cw = jb.n;
+  const uint32_t b_r = jb.p_off, b_z = b_r + p.Dp, b_in = b_z + p.Dp, b_hn = b_in + p.Dp;
+  const long long T1 = p.H + 1;
   float* hnext = p.deter_seq + (c.b * T1 + c.t + 1) * p.D;
-  for (int g = 0; g < cw / 16; ++g) {
-    const int col = jb.col0 + g * 16;
-    float hp[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) hp[i] = (c.valid && col + i < p.D) ? hprev[col + i] : 0.f;
-    float r[16], z[16], gi[16], gh[16];
-    tmem_ld16(tmem + g * 16, r);
-    tmem_ld16(tmem + cw + g * 16, z);
-    tmem_ld16(tmem + 2 * cw + g * 16, gi);
-    tmem_ld16(tmem + 3 * cw + g * 16, gh);
-    tmem_ld_wait();
+  for (int g = 0; g < 4; ++g) {
+    if (g * 16 < cw) {
+      const int col = jb.col0 + g * 16;
+      float r[16], z[16], gi[16], gh[16];
+      tmem_ld16(tmem + g * 16, r);
+      tmem_ld16(tmem + cw + g * 16, z);
+      tmem_ld16(tmem + 2 * cw + g * 16, gi);
+      tmem_ld16(tmem + 3 * cw + g * 16, gh);
+      tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float rr = sigmoid_fast(r[i] + __ldg(b_r + col + i));
-      const float zz = sigmoid_fast(z[i] + __ldg(b_z + col + i));
-      const float nn = tanh_fast(gi[i] + __ldg(b_in + col + i) + rr * (gh[i] + __ldg(b_hn + col + i)));
-      const float h = fmaf(zz, hp[i] - nn, nn);   // (1-z)*n + z*h
-      r[i] = h;
-      if (c.valid && col + i < p.D) hnext[col + i] = h;
+      for (int i = 0; i < 16; ++i) {
+        const float rr = sigmoid_fast(r[i] + c_eparams[b_r + col + i]);
+        const float zz = sigmoid_fast(z[i] + c_eparams[b_z + col + i]);
+        const float nn = tanh_fast(gi[i] + c_eparams[b_in + col + i] + rr * (gh[i] + c_eparams[b_hn + col + i]));
+        const float h = fmaf(zz, pf.hp[g * 16 + i] - nn, nn);   // (1-z)*n + z*h
+        r[i] = h;
+        if (c.valid && col + i < p.D) hnext[col + i] = h;
+      }
+      const uint32_t dst = c.smem_base + jb.dst_off + (col / 8) * 2048 + c.row * 16;
+      st_chunk(dst, r);
+      st_chunk(dst + 2048, r + 8);
     }
-    const uint32_t dst = c.smem_base + jb.dst_off + (col / 8) * 2048 + c.row * 16;
-    st_chunk(dst, r);
-    st_chunk(dst + 2048, r + 8);
   }
 }
 
 // Gaussian head (rssm.py:179-181) + end-of-step hand-over of h' into the P_h panel
-__device__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& jb) {
+struct EpsPrefetch { float e[32]; };
+__device__ __forceinline__ void eps_prefetch(const EpiCtx& c, EpsPrefetch& pf) {
   const TcParams& p = *c.p;
-  const float* b_m = p.eparams + jb.p_off;
-  const float* b_s = b_m + p.Sp;
+  const float* eps = p.noise + ((long long)c.t * p.B + c.b) * p.S;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) pf.e[i] = (c.valid && i < p.S) ? eps[i] : 0.f;
+}
+__device__ __forceinline__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& jb, const EpsPrefetch& pf) {
+  const TcParams& p = *c.p;
+  const uint32_t b_m = jb.p_off, b_s = b_m + p.Sp;
   const long long T1 = p.H + 1;
   const long long o = (c.b * T1 + c.t + 1) * p.S;
   const float* eps = p.noise + ((long long)c.t * p.B + c.b) * p.S;
@@ -563,10 +597,12 @@ __device__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& jb) {
     for (int i = 0; i < 16; ++i) {
       const int col = g * 16 + i;
       const bool ok = c.valid && col < p.S;
-      const float mean = m[i] + __ldg(b_m + col);
-      const float raw = s[i] + __ldg(b_s + col);
+      const float mean = m[i] + c_eparams[b_m + col];
+      const float raw = s[i] + c_eparams[b_s + col];
       const float sd = (raw > 20.f ? raw : __logf(1.f + __expf(raw))) + 0.1f;
-      const float e = ok ? eps[col] : 0.f;
+      float e;
+      if (g < 2) e = pf.e[(g & 1) * 16 + i];          // first 32 columns were prefetched
+      else e = ok ? eps[col] : 0.f;
       const float st = fmaf(sd, e, mean);
       m[i] = (col < p.S) ? st : 0.f;
       if (ok) {
@@ -625,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
         for (int t = 0; t < p.H; ++t)
           for (int s = 0; s < p.nstages; ++s) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.stages + s));
+            const uint4 raw = c_stages[s];
             const uint32_t bytes = (raw.y & 0xFFFFu) * 16u;
             mbar_wait(empty_bar(slot), phase ^ 1u);
             mbar_arrive_expect_tx(full_bar(slot), bytes);
@@ -642,7 +678,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
         ++job;
         for (int t = 0; t < p.H; ++t)
           for (int s = 0; s < p.nstages; ++s) {
-            const StageDesc st = p.stages[s];
+            const uint4 raw = c_stages[s];
+            const StageDesc st = *reinterpret_cast<const StageDesc*>(&raw);
             if ((st.flags & ST_FIRST_OF_JOB) && st.dep) {
               const uint32_t dj = job - st.dep;
               mbar_wait(acce_bar(dj), (dj >> 1) & 1u);
@@ -688,16 +725,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
       for (int t = 0; t < p.H; ++t) {
         c.t = t;
         for (int jb_i = 0; jb_i < p.njobs; ++jb_i) {
-          const JobDesc jb = p.jobs[jb_i];
-          mbar_wait(accf_bar(job), (job >> 1) & 1u);
-          tc_fence_after();
-          switch (jb.type) {
-            case JOB_ACTOR_LN: epi_actor_ln(c, jb); break;
-            case JOB_MU: epi_mu(c, jb); break;
-            case JOB_DENSE_ELU: epi_dense_elu(c, jb); break;
-            case JOB_GRU: epi_gru(c, jb, c.tmem_lane + (job & 1u) * 256u); break;
-            case JOB_PRIOR2_CONT: epi_prior2_cont(c, jb); break;
-            default: break;
+          const JobDesc jb = c_jobs[jb_i];
+          if (jb.type == JOB_GRU) {
+            GruPrefetch pf;
+            gru_prefetch(c, jb, pf);
+            mbar_wait(accf_bar(job), (job >> 1) & 1u);
+            tc_fence_after();
+            epi_gru(c, jb, c.tmem_lane + (job & 1u) * 256u, pf);
+          } else if (jb.type == JOB_PRIOR2_CONT) {
+            EpsPrefetch pf;
+            eps_prefetch(c, pf);
+            mbar_wait(accf_bar(job), (job >> 1) & 1u);
+            tc_fence_after();
+            epi_prior2_cont(c, jb, pf);
+          } else {
+            mbar_wait(accf_bar(job), (job >> 1) & 1u);
+            tc_fence_after();
+            switch (jb.type) {
+              case JOB_ACTOR_LN: epi_actor_ln(c, jb); break;
+              case JOB_MU: epi_mu(c, jb); break;
+              case JOB_DENSE_ELU: epi_dense_elu(c, jb); break;
+              default: break;
+            }
           }
           tc_fence_before();
           fence_proxy_async_smem();
@@ -735,6 +784,18 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
   p.off_h = pl.off_h; p.off_s = pl.off_s; p.off_a = pl.off_a; p.off_x = pl.off_x; p.off_h2 = pl.off_h2;
   p.ring_off = pl.ring_off; p.bar_off = pl.bar_off; p.nslots = pl.nslots;
   p.ntiles = (d.B + kTileM - 1) / kTileM;
+  // tables + epilogue parameters -> constant memory (device-to-device from the packed image,
+  // stream-ordered before the launch; skipped when this image is already resident)
+  if (g_const_src != packed || g_const_gen != pack_generation(packed)) {
+    WMRL_CUDA_OK(cudaMemcpyToSymbolAsync(c_stages, base + pl.off_stage_tab, pl.stages.size() * sizeof(StageDesc), 0,
+                                         cudaMemcpyDeviceToDevice, st));
+    WMRL_CUDA_OK(cudaMemcpyToSymbolAsync(c_jobs, base + pl.off_job_tab, pl.jobs.size() * sizeof(JobDesc), 0,
+                                         cudaMemcpyDeviceToDevice, st));
+    WMRL_CUDA_OK(cudaMemcpyToSymbolAsync(c_eparams, base + pl.off_eparams, pl.eparams_floats * sizeof(float), 0,
+                                         cudaMemcpyDeviceToDevice, st));
+    g_const_src = packed;
+    g_const_gen = pack_generation(packed);
+  }
   int dev = 0, sms = 148;
   WMRL_CUDA_OK(cudaGetDevice(&dev));
   WMRL_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
