@@ -35,8 +35,11 @@ namespace wmrl {
 constexpr int kTileM = 128;
 constexpr int kSlotBytes = 16384;       // ring slot (one weight stage)
 constexpr int kMaxSmem = 232448;        // 227 KB opt-in limit on sm_100
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kQ = 4;                   // epilogue warps per TMEM lane quarter
+constexpr int kEpiThreads = 4 * kQ * 32;
+constexpr int kThreads = kEpiThreads + 64;   // epilogue warps first; producer and MMA warps LAST: the issue
+                                              // arbiter favours high warp ids and these two must never starve
+constexpr int kProducerWarp = 4 * kQ, kMmaWarp = 4 * kQ + 1;
 
 enum : uint8_t { ST_FIRST_ACC = 1, ST_LAST_OF_JOB = 2, ST_FIRST_OF_JOB = 4, ST_DBUF = 8 };
 struct __align__(16) StageDesc {
@@ -182,7 +185,7 @@ static uint32_t add_vec(Plan& pl, const float* s1, const float* s2, int off, int
 static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw) {
   Plan pl;
   if (d.variant != WMRL_CONTINUOUS) return pl;
-  if (d.Ha % 32 != 0 || d.Ha > 512 || d.Ha < 32 || d.A > 16 || d.S > 128 || d.La < 1) return pl;
+  if (d.Ha % 32 != 0 || d.Ha > 512 || d.A > 16 || d.S > 128 || d.La < 1) return pl;
   pl.Dp = ceil16(d.D); pl.Sp = ceil16(d.S); pl.Ap = 16; pl.Ha = d.Ha; pl.Hdp = ceil16(d.Hd);
   if (pl.Hdp > 512 || pl.Dp > 4096) return pl;
   pl.h2c = std::max(pl.Dp, pl.Hdp);
@@ -409,22 +412,35 @@ int tc_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_p
 // --------------------------------------------------------------------------
 using namespace ptx;
 
+// Epilogue organisation: kQ warps per TMEM lane quarter (a warp may only read
+// lanes 32*(warp%4)..+31).  The kQ warps of a quarter own the same 32 batch
+// rows and split every job's accumulator COLUMNS between them, so each SM
+// sub-partition has kQ resident epilogue warps to hide TMEM / MUFU / constant
+// cache latency.  LayerNorm row statistics are combined across the kQ warps
+// through a scratch area (the P_a panel, idle during the actor blocks) and a
+// named barrier per quarter.
 struct EpiCtx {
   const TcParams* p;
   uint32_t smem_base, tmem_lane;   // tmem base with this warp's lane quarter folded in
   int row;                         // row within the tile == TMEM lane
+  int q, quarter;                  // column-split index within the quarter, lane quarter
   long long b;                     // global row
   bool valid;
   int t;
 };
 
-__device__ __forceinline__ float4 ldc4(uint32_t off) { return *reinterpret_cast<const float4*>(&c_eparams[off]); }
+__device__ __forceinline__ float4 ldc4(uint32_t off) {   // off: float offset, multiple of 4
+  return reinterpret_cast<const float4*>(c_eparams)[off >> 2];
+}
+__device__ __forceinline__ void quarter_sync(int quarter) {
+  asm volatile("bar.sync %0, %1;" ::"r"(quarter + 1), "r"(kQ * 32) : "memory");
+}
 
 // tile start: deter0 / stoch0 -> index 0 of the outputs and the bf16 panels
-__device__ void epi_init(const EpiCtx& c) {
+__device__ __forceinline__ void epi_init(const EpiCtx& c) {
   const TcParams& p = *c.p;
   const long long T1 = p.H + 1;
-  for (int k8 = 0; k8 < p.Dp / 8; ++k8) {
+  for (int k8 = c.q; k8 < p.Dp / 8; k8 += kQ) {
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -434,7 +450,7 @@ __device__ void epi_init(const EpiCtx& c) {
     }
     st_chunk(c.smem_base + p.off_h + k8 * 2048 + c.row * 16, v);
   }
-  for (int k8 = 0; k8 < p.Sp / 8; ++k8) {
+  for (int k8 = c.q; k8 < p.Sp / 8; k8 += kQ) {
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -444,17 +460,15 @@ __device__ void epi_init(const EpiCtx& c) {
     }
     st_chunk(c.smem_base + p.off_s + k8 * 2048 + c.row * 16, v);
   }
-  const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int k8 = 0; k8 < p.Ap / 8; ++k8) st_chunk(c.smem_base + p.off_a + k8 * 2048 + c.row * 16, z);
 }
 
-// Linear -> LayerNorm(eps 1e-5) -> ELU (actor.py:23-36); row statistics are thread-local
-__device__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb) {
+// Linear -> LayerNorm(eps 1e-5) -> ELU (actor.py:23-36).  This warp owns every kQ-th 32-column group.
+__device__ __forceinline__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb) {
   const TcParams& p = *c.p;
   const uint32_t bias = jb.p_off, gam = bias + p.Ha, bet = gam + p.Ha;
-  const int ngrp = p.Ha / 32;
+  const int ngrp = p.Ha / 32;          // 32-column groups, dealt round-robin to the kQ warps
   float sum = 0.f, sq = 0.f;
-  for (int g = 0; g < ngrp; ++g) {
+  for (int g = c.q; g < ngrp; g += kQ) {
     float v[32];
     tmem_ld32(c.tmem_lane + jb.tmem_col + g * 32, v);
     tmem_ld_wait();
@@ -466,11 +480,24 @@ __device__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb) {
       sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
     }
   }
+  // exchange partials with the other kQ-1 warps of this quarter (scratch = idle P_a panel)
+  const uint32_t scratch = c.smem_base + p.off_a;
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(scratch + (c.q * kTileM + c.row) * 8), "f"(sum), "f"(sq)
+               : "memory");
+  quarter_sync(c.quarter);
+  sum = 0.f; sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < kQ; ++k) {
+    float a, b;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "r"(scratch + (k * kTileM + c.row) * 8) : "memory");
+    sum += a; sq += b;
+  }
   const float inv = 1.f / (float)p.Ha;
   const float mean = sum * inv;
   const float var = fmaxf(sq * inv - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
-  for (int g = 0; g < ngrp; ++g) {
+  const float nmr = -mean * rstd;
+  for (int g = c.q; g < ngrp; g += kQ) {
     float v[32];
     tmem_ld32(c.tmem_lane + jb.tmem_col + g * 32, v);
     tmem_ld_wait();
@@ -479,10 +506,10 @@ __device__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb) {
       const float4 b4 = ldc4(bias + g * 32 + i);
       const float4 g4 = ldc4(gam + g * 32 + i);
       const float4 e4 = ldc4(bet + g * 32 + i);
-      v[i] = elu_fast(fmaf((v[i] + b4.x - mean) * rstd, g4.x, e4.x));
-      v[i + 1] = elu_fast(fmaf((v[i + 1] + b4.y - mean) * rstd, g4.y, e4.y));
-      v[i + 2] = elu_fast(fmaf((v[i + 2] + b4.z - mean) * rstd, g4.z, e4.z));
-      v[i + 3] = elu_fast(fmaf((v[i + 3] + b4.w - mean) * rstd, g4.w, e4.w));
+      v[i] = elu_fast(fmaf(fmaf(v[i] + b4.x, rstd, nmr), g4.x, e4.x));
+      v[i + 1] = elu_fast(fmaf(fmaf(v[i + 1] + b4.y, rstd, nmr), g4.y, e4.y));
+      v[i + 2] = elu_fast(fmaf(fmaf(v[i + 2] + b4.z, rstd, nmr), g4.z, e4.z));
+      v[i + 3] = elu_fast(fmaf(fmaf(v[i + 3] + b4.w, rstd, nmr), g4.w, e4.w));
     }
     const uint32_t dst = c.smem_base + jb.dst_off + (g * 4) * 2048 + c.row * 16;
 #pragma unroll
@@ -490,11 +517,10 @@ __device__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb) {
   }
 }
 
-// bias + ELU -> bf16 panel (embed rssm.py:65, prior hidden rssm.py:33-35)
-__device__ void epi_dense_elu(const EpiCtx& c, const JobDesc& jb) {
-  const TcParams& p = *c.p;
+// bias + ELU -> bf16 panel (embed rssm.py:65, prior hidden rssm.py:33-35); 16-column groups round-robin
+__device__ __forceinline__ void epi_dense_elu(const EpiCtx& c, const JobDesc& jb) {
   const uint32_t bias = jb.p_off;
-  for (int g = 0; g < jb.n / 16; ++g) {
+  for (int g = c.q; g < jb.n / 16; g += kQ) {
     float v[16];
     tmem_ld16(c.tmem_lane + jb.tmem_col + g * 16, v);
     tmem_ld_wait();
@@ -511,35 +537,56 @@ __device__ void epi_dense_elu(const EpiCtx& c, const JobDesc& jb) {
 }
 
 // a = tanh(mu / action_scale) * bound  (actor.py:49-50) -> actions[B,H,A] + P_a panel
-__device__ void epi_mu(const EpiCtx& c, const JobDesc& jb) {
+__device__ __forceinline__ void epi_mu(const EpiCtx& c, const JobDesc& jb) {
   const TcParams& p = *c.p;
+  if (c.q != 0) return;
   const uint32_t bias = jb.p_off, bound = bias + 16;
   float v[16];
   tmem_ld16(c.tmem_lane + jb.tmem_col, v);
   tmem_ld_wait();
 #pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 b4 = ldc4(bias + i), d4 = ldc4(bound + i);
+    v[i] = tanh_fast((v[i] + b4.x) * p.inv_action_scale) * d4.x;
+    v[i + 1] = tanh_fast((v[i + 1] + b4.y) * p.inv_action_scale) * d4.y;
+    v[i + 2] = tanh_fast((v[i + 2] + b4.z) * p.inv_action_scale) * d4.z;
+    v[i + 3] = tanh_fast((v[i + 3] + b4.w) * p.inv_action_scale) * d4.w;
+  }
+#pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float a = tanh_fast((v[i] + c_eparams[bias + i]) * p.inv_action_scale) * c_eparams[bound + i];
-    v[i] = (i < p.A) ? a : 0.f;
-    if (c.valid && i < p.A) p.actions[(c.b * p.H + c.t) * p.A + i] = v[i];
+    if (i >= p.A) v[i] = 0.f;
+    else if (c.valid) p.actions[(c.b * p.H + c.t) * p.A + i] = v[i];
   }
   const uint32_t dst = c.smem_base + jb.dst_off + c.row * 16;
   st_chunk(dst, v);
   st_chunk(dst + 2048, v + 8);
 }
 
-// GRUCell gates for one chunk of state columns (rssm.py:66); h_prev is the fp32
-// master copy in deter_seq[:, t] (written by this same thread one step earlier).
-// It is fetched BEFORE the accumulator barrier so the L2 round trip overlaps the MMAs.
-struct GruPrefetch { float hp[64]; };
+// GRUCell gates (rssm.py:66) for the 16-column groups of one chunk owned by this warp.
+// h_prev is the fp32 master copy in deter_seq[:, t] (written by the warp that owns the same
+// column group one step earlier: same thread).  It is fetched BEFORE the accumulator barrier
+// so the L2 round trip overlaps the MMAs.
+constexpr int kGruGroups = (64 / 16 + kQ - 1) / kQ;   // groups per warp per chunk
+struct GruPrefetch { float hp[kGruGroups][16]; };
 __device__ __forceinline__ void gru_prefetch(const EpiCtx& c, const JobDesc& jb, GruPrefetch& pf) {
   const TcParams& p = *c.p;
   const long long T1 = p.H + 1;
   const float* hprev = p.deter_seq + (c.b * T1 + c.t) * p.D;
 #pragma unroll
-  for (int i = 0; i < 64; ++i) {
-    const int col = jb.col0 + i;
-    pf.hp[i] = (c.valid && i < jb.n && col < p.D) ? hprev[col] : 0.f;
+  for (int k = 0; k < kGruGroups; ++k) {
+    const int g = c.q + k * kQ;
+    const int col = jb.col0 + g * 16;
+    const bool in = c.valid && g * 16 < jb.n;
+    if (in && col + 16 <= p.D && (p.D & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 h4 = *reinterpret_cast<const float4*>(hprev + col + i);
+        pf.hp[k][i] = h4.x; pf.hp[k][i + 1] = h4.y; pf.hp[k][i + 2] = h4.z; pf.hp[k][i + 3] = h4.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pf.hp[k][i] = (in && col + i < p.D) ? hprev[col + i] : 0.f;
+    }
   }
 }
 __device__ __forceinline__ void epi_gru(const EpiCtx& c, const JobDesc& jb, uint32_t tmem, const GruPrefetch& pf) {
@@ -549,7 +596,8 @@ __device__ __forceinline__ void epi_gru(const EpiCtx& c, const JobDesc& jb, uint
   const long long T1 = p.H + 1;
   float* hnext = p.deter_seq + (c.b * T1 + c.t + 1) * p.D;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int k = 0; k < kGruGroups; ++k) {
+    const int g = c.q + k * kQ;
     if (g * 16 < cw) {
       const int col = jb.col0 + g * 16;
       float r[16], z[16], gi[16], gh[16];
@@ -559,13 +607,29 @@ __device__ __forceinline__ void epi_gru(const EpiCtx& c, const JobDesc& jb, uint
       tmem_ld16(tmem + 3 * cw + g * 16, gh);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float rr = sigmoid_fast(r[i] + c_eparams[b_r + col + i]);
-        const float zz = sigmoid_fast(z[i] + c_eparams[b_z + col + i]);
-        const float nn = tanh_fast(gi[i] + c_eparams[b_in + col + i] + rr * (gh[i] + c_eparams[b_hn + col + i]));
-        const float h = fmaf(zz, pf.hp[g * 16 + i] - nn, nn);   // (1-z)*n + z*h
-        r[i] = h;
-        if (c.valid && col + i < p.D) hnext[col + i] = h;
+      for (int i = 0; i < 16; i += 4) {
+        const float4 br = ldc4(b_r + col + i), bz = ldc4(b_z + col + i);
+        const float4 bi = ldc4(b_in + col + i), bh = ldc4(b_hn + col + i);
+        const float brv[4] = {br.x, br.y, br.z, br.w}, bzv[4] = {bz.x, bz.y, bz.z, bz.w};
+        const float biv[4] = {bi.x, bi.y, bi.z, bi.w}, bhv[4] = {bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float rr = sigmoid_fast(r[i + e] + brv[e]);
+          const float zz = sigmoid_fast(z[i + e] + bzv[e]);
+          const float nn = tanh_fast(gi[i + e] + biv[e] + rr * (gh[i + e] + bhv[e]));
+          r[i + e] = fmaf(zz, pf.hp[k][i + e] - nn, nn);   // (1-z)*n + z*h
+        }
+      }
+      if (c.valid) {
+        if (col + 16 <= p.D && (p.D & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(hnext + col + i) = make_float4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (col + i < p.D) hnext[col + i] = r[i];
+        }
       }
       const uint32_t dst = c.smem_base + jb.dst_off + (col / 8) * 2048 + c.row * 16;
       st_chunk(dst, r);
@@ -575,12 +639,13 @@ __device__ __forceinline__ void epi_gru(const EpiCtx& c, const JobDesc& jb, uint
 }
 
 // Gaussian head (rssm.py:179-181) + end-of-step hand-over of h' into the P_h panel
-struct EpsPrefetch { float e[32]; };
+struct EpsPrefetch { float e[16]; };
 __device__ __forceinline__ void eps_prefetch(const EpiCtx& c, EpsPrefetch& pf) {
   const TcParams& p = *c.p;
   const float* eps = p.noise + ((long long)c.t * p.B + c.b) * p.S;
+  const int col = c.q * 16;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) pf.e[i] = (c.valid && i < p.S) ? eps[i] : 0.f;
+  for (int i = 0; i < 16; ++i) pf.e[i] = (c.valid && col + i < p.S) ? eps[col + i] : 0.f;
 }
 __device__ __forceinline__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& jb, const EpsPrefetch& pf) {
   const TcParams& p = *c.p;
@@ -588,7 +653,7 @@ __device__ __forceinline__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& 
   const long long T1 = p.H + 1;
   const long long o = (c.b * T1 + c.t + 1) * p.S;
   const float* eps = p.noise + ((long long)c.t * p.B + c.b) * p.S;
-  for (int g = 0; g < p.Sp / 16; ++g) {
+  for (int g = c.q; g < p.Sp / 16; g += kQ) {
     float m[16], s[16];
     tmem_ld16(c.tmem_lane + jb.tmem_col + g * 16, m);
     tmem_ld16(c.tmem_lane + jb.tmem_col + p.Sp + g * 16, s);
@@ -600,9 +665,7 @@ __device__ __forceinline__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& 
       const float mean = m[i] + c_eparams[b_m + col];
       const float raw = s[i] + c_eparams[b_s + col];
       const float sd = (raw > 20.f ? raw : __logf(1.f + __expf(raw))) + 0.1f;
-      float e;
-      if (g < 2) e = pf.e[(g & 1) * 16 + i];          // first 32 columns were prefetched
-      else e = ok ? eps[col] : 0.f;
+      const float e = (g == c.q) ? pf.e[i] : (ok ? eps[col] : 0.f);   // first group was prefetched
       const float st = fmaf(sd, e, mean);
       m[i] = (col < p.S) ? st : 0.f;
       if (ok) {
@@ -617,7 +680,7 @@ __device__ __forceinline__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& 
   }
   // h' (X[h2..]) -> P_h: every MMA that read the old P_h has completed (this job's
   // accumulator barrier is committed after them)
-  for (int k8 = 0; k8 < p.Dp / 8; ++k8) {
+  for (int k8 = c.q; k8 < p.Dp / 8; k8 += kQ) {
     uint32_t a, b, cc, d;
     const uint32_t src = c.smem_base + p.off_h2 + k8 * 2048 + c.row * 16;
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(cc), "=r"(d) : "r"(src) : "memory");
@@ -645,7 +708,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
     for (uint32_t j = 0; j < 2; ++j) { mbar_init(accf_bar(j), 1); mbar_init(acce_bar(j), kEpiThreads); }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
     tmem_relinquish();
   }
@@ -654,7 +717,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ===================== TMA producer: stream weight stages in consumption order
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
@@ -669,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
             if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
           }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer
     if (lane == 0) {
       uint32_t slot = 0, phase = 0, job = 0;
@@ -706,18 +769,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
       }
     }
   } else {
-    // ===================== epilogue warps: one batch row (TMEM lane) per thread
+    // ===================== epilogue warps: one batch row (TMEM lane) per thread, columns split kQ ways
     EpiCtx c;
     c.p = &p;
     c.smem_base = smem_base;
-    c.row = (warp & 3) * 32 + lane;
-    c.tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    c.quarter = warp & 3;
+    c.q = warp >> 2;
+    c.row = c.quarter * 32 + lane;
+    c.tmem_lane = tmem_base + ((uint32_t)(c.quarter * 32) << 16);
     uint32_t job = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       c.b = (long long)tile * kTileM + c.row;
       c.valid = c.b < p.B;
       c.t = 0;
-      mbar_wait(accf_bar(job), (job >> 1) & 1u);
+      mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
       epi_init(c);
       fence_proxy_async_smem();
       mbar_arrive(acce_bar(job));
@@ -729,24 +794,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
           if (jb.type == JOB_GRU) {
             GruPrefetch pf;
             gru_prefetch(c, jb, pf);
-            mbar_wait(accf_bar(job), (job >> 1) & 1u);
+            mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
             tc_fence_after();
             epi_gru(c, jb, c.tmem_lane + (job & 1u) * 256u, pf);
           } else if (jb.type == JOB_PRIOR2_CONT) {
             EpsPrefetch pf;
             eps_prefetch(c, pf);
-            mbar_wait(accf_bar(job), (job >> 1) & 1u);
+            mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
             tc_fence_after();
             epi_prior2_cont(c, jb, pf);
           } else {
-            mbar_wait(accf_bar(job), (job >> 1) & 1u);
+            mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
             tc_fence_after();
-            switch (jb.type) {
-              case JOB_ACTOR_LN: epi_actor_ln(c, jb); break;
-              case JOB_MU: epi_mu(c, jb); break;
-              case JOB_DENSE_ELU: epi_dense_elu(c, jb); break;
-              default: break;
-            }
+            if (jb.type == JOB_ACTOR_LN) epi_actor_ln(c, jb);
+            else if (jb.type == JOB_DENSE_ELU) epi_dense_elu(c, jb);
+            else if (jb.type == JOB_MU) epi_mu(c, jb);
           }
           tc_fence_before();
           fence_proxy_async_smem();
@@ -758,7 +820,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
 int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,

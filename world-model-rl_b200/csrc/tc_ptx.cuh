@@ -51,6 +51,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Same, for waiters that expect to wait long (epilogue warps): sleep between polls so the
+// polling does not steal issue slots from the producer / MMA warps.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) {
+      printf("wmrl: mbarrier watchdog (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
