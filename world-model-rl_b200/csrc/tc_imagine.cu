@@ -102,6 +102,7 @@ struct TcParams {
   uint32_t off_h, off_s, off_a, off_x, off_h2;   // smem byte offsets of the A panels
   uint32_t ring_off, bar_off;
   int nslots, ntiles;
+  long long* trace;   // optional timeline (WMRL_FLAG_TRACE): [step][job][4] SM clocks of CTA 0's first tile
 };
 
 static inline int ceil16(int x) { return (x + 15) / 16 * 16; }
@@ -332,7 +333,7 @@ size_t tc_packed_bytes(const Dims& d) {
   Plan pl = make_plan(d, nullptr, nullptr);
   return pl.ok ? pl.total_bytes : 0;
 }
-size_t tc_workspace_bytes(const Dims&) { return 256; }
+size_t tc_workspace_bytes(const Dims&) { return 4 * kMaxJobs * 4 * sizeof(long long) + 256; }
 
 // --------------------------------------------------------------------------
 // weight packing kernels
@@ -739,16 +740,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         mbar_arrive(accf_bar(job));   // INIT job has no MMA
         ++job;
-        for (int t = 0; t < p.H; ++t)
+        const bool tr = p.trace && blockIdx.x == 0 && tile == 0;
+        for (int t = 0; t < p.H; ++t) {
+          int jidx = -1;
           for (int s = 0; s < p.nstages; ++s) {
             const uint4 raw = c_stages[s];
             const StageDesc st = *reinterpret_cast<const StageDesc*>(&raw);
+            if (st.flags & ST_FIRST_OF_JOB) ++jidx;
             if ((st.flags & ST_FIRST_OF_JOB) && st.dep) {
               const uint32_t dj = job - st.dep;
               mbar_wait(acce_bar(dj), (dj >> 1) & 1u);
             }
             mbar_wait(full_bar(slot), phase);
             tc_fence_after();
+            if (tr && (st.flags & ST_FIRST_OF_JOB) && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 0] = clock64();
             const uint32_t a_addr = smem_base + (uint32_t)st.a_off16 * 16u;
             const uint32_t b_addr = ring + slot * kSlotBytes;
             const uint32_t tm = tmem_base + st.tmem_col + ((st.flags & ST_DBUF) ? (job & 1u) * 256u : 0u);
@@ -762,10 +767,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
             tc_commit(empty_bar(slot));
             if (st.flags & ST_LAST_OF_JOB) {
               tc_commit(accf_bar(job));
+              if (tr && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 1] = clock64();
               ++job;
             }
             if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
           }
+        }
       }
     }
   } else {
@@ -787,31 +794,40 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
       fence_proxy_async_smem();
       mbar_arrive(acce_bar(job));
       ++job;
+      const bool tr = p.trace && blockIdx.x == 0 && tile == 0 && threadIdx.x == 0;
       for (int t = 0; t < p.H; ++t) {
         c.t = t;
         for (int jb_i = 0; jb_i < p.njobs; ++jb_i) {
           const JobDesc jb = c_jobs[jb_i];
+          long long t_wake = 0;
           if (jb.type == JOB_GRU) {
             GruPrefetch pf;
             gru_prefetch(c, jb, pf);
             mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
             tc_fence_after();
+            if (tr) t_wake = clock64();
             epi_gru(c, jb, c.tmem_lane + (job & 1u) * 256u, pf);
           } else if (jb.type == JOB_PRIOR2_CONT) {
             EpsPrefetch pf;
             eps_prefetch(c, pf);
             mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
             tc_fence_after();
+            if (tr) t_wake = clock64();
             epi_prior2_cont(c, jb, pf);
           } else {
             mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
             tc_fence_after();
+            if (tr) t_wake = clock64();
             if (jb.type == JOB_ACTOR_LN) epi_actor_ln(c, jb);
             else if (jb.type == JOB_DENSE_ELU) epi_dense_elu(c, jb);
             else if (jb.type == JOB_MU) epi_mu(c, jb);
           }
           tc_fence_before();
           fence_proxy_async_smem();
+          if (tr && t < 4) {
+            p.trace[((t * p.njobs) + jb_i) * 4 + 2] = t_wake;
+            p.trace[((t * p.njobs) + jb_i) * 4 + 3] = clock64();
+          }
           mbar_arrive(acce_bar(job));
           ++job;
         }
@@ -827,7 +843,7 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
                    const void* packed, const float* deter0, const float* stoch0,
                    const float* noise, float* deter_seq, float* stoch_seq, float* dist_a,
                    float* dist_b, float* actions, int32_t* idx, void* ws, cudaStream_t st) {
-  (void)w; (void)aw; (void)idx; (void)ws;
+  (void)w; (void)aw; (void)idx;
   Plan pl = make_plan(d, nullptr, nullptr);
   WMRL_REQUIRE(pl.ok, "tc_imagine_fwd: unsupported shape");
   const uint8_t* base = (const uint8_t*)packed;
@@ -846,6 +862,7 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
   p.off_h = pl.off_h; p.off_s = pl.off_s; p.off_a = pl.off_a; p.off_x = pl.off_x; p.off_h2 = pl.off_h2;
   p.ring_off = pl.ring_off; p.bar_off = pl.bar_off; p.nslots = pl.nslots;
   p.ntiles = (d.B + kTileM - 1) / kTileM;
+  p.trace = (d.flags & 4) ? (long long*)ws : nullptr;
   // tables + epilogue parameters -> constant memory (device-to-device from the packed image,
   // stream-ordered before the launch; skipped when this image is already resident)
   if (g_const_src != packed || g_const_gen != pack_generation(packed)) {
