@@ -160,6 +160,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -187,7 +196,19 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return y;
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
-__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// ELU without predicates (a select per element makes the compiler pack 32 predicates into
+// registers): elu(z) = max(z,0) + (exp(min(z,0)) - 1).
+// elu_scaled takes zs = z*log2(e):  ln2*max(zs,0) + (2^min(zs,0) - 1)
+__device__ __forceinline__ float elu_scaled(float zs) {
+  const float e = ex2_fast(fminf(zs, 0.f)) - 1.f;
+  return fmaf(fmaxf(zs, 0.f), 0.6931471805599453f, e);
+}
+__device__ __forceinline__ float elu_fast(float z) { return elu_scaled(z * 1.4426950408889634f); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
