@@ -40,3 +40,9 @@ for j in range(njobs):
     nxt = int(tr[1, j + 1, 0]) - t0 if j + 1 < njobs else int(tr[2, 0, 0]) - t0
     print(f"  {names[j]:7s} {a:9d} {b:9d} {w_:9d} {e:9d} | {w_ - a:7d} {e - w_:7d} {nxt - e:7d}")
 print("step length", int(tr[2, 0, 0]) - int(tr[1, 0, 0]))
+
+pr = ws[600 * 8:(600 + 64) * 8].view(torch.int64).cpu()
+def d(a, b): return int(pr[b]) - int(pr[a])
+print("prior2 probes: math+stage", d(0, 1), " h'copy", d(1, 2), " barrier", d(2, 3), " copy-out", d(3, 4))
+print("LN (last layer) probes: pass1", d(8, 9), " exchange+sync", d(9, 10), " pass2", d(10, 11))
+print("job-end fences (tcgen05.fence + fence.proxy.async):", [d(16 + 2 * j, 17 + 2 * j) for j in range(njobs)])

@@ -104,6 +104,7 @@ struct TcParams {
   uint32_t off_h, off_s, off_a, off_x, off_h2;   // smem byte offsets of the A panels
   uint32_t ring_off, bar_off;
   int nslots, ntiles;
+  int stage_out;      // 1: the Gaussian head stages its fp32 rows in the idle X panel and stores coalesced
   long long* trace;   // optional timeline (WMRL_FLAG_TRACE): [step][job][4] SM clocks of CTA 0's first tile
 };
 
@@ -337,7 +338,7 @@ size_t tc_packed_bytes(const Dims& d) {
   Plan pl = make_plan(d, nullptr, nullptr);
   return pl.ok ? pl.total_bytes : 0;
 }
-size_t tc_workspace_bytes(const Dims&) { return 4 * kMaxJobs * 4 * sizeof(long long) + 256; }
+size_t tc_workspace_bytes(const Dims&) { return 1024 * sizeof(long long); }
 
 // --------------------------------------------------------------------------
 // weight packing kernels
@@ -417,6 +418,13 @@ int tc_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_p
 // --------------------------------------------------------------------------
 using namespace ptx;
 
+// fine-grained timeline probes (thread 0 of CTA 0, step 1 only; active when tracing)
+#define WMRL_PROBE(c, k)                                                                      \
+  do {                                                                                        \
+    if ((c).p->trace && blockIdx.x == 0 && threadIdx.x == 0 && (c).t == 1 && (c).b == 0)      \
+      (c).p->trace[600 + (k)] = clock64();                                                    \
+  } while (0)
+
 // Epilogue organisation: kQ warps per TMEM lane quarter (a warp may only read
 // lanes 32*(warp%4)..+31).  The kQ warps of a quarter own the same 32 batch
 // rows and split every job's accumulator COLUMNS between them, so each SM
@@ -473,6 +481,7 @@ __device__ __forceinline__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb)
   const uint32_t bias = jb.p_off, gam = bias + p.Ha, bet = gam + p.Ha;
   const int ngrp = p.Ha / 32;          // 32-column groups, dealt round-robin to the kQ warps
   float sum = 0.f, sq = 0.f;
+  WMRL_PROBE(c, 8);
   for (int g = c.q; g < ngrp; g += kQ) {
     float v[32];
     tmem_ld32(c.tmem_lane + jb.tmem_col + g * 32, v);
@@ -486,10 +495,12 @@ __device__ __forceinline__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb)
     }
   }
   // exchange partials with the other kQ-1 warps of this quarter (scratch = idle P_a panel)
+  WMRL_PROBE(c, 9);
   const uint32_t scratch = c.smem_base + p.off_a;
   asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(scratch + (c.q * kTileM + c.row) * 8), "f"(sum), "f"(sq)
                : "memory");
   quarter_sync(c.quarter);
+  WMRL_PROBE(c, 10);
   sum = 0.f; sq = 0.f;
 #pragma unroll
   for (int k = 0; k < kQ; ++k) {
@@ -520,6 +531,7 @@ __device__ __forceinline__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb)
 #pragma unroll
     for (int k = 0; k < 4; ++k) st_chunk(dst + k * 2048, v + k * 8);
   }
+  WMRL_PROBE(c, 11);
 }
 
 // bias + ELU -> bf16 panel (embed rssm.py:65, prior hidden rssm.py:33-35); 16-column groups round-robin
@@ -666,6 +678,7 @@ __device__ __forceinline__ void eps_prefetch(const EpiCtx& c, EpsPrefetch& pf) {
 }
 __device__ __forceinline__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& jb, const EpsPrefetch& pf) {
   const TcParams& p = *c.p;
+  WMRL_PROBE(c, 0);
   const uint32_t b_m = jb.p_off, b_s = b_m + p.Sp;
   const long long T1 = p.H + 1;
   const long long o = (c.b * T1 + c.t + 1) * p.S;
@@ -694,7 +707,20 @@ __device__ __forceinline__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& 
         st[i + e] = (col + i + e < p.S) ? fmaf(sd[i + e], ee, mean) : 0.f;
       }
     }
-    if (c.valid) {
+    if (p.stage_out) {
+      // fp32 staging [field][row][Sp] in X[0..h2) (idle: prior2's MMAs have completed); 16-byte chunks
+      // XOR-swizzled by (row & 7) so both these row-strided writes and the row-contiguous reads below
+      // are bank-conflict free
+      const uint32_t rowb = c.smem_base + p.off_x + (uint32_t)c.row * (uint32_t)p.Sp * 4u;
+      const uint32_t fstride = (uint32_t)kTileM * (uint32_t)p.Sp * 4u;
+      const uint32_t c0 = (uint32_t)((2 * g) ^ (c.row & 7)) * 16u, c1 = (uint32_t)((2 * g + 1) ^ (c.row & 7)) * 16u;
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + c0), "f"(m[0]), "f"(m[1]), "f"(m[2]), "f"(m[3]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + c1), "f"(m[4]), "f"(m[5]), "f"(m[6]), "f"(m[7]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + fstride + c0), "f"(sd[0]), "f"(sd[1]), "f"(sd[2]), "f"(sd[3]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + fstride + c1), "f"(sd[4]), "f"(sd[5]), "f"(sd[6]), "f"(sd[7]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + 2 * fstride + c0), "f"(st[0]), "f"(st[1]), "f"(st[2]), "f"(st[3]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + 2 * fstride + c1), "f"(st[4]), "f"(st[5]), "f"(st[6]), "f"(st[7]) : "memory");
+    } else if (c.valid) {
       if (col + 8 <= p.S && (p.S & 1) == 0) {
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
@@ -714,6 +740,7 @@ __device__ __forceinline__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& 
     }
     st_chunk(c.smem_base + jb.dst_off + g * 2048 + c.row * 16, st);
   }
+  WMRL_PROBE(c, 1);
   // h' (X[h2..]) -> P_h: every MMA that read the old P_h has completed (this job's
   // accumulator barrier is committed after them)
   for (int k8 = c.q; k8 < p.Dp / 8; k8 += kQ) {
@@ -724,6 +751,35 @@ __device__ __forceinline__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& 
                  "r"(a), "r"(b), "r"(cc), "r"(d)
                  : "memory");
   }
+  WMRL_PROBE(c, 2);
+  if (p.stage_out) {
+    // all epilogue warps have staged their columns -> each warp streams whole rows out:
+    // one row-field (S contiguous floats) per pass, lanes along the row = coalesced
+    asm volatile("bar.sync 5, %0;" ::"r"(kEpiThreads) : "memory");
+    WMRL_PROBE(c, 3);
+    const int warp = c.q * 4 + c.quarter;
+    const int lane = c.row & 31;
+    const long long tile_b0 = c.b - c.row;
+    const uint32_t fstride = (uint32_t)kTileM * (uint32_t)p.Sp * 4u;
+    const uint32_t xbase = c.smem_base + p.off_x;
+    for (int row = warp; row < kTileM; row += kEpiThreads / 32) {
+      const long long bb = tile_b0 + row;
+      if (bb >= p.B) break;
+      const long long off = (bb * T1 + c.t + 1) * p.S;
+      const uint32_t rb = xbase + (uint32_t)row * (uint32_t)p.Sp * 4u;
+      for (int col = lane; col < p.S; col += 32) {
+        const uint32_t a0 = rb + (uint32_t)(((col >> 2) ^ (row & 7)) * 16 + (col & 3) * 4);
+        float v0, v1, v2;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(a0));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(a0 + fstride));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v2) : "r"(a0 + 2 * fstride));
+        p.mean_seq[off + col] = v0;
+        p.std_seq[off + col] = v1;
+        p.stoch_seq[off + col] = v2;
+      }
+    }
+  }
+  WMRL_PROBE(c, 4);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams p) {
@@ -737,7 +793,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
   auto accf_bar = [&](uint32_t j) { return bars + 128u + 8u * (j & 1u); };
   auto acce_bar = [&](uint32_t j) { return bars + 144u + 8u * (j & 1u); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 192);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index broadcast through a shuffle: the compiler then treats it (and every epilogue
+  // parameter address derived from it) as warp-uniform -> uniform-datapath constant loads
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nslots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -857,8 +916,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
             else if (jb.type == JOB_DENSE_ELU) epi_dense_elu(c, jb);
             else if (jb.type == JOB_MU) epi_mu(c, jb);
           }
+          WMRL_PROBE(c, 16 + jb_i * 2);
           tc_fence_before();
           fence_proxy_async_smem();
+          WMRL_PROBE(c, 17 + jb_i * 2);
           if (tr && t < 4) {
             p.trace[((t * p.njobs) + jb_i) * 4 + 2] = t_wake;
             p.trace[((t * p.njobs) + jb_i) * 4 + 3] = clock64();
@@ -898,6 +959,8 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
   p.ring_off = pl.ring_off; p.bar_off = pl.bar_off; p.nslots = pl.nslots;
   p.ntiles = (d.B + kTileM - 1) / kTileM;
   p.trace = (d.flags & 4) ? (long long*)ws : nullptr;
+  // swizzle needs >= 8 16-byte chunks per row (Sp >= 32) and the staging must fit below the h' columns
+  p.stage_out = (pl.Sp >= 32 && pl.Sp % 32 == 0 && 3u * kTileM * pl.Sp * 4u <= (uint32_t)pl.h2c * 256u) ? 1 : 0;
   // tables + epilogue parameters -> constant memory (device-to-device from the packed image,
   // stream-ordered before the launch; skipped when this image is already resident)
   if (g_const_src != packed || g_const_gen != pack_generation(packed)) {
