@@ -259,7 +259,7 @@ def run_ours(args):
     # launching (current) stream, plus one event pair per launch for the roofline figure
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("WMRL_BENCH_NO_CLOCKS"):
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,6 +271,8 @@ def run_ours(args):
     t_end.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("WMRL_BENCH_DEBUG") and rank == 0:
+        sys.stderr.write("per-launch ms: " + " ".join(f"{a.elapsed_time(b):.1f}" for a, b in ev) + "\n")
     elapsed_ms = t_beg.elapsed_time(t_end)
     launch_ms = [a.elapsed_time(b) for a, b in ev]
     if world > 1:

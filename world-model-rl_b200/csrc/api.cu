@@ -45,11 +45,17 @@ int wmrl_abi_version(void) { return WMRL_ABI_VERSION; }
 const char* wmrl_last_error(void) { return g_last_error.c_str(); }
 
 int wmrl_device_supports_bf16(void) {
+  // cudaGetDeviceProperties costs milliseconds; the attribute query is cheap and cached per device
+  static int cached[64];
+  static bool have[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  cudaDeviceProp p;
-  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
-  return p.major == 10 ? 1 : 0;
+  if (dev >= 0 && dev < 64 && have[dev]) return cached[dev];
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  const int ok = major == 10 ? 1 : 0;
+  if (dev >= 0 && dev < 64) { cached[dev] = ok; have[dev] = true; }
+  return ok;
 }
 
 size_t wmrl_saved_bytes(const wmrl_dims* d, int op) {

@@ -973,11 +973,19 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
     g_const_src = packed;
     g_const_gen = pack_generation(packed);
   }
-  int dev = 0, sms = 148;
+  // per-device launch state, queried / set once
+  static int s_sms[64];
+  static unsigned s_smem[64];
+  int dev = 0;
   WMRL_CUDA_OK(cudaGetDevice(&dev));
-  WMRL_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)pl.smem_bytes));
+  WMRL_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
+  if (s_sms[dev] == 0) WMRL_CUDA_OK(cudaDeviceGetAttribute(&s_sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  if (s_smem[dev] < pl.smem_bytes) {
+    WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)pl.smem_bytes));
+    s_smem[dev] = pl.smem_bytes;
+  }
+  const int sms = s_sms[dev];
   const int grid = std::min(p.ntiles, sms);
   tc_imagine_kernel<<<grid, kThreads, pl.smem_bytes, st>>>(p);
   WMRL_CUDA_OK(cudaGetLastError());
