@@ -26,6 +26,7 @@ ws_n = lib.wmrl_workspace_bytes(C.byref(d), 0)
 ws = torch.zeros(ws_n, dtype=torch.uint8, device=dev)
 w, aw = Fn._rssm_ptrs([p.detach() for p in rssm_p]), Fn._actor_ptrs([p.detach() for p in actor_p], La, bound)
 for _ in range(2):
+    ws.zero_()
     _lib.check(lib.wmrl_imagine_fwd(C.byref(d), C.byref(w), C.byref(aw), packed.data_ptr(), d0.data_ptr(), s0.data_ptr(),
                                     nz.data_ptr(), deter.data_ptr(), stoch.data_ptr(), mean.data_ptr(), std.data_ptr(),
                                     act.data_ptr(), None, None, 0, ws.data_ptr(), ws_n, torch.cuda.current_stream().cuda_stream), "fwd")
@@ -46,3 +47,10 @@ def d(a, b): return int(pr[b]) - int(pr[a])
 print("prior2 probes: math+stage", d(0, 1), " h'copy", d(1, 2), " barrier", d(2, 3), " copy-out", d(3, 4))
 print("LN (last layer) probes: pass1", d(8, 9), " exchange+sync", d(9, 10), " pass2", d(10, 11))
 print("job-end fences (tcgen05.fence + fence.proxy.async):", [d(16 + 2 * j, 17 + 2 * j) for j in range(njobs)])
+
+mw = ws[700 * 8:704 * 8].view(torch.int64).cpu().tolist()
+print(f"MMA-thread waits in step 1 (cycles): dep {mw[0]}  local full {mw[1]}  peer full {mw[2]}  over {mw[3]} stages")
+
+x = ws[704 * 8:712 * 8].view(torch.int64).cpu().tolist()
+print(f"actor1 (32 stages) per-stage avg: MMA lane wait full {x[0]/32:.0f}, wait peer {x[1]/32:.0f}, issue+commit {x[2]/32:.0f} | "
+      f"producer wait empty {x[6]/32:.0f}, issue {x[7]/32:.0f}")

@@ -20,6 +20,8 @@
 // The work is described by two host-built tables (same for every step): STAGES
 // (what the producer loads and the MMA thread issues) and JOBS (what the
 // epilogue warps do once a job's accumulator is complete).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <unordered_map>
 #include <vector>
@@ -75,6 +77,7 @@ struct PackOp {
   int ld;
   int row0_a, valid_a, pad_a, row0_b, valid_b, pad_b;
   int k0, kvalid, nk8;
+  int split;   // 2: the stage is stored as two N-halves (one per CTA of a pair), each [k/8][N/2][8]
   unsigned long long dst_off;
 };
 struct VecOp {
@@ -110,16 +113,29 @@ struct TcParams {
 
 static inline int ceil16(int x) { return (x + 15) / 16 * 16; }
 
+// CTA-group size of the tcgen05 path: 2 = CTA pairs (cta_group::2, M=256 over two SMs, every weight
+// stage split across the pair), 1 = single CTAs.  WMRL_TC_CTA=1 forces the single-CTA kernel.
+static int tc_cta_mode() {
+  static int mode = 0;
+  if (mode == 0) {
+    const char* e = getenv("WMRL_TC_CTA");
+    mode = (e && e[0] == '1') ? 1 : 2;
+  }
+  return mode;
+}
+
 // With 227 KB of shared memory carved out the L1D is ~1 KB, so any global load
 // in the inner loops is a full L2 round trip.  The per-step tables and the
 // epilogue parameters (biases, LayerNorm affine, bound) are therefore served
 // from the constant cache: every access is warp-uniform.
 constexpr int kMaxStages = 512, kMaxJobs = 32, kMaxEparams = 12032;
+constexpr int kMaxStagesSmem = 144;      // stage descriptors mirrored in shared memory (16 B each)
 __constant__ uint4 c_stages[kMaxStages];
 __constant__ JobDesc c_jobs[kMaxJobs];
 __constant__ __align__(16) float c_eparams[kMaxEparams];
 
 struct Plan {
+  int cta = 1;
   int Dp, Sp, Ap, Ha, Hdp, h2c, XW;
   uint32_t off_h, off_s, off_a, off_x, off_h2, panels_bytes, ring_off, bar_off, smem_bytes;
   int nslots;
@@ -168,6 +184,7 @@ static void add_acc_group(Plan& pl, const RowSpec& rs, const std::vector<Seg>& s
       op.k0 = sg.k0 + done * 16;
       op.kvalid = std::max(0, sg.kvalid - done * 16);
       op.nk8 = nk * 2;
+      op.split = pl.cta;
       op.dst_off = pl.data_bytes;
       pl.pack_ops.push_back(op);
       pl.data_bytes += (size_t)nk * N * 32;
@@ -189,6 +206,7 @@ static uint32_t add_vec(Plan& pl, const float* s1, const float* s2, int off, int
 // Build the per-step tables.  Weight pointers may be null (size / launch queries).
 static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw) {
   Plan pl;
+  pl.cta = tc_cta_mode();
   if (d.variant != WMRL_CONTINUOUS) return pl;
   if (d.Ha % 32 != 0 || d.Ha > 512 || d.A > 16 || d.S > 8 * kQ * kP2Groups || d.La < 1) return pl;
   pl.Dp = ceil16(d.D); pl.Sp = ceil16(d.S); pl.Ap = 16; pl.Ha = d.Ha; pl.Hdp = ceil16(d.Hd);
@@ -202,12 +220,13 @@ static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor
   pl.off_h2 = pl.off_x + pl.h2c / 8 * 2048;
   pl.panels_bytes = pl.off_x + pl.XW / 8 * 2048;
   pl.ring_off = pl.panels_bytes;
-  const int avail = kMaxSmem - (int)pl.panels_bytes - 256;
-  pl.nslots = avail / kSlotBytes;
+  const int avail = kMaxSmem - (int)pl.panels_bytes - 256 - kMaxStagesSmem * 16;
+  const int slot_bytes = kSlotBytes / pl.cta;       // a CTA of a pair stores half of every stage
+  pl.nslots = avail / slot_bytes;
   if (pl.nslots < 2) return pl;
   if (pl.nslots > 8) pl.nslots = 8;
-  pl.bar_off = pl.ring_off + pl.nslots * kSlotBytes;
-  pl.smem_bytes = pl.bar_off + 256;
+  pl.bar_off = pl.ring_off + pl.nslots * slot_bytes;
+  pl.smem_bytes = pl.bar_off + 256 + kMaxStagesSmem * 16;   // barriers + the stage table copy
   if (pl.panels_bytes / 16 > 65535) return pl;
 
   const float* nul = nullptr;
@@ -319,7 +338,7 @@ static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor
   }
   for (const StageDesc& st : pl.stages)
     if ((int)st.bytes16 * 16 > kSlotBytes) return pl;
-  if ((int)pl.stages.size() > kMaxStages || (int)pl.jobs.size() > kMaxJobs ||
+  if ((int)pl.stages.size() > kMaxStagesSmem || (int)pl.stages.size() > kMaxStages || (int)pl.jobs.size() > kMaxJobs ||
       (int)pl.eparams_floats > kMaxEparams)
     return pl;
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
@@ -347,8 +366,10 @@ __global__ void pack_stage_kernel(const PackOp* __restrict__ ops, uint8_t* __res
   const PackOp op = ops[blockIdx.x];
   const int N = op.pad_a + op.pad_b;
   const int total = op.nk8 * N;
+  const int halfN = N / op.split;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int kc = i / N, n = i % N;
+    const int di = (n / halfN) * (op.nk8 * halfN) + kc * halfN + (n % halfN);
     int row = -1;
     if (n < op.pad_a) {
       if (n < op.valid_a) row = op.row0_a + n;
@@ -364,7 +385,7 @@ __global__ void pack_stage_kernel(const PackOp* __restrict__ ops, uint8_t* __res
       if (row >= 0 && k < op.kvalid) v = op.src[(size_t)row * op.ld + op.k0 + k];
       out[e] = __float2bfloat16_rn(v);
     }
-    *reinterpret_cast<uint4*>(data + op.dst_off + (size_t)i * 16) = *reinterpret_cast<const uint4*>(out);
+    *reinterpret_cast<uint4*>(data + op.dst_off + (size_t)di * 16) = *reinterpret_cast<const uint4*>(out);
   }
 }
 __global__ void pack_vec_kernel(const VecOp* __restrict__ ops, float* __restrict__ dst) {
@@ -421,8 +442,10 @@ using namespace ptx;
 // fine-grained timeline probes (thread 0 of CTA 0, step 1 only; active when tracing)
 #define WMRL_PROBE(c, k)                                                                      \
   do {                                                                                        \
-    if ((c).p->trace && blockIdx.x == 0 && threadIdx.x == 0 && (c).t == 1 && (c).b == 0)      \
-      (c).p->trace[600 + (k)] = clock64();                                                    \
+    if (kTraceBuild) {                                                                        \
+      if ((c).p->trace && blockIdx.x == 0 && threadIdx.x == 0 && (c).t == 1 && (c).b == 0)    \
+        (c).p->trace[600 + (k)] = clock64();                                                  \
+    }                                                                                         \
   } while (0)
 
 // Epilogue organisation: kQ warps per TMEM lane quarter (a warp may only read
@@ -476,6 +499,7 @@ __device__ __forceinline__ void epi_init(const EpiCtx& c) {
 }
 
 // Linear -> LayerNorm(eps 1e-5) -> ELU (actor.py:23-36).  This warp owns every kQ-th 32-column group.
+template <bool kTraceBuild>
 __device__ __forceinline__ void epi_actor_ln(const EpiCtx& c, const JobDesc& jb) {
   const TcParams& p = *c.p;
   const uint32_t bias = jb.p_off, gam = bias + p.Ha, bet = gam + p.Ha;
@@ -676,6 +700,7 @@ __device__ __forceinline__ void eps_prefetch(const EpiCtx& c, EpsPrefetch& pf) {
     }
   }
 }
+template <bool kTraceBuild>
 __device__ __forceinline__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& jb, const EpsPrefetch& pf) {
   const TcParams& p = *c.p;
   WMRL_PROBE(c, 0);
@@ -782,89 +807,167 @@ __device__ __forceinline__ void epi_prior2_cont(const EpiCtx& c, const JobDesc& 
   WMRL_PROBE(c, 4);
 }
 
+template <int kCta, bool kTraceBuild>
 __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr uint32_t kSlot = kSlotBytes / kCta;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t ring = smem_base + p.ring_off;
   const uint32_t bars = smem_base + p.bar_off;
-  // barrier map (8 B each): full[0..8) | empty[8..16) | acc_full[16..18) | acc_empty[18..20) | tmem ptr @ +192
+  // barrier map (8 B each): full[0..8) | empty[8..16) | acc_full[16..18) | acc_empty[18..20) |
+  // peer_full[20..28) | tmem ptr @ +232
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };
   auto accf_bar = [&](uint32_t j) { return bars + 128u + 8u * (j & 1u); };
   auto acce_bar = [&](uint32_t j) { return bars + 144u + 8u * (j & 1u); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 192);
+  auto peer_full_bar = [&](int s) { return bars + 160u + 8u * s; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 232);
   // warp index broadcast through a shuffle: the compiler then treats it (and every epilogue
   // parameter address derived from it) as warp-uniform -> uniform-datapath constant loads
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  // CTA pair: rank 0 is the leader (issues every MMA for both SMs)
+  const uint32_t rank = (kCta == 2) ? cluster_ctarank() : 0u;
+  const int unit = (kCta == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nunits = (kCta == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int ngroups = (p.ntiles + kCta - 1) / kCta;     // a group = kCta consecutive 128-row tiles
 
+  // The per-stage descriptors are on the critical path of the single-lane producer / MMA loops; the
+  // constant cache is being streamed through by the epilogue warps, so mirror the table in smem.
+  // Each 16-byte record is everything the MMA lane needs, precomputed here in parallel:
+  //   x = A descriptor low word (address | LBO), y = instruction descriptor,
+  //   z = B LBO field (rows per CTA) << 16 | nk16 << 8 | flags, w = tmem column | dep << 16
+  const uint4* stab = reinterpret_cast<const uint4*>(smem + p.bar_off + 256);
+  for (int i = threadIdx.x; i < p.nstages; i += kThreads) {
+    const uint4 raw = c_stages[i];
+    const StageDesc st = *reinterpret_cast<const StageDesc*>(&raw);
+    uint4 rec;
+    rec.x = (uint32_t)make_smem_desc(smem_base + (uint32_t)st.a_off16 * 16u, 2048u, 128u);
+    rec.y = make_idesc_bf16(kTileM * kCta, st.n);
+    rec.z = ((uint32_t)(st.n / kCta) << 16) | ((uint32_t)st.nk16 << 8) | st.flags;
+    rec.w = (uint32_t)st.tmem_col | ((uint32_t)st.dep << 16);
+    reinterpret_cast<uint4*>(smem + p.bar_off + 256)[i] = rec;
+  }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.nslots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (uint32_t j = 0; j < 2; ++j) { mbar_init(accf_bar(j), 1); mbar_init(acce_bar(j), kEpiThreads); }
+    for (int s = 0; s < p.nslots; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(peer_full_bar(s), 1);
+    }
+    for (uint32_t j = 0; j < 2; ++j) {
+      mbar_init(accf_bar(j), 1);
+      mbar_init(acce_bar(j), (kEpiThreads / 32) * kCta);   // one arrival per epilogue warp of the group
+    }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
-    tmem_relinquish();
+    if (kCta == 2) { tmem_alloc2(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512); tmem_relinquish2(); }
+    else { tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCta == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kProducerWarp) {
-    // ===================== TMA producer: stream weight stages in consumption order
+    // ===================== TMA producer: stream this CTA's share of every weight stage
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
-        for (int t = 0; t < p.H; ++t)
+      for (int grp = unit; grp < ngroups; grp += nunits)
+        for (int t = 0; t < p.H; ++t) {
+          const bool trp = kTraceBuild && p.trace && blockIdx.x == 0 && grp == unit && t == 1;
+          long long pw = 0, pi = 0;
           for (int s = 0; s < p.nstages; ++s) {
             const uint4 raw = c_stages[s];
-            const uint32_t bytes = (raw.y & 0xFFFFu) * 16u;
+            const uint32_t bytes = ((raw.y & 0xFFFFu) * 16u) / kCta;
+            const long long c0 = trp ? clock64() : 0;
             mbar_wait(empty_bar(slot), phase ^ 1u);
+            const long long c1 = trp ? clock64() : 0;
             mbar_arrive_expect_tx(full_bar(slot), bytes);
-            bulk_g2s(ring + slot * kSlotBytes, p.stage_data + (size_t)raw.x * 16u, bytes, full_bar(slot));
+            bulk_g2s(ring + slot * kSlot, p.stage_data + (size_t)raw.x * 16u + (size_t)rank * bytes, bytes,
+                     full_bar(slot));
+            if (trp && s >= 16 && s < 48) { pw += c1 - c0; pi += clock64() - c1; }
             if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
           }
+          if (trp) { p.trace[710] = pw; p.trace[711] = pi; }
+        }
     }
   } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && rank != 0) {
+      // ===================== peer CTA: forward "my half of the stage has landed" to the leader
+      uint32_t slot = 0, phase = 0;
+      for (int grp = unit; grp < ngroups; grp += nunits)
+        for (int t = 0; t < p.H; ++t)
+          for (int s = 0; s < p.nstages; ++s) {
+            mbar_wait(full_bar(slot), phase);
+            mbar_arrive_remote(mapa(peer_full_bar(slot), 0));
+            if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+          }
+    } else if (lane == 0) {
+      // ===================== MMA issuer (leader)
       uint32_t slot = 0, phase = 0, job = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int grp = unit; grp < ngroups; grp += nunits) {
         mbar_arrive(accf_bar(job));   // INIT job has no MMA
+        if (kCta == 2) mbar_arrive_remote(mapa(accf_bar(job), 1));
         ++job;
-        const bool tr = p.trace && blockIdx.x == 0 && tile == 0;
+        const bool tr = kTraceBuild && p.trace && blockIdx.x == 0 && grp == unit;
         for (int t = 0; t < p.H; ++t) {
           int jidx = -1;
+          long long acc_dep = 0, acc_full = 0, acc_peer = 0, a1_full = 0, a1_peer = 0, a1_issue = 0;
           for (int s = 0; s < p.nstages; ++s) {
-            const uint4 raw = c_stages[s];
-            const StageDesc st = *reinterpret_cast<const StageDesc*>(&raw);
-            if (st.flags & ST_FIRST_OF_JOB) ++jidx;
-            if ((st.flags & ST_FIRST_OF_JOB) && st.dep) {
-              const uint32_t dj = job - st.dep;
-              mbar_wait(acce_bar(dj), (dj >> 1) & 1u);
+            const uint4 rec = stab[s];
+            const uint32_t flags = rec.z & 0xFFu;
+            if (flags & ST_FIRST_OF_JOB) ++jidx;
+            const bool trw = tr && t == 1;
+            long long w0 = trw ? clock64() : 0;
+            if (flags & ST_FIRST_OF_JOB) {
+              const uint32_t dep = rec.w >> 16;
+              if (dep) {
+                const uint32_t dj = job - dep;
+                mbar_wait(acce_bar(dj), (dj >> 1) & 1u);
+              }
             }
+            long long w1 = trw ? clock64() : 0;
             mbar_wait(full_bar(slot), phase);
+            long long w2 = trw ? clock64() : 0;
+            if (kCta == 2) mbar_wait(peer_full_bar(slot), phase);
             tc_fence_after();
-            if (tr && (st.flags & ST_FIRST_OF_JOB) && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 0] = clock64();
-            const uint32_t a_addr = smem_base + (uint32_t)st.a_off16 * 16u;
-            const uint32_t b_addr = ring + slot * kSlotBytes;
-            const uint32_t tm = tmem_base + st.tmem_col + ((st.flags & ST_DBUF) ? (job & 1u) * 256u : 0u);
-            const uint32_t idesc = make_idesc_bf16(kTileM, st.n);
-            const uint32_t n = st.n;
-            for (uint32_t i = 0; i < st.nk16; ++i) {
-              const uint64_t ad = make_smem_desc(a_addr + i * 4096u, 2048u, 128u);
-              const uint64_t bd = make_smem_desc(b_addr + i * n * 32u, n * 16u, 128u);
-              mma_bf16_ss(tm, ad, bd, idesc, ((st.flags & ST_FIRST_ACC) && i == 0) ? 0u : 1u);
+            long long w3 = 0;
+            if (trw) {
+              w3 = clock64();
+              acc_dep += w1 - w0; acc_full += w2 - w1; acc_peer += w3 - w2;
+              if (s >= 16 && s < 48) { a1_full += w2 - w1; a1_peer += w3 - w2; }
             }
-            tc_commit(empty_bar(slot));
-            if (st.flags & ST_LAST_OF_JOB) {
-              tc_commit(accf_bar(job));
+            if (tr && (flags & ST_FIRST_OF_JOB) && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 0] = clock64();
+            const uint32_t tm = tmem_base + (rec.w & 0xFFFFu) + ((flags & ST_DBUF) ? (job & 1u) * 256u : 0u);
+            const uint32_t idesc = rec.y;
+            const uint32_t nh = rec.z >> 16;                         // B rows held by each CTA
+            uint32_t alo = rec.x;
+            uint32_t blo = (((ring + slot * kSlot) >> 4) & 0x3FFFu) | (nh << 16);   // address | LBO = nh*16 B
+            const uint32_t bstep = nh * 2u;                          // (nh*32 bytes) >> 4
+            constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
+            uint32_t acc = (flags & ST_FIRST_ACC) ? 0u : 1u;
+            const uint32_t nk = (rec.z >> 8) & 0xFFu;
+#pragma unroll 2
+            for (uint32_t i = 0; i < nk; ++i) {
+              if (kCta == 2) mma_bf16_lohi2(tm, alo, kDescHi, blo, kDescHi, idesc, acc);
+              else mma_bf16_lohi(tm, alo, kDescHi, blo, kDescHi, idesc, acc);
+              alo += 256u;                                           // 4096 bytes >> 4
+              blo += bstep;
+              acc = 1u;
+            }
+            if (kCta == 2) tc_commit2(empty_bar(slot), 3); else tc_commit(empty_bar(slot));
+            if (flags & ST_LAST_OF_JOB) {
+              if (kCta == 2) tc_commit2(accf_bar(job), 3); else tc_commit(accf_bar(job));
               if (tr && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 1] = clock64();
               ++job;
             }
+            if (trw && s >= 16 && s < 48) a1_issue += clock64() - w3;
             if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+          }
+          if (tr && t == 1) {
+            p.trace[704] = a1_full; p.trace[705] = a1_peer; p.trace[706] = a1_issue;
+            p.trace[700] = acc_dep; p.trace[701] = acc_full; p.trace[702] = acc_peer; p.trace[703] = p.nstages;
           }
         }
       }
@@ -878,17 +981,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
     c.q = warp >> 2;
     c.row = c.quarter * 32 + lane;
     c.tmem_lane = tmem_base + ((uint32_t)(c.quarter * 32) << 16);
+    const uint32_t acce_leader0 = (kCta == 2) ? mapa(acce_bar(0), 0) : 0u;
+    const uint32_t acce_leader1 = (kCta == 2) ? mapa(acce_bar(1), 0) : 0u;
+    auto job_done = [&](uint32_t job) {
+      // every thread has fenced its smem writes / TMEM reads; one arrival per warp on the leader
+      __syncwarp();
+      if (lane == 0) {
+        if (kCta == 2 && rank != 0) mbar_arrive_remote((job & 1u) ? acce_leader1 : acce_leader0);
+        else mbar_arrive(acce_bar(job));
+      }
+    };
+    auto wait_acc = [&](uint32_t job) {
+      mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
+    };
     uint32_t job = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int grp = unit; grp < ngroups; grp += nunits) {
+      const int tile = grp * kCta + (int)rank;
       c.b = (long long)tile * kTileM + c.row;
       c.valid = c.b < p.B;
       c.t = 0;
-      mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
+      wait_acc(job);
       epi_init(c);
       fence_proxy_async_smem();
-      mbar_arrive(acce_bar(job));
+      job_done(job);
       ++job;
-      const bool tr = p.trace && blockIdx.x == 0 && tile == 0 && threadIdx.x == 0;
+      const bool tr = kTraceBuild && p.trace && blockIdx.x == 0 && grp == unit && threadIdx.x == 0;
       for (int t = 0; t < p.H; ++t) {
         c.t = t;
         for (int jb_i = 0; jb_i < p.njobs; ++jb_i) {
@@ -897,22 +1014,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
           if (jb.type == JOB_GRU) {
             GruPrefetch pf;
             gru_prefetch(c, jb, pf);
-            mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
+            wait_acc(job);
             tc_fence_after();
             if (tr) t_wake = clock64();
             epi_gru(c, jb, c.tmem_lane + (job & 1u) * 256u, pf);
           } else if (jb.type == JOB_PRIOR2_CONT) {
             EpsPrefetch pf;
             eps_prefetch(c, pf);
-            mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
+            wait_acc(job);
             tc_fence_after();
             if (tr) t_wake = clock64();
-            epi_prior2_cont(c, jb, pf);
+            epi_prior2_cont<kTraceBuild>(c, jb, pf);
           } else {
-            mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
+            wait_acc(job);
             tc_fence_after();
             if (tr) t_wake = clock64();
-            if (jb.type == JOB_ACTOR_LN) epi_actor_ln(c, jb);
+            if (jb.type == JOB_ACTOR_LN) epi_actor_ln<kTraceBuild>(c, jb);
             else if (jb.type == JOB_DENSE_ELU) epi_dense_elu(c, jb);
             else if (jb.type == JOB_MU) epi_mu(c, jb);
           }
@@ -924,15 +1041,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
             p.trace[((t * p.njobs) + jb_i) * 4 + 2] = t_wake;
             p.trace[((t * p.njobs) + jb_i) * 4 + 3] = clock64();
           }
-          mbar_arrive(acce_bar(job));
+          job_done(job);
           ++job;
         }
       }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+  if (kCta == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == kMmaWarp) {
+    if (kCta == 2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
@@ -981,13 +1100,37 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
   WMRL_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
   if (s_sms[dev] == 0) WMRL_CUDA_OK(cudaDeviceGetAttribute(&s_sms[dev], cudaDevAttrMultiProcessorCount, dev));
   if (s_smem[dev] < pl.smem_bytes) {
-    WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)pl.smem_bytes));
+    WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)pl.smem_bytes));
+    WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)pl.smem_bytes));
+    WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem_bytes));
     s_smem[dev] = pl.smem_bytes;
   }
   const int sms = s_sms[dev];
-  const int grid = std::min(p.ntiles, sms);
-  tc_imagine_kernel<<<grid, kThreads, pl.smem_bytes, st>>>(p);
+  if (pl.cta == 2) {
+    // CTA pairs: one cluster of 2 per pair of 128-row tiles, at most one pair per two SMs
+    const int pairs = std::min((p.ntiles + 1) / 2, sms / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (p.trace) WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_kernel<2, true>, p));
+    else WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_kernel<2, false>, p));
+  } else {
+    const int grid = std::min(p.ntiles, sms);
+    if (p.trace) tc_imagine_kernel<1, true><<<grid, kThreads, pl.smem_bytes, st>>>(p);
+    else tc_imagine_kernel<1, false><<<grid, kThreads, pl.smem_bytes, st>>>(p);
+  }
   WMRL_CUDA_OK(cudaGetLastError());
   return 0;
 }
