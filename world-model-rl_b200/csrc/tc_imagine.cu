@@ -113,13 +113,15 @@ struct TcParams {
 
 static inline int ceil16(int x) { return (x + 15) / 16 * 16; }
 
-// CTA-group size of the tcgen05 path: 2 = CTA pairs (cta_group::2, M=256 over two SMs, every weight
-// stage split across the pair), 1 = single CTAs.  WMRL_TC_CTA=1 forces the single-CTA kernel.
+// CTA-group size of the tcgen05 path: 1 = single CTAs (default), 2 = CTA pairs (cta_group::2, M=256
+// over two SMs, every weight stage split across the pair; WMRL_TC_CTA=2).  Measured on B200 the pair
+// variant is ~4% slower today: the peer's "half landed" signal has to be relayed through a second
+// mbarrier hop (a plain bulk copy cannot complete_tx on the leader's barrier).
 static int tc_cta_mode() {
   static int mode = 0;
   if (mode == 0) {
     const char* e = getenv("WMRL_TC_CTA");
-    mode = (e && e[0] == '1') ? 1 : 2;
+    mode = (e && e[0] == '2') ? 2 : 1;
   }
   return mode;
 }
@@ -640,41 +642,42 @@ __device__ __forceinline__ void epi_gru(const EpiCtx& c, const JobDesc& jb, uint
   for (int k = 0; k < kGruGroups; ++k) {
     const int g = c.q + k * kQ;
     if (g * 16 < cw) {
-      const int col = jb.col0 + g * 16;
-      float r[16], z[16], gi[16], gh[16];
-      tmem_ld16(tmem + g * 16, r);
-      tmem_ld16(tmem + cw + g * 16, z);
-      tmem_ld16(tmem + 2 * cw + g * 16, gi);
-      tmem_ld16(tmem + 3 * cw + g * 16, gh);
-      tmem_ld_wait();
+      // two 8-column halves: 4 x 8 accumulator registers live at a time
 #pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 br = ldc4(b_r + col + i), bz = ldc4(b_z + col + i);
-        const float4 bi = ldc4(b_in + col + i), bh = ldc4(b_hn + col + i);
-        const float brv[4] = {br.x, br.y, br.z, br.w}, bzv[4] = {bz.x, bz.y, bz.z, bz.w};
-        const float biv[4] = {bi.x, bi.y, bi.z, bi.w}, bhv[4] = {bh.x, bh.y, bh.z, bh.w};
+      for (int hf = 0; hf < 2; ++hf) {
+        const int col = jb.col0 + g * 16 + hf * 8;
+        float r[8], z[8], gi[8], gh[8];
+        tmem_ld8(tmem + g * 16 + hf * 8, r);
+        tmem_ld8(tmem + cw + g * 16 + hf * 8, z);
+        tmem_ld8(tmem + 2 * cw + g * 16 + hf * 8, gi);
+        tmem_ld8(tmem + 3 * cw + g * 16 + hf * 8, gh);
+        tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float rr = sigmoid_fast(r[i + e] + brv[e]);
-          const float zz = sigmoid_fast(z[i + e] + bzv[e]);
-          const float nn = tanh_fast(gi[i + e] + biv[e] + rr * (gh[i + e] + bhv[e]));
-          r[i + e] = fmaf(zz, pf.hp[k][i + e] - nn, nn);   // (1-z)*n + z*h
+        for (int i = 0; i < 8; i += 4) {
+          const float4 br = ldc4(b_r + col + i), bz = ldc4(b_z + col + i);
+          const float4 bi = ldc4(b_in + col + i), bh = ldc4(b_hn + col + i);
+          const float brv[4] = {br.x, br.y, br.z, br.w}, bzv[4] = {bz.x, bz.y, bz.z, bz.w};
+          const float biv[4] = {bi.x, bi.y, bi.z, bi.w}, bhv[4] = {bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float rr = sigmoid_fast(r[i + e] + brv[e]);
+            const float zz = sigmoid_fast(z[i + e] + bzv[e]);
+            const float nn = tanh_fast(gi[i + e] + biv[e] + rr * (gh[i + e] + bhv[e]));
+            r[i + e] = fmaf(zz, pf.hp[k][hf * 8 + i + e] - nn, nn);   // (1-z)*n + z*h
+          }
         }
-      }
-      if (c.valid) {
-        if (col + 16 <= p.D && (p.D & 3) == 0) {
+        if (c.valid) {
+          if (col + 8 <= p.D && (p.D & 3) == 0) {
+            *reinterpret_cast<float4*>(hnext + col) = make_float4(r[0], r[1], r[2], r[3]);
+            *reinterpret_cast<float4*>(hnext + col + 4) = make_float4(r[4], r[5], r[6], r[7]);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(hnext + col + i) = make_float4(r[i], r[i + 1], r[i + 2], r[i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (col + i < p.D) hnext[col + i] = r[i];
+            for (int i = 0; i < 8; ++i)
+              if (col + i < p.D) hnext[col + i] = r[i];
+          }
         }
+        st_chunk(c.smem_base + jb.dst_off + (col / 8) * 2048 + c.row * 16, r);
       }
-      const uint32_t dst = c.smem_base + jb.dst_off + (col / 8) * 2048 + c.row * 16;
-      st_chunk(dst, r);
-      st_chunk(dst + 2048, r + 8);
     }
   }
 }
@@ -981,29 +984,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
     c.q = warp >> 2;
     c.row = c.quarter * 32 + lane;
     c.tmem_lane = tmem_base + ((uint32_t)(c.quarter * 32) << 16);
-    const uint32_t acce_leader0 = (kCta == 2) ? mapa(acce_bar(0), 0) : 0u;
-    const uint32_t acce_leader1 = (kCta == 2) ? mapa(acce_bar(1), 0) : 0u;
-    auto job_done = [&](uint32_t job) {
-      // every thread has fenced its smem writes / TMEM reads; one arrival per warp on the leader
-      __syncwarp();
-      if (lane == 0) {
-        if (kCta == 2 && rank != 0) mbar_arrive_remote((job & 1u) ? acce_leader1 : acce_leader0);
-        else mbar_arrive(acce_bar(job));
-      }
-    };
-    auto wait_acc = [&](uint32_t job) {
-      mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
-    };
+    // job_done: every thread has fenced its smem writes / TMEM reads; one arrival per warp on the leader
+#define WMRL_JOB_DONE(job)                                                              \
+  do {                                                                                  \
+    __syncwarp();                                                                       \
+    if (lane == 0) {                                                                    \
+      if (kCta == 2 && rank != 0) mbar_arrive_remote(mapa(acce_bar(job), 0));           \
+      else mbar_arrive(acce_bar(job));                                                  \
+    }                                                                                   \
+  } while (0)
+#define WMRL_WAIT_ACC(job) mbar_wait_backoff(accf_bar(job), ((job) >> 1) & 1u)
     uint32_t job = 0;
     for (int grp = unit; grp < ngroups; grp += nunits) {
       const int tile = grp * kCta + (int)rank;
       c.b = (long long)tile * kTileM + c.row;
       c.valid = c.b < p.B;
       c.t = 0;
-      wait_acc(job);
+      WMRL_WAIT_ACC(job);
       epi_init(c);
       fence_proxy_async_smem();
-      job_done(job);
+      WMRL_JOB_DONE(job);
       ++job;
       const bool tr = kTraceBuild && p.trace && blockIdx.x == 0 && grp == unit && threadIdx.x == 0;
       for (int t = 0; t < p.H; ++t) {
@@ -1014,19 +1014,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
           if (jb.type == JOB_GRU) {
             GruPrefetch pf;
             gru_prefetch(c, jb, pf);
-            wait_acc(job);
+            WMRL_WAIT_ACC(job);
             tc_fence_after();
             if (tr) t_wake = clock64();
             epi_gru(c, jb, c.tmem_lane + (job & 1u) * 256u, pf);
           } else if (jb.type == JOB_PRIOR2_CONT) {
             EpsPrefetch pf;
             eps_prefetch(c, pf);
-            wait_acc(job);
+            WMRL_WAIT_ACC(job);
             tc_fence_after();
             if (tr) t_wake = clock64();
             epi_prior2_cont<kTraceBuild>(c, jb, pf);
           } else {
-            wait_acc(job);
+            WMRL_WAIT_ACC(job);
             tc_fence_after();
             if (tr) t_wake = clock64();
             if (jb.type == JOB_ACTOR_LN) epi_actor_ln<kTraceBuild>(c, jb);
@@ -1041,7 +1041,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
             p.trace[((t * p.njobs) + jb_i) * 4 + 2] = t_wake;
             p.trace[((t * p.njobs) + jb_i) * 4 + 3] = clock64();
           }
-          job_done(job);
+          WMRL_JOB_DONE(job);
           ++job;
         }
       }
