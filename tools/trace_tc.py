@@ -31,7 +31,7 @@ for _ in range(2):
                                     nz.data_ptr(), deter.data_ptr(), stoch.data_ptr(), mean.data_ptr(), std.data_ptr(),
                                     act.data_ptr(), None, None, 0, ws.data_ptr(), ws_n, torch.cuda.current_stream().cuda_stream), "fwd")
 torch.cuda.synchronize()
-njobs = 3 + 1 + 1 + (((c["D"] + 15) // 16 * 16) + 63) // 64 + 2
+njobs = 3 + 1 + 1 + (((c["D"] + 15) // 16 * 16) + 127) // 128 + 2
 tr = ws[:4 * njobs * 4 * 8].view(torch.int64).cpu().reshape(4, njobs, 4)
 t0 = int(tr[1, 0, 0])
 names = ["actor0", "actor1", "actor2", "mu", "embed"] + [f"gru{i}" for i in range(njobs - 7)] + ["prior1", "prior2"]
@@ -54,3 +54,6 @@ print(f"MMA-thread waits in step 1 (cycles): dep {mw[0]}  local full {mw[1]}  pe
 x = ws[704 * 8:712 * 8].view(torch.int64).cpu().tolist()
 print(f"actor1 (32 stages) per-stage avg: MMA lane wait full {x[0]/32:.0f}, wait peer {x[1]/32:.0f}, issue+commit {x[2]/32:.0f} | "
       f"producer wait empty {x[6]/32:.0f}, issue {x[7]/32:.0f}")
+
+g = ws[712 * 8:716 * 8].view(torch.int64).cpu().tolist()
+print(f"GRU stages ({g[3]}): total dep wait {g[0]}, per-stage avg wait full {g[1]/max(g[3],1):.0f}, issue+commit {g[2]/max(g[3],1):.0f}")

@@ -42,6 +42,7 @@ constexpr int kEpiThreads = 4 * kQ * 32;
 constexpr int kThreads = kEpiThreads + 64;   // epilogue warps first; producer and MMA warps LAST: the issue
                                               // arbiter favours high warp ids and these two must never starve
 constexpr int kProducerWarp = 4 * kQ, kMmaWarp = 4 * kQ + 1;
+constexpr int kGruChunk = 128;           // max state columns per GRU job
 constexpr int kP2Groups = 2;            // Gaussian head: 8-column groups per epilogue warp (S <= 8*kQ*kP2Groups)
 
 enum : uint8_t { ST_FIRST_ACC = 1, ST_LAST_OF_JOB = 2, ST_FIRST_OF_JOB = 4, ST_DBUF = 8 };
@@ -295,23 +296,29 @@ static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor
     add_vec(pl, w ? w->b_ih : nul, w ? w->b_hh : nul, d.D, d.D, pl.Dp);                         // b_z
     add_vec(pl, w ? w->b_ih : nul, nul, 2 * d.D, d.D, pl.Dp);                                    // b_in
     add_vec(pl, w ? w->b_hh : nul, nul, 2 * d.D, d.D, pl.Dp);                                    // b_hn
-    const int nchunks = (pl.Dp + 63) / 64;
+    // Chunks of up to 128 state columns (4 accumulators per column = up to 512 TMEM columns), balanced
+    // in units of 16.  Wide chunks halve the number of MMAs (each costs >= ~61 cycles whatever its N)
+    // and of weight stages; the chunks run serially (MMA -> epilogue -> next chunk).
+    const int groups = pl.Dp / 16;
+    const int nchunks = (pl.Dp + kGruChunk - 1) / kGruChunk;
+    int col0 = 0;
     for (int c = 0; c < nchunks; ++c) {
-      const int cw = std::min(64, pl.Dp - c * 64);
-      const int valid = std::max(0, std::min(cw, d.D - c * 64));
+      const int gcount = groups / nchunks + (c < groups % nchunks ? 1 : 0);
+      const int cw = gcount * 16;
+      const int valid = std::max(0, std::min(cw, d.D - col0));
       JobDesc jb{};
-      jb.type = JOB_GRU; jb.dbuf = 1; jb.n = (uint16_t)cw; jb.tmem_col = 0; jb.col0 = (uint16_t)(c * 64);
+      jb.type = JOB_GRU; jb.dbuf = 0; jb.n = (uint16_t)cw; jb.tmem_col = 0; jb.col0 = (uint16_t)col0;
       jb.dst_off = pl.off_h2; jb.p_off = pb;
       pl.jobs.push_back(jb);
       const float* wih = w ? w->w_ih : nul;
       const float* whh = w ? w->w_hh : nul;
-      const int dep = (c < 2) ? (c + 1) : 2;   // chunk 0/1 wait for the embed epilogue, later ones for chunk c-2
-      RowSpec rz{c * 64, valid, cw, d.D + c * 64, valid, cw};
-      add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}, {pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 0, true,
-                    true, dep, false);
-      RowSpec rn{2 * d.D + c * 64, valid, cw, 0, 0, 0};
-      add_acc_group(pl, rn, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, 2 * cw, true, false, 0, false);
-      add_acc_group(pl, rn, {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 3 * cw, true, false, 0, true);
+      RowSpec rz{col0, valid, cw, d.D + col0, valid, cw};
+      add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}, {pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 0, false,
+                    true, 1, false);
+      RowSpec rn{2 * d.D + col0, valid, cw, 0, 0, 0};
+      add_acc_group(pl, rn, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, 2 * cw, false, false, 0, false);
+      add_acc_group(pl, rn, {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 3 * cw, false, false, 0, true);
+      col0 += cw;
     }
   }
   // ---- prior head
@@ -609,28 +616,27 @@ __device__ __forceinline__ void epi_mu(const EpiCtx& c, const JobDesc& jb) {
 // h_prev is the fp32 master copy in deter_seq[:, t] (written by the warp that owns the same
 // column group one step earlier: same thread).  It is fetched BEFORE the accumulator barrier
 // so the L2 round trip overlaps the MMAs.
-constexpr int kGruGroups = (64 / 16 + kQ - 1) / kQ;   // groups per warp per chunk
-struct GruPrefetch { float hp[kGruGroups][16]; };
-__device__ __forceinline__ void gru_prefetch(const EpiCtx& c, const JobDesc& jb, GruPrefetch& pf) {
+constexpr int kGruGroups = (kGruChunk / 16 + kQ - 1) / kQ;   // 16-column groups per warp per chunk
+struct GruPrefetch { float hp[16]; };   // h_prev of this warp's FIRST group; later groups are fetched in flight
+__device__ __forceinline__ void gru_load_h(const EpiCtx& c, const JobDesc& jb, int g, float (&hp)[16]) {
   const TcParams& p = *c.p;
   const long long T1 = p.H + 1;
   const float* hprev = p.deter_seq + (c.b * T1 + c.t) * p.D;
+  const int col = jb.col0 + g * 16;
+  const bool in = c.valid && g * 16 < jb.n;
+  if (in && col + 16 <= p.D && (p.D & 3) == 0) {
 #pragma unroll
-  for (int k = 0; k < kGruGroups; ++k) {
-    const int g = c.q + k * kQ;
-    const int col = jb.col0 + g * 16;
-    const bool in = c.valid && g * 16 < jb.n;
-    if (in && col + 16 <= p.D && (p.D & 3) == 0) {
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 h4 = *reinterpret_cast<const float4*>(hprev + col + i);
-        pf.hp[k][i] = h4.x; pf.hp[k][i + 1] = h4.y; pf.hp[k][i + 2] = h4.z; pf.hp[k][i + 3] = h4.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) pf.hp[k][i] = (in && col + i < p.D) ? hprev[col + i] : 0.f;
+    for (int i = 0; i < 16; i += 4) {
+      const float4 h4 = *reinterpret_cast<const float4*>(hprev + col + i);
+      hp[i] = h4.x; hp[i + 1] = h4.y; hp[i + 2] = h4.z; hp[i + 3] = h4.w;
     }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) hp[i] = (in && col + i < p.D) ? hprev[col + i] : 0.f;
   }
+}
+__device__ __forceinline__ void gru_prefetch(const EpiCtx& c, const JobDesc& jb, GruPrefetch& pf) {
+  gru_load_h(c, jb, c.q, pf.hp);
 }
 __device__ __forceinline__ void epi_gru(const EpiCtx& c, const JobDesc& jb, uint32_t tmem, const GruPrefetch& pf) {
   const TcParams& p = *c.p;
@@ -638,10 +644,15 @@ __device__ __forceinline__ void epi_gru(const EpiCtx& c, const JobDesc& jb, uint
   const uint32_t b_r = jb.p_off, b_z = b_r + p.Dp, b_in = b_z + p.Dp, b_hn = b_in + p.Dp;
   const long long T1 = p.H + 1;
   float* hnext = p.deter_seq + (c.b * T1 + c.t + 1) * p.D;
+  float hp[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) hp[i] = pf.hp[i];
 #pragma unroll
   for (int k = 0; k < kGruGroups; ++k) {
     const int g = c.q + k * kQ;
     if (g * 16 < cw) {
+      float hn_[16];
+      if (k + 1 < kGruGroups) gru_load_h(c, jb, g + kQ, hn_);     // next group's h_prev, in flight during the math
       // two 8-column halves: 4 x 8 accumulator registers live at a time
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -663,7 +674,7 @@ __device__ __forceinline__ void epi_gru(const EpiCtx& c, const JobDesc& jb, uint
             const float rr = sigmoid_fast(r[i + e] + brv[e]);
             const float zz = sigmoid_fast(z[i + e] + bzv[e]);
             const float nn = tanh_fast(gi[i + e] + biv[e] + rr * (gh[i + e] + bhv[e]));
-            r[i + e] = fmaf(zz, pf.hp[k][hf * 8 + i + e] - nn, nn);   // (1-z)*n + z*h
+            r[i + e] = fmaf(zz, hp[hf * 8 + i + e] - nn, nn);   // (1-z)*n + z*h
           }
         }
         if (c.valid) {
@@ -677,6 +688,10 @@ __device__ __forceinline__ void epi_gru(const EpiCtx& c, const JobDesc& jb, uint
           }
         }
         st_chunk(c.smem_base + jb.dst_off + (col / 8) * 2048 + c.row * 16, r);
+      }
+      if (k + 1 < kGruGroups) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hp[i] = hn_[i];
       }
     }
   }
@@ -917,6 +932,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
         for (int t = 0; t < p.H; ++t) {
           int jidx = -1;
           long long acc_dep = 0, acc_full = 0, acc_peer = 0, a1_full = 0, a1_peer = 0, a1_issue = 0;
+          long long g_dep = 0, g_full = 0, g_issue = 0, g_n = 0;
           for (int s = 0; s < p.nstages; ++s) {
             const uint4 rec = stab[s];
             const uint32_t flags = rec.z & 0xFFu;
@@ -940,6 +956,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
               w3 = clock64();
               acc_dep += w1 - w0; acc_full += w2 - w1; acc_peer += w3 - w2;
               if (s >= 16 && s < 48) { a1_full += w2 - w1; a1_peer += w3 - w2; }
+              if (flags & ST_DBUF) { g_dep += w1 - w0; g_full += w2 - w1; g_n += 1; }
             }
             if (tr && (flags & ST_FIRST_OF_JOB) && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 0] = clock64();
             const uint32_t tm = tmem_base + (rec.w & 0xFFFFu) + ((flags & ST_DBUF) ? (job & 1u) * 256u : 0u);
@@ -966,10 +983,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
               ++job;
             }
             if (trw && s >= 16 && s < 48) a1_issue += clock64() - w3;
+            if (trw && (flags & ST_DBUF)) g_issue += clock64() - w3;
             if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
           }
           if (tr && t == 1) {
             p.trace[704] = a1_full; p.trace[705] = a1_peer; p.trace[706] = a1_issue;
+            p.trace[712] = g_dep; p.trace[713] = g_full; p.trace[714] = g_issue; p.trace[715] = g_n;
             p.trace[700] = acc_dep; p.trace[701] = acc_full; p.trace[702] = acc_peer; p.trace[703] = p.nstages;
           }
         }
@@ -1017,7 +1036,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
             WMRL_WAIT_ACC(job);
             tc_fence_after();
             if (tr) t_wake = clock64();
-            epi_gru(c, jb, c.tmem_lane + (job & 1u) * 256u, pf);
+            epi_gru(c, jb, c.tmem_lane + (jb.dbuf ? (job & 1u) * 256u : 0u), pf);
           } else if (jb.type == JOB_PRIOR2_CONT) {
             EpsPrefetch pf;
             eps_prefetch(c, pf);
