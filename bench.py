@@ -179,7 +179,7 @@ def run_reference(args):
     torch.set_num_threads(threads)
     w = {k: v.detach() for k, v in rssm.state_dict().items()}
     aw = {k: v.detach() for k, v in actor.state_dict().items()}
-    rows = 4096     # bounded sample of the 65,536-row workload; CPU rate is flat in B beyond a few thousand rows
+    rows = 16384    # bounded sample of the 65,536-row workload (~0.4 s per step); the CPU rate is flat in B here
     d0, s0, _ = host_inputs(c, rows, 11, pin=False)
     times = []
     with torch.no_grad():
@@ -197,12 +197,48 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(c, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{rows} of 65536 start states x H=15 per step, fp32, torch CPU, "
+                         "sample": f"{rows} of 65536 start states x H=15 per step, fp32, torch CPU on {threads} threads, "
                                    f"oracle/rssm_oracle.py::imagine_rollout_reference_like"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+def aux_configs(dev):
+    """Informational, outside the timed region: BASELINE configs[1] (discrete D600/32x32, 2500 start states,
+    H=15) forward + hand-written actor-BPTT backward through the fp32 CUDA path, as latent-steps/s."""
+    import wmrl
+    torch.manual_seed(0)
+    B, H, D, S, C, A = 2500, 15, 600, 32, 32, 6
+    rssm = wmrl.DiscreteRSSM(D, D, S, C, 1024, A).to(dev)
+    actor = wmrl.Actor(D + S * C, A, 1.0, 3, 512).to(dev)
+    for p_ in rssm.parameters():
+        p_.requires_grad_(False)
+    g = torch.Generator().manual_seed(1)
+    d0 = torch.tanh(torch.randn(B, D, generator=g)).to(dev)
+    s0 = torch.nn.functional.one_hot(torch.randint(0, S, (B, C), generator=g), S).float().reshape(B, C * S).to(dev)
+    init = wmrl.InternalStateDiscrete(d0, s0, torch.randn(B, C, S, generator=g).to(dev))
+    q = torch.empty(H, B, C, S).exponential_(1.0, generator=g).to(dev)
+    gf = torch.randn(B, H, D + S * C, generator=g).to(dev) / B
+
+    def step():
+        actor.zero_grad(set_to_none=True)
+        seq = rssm.imagine_rollout(init, actor, H, noise=q)
+        (seq.get_features() * gf).sum().backward()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 3
+    return {"configs[1] discrete D600 32x32, 2500x15, fwd + actor-BPTT bwd, fp32 CUDA path":
+            {"ms": ms, "latent_steps_per_s": B * H / ms * 1e3, "flops_per_latent_step_fwd_bwd": 21499712}}
 
 
 def workload_config(c, n_gpus):
@@ -355,14 +391,16 @@ def run_ours(args):
                          "peak_source": f"{peaks_src} bf16_tflops_sustained (MEASURED_PEAKS.json)",
                          "frac_of_burst": achieved_tf / float(peaks.get("bf16_tflops", peak_tf))},
         }
+        if world == 1 and not args.no_aux:
+            line["aux"] = aux_configs(dev)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            rows = 4096
-            rate, secs = cpu_reference_rate(c, rssm, actor, rows, repeats=3, threads=threads)
+            rows = B          # the whole workload: ~1.5-2.5 s per pass on 16 cores, ~10 s in total
+            rate, secs = cpu_reference_rate(c, rssm, actor, rows, repeats=4, threads=threads)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{rows} of {B} start states x H={H}, best of 3 passes "
-                                              f"({secs:.2f} s each), fp32 torch CPU, oracle restatement of "
-                                              f"rssm.py:123-140"}
+                                    "sample": f"all {rows} start states x H={H}, 1 warm-up + best of 4 passes "
+                                              f"({secs:.2f} s each), fp32 torch CPU on {threads} threads, oracle "
+                                              f"restatement of rssm.py:123-140 (internal RNG, torch.cat growth)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -376,6 +414,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

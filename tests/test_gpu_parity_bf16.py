@@ -108,3 +108,17 @@ def test_bf16_with_grad_uses_recording_path():
     seq = rssm.imagine_rollout(HG.init_state(rssm, deter0, stoch0), actor, 3, noise=noise.cuda())
     seq.get_features().square().mean().backward()
     assert actor.mu.weight.grad is not None and torch.isfinite(actor.mu.weight.grad).all()
+
+
+def test_bf16_cta_pair_variant():
+    """the cta_group::2 (CTA pair) kernel variant stays parity-green (selected with WMRL_TC_CTA=2,
+    read once per process -> run in a subprocess)."""
+    import os, subprocess, sys
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    env = dict(os.environ, WMRL_TC_CTA="2")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity_bf16.py"), "-q", "-x",
+                        "-k", "teacher_forced or free_running", "-m", "gpu"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
