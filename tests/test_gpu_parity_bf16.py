@@ -110,13 +110,15 @@ def test_bf16_with_grad_uses_recording_path():
     assert actor.mu.weight.grad is not None and torch.isfinite(actor.mu.weight.grad).all()
 
 
-def test_bf16_cta_pair_variant():
-    """the cta_group::2 (CTA pair) kernel variant stays parity-green (selected with WMRL_TC_CTA=2,
-    read once per process -> run in a subprocess)."""
+@pytest.mark.parametrize("mode", ["1", "2", "3"])
+def test_bf16_kernel_variants(mode):
+    """every tcgen05 kernel variant stays parity-green: 1 = single CTA, 2 = CTA pair (cta_group::2, M=256),
+    3 = folded CTA pair (cta_group::2, M=128, 64 rows per CTA).  WMRL_TC_MODE is read once per process, so
+    each variant runs in a subprocess."""
     import os, subprocess, sys
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    env = dict(os.environ, WMRL_TC_CTA="2")
+    env = dict(os.environ, WMRL_TC_MODE=mode)
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity_bf16.py"), "-q", "-x",
                         "-k", "teacher_forced or free_running", "-m", "gpu"], env=env, capture_output=True, text=True,

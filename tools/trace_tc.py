@@ -32,6 +32,7 @@ for _ in range(2):
                                     act.data_ptr(), None, None, 0, ws.data_ptr(), ws_n, torch.cuda.current_stream().cuda_stream), "fwd")
 torch.cuda.synchronize()
 njobs = 3 + 1 + 1 + (((c["D"] + 15) // 16 * 16) + 127) // 128 + 2
+fold = os.environ.get("WMRL_TC_MODE") == "3"
 tr = ws[:4 * njobs * 4 * 8].view(torch.int64).cpu().reshape(4, njobs, 4)
 t0 = int(tr[1, 0, 0])
 names = ["actor0", "actor1", "actor2", "mu", "embed"] + [f"gru{i}" for i in range(njobs - 7)] + ["prior1", "prior2"]
@@ -57,3 +58,7 @@ print(f"actor1 (32 stages) per-stage avg: MMA lane wait full {x[0]/32:.0f}, wait
 
 g = ws[712 * 8:716 * 8].view(torch.int64).cpu().tolist()
 print(f"GRU stages ({g[3]}): total dep wait {g[0]}, per-stage avg wait full {g[1]/max(g[3],1):.0f}, issue+commit {g[2]/max(g[3],1):.0f}")
+
+f = ws[720 * 8:725 * 8].view(torch.int64).cpu().tolist()
+if f[4]:
+    print(f"fold kernel, actor1 ({f[4]} stages) per-stage avg: wait full {f[0]/f[4]:.0f}, wait peer {f[1]/f[4]:.0f}, MMA issue {f[2]/f[4]:.0f}, commit {f[3]/f[4]:.0f}")

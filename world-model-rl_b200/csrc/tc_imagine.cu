@@ -42,6 +42,7 @@ constexpr int kEpiThreads = 4 * kQ * 32;
 constexpr int kThreads = kEpiThreads + 64;   // epilogue warps first; producer and MMA warps LAST: the issue
                                               // arbiter favours high warp ids and these two must never starve
 constexpr int kProducerWarp = 4 * kQ, kMmaWarp = 4 * kQ + 1;
+constexpr int kDefaultTcMode = 3;
 constexpr int kGruChunk = 128;           // max state columns per GRU job
 constexpr int kP2Groups = 2;            // Gaussian head: 8-column groups per epilogue warp (S <= 8*kQ*kP2Groups)
 
@@ -76,7 +77,8 @@ static_assert(sizeof(JobDesc) == 32, "JobDesc must be 32 bytes");
 struct PackOp {
   const float* src;
   int ld;
-  int row0_a, valid_a, pad_a, row0_b, valid_b, pad_b;
+  int nseg;                 // the stage's N rows are the concatenation of up to 4 source row ranges
+  int row0[4], valid[4], pad[4];
   int k0, kvalid, nk8;
   int split;   // 2: the stage is stored as two N-halves (one per CTA of a pair), each [k/8][N/2][8]
   unsigned long long dst_off;
@@ -108,21 +110,24 @@ struct TcParams {
   uint32_t off_h, off_s, off_a, off_x, off_h2;   // smem byte offsets of the A panels
   uint32_t ring_off, bar_off;
   int nslots, ntiles;
+  uint32_t slot_bytes;   // ring slot size per CTA
   int stage_out;      // 1: the Gaussian head stages its fp32 rows in the idle X panel and stores coalesced
   long long* trace;   // optional timeline (WMRL_FLAG_TRACE): [step][job][4] SM clocks of CTA 0's first tile
 };
 
 static inline int ceil16(int x) { return (x + 15) / 16 * 16; }
 
-// CTA-group size of the tcgen05 path: 1 = single CTAs (default), 2 = CTA pairs (cta_group::2, M=256
-// over two SMs, every weight stage split across the pair; WMRL_TC_CTA=2).  Measured on B200 the pair
-// variant is ~4% slower today: the peer's "half landed" signal has to be relayed through a second
-// mbarrier hop (a plain bulk copy cannot complete_tx on the leader's barrier).
-static int tc_cta_mode() {
+// Kernel variants of the tcgen05 path (env WMRL_TC_MODE, read once):
+//   1 = single CTAs, 128-row tiles (cta_group::1, M=128)
+//   2 = CTA pairs, 2 x 128 rows (cta_group::2, M=256; every weight stage split across the pair)
+//   3 = CTA pairs, 2 x 64 rows ("folded": cta_group::2, M=128; each CTA's 64 rows use all 128 TMEM lanes,
+//       lanes 0-63 hold accumulator columns [0,N/2), lanes 64-127 columns [N/2,N); half-size panels leave room
+//       for a 16-slot weight ring)
+static int tc_mode() {
   static int mode = 0;
   if (mode == 0) {
-    const char* e = getenv("WMRL_TC_CTA");
-    mode = (e && e[0] == '2') ? 2 : 1;
+    const char* e = getenv("WMRL_TC_MODE");
+    mode = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : kDefaultTcMode;
   }
   return mode;
 }
@@ -133,12 +138,16 @@ static int tc_cta_mode() {
 // from the constant cache: every access is warp-uniform.
 constexpr int kMaxStages = 512, kMaxJobs = 32, kMaxEparams = 12032;
 constexpr int kMaxStagesSmem = 144;      // stage descriptors mirrored in shared memory (16 B each)
+constexpr int kMaxSlots = 16, kBarBytes = 512;   // barrier map: full[16] | empty[16] | peer_full[16] | acc | tmem ptr
 __constant__ uint4 c_stages[kMaxStages];
 __constant__ JobDesc c_jobs[kMaxJobs];
 __constant__ __align__(16) float c_eparams[kMaxEparams];
 
 struct Plan {
-  int cta = 1;
+  int cta = 1;          // CTAs per group (1 or 2)
+  bool fold = false;    // 64 rows per CTA, accumulator columns folded over the two TMEM lane halves
+  uint32_t ps = 2048;   // bytes between the 8-column chunks of an A panel (rows per CTA * 16)
+  int stage_bytes = kSlotBytes;   // max bytes of one weight stage (all CTAs of the group together)
   int Dp, Sp, Ap, Ha, Hdp, h2c, XW;
   uint32_t off_h, off_s, off_a, off_x, off_h2, panels_bytes, ring_off, bar_off, smem_bytes;
   int nslots;
@@ -151,13 +160,26 @@ struct Plan {
   bool ok = false;
 };
 
-struct RowSpec { int row0_a, valid_a, pad_a, row0_b, valid_b, pad_b; };
+struct RowSeg { int row0, valid, pad; };
+struct RowSpec {
+  int nseg = 0;
+  RowSeg seg[4];
+  RowSpec() {}
+  RowSpec(int r0, int v, int p) { nseg = 1; seg[0] = {r0, v, p}; }
+  RowSpec(int r0, int v0, int p0, int r1, int v1, int p1) {
+    nseg = 0;
+    add(r0, v0, p0);
+    if (p1 > 0) add(r1, v1, p1);
+  }
+  void add(int r0, int v, int p) { seg[nseg++] = {r0, v < 0 ? 0 : (v > p ? p : v), p}; }
+  int N() const { int n = 0; for (int i = 0; i < nseg; ++i) n += seg[i].pad; return n; }
+};
 struct Seg { uint32_t a_off; int kpad; const float* src; int ld; int k0; int kvalid; };
 
 static void add_acc_group(Plan& pl, const RowSpec& rs, const std::vector<Seg>& segs, int tmem_col,
                           bool dbuf, bool first_of_job, int dep, bool last_of_job) {
-  const int N = rs.pad_a + rs.pad_b;
-  int per = kSlotBytes / (N * 32);
+  const int N = rs.N();
+  int per = pl.stage_bytes / (N * 32);
   if (per < 1) per = 1;
   if (per > 64) per = 64;
   bool first_acc = true;
@@ -176,14 +198,14 @@ static void add_acc_group(Plan& pl, const RowSpec& rs, const std::vector<Seg>& s
       if (dbuf) st.flags |= ST_DBUF;
       const bool last = (si + 1 == segs.size()) && (done + nk == total);
       if (last && last_of_job) st.flags |= ST_LAST_OF_JOB;
-      st.a_off16 = (uint16_t)((sg.a_off + (uint32_t)done * 4096u) / 16);
+      st.a_off16 = (uint16_t)((sg.a_off + (uint32_t)done * 2u * pl.ps) / 16);
       st.n = (uint16_t)N;
       st.tmem_col = (uint16_t)tmem_col;
       pl.stages.push_back(st);
       PackOp op{};
       op.src = sg.src; op.ld = sg.ld;
-      op.row0_a = rs.row0_a; op.valid_a = rs.valid_a; op.pad_a = rs.pad_a;
-      op.row0_b = rs.row0_b; op.valid_b = rs.valid_b; op.pad_b = rs.pad_b;
+      op.nseg = rs.nseg;
+      for (int q = 0; q < rs.nseg; ++q) { op.row0[q] = rs.seg[q].row0; op.valid[q] = rs.seg[q].valid; op.pad[q] = rs.seg[q].pad; }
       op.k0 = sg.k0 + done * 16;
       op.kvalid = std::max(0, sg.kvalid - done * 16);
       op.nk8 = nk * 2;
@@ -207,30 +229,39 @@ static uint32_t add_vec(Plan& pl, const float* s1, const float* s2, int off, int
 }
 
 // Build the per-step tables.  Weight pointers may be null (size / launch queries).
-static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw) {
+static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw, int mode) {
   Plan pl;
-  pl.cta = tc_cta_mode();
+  pl.cta = mode >= 2 ? 2 : 1;
+  pl.fold = mode == 3;
+  pl.ps = pl.fold ? 1024u : 2048u;
+  // folded pairs have ~128 KB of ring per CTA: 64 KB stages (32 KB per CTA, 4 slots) cut the number of
+  // stages - and with it the per-stage handshakes of the pair protocol - by ~3.5x
+  pl.stage_bytes = pl.fold ? 65536 : kSlotBytes;
   if (d.variant != WMRL_CONTINUOUS) return pl;
   if (d.Ha % 32 != 0 || d.Ha > 512 || d.A > 16 || d.S > 8 * kQ * kP2Groups || d.La < 1) return pl;
+  if (pl.fold && (d.Ha % 64 != 0 || d.A > 8)) return pl;
   pl.Dp = ceil16(d.D); pl.Sp = ceil16(d.S); pl.Ap = 16; pl.Ha = d.Ha; pl.Hdp = ceil16(d.Hd);
   if (pl.Hdp > 512 || pl.Dp > 4096) return pl;
+  const uint32_t PS = pl.ps;
   pl.h2c = std::max(pl.Dp, pl.Hdp);
   pl.XW = std::max(d.Ha, pl.h2c + pl.Dp);
   pl.off_h = 0;
-  pl.off_s = pl.off_h + pl.Dp / 8 * 2048;
-  pl.off_a = pl.off_s + pl.Sp / 8 * 2048;
-  pl.off_x = pl.off_a + pl.Ap / 8 * 2048;
-  pl.off_h2 = pl.off_x + pl.h2c / 8 * 2048;
-  pl.panels_bytes = pl.off_x + pl.XW / 8 * 2048;
+  pl.off_s = pl.off_h + pl.Dp / 8 * PS;
+  pl.off_a = pl.off_s + pl.Sp / 8 * PS;
+  pl.off_x = pl.off_a + pl.Ap / 8 * PS;
+  pl.off_h2 = pl.off_x + pl.h2c / 8 * PS;
+  pl.panels_bytes = pl.off_x + pl.XW / 8 * PS;
   pl.ring_off = pl.panels_bytes;
-  const int avail = kMaxSmem - (int)pl.panels_bytes - 256 - kMaxStagesSmem * 16;
-  const int slot_bytes = kSlotBytes / pl.cta;       // a CTA of a pair stores half of every stage
+  const int avail = kMaxSmem - (int)pl.panels_bytes - kBarBytes - kMaxStagesSmem * 16;
+  const int slot_bytes = pl.stage_bytes / pl.cta;   // a CTA of a pair stores half of every stage
   pl.nslots = avail / slot_bytes;
   if (pl.nslots < 2) return pl;
-  if (pl.nslots > 8) pl.nslots = 8;
+  if (pl.nslots > kMaxSlots) pl.nslots = kMaxSlots;
   pl.bar_off = pl.ring_off + pl.nslots * slot_bytes;
-  pl.smem_bytes = pl.bar_off + 256 + kMaxStagesSmem * 16;   // barriers + the stage table copy
+  pl.smem_bytes = pl.bar_off + kBarBytes + kMaxStagesSmem * 16;   // barriers + the stage table copy
   if (pl.panels_bytes / 16 > 65535) return pl;
+  // TMEM columns taken by an accumulator group of N columns
+  auto tc = [&](int n) { return pl.fold ? n / 2 : n; };
 
   const float* nul = nullptr;
   auto W = [&](const float* const* p) { return p ? *p : nul; };
@@ -259,7 +290,7 @@ static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor
       } else {
         segs.push_back({pl.off_x, d.Ha, lw, d.Ha, 0, d.Ha});
       }
-      add_acc_group(pl, rs, segs, nc * 256, false, nc == 0, 1, nc == nchunks - 1);
+      add_acc_group(pl, rs, segs, nc * tc(256), false, nc == 0, 1, nc == nchunks - 1);
     }
   }
   // ---- mu head
@@ -287,7 +318,7 @@ static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor
       const int valid = std::max(0, std::min(padr, d.D - nc * 256));
       RowSpec rs{nc * 256, valid, padr, 0, 0, 0};
       add_acc_group(pl, rs, {{pl.off_s, pl.Sp, ew, Ke, 0, d.S_in}, {pl.off_a, pl.Ap, ew, Ke, d.S_in, d.A}},
-                    nc * 256, false, nc == 0, 1, nc == nchunks - 1);
+                    nc * tc(256), false, nc == 0, 1, nc == nchunks - 1);
     }
   }
   // ---- GRU, chunks of 64 state columns: TMEM [r | z | i_n | h_n], double buffered
@@ -307,17 +338,35 @@ static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor
       const int cw = gcount * 16;
       const int valid = std::max(0, std::min(cw, d.D - col0));
       JobDesc jb{};
-      jb.type = JOB_GRU; jb.dbuf = 0; jb.n = (uint16_t)cw; jb.tmem_col = 0; jb.col0 = (uint16_t)col0;
+      jb.type = JOB_GRU; jb.dbuf = pl.fold ? 1 : 0; jb.n = (uint16_t)cw; jb.tmem_col = 0; jb.col0 = (uint16_t)col0;
       jb.dst_off = pl.off_h2; jb.p_off = pb;
       pl.jobs.push_back(jb);
       const float* wih = w ? w->w_ih : nul;
       const float* whh = w ? w->w_hh : nul;
-      RowSpec rz{col0, valid, cw, d.D + col0, valid, cw};
-      add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}, {pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 0, false,
-                    true, 1, false);
-      RowSpec rn{2 * d.D + col0, valid, cw, 0, 0, 0};
-      add_acc_group(pl, rn, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, 2 * cw, false, false, 0, false);
-      add_acc_group(pl, rn, {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 3 * cw, false, false, 0, true);
+      if (pl.fold) {
+        // folded: a lane half owns state columns [col0 + hf*cw/2, +cw/2) and needs r, z, i_n, h_n of exactly
+        // those -> B rows of the r|z group are ordered [r lo, z lo, r hi, z hi]; TMEM (per lane half):
+        // r @0, z @cw/2, i_n @cw, h_n @cw+cw/2 - 2*cw columns, double buffered in the two 256-column halves
+        const int hw = cw / 2;
+        RowSpec rz;
+        rz.add(col0, d.D - col0, hw);
+        rz.add(d.D + col0, d.D - col0, hw);
+        rz.add(col0 + hw, d.D - col0 - hw, hw);
+        rz.add(d.D + col0 + hw, d.D - col0 - hw, hw);
+        const int dep = (c < 2) ? (c + 1) : 2;   // chunk 0/1 wait for the embed epilogue, later ones for chunk c-2
+        add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}, {pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 0, true,
+                      true, dep, false);
+        RowSpec rn(2 * d.D + col0, valid, cw);
+        add_acc_group(pl, rn, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, cw, true, false, 0, false);
+        add_acc_group(pl, rn, {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, cw + hw, true, false, 0, true);
+      } else {
+        RowSpec rz{col0, valid, cw, d.D + col0, valid, cw};
+        add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}, {pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 0, false,
+                      true, 1, false);
+        RowSpec rn{2 * d.D + col0, valid, cw, 0, 0, 0};
+        add_acc_group(pl, rn, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, 2 * cw, false, false, 0, false);
+        add_acc_group(pl, rn, {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 3 * cw, false, false, 0, true);
+      }
       col0 += cw;
     }
   }
@@ -332,7 +381,7 @@ static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor
       const int padr = std::min(256, pl.Hdp - nc * 256);
       const int valid = std::max(0, std::min(padr, d.Hd - nc * 256));
       RowSpec rs{nc * 256, valid, padr, 0, 0, 0};
-      add_acc_group(pl, rs, {{pl.off_h2, pl.Dp, w ? w->prior0_w : nul, d.D, 0, d.D}}, nc * 256, false, nc == 0, 1,
+      add_acc_group(pl, rs, {{pl.off_h2, pl.Dp, w ? w->prior0_w : nul, d.D, 0, d.D}}, nc * tc(256), false, nc == 0, 1,
                     nc == nchunks - 1);
     }
   }
@@ -342,11 +391,21 @@ static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor
     jb.p_off = add_vec(pl, w ? w->prior2_b : nul, nul, 0, d.S, pl.Sp);
     add_vec(pl, w ? w->prior2_b : nul, nul, d.S, d.S, pl.Sp);
     pl.jobs.push_back(jb);
-    RowSpec rs{0, d.S, pl.Sp, d.S, d.S, pl.Sp};   // mean rows -> cols [0,Sp), raw rows -> [Sp,2Sp)
+    RowSpec rs;
+    if (pl.fold) {   // per lane half: [mean | raw] of the latent columns it owns
+      const int hw = pl.Sp / 2;
+      rs.add(0, d.S, hw);
+      rs.add(d.S, d.S, hw);
+      rs.add(hw, d.S - hw, hw);
+      rs.add(d.S + hw, d.S - hw, hw);
+    } else {         // mean rows -> cols [0,Sp), raw rows -> [Sp,2Sp)
+      rs.add(0, d.S, pl.Sp);
+      rs.add(d.S, d.S, pl.Sp);
+    }
     add_acc_group(pl, rs, {{pl.off_x, pl.Hdp, w ? w->prior2_w : nul, d.Hd, 0, d.Hd}}, 0, false, true, 1, true);
   }
   for (const StageDesc& st : pl.stages)
-    if ((int)st.bytes16 * 16 > kSlotBytes) return pl;
+    if ((int)st.bytes16 * 16 > pl.stage_bytes) return pl;
   if ((int)pl.stages.size() > kMaxStagesSmem || (int)pl.stages.size() > kMaxStages || (int)pl.jobs.size() > kMaxJobs ||
       (int)pl.eparams_floats > kMaxEparams)
     return pl;
@@ -358,6 +417,13 @@ static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor
   pl.off_data = al(pl.off_eparams + pl.eparams_floats * sizeof(float));
   pl.total_bytes = al(pl.off_data + pl.data_bytes);
   pl.ok = true;
+  return pl;
+}
+
+// preferred variant first; shapes it does not cover fall back to the single-CTA kernel
+static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw) {
+  Plan pl = make_plan_mode(d, w, aw, tc_mode());
+  if (!pl.ok && tc_mode() != 1) pl = make_plan_mode(d, w, aw, 1);
   return pl;
 }
 
@@ -373,18 +439,17 @@ size_t tc_workspace_bytes(const Dims&) { return 1024 * sizeof(long long); }
 // --------------------------------------------------------------------------
 __global__ void pack_stage_kernel(const PackOp* __restrict__ ops, uint8_t* __restrict__ data) {
   const PackOp op = ops[blockIdx.x];
-  const int N = op.pad_a + op.pad_b;
+  int N = 0;
+  for (int q = 0; q < op.nseg; ++q) N += op.pad[q];
   const int total = op.nk8 * N;
   const int halfN = N / op.split;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int kc = i / N, n = i % N;
     const int di = (n / halfN) * (op.nk8 * halfN) + kc * halfN + (n % halfN);
-    int row = -1;
-    if (n < op.pad_a) {
-      if (n < op.valid_a) row = op.row0_a + n;
-    } else {
-      const int m = n - op.pad_a;
-      if (m < op.valid_b) row = op.row0_b + m;
+    int row = -1, m = n;
+    for (int q = 0; q < op.nseg; ++q) {
+      if (m < op.pad[q]) { if (m < op.valid[q]) row = op.row0[q] + m; break; }
+      m -= op.pad[q];
     }
     __align__(16) __nv_bfloat16 out[8];
 #pragma unroll
@@ -832,14 +897,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t ring = smem_base + p.ring_off;
   const uint32_t bars = smem_base + p.bar_off;
-  // barrier map (8 B each): full[0..8) | empty[8..16) | acc_full[16..18) | acc_empty[18..20) |
-  // peer_full[20..28) | tmem ptr @ +232
+  // barrier map (8 B each): full[16] @0 | empty[16] @128 | peer_full[16] @256 | acc_full[2] @384 |
+  // acc_empty[2] @400 | tmem ptr @416; the stage records follow at +kBarBytes
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };
-  auto accf_bar = [&](uint32_t j) { return bars + 128u + 8u * (j & 1u); };
-  auto acce_bar = [&](uint32_t j) { return bars + 144u + 8u * (j & 1u); };
-  auto peer_full_bar = [&](int s) { return bars + 160u + 8u * s; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 232);
+  auto empty_bar = [&](int s) { return bars + 128u + 8u * s; };
+  auto peer_full_bar = [&](int s) { return bars + 256u + 8u * s; };
+  auto accf_bar = [&](uint32_t j) { return bars + 384u + 8u * (j & 1u); };
+  auto acce_bar = [&](uint32_t j) { return bars + 400u + 8u * (j & 1u); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 416);
   // warp index broadcast through a shuffle: the compiler then treats it (and every epilogue
   // parameter address derived from it) as warp-uniform -> uniform-datapath constant loads
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -855,7 +920,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
   // Each 16-byte record is everything the MMA lane needs, precomputed here in parallel:
   //   x = A descriptor low word (address | LBO), y = instruction descriptor,
   //   z = B LBO field (rows per CTA) << 16 | nk16 << 8 | flags, w = tmem column | dep << 16
-  const uint4* stab = reinterpret_cast<const uint4*>(smem + p.bar_off + 256);
+  const uint4* stab = reinterpret_cast<const uint4*>(smem + p.bar_off + kBarBytes);
   for (int i = threadIdx.x; i < p.nstages; i += kThreads) {
     const uint4 raw = c_stages[i];
     const StageDesc st = *reinterpret_cast<const StageDesc*>(&raw);
@@ -864,7 +929,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
     rec.y = make_idesc_bf16(kTileM * kCta, st.n);
     rec.z = ((uint32_t)(st.n / kCta) << 16) | ((uint32_t)st.nk16 << 8) | st.flags;
     rec.w = (uint32_t)st.tmem_col | ((uint32_t)st.dep << 16);
-    reinterpret_cast<uint4*>(smem + p.bar_off + 256)[i] = rec;
+    reinterpret_cast<uint4*>(smem + p.bar_off + kBarBytes)[i] = rec;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nslots; ++s) {
@@ -1073,6 +1138,561 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_kernel(const TcParams 
   }
 }
 
+// ==========================================================================
+// Folded CTA-pair variant (mode 3): cta_group::2 with M=128, 64 batch rows per CTA.
+//
+// The D tile of such an MMA is folded over the TMEM lanes: lane r (0..63) holds accumulator columns
+// [0,N/2) of row r, lane 64+r holds columns [N/2,N) at the same TMEM column offsets (measured,
+// tools/micro/tmem_layout.cu).  So every batch row is served by TWO lane halves x kQ warps = 8 threads,
+// each accumulator group takes only N/2 TMEM columns, the A panels are [k/8][64 rows][8] (1 KB per
+// chunk, half the bytes), and the freed shared memory holds a 16-slot weight ring.
+// ==========================================================================
+constexpr uint32_t kPSF = 1024;   // bytes per 8-column chunk of a 64-row panel
+constexpr int kRowsF = 64;
+
+struct EpiCtxF {
+  const TcParams* p;
+  uint32_t smem_base, tmem_lane;
+  int row;        // row within this CTA's 64-row half tile
+  int hf;         // lane half: 0 -> accumulator columns [0,N/2), 1 -> [N/2,N)
+  int q;          // column-split index among the kQ warps of this lane quarter
+  int sidx;       // hf*kQ + q: index among the 8 threads that share a row
+  int quarter;
+  long long b;    // global row
+  bool valid;
+  int t;
+};
+__device__ __forceinline__ void rowpair_sync(int quarter) {
+  // the 2*kQ warps (two lane quarters) that share the same 32 batch rows
+  asm volatile("bar.sync %0, %1;" ::"r"((quarter & 1) + 1), "r"(2 * kQ * 32) : "memory");
+}
+
+__device__ __forceinline__ void epif_init(const EpiCtxF& c) {
+  const TcParams& p = *c.p;
+  const long long T1 = p.H + 1;
+  for (int k8 = c.sidx; k8 < p.Dp / 8; k8 += 2 * kQ) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = k8 * 8 + e;
+      v[e] = (c.valid && col < p.D) ? p.deter0[c.b * p.D + col] : 0.f;
+      if (c.valid && col < p.D) p.deter_seq[(c.b * T1) * p.D + col] = v[e];
+    }
+    st_chunk(c.smem_base + p.off_h + k8 * kPSF + c.row * 16, v);
+  }
+  for (int k8 = c.sidx; k8 < p.Sp / 8; k8 += 2 * kQ) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = k8 * 8 + e;
+      v[e] = (c.valid && col < p.S) ? p.stoch0[c.b * p.S + col] : 0.f;
+      if (c.valid && col < p.S) p.stoch_seq[(c.b * T1) * p.S + col] = v[e];
+    }
+    st_chunk(c.smem_base + p.off_s + k8 * kPSF + c.row * 16, v);
+  }
+}
+
+// Linear -> LayerNorm -> ELU.  MMA group mg (<= 256 features) sits in TMEM columns [mg*128, +Ng/2); this lane
+// half owns features mg*256 + hf*Ng/2 + [0, Ng/2).  32-column sub-groups are dealt round-robin to the kQ warps.
+__device__ __forceinline__ void epif_actor_ln(const EpiCtxF& c, const JobDesc& jb) {
+  const TcParams& p = *c.p;
+  const uint32_t bias = jb.p_off, gam = bias + p.Ha, bet = gam + p.Ha;
+  const int nmg = (p.Ha + 255) / 256;
+  float sum = 0.f, sq = 0.f;
+  int li = 0;
+  for (int mg = 0; mg < nmg; ++mg) {
+    const int hw = min(256, p.Ha - mg * 256) / 2;
+    for (int sub = 0; sub < hw / 32; ++sub, ++li) {
+      if ((li % kQ) != c.q) continue;
+      const int f0 = mg * 256 + c.hf * hw + sub * 32;
+      float v[32];
+      tmem_ld32(c.tmem_lane + jb.tmem_col + mg * 128 + sub * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b4 = ldc4(bias + f0 + i);
+        const float x0 = v[i] + b4.x, x1 = v[i + 1] + b4.y, x2 = v[i + 2] + b4.z, x3 = v[i + 3] + b4.w;
+        sum += (x0 + x1) + (x2 + x3);
+        sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+      }
+    }
+  }
+  // 8 partials per row (2 lane halves x kQ warps) exchanged through the head of the X panel, which is idle
+  // between this layer's MMAs (done) and its own pass-2 writes (after the second barrier)
+  const uint32_t scratch = c.smem_base + p.off_x;
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(scratch + (c.sidx * kRowsF + c.row) * 8), "f"(sum), "f"(sq)
+               : "memory");
+  rowpair_sync(c.quarter);
+  sum = 0.f; sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2 * kQ; ++k) {
+    float a, b;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "r"(scratch + (k * kRowsF + c.row) * 8) : "memory");
+    sum += a; sq += b;
+  }
+  // every epilogue thread of the CTA must have read its partials before anybody's pass 2 overwrites the
+  // scratch (it aliases the head of X, shared by both 32-row groups)
+  asm volatile("bar.sync 6, %0;" ::"r"(kEpiThreads) : "memory");
+  const float inv = 1.f / (float)p.Ha;
+  const float mean = sum * inv;
+  const float var = fmaxf(sq * inv - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float nmr = -mean * rstd;
+  li = 0;
+  for (int mg = 0; mg < nmg; ++mg) {
+    const int hw = min(256, p.Ha - mg * 256) / 2;
+    for (int sub = 0; sub < hw / 32; ++sub, ++li) {
+      if ((li % kQ) != c.q) continue;
+      const int f0 = mg * 256 + c.hf * hw + sub * 32;
+      float v[32];
+      tmem_ld32(c.tmem_lane + jb.tmem_col + mg * 128 + sub * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b4 = ldc4(bias + f0 + i);
+        const float4 g4 = ldc4(gam + f0 + i);
+        const float4 e4 = ldc4(bet + f0 + i);
+        v[i] = elu_scaled(fmaf(fmaf(v[i] + b4.x, rstd, nmr), g4.x, e4.x));
+        v[i + 1] = elu_scaled(fmaf(fmaf(v[i + 1] + b4.y, rstd, nmr), g4.y, e4.y));
+        v[i + 2] = elu_scaled(fmaf(fmaf(v[i + 2] + b4.z, rstd, nmr), g4.z, e4.z));
+        v[i + 3] = elu_scaled(fmaf(fmaf(v[i + 3] + b4.w, rstd, nmr), g4.w, e4.w));
+      }
+      const uint32_t dst = c.smem_base + jb.dst_off + (f0 / 8) * kPSF + c.row * 16;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st_chunk(dst + k * kPSF, v + k * 8);
+    }
+  }
+}
+
+// bias + ELU -> bf16 panel; 8-column sub-groups of this lane half's features, dealt to the kQ warps
+__device__ __forceinline__ void epif_dense_elu(const EpiCtxF& c, const JobDesc& jb) {
+  const uint32_t bias = jb.p_off;
+  const int nmg = (jb.n + 255) / 256;
+  int li = 0;
+  for (int mg = 0; mg < nmg; ++mg) {
+    const int hw = min(256, (int)jb.n - mg * 256) / 2;
+    for (int sub = 0; sub < hw / 8; ++sub, ++li) {
+      if ((li % kQ) != c.q) continue;
+      const int f0 = mg * 256 + c.hf * hw + sub * 8;
+      float v[8];
+      tmem_ld8(c.tmem_lane + jb.tmem_col + mg * 128 + sub * 8, v);
+      tmem_ld_wait();
+      const float4 b0 = ldc4(bias + f0), b1 = ldc4(bias + f0 + 4);
+      v[0] = elu_fast(v[0] + b0.x); v[1] = elu_fast(v[1] + b0.y); v[2] = elu_fast(v[2] + b0.z); v[3] = elu_fast(v[3] + b0.w);
+      v[4] = elu_fast(v[4] + b1.x); v[5] = elu_fast(v[5] + b1.y); v[6] = elu_fast(v[6] + b1.z); v[7] = elu_fast(v[7] + b1.w);
+      st_chunk(c.smem_base + jb.dst_off + (f0 / 8) * kPSF + c.row * 16, v);
+    }
+  }
+}
+
+// action head (N=16): lane half 0 holds actions 0..7, half 1 actions 8..15 (zero padding when A <= 8)
+__device__ __forceinline__ void epif_mu(const EpiCtxF& c, const JobDesc& jb) {
+  const TcParams& p = *c.p;
+  if (c.q != 0) return;
+  const uint32_t bias = jb.p_off + c.hf * 8, bound = jb.p_off + 16 + c.hf * 8;
+  float v[8];
+  tmem_ld8(c.tmem_lane + jb.tmem_col, v);
+  tmem_ld_wait();
+  const float4 b0 = ldc4(bias), b1 = ldc4(bias + 4), d0 = ldc4(bound), d1 = ldc4(bound + 4);
+  const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int a = c.hf * 8 + i;
+    v[i] = (a < p.A) ? tanh_fast((v[i] + bv[i]) * p.inv_action_scale) * dv[i] : 0.f;
+    if (c.valid && a < p.A) p.actions[(c.b * p.H + c.t) * p.A + a] = v[i];
+  }
+  st_chunk(c.smem_base + jb.dst_off + c.hf * kPSF + c.row * 16, v);
+}
+
+// GRU gates: this lane half owns state columns col0 + hf*cw/2 + [0, cw/2); per lane half the chunk's TMEM
+// is [r | z | i_n | h_n], cw/2 columns each.  8-column sub-groups dealt to the kQ warps.
+__device__ __forceinline__ void gruf_load_h(const EpiCtxF& c, const JobDesc& jb, int sub, float (&hp)[8]) {
+  const TcParams& p = *c.p;
+  const long long T1 = p.H + 1;
+  const float* hprev = p.deter_seq + (c.b * T1 + c.t) * p.D;
+  const int hw = jb.n / 2;
+  const int col = jb.col0 + c.hf * hw + sub * 8;
+  const bool in = c.valid && sub * 8 < hw;
+  if (in && col + 8 <= p.D && (p.D & 3) == 0) {
+    const float4 a = *reinterpret_cast<const float4*>(hprev + col);
+    const float4 b = *reinterpret_cast<const float4*>(hprev + col + 4);
+    hp[0] = a.x; hp[1] = a.y; hp[2] = a.z; hp[3] = a.w; hp[4] = b.x; hp[5] = b.y; hp[6] = b.z; hp[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hp[i] = (in && col + i < p.D) ? hprev[col + i] : 0.f;
+  }
+}
+constexpr int kGruSubsF = (kGruChunk / 2 / 8 + kQ - 1) / kQ;   // 8-column sub-groups per warp per chunk
+__device__ __forceinline__ void epif_gru(const EpiCtxF& c, const JobDesc& jb, uint32_t tmem, const float (&hp0)[8]) {
+  const TcParams& p = *c.p;
+  const int cw = jb.n, hw = cw / 2;
+  const uint32_t b_r = jb.p_off, b_z = b_r + p.Dp, b_in = b_z + p.Dp, b_hn = b_in + p.Dp;
+  const long long T1 = p.H + 1;
+  float* hnext = p.deter_seq + (c.b * T1 + c.t + 1) * p.D;
+  float hp[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) hp[i] = hp0[i];
+#pragma unroll
+  for (int k = 0; k < kGruSubsF; ++k) {
+    const int sub = c.q + k * kQ;
+    if (sub * 8 < hw) {
+      float hn_[8];
+      if (k + 1 < kGruSubsF) gruf_load_h(c, jb, sub + kQ, hn_);
+      const int col = jb.col0 + c.hf * hw + sub * 8;
+      float r[8], z[8], gi[8], gh[8];
+      tmem_ld8(tmem + sub * 8, r);
+      tmem_ld8(tmem + hw + sub * 8, z);
+      tmem_ld8(tmem + cw + sub * 8, gi);
+      tmem_ld8(tmem + cw + hw + sub * 8, gh);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; i += 4) {
+        const float4 br = ldc4(b_r + col + i), bz = ldc4(b_z + col + i);
+        const float4 bi = ldc4(b_in + col + i), bh = ldc4(b_hn + col + i);
+        const float brv[4] = {br.x, br.y, br.z, br.w}, bzv[4] = {bz.x, bz.y, bz.z, bz.w};
+        const float biv[4] = {bi.x, bi.y, bi.z, bi.w}, bhv[4] = {bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float rr = sigmoid_fast(r[i + e] + brv[e]);
+          const float zz = sigmoid_fast(z[i + e] + bzv[e]);
+          const float nn = tanh_fast(gi[i + e] + biv[e] + rr * (gh[i + e] + bhv[e]));
+          r[i + e] = fmaf(zz, hp[i + e] - nn, nn);
+        }
+      }
+      if (c.valid) {
+        if (col + 8 <= p.D && (p.D & 3) == 0) {
+          *reinterpret_cast<float4*>(hnext + col) = make_float4(r[0], r[1], r[2], r[3]);
+          *reinterpret_cast<float4*>(hnext + col + 4) = make_float4(r[4], r[5], r[6], r[7]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (col + i < p.D) hnext[col + i] = r[i];
+        }
+      }
+      st_chunk(c.smem_base + jb.dst_off + (col / 8) * kPSF + c.row * 16, r);
+      if (k + 1 < kGruSubsF) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hp[i] = hn_[i];
+      }
+    }
+  }
+}
+
+// Gaussian head: this lane half owns latent columns hf*Sp/2 + [0, Sp/2); TMEM per lane half [mean | raw]
+__device__ __forceinline__ void epsf_prefetch(const EpiCtxF& c, float (&e)[8]) {
+  const TcParams& p = *c.p;
+  const float* eps = p.noise + ((long long)c.t * p.B + c.b) * p.S;
+  const int col = c.hf * (p.Sp / 2) + c.q * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) e[i] = (c.valid && c.q * 8 < p.Sp / 2 && col + i < p.S) ? eps[col + i] : 0.f;
+}
+__device__ __forceinline__ void epif_prior2(const EpiCtxF& c, const JobDesc& jb, const float (&e0)[8]) {
+  const TcParams& p = *c.p;
+  const uint32_t b_m = jb.p_off, b_s = b_m + p.Sp;
+  const long long T1 = p.H + 1;
+  const long long o = (c.b * T1 + c.t + 1) * p.S;
+  const float* eps = p.noise + ((long long)c.t * p.B + c.b) * p.S;
+  const int hw = p.Sp / 2;
+  for (int sub = c.q; sub * 8 < hw; sub += kQ) {
+    const int col = c.hf * hw + sub * 8;
+    float m[8], s[8], sd[8], st[8];
+    tmem_ld8(c.tmem_lane + jb.tmem_col + sub * 8, m);
+    tmem_ld8(c.tmem_lane + jb.tmem_col + hw + sub * 8, s);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; i += 4) {
+      const float4 bm = ldc4(b_m + col + i), bs = ldc4(b_s + col + i);
+      const float bmv[4] = {bm.x, bm.y, bm.z, bm.w}, bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float mean = m[i + e] + bmv[e];
+        const float raw = s[i + e] + bsv[e];
+        const float sp = fmaxf(raw, 0.f) + __logf(1.f + ex2_fast(-fabsf(raw) * 1.4426950408889634f));
+        const float ee = (sub == c.q) ? e0[i + e] : ((c.valid && col + i + e < p.S) ? eps[col + i + e] : 0.f);
+        m[i + e] = mean;
+        sd[i + e] = sp + 0.1f;
+        st[i + e] = (col + i + e < p.S) ? fmaf(sd[i + e], ee, mean) : 0.f;
+      }
+    }
+    if (p.stage_out) {
+      const uint32_t rowb = c.smem_base + p.off_x + (uint32_t)c.row * (uint32_t)p.Sp * 4u;
+      const uint32_t fstride = (uint32_t)kRowsF * (uint32_t)p.Sp * 4u;
+      const int g = col / 8;
+      const uint32_t c0 = (uint32_t)((2 * g) ^ (c.row & 7)) * 16u, c1 = (uint32_t)((2 * g + 1) ^ (c.row & 7)) * 16u;
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + c0), "f"(m[0]), "f"(m[1]), "f"(m[2]), "f"(m[3]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + c1), "f"(m[4]), "f"(m[5]), "f"(m[6]), "f"(m[7]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + fstride + c0), "f"(sd[0]), "f"(sd[1]), "f"(sd[2]), "f"(sd[3]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + fstride + c1), "f"(sd[4]), "f"(sd[5]), "f"(sd[6]), "f"(sd[7]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + 2 * fstride + c0), "f"(st[0]), "f"(st[1]), "f"(st[2]), "f"(st[3]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowb + 2 * fstride + c1), "f"(st[4]), "f"(st[5]), "f"(st[6]), "f"(st[7]) : "memory");
+    } else if (c.valid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col + i < p.S) {
+          p.mean_seq[o + col + i] = m[i];
+          p.std_seq[o + col + i] = sd[i];
+          p.stoch_seq[o + col + i] = st[i];
+        }
+    }
+    st_chunk(c.smem_base + jb.dst_off + (col / 8) * kPSF + c.row * 16, st);
+  }
+  // h' (X[h2..]) -> P_h
+  for (int k8 = c.sidx; k8 < p.Dp / 8; k8 += 2 * kQ) {
+    uint32_t a, b, cc, d;
+    const uint32_t src = c.smem_base + p.off_h2 + k8 * kPSF + c.row * 16;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(cc), "=r"(d) : "r"(src) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(c.smem_base + p.off_h + k8 * kPSF + c.row * 16),
+                 "r"(a), "r"(b), "r"(cc), "r"(d)
+                 : "memory");
+  }
+  if (p.stage_out) {
+    asm volatile("bar.sync 5, %0;" ::"r"(kEpiThreads) : "memory");
+    const int warp = c.q * 4 + c.quarter;
+    const int lane = c.row & 31;
+    const long long tile_b0 = c.b - c.row;
+    const uint32_t fstride = (uint32_t)kRowsF * (uint32_t)p.Sp * 4u;
+    const uint32_t xbase = c.smem_base + p.off_x;
+    for (int row = warp; row < kRowsF; row += kEpiThreads / 32) {
+      const long long bb = tile_b0 + row;
+      if (bb >= p.B) break;
+      const long long off = (bb * T1 + c.t + 1) * p.S;
+      const uint32_t rb = xbase + (uint32_t)row * (uint32_t)p.Sp * 4u;
+      for (int col = lane; col < p.S; col += 32) {
+        const uint32_t a0 = rb + (uint32_t)(((col >> 2) ^ (row & 7)) * 16 + (col & 3) * 4);
+        float v0, v1, v2;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(a0));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(a0 + fstride));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v2) : "r"(a0 + 2 * fstride));
+        p.mean_seq[off + col] = v0;
+        p.std_seq[off + col] = v1;
+        p.stoch_seq[off + col] = v2;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t kSlot = p.slot_bytes;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring = smem_base + p.ring_off;
+  const uint32_t bars = smem_base + p.bar_off;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 128u + 8u * s; };
+  auto peer_full_bar = [&](int s) { return bars + 256u + 8u * s; };
+  auto accf_bar = [&](uint32_t j) { return bars + 384u + 8u * (j & 1u); };
+  auto acce_bar = [&](uint32_t j) { return bars + 400u + 8u * (j & 1u); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 416);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int unit = (int)(blockIdx.x >> 1), nunits = (int)(gridDim.x >> 1);
+  const int ngroups = p.ntiles;   // one group = one 128-row tile = 2 x 64 rows
+
+  // per-stage MMA records (see the non-folded kernel); A panels have 64 rows -> LBO = 1024 B
+  const uint4* stab = reinterpret_cast<const uint4*>(smem + p.bar_off + kBarBytes);
+  for (int i = threadIdx.x; i < p.nstages; i += kThreads) {
+    const uint4 raw = c_stages[i];
+    const StageDesc st = *reinterpret_cast<const StageDesc*>(&raw);
+    uint4 rec;
+    rec.x = (uint32_t)make_smem_desc(smem_base + (uint32_t)st.a_off16 * 16u, kPSF, 128u);
+    rec.y = make_idesc_bf16(128, st.n);
+    rec.z = ((uint32_t)(st.n / 2) << 16) | ((uint32_t)st.nk16 << 8) | st.flags;
+    rec.w = (uint32_t)st.tmem_col | ((uint32_t)st.dep << 16);
+    reinterpret_cast<uint4*>(smem + p.bar_off + kBarBytes)[i] = rec;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nslots; ++s) {
+      // leader: a stage is "full" when its own half has landed (producer arrive + tx bytes) AND the peer
+      // has forwarded that its half landed -> two arrivals on ONE barrier, one wait per stage
+      mbar_init(full_bar(s), rank == 0 ? 2 : 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(peer_full_bar(s), 1);
+    }
+    for (uint32_t j = 0; j < 2; ++j) {
+      mbar_init(accf_bar(j), 1);
+      mbar_init(acce_bar(j), (kEpiThreads / 32) * 2);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) { tmem_alloc2(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512); tmem_relinquish2(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int grp = unit; grp < ngroups; grp += nunits)
+        for (int t = 0; t < p.H; ++t)
+          for (int s = 0; s < p.nstages; ++s) {
+            const uint4 raw = c_stages[s];
+            const uint32_t bytes = ((raw.y & 0xFFFFu) * 16u) / 2u;
+            mbar_wait(empty_bar(slot), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(slot), bytes);
+            bulk_g2s(ring + slot * kSlot, p.stage_data + (size_t)raw.x * 16u + (size_t)rank * bytes, bytes,
+                     full_bar(slot));
+            if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+          }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0 && rank != 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int grp = unit; grp < ngroups; grp += nunits)
+        for (int t = 0; t < p.H; ++t)
+          for (int s = 0; s < p.nstages; ++s) {
+            mbar_wait(full_bar(slot), phase);
+            mbar_arrive_remote(mapa(full_bar(slot), 0));
+            if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+          }
+    } else if (lane == 0) {
+      uint32_t slot = 0, phase = 0, job = 0;
+      for (int grp = unit; grp < ngroups; grp += nunits) {
+        mbar_arrive(accf_bar(job));
+        mbar_arrive_remote(mapa(accf_bar(job), 1));
+        ++job;
+        const bool tr = p.trace && blockIdx.x == 0 && grp == unit;
+        for (int t = 0; t < p.H; ++t) {
+          int jidx = -1;
+          long long s_full = 0, s_peer = 0, s_issue = 0, s_commit = 0, s_n = 0;
+          for (int s = 0; s < p.nstages; ++s) {
+            const uint4 rec = stab[s];
+            const uint32_t flags = rec.z & 0xFFu;
+            if (flags & ST_FIRST_OF_JOB) ++jidx;
+            if (flags & ST_FIRST_OF_JOB) {
+              const uint32_t dep = rec.w >> 16;
+              if (dep) {
+                const uint32_t dj = job - dep;
+                mbar_wait(acce_bar(dj), (dj >> 1) & 1u);
+              }
+            }
+            const bool trw = tr && t == 1 && jidx == 1;     // actor1's stages
+            const long long w0 = trw ? clock64() : 0;
+            mbar_wait(full_bar(slot), phase);
+            const long long w1 = trw ? clock64() : 0;
+            tc_fence_after();
+            const long long w2 = trw ? clock64() : 0;
+            if (tr && (flags & ST_FIRST_OF_JOB) && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 0] = clock64();
+            const uint32_t tm = tmem_base + (rec.w & 0xFFFFu) + ((flags & ST_DBUF) ? (job & 1u) * 256u : 0u);
+            const uint32_t idesc = rec.y;
+            const uint32_t nh = rec.z >> 16;
+            uint32_t alo = rec.x;
+            uint32_t blo = (((ring + slot * kSlot) >> 4) & 0x3FFFu) | (nh << 16);
+            const uint32_t bstep = nh * 2u;
+            constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+            uint32_t acc = (flags & ST_FIRST_ACC) ? 0u : 1u;
+            const uint32_t nk = (rec.z >> 8) & 0xFFu;
+            constexpr uint32_t kAStep = (2u * kPSF) >> 4;
+            uint32_t i = 0;
+            for (; i + 4 <= nk; i += 4) {       // 4 MMAs per trip: the lane must stay ahead of a 64-cycle MMA
+              mma_bf16_lohi2(tm, alo, kDescHi, blo, kDescHi, idesc, acc);
+              mma_bf16_lohi2(tm, alo + kAStep, kDescHi, blo + bstep, kDescHi, idesc, 1u);
+              mma_bf16_lohi2(tm, alo + 2 * kAStep, kDescHi, blo + 2 * bstep, kDescHi, idesc, 1u);
+              mma_bf16_lohi2(tm, alo + 3 * kAStep, kDescHi, blo + 3 * bstep, kDescHi, idesc, 1u);
+              alo += 4 * kAStep;
+              blo += 4 * bstep;
+              acc = 1u;
+            }
+            for (; i < nk; ++i) {
+              mma_bf16_lohi2(tm, alo, kDescHi, blo, kDescHi, idesc, acc);
+              alo += kAStep;
+              blo += bstep;
+              acc = 1u;
+            }
+            const long long w3 = trw ? clock64() : 0;
+            tc_commit2(empty_bar(slot), 3);
+            if (trw) {
+              const long long w4 = clock64();
+              s_full += w1 - w0; s_peer += w2 - w1; s_issue += w3 - w2; s_commit += w4 - w3; s_n += 1;
+            }
+            if (flags & ST_LAST_OF_JOB) {
+              tc_commit2(accf_bar(job), 3);
+              if (tr && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 1] = clock64();
+              ++job;
+            }
+            if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+          }
+          if (tr && t == 1) {
+            p.trace[720] = s_full; p.trace[721] = s_peer; p.trace[722] = s_issue; p.trace[723] = s_commit; p.trace[724] = s_n;
+          }
+        }
+      }
+    }
+  } else {
+    EpiCtxF c;
+    c.p = &p;
+    c.smem_base = smem_base;
+    c.quarter = warp & 3;
+    c.hf = c.quarter >> 1;
+    c.q = warp >> 2;
+    c.sidx = c.hf * kQ + c.q;
+    c.row = (c.quarter & 1) * 32 + lane;
+    c.tmem_lane = tmem_base + ((uint32_t)(c.quarter * 32) << 16);
+    uint32_t job = 0;
+#define WMRL_JOB_DONE_F(job)                                                            \
+  do {                                                                                  \
+    __syncwarp();                                                                       \
+    if (lane == 0) {                                                                    \
+      if (rank != 0) mbar_arrive_remote(mapa(acce_bar(job), 0));                        \
+      else mbar_arrive(acce_bar(job));                                                  \
+    }                                                                                   \
+  } while (0)
+    for (int grp = unit; grp < ngroups; grp += nunits) {
+      c.b = (long long)grp * kTileM + (long long)rank * kRowsF + c.row;
+      c.valid = c.b < p.B;
+      c.t = 0;
+      mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
+      epif_init(c);
+      fence_proxy_async_smem();
+      WMRL_JOB_DONE_F(job);
+      ++job;
+      const bool tr = p.trace && blockIdx.x == 0 && grp == unit && threadIdx.x == 0;
+      for (int t = 0; t < p.H; ++t) {
+        c.t = t;
+        for (int jb_i = 0; jb_i < p.njobs; ++jb_i) {
+          const JobDesc jb = c_jobs[jb_i];
+          long long t_wake = 0;
+          if (jb.type == JOB_GRU) {
+            float hp[8];
+            gruf_load_h(c, jb, c.q, hp);
+            mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
+            tc_fence_after();
+            if (tr) t_wake = clock64();
+            epif_gru(c, jb, c.tmem_lane + (jb.dbuf ? (job & 1u) * 256u : 0u), hp);
+          } else if (jb.type == JOB_PRIOR2_CONT) {
+            float e0[8];
+            epsf_prefetch(c, e0);
+            mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
+            tc_fence_after();
+            if (tr) t_wake = clock64();
+            epif_prior2(c, jb, e0);
+          } else {
+            mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
+            tc_fence_after();
+            if (tr) t_wake = clock64();
+            if (jb.type == JOB_ACTOR_LN) epif_actor_ln(c, jb);
+            else if (jb.type == JOB_DENSE_ELU) epif_dense_elu(c, jb);
+            else if (jb.type == JOB_MU) epif_mu(c, jb);
+          }
+          tc_fence_before();
+          fence_proxy_async_smem();
+          if (tr && t < 4) {
+            p.trace[((t * p.njobs) + jb_i) * 4 + 2] = t_wake;
+            p.trace[((t * p.njobs) + jb_i) * 4 + 3] = clock64();
+          }
+          WMRL_JOB_DONE_F(job);
+          ++job;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == kMmaWarp) tmem_dealloc2(tmem_base, 512);
+}
+
 int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
                    const void* packed, const float* deter0, const float* stoch0,
                    const float* noise, float* deter_seq, float* stoch_seq, float* dist_a,
@@ -1095,10 +1715,14 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
   p.inv_action_scale = 1.f / d.action_scale;
   p.off_h = pl.off_h; p.off_s = pl.off_s; p.off_a = pl.off_a; p.off_x = pl.off_x; p.off_h2 = pl.off_h2;
   p.ring_off = pl.ring_off; p.bar_off = pl.bar_off; p.nslots = pl.nslots;
+  p.slot_bytes = (uint32_t)(pl.stage_bytes / pl.cta);
   p.ntiles = (d.B + kTileM - 1) / kTileM;
   p.trace = (d.flags & 4) ? (long long*)ws : nullptr;
   // swizzle needs >= 8 16-byte chunks per row (Sp >= 32) and the staging must fit below the h' columns
-  p.stage_out = (pl.Sp >= 32 && pl.Sp % 32 == 0 && 3u * kTileM * pl.Sp * 4u <= (uint32_t)pl.h2c * 256u) ? 1 : 0;
+  {
+    const uint32_t rows = pl.fold ? 64u : 128u;
+    p.stage_out = (pl.Sp >= 32 && pl.Sp % 32 == 0 && 3u * rows * pl.Sp * 4u <= (uint32_t)pl.h2c * 2u * rows) ? 1 : 0;
+  }
   // tables + epilogue parameters -> constant memory (device-to-device from the packed image,
   // stream-ordered before the launch; skipped when this image is already resident)
   if (g_const_src != packed || g_const_gen != pack_generation(packed)) {
@@ -1127,12 +1751,14 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
                                       (int)pl.smem_bytes));
     WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem_bytes));
+    WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)pl.smem_bytes));
     s_smem[dev] = pl.smem_bytes;
   }
   const int sms = s_sms[dev];
   if (pl.cta == 2) {
-    // CTA pairs: one cluster of 2 per pair of 128-row tiles, at most one pair per two SMs
-    const int pairs = std::min((p.ntiles + 1) / 2, sms / 2);
+    // CTA pairs: one cluster of 2 per pair of 128-row tiles (mode 2) / per 128-row tile (mode 3, folded)
+    const int pairs = std::min(pl.fold ? p.ntiles : (p.ntiles + 1) / 2, sms / 2);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(kThreads);
@@ -1143,7 +1769,8 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if (p.trace) WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_kernel<2, true>, p));
+    if (pl.fold) WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_fold_kernel, p));
+    else if (p.trace) WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_kernel<2, true>, p));
     else WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_kernel<2, false>, p));
   } else {
     const int grid = std::min(p.ntiles, sms);
