@@ -110,10 +110,10 @@ def test_bf16_with_grad_uses_recording_path():
     assert actor.mu.weight.grad is not None and torch.isfinite(actor.mu.weight.grad).all()
 
 
-@pytest.mark.parametrize("mode", ["1", "2", "3"])
+@pytest.mark.parametrize("mode", ["1", "2", "3", "4"])
 def test_bf16_kernel_variants(mode):
     """every tcgen05 kernel variant stays parity-green: 1 = single CTA, 2 = CTA pair (cta_group::2, M=256),
-    3 = folded CTA pair (cta_group::2, M=128, 64 rows per CTA).  WMRL_TC_MODE is read once per process, so
+    3 = folded CTA pair (cta_group::2, M=128, 64 rows per CTA), 4 = folded pair with two-tile ping-pong.  WMRL_TC_MODE is read once per process, so
     each variant runs in a subprocess."""
     import os, subprocess, sys
     if not torch.cuda.is_available():

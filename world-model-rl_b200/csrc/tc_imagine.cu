@@ -111,6 +111,7 @@ struct TcParams {
   uint32_t ring_off, bar_off;
   int nslots, ntiles;
   uint32_t slot_bytes;   // ring slot size per CTA
+  uint32_t panel_bytes;  // bytes of one tile's A panels (ping-pong: tile 1 sits at +panel_bytes)
   int stage_out;      // 1: the Gaussian head stages its fp32 rows in the idle X panel and stores coalesced
   long long* trace;   // optional timeline (WMRL_FLAG_TRACE): [step][job][4] SM clocks of CTA 0's first tile
 };
@@ -123,11 +124,13 @@ static inline int ceil16(int x) { return (x + 15) / 16 * 16; }
 //   3 = CTA pairs, 2 x 64 rows ("folded": cta_group::2, M=128; each CTA's 64 rows use all 128 TMEM lanes,
 //       lanes 0-63 hold accumulator columns [0,N/2), lanes 64-127 columns [N/2,N); half-size panels leave room
 //       for a 16-slot weight ring)
+//   4 = mode 3 + two-tile ping-pong: every CTA holds TWO 64-row tiles (2 x 96 KB of panels, one 256-column
+//       TMEM half each) and alternates tiles job by job, so one tile's epilogue overlaps the other's MMAs
 static int tc_mode() {
   static int mode = 0;
   if (mode == 0) {
     const char* e = getenv("WMRL_TC_MODE");
-    mode = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : kDefaultTcMode;
+    mode = (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : kDefaultTcMode;
   }
   return mode;
 }
@@ -146,6 +149,7 @@ __constant__ __align__(16) float c_eparams[kMaxEparams];
 struct Plan {
   int cta = 1;          // CTAs per group (1 or 2)
   bool fold = false;    // 64 rows per CTA, accumulator columns folded over the two TMEM lane halves
+  bool pp = false;      // two tiles per CTA in ping-pong (folded mode only)
   uint32_t ps = 2048;   // bytes between the 8-column chunks of an A panel (rows per CTA * 16)
   int stage_bytes = kSlotBytes;   // max bytes of one weight stage (all CTAs of the group together)
   int Dp, Sp, Ap, Ha, Hdp, h2c, XW;
@@ -232,11 +236,12 @@ static uint32_t add_vec(Plan& pl, const float* s1, const float* s2, int off, int
 static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw, int mode) {
   Plan pl;
   pl.cta = mode >= 2 ? 2 : 1;
-  pl.fold = mode == 3;
+  pl.fold = mode >= 3;
+  pl.pp = mode == 4;
   pl.ps = pl.fold ? 1024u : 2048u;
   // folded pairs have ~128 KB of ring per CTA: 64 KB stages (32 KB per CTA, 4 slots) cut the number of
   // stages - and with it the per-stage handshakes of the pair protocol - by ~3.5x
-  pl.stage_bytes = pl.fold ? 65536 : kSlotBytes;
+  pl.stage_bytes = pl.pp ? 32768 : (pl.fold ? 65536 : kSlotBytes);
   if (d.variant != WMRL_CONTINUOUS) return pl;
   if (d.Ha % 32 != 0 || d.Ha > 512 || d.A > 16 || d.S > 8 * kQ * kP2Groups || d.La < 1) return pl;
   if (pl.fold && (d.Ha % 64 != 0 || d.A > 8)) return pl;
@@ -251,8 +256,9 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
   pl.off_x = pl.off_a + pl.Ap / 8 * PS;
   pl.off_h2 = pl.off_x + pl.h2c / 8 * PS;
   pl.panels_bytes = pl.off_x + pl.XW / 8 * PS;
-  pl.ring_off = pl.panels_bytes;
-  const int avail = kMaxSmem - (int)pl.panels_bytes - kBarBytes - kMaxStagesSmem * 16;
+  const int ntl = pl.pp ? 2 : 1;   // tiles resident per CTA
+  pl.ring_off = ntl * pl.panels_bytes;
+  const int avail = kMaxSmem - ntl * (int)pl.panels_bytes - kBarBytes - kMaxStagesSmem * 16;
   const int slot_bytes = pl.stage_bytes / pl.cta;   // a CTA of a pair stores half of every stage
   pl.nslots = avail / slot_bytes;
   if (pl.nslots < 2) return pl;
@@ -338,7 +344,7 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
       const int cw = gcount * 16;
       const int valid = std::max(0, std::min(cw, d.D - col0));
       JobDesc jb{};
-      jb.type = JOB_GRU; jb.dbuf = pl.fold ? 1 : 0; jb.n = (uint16_t)cw; jb.tmem_col = 0; jb.col0 = (uint16_t)col0;
+      jb.type = JOB_GRU; jb.dbuf = (pl.fold && !pl.pp) ? 1 : 0; jb.n = (uint16_t)cw; jb.tmem_col = 0; jb.col0 = (uint16_t)col0;
       jb.dst_off = pl.off_h2; jb.p_off = pb;
       pl.jobs.push_back(jb);
       const float* wih = w ? w->w_ih : nul;
@@ -353,12 +359,14 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
         rz.add(d.D + col0, d.D - col0, hw);
         rz.add(col0 + hw, d.D - col0 - hw, hw);
         rz.add(d.D + col0 + hw, d.D - col0 - hw, hw);
-        const int dep = (c < 2) ? (c + 1) : 2;   // chunk 0/1 wait for the embed epilogue, later ones for chunk c-2
-        add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}, {pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 0, true,
+        // ping-pong mode gives each tile one 256-column TMEM half: chunks are single-buffered there
+        const bool db = !pl.pp;
+        const int dep = db ? ((c < 2) ? (c + 1) : 2) : 1;   // double-buffered: chunk c waits for chunk c-2's epilogue
+        add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}, {pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 0, db,
                       true, dep, false);
         RowSpec rn(2 * d.D + col0, valid, cw);
-        add_acc_group(pl, rn, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, cw, true, false, 0, false);
-        add_acc_group(pl, rn, {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, cw + hw, true, false, 0, true);
+        add_acc_group(pl, rn, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, cw, db, false, 0, false);
+        add_acc_group(pl, rn, {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, cw + hw, db, false, 0, true);
       } else {
         RowSpec rz{col0, valid, cw, d.D + col0, valid, cw};
         add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}, {pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 0, false,
@@ -1693,6 +1701,237 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcPa
   if (warp == kMmaWarp) tmem_dealloc2(tmem_base, 512);
 }
 
+// ==========================================================================
+// Mode 4: folded CTA pairs with a two-tile ping-pong.  Same epilogues as mode 3; the three role loops walk
+// the events (step, job, tile) in the order ... (j,A) (j,B) (j+1,A) (j+1,B) ...  While the epilogue warps work
+// on (j,A) the MMA lane issues (j,B); (j+1,A) only needs epilogue (j,A).  Tile T owns the A panels at
+// T*panel_bytes, TMEM columns [256*T, +256) and its own accumulator barriers.
+// ==========================================================================
+__global__ void __launch_bounds__(kThreads, 1) tc_imagine_pp_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t kSlot = p.slot_bytes;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring = smem_base + p.ring_off;
+  const uint32_t bars = smem_base + p.bar_off;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 128u + 8u * s; };
+  auto accf_bar = [&](int tile, uint32_t j) { return bars + 384u + 16u * tile + 8u * (j & 1u); };
+  auto acce_bar = [&](int tile, uint32_t j) { return bars + 416u + 16u * tile + 8u * (j & 1u); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 448);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int unit = (int)(blockIdx.x >> 1), nunits = (int)(gridDim.x >> 1);
+  const int ngroups = p.ntiles;   // one group = one 128-row tile = 2 x 64 rows
+  const int niter = (ngroups > unit) ? ((ngroups - unit + nunits - 1) / nunits + 1) / 2 : 0;   // two groups per trip
+
+  const uint4* stab = reinterpret_cast<const uint4*>(smem + p.bar_off + kBarBytes);
+  for (int i = threadIdx.x; i < p.nstages; i += kThreads) {
+    const uint4 raw = c_stages[i];
+    const StageDesc st = *reinterpret_cast<const StageDesc*>(&raw);
+    uint4 rec;
+    rec.x = (uint32_t)make_smem_desc(smem_base + (uint32_t)st.a_off16 * 16u, kPSF, 128u);
+    rec.y = make_idesc_bf16(128, st.n);
+    rec.z = ((uint32_t)(st.n / 2) << 16) | ((uint32_t)st.nk16 << 8) | st.flags;
+    rec.w = (uint32_t)st.tmem_col | ((uint32_t)st.dep << 16);
+    reinterpret_cast<uint4*>(smem + p.bar_off + kBarBytes)[i] = rec;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nslots; ++s) {
+      mbar_init(full_bar(s), rank == 0 ? 2 : 1);   // own half (arrive + tx) and the peer's forwarded arrival
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int tile = 0; tile < 2; ++tile)
+      for (uint32_t j = 0; j < 2; ++j) {
+        mbar_init(accf_bar(tile, j), 1);
+        mbar_init(acce_bar(tile, j), (kEpiThreads / 32) * 2);
+      }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) { tmem_alloc2(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512); tmem_relinquish2(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    // weight stages of a job are streamed twice in a row: once for tile A's MMAs, once for tile B's
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int it = 0; it < niter; ++it)
+        for (int t = 0; t < p.H; ++t)
+          for (int s0 = 0; s0 < p.nstages;) {
+            int s_end = s0;
+            for (int tile = 0; tile < 2; ++tile) {
+              int s = s0;
+              bool last;
+              do {
+                const uint4 raw = c_stages[s];
+                const uint32_t bytes = ((raw.y & 0xFFFFu) * 16u) / 2u;
+                last = ((raw.y >> 24) & ST_LAST_OF_JOB) != 0;
+                mbar_wait(empty_bar(slot), phase ^ 1u);
+                mbar_arrive_expect_tx(full_bar(slot), bytes);
+                bulk_g2s(ring + slot * kSlot, p.stage_data + (size_t)raw.x * 16u + (size_t)rank * bytes, bytes,
+                         full_bar(slot));
+                if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+                ++s;
+              } while (!last);
+              s_end = s;
+            }
+            s0 = s_end;
+          }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0 && rank != 0) {
+      // peer: forward "my half landed", once per stage instance (2 x nstages per step)
+      uint32_t slot = 0, phase = 0;
+      for (int it = 0; it < niter; ++it)
+        for (int t = 0; t < p.H; ++t)
+          for (int s = 0; s < 2 * p.nstages; ++s) {
+            mbar_wait(full_bar(slot), phase);
+            mbar_arrive_remote(mapa(full_bar(slot), 0));
+            if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+          }
+    } else if (lane == 0) {
+      uint32_t slot = 0, phase = 0, job = 0;
+      const uint32_t tile_a16 = p.panel_bytes >> 4;
+      for (int it = 0; it < niter; ++it) {
+        for (int tile = 0; tile < 2; ++tile) {   // INIT jobs have no MMA
+          mbar_arrive(accf_bar(tile, job));
+          mbar_arrive_remote(mapa(accf_bar(tile, job), 1));
+        }
+        ++job;
+        for (int t = 0; t < p.H; ++t)
+          for (int s0 = 0; s0 < p.nstages;) {
+            int s_end = s0;
+            for (int tile = 0; tile < 2; ++tile) {
+              int s = s0;
+              uint32_t flags;
+              do {
+                const uint4 rec = stab[s];
+                flags = rec.z & 0xFFu;
+                if (flags & ST_FIRST_OF_JOB) {
+                  const uint32_t dep = rec.w >> 16;
+                  if (dep) {
+                    const uint32_t dj = job - dep;
+                    mbar_wait(acce_bar(tile, dj), (dj >> 1) & 1u);
+                  }
+                }
+                mbar_wait(full_bar(slot), phase);
+                tc_fence_after();
+                const uint32_t tm = tmem_base + (uint32_t)tile * 256u + (rec.w & 0xFFFFu);
+                const uint32_t idesc = rec.y;
+                const uint32_t nh = rec.z >> 16;
+                uint32_t alo = rec.x + (uint32_t)tile * tile_a16;
+                uint32_t blo = (((ring + slot * kSlot) >> 4) & 0x3FFFu) | (nh << 16);
+                const uint32_t bstep = nh * 2u;
+                constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+                constexpr uint32_t kAStep = (2u * kPSF) >> 4;
+                uint32_t acc = (flags & ST_FIRST_ACC) ? 0u : 1u;
+                const uint32_t nk = (rec.z >> 8) & 0xFFu;
+                uint32_t i = 0;
+                for (; i + 4 <= nk; i += 4) {
+                  mma_bf16_lohi2(tm, alo, kDescHi, blo, kDescHi, idesc, acc);
+                  mma_bf16_lohi2(tm, alo + kAStep, kDescHi, blo + bstep, kDescHi, idesc, 1u);
+                  mma_bf16_lohi2(tm, alo + 2 * kAStep, kDescHi, blo + 2 * bstep, kDescHi, idesc, 1u);
+                  mma_bf16_lohi2(tm, alo + 3 * kAStep, kDescHi, blo + 3 * bstep, kDescHi, idesc, 1u);
+                  alo += 4 * kAStep;
+                  blo += 4 * bstep;
+                  acc = 1u;
+                }
+                for (; i < nk; ++i) {
+                  mma_bf16_lohi2(tm, alo, kDescHi, blo, kDescHi, idesc, acc);
+                  alo += kAStep;
+                  blo += bstep;
+                  acc = 1u;
+                }
+                tc_commit2(empty_bar(slot), 3);
+                if (flags & ST_LAST_OF_JOB) tc_commit2(accf_bar(tile, job), 3);
+                if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+                ++s;
+              } while (!(flags & ST_LAST_OF_JOB));
+              s_end = s;
+            }
+            s0 = s_end;
+            ++job;
+          }
+      }
+    }
+  } else {
+    EpiCtxF c;
+    c.p = &p;
+    c.quarter = warp & 3;
+    c.hf = c.quarter >> 1;
+    c.q = warp >> 2;
+    c.sidx = c.hf * kQ + c.q;
+    c.row = (c.quarter & 1) * 32 + lane;
+    uint32_t job = 0;
+#define WMRL_JOB_DONE_P(tile, job)                                                      \
+  do {                                                                                  \
+    __syncwarp();                                                                       \
+    if (lane == 0) {                                                                    \
+      if (rank != 0) mbar_arrive_remote(mapa(acce_bar(tile, job), 0));                  \
+      else mbar_arrive(acce_bar(tile, job));                                            \
+    }                                                                                   \
+  } while (0)
+    // per-tile context (recomputed, never indexed arrays: local memory is an L2 round trip here)
+#define WMRL_SET_TILE(tile)                                                                       \
+  do {                                                                                            \
+    const int grp_ = unit + (2 * it + (tile)) * nunits;                                           \
+    c.smem_base = smem_base + (uint32_t)(tile) * p.panel_bytes;                                   \
+    c.tmem_lane = tmem_base + (uint32_t)(tile) * 256u + ((uint32_t)(c.quarter * 32) << 16);       \
+    c.b = (long long)grp_ * kTileM + (long long)rank * kRowsF + c.row;                            \
+    c.valid = grp_ < ngroups && c.b < p.B;                                                        \
+  } while (0)
+    for (int it = 0; it < niter; ++it) {
+      for (int tile = 0; tile < 2; ++tile) {
+        WMRL_SET_TILE(tile);
+        c.t = 0;
+        mbar_wait_backoff(accf_bar(tile, job), (job >> 1) & 1u);
+        epif_init(c);
+        fence_proxy_async_smem();
+        WMRL_JOB_DONE_P(tile, job);
+      }
+      ++job;
+      for (int t = 0; t < p.H; ++t) {
+        c.t = t;
+        for (int jb_i = 0; jb_i < p.njobs; ++jb_i) {
+          const JobDesc jb = c_jobs[jb_i];
+          for (int tile = 0; tile < 2; ++tile) {
+            WMRL_SET_TILE(tile);
+            if (jb.type == JOB_GRU) {
+              float hp[8];
+              gruf_load_h(c, jb, c.q, hp);
+              mbar_wait_backoff(accf_bar(tile, job), (job >> 1) & 1u);
+              tc_fence_after();
+              epif_gru(c, jb, c.tmem_lane, hp);
+            } else if (jb.type == JOB_PRIOR2_CONT) {
+              float e0[8];
+              epsf_prefetch(c, e0);
+              mbar_wait_backoff(accf_bar(tile, job), (job >> 1) & 1u);
+              tc_fence_after();
+              epif_prior2(c, jb, e0);
+            } else {
+              mbar_wait_backoff(accf_bar(tile, job), (job >> 1) & 1u);
+              tc_fence_after();
+              if (jb.type == JOB_ACTOR_LN) epif_actor_ln(c, jb);
+              else if (jb.type == JOB_DENSE_ELU) epif_dense_elu(c, jb);
+              else if (jb.type == JOB_MU) epif_mu(c, jb);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            WMRL_JOB_DONE_P(tile, job);
+          }
+          ++job;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == kMmaWarp) tmem_dealloc2(tmem_base, 512);
+}
+
 int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
                    const void* packed, const float* deter0, const float* stoch0,
                    const float* noise, float* deter_seq, float* stoch_seq, float* dist_a,
@@ -1716,6 +1955,7 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
   p.off_h = pl.off_h; p.off_s = pl.off_s; p.off_a = pl.off_a; p.off_x = pl.off_x; p.off_h2 = pl.off_h2;
   p.ring_off = pl.ring_off; p.bar_off = pl.bar_off; p.nslots = pl.nslots;
   p.slot_bytes = (uint32_t)(pl.stage_bytes / pl.cta);
+  p.panel_bytes = pl.panels_bytes;
   p.ntiles = (d.B + kTileM - 1) / kTileM;
   p.trace = (d.flags & 4) ? (long long*)ws : nullptr;
   // swizzle needs >= 8 16-byte chunks per row (Sp >= 32) and the staging must fit below the h' columns
@@ -1753,12 +1993,14 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
                                       (int)pl.smem_bytes));
     WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem_bytes));
+    WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)pl.smem_bytes));
     s_smem[dev] = pl.smem_bytes;
   }
   const int sms = s_sms[dev];
   if (pl.cta == 2) {
     // CTA pairs: one cluster of 2 per pair of 128-row tiles (mode 2) / per 128-row tile (mode 3, folded)
-    const int pairs = std::min(pl.fold ? p.ntiles : (p.ntiles + 1) / 2, sms / 2);
+    const int pairs = std::min(pl.pp ? (p.ntiles + 1) / 2 : (pl.fold ? p.ntiles : (p.ntiles + 1) / 2), sms / 2);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(kThreads);
@@ -1769,7 +2011,8 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if (pl.fold) WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_fold_kernel, p));
+    if (pl.pp) WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_pp_kernel, p));
+    else if (pl.fold) WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_fold_kernel, p));
     else if (p.trace) WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_kernel<2, true>, p));
     else WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_kernel<2, false>, p));
   } else {
