@@ -241,3 +241,44 @@ def test_edge_cases():
     # one-hot samples
     s = seq.stoch_states[:, 1:].reshape(32, 10, 4, 8)
     assert torch.equal(s.sum(-1), torch.ones(32, 10, 4, device=dev))
+
+
+@pytest.mark.parametrize("variant", ["continuous", "discrete"])
+def test_observe_vs_oracle_few_rows_long_k(variant):
+    """posterior filtering at B ~ 50 with K >= 128: exercises the skinny-M GEMM (fwd, dgrad) next to the
+    tiled one (wgrad); forward fields and every RSSM / input gradient against autograd on the oracle."""
+    dev = _dev()
+    import helpers_gpu as HG
+    B, T, D, S, C, Hd, E, A = 40, 5, 160, 12, (6 if variant == "discrete" else 1), 144, 200, 3
+    rssm, _ = HG.build_modules(variant, D, S, C, Hd, E, A, 64, 1, seed=11)
+    g = torch.Generator().manual_seed(12)
+    obs = torch.relu(torch.randn(B, T, E, generator=g))
+    act = torch.rand(B, T, A, generator=g) * 2 - 1
+    mk = (lambda: torch.empty(T - 1, B, C, S).exponential_(1.0, generator=g)) if variant == "discrete" else \
+        (lambda: torch.randn(T - 1, B, S, generator=g))
+    n1, n2 = mk(), mk()
+    obs_d, act_d = obs.to(dev).requires_grad_(True), act.to(dev).requires_grad_(True)
+    pri, post = rssm.observe_rollout(obs_d, act_d, noise=(n1.to(dev), n2.to(dev)))
+    w = HG.cpu_weights(rssm)
+    for v in w.values():
+        v.requires_grad_(True)
+    obs_c, act_c = obs.clone().requires_grad_(True), act.clone().requires_grad_(True)
+    rpri, rpost = O.observe_rollout(variant, w, obs_c, act_c, n1, n2, S, C)
+    if variant == "discrete":
+        assert torch.equal(post.stoch_states[:, 1:].cpu(), rpost["stoch"].detach())
+        close(post.logits[:, 1:], rpost["logits"], 1e-5, 5e-5, msg="post logits")
+    else:
+        close(post.stoch_states[:, 1:], rpost["stoch"], msg="post stoch")
+        close(pri.means[:, 1:], rpri["mean"], msg="prior mean")
+    close(post.deter_states[:, 1:], rpost["deter"], msg="deter")
+    gw = torch.randn(B, T - 1, D + S * C, generator=g) / B
+    (post.get_features() * gw.to(dev)).sum().backward()
+    (torch.cat([rpost["deter"], rpost["stoch"]], -1) * gw).sum().backward()
+    named = dict(rssm.named_parameters())
+    for k, v in w.items():
+        if v.grad is None:
+            continue
+        scale = float(v.grad.abs().max())
+        close(named[k].grad, v.grad, 1e-3, 1e-4 * scale + 1e-7, msg=k)
+    close(obs_d.grad, obs_c.grad, 1e-3, 1e-6, msg="d obs")
+    close(act_d.grad, act_c.grad, 1e-3, 1e-6, msg="d act")

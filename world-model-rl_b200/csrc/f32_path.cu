@@ -10,6 +10,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace wmrl {
 
@@ -108,8 +109,178 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Skinny GEMM for M <= 64 rows (posterior filtering at B ~ 50).  The 64x64-tile kernel above would
+// launch N/64 blocks that each walk all of K serially; at these sizes the weight matrix (a few MB,
+// L2-resident) is the traffic and latency is the cost, so the work is spread over every SM instead:
+//   grid = (N/32 column strips, split), cluster = (1, split, 1): the CTAs of a cluster share a strip
+//   and each takes 1/split of K.  A CTA stages its [64 x kt] A tile and [32 x kt] B tile with 4-byte
+//   cp.async (any strides / alignment), two tiles in flight, and computes 4 rows x 2 columns per
+//   thread with 128-bit shared loads along k.  Partial tiles are reduced through distributed shared
+//   memory: rank r sums rows [r*64/split, ...) over all ranks, adds bias / activation and stores.
+// No atomics, so the result is deterministic and C needs no zero fill.
+// ---------------------------------------------------------------------------
+constexpr int SK_M = 64, SK_N = 32, SK_KT = 128, SK_KS = SK_KT + 4;
+constexpr int SK_STAGE_FLOATS = (SK_M + SK_N) * SK_KS;
+constexpr int SK_SMEM_BYTES = (2 * SK_STAGE_FLOATS + SK_M * SK_N) * (int)sizeof(float);
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ptx::smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ float ld_dsmem(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void sk_stage_tile(const GemmArgs& g, float* As, float* Bs, int k0,
+                                              int kend, int n0, int tid) {
+  const bool a_fastk = (g.a1_sk == 1);
+  const bool b_fastk = (g.b_sk == 1);
+#pragma unroll 4
+  for (int e = tid; e < SK_M * SK_KT; e += 256) {
+    int m, k;
+    if (a_fastk) { k = e % SK_KT; m = e / SK_KT; } else { m = e % SK_M; k = e / SK_M; }
+    const int gk = k0 + k;
+    float* dst = As + m * SK_KS + k;
+    if (m < g.M && gk < kend) {
+      const float* src = (gk < g.K1) ? g.A1 + (long long)m * g.a1_si + (long long)gk * g.a1_sk
+                                     : g.A2 + (long long)m * g.a2_si + (long long)(gk - g.K1) * g.a2_sk;
+      cp_async4(dst, src);
+    } else {
+      *dst = 0.f;
+    }
+  }
+#pragma unroll 4
+  for (int e = tid; e < SK_N * SK_KT; e += 256) {
+    int j, k;
+    if (b_fastk) { k = e % SK_KT; j = e / SK_KT; } else { j = e % SK_N; k = e / SK_N; }
+    const int gk = k0 + k, gn = n0 + j;
+    float* dst = Bs + j * SK_KS + k;
+    if (gn < g.N && gk < kend) cp_async4(dst, g.Bm + (long long)gk * g.b_sk + (long long)gn * g.b_sj);
+    else *dst = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) sgemm_skinny_kernel(GemmArgs g) {
+  extern __shared__ __align__(16) float sk_smem[];
+  float* red = sk_smem + 2 * SK_STAGE_FLOATS;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15;   // columns tx, tx + 16
+  const int ty = tid >> 4;   // rows ty*4 .. ty*4+3
+  const int n0 = blockIdx.x * SK_N;
+  const int split = gridDim.y;
+  const int rank = blockIdx.y;   // == %cluster_ctarank for cluster dims (1, split, 1)
+  const int K = g.K1 + g.K2;
+  const int kbeg = min(K, rank * g.kper), kend = min(K, kbeg + g.kper);
+  const int ntiles = (kend - kbeg + SK_KT - 1) / SK_KT;
+
+  float acc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+
+  if (ntiles > 0) sk_stage_tile(g, sk_smem, sk_smem + SK_M * SK_KS, kbeg, kend, n0, tid);
+  cp_async_commit();
+  for (int t = 0; t < ntiles; ++t) {
+    float* As = sk_smem + (t & 1) * SK_STAGE_FLOATS;
+    float* Bs = As + SK_M * SK_KS;
+    if (t + 1 < ntiles) {
+      float* An = sk_smem + ((t + 1) & 1) * SK_STAGE_FLOATS;
+      sk_stage_tile(g, An, An + SK_M * SK_KS, kbeg + (t + 1) * SK_KT, kend, n0, tid);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const int klen = min(SK_KT, kend - (kbeg + t * SK_KT));
+    const int k4n = (klen + 3) >> 2;   // the tail of the last float4 is zero-filled
+    const float* ap = As + (ty * 4) * SK_KS;
+    const float* bp = Bs + tx * SK_KS;
+#pragma unroll 2
+    for (int k4 = 0; k4 < k4n; ++k4) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bp + k4 * 4);
+      const float4 b1 = *reinterpret_cast<const float4*>(bp + 16 * SK_KS + k4 * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(ap + i * SK_KS + k4 * 4);
+        acc[i][0] = fmaf(a.x, b0.x, fmaf(a.y, b0.y, fmaf(a.z, b0.z, fmaf(a.w, b0.w, acc[i][0]))));
+        acc[i][1] = fmaf(a.x, b1.x, fmaf(a.y, b1.y, fmaf(a.z, b1.z, fmaf(a.w, b1.w, acc[i][1]))));
+      }
+    }
+    __syncthreads();   // the buffer is refilled by the staging of tile t + 2
+  }
+
+  if (split == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = ty * 4 + i;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = n0 + tx + 16 * j;
+        if (m < g.M && n < g.N) {
+          float v = acc[i][j] + (g.bias ? g.bias[n] : 0.f);
+          if (g.act == 1) v = elu_f(v);
+          float* c = g.C + (long long)m * g.ldc + n;
+          *c = g.accumulate ? (*c + v) : v;
+        }
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red[(ty * 4 + i) * SK_N + tx] = acc[i][0];
+    red[(ty * 4 + i) * SK_N + tx + 16] = acc[i][1];
+  }
+  ptx::cluster_sync_all();
+  const int rows = SK_M / split;   // split is 2, 4 or 8
+  for (int o = tid; o < rows * SK_N; o += 256) {
+    const int m = rank * rows + o / SK_N, j = o % SK_N, n = n0 + j;
+    const uint32_t local = ptx::smem_u32(red + m * SK_N + j);
+    float v = 0.f;
+    for (int r = 0; r < split; ++r) v += ld_dsmem(ptx::mapa(local, (uint32_t)r));
+    if (m < g.M && n < g.N) {
+      if (g.bias) v += g.bias[n];
+      if (g.act == 1) v = elu_f(v);
+      float* c = g.C + (long long)m * g.ldc + n;
+      *c = g.accumulate ? (*c + v) : v;
+    }
+  }
+  ptx::cluster_sync_all();   // peers may still be reading this CTA's partial tile
+}
+
+static int launch_skinny(cudaStream_t st, GemmArgs g) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    WMRL_CUDA_OK(cudaFuncSetAttribute(sgemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SK_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int K = g.K1 + g.K2;
+  const int strips = (g.N + SK_N - 1) / SK_N;
+  int split = 1;
+  while (split < 8 && strips * split < 148 && K / (split * 2) >= 32) split *= 2;
+  g.kper = ((K + split - 1) / split + 3) / 4 * 4;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(strips, split, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = SK_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = split; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, sgemm_skinny_kernel, g));
+  return 0;
+}
+
 static int launch_gemm(cudaStream_t st, GemmArgs g, int splitk) {
   if (g.M <= 0 || g.N <= 0) return 0;
+  if (splitk <= 1 && g.M <= SK_M && (g.K1 + g.K2) >= 128) return launch_skinny(st, g);
   const int K = g.K1 + g.K2;
   if (splitk < 1) splitk = 1;
   int kper = ((K + splitk - 1) / splitk + BK - 1) / BK * BK;
