@@ -201,6 +201,23 @@ WMRL_API int wmrl_lambda_return_bwd(const float* g_out, const float* d, float ga
 /* shift right by one, threshold 0.5, running max (value_trainer.py:148-149). */
 WMRL_API int wmrl_done_mask(const float* dones, int32_t B, int32_t H, float* out, void* stream);
 
+/*
+ * The Linear primitive every layer of the path is built from (torch.nn.Linear as used at
+ * rssm.py:28-42, actor.py:23-40 and by the heads next to the path, models.py:3-37), exposed so the
+ * callers either side can run their MLPs on the same kernels and so the GEMM can be tested directly.
+ * fp32 in / fp32 out; more than 64 rows run on the tensor cores as 3xTF32 (fp32-accurate), fewer on
+ * the cluster split-K SIMT kernel.  W is torch layout [N][K] row-major; ld* are row strides in elements.
+ *   fwd:   Y[M,N]  = act(X[M,K] W^T + bias)          act: 0 none, 1 ELU; bias may be NULL
+ *   dgrad: dX[M,K] (+)= dY[M,N] W                    accumulate != 0 adds into dX
+ *   wgrad: dW[N,K] += dY[M,N]^T X[M,K]               always accumulates (zero dW first)
+ */
+WMRL_API int wmrl_linear_fwd(int32_t M, int32_t N, int32_t K, const float* X, int64_t ldx, const float* W,
+                    const float* bias, float* Y, int64_t ldy, int32_t act, void* stream);
+WMRL_API int wmrl_linear_dgrad(int32_t M, int32_t N, int32_t K, const float* dY, int64_t lddy, const float* W,
+                      float* dX, int64_t lddx, int32_t accumulate, void* stream);
+WMRL_API int wmrl_linear_wgrad(int32_t M, int32_t N, int32_t K, const float* dY, int64_t lddy, const float* X,
+                      int64_t ldx, float* dW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,9 +8,11 @@
 // the weight gradients) plus fused element-wise kernels (LayerNorm+ELU, GRU
 // gates, sampling).  No cuBLAS, no host synchronisation.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "gemm.cuh"
 
 namespace wmrl {
 
@@ -19,18 +21,6 @@ namespace wmrl {
 // (two K-segments), B(k,j) = B[k*sk + j*sj].
 // ---------------------------------------------------------------------------
 constexpr int BM = 64, BN = 64, BK = 16;
-
-struct GemmArgs {
-  const float* A1; long long a1_si, a1_sk; int K1;
-  const float* A2; long long a2_si, a2_sk; int K2;
-  const float* Bm; long long b_sk, b_sj;
-  float* C; long long ldc;
-  const float* bias;  // per output column, added by z-slice 0; may be null
-  int M, N;
-  int act;         // 0 none, 1 ELU (only with a single K slice)
-  int accumulate;  // C += result
-  int kper;        // K elements per z-slice (multiple of BK)
-};
 
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
 
@@ -281,6 +271,24 @@ static int launch_skinny(cudaStream_t st, GemmArgs g) {
 static int launch_gemm(cudaStream_t st, GemmArgs g, int splitk) {
   if (g.M <= 0 || g.N <= 0) return 0;
   if (splitk <= 1 && g.M <= SK_M && (g.K1 + g.K2) >= 128) return launch_skinny(st, g);
+  // More than 64 rows: tensor cores (3xTF32, fp32-accurate).  WMRL_F32_GEMM=simt keeps the SIMT tile
+  // kernel below for A/B comparisons.
+  static const bool use_simt = [] {
+    const char* e = getenv("WMRL_F32_GEMM");
+    return e && e[0] == 's';
+  }();
+  if (!use_simt && g.M > SK_M) {
+    if (splitk > 1) {
+      // split-K (weight gradients: K = batch rows): aim at two 128-row tiles per SM, >= 256 k per slice
+      const int K = g.K1 + g.K2;
+      const int tiles = ((g.M + 127) / 128) * ((g.N + 255) / 256);
+      splitk = (296 + tiles - 1) / tiles;
+      const int maxsplit = (K + 255) / 256;
+      if (splitk > maxsplit) splitk = maxsplit;
+      if (splitk < 2) splitk = 2;   // callers rely on += semantics through the atomic epilogue
+    }
+    return tf32x3_gemm_launch(st, g, splitk);
+  }
   const int K = g.K1 + g.K2;
   if (splitk < 1) splitk = 1;
   int kper = ((K + splitk - 1) / splitk + BK - 1) / BK * BK;
@@ -1142,5 +1150,27 @@ int wmrl_done_mask(const float* dones, int32_t B, int32_t H, float* out, void* s
   wmrl::done_mask_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dones, B, H, out);
   WMRL_CUDA_OK(cudaGetLastError());
   return 0;
+}
+int wmrl_linear_fwd(int32_t M, int32_t N, int32_t K, const float* X, int64_t ldx, const float* W,
+                    const float* bias, float* Y, int64_t ldy, int32_t act, void* stream) {
+  WMRL_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_fwd: bad shape");
+  WMRL_REQUIRE(act == 0 || act == 1, "linear_fwd: act must be 0 (none) or 1 (ELU)");
+  if (M == 0) return 0;
+  WMRL_REQUIRE(X && W && Y, "linear_fwd: NULL tensor");
+  return wmrl::linear((cudaStream_t)stream, X, ldx, K, nullptr, 0, 0, W, bias, Y, ldy, M, N, act);
+}
+int wmrl_linear_dgrad(int32_t M, int32_t N, int32_t K, const float* dY, int64_t lddy, const float* W,
+                      float* dX, int64_t lddx, int32_t accumulate, void* stream) {
+  WMRL_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_dgrad: bad shape");
+  if (M == 0) return 0;
+  WMRL_REQUIRE(dY && W && dX, "linear_dgrad: NULL tensor");
+  return wmrl::dgrad((cudaStream_t)stream, dY, lddy, N, W, K, 0, K, dX, lddx, M, accumulate);
+}
+int wmrl_linear_wgrad(int32_t M, int32_t N, int32_t K, const float* dY, int64_t lddy, const float* X,
+                      int64_t ldx, float* dW, void* stream) {
+  WMRL_REQUIRE(M >= 0 && N > 0 && K > 0, "linear_wgrad: bad shape");
+  if (M == 0) return 0;
+  WMRL_REQUIRE(dY && X && dW, "linear_wgrad: NULL tensor");
+  return wmrl::wgrad((cudaStream_t)stream, dY, lddy, N, X, ldx, K, dW, K, 0, M);
 }
 }

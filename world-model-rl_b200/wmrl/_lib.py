@@ -79,6 +79,9 @@ _SIGNATURES = {
     "wmrl_lambda_return_fwd": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P]),
     "wmrl_lambda_return_bwd": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),
     "wmrl_done_mask": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
+    "wmrl_linear_fwd": (C.c_int, [C.c_int32] * 3 + [_P, C.c_int64, _P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "wmrl_linear_dgrad": (C.c_int, [C.c_int32] * 3 + [_P, C.c_int64, _P, _P, C.c_int64, C.c_int32, _P]),
+    "wmrl_linear_wgrad": (C.c_int, [C.c_int32] * 3 + [_P, C.c_int64, _P, C.c_int64, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

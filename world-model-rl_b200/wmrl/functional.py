@@ -427,3 +427,62 @@ def done_mask(dones: torch.Tensor) -> torch.Tensor:
         _lib.check(lib.wmrl_done_mask(d2.data_ptr(), d2.shape[0], d2.shape[1], out.data_ptr(), _stream_ptr(dev)),
                    "wmrl_done_mask")
     return out.reshape(shape)
+
+
+# ----------------------------------------------------------------------------
+# Linear primitive (the GEMM under every layer of the path)
+# ----------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) on libwmrl's GEMM kernels (3xTF32 tcgen05 for more than 64 rows, cluster
+    split-K SIMT below), with dgrad / wgrad through the same kernels.  `act`: 0 none, 1 ELU."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act: int):
+        lib = _lib.load()
+        dev = _require_cuda(x, weight)
+        x2 = _f32c(x.reshape(-1, x.shape[-1]))
+        w = _f32c(weight)
+        b = None if bias is None else _f32c(bias)
+        M, K = x2.shape
+        N = w.shape[0]
+        if w.shape[1] != K:
+            raise ValueError(f"linear: x has {K} features, weight expects {w.shape[1]}")
+        y = torch.empty(M, N, device=dev)
+        if M > 0:
+            _lib.check(lib.wmrl_linear_fwd(M, N, K, x2.data_ptr(), K, w.data_ptr(), _lib.ptr(b), y.data_ptr(), N,
+                                           int(act), _stream_ptr(dev)), "wmrl_linear_fwd")
+        ctx.save_for_backward(x2, w, y if act else None)
+        ctx.act, ctx.has_bias, ctx.x_shape = int(act), bias is not None, x.shape
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, g_y):
+        lib = _lib.load()
+        x2, w, y = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        g = _f32c(g_y.reshape(M, N))
+        if ctx.act == 1:   # ELU'(z) = 1 for z > 0 else y + 1
+            g = g * torch.where(y > 0, torch.ones_like(y), y + 1.0)
+        dev = g.device
+        g_x = g_w = g_b = None
+        if M > 0 and ctx.needs_input_grad[0]:
+            g_x = torch.empty(M, K, device=dev)
+            _lib.check(lib.wmrl_linear_dgrad(M, N, K, g.data_ptr(), N, w.data_ptr(), g_x.data_ptr(), K, 0,
+                                             _stream_ptr(dev)), "wmrl_linear_dgrad")
+            g_x = g_x.reshape(ctx.x_shape)
+        elif ctx.needs_input_grad[0]:
+            g_x = torch.zeros(ctx.x_shape, device=dev)
+        if ctx.needs_input_grad[1]:
+            g_w = torch.zeros(N, K, device=dev)
+            if M > 0:
+                _lib.check(lib.wmrl_linear_wgrad(M, N, K, g.data_ptr(), N, x2.data_ptr(), K, g_w.data_ptr(),
+                                                 _stream_ptr(dev)), "wmrl_linear_wgrad")
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            g_b = g.sum(0)
+        return g_x, g_w, g_b, None
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0) -> torch.Tensor:
+    """Drop-in for ``torch.nn.functional.linear`` (optionally fused ELU) on libwmrl's kernels."""
+    return LinearFn.apply(x, weight, bias, act)
