@@ -505,14 +505,34 @@ __global__ void elu_bwd_kernel(float* g, const float* y, long long n) {
 }
 
 // out[j] += sum_m dY[m*ld + j]
-__global__ void colsum_kernel(const float* dY, long long ld, int M, int N, float* out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N) return;
-  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+// out[j] += sum_m dY[m][j].  Block = 32 columns x 8 row phases; a block covers `rows_per` rows with
+// four independent loads in flight per thread, folds the 8 phases in shared memory and adds once.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dY, long long ld, int M, int N,
+                                                     int rows_per, float* out) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
   const int m0 = blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
-  float s = 0.f;
-  for (int m = m0; m < m1; ++m) s += dY[(long long)m * ld + j];
-  atomicAdd(&out[j], s);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (j < N) {
+    const float* p = dY + j;
+    int m = m0 + ty;
+    for (; m + 24 < m1; m += 32) {
+      s0 += p[(long long)m * ld];
+      s1 += p[(long long)(m + 8) * ld];
+      s2 += p[(long long)(m + 16) * ld];
+      s3 += p[(long long)(m + 24) * ld];
+    }
+    for (; m < m1; m += 8) s0 += p[(long long)m * ld];
+  }
+  part[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && j < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += part[i][tx];
+    atomicAdd(&out[j], s);
+  }
 }
 
 // continuous head (rssm.py:179-181)
@@ -633,10 +653,14 @@ static int combine(cudaStream_t st, const float* a, long long lda, const float* 
 }
 static int bgrad(cudaStream_t st, const float* dY, long long ld, int M, int N, float* db) {
   if (!db) return 0;
-  int gy = (M + 255) / 256;
-  if (gy > 64) gy = 64;
-  dim3 grid((N + 127) / 128, gy);
-  colsum_kernel<<<grid, 128, 0, st>>>(dY, ld, M, N, db);
+  const int gx = (N + 31) / 32;
+  int gy = (M + 63) / 64;                      // >= 64 rows per block ...
+  const int want = (148 * 8 + gx - 1) / gx;    // ... but no more blocks than fill the GPU a few times
+  if (gy > want) gy = want;
+  if (gy < 1) gy = 1;
+  const int rows_per = (M + gy - 1) / gy;
+  gy = (M + rows_per - 1) / rows_per;
+  colsum_kernel<<<dim3(gx, gy), 256, 0, st>>>(dY, ld, M, N, rows_per, db);
   WMRL_CUDA_OK(cudaGetLastError());
   return 0;
 }
