@@ -243,13 +243,15 @@ def test_edge_cases():
     assert torch.equal(s.sum(-1), torch.ones(32, 10, 4, device=dev))
 
 
+@pytest.mark.parametrize("B", [40, 150])
 @pytest.mark.parametrize("variant", ["continuous", "discrete"])
-def test_observe_vs_oracle_few_rows_long_k(variant):
-    """posterior filtering at B ~ 50 with K >= 128: exercises the skinny-M GEMM (fwd, dgrad) next to the
-    tiled one (wgrad); forward fields and every RSSM / input gradient against autograd on the oracle."""
+def test_observe_vs_oracle_few_rows_long_k(variant, B):
+    """posterior filtering with K >= 128 at B = 40 (cluster split-K skinny GEMM for fwd / dgrad next to the
+    tensor-core one for wgrad) and B = 150 (3xTF32 tcgen05 GEMM everywhere, ragged row tile); forward fields
+    and every RSSM / input gradient against autograd on the oracle."""
     dev = _dev()
     import helpers_gpu as HG
-    B, T, D, S, C, Hd, E, A = 40, 5, 160, 12, (6 if variant == "discrete" else 1), 144, 200, 3
+    T, D, S, C, Hd, E, A = 5, 160, 12, (6 if variant == "discrete" else 1), 144, 200, 3
     rssm, _ = HG.build_modules(variant, D, S, C, Hd, E, A, 64, 1, seed=11)
     g = torch.Generator().manual_seed(12)
     obs = torch.relu(torch.randn(B, T, E, generator=g))

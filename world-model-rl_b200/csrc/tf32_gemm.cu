@@ -115,9 +115,29 @@ __device__ __forceinline__ void item_rc(int it, int rows, bool kfast, int& row, 
   if (kfast) { quad = it & 3; row = it >> 2; } else { row = it % rows; quad = it / rows; }
 }
 
-__global__ void __launch_bounds__(TG_THREADS, 2) tf32x3_gemm_kernel(GemmArgs g, int BN, int tmem_cols) {
+// predicated, branch-free loads into pre-zeroed registers
+__device__ __forceinline__ void ldg128_if(float4& v, const float* p, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "l"(p), "r"((int)pred));
+}
+__device__ __forceinline__ void ldg32_if(float& v, const float* p, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q ld.global.nc.f32 %0, [%1];\n\t}"
+      : "+f"(v)
+      : "l"(p), "r"((int)pred));
+}
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// 256 staging / epilogue threads + one MMA-issuing warp.
+constexpr int TG_BLOCK = TG_THREADS + 32;
+
+__global__ void __launch_bounds__(TG_BLOCK, 2) tf32x3_gemm_kernel(GemmArgs g, int BN, int tmem_cols) {
   extern __shared__ __align__(128) uint8_t tg_smem[];
-  __shared__ __align__(8) uint64_t bars[TG_STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * TG_STAGES + 1];   // full[S] | empty[S] | accumulator ready
   __shared__ uint32_t tmem_slot;
   using namespace ptx;
 
@@ -127,10 +147,14 @@ __global__ void __launch_bounds__(TG_THREADS, 2) tf32x3_gemm_kernel(GemmArgs g, 
   const int kbeg = blockIdx.z * g.kper, kend = min(K, kbeg + g.kper);
   const int nkb = kend > kbeg ? (kend - kbeg + TG_BK - 1) / TG_BK : 0;
   const uint32_t smem0 = smem_u32(tg_smem);
-  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * TG_STAGES, bar_acc = bar_full + 16 * TG_STAGES;
 
   if (tid == 0) {
-    for (int i = 0; i <= TG_STAGES; ++i) mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i < TG_STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, TG_THREADS);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_acc, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -142,115 +166,172 @@ __global__ void __launch_bounds__(TG_THREADS, 2) tf32x3_gemm_kernel(GemmArgs g, 
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  Operand oa{g.A1, g.a1_si, g.a1_sk, g.K1, g.A2, g.a2_si, g.a2_sk};
-  Operand ob{g.Bm, g.b_sj, g.b_sk, K, g.Bm, g.b_sj, g.b_sk};   // B(k, j): row = j
-  const bool a_kfast = (g.a1_sk == 1), b_kfast = (g.b_sk == 1);
-  const int b_items = BN * TG_QUADS;
+  if (warp == TG_THREADS / 32) {
+    // ------------------------------------------------------------------ MMA issuer (one lane)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TG_BM, (uint32_t)BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TG_STAGES;
+        const uint32_t st = smem0 + s * TG_STAGE_BYTES;
+        mbar_wait(bar_full + 8 * s, (kb / TG_STAGES) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < TG_BK / 8; ++ks) {
+          const uint32_t a_hi = st + ks * 2 * TG_LBO_A, a_lo = a_hi + TG_A_BYTES;
+          const uint32_t b_hi = st + 2 * TG_A_BYTES + ks * 2 * TG_LBO_B, b_lo = b_hi + TG_B_BYTES;
+          const uint64_t dah = make_smem_desc(a_hi, TG_LBO_A, 128), dal = make_smem_desc(a_lo, TG_LBO_A, 128);
+          const uint64_t dbh = make_smem_desc(b_hi, TG_LBO_B, 128), dbl = make_smem_desc(b_lo, TG_LBO_B, 128);
+          mma_tf32_ss(tmem, dal, dbh, idesc, (kb | ks) != 0);   // small terms first
+          mma_tf32_ss(tmem, dah, dbl, idesc, 1);
+          mma_tf32_ss(tmem, dah, dbh, idesc, 1);
+        }
+        tc_commit(bar_empty + 8 * s);
+        if (kb == nkb - 1) tc_commit(bar_acc);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ staging + epilogue threads
+    const Operand oa{g.A1, g.a1_si, g.a1_sk, g.K1, g.A2, g.a2_si, g.a2_sk};
+    const Operand ob{g.Bm, g.b_sj, g.b_sk, K, g.Bm, g.b_sj, g.b_sk};   // B(k, j): row = j
+    const bool a_kfast = (g.a1_sk == 1), b_kfast = (g.b_sk == 1);
+    const int b_items = BN * TG_QUADS;
+    // How a whole 16-wide k-block of an operand can be loaded - uniform over the CTA, so the common cases
+    // are branch-free predicated loads off per-item row pointers (the generic path costs ~50 instructions
+    // per quad, which at 8 warps per SM was the bottleneck):
+    //   vec: k-contiguous, 16-byte aligned rows            -> one LDG.128 per quad
+    //   str: row-contiguous (dgrad's W, wgrad's dY^T / X)   -> 4 coalesced LDG.32 per quad
+    const bool a_vec1 = g.a1_sk == 1 && aligned16(g.A1) && (g.a1_si & 3) == 0;
+    const bool a_vec2 = g.K2 > 0 && g.a2_sk == 1 && aligned16(g.A2) && (g.a2_si & 3) == 0 && (g.K1 & 3) == 0;
+    const bool a_str = g.K2 == 0 && g.a1_si == 1 && g.a1_sk != 1;
+    const bool b_vec = g.b_sk == 1 && aligned16(g.Bm) && (g.b_sj & 3) == 0;
+    const bool b_str = g.b_sj == 1 && g.b_sk != 1;
 
-  // fixed (row, quad) assignment of this thread's items
-  int a_row[2], a_quad[2], b_row[4], b_quad[4];
-  bool a_ok[2], b_ok[4];
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    item_rc(tid + TG_THREADS * j, TG_BM, a_kfast, a_row[j], a_quad[j]);
-    a_ok[j] = (m0 + a_row[j]) < g.M;
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int it = tid + TG_THREADS * j;
-    item_rc(it < b_items ? it : 0, BN, b_kfast, b_row[j], b_quad[j]);
-    b_ok[j] = it < b_items && (n0 + b_row[j]) < g.N;
-    if (it >= b_items) b_row[j] = -1;   // nothing to stage
-  }
-
-  float4 ra[2], rb[4];
-  auto fetch = [&](int kb) {
-    const int k0 = kbeg + kb * TG_BK;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) ra[j] = load_quad(oa, a_ok[j], m0 + a_row[j], k0 + a_quad[j] * 4, kend);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) rb[j] = load_quad(ob, b_ok[j], n0 + b_row[j], k0 + b_quad[j] * 4, kend);
-  };
-  if (nkb > 0) fetch(0);
-
-  const uint32_t idesc = make_idesc_tf32(TG_BM, (uint32_t)BN);
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb % TG_STAGES;
-    const uint32_t st = smem0 + s * TG_STAGE_BYTES;
-    if (kb >= TG_STAGES) mbar_wait(bar0 + 8 * s, ((kb / TG_STAGES) - 1) & 1);
+    int a_row[2], a_kq[2], b_row[4], b_kq[4];
+    bool a_ok[2], b_ok[4];
+    uint32_t a_soff[2], b_soff[4];
+    const float* a_p1[2];
+    const float* a_p2[2];
+    const float* b_p[4];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const uint32_t off = a_quad[j] * TG_LBO_A + a_row[j] * 16;
-      store_split(st + off, st + TG_A_BYTES + off, ra[j]);
+      int q;
+      item_rc(tid + TG_THREADS * j, TG_BM, a_kfast, a_row[j], q);
+      a_kq[j] = q * 4;
+      a_ok[j] = (m0 + a_row[j]) < g.M;
+      a_soff[j] = q * TG_LBO_A + a_row[j] * 16;
+      const long long row = m0 + a_row[j];
+      a_p1[j] = a_str ? g.A1 + row + (long long)a_kq[j] * g.a1_sk : g.A1 + row * g.a1_si + a_kq[j];
+      a_p2[j] = g.K2 > 0 ? g.A2 + row * g.a2_si + a_kq[j] - g.K1 : a_p1[j];
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (b_row[j] >= 0) {
-        const uint32_t off = 2 * TG_A_BYTES + b_quad[j] * TG_LBO_B + b_row[j] * 16;
-        store_split(st + off, st + TG_B_BYTES + off, rb[j]);
-      }
+      const int it = tid + TG_THREADS * j;
+      int q;
+      item_rc(it < b_items ? it : 0, BN, b_kfast, b_row[j], q);
+      b_kq[j] = q * 4;
+      b_ok[j] = it < b_items && (n0 + b_row[j]) < g.N;
+      b_soff[j] = 2 * TG_A_BYTES + q * TG_LBO_B + b_row[j] * 16;
+      const long long row = n0 + b_row[j];
+      b_p[j] = b_str ? g.Bm + row + (long long)b_kq[j] * g.b_sk : g.Bm + row * g.b_sj + b_kq[j];
+      if (it >= b_items) b_row[j] = -1;   // nothing to stage
     }
-    if (kb + 1 < nkb) fetch(kb + 1);
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < TG_BK / 8; ++ks) {
-        const uint32_t a_hi = st + ks * 2 * TG_LBO_A, a_lo = a_hi + TG_A_BYTES;
-        const uint32_t b_hi = st + 2 * TG_A_BYTES + ks * 2 * TG_LBO_B, b_lo = b_hi + TG_B_BYTES;
-        const uint64_t dah = make_smem_desc(a_hi, TG_LBO_A, 128), dal = make_smem_desc(a_lo, TG_LBO_A, 128);
-        const uint64_t dbh = make_smem_desc(b_hi, TG_LBO_B, 128), dbl = make_smem_desc(b_lo, TG_LBO_B, 128);
-        mma_tf32_ss(tmem, dal, dbh, idesc, (kb | ks) != 0);   // small terms first
-        mma_tf32_ss(tmem, dah, dbl, idesc, 1);
-        mma_tf32_ss(tmem, dah, dbh, idesc, 1);
-      }
-      tc_commit(bar0 + 8 * s);
-      if (kb == nkb - 1) tc_commit(bar0 + 8 * TG_STAGES);
-    }
-  }
 
-  if (nkb > 0) {
-    mbar_wait(bar0 + 8 * TG_STAGES, 0);
-    tc_fence_after();
-  }
-  // Epilogue: 64 columns per round.  Warp w owns TMEM lanes 32*(w%4).., columns (w/4)*32.. of the round.
-  float* tile = reinterpret_cast<float*>(tg_smem);
-  const bool atomic = gridDim.z > 1;
-  const int ncols_tile = min(BN, g.N - n0);
-  for (int c0 = 0; c0 < BN; c0 += 64) {
-    const int cw = c0 + (warp >> 2) * 32;
-    if (cw < BN) {
-      float v[32];
-      if (nkb > 0) {
-        tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cw, v);
-        tmem_ld_wait();
+    float4 ra[2], rb[4];
+    auto fetch = [&](int kb) {
+      const int k0 = kbeg + kb * TG_BK;
+      const bool whole = k0 + TG_BK <= kend;
+      if (whole && a_vec1 && k0 + TG_BK <= g.K1) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { ra[j] = make_float4(0.f, 0.f, 0.f, 0.f); ldg128_if(ra[j], a_p1[j] + k0, a_ok[j]); }
+      } else if (whole && a_vec2 && k0 >= g.K1) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { ra[j] = make_float4(0.f, 0.f, 0.f, 0.f); ldg128_if(ra[j], a_p2[j] + k0, a_ok[j]); }
+      } else if (whole && a_str) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float* p = a_p1[j] + (long long)k0 * g.a1_sk;
+          ra[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          ldg32_if(ra[j].x, p, a_ok[j]); ldg32_if(ra[j].y, p + g.a1_sk, a_ok[j]);
+          ldg32_if(ra[j].z, p + 2 * g.a1_sk, a_ok[j]); ldg32_if(ra[j].w, p + 3 * g.a1_sk, a_ok[j]);
+        }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        for (int j = 0; j < 2; ++j) ra[j] = load_quad(oa, a_ok[j], m0 + a_row[j], k0 + a_kq[j], kend);
       }
-      float* trow = tile + ((warp & 3) * 32 + lane) * TG_TILE_LD + (warp >> 2) * 32;
+      if (whole && b_vec) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) trow[j] = v[j];
+        for (int j = 0; j < 4; ++j) { rb[j] = make_float4(0.f, 0.f, 0.f, 0.f); ldg128_if(rb[j], b_p[j] + k0, b_ok[j]); }
+      } else if (whole && b_str) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float* p = b_p[j] + (long long)k0 * g.b_sk;
+          rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          ldg32_if(rb[j].x, p, b_ok[j]); ldg32_if(rb[j].y, p + g.b_sk, b_ok[j]);
+          ldg32_if(rb[j].z, p + 2 * g.b_sk, b_ok[j]); ldg32_if(rb[j].w, p + 3 * g.b_sk, b_ok[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rb[j] = load_quad(ob, b_ok[j], n0 + b_row[j], k0 + b_kq[j], kend);
+      }
+    };
+    if (nkb > 0) fetch(0);
+
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TG_STAGES;
+      const uint32_t st = smem0 + s * TG_STAGE_BYTES;
+      if (kb >= TG_STAGES) mbar_wait(bar_empty + 8 * s, ((kb / TG_STAGES) - 1) & 1);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) store_split(st + a_soff[j], st + TG_A_BYTES + a_soff[j], ra[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (b_row[j] >= 0) store_split(st + b_soff[j], st + TG_B_BYTES + b_soff[j], rb[j]);
+      if (kb + 1 < nkb) fetch(kb + 1);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_full + 8 * s);
     }
-    __syncthreads();
-    for (int idx = tid; idx < TG_BM * 64; idx += TG_THREADS) {
-      const int r = idx >> 6, c = idx & 63;
-      const int gm = m0 + r, col = c0 + c;
-      if (gm < g.M && col < ncols_tile) {
-        const int gn = n0 + col;
-        float v = tile[r * TG_TILE_LD + c];
-        if (g.bias && blockIdx.z == 0) v += g.bias[gn];
-        float* cp = g.C + (long long)gm * g.ldc + gn;
-        if (atomic) {
-          atomicAdd(cp, v);
+
+    if (nkb > 0) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+    }
+    // Epilogue: 64 columns per round.  Warp w owns TMEM lanes 32*(w%4).., columns (w/4)*32.. of the round.
+    float* tile = reinterpret_cast<float*>(tg_smem);
+    const bool atomic = gridDim.z > 1;
+    const int ncols_tile = min(BN, g.N - n0);
+    for (int c0 = 0; c0 < BN; c0 += 64) {
+      const int cw = c0 + (warp >> 2) * 32;
+      if (cw < BN) {
+        float v[32];
+        if (nkb > 0) {
+          tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cw, v);
+          tmem_ld_wait();
         } else {
-          if (g.act == 1) v = elu_ref(v);
-          *cp = g.accumulate ? (*cp + v) : v;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        float* trow = tile + ((warp & 3) * 32 + lane) * TG_TILE_LD + (warp >> 2) * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) trow[j] = v[j];
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(TG_THREADS) : "memory");
+      for (int idx = tid; idx < TG_BM * 64; idx += TG_THREADS) {
+        const int r = idx >> 6, c = idx & 63;
+        const int gm = m0 + r, col = c0 + c;
+        if (gm < g.M && col < ncols_tile) {
+          const int gn = n0 + col;
+          float v = tile[r * TG_TILE_LD + c];
+          if (g.bias && blockIdx.z == 0) v += g.bias[gn];
+          float* cp = g.C + (long long)gm * g.ldc + gn;
+          if (atomic) {
+            atomicAdd(cp, v);
+          } else {
+            if (g.act == 1) v = elu_ref(v);
+            *cp = g.accumulate ? (*cp + v) : v;
+          }
         }
       }
+      asm volatile("bar.sync 1, %0;" ::"r"(TG_THREADS) : "memory");
     }
-    __syncthreads();
   }
   tc_fence_before();
   __syncthreads();
@@ -284,7 +365,7 @@ int tf32x3_gemm_launch(cudaStream_t st, const GemmArgs& g_in, int splitk) {
   int tmem_cols = 32;
   while (tmem_cols < BN) tmem_cols *= 2;
   dim3 grid(nt, mt, splitk);
-  tf32x3_gemm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, st>>>(g, BN, tmem_cols);
+  tf32x3_gemm_kernel<<<grid, TG_BLOCK, TG_SMEM_BYTES, st>>>(g, BN, tmem_cols);
   WMRL_CUDA_OK(cudaGetLastError());
   return 0;
 }
