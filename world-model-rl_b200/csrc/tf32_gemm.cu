@@ -17,6 +17,7 @@
 // MMAs that read it have retired.  Two CTAs fit per SM (97 KB smem, 256 TMEM columns each), so one
 // CTA's epilogue and staging overlap the other's MMAs.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -135,9 +136,12 @@ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_c
 // 256 staging / epilogue threads + one MMA-issuing warp.
 constexpr int TG_BLOCK = TG_THREADS + 32;
 
-__global__ void __launch_bounds__(TG_BLOCK, 2) tf32x3_gemm_kernel(GemmArgs g, int BN, int tmem_cols) {
+// <P, S>: P k-blocks of operand loads in flight per thread (register sets), S shared-memory stages.
+// <1, 2> (two CTAs per SM) is the shipped instantiation.
+template <int P, int S>
+__global__ void __launch_bounds__(TG_BLOCK, (P == 1 ? 2 : 1)) tf32x3_gemm_kernel(GemmArgs g, int BN, int tmem_cols) {
   extern __shared__ __align__(128) uint8_t tg_smem[];
-  __shared__ __align__(8) uint64_t bars[2 * TG_STAGES + 1];   // full[S] | empty[S] | accumulator ready
+  __shared__ __align__(8) uint64_t bars[2 * S + 1];   // full[S] | empty[S] | accumulator ready
   __shared__ uint32_t tmem_slot;
   using namespace ptx;
 
@@ -147,10 +151,10 @@ __global__ void __launch_bounds__(TG_BLOCK, 2) tf32x3_gemm_kernel(GemmArgs g, in
   const int kbeg = blockIdx.z * g.kper, kend = min(K, kbeg + g.kper);
   const int nkb = kend > kbeg ? (kend - kbeg + TG_BK - 1) / TG_BK : 0;
   const uint32_t smem0 = smem_u32(tg_smem);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * TG_STAGES, bar_acc = bar_full + 16 * TG_STAGES;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * S, bar_acc = bar_full + 16 * S;
 
   if (tid == 0) {
-    for (int i = 0; i < TG_STAGES; ++i) {
+    for (int i = 0; i < S; ++i) {
       mbar_init(bar_full + 8 * i, TG_THREADS);
       mbar_init(bar_empty + 8 * i, 1);
     }
@@ -171,9 +175,9 @@ __global__ void __launch_bounds__(TG_BLOCK, 2) tf32x3_gemm_kernel(GemmArgs g, in
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(TG_BM, (uint32_t)BN);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TG_STAGES;
+        const int s = kb % S;
         const uint32_t st = smem0 + s * TG_STAGE_BYTES;
-        mbar_wait(bar_full + 8 * s, (kb / TG_STAGES) & 1);
+        mbar_wait(bar_full + 8 * s, (kb / S) & 1);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < TG_BK / 8; ++ks) {
@@ -236,8 +240,8 @@ __global__ void __launch_bounds__(TG_BLOCK, 2) tf32x3_gemm_kernel(GemmArgs g, in
       if (it >= b_items) b_row[j] = -1;   // nothing to stage
     }
 
-    float4 ra[2], rb[4];
-    auto fetch = [&](int kb) {
+    float4 rav[P][2], rbv[P][4];
+    auto fetch = [&](int kb, float4 (&ra)[2], float4 (&rb)[4]) {
       const int k0 = kbeg + kb * TG_BK;
       const bool whole = k0 + TG_BK <= kend;
       if (whole && a_vec1 && k0 + TG_BK <= g.K1) {
@@ -274,20 +278,28 @@ __global__ void __launch_bounds__(TG_BLOCK, 2) tf32x3_gemm_kernel(GemmArgs g, in
         for (int j = 0; j < 4; ++j) rb[j] = load_quad(ob, b_ok[j], n0 + b_row[j], k0 + b_kq[j], kend);
       }
     };
-    if (nkb > 0) fetch(0);
+#pragma unroll
+    for (int u = 0; u < P; ++u)
+      if (u < nkb) fetch(u, rav[u], rbv[u]);
 
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % TG_STAGES;
-      const uint32_t st = smem0 + s * TG_STAGE_BYTES;
-      if (kb >= TG_STAGES) mbar_wait(bar_empty + 8 * s, ((kb / TG_STAGES) - 1) & 1);
+    for (int kb0 = 0; kb0 < nkb; kb0 += P) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) store_split(st + a_soff[j], st + TG_A_BYTES + a_soff[j], ra[j]);
+      for (int u = 0; u < P; ++u) {
+        const int kb = kb0 + u;
+        if (kb < nkb) {
+          const int s = kb % S;
+          const uint32_t st = smem0 + s * TG_STAGE_BYTES;
+          if (kb >= S) mbar_wait(bar_empty + 8 * s, ((kb / S) - 1) & 1);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (b_row[j] >= 0) store_split(st + b_soff[j], st + TG_B_BYTES + b_soff[j], rb[j]);
-      if (kb + 1 < nkb) fetch(kb + 1);
-      fence_proxy_async_smem();
-      mbar_arrive(bar_full + 8 * s);
+          for (int j = 0; j < 2; ++j) store_split(st + a_soff[j], st + TG_A_BYTES + a_soff[j], rav[u][j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (b_row[j] >= 0) store_split(st + b_soff[j], st + TG_B_BYTES + b_soff[j], rbv[u][j]);
+          if (kb + P < nkb) fetch(kb + P, rav[u], rbv[u]);
+          fence_proxy_async_smem();
+          mbar_arrive(bar_full + 8 * s);
+        }
+      }
     }
 
     if (nkb > 0) {
@@ -344,8 +356,8 @@ int tf32x3_gemm_launch(cudaStream_t st, const GemmArgs& g_in, int splitk) {
   GemmArgs g = g_in;
   static bool attr_set = false;
   if (!attr_set) {
-    WMRL_CUDA_OK(cudaFuncSetAttribute(tf32x3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      TG_SMEM_BYTES));
+    WMRL_CUDA_OK(cudaFuncSetAttribute(tf32x3_gemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      2 * TG_STAGE_BYTES));
     attr_set = true;
   }
   const int K = g.K1 + g.K2;
@@ -355,17 +367,19 @@ int tf32x3_gemm_launch(cudaStream_t st, const GemmArgs& g_in, int splitk) {
   splitk = (K + kper - 1) / kper;
   if (splitk < 1) splitk = 1;
   g.kper = kper;
-  // column tiles: as few as possible, but narrow them (>= 64 wide) while the grid under-fills the GPU
+  // Column tiles: as few as possible, narrowed (>= 32 wide) until there are two CTAs per SM.  (A one-CTA-per-SM
+  // instantiation with three k-blocks of loads in flight, <3, 4>, was measured 1.5x slower at 2 500 rows: the
+  // staging is throughput-bound, not latency-bound, and a second resident CTA overlaps it better.)
   const int mt = (g.M + TG_BM - 1) / TG_BM;
   int nt = (g.N + 255) / 256;
-  while ((long long)mt * nt * splitk < 148 && (g.N + nt) / (nt + 1) >= 64) ++nt;
+  while ((long long)mt * nt * splitk < 296 && (g.N + nt) / (nt + 1) >= 32) ++nt;
   int BN = ((g.N + nt - 1) / nt + 15) / 16 * 16;
   if (BN < 16) BN = 16;
   nt = (g.N + BN - 1) / BN;
   int tmem_cols = 32;
   while (tmem_cols < BN) tmem_cols *= 2;
   dim3 grid(nt, mt, splitk);
-  tf32x3_gemm_kernel<<<grid, TG_BLOCK, TG_SMEM_BYTES, st>>>(g, BN, tmem_cols);
+  tf32x3_gemm_kernel<1, 2><<<grid, TG_BLOCK, 2 * TG_STAGE_BYTES, st>>>(g, BN, tmem_cols);
   WMRL_CUDA_OK(cudaGetLastError());
   return 0;
 }
