@@ -218,6 +218,18 @@ WMRL_API int wmrl_linear_dgrad(int32_t M, int32_t N, int32_t K, const float* dY,
 WMRL_API int wmrl_linear_wgrad(int32_t M, int32_t N, int32_t K, const float* dY, int64_t lddy, const float* X,
                       int64_t ldx, float* dW, void* stream);
 
+/*
+ * Fused LayerNorm (eps 1e-5, affine) + activation over rows, the block that follows every hidden Linear
+ * of the actor (actor.py:27-36, ELU) and of the heads next to the path (models.py:3-37 SiLU,
+ * trainers/value/critic.py:4-29 ReLU).  act: 0 ELU, 1 SiLU, 2 ReLU.  x, xhat, y, dy, dx: [M][W] contiguous;
+ * rstd: [M].  fwd stores xhat and rstd for the backward; bwd ADDS into dgamma / dbeta (either may be NULL).
+ */
+WMRL_API int wmrl_ln_act_fwd(int32_t M, int32_t W, const float* x, const float* gamma, const float* beta, int32_t act,
+                    float* xhat, float* rstd, float* y, void* stream);
+WMRL_API int wmrl_ln_act_bwd(int32_t M, int32_t W, const float* dy, const float* xhat, const float* rstd,
+                    const float* gamma, const float* beta, int32_t act, float* dx, float* dgamma, float* dbeta,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,47 @@ def lambda_case(B, H):
     return dict(case=f"lambda-return fwd+bwd B={B} H={H}", gpu_ms=ms, cpu_ms=cms, cpu_rows=B, precision="fp32", bwd=True,
                 gpu_latent_steps_per_s=B * H / ms * 1e3, cpu_latent_steps_per_s=B * H / cms * 1e3)
 
+def actor_update_case(name, variant, B, H, D, S, C, Hd, A=6, Ha=512, La=3):
+    """The composition pinned by the reference's test_value_rssm.py: imagine from B start states,
+    reward / done / target-critic heads on the features, done mask, lambda-return, actor loss = -mean(target),
+    backward into the actor.  GPU: wmrl modules end to end.  CPU: oracle rollout + the same torch heads +
+    the reference's nested-loop lambda-return (oracle) under autograd."""
+    import copy
+    rssm, actor = HG.build_modules(variant, D, S, C, Hd, 64, A, Ha, La, seed=0)
+    S_in = S * (C if variant == "discrete" else 1)
+    F_ = D + S_in
+    torch.manual_seed(5)
+    reward = wmrl.DenseModel(3, F_, 256, 1).to(dev)
+    done = wmrl.DenseModel(3, F_, 256, 1, output_act=torch.nn.Sigmoid).to(dev)
+    critic = wmrl.ValueCritic(F_, 3, 512).to(dev)
+    heads = (reward, done, critic)
+    for m in (rssm,) + heads:
+        for p_ in m.parameters(): p_.requires_grad_(False)
+    d0, s0, nz = HG.synth_inputs(variant, B, H, D, S, C)
+    init = HG.init_state(rssm, d0, s0)
+    nzd = nz.to(dev)
+    from wmrl.functional import lambda_return, done_mask
+    def gpu():
+        actor.zero_grad(set_to_none=True)
+        feat = rssm.imagine_rollout(init, actor, H, noise=nzd).get_features()
+        r, dn, v = reward(feat), done(feat), critic(feat)
+        tgt = lambda_return(v, r, done_mask(dn.detach()), 0.99, 0.95)
+        (-tgt.mean()).backward()
+    ms = timeit(gpu)
+    w, aw = HG.cpu_weights(rssm), HG.cpu_weights(actor)
+    cheads = [copy.deepcopy(m).cpu() for m in heads]
+    Bc = min(B, 2500)
+    def cpu():
+        for v_ in aw.values(): v_.requires_grad_(True); v_.grad = None
+        ro = O.imagine_rollout(variant, w, aw, d0[:Bc], s0[:Bc], nz[:, :Bc], H, S, C)
+        feat = torch.cat([ro["deter"], ro["stoch"]], -1)
+        r, dn, v = (m(feat) for m in cheads)
+        tgt = O.lambda_return_loops(v, r, O.done_preprocess(dn.detach()), 0.99, 0.95)
+        (-tgt.mean()).backward()
+    cms = cpu_time(cpu, n=1)
+    return dict(case=name, gpu_ms=ms, gpu_latent_steps_per_s=B * H / ms * 1e3, cpu_ms=cms, cpu_rows=Bc,
+                cpu_latent_steps_per_s=Bc * H / cms * 1e3, precision="fp32", bwd=True)
+
 torch.set_num_threads(os.cpu_count())
 rows = [
     imagine_case("C1 continuous D200/S30 B=2500 H=15 fwd fp32", "continuous", 2500, 15, 200, 30, 1, 200),
@@ -103,13 +144,15 @@ rows = [
     imagine_case("C1 continuous B=2500 H=15 fwd+bwd fp32", "continuous", 2500, 15, 200, 30, 1, 200, bwd=True),
     imagine_case("C2 discrete D600/32x32 B=2500 H=15 fwd fp32", "discrete", 2500, 15, 600, 32, 32, 600),
     imagine_case("C2 discrete B=2500 H=15 fwd+bwd (actor BPTT) fp32", "discrete", 2500, 15, 600, 32, 32, 600, bwd=True),
+    actor_update_case("C1 actor-update step (rollout+heads+lambda-return+bwd) B=2500", "continuous", 2500, 15, 200, 30, 1, 200),
+    actor_update_case("C2 actor-update step (rollout+heads+lambda-return+bwd) B=2500", "discrete", 2500, 15, 600, 32, 32, 600),
     observe_case("C3 discrete observe B=50 T=51 E=1024 fwd fp32", "discrete", 50, 51, 600, 32, 32, 600),
     observe_case("C3 discrete observe B=50 T=51 fwd+bwd fp32", "discrete", 50, 51, 600, 32, 32, 600, bwd=True),
     imagine_case("C4 continuous B=65536 H=15 fwd bf16-tcgen05", "continuous", 65536, 15, 200, 30, 1, 200, precision="bf16"),
     imagine_case("C4 continuous B=65536 H=15 fwd fp32", "continuous", 65536, 15, 200, 30, 1, 200),
     lambda_case(2500, 15), lambda_case(2500, 64),
 ]
-print(f"{'case':58s} {'GPU ms':>9s} {'GPU steps/s':>12s} {'CPU ms':>9s} {'CPU steps/s':>12s} (CPU: oracle, {os.cpu_count()} threads)")
+print(f"{'case':66s} {'GPU ms':>9s} {'GPU steps/s':>12s} {'CPU ms':>9s} {'CPU steps/s':>12s} (CPU: oracle, {os.cpu_count()} threads)")
 for r in rows:
-    print(f"{r['case']:58s} {r['gpu_ms']:9.3f} {r['gpu_latent_steps_per_s']:12.3e} {r['cpu_ms']:9.1f} {r['cpu_latent_steps_per_s']:12.3e}")
+    print(f"{r['case']:66s} {r['gpu_ms']:9.3f} {r['gpu_latent_steps_per_s']:12.3e} {r['cpu_ms']:9.1f} {r['cpu_latent_steps_per_s']:12.3e}")
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "configs_r1.json"), "w"), indent=1)

@@ -375,8 +375,24 @@ __global__ void combine_kernel(const float* a, long long lda, const float* c, lo
   }
 }
 
-// LayerNorm(eps 1e-5, affine) + ELU, one warp per row (actor.py:27-36).
-__global__ void ln_elu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gam,
+// LayerNorm(eps 1e-5, affine) + activation, one warp per row (actor.py:27-36 with ELU; the heads next to
+// the path use SiLU - models.py:3-37 - and ReLU - trainers/value/critic.py:4-29).
+// kAct: 0 ELU, 1 SiLU, 2 ReLU.
+template <int kAct>
+__device__ __forceinline__ float act_f(float z) {
+  if (kAct == 0) return z > 0.f ? z : expm1f(z);
+  if (kAct == 1) return z / (1.f + expf(-z));
+  return fmaxf(z, 0.f);
+}
+template <int kAct>
+__device__ __forceinline__ float dact_f(float z) {
+  if (kAct == 0) return z > 0.f ? 1.f : expf(z);
+  if (kAct == 1) { const float sg = 1.f / (1.f + expf(-z)); return sg * (1.f + z * (1.f - sg)); }
+  return z > 0.f ? 1.f : 0.f;
+}
+
+template <int kAct>
+__global__ void ln_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gam,
                                   const float* __restrict__ bet, float* __restrict__ xhat,
                                   float* __restrict__ rstd, float* __restrict__ y, int Bn, int W) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -392,12 +408,16 @@ __global__ void ln_elu_fwd_kernel(const float* __restrict__ x, const float* __re
   for (int j = lane; j < W; j += 32) {
     const float xh = (xr[j] - mean) * rs;
     xhat[(long long)warp * W + j] = xh;
-    y[(long long)warp * W + j] = elu_f(xh * gam[j] + bet[j]);
+    y[(long long)warp * W + j] = act_f<kAct>(xh * gam[j] + bet[j]);
   }
 }
 
-// Backward of the block above: dy -> dx, and per-column dgamma / dbeta (atomics).
-__global__ void ln_elu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ xhat,
+// Backward of the block above: dy -> dx, and per-column dgamma / dbeta.  A lane always handles the same
+// columns (lane, lane+32, ...), so for W <= 32*kLnCols it keeps their gamma / beta and the running column
+// sums in registers over all the rows its warp walks and adds once at the end (shared, then global).
+constexpr int kLnCols = 16;
+template <int kAct, bool kRegs>
+__global__ void ln_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ xhat,
                                   const float* __restrict__ rstd, const float* __restrict__ gam,
                                   const float* __restrict__ bet, float* __restrict__ dx,
                                   float* dgam, float* dbet, int Bn, int W) {
@@ -407,27 +427,69 @@ __global__ void ln_elu_bwd_kernel(const float* __restrict__ dy, const float* __r
   for (int j = threadIdx.x; j < 2 * W; j += blockDim.x) sm[j] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float g_r[kLnCols], b_r[kLnCols], ag[kLnCols], ab[kLnCols];
+  if (kRegs) {
+#pragma unroll
+    for (int i = 0; i < kLnCols; ++i) {
+      const int j = lane + 32 * i;
+      g_r[i] = j < W ? gam[j] : 0.f;
+      b_r[i] = j < W ? bet[j] : 0.f;
+      ag[i] = 0.f; ab[i] = 0.f;
+    }
+  }
   for (int row = blockIdx.x * wpb + wib; row < Bn; row += gridDim.x * wpb) {
     const long long o = (long long)row * W;
     const float rs = rstd[row];
     float s1 = 0.f, s2 = 0.f;
-    for (int j = lane; j < W; j += 32) {
-      const float xh = xhat[o + j];
-      const float z = xh * gam[j] + bet[j];
-      const float dz = dy[o + j] * (z > 0.f ? 1.f : expf(z));
-      const float dxh = dz * gam[j];
-      s1 += dxh;
-      s2 += dxh * xh;
-      if (dgam) atomicAdd(&sg[j], dz * xh);
-      if (dbet) atomicAdd(&sb[j], dz);
+    if (kRegs) {
+      float dzv[kLnCols], xhv[kLnCols];
+#pragma unroll
+      for (int i = 0; i < kLnCols; ++i) {
+        const int j = lane + 32 * i;
+        const bool ok = j < W;
+        const float xh = ok ? xhat[o + j] : 0.f;
+        const float dz = ok ? dy[o + j] * dact_f<kAct>(xh * g_r[i] + b_r[i]) : 0.f;
+        xhv[i] = xh; dzv[i] = dz;
+        const float dxh = dz * g_r[i];
+        s1 += dxh;
+        s2 += dxh * xh;
+        ag[i] += dz * xh;
+        ab[i] += dz;
+      }
+      s1 = warp_sum(s1) / W;
+      s2 = warp_sum(s2) / W;
+#pragma unroll
+      for (int i = 0; i < kLnCols; ++i) {
+        const int j = lane + 32 * i;
+        if (j < W) dx[o + j] = rs * (dzv[i] * g_r[i] - s1 - xhv[i] * s2);
+      }
+    } else {
+      for (int j = lane; j < W; j += 32) {
+        const float xh = xhat[o + j];
+        const float dz = dy[o + j] * dact_f<kAct>(xh * gam[j] + bet[j]);
+        const float dxh = dz * gam[j];
+        s1 += dxh;
+        s2 += dxh * xh;
+        if (dgam) atomicAdd(&sg[j], dz * xh);
+        if (dbet) atomicAdd(&sb[j], dz);
+      }
+      s1 = warp_sum(s1) / W;
+      s2 = warp_sum(s2) / W;
+      for (int j = lane; j < W; j += 32) {
+        const float xh = xhat[o + j];
+        const float dz = dy[o + j] * dact_f<kAct>(xh * gam[j] + bet[j]);
+        dx[o + j] = rs * (dz * gam[j] - s1 - xh * s2);
+      }
     }
-    s1 = warp_sum(s1) / W;
-    s2 = warp_sum(s2) / W;
-    for (int j = lane; j < W; j += 32) {
-      const float xh = xhat[o + j];
-      const float z = xh * gam[j] + bet[j];
-      const float dz = dy[o + j] * (z > 0.f ? 1.f : expf(z));
-      dx[o + j] = rs * (dz * gam[j] - s1 - xh * s2);
+  }
+  if (kRegs) {
+#pragma unroll
+    for (int i = 0; i < kLnCols; ++i) {
+      const int j = lane + 32 * i;
+      if (j < W) {
+        if (dgam) atomicAdd(&sg[j], ag[i]);
+        if (dbet) atomicAdd(&sb[j], ab[i]);
+      }
     }
   }
   __syncthreads();
@@ -435,6 +497,33 @@ __global__ void ln_elu_bwd_kernel(const float* __restrict__ dy, const float* __r
     if (dgam) atomicAdd(&dgam[j], sg[j]);
     if (dbet) atomicAdd(&dbet[j], sb[j]);
   }
+}
+
+static int ln_act_fwd(cudaStream_t st, int act, const float* x, const float* gam, const float* bet, float* xhat,
+                      float* rstd, float* y, int Bn, int W) {
+  if (Bn <= 0) return 0;
+  const int nb = (int)(((long long)Bn * 32 + 255) / 256);
+  if (act == 0) ln_act_fwd_kernel<0><<<nb, 256, 0, st>>>(x, gam, bet, xhat, rstd, y, Bn, W);
+  else if (act == 1) ln_act_fwd_kernel<1><<<nb, 256, 0, st>>>(x, gam, bet, xhat, rstd, y, Bn, W);
+  else ln_act_fwd_kernel<2><<<nb, 256, 0, st>>>(x, gam, bet, xhat, rstd, y, Bn, W);
+  WMRL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static int ln_act_bwd(cudaStream_t st, int act, const float* dy, const float* xhat, const float* rstd,
+                      const float* gam, const float* bet, float* dx, float* dgam, float* dbet, int Bn, int W) {
+  if (Bn <= 0) return 0;
+  int nb = (Bn + 7) / 8;              // one row per warp until the GPU is full (4 blocks per SM), then warps loop
+  if (nb > 592) nb = 592;             // and the register column sums start to pay off
+  if (nb < 1) nb = 1;
+  const size_t sh = 2 * (size_t)W * sizeof(float);
+  const bool regs = W <= 32 * kLnCols;
+#define WMRL_LN_BWD(A, R) ln_act_bwd_kernel<A, R><<<nb, 256, sh, st>>>(dy, xhat, rstd, gam, bet, dx, dgam, dbet, Bn, W)
+  if (act == 0) { if (regs) WMRL_LN_BWD(0, true); else WMRL_LN_BWD(0, false); }
+  else if (act == 1) { if (regs) WMRL_LN_BWD(1, true); else WMRL_LN_BWD(1, false); }
+  else { if (regs) WMRL_LN_BWD(2, true); else WMRL_LN_BWD(2, false); }
+#undef WMRL_LN_BWD
+  WMRL_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 // a = tanh(mu/scale)*bound  (actor.py:50); th saved for the backward.
@@ -877,9 +966,7 @@ int f32_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_p
         TRY(linear(st, h_t, ldD, d.D, s_t, ldS, d.S_in, aw->lin_w[0], aw->lin_b[0], tmp, d.Ha, B, d.Ha, 0));
       else
         TRY(linear(st, sv.y[l - 1], d.Ha, d.Ha, nullptr, 0, 0, aw->lin_w[l], aw->lin_b[l], tmp, d.Ha, B, d.Ha, 0));
-      ln_elu_fwd_kernel<<<blocks_for((long long)B * 32), 256, 0, st>>>(tmp, aw->ln_g[l], aw->ln_b[l],
-                                                                       sv.xhat[l], sv.rstd[l], sv.y[l], B, d.Ha);
-      WMRL_CUDA_OK(cudaGetLastError());
+      TRY(ln_act_fwd(st, 0, tmp, aw->ln_g[l], aw->ln_b[l], sv.xhat[l], sv.rstd[l], sv.y[l], B, d.Ha));
     }
     TRY(linear(st, sv.y[d.La - 1], d.Ha, d.Ha, nullptr, 0, 0, aw->mu_w, aw->mu_b, mu, d.A, B, d.A, 0));
     tanh_squash_kernel<<<blocks_for((long long)B * d.A), 256, 0, st>>>(mu, aw->bound, d.action_scale,
@@ -956,11 +1043,8 @@ int f32_imagine_bwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_p
     TRY(bgrad(st, g_mu, d.A, B, d.A, gaw->mu_b));
     TRY(dgrad(st, g_mu, d.A, d.A, aw->mu_w, d.Ha, 0, d.Ha, g_y, d.Ha, B, 0));
     for (int l = d.La - 1; l >= 0; --l) {
-      int nb = (B + 7) / 8;
-      if (nb > 592) nb = 592;
-      ln_elu_bwd_kernel<<<nb, 256, 2 * d.Ha * sizeof(float), st>>>(
-          g_y, sv.xhat[l], sv.rstd[l], aw->ln_g[l], aw->ln_b[l], g_lin, gaw->ln_g[l], gaw->ln_b[l], B, d.Ha);
-      WMRL_CUDA_OK(cudaGetLastError());
+      TRY(ln_act_bwd(st, 0, g_y, sv.xhat[l], sv.rstd[l], aw->ln_g[l], aw->ln_b[l], g_lin, gaw->ln_g[l], gaw->ln_b[l], B,
+                     d.Ha));
       if (l == 0) {
         TRY(wgrad(st, g_lin, d.Ha, d.Ha, h_t, ldD, d.D, gaw->lin_w[0], d.F, 0, B));
         TRY(wgrad(st, g_lin, d.Ha, d.Ha, s_t, ldS, d.S_in, gaw->lin_w[0], d.F, d.D, B));
@@ -1174,6 +1258,23 @@ int wmrl_done_mask(const float* dones, int32_t B, int32_t H, float* out, void* s
   wmrl::done_mask_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dones, B, H, out);
   WMRL_CUDA_OK(cudaGetLastError());
   return 0;
+}
+int wmrl_ln_act_fwd(int32_t M, int32_t W, const float* x, const float* gamma, const float* beta, int32_t act,
+                    float* xhat, float* rstd, float* y, void* stream) {
+  WMRL_REQUIRE(M >= 0 && W > 0, "ln_act_fwd: bad shape");
+  WMRL_REQUIRE(act >= 0 && act <= 2, "ln_act_fwd: act must be 0 (ELU), 1 (SiLU) or 2 (ReLU)");
+  if (M == 0) return 0;
+  WMRL_REQUIRE(x && gamma && beta && xhat && rstd && y, "ln_act_fwd: NULL tensor");
+  return wmrl::ln_act_fwd((cudaStream_t)stream, act, x, gamma, beta, xhat, rstd, y, M, W);
+}
+int wmrl_ln_act_bwd(int32_t M, int32_t W, const float* dy, const float* xhat, const float* rstd,
+                    const float* gamma, const float* beta, int32_t act, float* dx, float* dgamma, float* dbeta,
+                    void* stream) {
+  WMRL_REQUIRE(M >= 0 && W > 0, "ln_act_bwd: bad shape");
+  WMRL_REQUIRE(act >= 0 && act <= 2, "ln_act_bwd: act must be 0 (ELU), 1 (SiLU) or 2 (ReLU)");
+  if (M == 0) return 0;
+  WMRL_REQUIRE(dy && xhat && rstd && gamma && beta && dx, "ln_act_bwd: NULL tensor");
+  return wmrl::ln_act_bwd((cudaStream_t)stream, act, dy, xhat, rstd, gamma, beta, dx, dgamma, dbeta, M, W);
 }
 int wmrl_linear_fwd(int32_t M, int32_t N, int32_t K, const float* X, int64_t ldx, const float* W,
                     const float* bias, float* Y, int64_t ldy, int32_t act, void* stream) {

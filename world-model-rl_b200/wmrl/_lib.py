@@ -82,6 +82,8 @@ _SIGNATURES = {
     "wmrl_linear_fwd": (C.c_int, [C.c_int32] * 3 + [_P, C.c_int64, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "wmrl_linear_dgrad": (C.c_int, [C.c_int32] * 3 + [_P, C.c_int64, _P, _P, C.c_int64, C.c_int32, _P]),
     "wmrl_linear_wgrad": (C.c_int, [C.c_int32] * 3 + [_P, C.c_int64, _P, C.c_int64, _P, _P]),
+    "wmrl_ln_act_fwd": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    "wmrl_ln_act_bwd": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -486,3 +486,80 @@ class LinearFn(torch.autograd.Function):
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0) -> torch.Tensor:
     """Drop-in for ``torch.nn.functional.linear`` (optionally fused ELU) on libwmrl's kernels."""
     return LinearFn.apply(x, weight, bias, act)
+
+
+# ----------------------------------------------------------------------------
+# fused LayerNorm + activation (the block after every hidden Linear of the actor and the MLP heads)
+# ----------------------------------------------------------------------------
+ACT_ELU, ACT_SILU, ACT_RELU = 0, 1, 2
+
+
+class LayerNormAct(torch.autograd.Function):
+    """y = act(LayerNorm(x) * gamma + beta), eps 1e-5, over the last dim; act: 0 ELU, 1 SiLU, 2 ReLU
+    (actor.py:27-36, models.py:3-37, trainers/value/critic.py:4-29)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, act: int):
+        lib = _lib.load()
+        dev = _require_cuda(x, gamma, beta)
+        x2 = _f32c(x.reshape(-1, x.shape[-1]))
+        g, b = _f32c(gamma), _f32c(beta)
+        M, W = x2.shape
+        xhat, y = torch.empty_like(x2), torch.empty_like(x2)
+        rstd = torch.empty(M, device=dev)
+        if M > 0:
+            _lib.check(lib.wmrl_ln_act_fwd(M, W, x2.data_ptr(), g.data_ptr(), b.data_ptr(), int(act), xhat.data_ptr(),
+                                           rstd.data_ptr(), y.data_ptr(), _stream_ptr(dev)), "wmrl_ln_act_fwd")
+        ctx.save_for_backward(xhat, rstd, g, b)
+        ctx.act, ctx.x_shape = int(act), x.shape
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, g_y):
+        lib = _lib.load()
+        xhat, rstd, g, b = ctx.saved_tensors
+        M, W = xhat.shape
+        dy = _f32c(g_y.reshape(M, W))
+        dev = dy.device
+        dx = torch.empty_like(xhat)
+        need_p = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dg = torch.zeros(W, device=dev) if need_p else None
+        db = torch.zeros(W, device=dev) if need_p else None
+        if M > 0:
+            _lib.check(lib.wmrl_ln_act_bwd(M, W, dy.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), g.data_ptr(),
+                                           b.data_ptr(), ctx.act, dx.data_ptr(), _lib.ptr(dg), _lib.ptr(db),
+                                           _stream_ptr(dev)), "wmrl_ln_act_bwd")
+        return (dx.reshape(ctx.x_shape) if ctx.needs_input_grad[0] else None,
+                dg if ctx.needs_input_grad[1] else None, db if ctx.needs_input_grad[2] else None, None)
+
+
+def layer_norm_act(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, act: int) -> torch.Tensor:
+    return LayerNormAct.apply(x, gamma, beta, act)
+
+
+def mlp_forward(seq: "torch.nn.Sequential", x: torch.Tensor) -> torch.Tensor:
+    """Run an ``nn.Sequential`` of the reference's head pattern - [Linear, LayerNorm, act] x depth, Linear -
+    on libwmrl's kernels (3xTF32 tensor-core GEMM + fused LayerNorm/activation) when ``x`` is a CUDA fp32
+    tensor; any other layer, dtype or device runs the torch module itself.  Parameters stay in the module,
+    so checkpoints and optimisers are untouched."""
+    nn = torch.nn
+    acts = {nn.ELU: ACT_ELU, nn.SiLU: ACT_SILU, nn.ReLU: ACT_RELU}
+    mods = list(seq)
+    native = x.is_cuda and x.dtype == torch.float32
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if native and isinstance(m, nn.Linear):
+            x = linear(x, m.weight, m.bias, 0)
+            nxt, nxt2 = (mods[i + 1] if i + 1 < len(mods) else None), (mods[i + 2] if i + 2 < len(mods) else None)
+            if (isinstance(nxt, nn.LayerNorm) and nxt.elementwise_affine and abs(nxt.eps - 1e-5) < 1e-12
+                    and len(nxt.normalized_shape) == 1 and type(nxt2) in acts
+                    and not (isinstance(nxt2, nn.ELU) and nxt2.alpha != 1.0)):
+                x = layer_norm_act(x, nxt.weight, nxt.bias, acts[type(nxt2)])
+                i += 3
+                continue
+            i += 1
+            continue
+        x = m(x)
+        i += 1
+    return x

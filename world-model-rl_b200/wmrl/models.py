@@ -1,11 +1,15 @@
-"""Adjacent MLP heads kept in plain torch (cuBLAS): ``DenseModel`` (reward /
-done / state enc-dec heads, rssm_world_model/models.py:3-37) and ``ValueCritic``
-(trainers/value/critic.py:4-29).  They consume the ``features[B,H,F]`` the
-native rollout returns; fusing them onto it is SURVEY.md §8(f) rank 1."""
+"""The MLP heads next to the path: ``DenseModel`` (reward / done / state enc-dec heads,
+rssm_world_model/models.py:3-37) and ``ValueCritic`` (trainers/value/critic.py:4-29).  They consume the
+``features[B,H,F]`` the native rollout returns.  Same constructor arguments, module tree and ``state_dict``
+keys as the reference; on CUDA fp32 inputs their Linear / LayerNorm+activation blocks run on libwmrl's kernels
+(``wmrl.functional.mlp_forward``: 3xTF32 tcgen05 GEMM, fused LayerNorm+SiLU/ReLU, forward and backward) -
+the first step of SURVEY.md §8(f) rank 1 (fusing them onto the rollout itself comes next)."""
 from __future__ import annotations
 
 import torch
 from torch import nn
+
+from .functional import mlp_forward
 
 
 def _mlp(in_dim, hidden, depth, out_dim, act, layernorm=True):
@@ -28,7 +32,7 @@ class DenseModel(nn.Module):
         self.output_act = output_act()
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
-        return self.output_act(self.fc(z))
+        return self.output_act(mlp_forward(self.fc, z))
 
 
 class ValueCritic(nn.Module):
@@ -38,4 +42,4 @@ class ValueCritic(nn.Module):
         self.layers = _mlp(state_dim, hidden_dim, num_layers, 1, nn.ReLU, True)
 
     def forward(self, x):
-        return self.layers(x)
+        return mlp_forward(self.layers, x)
