@@ -417,7 +417,7 @@ __global__ void ln_act_fwd_kernel(const float* __restrict__ x, const float* __re
 // sums in registers over all the rows its warp walks and adds once at the end (shared, then global).
 constexpr int kLnCols = 16;
 template <int kAct, bool kRegs>
-__global__ void ln_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ xhat,
+__global__ void __launch_bounds__(256, 2) ln_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ xhat,
                                   const float* __restrict__ rstd, const float* __restrict__ gam,
                                   const float* __restrict__ bet, float* __restrict__ dx,
                                   float* dgam, float* dbet, int Bn, int W) {
@@ -442,26 +442,29 @@ __global__ void ln_act_bwd_kernel(const float* __restrict__ dy, const float* __r
     const float rs = rstd[row];
     float s1 = 0.f, s2 = 0.f;
     if (kRegs) {
-      float dzv[kLnCols], xhv[kLnCols];
 #pragma unroll
       for (int i = 0; i < kLnCols; ++i) {
         const int j = lane + 32 * i;
-        const bool ok = j < W;
-        const float xh = ok ? xhat[o + j] : 0.f;
-        const float dz = ok ? dy[o + j] * dact_f<kAct>(xh * g_r[i] + b_r[i]) : 0.f;
-        xhv[i] = xh; dzv[i] = dz;
-        const float dxh = dz * g_r[i];
-        s1 += dxh;
-        s2 += dxh * xh;
-        ag[i] += dz * xh;
-        ab[i] += dz;
+        if (j < W) {
+          const float xh = xhat[o + j];
+          const float dz = dy[o + j] * dact_f<kAct>(xh * g_r[i] + b_r[i]);
+          const float dxh = dz * g_r[i];
+          s1 += dxh;
+          s2 += dxh * xh;
+          ag[i] += dz * xh;
+          ab[i] += dz;
+        }
       }
       s1 = warp_sum(s1) / W;
       s2 = warp_sum(s2) / W;
 #pragma unroll
       for (int i = 0; i < kLnCols; ++i) {
         const int j = lane + 32 * i;
-        if (j < W) dx[o + j] = rs * (dzv[i] * g_r[i] - s1 - xhv[i] * s2);
+        if (j < W) {
+          const float xh = xhat[o + j];
+          const float dz = dy[o + j] * dact_f<kAct>(xh * g_r[i] + b_r[i]);
+          dx[o + j] = rs * (dz * g_r[i] - s1 - xh * s2);
+        }
       }
     } else {
       for (int j = lane; j < W; j += 32) {
@@ -516,7 +519,7 @@ static int ln_act_bwd(cudaStream_t st, int act, const float* dy, const float* xh
   if (nb > 592) nb = 592;             // and the register column sums start to pay off
   if (nb < 1) nb = 1;
   const size_t sh = 2 * (size_t)W * sizeof(float);
-  const bool regs = W <= 32 * kLnCols;
+  const bool regs = W <= 32 * kLnCols && Bn >= 4 * 592 * 8;   // only when a warp walks >= 4 rows
 #define WMRL_LN_BWD(A, R) ln_act_bwd_kernel<A, R><<<nb, 256, sh, st>>>(dy, xhat, rstd, gam, bet, dx, dgam, dbet, Bn, W)
   if (act == 0) { if (regs) WMRL_LN_BWD(0, true); else WMRL_LN_BWD(0, false); }
   else if (act == 1) { if (regs) WMRL_LN_BWD(1, true); else WMRL_LN_BWD(1, false); }
