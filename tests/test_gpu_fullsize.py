@@ -1,0 +1,146 @@
+"""BASELINE.json's FULL sizes, checked through size-independent properties of the domain (the oracle cannot
+run 65 536 x 15 in seconds) plus oracle agreement on sampled rows:
+
+* rows are independent (no cross-sample op on the path: LayerNorm is per row, softmax per group), so the rollout
+  of a slice of the batch must be BIT-IDENTICAL to the same rows inside the full-batch rollout, wherever the
+  slice falls relative to the kernels' 64/128-row tiles;
+* invariants: index 0 of every sequence is the given start state, std >= 0.1 (softplus + 0.1, rssm.py:180),
+  |h| <= 1 (GRU convex combination of tanh and the previous h), |a| <= bound, categorical samples are exact
+  one-hot rows, everything finite;
+* the first step of sampled rows against the oracle within the stated tolerance (bf16: rtol 1e-2 + 5e-3;
+  fp32: 1e-5 + 2e-5), later steps only through the invariants (trajectories are chaotic);
+* lambda-return: linear in (V, r) for a fixed mask, oracle agreement on sampled rows.
+"""
+import pytest
+import torch
+
+from oracle import rssm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _finite(*ts):
+    return all(bool(torch.isfinite(t).all()) for t in ts)
+
+
+def test_c4_bf16_65536x15_properties():
+    """configs[3] top point on the fused tcgen05 kernel (the bench workload)."""
+    import helpers_gpu as HG
+    from wmrl import _lib
+    if not _lib.load().wmrl_device_supports_bf16():
+        pytest.skip("not an sm_100 device")
+    B, H, D, S, Hd, A = 65536, 15, 200, 30, 200, 6
+    rssm, actor = HG.build_modules("continuous", D, S, 1, Hd, 64, A, 512, 3, seed=0, precision="bf16")
+    d0, s0, nz = HG.synth_inputs("continuous", B, H, D, S, 1)
+    init = HG.init_state(rssm, d0, s0)
+    nzd = nz.cuda()
+    with torch.no_grad():
+        seq, act = rssm.imagine_rollout(init, actor, H, noise=nzd, return_actions=True)
+    assert seq.deter_states.shape == (B, H + 1, D) and seq.stoch_states.shape == (B, H + 1, S) and act.shape == (B, H, A)
+    assert _finite(seq.deter_states, seq.stoch_states, seq.means, seq.stds, act)
+    assert torch.equal(seq.deter_states[:, 0].cpu(), d0) and torch.equal(seq.stoch_states[:, 0].cpu(), s0)
+    assert float(seq.stds[:, 1:].min()) >= 0.1 and float(seq.deter_states.abs().max()) <= 1.0
+    assert float(act.abs().max()) <= 1.0
+    # reparameterisation identity on the stored fields: stoch = mean + std * eps (fp32 epilogue math)
+    recon = seq.means[:, 1:] + seq.stds[:, 1:] * nzd.permute(1, 0, 2)
+    torch.testing.assert_close(seq.stoch_states[:, 1:], recon, rtol=1e-5, atol=1e-5)
+    # batch-split bit-exactness: slices at awkward offsets / lengths relative to the 64- and 128-row tiles
+    for lo, n in [(0, 128), (12345, 300), (65536 - 77, 77), (40000, 1)]:
+        sub = HG.init_state(rssm, d0[lo:lo + n], s0[lo:lo + n])
+        with torch.no_grad():
+            s2, a2 = rssm.imagine_rollout(sub, actor, H, noise=nzd[:, lo:lo + n].contiguous(), return_actions=True)
+        assert torch.equal(s2.deter_states, seq.deter_states[lo:lo + n]), f"deter rows {lo}+{n}"
+        assert torch.equal(s2.stoch_states, seq.stoch_states[lo:lo + n]) and torch.equal(a2, act[lo:lo + n])
+    # first step of 512 sampled rows vs the oracle
+    idx = torch.randperm(B, generator=torch.Generator().manual_seed(1))[:512]
+    w, aw = HG.cpu_weights(rssm), HG.cpu_weights(actor)
+    with torch.no_grad():
+        ref = O.imagine_rollout("continuous", w, aw, d0[idx], s0[idx], nz[:1, idx], 1, S)
+    for name, got, r in [("deter", seq.deter_states[idx, 1], ref["deter"][:, 0]), ("mean", seq.means[idx, 1], ref["mean"][:, 0]),
+                         ("std", seq.stds[idx, 1], ref["std"][:, 0]), ("action", act[idx, 0], ref["actions"][:, 0])]:
+        err = (got.cpu() - r).abs()
+        assert bool((err <= 1e-2 * r.abs() + 5e-3).all()), f"{name}: max err {float(err.max()):.3e}"
+
+
+def test_c2_discrete_2500x15_fp32_properties():
+    """configs[1] forward on the fp32 path (3xTF32 tensor-core GEMMs)."""
+    import helpers_gpu as HG
+    B, H, D, S, C, Hd, A = 2500, 15, 600, 32, 32, 600, 6
+    rssm, actor = HG.build_modules("discrete", D, S, C, Hd, 64, A, 512, 3, seed=0)
+    d0, s0, nz = HG.synth_inputs("discrete", B, H, D, S, C)
+    init = HG.init_state(rssm, d0, s0)
+    nzd = nz.cuda()
+    with torch.no_grad():
+        seq, act = rssm.imagine_rollout(init, actor, H, noise=nzd, return_actions=True)
+    assert _finite(seq.deter_states, seq.logits, act)
+    oh = seq.stoch_states[:, 1:].reshape(B, H, C, S)
+    assert torch.equal(oh.sum(-1), torch.ones(B, H, C, device="cuda")) and bool(((oh == 0) | (oh == 1)).all())
+    assert float(seq.deter_states.abs().max()) <= 1.0 and float(act.abs().max()) <= 1.0
+    # the sampled class is argmax(softmax(logits) / q) (state/discrete.py:27-30 with the multinomial contract)
+    p = torch.softmax(seq.logits[:, 1:], -1)
+    want = (p / nzd.permute(1, 0, 2, 3)).argmax(-1)
+    got = oh.argmax(-1)
+    agree = float((want == got).float().mean())
+    assert agree > 0.9999, agree            # ties / 1-ulp differences in p only
+    for lo, n in [(0, 128), (1000, 129), (2500 - 40, 40)]:     # tensor-core tiles and the <= 64-row kernel
+        sub = HG.init_state(rssm, d0[lo:lo + n], s0[lo:lo + n])
+        with torch.no_grad():
+            s2 = rssm.imagine_rollout(sub, actor, 2, noise=nzd[:2, lo:lo + n].contiguous())
+        torch.testing.assert_close(s2.deter_states[:, 1], seq.deter_states[lo:lo + n, 1], rtol=1e-5, atol=2e-5)
+    idx = torch.arange(0, B, 25)
+    w, aw = HG.cpu_weights(rssm), HG.cpu_weights(actor)
+    with torch.no_grad():
+        ref = O.imagine_rollout("discrete", w, aw, d0[idx], s0[idx], nz[:1, idx], 1, S, C)
+    torch.testing.assert_close(seq.deter_states[idx, 1].cpu(), ref["deter"][:, 0], rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(seq.logits[idx, 1].cpu(), ref["logits"][:, 0], rtol=1e-5, atol=5e-5)
+
+
+def test_c3_observe_50x51_properties():
+    """configs[2] posterior filtering (E = 1024) on the cluster split-K GEMM."""
+    import helpers_gpu as HG
+    B, T, D, S, C, Hd, E, A = 50, 51, 600, 32, 32, 600, 1024, 6
+    rssm, _ = HG.build_modules("discrete", D, S, C, Hd, E, A, 64, 1, seed=0)
+    g = torch.Generator().manual_seed(0)
+    obs = torch.relu(torch.randn(B, T, E, generator=g))
+    act = torch.rand(B, T, A, generator=g) * 2 - 1
+    n1 = torch.empty(T - 1, B, C, S).exponential_(1.0, generator=g)
+    n2 = torch.empty(T - 1, B, C, S).exponential_(1.0, generator=g)
+    with torch.no_grad():
+        pri, post = rssm.observe_rollout(obs.cuda(), act.cuda(), noise=(n1.cuda(), n2.cuda()))
+    assert pri.deter_states.shape == (B, T, D) and post.stoch_states.shape == (B, T, S * C)
+    assert _finite(pri.deter_states, pri.logits, post.logits)
+    # the posterior reuses the prior's deterministic state (rssm.py:70-82); index 0 is the zero state
+    assert torch.equal(pri.deter_states, post.deter_states)
+    assert float(post.deter_states[:, 0].abs().max()) == 0.0
+    oh = post.stoch_states[:, 1:].reshape(B, T - 1, C, S)
+    assert torch.equal(oh.sum(-1), torch.ones(B, T - 1, C, device="cuda"))
+    # 2 450 start states for the imagination that follows (state/discrete.py:81-89)
+    assert post.flatten_batch_time().deter_state.shape == (B * (T - 1), D)
+    # first filtering step vs the oracle (later steps: invariants only)
+    w = HG.cpu_weights(rssm)
+    with torch.no_grad():
+        rpri, rpost = O.observe_rollout("discrete", w, obs[:, :2], act[:, :2], n1[:1], n2[:1], S, C)
+    torch.testing.assert_close(post.deter_states[:, 1].cpu(), rpost["deter"][:, 0], rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(post.logits[:, 1].cpu(), rpost["logits"][:, 0], rtol=1e-5, atol=5e-5)
+    torch.testing.assert_close(pri.logits[:, 1].cpu(), rpri["logits"][:, 0], rtol=1e-5, atol=5e-5)
+
+
+def test_lambda_return_65536x64_linearity_and_oracle():
+    from wmrl.functional import lambda_return, done_mask
+    B, H = 65536, 64
+    g = torch.Generator().manual_seed(4)
+    V1, V2, r1, r2 = (torch.randn(B, H, 1, generator=g).cuda() for _ in range(4))
+    d = done_mask((torch.rand(B, H, 1, generator=g) > 0.98).float().cuda())
+    assert bool(((d == 0) | (d == 1)).all()) and bool((d[:, 1:] >= d[:, :-1]).all())     # monotone 0/1 mask
+    t1, t2 = lambda_return(V1, r1, d, 0.99, 0.95), lambda_return(V2, r2, d, 0.99, 0.95)
+    t12 = lambda_return(2.0 * V1 - 0.5 * V2, 2.0 * r1 - 0.5 * r2, d, 0.99, 0.95)
+    torch.testing.assert_close(t12, 2.0 * t1 - 0.5 * t2, rtol=1e-4, atol=1e-4)
+    idx = torch.arange(0, B, 4096)
+    ref = O.lambda_return_loops(V1[idx].cpu(), r1[idx].cpu(), d[idx].cpu(), 0.99, 0.95)
+    torch.testing.assert_close(t1[idx].cpu(), ref, rtol=1e-5, atol=1e-5)
