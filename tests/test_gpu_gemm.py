@@ -79,3 +79,54 @@ def test_linear_strided_rows_and_empty():
     w = torch.randn(24, 40, device="cuda")
     torch.testing.assert_close(F.linear(x, w), x @ w.t(), rtol=1e-5, atol=1e-5)
     assert F.linear(torch.empty(0, 40, device="cuda"), w).shape == (0, 24)
+
+
+@pytest.mark.parametrize("M,N,K", [(129, 257, 17), (300, 40, 230), (64, 100, 300), (65, 16, 36), (2500, 600, 203), (1, 7, 129)])
+def test_linear_c_abi_strided_with_guard_bands(M, N, K):
+    """Through the C ABI with row strides larger than the logical widths (how the chain reads / writes the [B,T,.]
+    tensors in place) and NaN guard bands around the output: nothing outside Y[M,N] may be written, padding
+    columns of X and W must not be read into the result."""
+    import ctypes as C
+    from wmrl import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M * 3 + N * 5 + K)
+    ldx, ldy, pad_rows = K + 5, N + 9, 3
+    xbuf = torch.full((M, ldx), float("nan"), device="cuda")
+    x = torch.randn(M, K, generator=g).cuda()
+    xbuf[:, :K] = x
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    ybuf = torch.full((M + 2 * pad_rows, ldy), float("nan"), device="cuda")
+    y_ptr = ybuf.data_ptr() + pad_rows * ldy * 4
+    st = torch.cuda.current_stream().cuda_stream
+    for act in (0, 1):
+        ybuf.fill_(float("nan"))
+        rc = lib.wmrl_linear_fwd(M, N, K, xbuf.data_ptr(), ldx, w.data_ptr(), b.data_ptr(), y_ptr, ldy, act, st)
+        assert rc == 0, lib.wmrl_last_error()
+        torch.cuda.synchronize()
+        y = ybuf[pad_rows:pad_rows + M, :N]
+        ref = x.double() @ w.double().t() + b.double()
+        if act:
+            ref = torch.nn.functional.elu(ref)
+        torch.testing.assert_close(y.double(), ref, rtol=1e-4, atol=1e-4)
+        assert bool(torch.isnan(ybuf[:pad_rows]).all()) and bool(torch.isnan(ybuf[pad_rows + M:]).all()), "rows outside Y written"
+        assert bool(torch.isnan(ybuf[pad_rows:pad_rows + M, N:]).all()), "columns outside Y written"
+    # dgrad into a strided dX with guard bands, accumulate on top of existing values
+    dy = torch.randn(M, N, generator=g).cuda()
+    lddx = K + 4
+    dxbuf = torch.full((M + 2, lddx), float("nan"), device="cuda")
+    dxbuf[1:M + 1, :K] = 1.0
+    rc = lib.wmrl_linear_dgrad(M, N, K, dy.data_ptr(), N, w.data_ptr(), dxbuf.data_ptr() + lddx * 4, lddx, 1, st)
+    assert rc == 0, lib.wmrl_last_error()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dxbuf[1:M + 1, :K].double(), 1.0 + dy.double() @ w.double(), rtol=1e-4, atol=1e-4)
+    assert bool(torch.isnan(dxbuf[0]).all()) and bool(torch.isnan(dxbuf[M + 1]).all()) and bool(torch.isnan(dxbuf[1:M + 1, K:]).all())
+    # wgrad accumulates into dW exactly [N, K]
+    dwbuf = torch.full((N + 2, K), float("nan"), device="cuda")
+    dwbuf[1:N + 1] = 0.0
+    rc = lib.wmrl_linear_wgrad(M, N, K, dy.data_ptr(), N, xbuf.data_ptr(), ldx, dwbuf.data_ptr() + K * 4, st)
+    assert rc == 0, lib.wmrl_last_error()
+    torch.cuda.synchronize()
+    ref = dy.double().t() @ x.double()
+    torch.testing.assert_close(dwbuf[1:N + 1].double(), ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))
+    assert bool(torch.isnan(dwbuf[0]).all()) and bool(torch.isnan(dwbuf[N + 1]).all())
