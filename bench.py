@@ -406,7 +406,7 @@ def run_ours(args):
                                          "the noise is drawn on the device inside imagine_rollout"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": traffic, "kernel": "tc_imagine_kernel",
+                         "frac": achieved_tf / peak_tf, "traffic": traffic, "kernel": "tc_imagine_fold_kernel",
                          "flops_per_latent_step": fl, "latent_steps_per_launch": B * H,
                          "avg_launch_ms": avg_launch_s * 1e3,
                          "peak_source": f"{peaks_src} bf16_tflops_sustained (MEASURED_PEAKS.json)",
