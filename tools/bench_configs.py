@@ -85,6 +85,31 @@ def observe_case(name, variant, B, T, D, S, C, Hd, E=1024, A=6, bwd=False):
     return dict(case=name, gpu_ms=ms, gpu_latent_steps_per_s=steps / ms * 1e3, cpu_ms=cms, cpu_rows=B,
                 cpu_latent_steps_per_s=steps / cms * 1e3, precision="fp32", bwd=bwd)
 
+def c3_pipeline_case(name, B=50, T=51, H=15, D=600, S=32, C=32, Hd=600, E=1024, A=6):
+    """BASELINE configs[2] end to end (encoder outside the path): posterior filtering over B sequences of length T,
+    the B*(T-1) posteriors become the start states (state/discrete.py:81-89) of a horizon-H imagined rollout."""
+    variant = "discrete"
+    rssm, actor = HG.build_modules(variant, D, S, C, Hd, E, A, 512, 3, seed=0)
+    g = torch.Generator().manual_seed(0)
+    obs = torch.relu(torch.randn(B, T, E, generator=g)); act = torch.rand(B, T, A, generator=g) * 2 - 1
+    mk = lambda n, b: torch.empty(n, b, C, S).exponential_(1.0, generator=g)
+    n1, n2, nz = mk(T - 1, B), mk(T - 1, B), mk(H, B * (T - 1))
+    obs_d, act_d, n1d, n2d, nzd = (t.to(dev) for t in (obs, act, n1, n2, nz))
+    def gpu():
+        with torch.no_grad():
+            _, post = rssm.observe_rollout(obs_d, act_d, noise=(n1d, n2d))
+            rssm.imagine_rollout(post.flatten_batch_time(), actor, H, noise=nzd)
+    ms = timeit(gpu)
+    w, aw = HG.cpu_weights(rssm), HG.cpu_weights(actor)
+    def cpu():
+        with torch.no_grad():
+            _, post = O.observe_rollout(variant, w, obs, act, n1, n2, S, C)
+            O.imagine_rollout(variant, w, aw, post["deter"].reshape(-1, D), post["stoch"].reshape(-1, S * C), nz, H, S, C)
+    cms = cpu_time(cpu, n=1)
+    steps = B * (T - 1) * H
+    return dict(case=name, gpu_ms=ms, gpu_latent_steps_per_s=steps / ms * 1e3, cpu_ms=cms, cpu_rows=B * (T - 1),
+                cpu_latent_steps_per_s=steps / cms * 1e3, precision="fp32", bwd=False)
+
 def lambda_case(B, H):
     from wmrl.functional import lambda_return
     V = torch.randn(B, H, 1, device=dev, requires_grad=True); r = torch.randn(B, H, 1, device=dev, requires_grad=True)
@@ -148,6 +173,7 @@ rows = [
     actor_update_case("C2 actor-update step (rollout+heads+lambda-return+bwd) B=2500", "discrete", 2500, 15, 600, 32, 32, 600),
     observe_case("C3 discrete observe B=50 T=51 E=1024 fwd fp32", "discrete", 50, 51, 600, 32, 32, 600),
     observe_case("C3 discrete observe B=50 T=51 fwd+bwd fp32", "discrete", 50, 51, 600, 32, 32, 600, bwd=True),
+    c3_pipeline_case("C3 pipeline: observe 50x51 -> 2500 posteriors -> imagine H=15 (fwd)"),
     imagine_case("C4 continuous B=65536 H=15 fwd bf16-tcgen05", "continuous", 65536, 15, 200, 30, 1, 200, precision="bf16"),
     imagine_case("C4 continuous B=65536 H=15 fwd fp32", "continuous", 65536, 15, 200, 30, 1, 200),
     lambda_case(2500, 15), lambda_case(2500, 64),
