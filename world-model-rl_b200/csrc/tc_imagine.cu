@@ -46,7 +46,8 @@ constexpr int kDefaultTcMode = 3;
 constexpr int kGruChunk = 128;           // max state columns per GRU job
 constexpr int kP2Groups = 2;            // Gaussian head: 8-column groups per epilogue warp (S <= 8*kQ*kP2Groups)
 
-enum : uint8_t { ST_FIRST_ACC = 1, ST_LAST_OF_JOB = 2, ST_FIRST_OF_JOB = 4, ST_DBUF = 8 };
+// ST_PRE: stage belongs to the NEXT step (issued early, once before the first step, skipped in the last)
+enum : uint8_t { ST_FIRST_ACC = 1, ST_LAST_OF_JOB = 2, ST_FIRST_OF_JOB = 4, ST_DBUF = 8, ST_PRE = 16 };
 struct __align__(16) StageDesc {
   uint32_t w_off16;   // byte offset / 16 of this stage in the packed stage area
   uint16_t bytes16;   // stage bytes / 16
@@ -181,12 +182,14 @@ struct RowSpec {
 struct Seg { uint32_t a_off; int kpad; const float* src; int ld; int k0; int kvalid; };
 
 static void add_acc_group(Plan& pl, const RowSpec& rs, const std::vector<Seg>& segs, int tmem_col,
-                          bool dbuf, bool first_of_job, int dep, bool last_of_job) {
+                          bool dbuf, bool first_of_job, int dep, bool last_of_job, bool onto_existing = false,
+                          uint8_t extra_flags = 0) {
   const int N = rs.N();
   int per = pl.stage_bytes / (N * 32);
   if (per < 1) per = 1;
   if (per > 64) per = 64;
-  bool first_acc = true;
+  bool first_acc = !onto_existing;   // onto_existing: the accumulator already holds an earlier group's partial sums
+  bool first_stage = true;
   for (size_t si = 0; si < segs.size(); ++si) {
     const Seg& sg = segs[si];
     const int total = sg.kpad / 16;
@@ -196,9 +199,9 @@ static void add_acc_group(Plan& pl, const RowSpec& rs, const std::vector<Seg>& s
       st.w_off16 = (uint32_t)(pl.data_bytes / 16);
       st.bytes16 = (uint16_t)(nk * N * 32 / 16);
       st.nk16 = (uint8_t)nk;
-      st.flags = 0;
+      st.flags = extra_flags;
       if (first_acc) st.flags |= ST_FIRST_ACC;
-      if (first_of_job && first_acc) { st.flags |= ST_FIRST_OF_JOB; st.dep = (uint8_t)dep; }
+      if (first_of_job && first_stage) { st.flags |= ST_FIRST_OF_JOB; st.dep = (uint8_t)dep; }
       if (dbuf) st.flags |= ST_DBUF;
       const bool last = (si + 1 == segs.size()) && (done + nk == total);
       if (last && last_of_job) st.flags |= ST_LAST_OF_JOB;
@@ -219,6 +222,7 @@ static void add_acc_group(Plan& pl, const RowSpec& rs, const std::vector<Seg>& s
       pl.data_bytes += (size_t)nk * N * 32;
       done += nk;
       first_acc = false;
+      first_stage = false;
     }
   }
 }
@@ -273,6 +277,10 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
   auto W = [&](const float* const* p) { return p ? *p : nul; };
   (void)W;
   const int Ke = d.S_in + d.A;
+  // Folded pairs: the h part of the first actor layer (13 of its 15 K steps at C4) does not depend on the
+  // prior head, so its MMAs for step t+1 are issued right after the prior2 MMAs of step t and run under
+  // prior2's epilogue; only the s part stays on the critical path.  prior2 accumulates at TMEM column 256.
+  const bool early_h = pl.fold && !pl.pp;
   // ---- actor blocks
   for (int l = 0; l < d.La; ++l) {
     JobDesc jb{};
@@ -291,12 +299,12 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
       std::vector<Seg> segs;
       if (l == 0) {
         // A = [P_h | P_s]: contiguous panels, source columns [0,D) and [D,D+S)
-        segs.push_back({pl.off_h, pl.Dp, lw, d.F, 0, d.D});
+        if (!early_h) segs.push_back({pl.off_h, pl.Dp, lw, d.F, 0, d.D});
         segs.push_back({pl.off_s, pl.Sp, lw, d.F, d.D, d.S_in});
       } else {
         segs.push_back({pl.off_x, d.Ha, lw, d.Ha, 0, d.Ha});
       }
-      add_acc_group(pl, rs, segs, nc * tc(256), false, nc == 0, 1, nc == nchunks - 1);
+      add_acc_group(pl, rs, segs, nc * tc(256), false, nc == 0, 1, nc == nchunks - 1, l == 0 && early_h);
     }
   }
   // ---- mu head
@@ -395,7 +403,7 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
   }
   {
     JobDesc jb{};
-    jb.type = JOB_PRIOR2_CONT; jb.n = (uint16_t)(2 * pl.Sp); jb.tmem_col = 0; jb.dst_off = pl.off_s;
+    jb.type = JOB_PRIOR2_CONT; jb.n = (uint16_t)(2 * pl.Sp); jb.tmem_col = early_h ? 256 : 0; jb.dst_off = pl.off_s;
     jb.p_off = add_vec(pl, w ? w->prior2_b : nul, nul, 0, d.S, pl.Sp);
     add_vec(pl, w ? w->prior2_b : nul, nul, d.S, d.S, pl.Sp);
     pl.jobs.push_back(jb);
@@ -410,7 +418,18 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
       rs.add(0, d.S, pl.Sp);
       rs.add(d.S, d.S, pl.Sp);
     }
-    add_acc_group(pl, rs, {{pl.off_x, pl.Hdp, w ? w->prior2_w : nul, d.Hd, 0, d.Hd}}, 0, false, true, 1, true);
+    add_acc_group(pl, rs, {{pl.off_x, pl.Hdp, w ? w->prior2_w : nul, d.Hd, 0, d.Hd}}, early_h ? 256 : 0, false, true, 1,
+                  true);
+  }
+  if (early_h) {   // next step's first actor layer, h part.  It reads h' where the GRU epilogues put it (X[h2..]); P_h is being
+                   // rewritten by prior2's epilogue at that time.  The tile initialisation stores h0 there as well.
+    const float* lw = aw ? aw->lin_w[0] : nul;
+    const int nchunks = (d.Ha + 255) / 256;
+    for (int nc = 0; nc < nchunks; ++nc) {
+      const int rows = std::min(256, d.Ha - nc * 256);
+      RowSpec rs{nc * 256, rows, rows, 0, 0, 0};
+      add_acc_group(pl, rs, {{pl.off_h2, pl.Dp, lw, d.F, 0, d.D}}, nc * tc(256), false, false, 0, false, false, ST_PRE);
+    }
   }
   for (const StageDesc& st : pl.stages)
     if ((int)st.bytes16 * 16 > pl.stage_bytes) return pl;
@@ -1187,6 +1206,7 @@ __device__ __forceinline__ void epif_init(const EpiCtxF& c) {
       if (c.valid && col < p.D) p.deter_seq[(c.b * T1) * p.D + col] = v[e];
     }
     st_chunk(c.smem_base + p.off_h + k8 * kPSF + c.row * 16, v);
+    st_chunk(c.smem_base + p.off_h2 + k8 * kPSF + c.row * 16, v);   // read by the early first-actor-layer MMAs (ST_PRE)
   }
   for (int k8 = c.sidx; k8 < p.Sp / 8; k8 += 2 * kQ) {
     float v[8];
@@ -1532,98 +1552,119 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcPa
 
   if (warp == kProducerWarp) {
     if (lane == 0) {
+      // Stage sequence of a tile (all three role loops walk exactly this): the ST_PRE stages once, then per step
+      // every stage - except that the last step skips the ST_PRE stages (they belong to a step that does not exist).
       uint32_t slot = 0, phase = 0;
-      for (int grp = unit; grp < ngroups; grp += nunits)
+      auto issue = [&](int s, const uint4& raw) {
+        const uint32_t bytes = ((raw.y & 0xFFFFu) * 16u) / 2u;
+        mbar_wait(empty_bar(slot), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(slot), bytes);
+        bulk_g2s(ring + slot * kSlot, p.stage_data + (size_t)raw.x * 16u + (size_t)rank * bytes, bytes, full_bar(slot));
+        if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+      };
+      for (int grp = unit; grp < ngroups; grp += nunits) {
+        for (int s = 0; s < p.nstages; ++s) {
+          const uint4 raw = c_stages[s];
+          if ((raw.y >> 24) & ST_PRE) issue(s, raw);
+        }
         for (int t = 0; t < p.H; ++t)
           for (int s = 0; s < p.nstages; ++s) {
             const uint4 raw = c_stages[s];
-            const uint32_t bytes = ((raw.y & 0xFFFFu) * 16u) / 2u;
-            mbar_wait(empty_bar(slot), phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(slot), bytes);
-            bulk_g2s(ring + slot * kSlot, p.stage_data + (size_t)raw.x * 16u + (size_t)rank * bytes, bytes,
-                     full_bar(slot));
-            if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+            if (((raw.y >> 24) & ST_PRE) && t == p.H - 1) continue;
+            issue(s, raw);
           }
+      }
     }
   } else if (warp == kMmaWarp) {
     if (lane == 0 && rank != 0) {
       uint32_t slot = 0, phase = 0;
-      for (int grp = unit; grp < ngroups; grp += nunits)
-        for (int t = 0; t < p.H; ++t)
-          for (int s = 0; s < p.nstages; ++s) {
-            mbar_wait(full_bar(slot), phase);
-            mbar_arrive_remote(mapa(full_bar(slot), 0));
-            if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
-          }
+      int npre = 0;
+      for (int s = 0; s < p.nstages; ++s) npre += ((c_stages[s].y >> 24) & ST_PRE) ? 1 : 0;
+      for (int grp = unit; grp < ngroups; grp += nunits) {
+        const int total = npre + p.H * p.nstages - npre;   // prologue + H steps - the last step's skipped stages
+        for (int i = 0; i < total; ++i) {
+          mbar_wait(full_bar(slot), phase);
+          mbar_arrive_remote(mapa(full_bar(slot), 0));
+          if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+        }
+      }
     } else if (lane == 0) {
       uint32_t slot = 0, phase = 0, job = 0;
+      // issue one stage's MMAs and release its slot
+      auto run_stage = [&](const uint4& rec, uint32_t flags) {
+        mbar_wait(full_bar(slot), phase);
+        tc_fence_after();
+        const uint32_t tm = tmem_base + (rec.w & 0xFFFFu) + ((flags & ST_DBUF) ? (job & 1u) * 256u : 0u);
+        const uint32_t idesc = rec.y;
+        const uint32_t nh = rec.z >> 16;
+        uint32_t alo = rec.x;
+        uint32_t blo = (((ring + slot * kSlot) >> 4) & 0x3FFFu) | (nh << 16);
+        const uint32_t bstep = nh * 2u;
+        constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+        uint32_t acc = (flags & ST_FIRST_ACC) ? 0u : 1u;
+        const uint32_t nk = (rec.z >> 8) & 0xFFu;
+        constexpr uint32_t kAStep = (2u * kPSF) >> 4;
+        uint32_t i = 0;
+        for (; i + 4 <= nk; i += 4) {       // 4 MMAs per trip: the lane must stay ahead of a 64-cycle MMA
+          mma_bf16_lohi2(tm, alo, kDescHi, blo, kDescHi, idesc, acc);
+          mma_bf16_lohi2(tm, alo + kAStep, kDescHi, blo + bstep, kDescHi, idesc, 1u);
+          mma_bf16_lohi2(tm, alo + 2 * kAStep, kDescHi, blo + 2 * bstep, kDescHi, idesc, 1u);
+          mma_bf16_lohi2(tm, alo + 3 * kAStep, kDescHi, blo + 3 * bstep, kDescHi, idesc, 1u);
+          alo += 4 * kAStep;
+          blo += 4 * bstep;
+          acc = 1u;
+        }
+        for (; i < nk; ++i) {
+          mma_bf16_lohi2(tm, alo, kDescHi, blo, kDescHi, idesc, acc);
+          alo += kAStep;
+          blo += bstep;
+          acc = 1u;
+        }
+        tc_commit2(empty_bar(slot), 3);
+      };
       for (int grp = unit; grp < ngroups; grp += nunits) {
         mbar_arrive(accf_bar(job));
         mbar_arrive_remote(mapa(accf_bar(job), 1));
         ++job;
         const bool tr = p.trace && blockIdx.x == 0 && grp == unit;
-        for (int t = 0; t < p.H; ++t) {
-          int jidx = -1;
-          long long s_full = 0, s_peer = 0, s_issue = 0, s_commit = 0, s_n = 0;
+        // prologue: the ST_PRE stages (first actor layer over the h panel) need the INIT job's panels
+        {
+          bool waited = false;
           for (int s = 0; s < p.nstages; ++s) {
             const uint4 rec = stab[s];
             const uint32_t flags = rec.z & 0xFFu;
-            if (flags & ST_FIRST_OF_JOB) ++jidx;
+            if (!(flags & ST_PRE)) continue;
+            if (!waited) {
+              const uint32_t dj = job - 1u;
+              mbar_wait(acce_bar(dj), (dj >> 1) & 1u);
+              waited = true;
+            }
+            run_stage(rec, flags);
+            if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+          }
+        }
+        for (int t = 0; t < p.H; ++t) {
+          int jidx = -1;
+          for (int s = 0; s < p.nstages; ++s) {
+            const uint4 rec = stab[s];
+            const uint32_t flags = rec.z & 0xFFu;
+            if ((flags & ST_PRE) && t == p.H - 1) continue;
             if (flags & ST_FIRST_OF_JOB) {
+              ++jidx;
               const uint32_t dep = rec.w >> 16;
               if (dep) {
                 const uint32_t dj = job - dep;
                 mbar_wait(acce_bar(dj), (dj >> 1) & 1u);
               }
+              if (tr && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 0] = clock64();
             }
-            const bool trw = tr && t == 1 && jidx == 1;     // actor1's stages
-            const long long w0 = trw ? clock64() : 0;
-            mbar_wait(full_bar(slot), phase);
-            const long long w1 = trw ? clock64() : 0;
-            tc_fence_after();
-            const long long w2 = trw ? clock64() : 0;
-            if (tr && (flags & ST_FIRST_OF_JOB) && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 0] = clock64();
-            const uint32_t tm = tmem_base + (rec.w & 0xFFFFu) + ((flags & ST_DBUF) ? (job & 1u) * 256u : 0u);
-            const uint32_t idesc = rec.y;
-            const uint32_t nh = rec.z >> 16;
-            uint32_t alo = rec.x;
-            uint32_t blo = (((ring + slot * kSlot) >> 4) & 0x3FFFu) | (nh << 16);
-            const uint32_t bstep = nh * 2u;
-            constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
-            uint32_t acc = (flags & ST_FIRST_ACC) ? 0u : 1u;
-            const uint32_t nk = (rec.z >> 8) & 0xFFu;
-            constexpr uint32_t kAStep = (2u * kPSF) >> 4;
-            uint32_t i = 0;
-            for (; i + 4 <= nk; i += 4) {       // 4 MMAs per trip: the lane must stay ahead of a 64-cycle MMA
-              mma_bf16_lohi2(tm, alo, kDescHi, blo, kDescHi, idesc, acc);
-              mma_bf16_lohi2(tm, alo + kAStep, kDescHi, blo + bstep, kDescHi, idesc, 1u);
-              mma_bf16_lohi2(tm, alo + 2 * kAStep, kDescHi, blo + 2 * bstep, kDescHi, idesc, 1u);
-              mma_bf16_lohi2(tm, alo + 3 * kAStep, kDescHi, blo + 3 * bstep, kDescHi, idesc, 1u);
-              alo += 4 * kAStep;
-              blo += 4 * bstep;
-              acc = 1u;
-            }
-            for (; i < nk; ++i) {
-              mma_bf16_lohi2(tm, alo, kDescHi, blo, kDescHi, idesc, acc);
-              alo += kAStep;
-              blo += bstep;
-              acc = 1u;
-            }
-            const long long w3 = trw ? clock64() : 0;
-            tc_commit2(empty_bar(slot), 3);
-            if (trw) {
-              const long long w4 = clock64();
-              s_full += w1 - w0; s_peer += w2 - w1; s_issue += w3 - w2; s_commit += w4 - w3; s_n += 1;
-            }
+            run_stage(rec, flags);
             if (flags & ST_LAST_OF_JOB) {
               tc_commit2(accf_bar(job), 3);
               if (tr && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 1] = clock64();
               ++job;
             }
             if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
-          }
-          if (tr && t == 1) {
-            p.trace[720] = s_full; p.trace[721] = s_peer; p.trace[722] = s_issue; p.trace[723] = s_commit; p.trace[724] = s_n;
           }
         }
       }
