@@ -389,7 +389,7 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
   // ---- prior head
   {
     JobDesc jb{};
-    jb.type = JOB_DENSE_ELU; jb.n = (uint16_t)pl.Hdp; jb.tmem_col = 0; jb.dst_off = pl.off_x;
+    jb.type = JOB_DENSE_ELU; jb.n = (uint16_t)pl.Hdp; jb.tmem_col = early_h ? 256 : 0; jb.dst_off = pl.off_x;
     jb.p_off = add_vec(pl, w ? w->prior0_b : nul, nul, 0, d.Hd, pl.Hdp);
     pl.jobs.push_back(jb);
     const int nchunks = (pl.Hdp + 255) / 256;
@@ -397,10 +397,23 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
       const int padr = std::min(256, pl.Hdp - nc * 256);
       const int valid = std::max(0, std::min(padr, d.Hd - nc * 256));
       RowSpec rs{nc * 256, valid, padr, 0, 0, 0};
-      add_acc_group(pl, rs, {{pl.off_h2, pl.Dp, w ? w->prior0_w : nul, d.D, 0, d.D}}, nc * tc(256), false, nc == 0, 1,
-                    nc == nchunks - 1);
+      add_acc_group(pl, rs, {{pl.off_h2, pl.Dp, w ? w->prior0_w : nul, d.D, 0, d.D}}, (early_h ? 256 : 0) + nc * tc(256), false,
+                    nc == 0, 1, nc == nchunks - 1);
     }
   }
+  // next step's first actor layer, h part (ST_PRE).  It reads h' where the GRU epilogues put it (X[h2..]); P_h is being
+  // rewritten by prior2's epilogue at that time.  The tile initialisation stores h0 there as well.  The first N chunk
+  // runs under prior1's epilogue, the rest under prior2's.
+  auto early_actor0_h = [&](int nc_begin, int nc_end) {
+    const float* lw = aw ? aw->lin_w[0] : nul;
+    for (int nc = nc_begin; nc < nc_end; ++nc) {
+      const int rows = std::min(256, d.Ha - nc * 256);
+      RowSpec rs{nc * 256, rows, rows, 0, 0, 0};
+      add_acc_group(pl, rs, {{pl.off_h2, pl.Dp, lw, d.F, 0, d.D}}, nc * tc(256), false, false, 0, false, false, ST_PRE);
+    }
+  };
+  const int a0_chunks = (d.Ha + 255) / 256;
+  if (early_h) early_actor0_h(0, 1);
   {
     JobDesc jb{};
     jb.type = JOB_PRIOR2_CONT; jb.n = (uint16_t)(2 * pl.Sp); jb.tmem_col = early_h ? 256 : 0; jb.dst_off = pl.off_s;
@@ -421,16 +434,7 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
     add_acc_group(pl, rs, {{pl.off_x, pl.Hdp, w ? w->prior2_w : nul, d.Hd, 0, d.Hd}}, early_h ? 256 : 0, false, true, 1,
                   true);
   }
-  if (early_h) {   // next step's first actor layer, h part.  It reads h' where the GRU epilogues put it (X[h2..]); P_h is being
-                   // rewritten by prior2's epilogue at that time.  The tile initialisation stores h0 there as well.
-    const float* lw = aw ? aw->lin_w[0] : nul;
-    const int nchunks = (d.Ha + 255) / 256;
-    for (int nc = 0; nc < nchunks; ++nc) {
-      const int rows = std::min(256, d.Ha - nc * 256);
-      RowSpec rs{nc * 256, rows, rows, 0, 0, 0};
-      add_acc_group(pl, rs, {{pl.off_h2, pl.Dp, lw, d.F, 0, d.D}}, nc * tc(256), false, false, 0, false, false, ST_PRE);
-    }
-  }
+  if (early_h) early_actor0_h(1, a0_chunks);
   for (const StageDesc& st : pl.stages)
     if ((int)st.bytes16 * 16 > pl.stage_bytes) return pl;
   if ((int)pl.stages.size() > kMaxStagesSmem || (int)pl.stages.size() > kMaxStages || (int)pl.jobs.size() > kMaxJobs ||
