@@ -307,6 +307,38 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
       add_acc_group(pl, rs, segs, nc * tc(256), false, nc == 0, 1, nc == nchunks - 1, l == 0 && early_h);
     }
   }
+  // ---- GRU chunk geometry (see the GRU block below)
+  const int gru_groups = pl.Dp / 16;
+  const int gru_nchunks = (pl.Dp + kGruChunk - 1) / kGruChunk;
+  auto gru_geom = [&](int c, int& col0, int& cw) {
+    col0 = 0;
+    for (int i = 0; i <= c; ++i) {
+      cw = (gru_groups / gru_nchunks + (i < gru_groups % gru_nchunks ? 1 : 0)) * 16;
+      if (i < c) col0 += cw;
+    }
+  };
+  // static TMEM halves in early_h mode: even chunks at column 256, odd chunks at 0
+  auto gru_base = [&](int c) { return early_h ? ((c % 2 == 0) ? 256 : 0) : 0; };
+  auto gru_rz = [&](int col0, int cw) {
+    const int hw = cw / 2;
+    RowSpec rz;
+    rz.add(col0, d.D - col0, hw);
+    rz.add(d.D + col0, d.D - col0, hw);
+    rz.add(col0 + hw, d.D - col0 - hw, hw);
+    rz.add(d.D + col0 + hw, d.D - col0 - hw, hw);
+    return rz;
+  };
+  if (early_h) {
+    // h side of GRU chunk 0 (W_hh h for r|z and for h_n: half of the chunk's MMAs) only needs h(t): issued right
+    // after the last actor layer's MMAs, it runs under that layer's LayerNorm epilogue.
+    int col0, cw;
+    gru_geom(0, col0, cw);
+    const int valid = std::max(0, std::min(cw, d.D - col0));
+    const float* whh = w ? w->w_hh : nul;
+    add_acc_group(pl, gru_rz(col0, cw), {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, gru_base(0), false, false, 0, false);
+    RowSpec rn(2 * d.D + col0, valid, cw);
+    add_acc_group(pl, rn, {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, gru_base(0) + cw + cw / 2, false, false, 0, false);
+  }
   // ---- mu head
   {
     JobDesc jb{};
@@ -352,7 +384,8 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
       const int cw = gcount * 16;
       const int valid = std::max(0, std::min(cw, d.D - col0));
       JobDesc jb{};
-      jb.type = JOB_GRU; jb.dbuf = (pl.fold && !pl.pp) ? 1 : 0; jb.n = (uint16_t)cw; jb.tmem_col = 0; jb.col0 = (uint16_t)col0;
+      jb.type = JOB_GRU; jb.dbuf = (pl.fold && !pl.pp && !early_h) ? 1 : 0; jb.n = (uint16_t)cw;
+      jb.tmem_col = (uint16_t)gru_base(c); jb.col0 = (uint16_t)col0;
       jb.dst_off = pl.off_h2; jb.p_off = pb;
       pl.jobs.push_back(jb);
       const float* wih = w ? w->w_ih : nul;
@@ -362,19 +395,24 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
         // those -> B rows of the r|z group are ordered [r lo, z lo, r hi, z hi]; TMEM (per lane half):
         // r @0, z @cw/2, i_n @cw, h_n @cw+cw/2 - 2*cw columns, double buffered in the two 256-column halves
         const int hw = cw / 2;
-        RowSpec rz;
-        rz.add(col0, d.D - col0, hw);
-        rz.add(d.D + col0, d.D - col0, hw);
-        rz.add(col0 + hw, d.D - col0 - hw, hw);
-        rz.add(d.D + col0 + hw, d.D - col0 - hw, hw);
-        // ping-pong mode gives each tile one 256-column TMEM half: chunks are single-buffered there
-        const bool db = !pl.pp;
-        const int dep = db ? ((c < 2) ? (c + 1) : 2) : 1;   // double-buffered: chunk c waits for chunk c-2's epilogue
-        add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}, {pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 0, db,
-                      true, dep, false);
+        const RowSpec rz = gru_rz(col0, cw);
+        // ping-pong mode gives each tile one 256-column TMEM half: chunks are single-buffered there; early_h mode
+        // uses static halves (even chunks at column 256, odd at 0) so that chunk 0's h side can be issued early
+        const bool two_halves = !pl.pp;
+        const bool db = two_halves && !early_h;
+        const int base = gru_base(c);
+        const int dep = two_halves ? ((c < 2) ? (c + 1) : 2) : 1;   // chunk c waits for chunk c-2's epilogue (same half)
         RowSpec rn(2 * d.D + col0, valid, cw);
-        add_acc_group(pl, rn, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, cw, db, false, 0, false);
-        add_acc_group(pl, rn, {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, cw + hw, db, false, 0, true);
+        if (early_h && c == 0) {
+          // the h side was issued after the actor layers; here only the x side, on top of it
+          add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, base, false, true, dep, false, true);
+          add_acc_group(pl, rn, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, base + cw, false, false, 0, true);
+        } else {
+          add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}, {pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, base, db,
+                        true, dep, false);
+          add_acc_group(pl, rn, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, base + cw, db, false, 0, false);
+          add_acc_group(pl, rn, {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, base + cw + hw, db, false, 0, true);
+        }
       } else {
         RowSpec rz{col0, valid, cw, d.D + col0, valid, cw};
         add_acc_group(pl, rz, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}, {pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 0, false,
@@ -1713,7 +1751,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcPa
             mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
             tc_fence_after();
             if (tr) t_wake = clock64();
-            epif_gru(c, jb, c.tmem_lane + (jb.dbuf ? (job & 1u) * 256u : 0u), hp);
+            epif_gru(c, jb, c.tmem_lane + jb.tmem_col + (jb.dbuf ? (job & 1u) * 256u : 0u), hp);
           } else if (jb.type == JOB_PRIOR2_CONT) {
             float e0[8];
             epsf_prefetch(c, e0);
