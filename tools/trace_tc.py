@@ -62,3 +62,7 @@ print(f"GRU stages ({g[3]}): total dep wait {g[0]}, per-stage avg wait full {g[1
 f = ws[720 * 8:725 * 8].view(torch.int64).cpu().tolist()
 if f[4]:
     print(f"fold kernel, actor1 ({f[4]} stages) per-stage avg: wait full {f[0]/f[4]:.0f}, wait peer {f[1]/f[4]:.0f}, MMA issue {f[2]/f[4]:.0f}, commit {f[3]/f[4]:.0f}")
+
+raw = ws[:1024 * 8].view(torch.int64).cpu()
+print("dependency wait per job (step 1):", [int(raw[760 + j]) for j in range(njobs)])
+print("gru1 stages (wait-weights, issue+commit):", [(int(raw[730 + 2 * i]), int(raw[731 + 2 * i])) for i in range(6)])

@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-]
+] + os.environ.get("WMRL_NVCC_EXTRA", "").split()   # e.g. -DWMRL_TC_STAGE_TRACE for tools/trace_tc.py
 
 
 def _nvcc() -> str:

@@ -1633,8 +1633,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcPa
     } else if (lane == 0) {
       uint32_t slot = 0, phase = 0, job = 0;
       // issue one stage's MMAs and release its slot
+#ifdef WMRL_TC_STAGE_TRACE   // per-stage timing of one job (tools/trace_tc.py); off in production: the lane is latency-critical
+      long long* stage_trace = nullptr;   // when set: [2*i] = wait for the stage's weights, [2*i+1] = issue + commit
+#endif
       auto run_stage = [&](const uint4& rec, uint32_t flags) {
+#ifdef WMRL_TC_STAGE_TRACE
+        const long long w0 = stage_trace ? clock64() : 0;
+#endif
         mbar_wait(full_bar(slot), phase);
+#ifdef WMRL_TC_STAGE_TRACE
+        const long long w1 = stage_trace ? clock64() : 0;
+#endif
         tc_fence_after();
         const uint32_t tm = tmem_base + (rec.w & 0xFFFFu) + ((flags & ST_DBUF) ? (job & 1u) * 256u : 0u);
         const uint32_t idesc = rec.y;
@@ -1663,6 +1672,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcPa
           acc = 1u;
         }
         tc_commit2(empty_bar(slot), 3);
+#ifdef WMRL_TC_STAGE_TRACE
+        if (stage_trace) { stage_trace[0] = w1 - w0; stage_trace[1] = clock64() - w1; stage_trace += 2; }
+#endif
       };
       for (int grp = unit; grp < ngroups; grp += nunits) {
         mbar_arrive(accf_bar(job));
@@ -1687,18 +1699,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcPa
         }
         for (int t = 0; t < p.H; ++t) {
           int jidx = -1;
+          uint4 rec_next = stab[0];
           for (int s = 0; s < p.nstages; ++s) {
-            const uint4 rec = stab[s];
+            const uint4 rec = rec_next;
+            if (s + 1 < p.nstages) rec_next = stab[s + 1];   // the next record's LDS latency hides under this stage
             const uint32_t flags = rec.z & 0xFFu;
             if ((flags & ST_PRE) && t == p.H - 1) continue;
             if (flags & ST_FIRST_OF_JOB) {
               ++jidx;
               const uint32_t dep = rec.w >> 16;
+#ifdef WMRL_TC_STAGE_TRACE
+              const long long d0 = tr ? clock64() : 0;
+#endif
               if (dep) {
                 const uint32_t dj = job - dep;
                 mbar_wait(acce_bar(dj), (dj >> 1) & 1u);
               }
               if (tr && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 0] = clock64();
+#ifdef WMRL_TC_STAGE_TRACE
+              if (tr && t == 1) p.trace[760 + jidx] = clock64() - d0;          // dependency wait of each job
+              stage_trace = (tr && t == 1 && jidx == p.njobs - 3) ? p.trace + 730 : nullptr;   // gru1's stages
+#endif
             }
             run_stage(rec, flags);
             if (flags & ST_LAST_OF_JOB) {
