@@ -1268,7 +1268,7 @@ __device__ __forceinline__ void epif_actor_ln(const EpiCtxF& c, const JobDesc& j
   const TcParams& p = *c.p;
   const uint32_t bias = jb.p_off, gam = bias + p.Ha, bet = gam + p.Ha;
   const int nmg = (p.Ha + 255) / 256;
-  float sum = 0.f, sq = 0.f;
+  float sum = 0.f, sq = 0.f, sum1 = 0.f, sq1 = 0.f;   // two partial sums each: packed f32x2 arithmetic
   int li = 0;
   for (int mg = 0; mg < nmg; ++mg) {
     const int hw = min(256, p.Ha - mg * 256) / 2;
@@ -1281,14 +1281,20 @@ __device__ __forceinline__ void epif_actor_ln(const EpiCtxF& c, const JobDesc& j
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         const float4 b4 = ldc4(bias + f0 + i);
-        const float x0 = v[i] + b4.x, x1 = v[i + 1] + b4.y, x2 = v[i + 2] + b4.z, x3 = v[i + 3] + b4.w;
-        sum += (x0 + x1) + (x2 + x3);
-        sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+        float x0, x1, x2, x3;
+        add2(x0, x1, v[i], v[i + 1], b4.x, b4.y);
+        add2(x2, x3, v[i + 2], v[i + 3], b4.z, b4.w);
+        add2(sum, sum1, sum, sum1, x0, x1);
+        add2(sum, sum1, sum, sum1, x2, x3);
+        fma2(sq, sq1, x0, x1, x0, x1, sq, sq1);
+        fma2(sq, sq1, x2, x3, x2, x3, sq, sq1);
       }
     }
   }
   // 8 partials per row (2 lane halves x kQ warps) exchanged through the head of the X panel, which is idle
   // between this layer's MMAs (done) and its own pass-2 writes (after the second barrier)
+  sum += sum1;
+  sq += sq1;
   const uint32_t scratch = c.smem_base + p.off_x;
   asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(scratch + (c.sidx * kRowsF + c.row) * 8), "f"(sum), "f"(sq)
                : "memory");
@@ -1322,10 +1328,17 @@ __device__ __forceinline__ void epif_actor_ln(const EpiCtxF& c, const JobDesc& j
         const float4 b4 = ldc4(bias + f0 + i);
         const float4 g4 = ldc4(gam + f0 + i);
         const float4 e4 = ldc4(bet + f0 + i);
-        v[i] = elu_scaled(fmaf(fmaf(v[i] + b4.x, rstd, nmr), g4.x, e4.x));
-        v[i + 1] = elu_scaled(fmaf(fmaf(v[i + 1] + b4.y, rstd, nmr), g4.y, e4.y));
-        v[i + 2] = elu_scaled(fmaf(fmaf(v[i + 2] + b4.z, rstd, nmr), g4.z, e4.z));
-        v[i + 3] = elu_scaled(fmaf(fmaf(v[i + 3] + b4.w, rstd, nmr), g4.w, e4.w));
+        float t0, t1, t2, t3;
+        add2(t0, t1, v[i], v[i + 1], b4.x, b4.y);
+        add2(t2, t3, v[i + 2], v[i + 3], b4.z, b4.w);
+        fma2(t0, t1, t0, t1, rstd, rstd, nmr, nmr);
+        fma2(t2, t3, t2, t3, rstd, rstd, nmr, nmr);
+        fma2(t0, t1, t0, t1, g4.x, g4.y, e4.x, e4.y);
+        fma2(t2, t3, t2, t3, g4.z, g4.w, e4.z, e4.w);
+        v[i] = elu_scaled(t0);
+        v[i + 1] = elu_scaled(t1);
+        v[i + 2] = elu_scaled(t2);
+        v[i + 3] = elu_scaled(t3);
       }
       const uint32_t dst = c.smem_base + jb.dst_off + (f0 / 8) * kPSF + c.row * 16;
 #pragma unroll
@@ -1334,23 +1347,37 @@ __device__ __forceinline__ void epif_actor_ln(const EpiCtxF& c, const JobDesc& j
   }
 }
 
-// bias + ELU -> bf16 panel; 8-column sub-groups of this lane half's features, dealt to the kQ warps
+// bias + ELU -> bf16 panel; 8-column sub-groups of this lane half's features, dealt to the kQ warps.  A thread has
+// only a few sub-groups, so the job is TMEM-latency-bound: its loads are issued four at a time before one wait.
 __device__ __forceinline__ void epif_dense_elu(const EpiCtxF& c, const JobDesc& jb) {
   const uint32_t bias = jb.p_off;
   const int nmg = (jb.n + 255) / 256;
-  int li = 0;
   for (int mg = 0; mg < nmg; ++mg) {
     const int hw = min(256, (int)jb.n - mg * 256) / 2;
-    for (int sub = 0; sub < hw / 8; ++sub, ++li) {
-      if ((li % kQ) != c.q) continue;
-      const int f0 = mg * 256 + c.hf * hw + sub * 8;
-      float v[8];
-      tmem_ld8(c.tmem_lane + jb.tmem_col + mg * 128 + sub * 8, v);
+    const int nsub = hw / 8;
+    // this thread's sub-groups: sub = first, first + kQ, ... (li = sub + mg * (sub-groups of earlier groups) keeps the
+    // round-robin of the unbatched version: groups before this one have 128/8 = 16 sub-groups, a multiple of kQ)
+    for (int sub0 = c.q; sub0 < nsub; sub0 += 4 * kQ) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int sub = sub0 + u * kQ;
+        if (sub < nsub) tmem_ld8(c.tmem_lane + jb.tmem_col + mg * 128 + sub * 8, v[u]);
+      }
       tmem_ld_wait();
-      const float4 b0 = ldc4(bias + f0), b1 = ldc4(bias + f0 + 4);
-      v[0] = elu_fast(v[0] + b0.x); v[1] = elu_fast(v[1] + b0.y); v[2] = elu_fast(v[2] + b0.z); v[3] = elu_fast(v[3] + b0.w);
-      v[4] = elu_fast(v[4] + b1.x); v[5] = elu_fast(v[5] + b1.y); v[6] = elu_fast(v[6] + b1.z); v[7] = elu_fast(v[7] + b1.w);
-      st_chunk(c.smem_base + jb.dst_off + (f0 / 8) * kPSF + c.row * 16, v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int sub = sub0 + u * kQ;
+        if (sub < nsub) {
+          const int f0 = mg * 256 + c.hf * hw + sub * 8;
+          const float4 b0 = ldc4(bias + f0), b1 = ldc4(bias + f0 + 4);
+          v[u][0] = elu_fast(v[u][0] + b0.x); v[u][1] = elu_fast(v[u][1] + b0.y);
+          v[u][2] = elu_fast(v[u][2] + b0.z); v[u][3] = elu_fast(v[u][3] + b0.w);
+          v[u][4] = elu_fast(v[u][4] + b1.x); v[u][5] = elu_fast(v[u][5] + b1.y);
+          v[u][6] = elu_fast(v[u][6] + b1.z); v[u][7] = elu_fast(v[u][7] + b1.w);
+          st_chunk(c.smem_base + jb.dst_off + (f0 / 8) * kPSF + c.row * 16, v[u]);
+        }
+      }
     }
   }
 }

@@ -321,5 +321,20 @@ __device__ __forceinline__ void st_chunk(uint32_t smem_addr, const float* v) {
                : "memory");
 }
 
+
+// Packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2, two fp32 per issue slot) for the issue-bound epilogues.
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 a, b, d;\n\tmov.b64 a, {%2,%3};\n\tmov.b64 b, {%4,%5};\n\tadd.rn.f32x2 d, a, b;\n\tmov.b64 {%0,%1}, d;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0,
+                                     float c1) {
+  asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2,%3};\n\tmov.b64 b, {%4,%5};\n\tmov.b64 c, {%6,%7};\n\t"
+      "fma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0,%1}, d;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+
 }  // namespace ptx
 }  // namespace wmrl
