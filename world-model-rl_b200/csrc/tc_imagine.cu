@@ -1335,10 +1335,8 @@ __device__ __forceinline__ void epif_actor_ln(const EpiCtxF& c, const JobDesc& j
         fma2(t2, t3, t2, t3, rstd, rstd, nmr, nmr);
         fma2(t0, t1, t0, t1, g4.x, g4.y, e4.x, e4.y);
         fma2(t2, t3, t2, t3, g4.z, g4.w, e4.z, e4.w);
-        v[i] = elu_scaled(t0);
-        v[i + 1] = elu_scaled(t1);
-        v[i + 2] = elu_scaled(t2);
-        v[i + 3] = elu_scaled(t3);
+        elu_scaled2(v[i], v[i + 1], t0, t1);
+        elu_scaled2(v[i + 2], v[i + 3], t2, t3);
       }
       const uint32_t dst = c.smem_base + jb.dst_off + (f0 / 8) * kPSF + c.row * 16;
 #pragma unroll
@@ -1371,10 +1369,15 @@ __device__ __forceinline__ void epif_dense_elu(const EpiCtxF& c, const JobDesc& 
         if (sub < nsub) {
           const int f0 = mg * 256 + c.hf * hw + sub * 8;
           const float4 b0 = ldc4(bias + f0), b1 = ldc4(bias + f0 + 4);
-          v[u][0] = elu_fast(v[u][0] + b0.x); v[u][1] = elu_fast(v[u][1] + b0.y);
-          v[u][2] = elu_fast(v[u][2] + b0.z); v[u][3] = elu_fast(v[u][3] + b0.w);
-          v[u][4] = elu_fast(v[u][4] + b1.x); v[u][5] = elu_fast(v[u][5] + b1.y);
-          v[u][6] = elu_fast(v[u][6] + b1.z); v[u][7] = elu_fast(v[u][7] + b1.w);
+          constexpr float kL2e = 1.4426950408889634f;
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            float t0, t1;
+            add2(t0, t1, v[u][e], v[u][e + 1], bb[e], bb[e + 1]);
+            fma2(t0, t1, t0, t1, kL2e, kL2e, 0.f, 0.f);
+            elu_scaled2(v[u][e], v[u][e + 1], t0, t1);
+          }
           st_chunk(c.smem_base + jb.dst_off + (f0 / 8) * kPSF + c.row * 16, v[u]);
         }
       }

@@ -336,5 +336,12 @@ __device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, f
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
 }
 
+// two ELUs at once: the -1 and the final multiply-add are packed (4 issue slots per element instead of 5)
+__device__ __forceinline__ void elu_scaled2(float& y0, float& y1, float zs0, float zs1) {
+  float e0 = ex2_fast(fminf(zs0, 0.f)), e1 = ex2_fast(fminf(zs1, 0.f));
+  add2(e0, e1, e0, e1, -1.f, -1.f);
+  fma2(y0, y1, fmaxf(zs0, 0.f), fmaxf(zs1, 0.f), 0.6931471805599453f, 0.6931471805599453f, e0, e1);
+}
+
 }  // namespace ptx
 }  // namespace wmrl
