@@ -83,6 +83,8 @@ struct PackOp {
   int k0, kvalid, nk8;
   int split;   // 2: the stage is stored as two N-halves (one per CTA of a pair), each [k/8][N/2][8]
   unsigned long long dst_off;
+  const float* bias;   // optional: K index bias_k of this op holds bias[row] (bias folded into the GEMM through a
+  int bias_k;          // constant-one column of the A panel); -1: none
 };
 struct VecOp {
   const float* src1;
@@ -179,7 +181,7 @@ struct RowSpec {
   void add(int r0, int v, int p) { seg[nseg++] = {r0, v < 0 ? 0 : (v > p ? p : v), p}; }
   int N() const { int n = 0; for (int i = 0; i < nseg; ++i) n += seg[i].pad; return n; }
 };
-struct Seg { uint32_t a_off; int kpad; const float* src; int ld; int k0; int kvalid; };
+struct Seg { uint32_t a_off; int kpad; const float* src; int ld; int k0; int kvalid; const float* bias = nullptr; int bias_k = -1; };
 
 static void add_acc_group(Plan& pl, const RowSpec& rs, const std::vector<Seg>& segs, int tmem_col,
                           bool dbuf, bool first_of_job, int dep, bool last_of_job, bool onto_existing = false,
@@ -218,6 +220,8 @@ static void add_acc_group(Plan& pl, const RowSpec& rs, const std::vector<Seg>& s
       op.nk8 = nk * 2;
       op.split = pl.cta;
       op.dst_off = pl.data_bytes;
+      op.bias = nullptr; op.bias_k = -1;
+      if (sg.bias_k >= done * 16 && sg.bias_k < (done + nk) * 16) { op.bias = sg.bias; op.bias_k = sg.bias_k - done * 16; }
       pl.pack_ops.push_back(op);
       pl.data_bytes += (size_t)nk * N * 32;
       done += nk;
@@ -291,6 +295,10 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
     add_vec(pl, aw ? aw->ln_g[l] : nul, nul, 0, d.Ha, d.Ha, 1.4426950408889634f);
     add_vec(pl, aw ? aw->ln_b[l] : nul, nul, 0, d.Ha, d.Ha, 1.4426950408889634f);
     jb.p_off = pb;
+    // aux 1: the Linear bias is folded into the GEMM (bias row x the constant-one column 15 of P_a).  Only layer 0:
+    // its [P_s | P_a] panels are contiguous, so the bias rides in the s-part stage; for the other layers it would
+    // cost an extra weight stage per N group (measured: slower than the adds it removes).
+    jb.aux = (early_h && l == 0) ? 1u : 0u;
     pl.jobs.push_back(jb);
     const int nchunks = (d.Ha + 255) / 256;
     for (int nc = 0; nc < nchunks; ++nc) {
@@ -299,8 +307,12 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
       std::vector<Seg> segs;
       if (l == 0) {
         // A = [P_h | P_s]: contiguous panels, source columns [0,D) and [D,D+S)
-        if (!early_h) segs.push_back({pl.off_h, pl.Dp, lw, d.F, 0, d.D});
-        segs.push_back({pl.off_s, pl.Sp, lw, d.F, d.D, d.S_in});
+        if (!early_h) {
+          segs.push_back({pl.off_h, pl.Dp, lw, d.F, 0, d.D});
+          segs.push_back({pl.off_s, pl.Sp, lw, d.F, d.D, d.S_in});
+        } else {   // [P_s | P_a] as one K range: s columns, zeros, and the bias row at the ones column (P_a column 15)
+          segs.push_back({pl.off_s, pl.Sp + pl.Ap, lw, d.F, d.D, d.S_in, aw ? aw->lin_b[l] : nul, pl.Sp + 15});
+        }
       } else {
         segs.push_back({pl.off_x, d.Ha, lw, d.Ha, 0, d.Ha});
       }
@@ -342,7 +354,7 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
   // ---- mu head
   {
     JobDesc jb{};
-    jb.type = JOB_MU; jb.n = 16; jb.tmem_col = 0; jb.dst_off = pl.off_a;
+    jb.type = JOB_MU; jb.n = 16; jb.tmem_col = 0; jb.dst_off = pl.off_a; jb.aux = early_h ? 1u : 0u;
     jb.p_off = add_vec(pl, aw ? aw->mu_b : nul, nul, 0, d.A, 16);
     add_vec(pl, aw ? aw->bound : nul, nul, 0, d.A, 16);
     pl.jobs.push_back(jb);
@@ -526,6 +538,7 @@ __global__ void pack_stage_kernel(const PackOp* __restrict__ ops, uint8_t* __res
       const int k = kc * 8 + e;
       float v = 0.f;
       if (row >= 0 && k < op.kvalid) v = op.src[(size_t)row * op.ld + op.k0 + k];
+      if (op.bias && row >= 0 && k == op.bias_k) v = op.bias[row];
       out[e] = __float2bfloat16_rn(v);
     }
     *reinterpret_cast<uint4*>(data + op.dst_off + (size_t)di * 16) = *reinterpret_cast<const uint4*>(out);
@@ -1260,10 +1273,20 @@ __device__ __forceinline__ void epif_init(const EpiCtxF& c) {
     }
     st_chunk(c.smem_base + p.off_s + k8 * kPSF + c.row * 16, v);
   }
+  // action panel: zeros (it is read as a K segment before the first mu epilogue writes it) and the constant one
+  // in column 15 that carries the folded biases
+  if (c.sidx == 0) {
+    const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+    st_chunk(c.smem_base + p.off_a + c.row * 16, z8);
+    st_chunk(c.smem_base + p.off_a + kPSF + c.row * 16, o8);
+  }
 }
 
 // Linear -> LayerNorm -> ELU.  MMA group mg (<= 256 features) sits in TMEM columns [mg*128, +Ng/2); this lane
 // half owns features mg*256 + hf*Ng/2 + [0, Ng/2).  32-column sub-groups are dealt round-robin to the kQ warps.
+// kBias = false: the Linear bias is already in the accumulators (folded into the GEMM, JobDesc.aux & 1)
+template <bool kBias>
 __device__ __forceinline__ void epif_actor_ln(const EpiCtxF& c, const JobDesc& jb) {
   const TcParams& p = *c.p;
   const uint32_t bias = jb.p_off, gam = bias + p.Ha, bet = gam + p.Ha;
@@ -1280,10 +1303,12 @@ __device__ __forceinline__ void epif_actor_ln(const EpiCtxF& c, const JobDesc& j
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        const float4 b4 = ldc4(bias + f0 + i);
-        float x0, x1, x2, x3;
-        add2(x0, x1, v[i], v[i + 1], b4.x, b4.y);
-        add2(x2, x3, v[i + 2], v[i + 3], b4.z, b4.w);
+        float x0 = v[i], x1 = v[i + 1], x2 = v[i + 2], x3 = v[i + 3];
+        if (kBias) {
+          const float4 b4 = ldc4(bias + f0 + i);
+          add2(x0, x1, x0, x1, b4.x, b4.y);
+          add2(x2, x3, x2, x3, b4.z, b4.w);
+        }
         add2(sum, sum1, sum, sum1, x0, x1);
         add2(sum, sum1, sum, sum1, x2, x3);
         fma2(sq, sq1, x0, x1, x0, x1, sq, sq1);
@@ -1325,12 +1350,14 @@ __device__ __forceinline__ void epif_actor_ln(const EpiCtxF& c, const JobDesc& j
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        const float4 b4 = ldc4(bias + f0 + i);
         const float4 g4 = ldc4(gam + f0 + i);
         const float4 e4 = ldc4(bet + f0 + i);
-        float t0, t1, t2, t3;
-        add2(t0, t1, v[i], v[i + 1], b4.x, b4.y);
-        add2(t2, t3, v[i + 2], v[i + 3], b4.z, b4.w);
+        float t0 = v[i], t1 = v[i + 1], t2 = v[i + 2], t3 = v[i + 3];
+        if (kBias) {
+          const float4 b4 = ldc4(bias + f0 + i);
+          add2(t0, t1, t0, t1, b4.x, b4.y);
+          add2(t2, t3, t2, t3, b4.z, b4.w);
+        }
         fma2(t0, t1, t0, t1, rstd, rstd, nmr, nmr);
         fma2(t2, t3, t2, t3, rstd, rstd, nmr, nmr);
         fma2(t0, t1, t0, t1, g4.x, g4.y, e4.x, e4.y);
@@ -1399,7 +1426,8 @@ __device__ __forceinline__ void epif_mu(const EpiCtxF& c, const JobDesc& jb) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int a = c.hf * 8 + i;
-    v[i] = (a < p.A) ? tanh_fast((v[i] + bv[i]) * p.inv_action_scale) * dv[i] : 0.f;
+    // padding columns are zero, except column 15: the constant one the folded biases multiply (JobDesc.aux & 1)
+    v[i] = (a < p.A) ? tanh_fast((v[i] + bv[i]) * p.inv_action_scale) * dv[i] : ((a == 15 && (jb.aux & 1u)) ? 1.f : 0.f);
     if (c.valid && a < p.A) p.actions[(c.b * p.H + c.t) * p.A + a] = v[i];
   }
   st_chunk(c.smem_base + jb.dst_off + c.hf * kPSF + c.row * 16, v);
@@ -1814,7 +1842,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcPa
             mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
             tc_fence_after();
             if (tr) t_wake = clock64();
-            if (jb.type == JOB_ACTOR_LN) epif_actor_ln(c, jb);
+            if (jb.type == JOB_ACTOR_LN) { if (jb.aux & 1u) epif_actor_ln<false>(c, jb); else epif_actor_ln<true>(c, jb); }
             else if (jb.type == JOB_DENSE_ELU) epif_dense_elu(c, jb);
             else if (jb.type == JOB_MU) epif_mu(c, jb);
           }
@@ -2048,7 +2076,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_pp_kernel(const TcPara
             } else {
               mbar_wait_backoff(accf_bar(tile, job), (job >> 1) & 1u);
               tc_fence_after();
-              if (jb.type == JOB_ACTOR_LN) epif_actor_ln(c, jb);
+              if (jb.type == JOB_ACTOR_LN) { if (jb.aux & 1u) epif_actor_ln<false>(c, jb); else epif_actor_ln<true>(c, jb); }
               else if (jb.type == JOB_DENSE_ELU) epif_dense_elu(c, jb);
               else if (jb.type == JOB_MU) epif_mu(c, jb);
             }
