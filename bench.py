@@ -260,6 +260,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU, pinned to that GPU's NUMA node before any pinned host buffer is allocated
+    from wmrl.parallel import bind_to_gpu_numa
+    numa_bound = bind_to_gpu_numa(local) if os.environ.get("WMRL_BENCH_NO_NUMA") is None else False
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -407,6 +410,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(c, world),
             "clocks": clocks,
+            "host": {"numa_bound": bool(numa_bound)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "note": "pinned host start states + noise -> H2D (prefetched on a copy stream) -> "
                             "RSSM.imagine_rollout -> scalar summary -> D2H, read on the host every step (one step behind the launch)"},

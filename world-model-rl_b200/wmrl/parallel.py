@@ -53,3 +53,25 @@ def reduce_scalar(value: float, device, op=dist.ReduceOp.SUM, group=None) -> flo
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=op, group=group)
     return float(t.item())
+
+
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Pin the calling process to the CPUs NVML reports as local to GPU `device_index` (one process per GPU).
+    Host buffers allocated afterwards (pinned staging memory) are first-touched on that NUMA node, so the per-step
+    host->device copies of 8 ranks do not all cross the socket interconnect.  Best effort: returns False when NVML
+    or the affinity call is unavailable."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
