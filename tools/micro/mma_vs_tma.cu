@@ -10,6 +10,7 @@ __global__ void __launch_bounds__(128, 1) k(const uint8_t* src, int copy_bytes, 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar, cbars[8];
   __shared__ uint32_t tslot;
+  __shared__ volatile long long n_shared, t_mma_end;
     const uint32_t base = smem_u32(smem);
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bar), 1);
@@ -36,7 +37,8 @@ __global__ void __launch_bounds__(128, 1) k(const uint8_t* src, int copy_bytes, 
     tc_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);
     long long t1 = clock64();
-    if (blockIdx.x == 0) out[0] = t1 - t0;
+    t_mma_end = t1;
+    if (blockIdx.x == 0) { out[0] = t1 - t0; out[3] = n_shared; out[4] = t0; }
   } else if (threadIdx.x == 32 && depth > 0) {
     // copy stream into smem [96 KB, 96 KB + depth * copy_bytes): a fixed number of rounds that outlasts the MMA loop
     const int rounds = (iters * 4 * 200) / (400 * 1) + 8;
@@ -50,6 +52,7 @@ __global__ void __launch_bounds__(128, 1) k(const uint8_t* src, int copy_bytes, 
       for (int s = 0; s < depth; ++s) {
         mbar_wait(smem_u32(&cbars[s]), ph);
         ++n;
+        n_shared = n;
         if (r + 1 < rounds) {
           mbar_arrive_expect_tx(smem_u32(&cbars[s]), copy_bytes);
           bulk_g2s(base + 96 * 1024 + s * copy_bytes, src + ((size_t)(n * 7 + s) * copy_bytes) % (1 << 21), copy_bytes,
@@ -72,13 +75,14 @@ int main() {
   for (int bytes : {0, 16384, 32768})
     for (int depth : {1, 2, 3}) {
       if (bytes == 0 && depth > 1) continue;
-      out[0] = out[1] = out[2] = 0;
+      out[0] = out[1] = out[2] = out[3] = out[4] = 0;
       for (int rep = 0; rep < 2; ++rep) k<<<148, 128, 224 * 1024>>>(src, bytes, bytes ? depth : 0, iters, out);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
       const double cyc = (double)out[0];
-      printf("copy stream %5d B x depth %d: %6.1f cycles per MMA (N=256: ideal 128); copy stream %5.1f B/clk\n", bytes,
-             bytes ? depth : 0, cyc / (iters * 4), out[2] ? (double)out[1] * bytes / (double)out[2] : 0.0);
+      printf("copy stream %5d B x depth %d: %6.1f cycles per MMA (ideal 128); copies: %5.1f B/clk over their whole run, %5.1f B/clk while the MMAs ran\n",
+             bytes, bytes ? depth : 0, cyc / (iters * 4), out[2] ? (double)out[1] * bytes / (double)out[2] : 0.0,
+             (double)out[3] * bytes / cyc);
     }
   return 0;
 }

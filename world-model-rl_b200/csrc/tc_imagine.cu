@@ -1600,7 +1600,13 @@ __device__ __forceinline__ void epif_prior2(const EpiCtxF& c, const JobDesc& jb,
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcParams p) {
+// + one warp: its lane 0 (leader CTA) turns the ring's `full` mbarriers into a plain shared-memory counter.  A
+// try_wait on an already-complete mbarrier costs the MMA-issuing lane ~130 cycles per stage that nothing can hide (the
+// tcgen05 queue is ~1 deep: tools/micro/stage_overhead.cu, 515 -> 644 cycles per 8-MMA stage); a shared-memory load of
+// the counter, re-read only when the cached value runs out, costs a fraction of that.
+constexpr int kThreadsFold = kThreads + 32;
+constexpr int kReadyWarp = kMmaWarp + 1;
+__global__ void __launch_bounds__(kThreadsFold, 1) tc_imagine_fold_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t kSlot = p.slot_bytes;
   const uint32_t smem_base = smem_u32(smem);
@@ -1620,7 +1626,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcPa
 
   // per-stage MMA records (see the non-folded kernel); A panels have 64 rows -> LBO = 1024 B
   const uint4* stab = reinterpret_cast<const uint4*>(smem + p.bar_off + kBarBytes);
-  for (int i = threadIdx.x; i < p.nstages; i += kThreads) {
+  for (int i = threadIdx.x; i < p.nstages; i += kThreadsFold) {
     const uint4 raw = c_stages[i];
     const StageDesc st = *reinterpret_cast<const StageDesc*>(&raw);
     uint4 rec;
@@ -1630,7 +1636,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcPa
     rec.w = (uint32_t)st.tmem_col | ((uint32_t)st.dep << 16);
     reinterpret_cast<uint4*>(smem + p.bar_off + kBarBytes)[i] = rec;
   }
+  volatile uint32_t* ready_ctr = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 424);   // stages landed so far
   if (threadIdx.x == 0) {
+    *ready_ctr = 0u;
     for (int s = 0; s < p.nslots; ++s) {
       // leader: a stage is "full" when its own half has landed (producer arrive + tx bytes) AND the peer
       // has forwarded that its half landed -> two arrivals on ONE barrier, one wait per stage
@@ -1690,6 +1698,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcPa
       }
     } else if (lane == 0) {
       uint32_t slot = 0, phase = 0, job = 0;
+      uint32_t g = 0, ready_seen = 0;   // stage sequence number; last value read from the ready counter
       // issue one stage's MMAs and release its slot
 #ifdef WMRL_TC_STAGE_TRACE   // per-stage timing of one job (tools/trace_tc.py); off in production: the lane is latency-critical
       long long* stage_trace = nullptr;   // when set: [2*i] = wait for the stage's weights, [2*i+1] = issue + commit
@@ -1698,7 +1707,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcPa
 #ifdef WMRL_TC_STAGE_TRACE
         const long long w0 = stage_trace ? clock64() : 0;
 #endif
-        mbar_wait(full_bar(slot), phase);
+        if (g >= ready_seen) {
+          do { ready_seen = *ready_ctr; } while (ready_seen <= g);   // published by the kReadyWarp lane below
+        }
+        ++g;
 #ifdef WMRL_TC_STAGE_TRACE
         const long long w1 = stage_trace ? clock64() : 0;
 #endif
@@ -1787,6 +1799,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_fold_kernel(const TcPa
             }
             if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
           }
+        }
+      }
+    }
+  } else if (warp == kReadyWarp) {
+    if (lane == 0 && rank == 0) {
+      // every stage instance in ring order: wait until both halves have landed (own copy + the peer's forwarded
+      // arrival), then publish the count
+      uint32_t slot = 0, phase = 0, n = 0;
+      for (int grp = unit; grp < ngroups; grp += nunits) {
+        const int total = p.H * p.nstages;   // prologue + H steps - the stages the last step skips
+        for (int i = 0; i < total; ++i) {
+          mbar_wait(full_bar(slot), phase);
+          *ready_ctr = ++n;
+          if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
         }
       }
     }
@@ -2174,7 +2200,10 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
     cfg.attrs = at;
     cfg.numAttrs = 1;
     if (pl.pp) WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_pp_kernel, p));
-    else if (pl.fold) WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_fold_kernel, p));
+    else if (pl.fold) {
+      cfg.blockDim = dim3(kThreadsFold);
+      WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_fold_kernel, p));
+    }
     else if (p.trace) WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_kernel<2, true>, p));
     else WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_imagine_kernel<2, false>, p));
   } else {
