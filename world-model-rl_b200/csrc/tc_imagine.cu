@@ -1699,6 +1699,8 @@ __global__ void __launch_bounds__(kThreadsFold, 1) tc_imagine_fold_kernel(const 
     } else if (lane == 0) {
       uint32_t slot = 0, phase = 0, job = 0;
       uint32_t g = 0, ready_seen = 0;   // stage sequence number; last value read from the ready counter
+      const uint32_t bslot0 = (ring >> 4) & 0x3FFFu, bslot_step = kSlot >> 4;
+      uint32_t bslot = bslot0;          // descriptor address field of the current ring slot
       // issue one stage's MMAs and release its slot
 #ifdef WMRL_TC_STAGE_TRACE   // per-stage timing of one job (tools/trace_tc.py); off in production: the lane is latency-critical
       long long* stage_trace = nullptr;   // when set: [2*i] = wait for the stage's weights, [2*i+1] = issue + commit
@@ -1715,12 +1717,12 @@ __global__ void __launch_bounds__(kThreadsFold, 1) tc_imagine_fold_kernel(const 
         const long long w1 = stage_trace ? clock64() : 0;
 #endif
         tc_fence_after();
-        const uint32_t tm = tmem_base + (rec.w & 0xFFFFu) + ((flags & ST_DBUF) ? (job & 1u) * 256u : 0u);
+        // (mode 3 places every accumulator statically: no ST_DBUF here)
+        const uint32_t tm = tmem_base + (rec.w & 0xFFFFu);
         const uint32_t idesc = rec.y;
-        const uint32_t nh = rec.z >> 16;
         uint32_t alo = rec.x;
-        uint32_t blo = (((ring + slot * kSlot) >> 4) & 0x3FFFu) | (nh << 16);
-        const uint32_t bstep = nh * 2u;
+        uint32_t blo = bslot | (rec.z & 0xFFFF0000u);       // slot address field | LBO field (N/2 rows x 16 B)
+        const uint32_t bstep = (rec.z >> 16) * 2u;
         constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
         uint32_t acc = (flags & ST_FIRST_ACC) ? 0u : 1u;
         const uint32_t nk = (rec.z >> 8) & 0xFFu;
@@ -1764,7 +1766,8 @@ __global__ void __launch_bounds__(kThreadsFold, 1) tc_imagine_fold_kernel(const 
               waited = true;
             }
             run_stage(rec, flags);
-            if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+            bslot += bslot_step;
+            if (++slot == (uint32_t)p.nslots) { slot = 0; bslot = bslot0; }
           }
         }
         for (int t = 0; t < p.H; ++t) {
@@ -1797,7 +1800,8 @@ __global__ void __launch_bounds__(kThreadsFold, 1) tc_imagine_fold_kernel(const 
               if (tr && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 1] = clock64();
               ++job;
             }
-            if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
+            bslot += bslot_step;
+            if (++slot == (uint32_t)p.nslots) { slot = 0; bslot = bslot0; }
           }
         }
       }
