@@ -1,3 +1,4 @@
+"""Time the 3xTF32 GEMM at the 2 500-row shapes of BASELINE configs[0..2] (includes ~20 us of Python/ctypes per call)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "world-model-rl_b200")]
@@ -16,4 +17,4 @@ for M, N, K in [(2500, 600, 600), (2500, 1800, 600), (2500, 512, 1624), (2500, 5
     x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5; b = torch.randn(N, device="cuda")
     with torch.no_grad():
         out.append(f"{t(lambda: F.linear(x, w, b, 0))*1e3:6.1f}")
-print(f"minbn={os.environ.get('WMRL_TG_MINBN','64'):>3} want={os.environ.get('WMRL_TG_WANT','148'):>3}: " + " ".join(out) + " us", flush=True)
+print("wmrl.functional.linear at 2 500 rows, (N, K) = (600,600) (1800,600) (512,1624) (512,512) (600,1030) (1024,600): " + " ".join(out) + " us", flush=True)
