@@ -1515,6 +1515,8 @@ __device__ __forceinline__ void epsf_prefetch(const EpiCtxF& c, float (&e)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) e[i] = (c.valid && c.q * 8 < p.Sp / 2 && col + i < p.S) ? eps[col + i] : 0.f;
 }
+__device__ __forceinline__ void epif_prior2_copyout(const EpiCtxF& c);
+template <bool kCopyOut>
 __device__ __forceinline__ void epif_prior2(const EpiCtxF& c, const JobDesc& jb, const float (&e0)[8]) {
   const TcParams& p = *c.p;
   const uint32_t b_m = jb.p_off, b_s = b_m + p.Sp;
@@ -1574,6 +1576,16 @@ __device__ __forceinline__ void epif_prior2(const EpiCtxF& c, const JobDesc& jb,
                  "r"(a), "r"(b), "r"(cc), "r"(d)
                  : "memory");
   }
+  if (kCopyOut) epif_prior2_copyout(c);
+}
+
+// Coalesced copy-out of the rows staged by epif_prior2 (mean / std / stoch of this step).  Mode 3 runs it AFTER the
+// job has been signalled done: the next job only needs P_s, which is final before this.  The staging region (head of
+// X) is next written by these same warps (LayerNorm scratch of the following epilogue); the closing barrier keeps a
+// fast warp from getting there while a slow one is still reading.
+__device__ __forceinline__ void epif_prior2_copyout(const EpiCtxF& c) {
+  const TcParams& p = *c.p;
+  const long long T1 = p.H + 1;
   if (p.stage_out) {
     asm volatile("bar.sync 5, %0;" ::"r"(kEpiThreads) : "memory");
     const int warp = c.q * 4 + c.quarter;
@@ -1597,6 +1609,7 @@ __device__ __forceinline__ void epif_prior2(const EpiCtxF& c, const JobDesc& jb,
         p.stoch_seq[off + col] = v2;
       }
     }
+    asm volatile("bar.sync 5, %0;" ::"r"(kEpiThreads) : "memory");
   }
 }
 
@@ -1867,7 +1880,7 @@ __global__ void __launch_bounds__(kThreadsFold, 1) tc_imagine_fold_kernel(const 
             mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
             tc_fence_after();
             if (tr) t_wake = clock64();
-            epif_prior2(c, jb, e0);
+            epif_prior2<false>(c, jb, e0);
           } else {
             mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
             tc_fence_after();
@@ -1884,6 +1897,7 @@ __global__ void __launch_bounds__(kThreadsFold, 1) tc_imagine_fold_kernel(const 
           }
           WMRL_JOB_DONE_F(job);
           ++job;
+          if (jb.type == JOB_PRIOR2_CONT) epif_prior2_copyout(c);   // off the critical path: after the job-done signal
         }
       }
     }
@@ -2102,7 +2116,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_imagine_pp_kernel(const TcPara
               epsf_prefetch(c, e0);
               mbar_wait_backoff(accf_bar(tile, job), (job >> 1) & 1u);
               tc_fence_after();
-              epif_prior2(c, jb, e0);
+              epif_prior2<true>(c, jb, e0);
             } else {
               mbar_wait_backoff(accf_bar(tile, job), (job >> 1) & 1u);
               tc_fence_after();
