@@ -1567,15 +1567,6 @@ __device__ __forceinline__ void epif_prior2(const EpiCtxF& c, const JobDesc& jb,
     }
     st_chunk(c.smem_base + jb.dst_off + (col / 8) * kPSF + c.row * 16, st);
   }
-  // h' (X[h2..]) -> P_h
-  for (int k8 = c.sidx; k8 < p.Dp / 8; k8 += 2 * kQ) {
-    uint32_t a, b, cc, d;
-    const uint32_t src = c.smem_base + p.off_h2 + k8 * kPSF + c.row * 16;
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(cc), "=r"(d) : "r"(src) : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(c.smem_base + p.off_h + k8 * kPSF + c.row * 16),
-                 "r"(a), "r"(b), "r"(cc), "r"(d)
-                 : "memory");
-  }
   if (kCopyOut) epif_prior2_copyout(c);
 }
 
@@ -1586,6 +1577,18 @@ __device__ __forceinline__ void epif_prior2(const EpiCtxF& c, const JobDesc& jb,
 __device__ __forceinline__ void epif_prior2_copyout(const EpiCtxF& c) {
   const TcParams& p = *c.p;
   const long long T1 = p.H + 1;
+  // (only the next step's GRU reads P_h; the epilogue in between publishes this copy to the async proxy with its own
+  //  fence + job-done arrive)
+  // h' (X[h2..]) -> P_h
+  for (int k8 = c.sidx; k8 < p.Dp / 8; k8 += 2 * kQ) {
+    uint32_t a, b, cc, d;
+    const uint32_t src = c.smem_base + p.off_h2 + k8 * kPSF + c.row * 16;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(cc), "=r"(d) : "r"(src) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(c.smem_base + p.off_h + k8 * kPSF + c.row * 16),
+                 "r"(a), "r"(b), "r"(cc), "r"(d)
+                 : "memory");
+  }
+  fence_proxy_async_smem();
   if (p.stage_out) {
     asm volatile("bar.sync 5, %0;" ::"r"(kEpiThreads) : "memory");
     const int warp = c.q * 4 + c.quarter;
