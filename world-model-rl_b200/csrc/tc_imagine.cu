@@ -1292,27 +1292,39 @@ __device__ __forceinline__ void epif_actor_ln(const EpiCtxF& c, const JobDesc& j
   const uint32_t bias = jb.p_off, gam = bias + p.Ha, bet = gam + p.Ha;
   const int nmg = (p.Ha + 255) / 256;
   float sum = 0.f, sq = 0.f, sum1 = 0.f, sq1 = 0.f;   // two partial sums each: packed f32x2 arithmetic
-  int li = 0;
-  for (int mg = 0; mg < nmg; ++mg) {
-    const int hw = min(256, p.Ha - mg * 256) / 2;
-    for (int sub = 0; sub < hw / 32; ++sub, ++li) {
-      if ((li % kQ) != c.q) continue;
-      const int f0 = mg * 256 + c.hf * hw + sub * 32;
-      float v[32];
-      tmem_ld32(c.tmem_lane + jb.tmem_col + mg * 128 + sub * 32, v);
-      tmem_ld_wait();
+  auto pass1 = [&](const float (&v)[32], int f0) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float x0 = v[i], x1 = v[i + 1], x2 = v[i + 2], x3 = v[i + 3];
-        if (kBias) {
-          const float4 b4 = ldc4(bias + f0 + i);
-          add2(x0, x1, x0, x1, b4.x, b4.y);
-          add2(x2, x3, x2, x3, b4.z, b4.w);
-        }
-        add2(sum, sum1, sum, sum1, x0, x1);
-        add2(sum, sum1, sum, sum1, x2, x3);
-        fma2(sq, sq1, x0, x1, x0, x1, sq, sq1);
-        fma2(sq, sq1, x2, x3, x2, x3, sq, sq1);
+    for (int i = 0; i < 32; i += 4) {
+      float x0 = v[i], x1 = v[i + 1], x2 = v[i + 2], x3 = v[i + 3];
+      if (kBias) {
+        const float4 b4 = ldc4(bias + f0 + i);
+        add2(x0, x1, x0, x1, b4.x, b4.y);
+        add2(x2, x3, x2, x3, b4.z, b4.w);
+      }
+      add2(sum, sum1, sum, sum1, x0, x1);
+      add2(sum, sum1, sum, sum1, x2, x3);
+      fma2(sq, sq1, x0, x1, x0, x1, sq, sq1);
+      fma2(sq, sq1, x2, x3, x2, x3, sq, sq1);
+    }
+  };
+  int li = 0;
+  if (p.Ha == 512) {
+    // the usual width: this thread's two sub-groups (one per MMA group); both TMEM loads in flight before the wait
+    float v0[32], v1[32];
+    tmem_ld32(c.tmem_lane + jb.tmem_col + c.q * 32, v0);
+    tmem_ld32(c.tmem_lane + jb.tmem_col + 128 + c.q * 32, v1);
+    tmem_ld_wait();
+    pass1(v0, c.hf * 128 + c.q * 32);
+    pass1(v1, 256 + c.hf * 128 + c.q * 32);
+  } else {
+    for (int mg = 0; mg < nmg; ++mg) {
+      const int hw = min(256, p.Ha - mg * 256) / 2;
+      for (int sub = 0; sub < hw / 32; ++sub, ++li) {
+        if ((li % kQ) != c.q) continue;
+        float v[32];
+        tmem_ld32(c.tmem_lane + jb.tmem_col + mg * 128 + sub * 32, v);
+        tmem_ld_wait();
+        pass1(v, mg * 256 + c.hf * hw + sub * 32);
       }
     }
   }
