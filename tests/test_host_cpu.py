@@ -128,3 +128,41 @@ def test_shard_range_partitions():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         sizes = [hi - lo for lo, hi in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_linear_and_ln_entry_points_reject_bad_arguments_without_gpu():
+    lib = _lib.load()
+    assert lib.wmrl_linear_fwd(4, 0, 8, None, 8, None, None, None, 4, 0, None) != 0          # N = 0
+    assert b"shape" in lib.wmrl_last_error()
+    assert lib.wmrl_linear_fwd(4, 4, 8, None, 8, None, None, None, 4, 3, None) != 0          # unknown activation
+    assert lib.wmrl_linear_fwd(4, 4, 8, None, 8, None, None, None, 4, 0, None) != 0          # NULL tensors
+    assert b"NULL" in lib.wmrl_last_error()
+    assert lib.wmrl_linear_fwd(0, 4, 8, None, 8, None, None, None, 4, 0, None) == 0          # empty batch: no-op
+    assert lib.wmrl_linear_dgrad(4, 4, 8, None, 4, None, None, 8, 0, None) != 0
+    assert lib.wmrl_linear_wgrad(4, 4, 8, None, 4, None, 8, None, None) != 0
+    assert lib.wmrl_ln_act_fwd(4, 8, None, None, None, 5, None, None, None, None) != 0       # act out of range
+    assert lib.wmrl_ln_act_fwd(0, 8, None, None, None, 1, None, None, None, None) == 0
+    assert lib.wmrl_ln_act_bwd(4, 8, None, None, None, None, None, 1, None, None, None, None) != 0
+
+
+def test_heads_run_their_own_modules_on_cpu_tensors():
+    """DenseModel / ValueCritic keep the reference's module tree; on CPU tensors (adjacent code, not the path) the
+    torch modules themselves run - same numbers as the plain nn.Sequential."""
+    torch.manual_seed(0)
+    m = wmrl.DenseModel(depth=2, input_dim=12, hidden_dim=16, output_dim=3, output_act=torch.nn.Sigmoid)
+    x = torch.randn(5, 7, 12)
+    assert torch.equal(m(x), torch.sigmoid(m.fc(x)))
+    c = wmrl.ValueCritic(12, num_layers=2, hidden_dim=16)
+    assert torch.equal(c(x), c.layers(x))
+    from wmrl.functional import mlp_forward
+    seq = torch.nn.Sequential(torch.nn.Linear(12, 8), torch.nn.Tanh(), torch.nn.Linear(8, 2))   # not the head pattern
+    assert torch.equal(mlp_forward(seq, x), seq(x))
+
+
+def test_numa_binding_is_best_effort():
+    from wmrl.parallel import bind_to_gpu_numa
+    import os
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa(0) in (True, False)      # no NVML / no GPU here -> False, never raises
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
