@@ -278,8 +278,6 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
   auto tc = [&](int n) { return pl.fold ? n / 2 : n; };
 
   const float* nul = nullptr;
-  auto W = [&](const float* const* p) { return p ? *p : nul; };
-  (void)W;
   const int Ke = d.S_in + d.A;
   // Folded pairs: the h part of the first actor layer (13 of its 15 K steps at C4) does not depend on the
   // prior head, so its MMAs for step t+1 are issued right after the prior2 MMAs of step t and run under
@@ -1725,7 +1723,7 @@ __global__ void __launch_bounds__(kThreadsFold, 1) tc_imagine_fold_kernel(const 
         }
       }
     } else if (lane == 0) {
-      uint32_t slot = 0, phase = 0, job = 0;
+      uint32_t slot = 0, job = 0;
       uint32_t g = 0, ready_seen = 0;   // stage sequence number; last value read from the ready counter
       const uint32_t bslot0 = (ring >> 4) & 0x3FFFu, bslot_step = kSlot >> 4;
       uint32_t bslot = bslot0;          // descriptor address field of the current ring slot
