@@ -1577,6 +1577,24 @@ __device__ __forceinline__ void epif_prior2(const EpiCtxF& c, const JobDesc& jb,
     }
     st_chunk(c.smem_base + jb.dst_off + (col / 8) * kPSF + c.row * 16, st);
   }
+  // h' (X[h2..]) -> P_h for the next step's GRU.  Independent of this job's accumulators: done by the warps that have
+  // no latent columns here (q >= active) while the others do the head's math; with every warp active, by all.
+  {
+    const int active = min(kQ, (hw + 7) / 8);     // warps per lane quarter that own a sub-group of latent columns
+    const bool all = active >= kQ;
+    if (all || c.q >= active) {
+      const int nhelp = all ? 2 * kQ : 2 * (kQ - active);
+      const int idx = all ? c.sidx : c.hf * (kQ - active) + (c.q - active);
+      for (int k8 = idx; k8 < p.Dp / 8; k8 += nhelp) {
+        uint32_t a, b, cc, d;
+        const uint32_t src = c.smem_base + p.off_h2 + k8 * kPSF + c.row * 16;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(cc), "=r"(d) : "r"(src) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(c.smem_base + p.off_h + k8 * kPSF + c.row * 16),
+                     "r"(a), "r"(b), "r"(cc), "r"(d)
+                     : "memory");
+      }
+    }
+  }
   if (kCopyOut) epif_prior2_copyout(c);
 }
 
@@ -1587,18 +1605,6 @@ __device__ __forceinline__ void epif_prior2(const EpiCtxF& c, const JobDesc& jb,
 __device__ __forceinline__ void epif_prior2_copyout(const EpiCtxF& c) {
   const TcParams& p = *c.p;
   const long long T1 = p.H + 1;
-  // (only the next step's GRU reads P_h; the epilogue in between publishes this copy to the async proxy with its own
-  //  fence + job-done arrive)
-  // h' (X[h2..]) -> P_h
-  for (int k8 = c.sidx; k8 < p.Dp / 8; k8 += 2 * kQ) {
-    uint32_t a, b, cc, d;
-    const uint32_t src = c.smem_base + p.off_h2 + k8 * kPSF + c.row * 16;
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(cc), "=r"(d) : "r"(src) : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(c.smem_base + p.off_h + k8 * kPSF + c.row * 16),
-                 "r"(a), "r"(b), "r"(cc), "r"(d)
-                 : "memory");
-  }
-  fence_proxy_async_smem();
   if (p.stage_out) {
     asm volatile("bar.sync 5, %0;" ::"r"(kEpiThreads) : "memory");
     const int warp = c.q * 4 + c.quarter;
