@@ -324,6 +324,9 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
     col0 = 0;
     for (int i = 0; i <= c; ++i) {
       cw = (gru_groups / gru_nchunks + (i < gru_groups % gru_nchunks ? 1 : 0)) * 16;
+      // early_h, two chunks: chunk 0 as wide as its TMEM half allows (128 state columns = 256 TMEM columns) - more of
+      // the h-side work is hoisted and the second chunk's epilogue, which nothing overlaps, gets shorter
+      if (early_h && gru_nchunks == 2) cw = (i == 0) ? std::min(kGruChunk, pl.Dp) : pl.Dp - std::min(kGruChunk, pl.Dp);
       if (i < c) col0 += cw;
     }
   };
@@ -386,12 +389,10 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
     // Chunks of up to 128 state columns (4 accumulators per column = up to 512 TMEM columns), balanced
     // in units of 16.  Wide chunks halve the number of MMAs (each costs >= ~61 cycles whatever its N)
     // and of weight stages; the chunks run serially (MMA -> epilogue -> next chunk).
-    const int groups = pl.Dp / 16;
-    const int nchunks = (pl.Dp + kGruChunk - 1) / kGruChunk;
-    int col0 = 0;
+    const int nchunks = gru_nchunks;
     for (int c = 0; c < nchunks; ++c) {
-      const int gcount = groups / nchunks + (c < groups % nchunks ? 1 : 0);
-      const int cw = gcount * 16;
+      int col0, cw;
+      gru_geom(c, col0, cw);
       const int valid = std::max(0, std::min(cw, d.D - col0));
       JobDesc jb{};
       jb.type = JOB_GRU; jb.dbuf = (pl.fold && !pl.pp && !early_h) ? 1 : 0; jb.n = (uint16_t)cw;
@@ -431,7 +432,6 @@ static Plan make_plan_mode(const Dims& d, const wmrl_rssm_params* w, const wmrl_
         add_acc_group(pl, rn, {{pl.off_x, pl.Dp, wih, d.D, 0, d.D}}, 2 * cw, false, false, 0, false);
         add_acc_group(pl, rn, {{pl.off_h, pl.Dp, whh, d.D, 0, d.D}}, 3 * cw, false, false, 0, true);
       }
-      col0 += cw;
     }
   }
   // ---- prior head
