@@ -43,6 +43,23 @@ Weights = Dict[str, torch.Tensor]
 
 
 # --------------------------------------------------------------------------
+# bf16 operand emulation (checker for the tcgen05 path)
+# --------------------------------------------------------------------------
+def bf16_round(x: torch.Tensor) -> torch.Tensor:
+    """round-to-nearest-even to bf16 and back: what a tcgen05 kind::f16 operand holds."""
+    return x.to(torch.bfloat16).to(x.dtype)
+
+
+def _lin(x, w, b, emu: bool):
+    """F.linear; with ``emu`` both MMA operands (activation panel and weight) are rounded to bf16 and
+    the products accumulate in fp32 - the arithmetic of the bf16 tcgen05 kernels (bias added in fp32
+    by the epilogue)."""
+    if emu:
+        return F.linear(bf16_round(x), bf16_round(w), b)
+    return F.linear(x, w, b)
+
+
+# --------------------------------------------------------------------------
 # Actor  (components/models/actor.py)
 # --------------------------------------------------------------------------
 def actor_num_layers(aw: Weights) -> int:
@@ -53,21 +70,25 @@ def actor_num_layers(aw: Weights) -> int:
     return n
 
 
-def actor_hidden(aw: Weights, x: torch.Tensor) -> torch.Tensor:
-    """[Linear, LayerNorm(eps=1e-5), ELU] x La  (actor.py:23-37, 48)."""
+def actor_hidden(aw: Weights, x: torch.Tensor, emu: bool = False, bias0_bf16: bool = False) -> torch.Tensor:
+    """[Linear, LayerNorm(eps=1e-5), ELU] x La  (actor.py:23-37, 48).  ``emu``: bf16 MMA operands;
+    ``bias0_bf16``: the first layer's bias rides inside the GEMM as a bf16 weight row (folded-pair kernel)."""
     for l in range(actor_num_layers(aw)):
         w, b = aw[f"layers.{3 * l}.weight"], aw[f"layers.{3 * l}.bias"]
         g, be = aw[f"layers.{3 * l + 1}.weight"], aw[f"layers.{3 * l + 1}.bias"]
-        x = F.linear(x, w, b)
+        if emu and bias0_bf16 and l == 0:
+            b = bf16_round(b)
+        x = _lin(x, w, b, emu)
         x = F.layer_norm(x, (w.shape[0],), g, be, 1e-5)
         x = F.elu(x)
     return x
 
 
-def actor_mu(aw: Weights, x: torch.Tensor, action_scale: float, bound: torch.Tensor) -> torch.Tensor:
+def actor_mu(aw: Weights, x: torch.Tensor, action_scale: float, bound: torch.Tensor, emu: bool = False,
+             bias0_bf16: bool = False) -> torch.Tensor:
     """deterministic action: tanh(mu / action_scale) * bound  (actor.py:48-52)."""
-    hid = actor_hidden(aw, x)
-    mu = F.linear(hid, aw["mu.weight"], aw["mu.bias"])
+    hid = actor_hidden(aw, x, emu, bias0_bf16)
+    mu = _lin(hid, aw["mu.weight"], aw["mu.bias"], emu)
     return torch.tanh(mu / action_scale) * bound
 
 
@@ -97,7 +118,7 @@ def categorical_probs(logits: torch.Tensor) -> torch.Tensor:
     return F.softmax(ln, dim=-1)
 
 
-def gen_stoch_discrete(out: torch.Tensor, C: int, S: int, q: torch.Tensor):
+def gen_stoch_discrete(out: torch.Tensor, C: int, S: int, q: torch.Tensor, forced_idx: Optional[torch.Tensor] = None):
     """logits = out.reshape(B, num_categories, stoch_size) (rssm.py:223) - the
     categorical axis is the LAST one (size ``stoch_size``).  sample =
     one_hot(argmax(p/q)) + (p - p.detach())  (state/discrete.py:27-32,
@@ -105,6 +126,9 @@ def gen_stoch_discrete(out: torch.Tensor, C: int, S: int, q: torch.Tensor):
     logits = out.reshape(-1, C, S)
     p = categorical_probs(logits)
     idx = torch.argmax(p.detach() / q.reshape(-1, C, S), dim=-1)
+    if forced_idx is not None:      # replay of a recorded trajectory (test helper): idx stays the oracle's own draw
+        onehot = F.one_hot(forced_idx.reshape(-1, C).long(), S).to(p.dtype)
+        return (onehot + (p - p.detach())).reshape(-1, C * S), logits, idx
     onehot = F.one_hot(idx, S).to(p.dtype)
     stoch = onehot + (p - p.detach())
     return stoch.reshape(-1, C * S), logits, idx
@@ -113,10 +137,11 @@ def gen_stoch_discrete(out: torch.Tensor, C: int, S: int, q: torch.Tensor):
 # --------------------------------------------------------------------------
 # RSSM single steps (rssm.py:53-91)
 # --------------------------------------------------------------------------
-def gru_cell(w: Weights, x: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
-    """torch.nn.GRUCell, gate order r,z,n; b_hn inside r*(.) (rssm.py:28,66)."""
-    gi = F.linear(x, w["rnn.weight_ih"], w["rnn.bias_ih"])
-    gh = F.linear(h, w["rnn.weight_hh"], w["rnn.bias_hh"])
+def gru_cell(w: Weights, x: torch.Tensor, h: torch.Tensor, emu: bool = False) -> torch.Tensor:
+    """torch.nn.GRUCell, gate order r,z,n; b_hn inside r*(.) (rssm.py:28,66).  ``emu``: the two GEMMs read
+    bf16 operands; the convex update keeps the fp32 master copy of h."""
+    gi = _lin(x, w["rnn.weight_ih"], w["rnn.bias_ih"], emu)
+    gh = _lin(h, w["rnn.weight_hh"], w["rnn.bias_hh"], emu)
     i_r, i_z, i_n = gi.chunk(3, -1)
     h_r, h_z, h_n = gh.chunk(3, -1)
     r = torch.sigmoid(i_r + h_r)
@@ -125,13 +150,13 @@ def gru_cell(w: Weights, x: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
     return (1.0 - z) * n + z * h
 
 
-def prior_deter(w: Weights, stoch: torch.Tensor, action: torch.Tensor, deter: torch.Tensor):
+def prior_deter(w: Weights, stoch: torch.Tensor, action: torch.Tensor, deter: torch.Tensor, emu: bool = False):
     """cat(stoch, a) -> Linear -> ELU -> GRUCell -> prior head (rssm.py:64-67)."""
     sa = torch.cat([stoch, action], dim=-1)
-    x = F.elu(F.linear(sa, w["fc_state_action_embed.weight"], w["fc_state_action_embed.bias"]))
-    h = gru_cell(w, x, deter)
-    hid = F.elu(F.linear(h, w["state_prior.0.weight"], w["state_prior.0.bias"]))
-    out = F.linear(hid, w["state_prior.2.weight"], w["state_prior.2.bias"])
+    x = F.elu(_lin(sa, w["fc_state_action_embed.weight"], w["fc_state_action_embed.bias"], emu))
+    h = gru_cell(w, x, deter, emu)
+    hid = F.elu(_lin(h, w["state_prior.0.weight"], w["state_prior.0.bias"], emu))
+    out = _lin(hid, w["state_prior.2.weight"], w["state_prior.2.bias"], emu)
     return h, out
 
 
@@ -157,8 +182,21 @@ def imagine_rollout(
     C: int = 1,
     action_scale: float = 5.0,
     bound: Optional[torch.Tensor] = None,
+    emulate_bf16: bool = False,
+    bias0_bf16: bool = True,
+    forced_idx: Optional[torch.Tensor] = None,
 ):
     """RSSMBase.imagine_rollout (rssm.py:123-140).
+
+    ``forced_idx`` [B,H,C] (discrete): the one-hot sample fed forward is taken from these indices instead
+    of the oracle's own argmax (which is still returned in ``idx``) - used to replay a long recorded
+    trajectory so that a single near-tie flip does not turn a gradient comparison into chaos.
+
+    ``emulate_bf16``: same op order, but every GEMM reads its activation panel and its weight rounded to
+    bf16 and accumulates in fp32 - the rounding points of the bf16 tcgen05 kernels (state, latent, action,
+    hidden activations; fp32 master copy of h in the GRU update; fp32 biases except, with ``bias0_bf16``,
+    the first actor layer's, which the folded-pair kernel carries inside the GEMM).  It pins FREE-RUNNING
+    multi-step parity of that path: what is left is accumulation order and tanh.approx / ex2.approx.
 
     Per step: features.detach() -> actor(deterministic=True) -> prior.  Returns
     per-step lists stacked on dim 1 WITHOUT the index-0 slot (the caller owns
@@ -172,14 +210,15 @@ def imagine_rollout(
     o_deter, o_stoch, o_a, o_d1, o_d2, o_idx = [], [], [], [], [], []
     for t in range(n_steps):
         feat = torch.cat([deter, stoch], dim=-1).detach()          # rssm.py:135
-        action = actor_mu(aw, feat, action_scale, bound)            # rssm.py:136
-        deter, out = prior_deter(w, stoch, action, deter)           # rssm.py:137
+        action = actor_mu(aw, feat, action_scale, bound, emulate_bf16, bias0_bf16)   # rssm.py:136
+        deter, out = prior_deter(w, stoch, action, deter, emulate_bf16)              # rssm.py:137
         if variant == "continuous":
             stoch, mean, std = gen_stoch_continuous(out, S, noise[t])
             o_d1.append(mean)
             o_d2.append(std)
         else:
-            stoch, logits, idx = gen_stoch_discrete(out, C, S, noise[t])
+            stoch, logits, idx = gen_stoch_discrete(out, C, S, noise[t],
+                                                    None if forced_idx is None else forced_idx[:, t])
             o_d1.append(logits)
             o_idx.append(idx)
         o_deter.append(deter)

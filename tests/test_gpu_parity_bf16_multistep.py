@@ -1,0 +1,125 @@
+"""GPU parity of the bf16 tcgen05 rollout kernel over ALL H steps, FREE-RUNNING.
+
+The teacher-forced test (test_gpu_parity_bf16.py) restarts every step from the oracle state, so it never
+exercises what the persistent kernel carries from step to step on-chip: the hoisted next-step MMAs (ST_PRE
+stages), the h' -> P_h hand-over, the static-TMEM-half GRU chunks.  Here the kernel runs H = 15 steps on
+its own and is held to ``oracle.imagine_rollout(..., emulate_bf16=True)``: the reference algorithm
+(rssm.py:123-140) with every GEMM operand rounded to bf16 exactly where the kernel rounds it (activation
+panels, weights, the folded first-layer bias) and fp32 accumulation.  What remains between the two is
+accumulation order and the hardware approximations in the epilogues (tanh.approx: 2^-11 relative,
+ex2.approx), so the tolerance is tight and ABSOLUTE - no relative term, no floor on top:
+
+    |kernel - emulated oracle| <= 2e-3 on deter / mean / std / stoch / actions, every step, every row
+
+(all fields are O(1)).  Against the plain fp32 oracle the same rollout stays within the north-star's
+bf16 tolerance band (rtol 1e-2 on the Frobenius norm per field).
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import rssm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-3
+C4 = (200, 30, 200, 6, 512, 3)   # D, S, Hd, A, Ha, La  (BASELINE configs[0] / configs[3] dims)
+
+
+def _setup(D, S, Hd, A, Ha, La, seed=3):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import helpers_gpu as HG
+    from wmrl import _lib
+    if not _lib.load().wmrl_device_supports_bf16():
+        pytest.skip("not an sm_100 device")
+    rssm, actor = HG.build_modules("continuous", D, S, 1, Hd, 64, A, Ha, La, bound=1.0, seed=seed, precision="bf16")
+    return HG, rssm, actor
+
+
+def _bias_folded() -> bool:
+    # only the default folded-pair kernel (mode 3) carries the first actor bias inside the GEMM
+    return os.environ.get("WMRL_TC_MODE", "3")[:1] == "3"
+
+
+def _compare(seq, actions, ref, rows=None, tol=TOL):
+    sel = (lambda t: t) if rows is None else (lambda t: t[rows])
+    worst = {}
+    for name, got, want in [("deter", seq.deter_states[:, 1:], ref["deter"]), ("stoch", seq.stoch_states[:, 1:], ref["stoch"]),
+                            ("mean", seq.means[:, 1:], ref["mean"]), ("std", seq.stds[:, 1:], ref["std"]),
+                            ("actions", actions, ref["actions"])]:
+        err = (sel(got).detach().cpu().float() - want).abs()
+        per_step = err.amax(dim=(0, 2))
+        worst[name] = float(err.max())
+        assert worst[name] <= tol, f"{name}: max |err| {worst[name]:.3e} > {tol} (per step: {per_step.tolist()})"
+    return worst
+
+
+@pytest.mark.parametrize("B", [300, 64, 1])
+def test_bf16_free_running_vs_bf16_oracle(B):
+    """B = 300: two full 128-row tiles + a ragged one; 64: one CTA of a pair idle; 1: a single row."""
+    D, S, Hd, A, Ha, La = C4
+    HG, rssm, actor = _setup(D, S, Hd, A, Ha, La)
+    H = 15
+    deter0, stoch0, noise = HG.synth_inputs("continuous", B, H, D, S, 1)
+    init = HG.init_state(rssm, deter0, stoch0)
+    w, aw = HG.cpu_weights(rssm), HG.cpu_weights(actor)
+    with torch.no_grad():
+        seq, actions = rssm.imagine_rollout(init, actor, H, noise=noise.cuda(), return_actions=True)
+        ref = O.imagine_rollout("continuous", w, aw, deter0, stoch0, noise, H, S, emulate_bf16=True,
+                                bias0_bf16=_bias_folded())
+        ref32 = O.imagine_rollout("continuous", w, aw, deter0, stoch0, noise, H, S)
+    worst = _compare(seq, actions, ref)
+    print("free-running max |err| vs bf16-emulating oracle:", worst)
+    # and the north-star band against the plain fp32 reference arithmetic
+    for name, got, want in [("deter", seq.deter_states[:, 1:], ref32["deter"]), ("mean", seq.means[:, 1:], ref32["mean"]),
+                            ("std", seq.stds[:, 1:], ref32["std"]), ("actions", actions, ref32["actions"])]:
+        rel = float((got.cpu() - want).norm() / want.norm())
+        assert rel <= 1e-2, f"{name}: relative Frobenius error vs fp32 oracle {rel:.3e}"
+
+
+def test_bf16_free_running_other_shapes():
+    """shapes that take other table layouts: one GRU chunk, Hd > D, a single actor block."""
+    for D, S, Hd, A, Ha, La in [(32, 8, 32, 1, 64, 2), (48, 16, 96, 3, 128, 1), (120, 24, 120, 4, 256, 3)]:
+        HG, rssm, actor = _setup(D, S, Hd, A, Ha, La)
+        B, H = 200, 12
+        deter0, stoch0, noise = HG.synth_inputs("continuous", B, H, D, S, 1)
+        init = HG.init_state(rssm, deter0, stoch0)
+        with torch.no_grad():
+            seq, actions = rssm.imagine_rollout(init, actor, H, noise=noise.cuda(), return_actions=True)
+            ref = O.imagine_rollout("continuous", HG.cpu_weights(rssm), HG.cpu_weights(actor), deter0, stoch0, noise,
+                                    H, S, emulate_bf16=True, bias0_bf16=_bias_folded())
+        _compare(seq, actions, ref)
+
+
+@pytest.mark.parametrize("B", [8192, 16384, 32768, 65536])
+def test_bf16_sweep_points_sampled_rows_all_steps(B):
+    """BASELINE configs[3] sweep points: the kernel runs the whole batch; 512 sampled rows (rollouts are
+    row-independent) are held to the bf16-emulating oracle over all 15 steps."""
+    D, S, Hd, A, Ha, La = C4
+    HG, rssm, actor = _setup(D, S, Hd, A, Ha, La, seed=0)
+    H = 15
+    deter0, stoch0, noise = HG.synth_inputs("continuous", B, H, D, S, 1)
+    init = HG.init_state(rssm, deter0, stoch0)
+    with torch.no_grad():
+        seq, actions = rssm.imagine_rollout(init, actor, H, noise=noise.cuda(), return_actions=True)
+    rows = torch.randperm(B, generator=torch.Generator().manual_seed(B))[:512].sort().values
+    rows[0], rows[-1] = 0, B - 1     # first and last row of the batch (tile edges)
+    with torch.no_grad():
+        ref = O.imagine_rollout("continuous", HG.cpu_weights(rssm), HG.cpu_weights(actor), deter0[rows], stoch0[rows],
+                                noise[:, rows], H, S, emulate_bf16=True, bias0_bf16=_bias_folded())
+    _compare(seq, actions, ref, rows=rows.cuda())
+
+
+def test_bf16_multistep_single_cta_kernel():
+    """the same free-running check on the single-CTA kernel (WMRL_TC_MODE=1; read once per process)."""
+    import subprocess
+    import sys
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    env = dict(os.environ, WMRL_TC_MODE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "free_running_vs_bf16_oracle or other_shapes"], env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -166,3 +166,64 @@ def test_numa_binding_is_best_effort():
     assert bind_to_gpu_numa(0) in (True, False)      # no NVML / no GPU here -> False, never raises
     if not torch.cuda.is_available():
         assert os.sched_getaffinity(0) == before
+
+
+def test_actor_shape_validation_is_loud():
+    """an Actor-shaped module that deviates from [Linear, LayerNorm(eps 1e-5), ELU] x L + Linear mu must be
+    rejected, not silently mis-evaluated by the fused path (the reference just calls actor(...))."""
+    from wmrl.rssm import _actor_tensors, _actor_bound
+    good = wmrl.Actor(40, 3, 1.0, 2, 64)
+    La, Ha, flat = _actor_tensors(good)
+    assert (La, Ha, len(flat)) == (2, 64, 10)
+    bad = wmrl.Actor(40, 3, 1.0, 2, 64)
+    bad.layers[1] = torch.nn.LayerNorm(64, eps=1e-3)
+    with pytest.raises(TypeError, match="LayerNorm"):
+        _actor_tensors(bad)
+    bad = wmrl.Actor(40, 3, 1.0, 2, 64)
+    bad.layers[2] = torch.nn.ReLU()
+    with pytest.raises(TypeError, match="ELU"):
+        _actor_tensors(bad)
+    bad = wmrl.Actor(40, 3, 1.0, 2, 64)
+    bad.layers.append(torch.nn.Identity())
+    with pytest.raises(TypeError, match="must hold"):
+        _actor_tensors(bad)
+    # bound: cached expansion, same storage across calls, refreshed by an in-place edit or a re-assignment
+    b1 = _actor_bound(good, 3, "cpu")
+    assert b1.shape == (3,) and _actor_bound(good, 3, "cpu") is b1
+    good.bound.mul_(2.0)
+    b2 = _actor_bound(good, 3, "cpu")
+    assert b2 is not b1 and float(b2[0]) == 2.0
+    good.bound = torch.tensor([1.0, 2.0, 3.0])
+    assert _actor_bound(good, 3, "cpu").tolist() == [1.0, 2.0, 3.0]
+    with pytest.raises(ValueError):
+        _actor_bound(good, 4, "cpu")
+
+
+def test_compute_rollout_value_shim_matches_reference_loops():
+    from oracle import rssm_oracle as O
+    g = torch.Generator().manual_seed(0)
+    B, H = 5, 7
+    V, r = torch.randn(B, H, 1, generator=g), torch.randn(B, H, 1, generator=g)
+    d = O.done_preprocess((torch.rand(B, H, 1, generator=g) > 0.8).float())
+    tr = wmrl.ValueGradTrainer(wmrl.Actor(4, 1, 1.0, 1, 8), wmrl.ValueCritic(4, 1, 8))
+    gam = torch.tensor([0.99 ** i for i in range(H)])
+    for k in (1, 3, H, H + 2):
+        got = tr.compute_rollout_value(V, r, torch.zeros(B, H, 4), d, k)
+        torch.testing.assert_close(got, O._rollout_value(V, r, d, gam, k))
+
+
+def test_oracle_bf16_emulation_is_a_small_perturbation():
+    """the bf16-emulating oracle (checker of the tcgen05 path) stays within the north-star bf16 band of the
+    fp32 restatement on the reference fixture, and is exact when nothing needs rounding."""
+    from helpers import Golden
+    from oracle import rssm_oracle as O
+    g = Golden("cont_fixture")
+    w, aw = g.weights("rssm."), g.weights("actor.")
+    args = ("continuous", w, aw, g.t("deter0"), g.t("stoch0"), g.t("noise_im"), g.H, g.S)
+    with torch.no_grad():
+        a = O.imagine_rollout(*args)
+        b = O.imagine_rollout(*args, emulate_bf16=True)
+    for k in ("deter", "mean", "std", "actions"):
+        assert float((a[k] - b[k]).norm() / a[k].norm()) < 1e-2, k
+    x = torch.tensor([1.0, 0.5, -2.0, 3.140625])
+    assert torch.equal(O.bf16_round(x), x)

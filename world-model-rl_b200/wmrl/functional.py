@@ -66,6 +66,19 @@ def _require_cuda(*tensors: torch.Tensor) -> torch.device:
     return dev
 
 
+def _on(dev):
+    """libwmrl launches kernels, uploads constants and sets function attributes on the CUDA *current*
+    device; every native call therefore runs with the tensors' device made current (the modules may live
+    on a device other than torch's current one, as with the reference)."""
+    return torch.cuda.device(dev)
+
+
+def _native(dev, fn, *args) -> None:
+    """one C-ABI call with ``dev`` current; non-zero status raises with wmrl_last_error()."""
+    with _on(dev):
+        _lib.check(fn(*args), fn.__name__)
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
@@ -118,7 +131,7 @@ class PackedWeights:
     def get(self, cfg: PathConfig, rssm_p: Sequence[torch.Tensor], actor_p: Sequence[torch.Tensor],
             bound: torch.Tensor) -> torch.Tensor:
         lib = _lib.load()
-        key = (dataclasses.replace(cfg, record=True), bound.data_ptr(),
+        key = (dataclasses.replace(cfg, record=True), bound.data_ptr(), bound._version,
                tuple((p.data_ptr(), p._version) for p in list(rssm_p) + list(actor_p)))
         if self.key == key and self.buf is not None:
             return self.buf
@@ -131,8 +144,7 @@ class PackedWeights:
         r32 = [_f32c(p) for p in rssm_p]
         a32 = [_f32c(p) for p in actor_p]
         w, aw = _rssm_ptrs(r32), _actor_ptrs(a32, cfg.La, bound)
-        _lib.check(lib.wmrl_pack_weights(C.byref(d), C.byref(w), C.byref(aw), buf.data_ptr(), _stream_ptr(dev)),
-                   "wmrl_pack_weights")
+        _native(dev, lib.wmrl_pack_weights, C.byref(d), C.byref(w), C.byref(aw), buf.data_ptr(), _stream_ptr(dev))
         self.key, self.buf = key, buf
         return buf
 
@@ -185,11 +197,11 @@ class ImagineRollout(torch.autograd.Function):
         ws = _bytes(ws_n, dev)
         w, aw = _rssm_ptrs(r32), _actor_ptrs(a32, cfg.La, bd)
         if B > 0 and H > 0:
-            _lib.check(lib.wmrl_imagine_fwd(
+            _native(dev, lib.wmrl_imagine_fwd,
                 C.byref(d), C.byref(w), C.byref(aw), _lib.ptr(packed) if precision == _lib.BF16 else None,
                 d0.data_ptr(), s0.data_ptr(), nz.data_ptr(), deter_seq.data_ptr(), stoch_seq.data_ptr(),
                 dist_a.data_ptr(), _lib.ptr(dist_b), actions.data_ptr(), _lib.ptr(idx), _lib.ptr(saved),
-                saved_n, ws.data_ptr(), ws_n, _stream_ptr(dev)), "wmrl_imagine_fwd")
+                saved_n, ws.data_ptr(), ws_n, _stream_ptr(dev))
         else:
             deter_seq[:, 0], stoch_seq[:, 0] = d0, s0
         dist_a[:, 0] = init_da.detach()
@@ -241,12 +253,12 @@ class ImagineRollout(torch.autograd.Function):
         gaw = _actor_ptrs(ga, cfg.La, None, grads=True)
         gw = _rssm_ptrs(gr)
         if B > 0 and H > 0:
-            _lib.check(lib.wmrl_imagine_bwd(
+            _native(dev, lib.wmrl_imagine_bwd,
                 C.byref(d), C.byref(w), C.byref(aw), None, nz.data_ptr(), deter_seq.data_ptr(),
                 stoch_seq.data_ptr(), dist_a.data_ptr(), _lib.ptr(dist_b if ctx.has_b else None),
                 actions.data_ptr(), saved.data_ptr(), _lib.ptr(g_deter), _lib.ptr(g_stoch), _lib.ptr(g_da),
                 _lib.ptr(g_db), C.byref(gaw), C.byref(gw) if need_rssm else None, g_d0.data_ptr(),
-                g_s0.data_ptr(), ws.data_ptr(), ws_n, _stream_ptr(dev)), "wmrl_imagine_bwd")
+                g_s0.data_ptr(), ws.data_ptr(), ws_n, _stream_ptr(dev))
         else:
             if g_deter is not None:
                 g_d0 = g_deter[:, 0].clone()
@@ -300,11 +312,11 @@ class ObserveRollout(torch.autograd.Function):
         ws = _bytes(ws_n, dev)
         w = _rssm_ptrs(r32)
         if B > 0 and T > 0:
-            _lib.check(lib.wmrl_observe_fwd(
+            _native(dev, lib.wmrl_observe_fwd,
                 C.byref(d), C.byref(w), ob.data_ptr(), ac.data_ptr(), _lib.ptr(n1), _lib.ptr(n2),
                 pri[0].data_ptr(), pri[1].data_ptr(), pri[2].data_ptr(), _lib.ptr(pri[3]),
                 post[0].data_ptr(), post[1].data_ptr(), post[2].data_ptr(), _lib.ptr(post[3]),
-                _lib.ptr(saved), saved_n, ws.data_ptr(), ws_n, _stream_ptr(dev)), "wmrl_observe_fwd")
+                _lib.ptr(saved), saved_n, ws.data_ptr(), ws_n, _stream_ptr(dev))
         if T > 0:
             pri[2][:, 0] = init_pri_da.detach()
             post[2][:, 0] = init_post_da.detach()
@@ -348,15 +360,14 @@ class ObserveRollout(torch.autograd.Function):
         ws = _bytes(ws_n, dev)
         w, gw = _rssm_ptrs(r32), _rssm_ptrs(gr)
         if B > 0 and T > 1:
-            _lib.check(lib.wmrl_observe_bwd(
+            _native(dev, lib.wmrl_observe_bwd,
                 C.byref(d), C.byref(w), ob.data_ptr(), ac.data_ptr(), n1.data_ptr(), n2.data_ptr(),
                 p_de.data_ptr(), p_st.data_ptr(), p_da.data_ptr(), None if disc else p_db.data_ptr(),
                 q_de.data_ptr(), q_st.data_ptr(), q_da.data_ptr(), None if disc else q_db.data_ptr(),
                 saved.data_ptr(),
                 _lib.ptr(gp[0]), _lib.ptr(gp[1]), _lib.ptr(gp[2]), _lib.ptr(gp[3]),
                 _lib.ptr(gq[0]), _lib.ptr(gq[1]), _lib.ptr(gq[2]), _lib.ptr(gq[3]),
-                C.byref(gw), g_obs.data_ptr(), g_act.data_ptr(), ws.data_ptr(), ws_n, _stream_ptr(dev)),
-                "wmrl_observe_bwd")
+                C.byref(gw), g_obs.data_ptr(), g_act.data_ptr(), ws.data_ptr(), ws_n, _stream_ptr(dev))
         need = ctx.needs_input_grad
 
         def first(gseq):
@@ -386,8 +397,8 @@ class LambdaReturn(torch.autograd.Function):
         v32, r32, d32 = _f32c(V), _f32c(r), _f32c(d)
         out = torch.empty(B, H, device=dev)
         if B > 0:
-            _lib.check(lib.wmrl_lambda_return_fwd(v32.data_ptr(), r32.data_ptr(), d32.data_ptr(), gamma, lam,
-                                                  B, H, out.data_ptr(), _stream_ptr(dev)), "wmrl_lambda_return_fwd")
+            _native(dev, lib.wmrl_lambda_return_fwd, v32.data_ptr(), r32.data_ptr(), d32.data_ptr(), gamma, lam,
+                                                  B, H, out.data_ptr(), _stream_ptr(dev))
         ctx.save_for_backward(d32)
         ctx.gamma, ctx.lam = gamma, lam
         return out
@@ -400,9 +411,8 @@ class LambdaReturn(torch.autograd.Function):
         g = g_out.to(torch.float32).contiguous()
         g_V, g_r = torch.empty_like(g), torch.empty_like(g)
         if B > 0:
-            _lib.check(lib.wmrl_lambda_return_bwd(g.data_ptr(), d32.data_ptr(), ctx.gamma, ctx.lam, B, H,
-                                                  g_V.data_ptr(), g_r.data_ptr(), _stream_ptr(g.device)),
-                       "wmrl_lambda_return_bwd")
+            _native(g.device, lib.wmrl_lambda_return_bwd, g.data_ptr(), d32.data_ptr(), ctx.gamma, ctx.lam, B, H,
+                                                  g_V.data_ptr(), g_r.data_ptr(), _stream_ptr(g.device))
         return g_V, g_r, None, None, None
 
 
@@ -424,8 +434,7 @@ def done_mask(dones: torch.Tensor) -> torch.Tensor:
     d2 = _f32c(dones.reshape(shape[0], shape[1]))
     out = torch.empty_like(d2)
     if d2.shape[0] > 0:
-        _lib.check(lib.wmrl_done_mask(d2.data_ptr(), d2.shape[0], d2.shape[1], out.data_ptr(), _stream_ptr(dev)),
-                   "wmrl_done_mask")
+        _native(dev, lib.wmrl_done_mask, d2.data_ptr(), d2.shape[0], d2.shape[1], out.data_ptr(), _stream_ptr(dev))
     return out.reshape(shape)
 
 
@@ -449,8 +458,8 @@ class LinearFn(torch.autograd.Function):
             raise ValueError(f"linear: x has {K} features, weight expects {w.shape[1]}")
         y = torch.empty(M, N, device=dev)
         if M > 0:
-            _lib.check(lib.wmrl_linear_fwd(M, N, K, x2.data_ptr(), K, w.data_ptr(), _lib.ptr(b), y.data_ptr(), N,
-                                           int(act), _stream_ptr(dev)), "wmrl_linear_fwd")
+            _native(dev, lib.wmrl_linear_fwd, M, N, K, x2.data_ptr(), K, w.data_ptr(), _lib.ptr(b), y.data_ptr(), N,
+                                           int(act), _stream_ptr(dev))
         ctx.save_for_backward(x2, w, y if act else None)
         ctx.act, ctx.has_bias, ctx.x_shape = int(act), bias is not None, x.shape
         return y.reshape(*x.shape[:-1], N)
@@ -468,16 +477,16 @@ class LinearFn(torch.autograd.Function):
         g_x = g_w = g_b = None
         if M > 0 and ctx.needs_input_grad[0]:
             g_x = torch.empty(M, K, device=dev)
-            _lib.check(lib.wmrl_linear_dgrad(M, N, K, g.data_ptr(), N, w.data_ptr(), g_x.data_ptr(), K, 0,
-                                             _stream_ptr(dev)), "wmrl_linear_dgrad")
+            _native(dev, lib.wmrl_linear_dgrad, M, N, K, g.data_ptr(), N, w.data_ptr(), g_x.data_ptr(), K, 0,
+                                             _stream_ptr(dev))
             g_x = g_x.reshape(ctx.x_shape)
         elif ctx.needs_input_grad[0]:
             g_x = torch.zeros(ctx.x_shape, device=dev)
         if ctx.needs_input_grad[1]:
             g_w = torch.zeros(N, K, device=dev)
             if M > 0:
-                _lib.check(lib.wmrl_linear_wgrad(M, N, K, g.data_ptr(), N, x2.data_ptr(), K, g_w.data_ptr(),
-                                                 _stream_ptr(dev)), "wmrl_linear_wgrad")
+                _native(dev, lib.wmrl_linear_wgrad, M, N, K, g.data_ptr(), N, x2.data_ptr(), K, g_w.data_ptr(),
+                                                 _stream_ptr(dev))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             g_b = g.sum(0)
         return g_x, g_w, g_b, None
@@ -508,8 +517,8 @@ class LayerNormAct(torch.autograd.Function):
         xhat, y = torch.empty_like(x2), torch.empty_like(x2)
         rstd = torch.empty(M, device=dev)
         if M > 0:
-            _lib.check(lib.wmrl_ln_act_fwd(M, W, x2.data_ptr(), g.data_ptr(), b.data_ptr(), int(act), xhat.data_ptr(),
-                                           rstd.data_ptr(), y.data_ptr(), _stream_ptr(dev)), "wmrl_ln_act_fwd")
+            _native(dev, lib.wmrl_ln_act_fwd, M, W, x2.data_ptr(), g.data_ptr(), b.data_ptr(), int(act), xhat.data_ptr(),
+                                           rstd.data_ptr(), y.data_ptr(), _stream_ptr(dev))
         ctx.save_for_backward(xhat, rstd, g, b)
         ctx.act, ctx.x_shape = int(act), x.shape
         return y.reshape(x.shape)
@@ -526,9 +535,9 @@ class LayerNormAct(torch.autograd.Function):
         dg = torch.zeros(W, device=dev) if need_p else None
         db = torch.zeros(W, device=dev) if need_p else None
         if M > 0:
-            _lib.check(lib.wmrl_ln_act_bwd(M, W, dy.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), g.data_ptr(),
+            _native(dev, lib.wmrl_ln_act_bwd, M, W, dy.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), g.data_ptr(),
                                            b.data_ptr(), ctx.act, dx.data_ptr(), _lib.ptr(dg), _lib.ptr(db),
-                                           _stream_ptr(dev)), "wmrl_ln_act_bwd")
+                                           _stream_ptr(dev))
         return (dx.reshape(ctx.x_shape) if ctx.needs_input_grad[0] else None,
                 dg if ctx.needs_input_grad[1] else None, db if ctx.needs_input_grad[2] else None, None)
 

@@ -35,12 +35,48 @@ def _actor_tensors(actor: nn.Module):
         La, layers, mu = int(actor.num_layers), actor.layers, actor.mu
     except AttributeError as e:  # pragma: no cover - defensive
         raise TypeError("imagine_rollout needs an Actor-shaped module (layers/mu/num_layers/bound)") from e
+    # The native path hard-codes the block structure of actor.py:22-37 - [Linear, LayerNorm(eps 1e-5, affine),
+    # ELU(alpha 1)] x num_layers and a Linear mu head.  Anything else would give silently different rollouts
+    # where the reference simply calls actor(...), so it is rejected here.
+    if len(layers) != 3 * La:
+        raise TypeError(f"actor.layers must hold {3 * La} modules ([Linear, LayerNorm, ELU] x {La}), has {len(layers)}")
+    Ha = int(actor.hidden_dim)
     flat = []
     for l in range(La):
-        lin, ln = layers[3 * l], layers[3 * l + 1]
+        lin, ln, act = layers[3 * l], layers[3 * l + 1], layers[3 * l + 2]
+        if not isinstance(lin, nn.Linear) or lin.bias is None or lin.out_features != Ha:
+            raise TypeError(f"actor.layers[{3 * l}] must be nn.Linear(.., {Ha}) with a bias")
+        if (not isinstance(ln, nn.LayerNorm) or not ln.elementwise_affine or ln.bias is None
+                or tuple(ln.normalized_shape) != (Ha,) or abs(ln.eps - 1e-5) > 1e-12):
+            raise TypeError(f"actor.layers[{3 * l + 1}] must be nn.LayerNorm({Ha}, eps=1e-5, elementwise_affine=True)")
+        if not isinstance(act, nn.ELU) or act.alpha != 1.0:
+            raise TypeError(f"actor.layers[{3 * l + 2}] must be nn.ELU(alpha=1.0)")
         flat += [lin.weight, lin.bias, ln.weight, ln.bias]
+    if not isinstance(mu, nn.Linear) or mu.bias is None or mu.in_features != Ha:
+        raise TypeError(f"actor.mu must be nn.Linear({Ha}, A) with a bias")
     flat += [mu.weight, mu.bias]
-    return La, int(actor.hidden_dim), flat
+    return La, Ha, flat
+
+
+def _actor_bound(actor: nn.Module, A: int, device) -> torch.Tensor:
+    """``actor.bound`` (actor.py:20: a plain fp32 tensor attribute, scalar or one entry per action) as a
+    contiguous [A] device tensor.  The expansion is cached on the actor keyed on the source tensor's identity
+    and version, so repeated calls hand the same storage to the packed-weight cache (no repack, no per-call
+    allocation) while an in-place edit of ``actor.bound`` is still picked up."""
+    src = actor.bound if torch.is_tensor(actor.bound) else torch.as_tensor(actor.bound, dtype=torch.float32)
+    key = (id(actor.bound), getattr(src, "_version", 0), src.data_ptr() if torch.is_tensor(actor.bound) else None,
+           str(device), A)
+    cached = actor.__dict__.get("_wmrl_bound_cache")
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    b = src.detach().to(device=device, dtype=torch.float32).reshape(-1)
+    if b.numel() == 1:
+        b = b.expand(A)
+    if b.numel() != A:
+        raise ValueError("actor.bound must be a scalar or have one entry per action dim")
+    b = b.contiguous().clone()
+    actor.__dict__["_wmrl_bound_cache"] = (key, b)
+    return b
 
 
 class RSSMBase(nn.Module):
@@ -151,10 +187,7 @@ class RSSMBase(nn.Module):
             (n_steps, B, self.stoch_size)
         if tuple(noise.shape) != want:
             raise ValueError(f"noise must have shape {want}, got {tuple(noise.shape)}")
-        bound = torch.as_tensor(actor.bound, dtype=torch.float32, device=device).reshape(-1)
-        bound = bound.expand(A).contiguous() if bound.numel() == 1 else bound
-        if bound.numel() != A:
-            raise ValueError("actor.bound must be a scalar or have one entry per action dim")
+        bound = _actor_bound(actor, A, device)
         rssm_p = self._rssm_tensors()
         packed = None
         if cfg.precision == _lib.BF16:

@@ -43,6 +43,17 @@ class ValueGradTrainer:
         self.critic_optim = AdamOptim(critic.parameters(), lr=critic_lr, grad_clip=grad_clip)
 
     # -- lambda-return ------------------------------------------------------
+    def compute_rollout_value(self, target_state_values, rewards, states, dones, k):
+        """k-step return G_k of the first step of the slice, [B,1] (value_trainer.py:62-86): sum_{j<h} gamma^j
+        r_j (1-d_j) + gamma^h V_h (1-d_h), h = min(k, H-1).  Public in the reference, kept as a thin torch
+        shim for callers that use it directly; the lambda-return itself never goes through it here
+        (``wmrl_lambda_return_fwd`` evaluates all G_k of all steps in one O(H) scan)."""
+        big_h = states.shape[1]
+        h = min(int(k), big_h - 1)
+        gam = torch.tensor([self.gamma ** i for i in range(big_h)], device=rewards.device, dtype=rewards.dtype)
+        ret = (gam[:h][None, :, None] * rewards[:, :h] * (1 - dones[:, :h])).sum(1)
+        return ret + gam[h] * target_state_values[:, h] * (1 - dones[:, h])
+
     def compute_value_target(self, target_state_values, rewards, states, dones):
         """lambda-return of the FIRST step of the given slice, [B,1]
         (value_trainer.py:88-113; ``states`` only fixes the horizon there)."""
