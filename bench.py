@@ -205,6 +205,95 @@ def run_reference(args):
     return 0
 
 
+def reference_modules(c, device="cpu", seed=0):
+    """The UNMODIFIED reference modules (staged copy, oracle/make_ref.py) built under the same seed as
+    ``build_problem``; None when the staged copy is absent (then the oracle port stands in)."""
+    try:
+        from oracle import make_ref
+        make_ref.import_reference()
+        from reflect.components.models.actor import Actor as RefActor
+        from reflect.components.rssm_world_model.rssm import ContinuousRSSM as RefRSSM
+    except Exception:
+        return None
+    torch.manual_seed(seed)
+    rssm = RefRSSM(hidden_size=c["Hd"], deter_size=c["D"], stoch_size=c["S"], obs_embed_size=c["E"],
+                   action_size=c["A"])
+    actor = RefActor(c["D"] + c["S"], c["A"], 1.0, num_layers=c["La"], hidden_dim=c["Ha"])
+    return rssm.to(device), actor.to(device)
+
+
+def reference_initial_state(c, deter0, stoch0):
+    from reflect.components.rssm_world_model.state import InternalStateContinuous as RefState
+    return RefState(deter_state=deter0, stoch_state=stoch0, mean=stoch0.clone(), std=torch.ones_like(stoch0))
+
+
+def gpu_eager_baseline(c, dev, ours_ms):
+    """Same-box GPU baseline: the reference's own code path - eager PyTorch,
+    ~25 ATen launches per step, torch.cat growth, internal RNG (rssm.py:123-140) - on THIS B200 at the bench
+    shape, CUDA-event timed.  Three numeric modes: strict fp32, TF32 matmuls allowed, bf16 autocast.  Uses the
+    unmodified reference modules when staged (kind "reference"), else the oracle port (kind "port")."""
+    B, H = c["B"], c["H"]
+    ref = reference_modules(c, dev)
+    g = torch.Generator().manual_seed(5)
+    d0 = torch.tanh(torch.randn(B, c["D"], generator=g)).to(dev)
+    s0 = torch.randn(B, c["S"], generator=g).to(dev)
+    if ref is not None:
+        rssm, actor = ref
+        for p_ in list(rssm.parameters()) + list(actor.parameters()):
+            p_.requires_grad_(False)
+        init = reference_initial_state(c, d0, s0)
+        kind = "reference"
+
+        def call():
+            return rssm.imagine_rollout(init, actor, H)
+    else:
+        import wmrl
+        from oracle import rssm_oracle as O
+        torch.manual_seed(0)
+        r_ = wmrl.ContinuousRSSM(c["Hd"], c["D"], c["S"], c["E"], c["A"])
+        a_ = wmrl.Actor(c["D"] + c["S"], c["A"], 1.0, c["La"], c["Ha"])
+        w = {k: v.detach().to(dev) for k, v in r_.state_dict().items()}
+        aw = {k: v.detach().to(dev) for k, v in a_.state_dict().items()}
+        bound = torch.tensor(1.0, device=dev)
+        kind = "port"
+
+        def call():
+            return O.imagine_rollout_reference_like(c["variant"], w, aw, d0, s0, H, c["S"], c["C"], bound=bound)
+
+    def timed(n=5):
+        with torch.no_grad():
+            for _ in range(2):
+                call()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                call()
+            b.record()
+            torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    out = {"kind": kind, "start_states": B, "horizon": H, "unit": "ms per rollout"}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        out["fp32"] = timed()
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+        out["tf32"] = timed()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out["bf16_autocast"] = timed()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    best = min(out["fp32"], out["tf32"], out["bf16_autocast"])
+    out["latent_steps_per_s_best"] = B * H / best * 1e3
+    out["ours_ms"] = ours_ms
+    out["speedup_vs_best_eager"] = best / ours_ms
+    out["speedup_vs_fp32_eager"] = out["fp32"] / ours_ms
+    return out
+
+
 def aux_configs(dev):
     """Informational, outside the timed region: BASELINE configs[1] (discrete D600/32x32, 2500 start states,
     H=15) forward + hand-written actor-BPTT backward through the fp32 CUDA path, as latent-steps/s."""
@@ -428,6 +517,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_aux:
             line["aux"] = aux_configs(dev)
+            line["gpu_eager_baseline"] = gpu_eager_baseline(c, dev, avg_launch_s * 1e3)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rows = B          # the whole workload: ~1.5-2.5 s per pass on 16 cores, ~10 s in total

@@ -116,7 +116,7 @@ int wmrl_imagine_fwd(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_a
     WMRL_REQUIRE(!save, "imagine_fwd: bf16 path does not record activations; the backward "
                         "recomputes them (call the fp32 forward with SAVE_FOR_BWD)");
     return tc_imagine_fwd(dd, w, aw, packed, deter0, stoch0, noise, deter_seq, stoch_seq, dist_a,
-                          dist_b, actions, idx, ws, (cudaStream_t)stream);
+                          dist_b, actions, idx, nullptr, ws, (cudaStream_t)stream);
   }
   return f32_imagine_fwd(dd, w, aw, deter0, stoch0, noise, deter_seq, stoch_seq, dist_a, dist_b,
                          actions, idx, save ? (float*)saved : nullptr, (float*)ws,

@@ -83,6 +83,6 @@ int tc_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_p
 int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
                    const void* packed, const float* deter0, const float* stoch0,
                    const float* noise, float* deter_seq, float* stoch_seq, float* dist_a,
-                   float* dist_b, float* actions, int32_t* idx, void* ws, cudaStream_t st);
+                   float* dist_b, float* actions, int32_t* idx, void* saved, void* ws, cudaStream_t st);
 
 }  // namespace wmrl

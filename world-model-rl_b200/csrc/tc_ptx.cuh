@@ -320,7 +320,27 @@ __device__ __forceinline__ void st_chunk(uint32_t smem_addr, const float* v) {
                "r"(d)
                : "memory");
 }
-
+// same, and the identical 16 bytes to a global-memory stash panel (training: activations recorded for the BPTT)
+__device__ __forceinline__ void st_chunk_sg(uint32_t smem_addr, void* gptr, const float* v) {
+  const uint32_t a = pack_bf16x2(v[0], v[1]), b = pack_bf16x2(v[2], v[3]);
+  const uint32_t c = pack_bf16x2(v[4], v[5]), d = pack_bf16x2(v[6], v[7]);
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(smem_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  *reinterpret_cast<uint4*>(gptr) = make_uint4(a, b, c, d);
+}
+__device__ __forceinline__ void st_chunk_g(void* gptr, const float* v) {
+  *reinterpret_cast<uint4*>(gptr) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                               pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+// 8 bf16 of a stash panel chunk -> fp32
+__device__ __forceinline__ void ld_chunk_g(const void* gptr, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(gptr);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
 
 // Packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2, two fp32 per issue slot) for the issue-bound epilogues.
 __device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
