@@ -48,7 +48,10 @@ enum { WMRL_FP32 = 0, WMRL_BF16 = 1 };
 /* dims.flags */
 enum {
   WMRL_FLAG_WM_WGRAD = 1,   /* imagine_bwd: also produce RSSM weight grads (WM not frozen) */
-  WMRL_FLAG_SAVE_FOR_BWD = 2 /* imagine_fwd / observe_fwd: fill `saved` for a later *_bwd   */
+  WMRL_FLAG_SAVE_FOR_BWD = 2, /* imagine_fwd / observe_fwd: fill `saved` for a later *_bwd  */
+  WMRL_FLAG_TRACE = 4,        /* imagine_fwd (bf16): write a cycle timeline into the workspace (tools/trace_tc.py) */
+  WMRL_FLAG_BACKWARD = 8      /* wmrl_workspace_bytes / imagine_bwd: size the workspace for the BACKWARD call (the
+                                 bf16 BPTT keeps its gradient stash there; the forward does not need it)       */
 };
 
 typedef struct wmrl_dims {
@@ -114,7 +117,14 @@ WMRL_API const char* wmrl_last_error(void);
 /* 1 if the running device can execute the sm_100a tcgen05 path, else 0. */
 WMRL_API int wmrl_device_supports_bf16(void);
 
-/* Buffer sizes the caller must provide.  op: 0 imagine, 1 observe. */
+/* 1 if WMRL_BF16 can also TRAIN at this shape: wmrl_imagine_fwd with WMRL_FLAG_SAVE_FOR_BWD records a bf16
+ * activation stash from inside the persistent rollout kernel and wmrl_imagine_bwd(precision WMRL_BF16) runs the
+ * persistent tcgen05 BPTT kernel + weight-gradient GEMMs over it (autograd of rssm.py:123-140, actor gradients
+ * only: the world model is frozen by the caller, world_model.py:172).  0: record with WMRL_FP32. */
+WMRL_API int wmrl_bf16_train_supported(const wmrl_dims* d);
+
+/* Buffer sizes the caller must provide.  op: 0 imagine, 1 observe.  They depend on d->precision and d->flags
+ * (the bf16 training path keeps a bf16 stash in `saved` and a gradient stash in the workspace). */
 WMRL_API size_t wmrl_saved_bytes(const wmrl_dims* d, int op);
 WMRL_API size_t wmrl_workspace_bytes(const wmrl_dims* d, int op);
 /* Bytes of the packed bf16 weight image used by the WMRL_BF16 path (0 if the
@@ -145,7 +155,8 @@ WMRL_API int wmrl_imagine_fwd(const wmrl_dims* d, const wmrl_rssm_params* w, con
                      void* ws, size_t ws_bytes, void* stream);
 
 /*
- * Hand-written BPTT of the above.  Actor input is detached (rssm.py:135): actor
+ * Hand-written BPTT of the above.  d->precision must be the precision the forward recorded with (`saved` is the
+ * fp32 activation record of the fp32 chain or the bf16 stash of the tcgen05 kernel); WMRL_BF16 needs `packed`.  Actor input is detached (rssm.py:135): actor
  * weights get gradient only through a_t -> dynamics.  g_* inputs are the
  * upstream gradients of the forward outputs (same shapes; index 0 slots of
  * g_deter_seq / g_stoch_seq flow straight to g_deter0 / g_stoch0).  Any g_*

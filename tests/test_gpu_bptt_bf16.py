@@ -1,0 +1,191 @@
+"""GPU parity of the bf16 TRAINING path: the persistent rollout kernel records a bf16 activation stash, the
+persistent tcgen05 BPTT kernel walks it backwards, big-K tcgen05 GEMMs + column sums over the two stashes give
+the actor parameter gradients (autograd of rssm.py:123-140 as driven by value_trainer.py:164-173 through the
+frozen world model, world_model.py:172).
+
+Checked through the public module API (``RSSM.imagine_rollout(...)`` -> ``.backward()``) against torch autograd
+on the fp32 oracle with the same weights, inputs and pre-drawn noise.  Tolerance for bf16 gradients (stated by
+the round-1 review, north-star rtol 1e-2 class): per parameter tensor cosine >= 0.999 and relative Frobenius
+error <= 2e-2; start-state gradients the same.
+"""
+import warnings
+
+import pytest
+import torch
+
+from oracle import rssm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+COS_MIN, REL_MAX = 0.999, 2e-2
+SHAPES = {"c1": (200, 30, 200, 6, 512, 3), "small": (32, 8, 32, 1, 64, 2), "mid": (120, 24, 120, 4, 256, 3),
+          "wide_hd": (48, 16, 96, 3, 128, 1)}
+
+
+def _setup(shape, seed=3):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import helpers_gpu as HG
+    from wmrl import _lib
+    if not _lib.load().wmrl_device_supports_bf16():
+        pytest.skip("not an sm_100 device")
+    D, S, Hd, A, Ha, La = SHAPES[shape]
+    rssm, actor = HG.build_modules("continuous", D, S, 1, Hd, 64, A, Ha, La, bound=1.0, seed=seed, precision="bf16")
+    for p in rssm.parameters():          # WorldModel.imagine_rollout freezes the world model (world_model.py:172)
+        p.requires_grad_(False)
+    return HG, rssm, actor, (D, S, Hd, A, Ha, La)
+
+
+def _agree(name, got, ref, cos_min=COS_MIN, rel_max=REL_MAX):
+    got, ref = got.detach().float().cpu().flatten(), ref.detach().float().cpu().flatten()
+    cos = float(got @ ref / (got.norm() * ref.norm() + 1e-30))
+    rel = float((got - ref).norm() / (ref.norm() + 1e-30))
+    assert cos >= cos_min and rel <= rel_max, f"{name}: cosine {cos:.6f}, relative error {rel:.3e}"
+    return cos, rel
+
+
+def _oracle_grads(rssm, actor, HG, deter0, stoch0, noise, H, S, gfeat, gmean, gstd):
+    w, aw = HG.cpu_weights(rssm), HG.cpu_weights(actor)
+    for v in aw.values():
+        v.requires_grad_(True)
+    d0, s0 = deter0.clone().requires_grad_(True), stoch0.clone().requires_grad_(True)
+    ref = O.imagine_rollout("continuous", w, aw, d0, s0, noise, H, S)
+    loss = (torch.cat([ref["deter"], ref["stoch"]], -1) * gfeat).sum() + (ref["mean"] * gmean).sum() + (ref["std"] * gstd).sum()
+    loss.backward()
+    return {k: v.grad for k, v in aw.items()}, d0.grad, s0.grad
+
+
+@pytest.mark.parametrize("shape,B,H", [("c1", 300, 15), ("small", 200, 7), ("mid", 130, 9), ("wide_hd", 64, 4), ("c1", 1, 3)])
+def test_bf16_bptt_actor_gradients_vs_oracle_autograd(shape, B, H):
+    HG, rssm, actor, (D, S, Hd, A, Ha, La) = _setup(shape)
+    from wmrl.functional import effective_imagine_precision
+    assert effective_imagine_precision(rssm._config(A, Ha, La), B, H, True, False) == "bf16"
+    deter0, stoch0, noise = HG.synth_inputs("continuous", B, H, D, S, 1)
+    g = torch.Generator().manual_seed(9)
+    gfeat = torch.randn(B, H, D + S, generator=g) / B
+    gmean, gstd = torch.randn(B, H, S, generator=g) / B, torch.randn(B, H, S, generator=g) / B
+    init = HG.init_state(rssm, deter0, stoch0)
+    init.deter_state.requires_grad_(True)
+    init.stoch_state.requires_grad_(True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")     # a silent or loud fp32 downgrade fails the test
+        seq = rssm.imagine_rollout(init, actor, H, noise=noise.cuda())
+    loss = (seq.get_features() * gfeat.cuda()).sum() + (seq.means[:, 1:] * gmean.cuda()).sum() + \
+        (seq.stds[:, 1:] * gstd.cuda()).sum()
+    loss.backward()
+    ref_g, ref_d0, ref_s0 = _oracle_grads(rssm, actor, HG, deter0, stoch0, noise, H, S, gfeat, gmean, gstd)
+    named = dict(actor.named_parameters())
+    for k, v in ref_g.items():
+        if v is None:
+            assert named[k].grad is None or float(named[k].grad.abs().max()) == 0.0, k
+            continue
+        assert named[k].grad is not None, k
+        _agree(k, named[k].grad, v)
+    _agree("d loss / d deter0", init.deter_state.grad, ref_d0)
+    _agree("d loss / d stoch0", init.stoch_state.grad, ref_s0)
+
+
+def test_bf16_recording_forward_is_bit_identical_to_plain_forward():
+    HG, rssm, actor, (D, S, Hd, A, Ha, La) = _setup("c1")
+    B, H = 300, 6
+    deter0, stoch0, noise = HG.synth_inputs("continuous", B, H, D, S, 1)
+    init = HG.init_state(rssm, deter0, stoch0)
+    seq = rssm.imagine_rollout(init, actor, H, noise=noise.cuda())
+    assert seq.deter_states.requires_grad
+    with torch.no_grad():
+        seq0 = rssm.imagine_rollout(init, actor, H, noise=noise.cuda())
+    assert torch.equal(seq.deter_states.detach(), seq0.deter_states) and torch.equal(seq.stoch_states.detach(), seq0.stoch_states)
+    assert torch.equal(seq.means.detach(), seq0.means) and torch.equal(seq.stds.detach(), seq0.stds)
+
+
+def test_bf16_gradients_are_additive_over_batch_shards():
+    """rollouts are independent per start state -> the gradient of a sum over rows is the sum of the shard
+    gradients (what the multi-GPU all-reduce relies on), wherever the split falls relative to the 64/128-row tiles."""
+    HG, rssm, actor, (D, S, Hd, A, Ha, La) = _setup("c1")
+    B, H = 450, 5
+    deter0, stoch0, noise = HG.synth_inputs("continuous", B, H, D, S, 1)
+    gfeat = (torch.randn(B, H, D + S, generator=torch.Generator().manual_seed(2)) / B).cuda()
+
+    def grads(lo, hi):
+        actor.zero_grad(set_to_none=True)
+        init = HG.init_state(rssm, deter0[lo:hi], stoch0[lo:hi])
+        seq = rssm.imagine_rollout(init, actor, H, noise=noise[:, lo:hi].contiguous().cuda())
+        (seq.get_features() * gfeat[lo:hi]).sum().backward()
+        return {k: p.grad.clone() for k, p in actor.named_parameters() if p.grad is not None}
+
+    full, a, b = grads(0, B), grads(0, 193), grads(193, B)
+    for k in full:
+        _agree(k, a[k] + b[k], full[k], cos_min=0.99999, rel_max=1e-3)
+
+
+def test_bf16_value_trainer_step_runs_on_the_fused_kernels():
+    """WorldModel.imagine_rollout -> ValueGradTrainer.update (test_value_rssm.py:7-46 composition) with the
+    rollout and its BPTT on the bf16 kernels: actor parameters move, losses are finite."""
+    import wmrl
+    HG, rssm, actor, (D, S, Hd, A, Ha, La) = _setup("c1")
+    dev = "cuda"
+    torch.manual_seed(0)
+    wm = wmrl.WorldModel(encoder=torch.nn.Identity(), decoder=torch.nn.Identity(),
+                         done_model=wmrl.DenseModel(D + S, 1, 2, 64, output_act="sigmoid") if hasattr(wmrl.DenseModel, "__init__") else None,
+                         reward_model=wmrl.DenseModel(D + S, 1, 2, 64), dynamic_model=rssm).to(dev)
+    critic = wmrl.ValueCritic(D + S, 2, 64).to(dev)
+    trainer = wmrl.ValueGradTrainer(actor, critic)
+    B, H = 256, 10
+    deter0, stoch0, noise = HG.synth_inputs("continuous", B, H, D, S, 1)
+    init = HG.init_state(rssm, deter0, stoch0)
+    before = actor.mu.weight.detach().clone()
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        roll = wm.imagine_rollout(init, actor, H, noise=noise.cuda())
+    losses = trainer.update(roll.features, roll.rewards, roll.dones)
+    assert losses.actor_loss is not None and all(map(lambda v: v == v, (losses.actor_loss, losses.value_loss)))
+    assert not torch.equal(before, actor.mu.weight.detach())
+
+
+def test_bf16_training_falls_back_loudly_where_unsupported():
+    """discrete latent / RSSM weight gradients: the fp32 chain records instead, with a RuntimeWarning (no silent
+    change of numerics)."""
+    import helpers_gpu as HG
+    from wmrl import functional as WF
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    WF._WARNED.clear()
+    rssm, actor = HG.build_modules("continuous", 32, 8, 1, 32, 64, 1, 64, 2, precision="bf16")   # RSSM params trainable
+    deter0, stoch0, noise = HG.synth_inputs("continuous", 16, 2, 32, 8, 1)
+    with pytest.warns(RuntimeWarning, match="fp32"):
+        seq = rssm.imagine_rollout(HG.init_state(rssm, deter0, stoch0), actor, 2, noise=noise.cuda())
+    seq.get_features().sum().backward()
+    assert rssm.rnn.weight_hh.grad is not None and actor.mu.weight.grad is not None
+
+
+def test_bf16_bptt_c4_full_size_properties():
+    """configs[3] top point, forward + BPTT at 65 536 x 15 (9 GB stash + 6 GB gradient stash): finite, the
+    start-state gradient of 256 sampled rows agrees with the oracle's autograd on those rows (rows are independent),
+    and the parameter gradients of the full batch equal the sum over two half-batch runs."""
+    HG, rssm, actor, (D, S, Hd, A, Ha, La) = _setup("c1", seed=0)
+    B, H = 65536, 15
+    deter0, stoch0, noise = HG.synth_inputs("continuous", B, H, D, S, 1)
+    gen = torch.Generator().manual_seed(4)
+    gfeat_rows = torch.randn(B, 1, D + S, generator=gen) / B          # same upstream gradient at every step
+    noise_d, gf_d = noise.cuda(), gfeat_rows.cuda()
+
+    def run(lo, hi):
+        actor.zero_grad(set_to_none=True)
+        init = HG.init_state(rssm, deter0[lo:hi], stoch0[lo:hi])
+        init.deter_state.requires_grad_(True)
+        seq = rssm.imagine_rollout(init, actor, H, noise=noise_d[:, lo:hi].contiguous())
+        (seq.get_features() * gf_d[lo:hi]).sum().backward()
+        return {k: p.grad.clone() for k, p in actor.named_parameters() if p.grad is not None}, init.deter_state.grad
+
+    full, gd0 = run(0, B)
+    assert all(bool(torch.isfinite(v).all()) for v in full.values()) and bool(torch.isfinite(gd0).all())
+    a, _ = run(0, B // 2)
+    b, _ = run(B // 2, B)
+    for k in full:
+        _agree(k, a[k] + b[k], full[k], cos_min=0.9999, rel_max=5e-3)
+    rows = torch.randperm(B, generator=gen)[:256]
+    w, aw = HG.cpu_weights(rssm), HG.cpu_weights(actor)
+    d0 = deter0[rows].clone().requires_grad_(True)
+    ref = O.imagine_rollout("continuous", w, aw, d0, stoch0[rows], noise[:, rows], H, S)
+    (torch.cat([ref["deter"], ref["stoch"]], -1) * gfeat_rows[rows]).sum().backward()
+    _agree("d loss / d deter0 (sampled rows)", gd0[rows.cuda()], d0.grad)

@@ -58,9 +58,16 @@ int wmrl_device_supports_bf16(void) {
   return ok;
 }
 
+int wmrl_bf16_train_supported(const wmrl_dims* d) {
+  if (check_dims(d, 0)) return 0;
+  Dims dd(*d);
+  return tc_train_supported(dd) ? 1 : 0;
+}
+
 size_t wmrl_saved_bytes(const wmrl_dims* d, int op) {
   if (check_dims(d, op)) return 0;
   Dims dd(*d);
+  if (op == 0 && d->precision == WMRL_BF16 && tc_train_supported(dd)) return tc_saved_bytes(dd);
   return f32_saved_bytes(dd, op);
 }
 
@@ -71,6 +78,10 @@ size_t wmrl_workspace_bytes(const wmrl_dims* d, int op) {
   if (d->precision == WMRL_BF16 && op == 0) {
     size_t b = tc_workspace_bytes(dd);
     if (b > a) a = b;
+    if ((d->flags & WMRL_FLAG_BACKWARD) && tc_train_supported(dd)) {   // gradient stash of the bf16 BPTT
+      b = tc_bwd_workspace_bytes(dd);
+      if (b > a) a = b;
+    }
   }
   return a;
 }
@@ -108,15 +119,15 @@ int wmrl_imagine_fwd(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_a
   if (int r = require_device()) return r;
   const bool save = (d->flags & WMRL_FLAG_SAVE_FOR_BWD) != 0;
   if (save)
-    WMRL_REQUIRE(saved && saved_bytes >= f32_saved_bytes(dd, 0), "imagine_fwd: saved buffer too small");
+    WMRL_REQUIRE(saved && saved_bytes >= wmrl_saved_bytes(d, 0), "imagine_fwd: saved buffer too small");
   if (d->precision == WMRL_BF16) {
     WMRL_REQUIRE(tc_supported(dd), "imagine_fwd: shape not supported by the bf16 tcgen05 path");
     WMRL_REQUIRE(packed, "imagine_fwd: bf16 path needs the packed weight image");
     WMRL_REQUIRE(wmrl_device_supports_bf16(), "imagine_fwd: bf16 path needs an sm_100 device");
-    WMRL_REQUIRE(!save, "imagine_fwd: bf16 path does not record activations; the backward "
-                        "recomputes them (call the fp32 forward with SAVE_FOR_BWD)");
+    WMRL_REQUIRE(!save || tc_train_supported(dd), "imagine_fwd: this shape has no bf16 training path (activation "
+                                                  "stash + BPTT kernel); record with the fp32 forward");
     return tc_imagine_fwd(dd, w, aw, packed, deter0, stoch0, noise, deter_seq, stoch_seq, dist_a,
-                          dist_b, actions, idx, nullptr, ws, (cudaStream_t)stream);
+                          dist_b, actions, idx, save ? saved : nullptr, ws, (cudaStream_t)stream);
   }
   return f32_imagine_fwd(dd, w, aw, deter0, stoch0, noise, deter_seq, stoch_seq, dist_a, dist_b,
                          actions, idx, save ? (float*)saved : nullptr, (float*)ws,
@@ -130,7 +141,6 @@ int wmrl_imagine_bwd(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_a
                      const float* g_stoch_seq, const float* g_dist_a, const float* g_dist_b,
                      const wmrl_actor_grads* gaw, const wmrl_rssm_grads* gw, float* g_deter0,
                      float* g_stoch0, void* ws, size_t ws_bytes, void* stream) {
-  (void)packed;
   if (int r = check_dims(d, 0)) return r;
   WMRL_REQUIRE(w && aw && gaw, "imagine_bwd: NULL weights / grads");
   Dims dd(*d);
@@ -139,6 +149,17 @@ int wmrl_imagine_bwd(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_a
   WMRL_REQUIRE(!(d->flags & WMRL_FLAG_WM_WGRAD) || gw, "imagine_bwd: WM_WGRAD needs gw");
   WMRL_REQUIRE(ws && ws_bytes >= wmrl_workspace_bytes(d, 0), "imagine_bwd: workspace too small");
   if (int r = require_device()) return r;
+  if (d->precision == WMRL_BF16) {
+    // `saved` is the bf16 activation stash written by wmrl_imagine_fwd(precision BF16, SAVE_FOR_BWD)
+    WMRL_REQUIRE(tc_train_supported(dd), "imagine_bwd: this shape has no bf16 BPTT kernel");
+    WMRL_REQUIRE(packed, "imagine_bwd: bf16 path needs the packed weight image");
+    WMRL_REQUIRE(!(d->flags & WMRL_FLAG_WM_WGRAD), "imagine_bwd: the bf16 BPTT produces actor gradients only "
+                                                   "(world model frozen, world_model.py:172); use the fp32 path");
+    WMRL_REQUIRE(dist_b && g_deter0 && g_stoch0, "imagine_bwd: NULL tensor");
+    WMRL_REQUIRE(wmrl_device_supports_bf16(), "imagine_bwd: bf16 path needs an sm_100 device");
+    return tc_imagine_bwd(dd, packed, noise, deter_seq, dist_b, actions, saved, g_deter_seq, g_stoch_seq, g_dist_a,
+                          g_dist_b, gaw, g_deter0, g_stoch0, ws, (cudaStream_t)stream);
+  }
   return f32_imagine_bwd(dd, w, aw, noise, deter_seq, stoch_seq, dist_a, dist_b, actions,
                          (const float*)saved, g_deter_seq, g_stoch_seq, g_dist_a, g_dist_b, gaw, gw,
                          g_deter0, g_stoch0, (float*)ws, (cudaStream_t)stream);

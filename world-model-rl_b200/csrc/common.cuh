@@ -84,5 +84,13 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
                    const void* packed, const float* deter0, const float* stoch0,
                    const float* noise, float* deter_seq, float* stoch_seq, float* dist_a,
                    float* dist_b, float* actions, int32_t* idx, void* saved, void* ws, cudaStream_t st);
+// bf16 BPTT (tc_bptt.cu): persistent reverse-time kernel + weight-gradient GEMMs over the activation stash
+bool tc_train_supported(const Dims& d);
+size_t tc_saved_bytes(const Dims& d);
+size_t tc_bwd_workspace_bytes(const Dims& d);
+int tc_imagine_bwd(const Dims& d, const void* packed, const float* noise, const float* deter_seq, const float* dist_b,
+                   const float* actions, const void* saved, const float* g_deter_seq, const float* g_stoch_seq,
+                   const float* g_dist_a, const float* g_dist_b, const wmrl_actor_grads* gaw, float* g_deter0,
+                   float* g_stoch0, void* ws, cudaStream_t st);
 
 }  // namespace wmrl

@@ -31,6 +31,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 
@@ -345,7 +346,19 @@ static Plan make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor
 bool tc_supported(const Dims& d) { return make_plan(d, nullptr, nullptr).ok; }
 size_t tc_packed_bytes(const Dims& d) {
   Plan pl = make_plan(d, nullptr, nullptr);
-  return pl.ok ? pl.total_bytes : 0;
+  if (!pl.ok) return 0;
+  size_t n = pl.total_bytes;
+  if (pl.fold && !pl.pp) {
+    Plan bp = tc_make_bwd_plan(d, nullptr, nullptr);
+    if (bp.ok) n += bp.total_bytes;
+  }
+  return n;
+}
+// byte offset of the BPTT image inside the packed buffer (0: this shape has no bf16 training path)
+size_t tc_bwd_image_offset(const Dims& d) {
+  Plan pl = make_plan(d, nullptr, nullptr);
+  if (!pl.ok || !pl.fold || pl.pp) return 0;
+  return tc_make_bwd_plan(d, nullptr, nullptr).ok ? pl.total_bytes : 0;
 }
 size_t tc_workspace_bytes(const Dims&) { return 1024 * sizeof(long long); }
 
@@ -371,8 +384,17 @@ __global__ void pack_stage_kernel(const PackOp* __restrict__ ops, uint8_t* __res
     for (int e = 0; e < 8; ++e) {
       const int k = kc * 8 + e;
       float v = 0.f;
-      if (row >= 0 && k < op.kvalid)
-        v = op.trans ? op.src[(size_t)(op.k0 + k) * op.ld + row] : op.src[(size_t)row * op.ld + op.k0 + k];
+      int ks = (k < op.kvalid) ? op.k0 + k : -1;     // source K index, -1: padding
+      if (op.nks > 0) {
+        ks = -1;
+        int m2 = op.kbegin + k;
+        for (int q = 0; q < op.nks; ++q) {
+          if (m2 < op.kkpad[q]) { if (m2 < op.kkvalid[q]) ks = op.kk0[q] + m2; break; }
+          m2 -= op.kkpad[q];
+        }
+      }
+      if (row >= 0 && ks >= 0)
+        v = op.trans ? op.src[(size_t)ks * op.ld + row] : op.src[(size_t)row * op.ld + ks];
       if (op.bias && row >= 0 && k == op.bias_k) v = op.bias[row];
       out[e] = __float2bfloat16_rn(v);
     }
@@ -392,20 +414,47 @@ __global__ void pack_vec_kernel(const VecOp* __restrict__ ops, float* __restrict
 }
 
 // which packed image currently sits in constant memory (single host thread per device, see wmrl.h)
-static const void* g_const_src = nullptr;
-static unsigned long long g_const_gen = 0, g_pack_counter = 0;
-static std::unordered_map<const void*, unsigned long long> g_pack_gen;
-static unsigned long long pack_generation(const void* packed) {
+// Which packed image currently sits in constant memory, PER DEVICE, plus the event of the last launch that reads
+// it: several RSSM / actor pairs (different images) may be driven from different streams or host threads.  The
+// mutex serialises {constant upload, launch, event record}; an upload of a different image first makes its stream
+// wait for the previous launch, so a running persistent kernel never has its tables overwritten.
+std::mutex g_tc_mutex;
+unsigned long long g_pack_counter = 0;
+std::unordered_map<const void*, unsigned long long> g_pack_gen;
+unsigned long long tc_pack_generation(const void* packed) {   // caller holds g_tc_mutex
   auto it = g_pack_gen.find(packed);
   return it == g_pack_gen.end() ? 0ull : it->second;
 }
+struct ConstState {
+  const void* src = nullptr;
+  unsigned long long gen = 0;
+  cudaEvent_t last_launch = nullptr;
+  cudaStream_t last_stream = nullptr;
+};
+static ConstState g_const[64];
+
+// tables + packed stages + epilogue parameters of one plan -> its image at `base`
+int tc_pack_plan(const Plan& pl, uint8_t* base, cudaStream_t st);
 
 int tc_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
                     void* packed, cudaStream_t st) {
   Plan pl = make_plan(d, w, aw);
   WMRL_REQUIRE(pl.ok, "pack_weights: unsupported shape");
-  g_pack_gen[packed] = ++g_pack_counter;
-  uint8_t* base = (uint8_t*)packed;
+  {
+    std::lock_guard<std::mutex> lk(g_tc_mutex);
+    if (g_pack_gen.size() > 4096) g_pack_gen.clear();   // stale entries only cost a re-upload of the tables
+    g_pack_gen[packed] = ++g_pack_counter;
+  }
+  if (int r = tc_pack_plan(pl, (uint8_t*)packed, st)) return r;
+  // training: the BPTT kernel's image (transposed weight stages) follows the rollout kernel's
+  if (pl.fold && !pl.pp) {
+    Plan bp = tc_make_bwd_plan(d, w, aw);
+    if (bp.ok) return tc_pack_plan(bp, (uint8_t*)packed + pl.total_bytes, st);
+  }
+  return 0;
+}
+
+int tc_pack_plan(const Plan& pl, uint8_t* base, cudaStream_t st) {
   // tables travel host -> device inside the packed image (synchronous for pageable memory)
   WMRL_CUDA_OK(cudaMemcpyAsync(base + pl.off_stage_tab, pl.stages.data(), pl.stages.size() * sizeof(StageDesc),
                                cudaMemcpyHostToDevice, st));
@@ -2068,24 +2117,13 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
     const uint32_t rows = pl.fold ? 64u : 128u;
     p.stage_out = (pl.Sp >= 32 && pl.Sp % 32 == 0 && 3u * rows * pl.Sp * 4u <= (uint32_t)pl.h2c * 2u * rows) ? 1 : 0;
   }
-  // tables + epilogue parameters -> constant memory (device-to-device from the packed image,
-  // stream-ordered before the launch; skipped when this image is already resident)
-  if (g_const_src != packed || g_const_gen != pack_generation(packed)) {
-    WMRL_CUDA_OK(cudaMemcpyToSymbolAsync(c_stages, base + pl.off_stage_tab, pl.stages.size() * sizeof(StageDesc), 0,
-                                         cudaMemcpyDeviceToDevice, st));
-    WMRL_CUDA_OK(cudaMemcpyToSymbolAsync(c_jobs, base + pl.off_job_tab, pl.jobs.size() * sizeof(JobDesc), 0,
-                                         cudaMemcpyDeviceToDevice, st));
-    WMRL_CUDA_OK(cudaMemcpyToSymbolAsync(c_eparams, base + pl.off_eparams, pl.eparams_floats * sizeof(float), 0,
-                                         cudaMemcpyDeviceToDevice, st));
-    g_const_src = packed;
-    g_const_gen = pack_generation(packed);
-  }
   // per-device launch state, queried / set once
   static int s_sms[64];
   static unsigned s_smem[64];
   int dev = 0;
   WMRL_CUDA_OK(cudaGetDevice(&dev));
   WMRL_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
+  std::lock_guard<std::mutex> lk(g_tc_mutex);
   if (s_sms[dev] == 0) WMRL_CUDA_OK(cudaDeviceGetAttribute(&s_sms[dev], cudaDevAttrMultiProcessorCount, dev));
   if (s_smem[dev] < pl.smem_bytes) {
     WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2103,6 +2141,20 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
     WMRL_CUDA_OK(cudaFuncSetAttribute(tc_imagine_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem_bytes));
     s_smem[dev] = pl.smem_bytes;
+  }
+  // tables + epilogue parameters -> constant memory (device-to-device from the packed image, stream-ordered
+  // before the launch; skipped when this image is already resident on this device)
+  ConstState& cs = g_const[dev];
+  if (cs.src != packed || cs.gen != tc_pack_generation(packed)) {
+    if (cs.last_launch && cs.last_stream != st) WMRL_CUDA_OK(cudaStreamWaitEvent(st, cs.last_launch, 0));
+    WMRL_CUDA_OK(cudaMemcpyToSymbolAsync(c_stages, base + pl.off_stage_tab, pl.stages.size() * sizeof(StageDesc), 0,
+                                         cudaMemcpyDeviceToDevice, st));
+    WMRL_CUDA_OK(cudaMemcpyToSymbolAsync(c_jobs, base + pl.off_job_tab, pl.jobs.size() * sizeof(JobDesc), 0,
+                                         cudaMemcpyDeviceToDevice, st));
+    WMRL_CUDA_OK(cudaMemcpyToSymbolAsync(c_eparams, base + pl.off_eparams, pl.eparams_floats * sizeof(float), 0,
+                                         cudaMemcpyDeviceToDevice, st));
+    cs.src = packed;
+    cs.gen = tc_pack_generation(packed);
   }
   const int sms = s_sms[dev];
   if (pl.cta == 2) {
@@ -2132,6 +2184,9 @@ int tc_imagine_fwd(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_pa
     else tc_imagine_kernel<1, false><<<grid, kThreads, pl.smem_bytes, st>>>(p);
   }
   WMRL_CUDA_OK(cudaGetLastError());
+  if (!cs.last_launch) WMRL_CUDA_OK(cudaEventCreateWithFlags(&cs.last_launch, cudaEventDisableTiming));
+  WMRL_CUDA_OK(cudaEventRecord(cs.last_launch, st));
+  cs.last_stream = st;
   return 0;
 }
 

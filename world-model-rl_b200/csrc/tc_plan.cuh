@@ -102,6 +102,10 @@ struct PackOp {
   int nseg;                 // the stage's N rows are the concatenation of up to 4 source row ranges
   int row0[4], valid[4], pad[4];
   int k0, kvalid, nk8;
+  // composite K (nks > 0): the K index space is the concatenation of up to 4 source ranges [kk0, +kkvalid) padded to
+  // kkpad each (e.g. the GRU gate blocks [n | r | z] of W_ih^T); this op covers K [kbegin, kbegin + 8 * nk8) of it
+  int nks, kbegin;
+  int kk0[4], kkvalid[4], kkpad[4];
   int split;   // 2: the stage is stored as two N-halves (one per CTA of a pair), each [k/8][N/2][8]
   unsigned long long dst_off;
   const float* bias;   // optional: K index bias_k of this op holds bias[row] (bias folded into the GEMM through a
@@ -154,6 +158,7 @@ struct Plan {
   uint32_t off_h, off_s, off_a, off_x, off_h2, panels_bytes, ring_off, bar_off, smem_bytes;
   int nslots;
   StashLayout sl{};     // training stash (folded-pair kernel only)
+  uint32_t boff[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // BPTT plan: panel offsets (go, gmu, gx, big, carry, red) and bound's eparams offset
   std::vector<StageDesc> stages;
   std::vector<JobDesc> jobs;
   std::vector<PackOp> pack_ops;
@@ -177,7 +182,13 @@ struct RowSpec {
   void add(int r0, int v, int p) { seg[nseg++] = {r0, v < 0 ? 0 : (v > p ? p : v), p}; }
   int N() const { int n = 0; for (int i = 0; i < nseg; ++i) n += seg[i].pad; return n; }
 };
-struct Seg { uint32_t a_off; int kpad; const float* src; int ld; int k0; int kvalid; const float* bias = nullptr; int bias_k = -1; int trans = 0; };
+struct Seg {
+  uint32_t a_off; int kpad; const float* src; int ld; int k0; int kvalid; const float* bias = nullptr; int bias_k = -1;
+  int trans = 0;
+  int nks = 0;           // composite K: kpad must equal the sum of kkpad
+  int kk0[4] = {0, 0, 0, 0}, kkvalid[4] = {0, 0, 0, 0}, kkpad[4] = {0, 0, 0, 0};
+  void add_k(int k0_, int valid_, int pad_) { kk0[nks] = k0_; kkvalid[nks] = valid_; kkpad[nks] = pad_; ++nks; }
+};
 
 static void add_acc_group(Plan& pl, const RowSpec& rs, const std::vector<Seg>& segs, int tmem_col,
                           bool dbuf, bool first_of_job, int dep, bool last_of_job, bool onto_existing = false,
@@ -214,6 +225,8 @@ static void add_acc_group(Plan& pl, const RowSpec& rs, const std::vector<Seg>& s
       op.k0 = sg.k0 + done * 16;
       op.kvalid = std::max(0, sg.kvalid - done * 16);
       op.nk8 = nk * 2;
+      op.nks = sg.nks; op.kbegin = done * 16;
+      for (int q = 0; q < 4; ++q) { op.kk0[q] = sg.kk0[q]; op.kkvalid[q] = sg.kkvalid[q]; op.kkpad[q] = sg.kkpad[q]; }
       op.split = pl.cta;
       op.dst_off = pl.data_bytes;
       op.bias = nullptr; op.bias_k = -1;
@@ -235,5 +248,9 @@ static uint32_t add_vec(Plan& pl, const float* s1, const float* s2, int off, int
   pl.eparams_floats += pad;
   return at;
 }
+
+// BPTT plan (tc_bptt.cu): transposed weight stages + backward jobs; ok == false when the shape has no bf16 training path
+Plan tc_make_bwd_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw);
+size_t tc_bwd_image_offset(const Dims& d);
 
 }  // namespace wmrl

@@ -16,7 +16,7 @@ ABI_VERSION = 1
 
 CONTINUOUS, DISCRETE = 0, 1
 FP32, BF16 = 0, 1
-FLAG_WM_WGRAD, FLAG_SAVE_FOR_BWD = 1, 2
+FLAG_WM_WGRAD, FLAG_SAVE_FOR_BWD, FLAG_TRACE, FLAG_BACKWARD = 1, 2, 4, 8
 OP_IMAGINE, OP_OBSERVE = 0, 1
 
 _f32p = C.c_void_p  # device pointers travel as integers
@@ -64,6 +64,7 @@ _SIGNATURES = {
     "wmrl_abi_version": (C.c_int, []),
     "wmrl_last_error": (C.c_char_p, []),
     "wmrl_device_supports_bf16": (C.c_int, []),
+    "wmrl_bf16_train_supported": (C.c_int, [C.POINTER(Dims)]),
     "wmrl_saved_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int]),
     "wmrl_workspace_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int]),
     "wmrl_packed_bytes": (C.c_size_t, [C.POINTER(Dims)]),

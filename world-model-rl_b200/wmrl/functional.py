@@ -66,6 +66,26 @@ def _require_cuda(*tensors: torch.Tensor) -> torch.device:
     return dev
 
 
+_WARNED = set()
+
+
+def _warn_once(key: str, msg: str) -> None:
+    if key not in _WARNED:
+        _WARNED.add(key)
+        import warnings
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
+
+def effective_imagine_precision(cfg: "PathConfig", B: int, H: int, need_actor_grad: bool, need_rssm_grad: bool) -> str:
+    """'bf16' or 'fp32': which kernels an ``imagine_rollout`` call with this configuration runs."""
+    if cfg.precision != _lib.BF16:
+        return "fp32"
+    if not (need_actor_grad or need_rssm_grad):
+        return "bf16"
+    dq = cfg.dims(B, H, _lib.FLAG_SAVE_FOR_BWD, _lib.BF16)
+    return "bf16" if (not need_rssm_grad and _lib.load().wmrl_bf16_train_supported(C.byref(dq))) else "fp32"
+
+
 def _on(dev):
     """libwmrl launches kernels, uploads constants and sets function attributes on the CUDA *current*
     device; every native call therefore runs with the tensors' device made current (the modules may live
@@ -184,11 +204,20 @@ class ImagineRollout(torch.autograd.Function):
             dist_b = torch.empty(B, T1, cfg.S, device=dev)
             idx = None
         actions = torch.empty(B, H, cfg.A, device=dev)
-        # the tcgen05 kernel does not record activations; when a backward will
-        # follow, the fp32 chain runs (and records) instead - see DESIGN.md
+        # bf16 + autograd: the persistent rollout kernel records a bf16 activation stash and the backward is the
+        # persistent tcgen05 BPTT kernel (continuous variant, world model frozen as in world_model.py:172).
+        # Shapes / cases it does not cover (RSSM weight gradients requested, discrete latent) record with the
+        # fp32 chain instead - loudly, once per process.
         precision = cfg.precision
         if need_bwd and precision == _lib.BF16:
-            precision = _lib.FP32
+            need_rssm = any(ctx.needs_input_grad[9 + n_actor:])
+            dq = cfg.dims(B, H, _lib.FLAG_SAVE_FOR_BWD, _lib.BF16)
+            if need_rssm or not lib.wmrl_bf16_train_supported(C.byref(dq)):
+                _warn_once("bf16-train-fallback",
+                           "wmrl: precision='bf16' with autograd recording runs the fp32 tensor-core chain for this call "
+                           + ("(RSSM weight gradients requested: the bf16 BPTT kernel covers the frozen-world-model case)"
+                              if need_rssm else "(this shape / variant has no bf16 BPTT kernel)"))
+                precision = _lib.FP32
         flags = _lib.FLAG_SAVE_FOR_BWD if need_bwd else 0
         d = cfg.dims(B, H, flags, precision)
         saved_n = lib.wmrl_saved_bytes(C.byref(d), _lib.OP_IMAGINE) if need_bwd else 0
@@ -209,6 +238,8 @@ class ImagineRollout(torch.autograd.Function):
             dist_b[:, 0] = init_db.detach()
         ctx.cfg, ctx.H, ctx.n_actor = cfg, H, n_actor
         ctx.has_b = dist_b is not None
+        ctx.precision = precision
+        ctx.packed = packed if precision == _lib.BF16 else None
         if need_bwd:
             ctx.save_for_backward(nz, bd, deter_seq, stoch_seq, dist_a,
                                   dist_b if dist_b is not None else torch.empty(0, device=dev),
@@ -241,8 +272,8 @@ class ImagineRollout(torch.autograd.Function):
         need = ctx.needs_input_grad
         base = 9
         need_rssm = any(need[base + n_actor:])
-        flags = _lib.FLAG_SAVE_FOR_BWD | (_lib.FLAG_WM_WGRAD if need_rssm else 0)
-        d = cfg.dims(B, H, flags, _lib.FP32)
+        flags = _lib.FLAG_SAVE_FOR_BWD | _lib.FLAG_BACKWARD | (_lib.FLAG_WM_WGRAD if need_rssm else 0)
+        d = cfg.dims(B, H, flags, ctx.precision)
         ga = [torch.zeros_like(p) for p in a32]
         gr = [torch.zeros_like(p) for p in r32] if need_rssm else [None] * len(r32)
         g_d0 = torch.zeros(B, cfg.D, device=dev)
@@ -254,7 +285,7 @@ class ImagineRollout(torch.autograd.Function):
         gw = _rssm_ptrs(gr)
         if B > 0 and H > 0:
             _native(dev, lib.wmrl_imagine_bwd,
-                C.byref(d), C.byref(w), C.byref(aw), None, nz.data_ptr(), deter_seq.data_ptr(),
+                C.byref(d), C.byref(w), C.byref(aw), _lib.ptr(ctx.packed), nz.data_ptr(), deter_seq.data_ptr(),
                 stoch_seq.data_ptr(), dist_a.data_ptr(), _lib.ptr(dist_b if ctx.has_b else None),
                 actions.data_ptr(), saved.data_ptr(), _lib.ptr(g_deter), _lib.ptr(g_stoch), _lib.ptr(g_da),
                 _lib.ptr(g_db), C.byref(gaw), C.byref(gw) if need_rssm else None, g_d0.data_ptr(),
