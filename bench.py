@@ -148,57 +148,92 @@ def host_inputs(c, B, seed, pin):
 
 
 def cpu_reference_rate(c, rssm, actor, sample_rows, repeats, threads):
-    """oracle (reference restatement) on the host cores; returns (latent-steps/s, seconds per pass)."""
+    """the reference (staged copy) or its oracle restatement on the host cores; returns (latent-steps/s, seconds per
+    pass, kind)."""
     from oracle import rssm_oracle as O
     torch.set_num_threads(threads)
-    w = {k: v.detach().cpu() for k, v in rssm.state_dict().items()}
-    aw = {k: v.detach().cpu() for k, v in actor.state_dict().items()}
     d0, s0, nz = host_inputs(c, sample_rows, 11, pin=False)
+    ref = reference_modules(c, "cpu")
+    if ref is not None:
+        r_, a_ = ref
+        for p_ in list(r_.parameters()) + list(a_.parameters()):
+            p_.requires_grad_(False)
+        init = reference_initial_state(c, d0, s0)
+        kind = "reference"
+
+        def call():
+            return r_.imagine_rollout(init, a_, c["H"])
+    else:
+        w = {k: v.detach().cpu() for k, v in rssm.state_dict().items()}
+        aw = {k: v.detach().cpu() for k, v in actor.state_dict().items()}
+        kind = "port"
+
+        def call():
+            return O.imagine_rollout_reference_like(c["variant"], w, aw, d0, s0, c["H"], c["S"], c["C"])
     best = None
     with torch.no_grad():
         for i in range(repeats + 1):           # first pass is the warm-up
             t0 = time.perf_counter()
-            O.imagine_rollout_reference_like(c["variant"], w, aw, d0, s0, c["H"], c["S"], c["C"])
+            call()
             dt = time.perf_counter() - t0
             if i > 0:
                 best = dt if best is None else min(best, dt)
-    return sample_rows * c["H"] / best, best
+    return sample_rows * c["H"] / best, best, kind
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores - the
+    UNMODIFIED reference modules (oracle/_ref, staged by oracle/make_ref.py; kind "reference") when present,
+    else the oracle port (kind "port") - each step a bounded 16 384-row sample of the 65 536-row workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     c = dict(CFG)
     threads = os.cpu_count() or 1
-    torch.manual_seed(0)
-    import wmrl
-    rssm = wmrl.ContinuousRSSM(c["Hd"], c["D"], c["S"], c["E"], c["A"])
-    actor = wmrl.Actor(c["D"] + c["S"], c["A"], 1.0, c["La"], c["Ha"])
-    from oracle import rssm_oracle as O
     torch.set_num_threads(threads)
-    w = {k: v.detach() for k, v in rssm.state_dict().items()}
-    aw = {k: v.detach() for k, v in actor.state_dict().items()}
-    rows = 16384    # bounded sample of the 65,536-row workload (~0.4 s per step); the CPU rate is flat in B here
+    rows = 16384    # bounded sample (~0.4 s per step); the CPU rate falls slightly with B, so this flatters the CPU arm
     d0, s0, _ = host_inputs(c, rows, 11, pin=False)
+    ref = reference_modules(c, "cpu")
+    if ref is not None:
+        rssm, actor = ref
+        for p_ in list(rssm.parameters()) + list(actor.parameters()):
+            p_.requires_grad_(False)
+        init = reference_initial_state(c, d0, s0)
+        kind, what = "reference", "reflect.components.rssm_world_model.rssm.ContinuousRSSM.imagine_rollout (unmodified, oracle/_ref)"
+
+        def call():
+            return rssm.imagine_rollout(init, actor, c["H"])
+    else:
+        import wmrl
+        from oracle import rssm_oracle as O
+        torch.manual_seed(0)
+        r_ = wmrl.ContinuousRSSM(c["Hd"], c["D"], c["S"], c["E"], c["A"])
+        a_ = wmrl.Actor(c["D"] + c["S"], c["A"], 1.0, c["La"], c["Ha"])
+        w = {k: v.detach() for k, v in r_.state_dict().items()}
+        aw = {k: v.detach() for k, v in a_.state_dict().items()}
+        kind, what = "port", "oracle/rssm_oracle.py::imagine_rollout_reference_like"
+
+        def call():
+            return O.imagine_rollout_reference_like(c["variant"], w, aw, d0, s0, c["H"], c["S"], c["C"])
     times = []
     with torch.no_grad():
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            O.imagine_rollout_reference_like(c["variant"], w, aw, d0, s0, c["H"], c["S"], c["C"])
+            call()
             dt = time.perf_counter() - t0
             if i >= args.warmup:
                 times.append(dt)
     total = sum(times)
     value = rows * c["H"] * len(times) / total
+    cfg = workload_config(c, args.gpus)
+    cfg["reference_sample"] = f"{rows} of {c['B']} start states per step (bounded CPU sample), horizon {c['H']}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(c, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{rows} of 65536 start states x H=15 per step, fp32, torch CPU on {threads} threads, "
-                                   f"oracle/rssm_oracle.py::imagine_rollout_reference_like"},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{rows} of 65536 start states x H=15 per step, fp32, torch CPU on {threads} threads, {what}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -291,6 +326,102 @@ def gpu_eager_baseline(c, dev, ours_ms):
     out["ours_ms"] = ours_ms
     out["speedup_vs_best_eager"] = best / ours_ms
     out["speedup_vs_fp32_eager"] = out["fp32"] / ours_ms
+    return out
+
+
+def aux_all_ranks(c, rssm, actor, dev, world, rank, barrier):
+    """Legs every rank takes part in (informational, outside the headline timed region):
+      train_weak    each rank: 65 536 x 15 forward (recording) + persistent bf16 BPTT + ONE flat NCCL all-reduce of
+                    the actor gradients (the only collective on the path) - whole-job latent-steps/s,
+                    all-reduce bytes and device time, and the fwd+bwd roofline fraction
+      strong_*      forward rollouts with a FIXED global batch (65 536 and 8 192 start states) sharded over the ranks
+    Device-timed with CUDA events, max over ranks."""
+    import torch.distributed as dist
+    import wmrl
+    from wmrl.parallel import allreduce_gradients, shard_range
+    H = c["H"]
+    out = {}
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def timed(fn, n, warm=2):
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) / n)
+
+    # ---- weak-scaling training step
+    B = c["B"]
+    g = torch.Generator().manual_seed(200 + rank)
+    d0 = torch.tanh(torch.randn(B, c["D"], generator=g)).to(dev)
+    s0 = torch.randn(B, c["S"], generator=g).to(dev)
+    init = wmrl.InternalStateContinuous(d0, s0, s0.clone(), torch.ones_like(s0))
+    gfeat = torch.randn(B, H, c["D"] + c["S"], device=dev) / (B * world)
+    for p_ in rssm.parameters():
+        p_.requires_grad_(False)
+    ar_ms, ar_elems = [], [0]
+
+    def train_step():
+        actor.zero_grad(set_to_none=True)
+        seq = rssm.imagine_rollout(init, actor, H)          # noise drawn inside, as the reference does
+        (seq.get_features() * gfeat).sum().backward()
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ar_elems[0] = allreduce_gradients(actor.parameters(), average=False)
+            e1.record()
+            ar_ms.append((e0, e1))
+
+    try:
+        ms = timed(train_step, 5)
+        S_in, F_ = c["S"], c["D"] + c["S"]
+        mac_actor = F_ * c["Ha"] + (c["La"] - 1) * c["Ha"] ** 2 + c["Ha"] * c["A"]
+        mac_dyn = (S_in + c["A"]) * c["D"] + 6 * c["D"] ** 2 + c["D"] * c["Hd"] + c["Hd"] * 2 * c["S"]
+        fl_fb = 2 * (mac_actor + mac_dyn) + 2 * (mac_dyn + 2 * mac_actor - F_ * c["Ha"])    # SURVEY 8d: fwd + bwd (WM frozen)
+        peaks, _ = measured_peaks()
+        tf = fl_fb * B * H / (ms * 1e-3) / 1e12
+        ar = [a_.elapsed_time(b_) for a_, b_ in ar_ms[2:]] if ar_ms else []
+        out["train_weak"] = {
+            "what": "forward (recording) + persistent bf16 BPTT + weight-gradient GEMMs + flat NCCL all-reduce of the actor "
+                    "gradients; 65536 start states per GPU x H 15; precision bf16",
+            "ms_per_step": ms, "latent_steps_per_s": world * B * H / ms * 1e3, "flops_per_latent_step_fwd_bwd": fl_fb,
+            "tflops_per_gpu": tf, "frac_of_bf16_burst": tf / float(peaks.get("bf16_tflops", 1628.3)),
+            "allreduce_bytes": 4 * ar_elems[0], "allreduce_ms_mean": (sum(ar) / len(ar)) if ar else 0.0,
+            "effective_precision": "bf16"}
+    except RuntimeError as e:   # pragma: no cover - reported, not fatal for the headline line
+        out["train_weak"] = {"error": str(e)[:300]}
+    del gfeat
+    actor.zero_grad(set_to_none=True)
+
+    # ---- strong scaling of the forward rollout: fixed global batch sharded over the ranks
+    for gb in (65536, 8192):
+        lo, hi = shard_range(gb, rank, world)
+        n = hi - lo
+        g = torch.Generator().manual_seed(300 + rank)
+        d0 = torch.tanh(torch.randn(n, c["D"], generator=g)).to(dev)
+        s0 = torch.randn(n, c["S"], generator=g).to(dev)
+        nz = torch.randn(H, n, c["S"], generator=g).to(dev)
+        st = wmrl.InternalStateContinuous(d0, s0, s0.clone(), torch.ones_like(s0))
+
+        def fwd():
+            with torch.no_grad():
+                rssm.imagine_rollout(st, actor, H, noise=nz)
+
+        ms = timed(fwd, 20, warm=5)
+        out[f"strong_{gb}"] = {"global_start_states": gb, "start_states_per_gpu": n, "ms_per_rollout": ms,
+                               "latent_steps_per_s": gb * H / ms * 1e3,
+                               "row_tiles_per_gpu": (n + 127) // 128}
     return out
 
 
@@ -482,17 +613,22 @@ def run_ours(args):
     e2e2_value = world * B * H * args.steps / e2e2_s
     h2d2_bytes = sum(t.numel() * 4 for t in (deter0_h, stoch0_h))
 
+    aux_all = None
+    if not args.no_aux:
+        aux_all = aux_all_ranks(c, rssm, actor, dev, world, rank, barrier)
     if rank == 0:
         peaks, peaks_src = measured_peaks()
         fl = flops_per_latent_step(c)
         avg_launch_s = statistics.mean(launch_ms) * 1e-3
         achieved_tf = fl * B * H / avg_launch_s / 1e12
-        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        # the kernel is timed alone, per launch, at un-capped clocks: the BURST bf16 figure is its denominator
+        # (MEASURED_PEAKS.json; the sustained figure was taken at a power-capped 1327 MHz median)
+        peak_tf = float(peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained")))
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath):    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
             with open(tpath) as fh:
-                traffic = json.load(fh).get("tc_imagine_kernel_dram_bytes_per_launch")
+                traffic = json.load(fh).get("tc_imagine_fold_kernel_dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -500,32 +636,36 @@ def run_ours(args):
             "config": workload_config(c, world),
             "clocks": clocks,
             "host": {"numa_bound": bool(numa_bound)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "note": "pinned host start states + noise -> H2D (prefetched on a copy stream) -> "
-                            "RSSM.imagine_rollout -> scalar summary -> D2H, read on the host every step (one step behind the launch)"},
-            "e2e_device_noise": {"value": e2e2_value, "unit": UNIT, "h2d_bytes_per_step": h2d2_bytes,
-                                 "d2h_bytes_per_step": 4,
-                                 "note": "the reference's call shape: only the start states are copied from the host, "
-                                         "the noise is drawn on the device inside imagine_rollout"},
+            "e2e": {"value": e2e2_value, "unit": UNIT, "h2d_bytes_per_step": h2d2_bytes, "d2h_bytes_per_step": 4,
+                    "note": "the reference's call shape through the public module API (rssm.py:123-140: the caller hands "
+                            "over start states, the noise is drawn inside imagine_rollout): pinned host start states -> H2D "
+                            "(prefetched on a copy stream) -> RSSM.imagine_rollout (noise drawn on the device) -> scalar "
+                            "summary of the final latent state -> D2H, read on the host every step (one step behind the launch)"},
+            "e2e_host_noise": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                               "note": "same, with the pre-drawn noise tensor also fed from pinned host memory every step "
+                                       "(the parity-test call shape: 178 MB of H2D per 4 ms step)"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": traffic, "kernel": "tc_imagine_fold_kernel",
                          "flops_per_latent_step": fl, "latent_steps_per_launch": B * H,
                          "avg_launch_ms": avg_launch_s * 1e3,
-                         "peak_source": f"{peaks_src} bf16_tflops_sustained (MEASURED_PEAKS.json)",
-                         "frac_of_burst": achieved_tf / float(peaks.get("bf16_tflops", peak_tf))},
+                         "peak_source": f"{peaks_src} bf16_tflops (burst, MEASURED_PEAKS.json): kernel timed alone per launch",
+                         "frac_of_sustained": achieved_tf / float(peaks.get("bf16_tflops_sustained", peak_tf))},
         }
+        if aux_all is not None:
+            line["aux"] = aux_all
         if world == 1 and not args.no_aux:
-            line["aux"] = aux_configs(dev)
+            line.setdefault("aux", {}).update(aux_configs(dev))
             line["gpu_eager_baseline"] = gpu_eager_baseline(c, dev, avg_launch_s * 1e3)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rows = B          # the whole workload: ~1.5-2.5 s per pass on 16 cores, ~10 s in total
-            rate, secs = cpu_reference_rate(c, rssm, actor, rows, repeats=4, threads=threads)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            rate, secs, kind = cpu_reference_rate(c, rssm, actor, rows, repeats=4, threads=threads)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                                     "sample": f"all {rows} start states x H={H}, 1 warm-up + best of 4 passes "
-                                              f"({secs:.2f} s each), fp32 torch CPU on {threads} threads, oracle "
-                                              f"restatement of rssm.py:123-140 (internal RNG, torch.cat growth)"}
+                                              f"({secs:.2f} s each), fp32 torch CPU on {threads} threads, "
+                                              + ("the unmodified reference RSSM.imagine_rollout (oracle/_ref)" if kind == "reference"
+                                                 else "oracle restatement of rssm.py:123-140 (internal RNG, torch.cat growth)")}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -126,8 +126,10 @@ def test_bf16_value_trainer_step_runs_on_the_fused_kernels():
     dev = "cuda"
     torch.manual_seed(0)
     wm = wmrl.WorldModel(encoder=torch.nn.Identity(), decoder=torch.nn.Identity(),
-                         done_model=wmrl.DenseModel(D + S, 1, 2, 64, output_act="sigmoid") if hasattr(wmrl.DenseModel, "__init__") else None,
-                         reward_model=wmrl.DenseModel(D + S, 1, 2, 64), dynamic_model=rssm).to(dev)
+                         done_model=wmrl.DenseModel(depth=2, input_dim=D + S, hidden_dim=64, output_dim=1,
+                                                    output_act=torch.nn.Sigmoid),
+                         reward_model=wmrl.DenseModel(depth=2, input_dim=D + S, hidden_dim=64, output_dim=1),
+                         dynamic_model=rssm).to(dev)
     critic = wmrl.ValueCritic(D + S, 2, 64).to(dev)
     trainer = wmrl.ValueGradTrainer(actor, critic)
     B, H = 256, 10

@@ -54,6 +54,8 @@ struct BwdParams {
   uint32_t off_go, off_gmu, off_gx, off_big, off_carry, off_red, ring_off, bar_off, slot_bytes, bound_off;
   int nslots, ntiles;
   StashLayout sl;
+  long long* trace;   // WMRL_FLAG_TRACE: SM clocks of CTA 0's first tile: [backward step][job][4] =
+                      // {first MMA issued, accumulator committed, epilogue woke, epilogue done}
 };
 
 // --------------------------------------------------------------------------
@@ -171,7 +173,7 @@ size_t tc_saved_bytes(const Dims& d) {
 size_t tc_bwd_workspace_bytes(const Dims& d) {
   Plan bp = tc_make_bwd_plan(d, nullptr, nullptr);
   if (!bp.ok) return 0;
-  return n_blocks(d) * bp.sl.blk_g + (size_t)((d.B + kTileM - 1) / kTileM) * kTileM * bp.Dp * sizeof(float) + 256;
+  return n_blocks(d) * bp.sl.blk_g + (size_t)((d.B + kTileM - 1) / kTileM) * kTileM * bp.Dp * sizeof(float) + 256 + 65536;
 }
 
 // --------------------------------------------------------------------------
@@ -228,60 +230,97 @@ __device__ __forceinline__ void sample_bwd(const BCtx& c, int ts, bool use_carry
   st_chunk(c.smem_base + p.off_go + (p.Sp / 8 + c.sidx) * kPSB + c.row * 16, gr);
 }
 
-// g = acc * ELU'(a), a = the recorded post-ELU activation (ELU'(z) = 1 for z > 0, else a + 1) -> bf16 panel
-__device__ __forceinline__ void epib_elu(const BCtx& c, const JobDesc& jb) {
-  const int hw = jb.n / 2;
-  for (int sub = c.q; sub * 8 < hw; sub += kQ) {
-    const int f0 = c.hf * hw + sub * 8;
-    float v[8], a[8];
-    tmem_ld8(c.tmem_lane + jb.tmem_col + sub * 8, v);
-    ld_chunk_g(c.fblk + jb.st0 + (f0 / 8) * kStashChunk, a);
-    tmem_ld_wait();
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* ptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= (a[i] > 0.f) ? 1.f : (a[i] + 1.f);
-    st_chunk(c.smem_base + jb.dst_off + (f0 / 8) * kPSB + c.row * 16, v);
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ uint4 ldg16(const void* ptr) { return *reinterpret_cast<const uint4*>(ptr); }
+
+// Every epilogue needs recorded activations from HBM.  The epilogue warps idle while the job's MMAs run, so each job
+// has a PREFETCH half that issues its global loads BEFORE the accumulator wait (the round trip overlaps the MMAs),
+// and the producer lane pulls the next step's stash block into L2 one step ahead.
+constexpr int kSubMax = 4;   // 8-column sub-groups per thread of a <= 256-wide accumulator (13 per lane half / kQ warps)
+
+// ---- g = acc * ELU'(a), a = the recorded post-ELU activation (ELU'(z) = 1 for z > 0, else a + 1) -> bf16 panel
+struct EluPre { uint4 a[kSubMax]; };
+__device__ __forceinline__ void elu_prefetch(const BCtx& c, const JobDesc& jb, EluPre& pf) {
+  const int hw = jb.n / 2;
+#pragma unroll
+  for (int o = 0; o < kSubMax; ++o) {
+    const int sub = c.q + o * kQ;
+    if (sub * 8 < hw) pf.a[o] = ldg16(c.fblk + jb.st0 + ((c.hf * hw) / 8 + sub) * kStashChunk);
+  }
+}
+__device__ __forceinline__ void epib_elu(const BCtx& c, const JobDesc& jb, const EluPre& pf) {
+  const int hw = jb.n / 2;
+#pragma unroll
+  for (int o = 0; o < kSubMax; ++o) {
+    const int sub = c.q + o * kQ;
+    if (sub * 8 < hw) {
+      const int f0 = c.hf * hw + sub * 8;
+      float v[8], a[8];
+      tmem_ld8(c.tmem_lane + jb.tmem_col + sub * 8, v);
+      unpack8(pf.a[o], a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= (a[i] > 0.f) ? 1.f : (a[i] + 1.f);
+      st_chunk(c.smem_base + jb.dst_off + (f0 / 8) * kPSB + c.row * 16, v);
+    }
   }
 }
 
-// GRUCell backward (torch.nn.GRUCell as used at rssm.py:66; h' = (1-z) n + z h, n = tanh(i_n + r h_n)):
-// accumulator = g_hid W1 (prior-head path of dL/dh'); + carried dL/dh' + upstream dL/ddeter[t+1].  Writes the gate
+// ---- GRUCell backward (torch.nn.GRUCell as used at rssm.py:66; h' = (1-z) n + z h, n = tanh(i_n + r h_n)):
+// accumulator = g_hid W1 (prior-head path of dL/dh'); the scratch row holds the rest of dL/dh' (carried gradient +
+// upstream dL/ddeter[t+1], put there by the previous backward step / the tile initialisation).  Writes the gate
 // gradient panels [g_n | g_r | g_z | g_n r] and parks the direct term dL/dh' z in the scratch row.
-__device__ __forceinline__ void epib_gru(const BCtx& c, const JobDesc& jb) {
+struct GruPre { uint4 g[4]; float hp[8], cr[8]; };
+__device__ __forceinline__ void gru_load(const BCtx& c, int sub, GruPre& pf) {
+  const BwdParams& p = *c.p;
+  const int col = c.hf * (p.Dp / 2) + sub * 8;
+  const uint8_t* f = c.fblk + (col / 8) * kStashChunk;
+  pf.g[0] = ldg16(f + p.sl.gr);
+  pf.g[1] = ldg16(f + p.sl.gz);
+  pf.g[2] = ldg16(f + p.sl.gn);
+  pf.g[3] = ldg16(f + p.sl.ghn);
+  const float* scr = p.gh_scratch + c.prow * p.Dp + col;
+  const float4 a = *reinterpret_cast<const float4*>(scr), b4 = *reinterpret_cast<const float4*>(scr + 4);
+  pf.cr[0] = a.x; pf.cr[1] = a.y; pf.cr[2] = a.z; pf.cr[3] = a.w; pf.cr[4] = b4.x; pf.cr[5] = b4.y; pf.cr[6] = b4.z; pf.cr[7] = b4.w;
+  const float* hrow = p.deter_seq + (c.b * (p.H + 1) + c.t) * p.D + col;
+  if (c.valid && col + 8 <= p.D && (p.D & 3) == 0) {
+    const float4 h0 = *reinterpret_cast<const float4*>(hrow), h1 = *reinterpret_cast<const float4*>(hrow + 4);
+    pf.hp[0] = h0.x; pf.hp[1] = h0.y; pf.hp[2] = h0.z; pf.hp[3] = h0.w; pf.hp[4] = h1.x; pf.hp[5] = h1.y; pf.hp[6] = h1.z; pf.hp[7] = h1.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pf.hp[i] = (c.valid && col + i < p.D) ? hrow[i] : 0.f;
+  }
+}
+__device__ __forceinline__ void epib_gru(const BCtx& c, const JobDesc& jb, GruPre& pf) {
   const BwdParams& p = *c.p;
   const int hw = p.Dp / 2;
-  const long long T1 = p.H + 1;
   const uint32_t gate = c.smem_base + jb.dst_off + c.row * 16;
   const uint32_t gstride = (uint32_t)(p.Dp / 8) * kPSB;
+#pragma unroll 1
   for (int sub = c.q; sub * 8 < hw; sub += kQ) {
     const int col = c.hf * hw + sub * 8;
-    float acc[8], r[8], z[8], n[8], hn[8], hp[8], up[8], cr[8];
+    float acc[8], r[8], z[8], n[8], hn[8];
     tmem_ld8(c.tmem_lane + jb.tmem_col + sub * 8, acc);
-    const uint8_t* f = c.fblk + (col / 8) * kStashChunk;
-    ld_chunk_g(f + p.sl.gr, r);
-    ld_chunk_g(f + p.sl.gz, z);
-    ld_chunk_g(f + p.sl.gn, n);
-    ld_chunk_g(f + p.sl.ghn, hn);
-    float* scr = p.gh_scratch + c.prow * p.Dp + col;
-    if (!c.first) {
-      const float4 a = *reinterpret_cast<const float4*>(scr), b4 = *reinterpret_cast<const float4*>(scr + 4);
-      cr[0] = a.x; cr[1] = a.y; cr[2] = a.z; cr[3] = a.w; cr[4] = b4.x; cr[5] = b4.y; cr[6] = b4.z; cr[7] = b4.w;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) cr[i] = 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const bool ok = c.valid && col + i < p.D;
-      hp[i] = ok ? p.deter_seq[(c.b * T1 + c.t) * p.D + col + i] : 0.f;
-      up[i] = (ok && p.g_deter) ? p.g_deter[(c.b * T1 + c.t + 1) * p.D + col + i] : 0.f;
-    }
+    if (sub != c.q) gru_load(c, sub, pf);      // the first sub-group was fetched before the accumulator wait
+    unpack8(pf.g[0], r); unpack8(pf.g[1], z); unpack8(pf.g[2], n); unpack8(pf.g[3], hn);
     tmem_ld_wait();
     float on[8], orr[8], oz[8], oh[8], od[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float gh = acc[i] + up[i] + cr[i];
+      const float gh = acc[i] + pf.cr[i];
       const float gn = gh * (1.f - z[i]);
-      const float gz = gh * (hp[i] - n[i]);
+      const float gz = gh * (pf.hp[i] - n[i]);
       od[i] = gh * z[i];
       const float gnp = gn * (1.f - n[i] * n[i]);
       on[i] = gnp;
@@ -294,41 +333,89 @@ __device__ __forceinline__ void epib_gru(const BCtx& c, const JobDesc& jb) {
     st_chunk(dst + gstride, orr);
     st_chunk(dst + 2 * gstride, oz);
     st_chunk(dst + 3 * gstride, oh);
+    float* scr = p.gh_scratch + c.prow * p.Dp + col;
     *reinterpret_cast<float4*>(scr) = make_float4(od[0], od[1], od[2], od[3]);
     *reinterpret_cast<float4*>(scr + 4) = make_float4(od[4], od[5], od[6], od[7]);
   }
 }
 
-// dL/dh_t = [g_r | g_z | g_n r] W_hh + dL/dh' z: carried to the previous step (scratch row), or - at t = 0 - the
-// gradient of the start state (+ the upstream gradient of index 0 of the deter sequence)
-__device__ __forceinline__ void epib_carry(const BCtx& c, const JobDesc& jb) {
+// upstream gradient of the deter sequence at index `ts` for 8 columns of this row (0 where absent / padding)
+__device__ __forceinline__ void load_g_deter(const BCtx& c, int ts, int col, float (&up)[8]) {
+  const BwdParams& p = *c.p;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) up[i] = 0.f;
+  if (!p.g_deter || !c.valid) return;
+  const float* g = p.g_deter + (c.b * (p.H + 1) + ts) * p.D + col;
+  if (col + 8 <= p.D && (p.D & 3) == 0) {
+    const float4 a = *reinterpret_cast<const float4*>(g), b4 = *reinterpret_cast<const float4*>(g + 4);
+    up[0] = a.x; up[1] = a.y; up[2] = a.z; up[3] = a.w; up[4] = b4.x; up[5] = b4.y; up[6] = b4.z; up[7] = b4.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (col + i < p.D) up[i] = g[i];
+  }
+}
+
+// tile start: the scratch rows take the upstream gradient of the LAST deter state (the carried part is zero)
+__device__ __forceinline__ void carry_init(const BCtx& c) {
   const BwdParams& p = *c.p;
   const int hw = p.Dp / 2;
   for (int sub = c.q; sub * 8 < hw; sub += kQ) {
     const int col = c.hf * hw + sub * 8;
-    float acc[8];
-    tmem_ld8(c.tmem_lane + jb.tmem_col + sub * 8, acc);
+    float up[8];
+    load_g_deter(c, p.H, col, up);
     float* scr = p.gh_scratch + c.prow * p.Dp + col;
-    const float4 a = *reinterpret_cast<const float4*>(scr), b4 = *reinterpret_cast<const float4*>(scr + 4);
-    tmem_ld_wait();
-    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-    acc[4] += b4.x; acc[5] += b4.y; acc[6] += b4.z; acc[7] += b4.w;
-    if (c.t > 0) {
-      *reinterpret_cast<float4*>(scr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(scr + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    } else if (c.valid) {
+    *reinterpret_cast<float4*>(scr) = make_float4(up[0], up[1], up[2], up[3]);
+    *reinterpret_cast<float4*>(scr + 4) = make_float4(up[4], up[5], up[6], up[7]);
+  }
+}
+
+// ---- dL/dh_t = [g_r | g_z | g_n r] W_hh + dL/dh' z (+ the upstream gradient of deter[t]): carried to the previous
+// step through the scratch row, or - at t = 0 - the gradient of the start state
+struct CarryPre { float4 s[kSubMax][2]; };
+__device__ __forceinline__ void carry_prefetch(const BCtx& c, CarryPre& pf) {
+  const BwdParams& p = *c.p;
+  const int hw = p.Dp / 2;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (col + i < p.D) {
-          float g = acc[i];
-          if (p.g_deter) g += p.g_deter[(c.b * (p.H + 1)) * p.D + col + i];
-          p.g_deter0[c.b * p.D + col + i] = g;
-        }
+  for (int o = 0; o < kSubMax; ++o) {
+    const int sub = c.q + o * kQ;
+    if (sub * 8 < hw) {
+      const float* scr = p.gh_scratch + c.prow * p.Dp + c.hf * hw + sub * 8;
+      pf.s[o][0] = *reinterpret_cast<const float4*>(scr);
+      pf.s[o][1] = *reinterpret_cast<const float4*>(scr + 4);
+    }
+  }
+}
+__device__ __forceinline__ void epib_carry(const BCtx& c, const JobDesc& jb, const CarryPre& pf) {
+  const BwdParams& p = *c.p;
+  const int hw = p.Dp / 2;
+#pragma unroll
+  for (int o = 0; o < kSubMax; ++o) {
+    const int sub = c.q + o * kQ;
+    if (sub * 8 < hw) {
+      const int col = c.hf * hw + sub * 8;
+      float acc[8], up[8];
+      tmem_ld8(c.tmem_lane + jb.tmem_col + sub * 8, acc);
+      load_g_deter(c, c.t, col, up);
+      tmem_ld_wait();
+      acc[0] += pf.s[o][0].x + up[0]; acc[1] += pf.s[o][0].y + up[1]; acc[2] += pf.s[o][0].z + up[2]; acc[3] += pf.s[o][0].w + up[3];
+      acc[4] += pf.s[o][1].x + up[4]; acc[5] += pf.s[o][1].y + up[5]; acc[6] += pf.s[o][1].z + up[6]; acc[7] += pf.s[o][1].w + up[7];
+      if (c.t > 0) {
+        float* scr = p.gh_scratch + c.prow * p.Dp + col;
+        *reinterpret_cast<float4*>(scr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(scr + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        // the previous step's GRU backward reads h_{t-1} of these columns: pull the sector into L2 now
+        if (c.valid && col < p.D) prefetch_l2(p.deter_seq + (c.b * (p.H + 1) + c.t - 1) * p.D + col);
+      } else if (c.valid) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (col + i < p.D) p.g_deter0[c.b * p.D + col + i] = acc[i];
+      }
     }
   }
 }
 
-// [dL/ds_t | dL/da_t] = g_x W_e.  dL/ds_t is carried (shared memory) or, at t = 0, the start-state gradient;
+// ---- [dL/ds_t | dL/da_t] = g_x W_e.  dL/ds_t is carried (shared memory) or, at t = 0, the start-state gradient;
 // dL/da_t goes through the tanh squash (actor.py:49-50: a = tanh(mu / scale) bound) into the g_mu panel + stash.
 // Then - all warps - the Gaussian-sample backward of step t-1, which needs the carried dL/ds.
 __device__ __forceinline__ void epib_emb(const BCtx& c, const JobDesc& jb) {
@@ -377,39 +464,61 @@ __device__ __forceinline__ void epib_emb(const BCtx& c, const JobDesc& jb) {
   }
 }
 
-// LayerNorm(eps 1e-5, affine) + ELU backward of actor block `layer` (actor.py:23-36), from the recorded x-hat and rstd:
+// ---- LayerNorm(eps 1e-5, affine) + ELU backward of actor block `layer` (actor.py:23-36), from the recorded x-hat, rstd:
 //   u = gamma xh + beta, g_u = g_y ELU'(u), g_xh = g_u gamma, g_pre = rstd (g_xh - mean(g_xh) - xh mean(g_xh xh)).
 // g_u and g_pre go to the gradient stash (column sums / weight gradients after the scan); g_pre also becomes the A panel
 // of the next dgrad GEMM unless this is block 0 (the actor input is detached, rssm.py:135).
-__device__ __forceinline__ void epib_ln(const BCtx& c, const JobDesc& jb) {
+// A thread owns up to two 32-column sub-groups; their x-hat (8 x 16 B, packed bf16) is fetched before the wait and
+// kept in registers across both passes.
+struct LnPre { uint4 xh[2][4]; float rstd; };
+__device__ __forceinline__ bool ln_sub(const BwdParams& p, int li, int hf, int& f0, int& tcol) {
+  const int w0 = min(256, p.Ha), nsub0 = w0 / 64;     // 32-column sub-groups per lane half of MMA group 0
+  if (li < nsub0) { f0 = hf * (w0 / 2) + li * 32; tcol = li * 32; return true; }
+  const int l2 = li - nsub0, w1 = p.Ha - 256;
+  if (w1 <= 0 || l2 >= w1 / 64) return false;
+  f0 = 256 + hf * (w1 / 2) + l2 * 32; tcol = 128 + l2 * 32;
+  return true;
+}
+__device__ __forceinline__ void ln_prefetch(const BCtx& c, const JobDesc& jb, LnPre& pf) {
+  const uint8_t* xh_f = c.fblk + jb.st0;
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    int f0, tcol;
+    if (ln_sub(*c.p, c.q + o * kQ, c.hf, f0, tcol)) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pf.xh[o][k] = ldg16(xh_f + (f0 / 8 + k) * kStashChunk);
+    }
+  }
+  pf.rstd = *reinterpret_cast<const float*>(c.fblk - c.row * 16 + c.p->sl.rstd + (jb.layer * kRowsB + c.row) * 4);
+}
+__device__ __forceinline__ void epib_ln(const BCtx& c, const JobDesc& jb, const LnPre& pf) {
   const BwdParams& p = *c.p;
   const uint32_t gsc = jb.p_off, bsc = gsc + p.Ha, gam = bsc + p.Ha;   // gamma*log2e, beta*log2e, gamma
-  const int nmg = (p.Ha + 255) / 256;
-  const uint8_t* xh_f = c.fblk + jb.st0;
   uint8_t* gu_g = c.gblk + p.sl.gu[jb.layer];
   uint8_t* gp_g = c.gblk + p.sl.gp[jb.layer];
   float s1 = 0.f, s2 = 0.f;
-  int li = 0;
-  for (int mg = 0; mg < nmg; ++mg) {
-    const int hw = min(256, p.Ha - mg * 256) / 2;
-    for (int sub = 0; sub < hw / 32; ++sub, ++li) {
-      if ((li % kQ) != c.q) continue;
-      const int f0 = mg * 256 + c.hf * hw + sub * 32;
-      float v[32];
-      tmem_ld32(c.tmem_lane + jb.tmem_col + mg * 128 + sub * 32, v);
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    int f0, tcol;
+    if (!ln_sub(p, c.q + o * kQ, c.hf, f0, tcol)) continue;
+#pragma unroll
+    for (int hk = 0; hk < 2; ++hk) {
+      float v[16];
+      tmem_ld16(c.tmem_lane + jb.tmem_col + tcol + hk * 16, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k = hk * 2 + kk;
         float xh[8], gu[8];
-        ld_chunk_g(xh_f + (f0 / 8 + k) * kStashChunk, xh);
+        unpack8(pf.xh[o][k], xh);
 #pragma unroll
         for (int i = 0; i < 8; i += 4) {
           const float4 g4 = ldcb4(gsc + f0 + k * 8 + i), b4 = ldcb4(bsc + f0 + k * 8 + i), w4 = ldcb4(gam + f0 + k * 8 + i);
           const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w}, gw[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float us = fmaf(gs[e], xh[i + e], bs[e]);            // u * log2(e)
-            const float g_u = v[k * 8 + i + e] * ex2_fast(fminf(us, 0.f));   // ELU'(u) = 1 (u > 0) | exp(u)
+            const float us = fmaf(gs[e], xh[i + e], bs[e]);                          // u * log2(e)
+            const float g_u = v[kk * 8 + i + e] * ex2_fast(fminf(us, 0.f));          // ELU'(u) = 1 (u > 0) | exp(u)
             const float g_x = g_u * gw[e];
             gu[i + e] = g_u;
             s1 += g_x;
@@ -433,20 +542,21 @@ __device__ __forceinline__ void epib_ln(const BCtx& c, const JobDesc& jb) {
   }
   const float inv = 1.f / (float)p.Ha;
   const float m1 = s1 * inv, m2 = s2 * inv;
-  const float rstd = *reinterpret_cast<const float*>(c.fblk - c.row * 16 + p.sl.rstd + (jb.layer * kRowsB + c.row) * 4);
-  li = 0;
-  for (int mg = 0; mg < nmg; ++mg) {
-    const int hw = min(256, p.Ha - mg * 256) / 2;
-    for (int sub = 0; sub < hw / 32; ++sub, ++li) {
-      if ((li % kQ) != c.q) continue;
-      const int f0 = mg * 256 + c.hf * hw + sub * 32;
-      float v[32];
-      tmem_ld32(c.tmem_lane + jb.tmem_col + mg * 128 + sub * 32, v);
+  const float rstd = pf.rstd;
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    int f0, tcol;
+    if (!ln_sub(p, c.q + o * kQ, c.hf, f0, tcol)) continue;
+#pragma unroll
+    for (int hk = 0; hk < 2; ++hk) {
+      float v[16];
+      tmem_ld16(c.tmem_lane + jb.tmem_col + tcol + hk * 16, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k = hk * 2 + kk;
         float xh[8], gp[8];
-        ld_chunk_g(xh_f + (f0 / 8 + k) * kStashChunk, xh);
+        unpack8(pf.xh[o][k], xh);
 #pragma unroll
         for (int i = 0; i < 8; i += 4) {
           const float4 g4 = ldcb4(gsc + f0 + k * 8 + i), b4 = ldcb4(bsc + f0 + k * 8 + i), w4 = ldcb4(gam + f0 + k * 8 + i);
@@ -454,7 +564,7 @@ __device__ __forceinline__ void epib_ln(const BCtx& c, const JobDesc& jb) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float us = fmaf(gs[e], xh[i + e], bs[e]);
-            const float g_x = v[k * 8 + i + e] * ex2_fast(fminf(us, 0.f)) * gw[e];
+            const float g_x = v[kk * 8 + i + e] * ex2_fast(fminf(us, 0.f)) * gw[e];
             gp[i + e] = rstd * (g_x - m1 - xh[i + e] * m2);
           }
         }
@@ -468,6 +578,7 @@ __device__ __forceinline__ void epib_ln(const BCtx& c, const JobDesc& jb) {
 // --------------------------------------------------------------------------
 // the persistent BPTT kernel
 // --------------------------------------------------------------------------
+template <bool kTrace>
 __global__ void __launch_bounds__(kThreadsB, 1) tc_bptt_kernel(const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t kSlot = p.slot_bytes;
@@ -521,8 +632,19 @@ __global__ void __launch_bounds__(kThreadsB, 1) tc_bptt_kernel(const BwdParams p
   if (warp == kProducerWarp) {
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
+      // the fields the epilogues read (x-hat of every block; x, gates, prior hidden, rstd) are two contiguous ranges
+      const uint32_t pf0 = p.sl.xh[0], pf0_bytes = (uint32_t)p.La * (uint32_t)(p.Ha / 8) * kStashChunk;
+      const uint32_t pf1 = p.sl.xe, pf1_bytes = p.sl.blk_f - p.sl.xe;
+      auto pull = [&](size_t blk) {
+        const uint8_t* b0 = p.stash_f + blk * p.sl.blk_f;
+        for (uint32_t o = 0; o < pf0_bytes; o += 65536u) bulk_prefetch_l2(b0 + pf0 + o, min(65536u, pf0_bytes - o));
+        for (uint32_t o = 0; o < pf1_bytes; o += 65536u) bulk_prefetch_l2(b0 + pf1 + o, min(65536u, pf1_bytes - o));
+      };
       for (int grp = unit; grp < ngroups; grp += nunits)
-        for (int ti = 0; ti < p.H; ++ti)
+        for (int ti = 0; ti < p.H; ++ti) {
+          const size_t blk0 = ((size_t)grp * 2 + rank) * (size_t)p.H;
+          if (ti == 0) pull(blk0 + p.H - 1);
+          if (ti + 1 < p.H) pull(blk0 + p.H - 2 - ti);      // one step ahead of the epilogues
           for (int s = 0; s < p.nstages; ++s) {
             const uint4 raw = cb_stages[s];
             const uint32_t bytes = ((raw.y & 0xFFFFu) * 16u) / 2u;
@@ -531,6 +653,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) tc_bptt_kernel(const BwdParams p
             bulk_g2s(ring + slot * kSlot, p.stage_data + (size_t)raw.x * 16u + (size_t)rank * bytes, bytes, full_bar(slot));
             if (++slot == (uint32_t)p.nslots) { slot = 0; phase ^= 1u; }
           }
+        }
     }
   } else if (warp == kMmaWarp) {
     if (lane == 0 && rank != 0) {
@@ -552,18 +675,22 @@ __global__ void __launch_bounds__(kThreadsB, 1) tc_bptt_kernel(const BwdParams p
         mbar_arrive(accf_bar(job));                    // INIT job (sample backward of the last step) has no MMA
         mbar_arrive_remote(mapa(accf_bar(job), 1));
         ++job;
+        const bool tr = kTrace && p.trace && blockIdx.x == 0 && grp == unit;
         for (int ti = 0; ti < p.H; ++ti) {
           uint4 rec_next = stab[0];
+          int jidx = -1;
           for (int s = 0; s < p.nstages; ++s) {
             const uint4 rec = rec_next;
             if (s + 1 < p.nstages) rec_next = stab[s + 1];
             const uint32_t flags = rec.z & 0xFFu;
             if (flags & ST_FIRST_OF_JOB) {
+              ++jidx;
               const uint32_t dep = rec.w >> 16;
               if (dep) {
                 const uint32_t dj = job - dep;
                 mbar_wait(acce_bar(dj), (dj >> 1) & 1u);
               }
+              if (kTrace && tr && ti < 4) p.trace[((ti * p.njobs) + jidx) * 4 + 0] = clock64();
             }
             if (g >= ready_seen) {
               do { ready_seen = *ready_ctr; } while (ready_seen <= g);
@@ -598,6 +725,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) tc_bptt_kernel(const BwdParams p
             tc_commit2(empty_bar(slot), 3);
             if (flags & ST_LAST_OF_JOB) {
               tc_commit2(accf_bar(job), 3);
+              if (kTrace && tr && ti < 4) p.trace[((ti * p.njobs) + jidx) * 4 + 1] = clock64();
               ++job;
             }
             bslot += bslot_step;
@@ -643,9 +771,11 @@ __global__ void __launch_bounds__(kThreadsB, 1) tc_bptt_kernel(const BwdParams p
       c.valid = c.b < p.B;
       const size_t blk0 = ((size_t)grp * 2 + rank) * (size_t)p.H;
       // INIT: the Gaussian-sample backward of the last step (no carried dL/ds yet)
-      mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
+      mbar_wait_backoff_quiet(accf_bar(job), (job >> 1) & 1u);
       c.t = p.H - 1;
+      c.first = true;
       sample_bwd(c, p.H, false);
+      carry_init(c);
       fence_proxy_async_smem();
       WMRL_JOB_DONE_B(job);
       ++job;
@@ -654,17 +784,49 @@ __global__ void __launch_bounds__(kThreadsB, 1) tc_bptt_kernel(const BwdParams p
         c.first = ti == 0;
         c.fblk = p.stash_f + (blk0 + c.t) * p.sl.blk_f + c.row * 16;
         c.gblk = p.stash_g + (blk0 + c.t) * p.sl.blk_g + c.row * 16;
+        const bool tr = kTrace && p.trace && blockIdx.x == 0 && grp == unit && threadIdx.x == 0 && ti < 4;
         for (int jb_i = 0; jb_i < p.njobs; ++jb_i) {
           const JobDesc jb = cb_jobs[jb_i];
-          mbar_wait_backoff(accf_bar(job), (job >> 1) & 1u);
-          tc_fence_after();
-          if (jb.type == JB_ELUB) epib_elu(c, jb);
-          else if (jb.type == JB_GRUB) epib_gru(c, jb);
-          else if (jb.type == JB_CARRY) epib_carry(c, jb);
-          else if (jb.type == JB_EMB) epib_emb(c, jb);
-          else if (jb.type == JB_LNB) epib_ln(c, jb);
+          if (jb.type == JB_LNB) {
+            LnPre pf;
+            ln_prefetch(c, jb, pf);
+            mbar_wait_backoff_quiet(accf_bar(job), (job >> 1) & 1u);
+            tc_fence_after();
+            if (kTrace && tr) p.trace[((ti * p.njobs) + jb_i) * 4 + 2] = clock64();
+            epib_ln(c, jb, pf);
+          } else if (jb.type == JB_ELUB) {
+            EluPre pf;
+            elu_prefetch(c, jb, pf);
+            mbar_wait_backoff_quiet(accf_bar(job), (job >> 1) & 1u);
+            tc_fence_after();
+            if (kTrace && tr) p.trace[((ti * p.njobs) + jb_i) * 4 + 2] = clock64();
+            epib_elu(c, jb, pf);
+          } else if (jb.type == JB_GRUB) {
+            GruPre pf;
+            if (c.q * 8 < p.Dp / 2) gru_load(c, c.q, pf);
+            mbar_wait_backoff_quiet(accf_bar(job), (job >> 1) & 1u);
+            tc_fence_after();
+            if (kTrace && tr) p.trace[((ti * p.njobs) + jb_i) * 4 + 2] = clock64();
+            epib_gru(c, jb, pf);
+          } else if (jb.type == JB_CARRY) {
+            // (its scratch rows were written by this thread in the GRU epilogue of this step: program order)
+            CarryPre pf;
+            carry_prefetch(c, pf);
+            mbar_wait_backoff_quiet(accf_bar(job), (job >> 1) & 1u);
+            tc_fence_after();
+            if (kTrace && tr) p.trace[((ti * p.njobs) + jb_i) * 4 + 2] = clock64();
+            epib_carry(c, jb, pf);
+          } else {
+            mbar_wait_backoff_quiet(accf_bar(job), (job >> 1) & 1u);
+            tc_fence_after();
+            if (kTrace && tr) p.trace[((ti * p.njobs) + jb_i) * 4 + 2] = clock64();
+            epib_emb(c, jb);
+          }
           tc_fence_before();
           fence_proxy_async_smem();
+          if (kTrace && tr) {
+            p.trace[((ti * p.njobs) + jb_i) * 4 + 3] = clock64();
+          }
           WMRL_JOB_DONE_B(job);
           ++job;
         }
@@ -879,6 +1041,8 @@ int tc_imagine_bwd(const Dims& d, const void* packed, const float* noise, const 
   p.ring_off = pl.ring_off; p.bar_off = pl.bar_off; p.slot_bytes = (uint32_t)(pl.stage_bytes / 2);
   p.nslots = pl.nslots; p.ntiles = (d.B + kTileM - 1) / kTileM;
   p.sl = pl.sl;
+  // timeline (tools/trace_bptt.py): the last 64 KB of the gradient-stash workspace are not used by the kernels
+  p.trace = (d.flags & WMRL_FLAG_TRACE) ? (long long*)(p.gh_scratch + (size_t)p.ntiles * kTileM * pl.Dp) : nullptr;
   int dev = 0;
   WMRL_CUDA_OK(cudaGetDevice(&dev));
   WMRL_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
@@ -889,7 +1053,8 @@ int tc_imagine_bwd(const Dims& d, const void* packed, const float* noise, const 
     std::lock_guard<std::mutex> lk(g_tc_mutex);
     if (s_sms[dev] == 0) WMRL_CUDA_OK(cudaDeviceGetAttribute(&s_sms[dev], cudaDevAttrMultiProcessorCount, dev));
     if (s_smem[dev] < pl.smem_bytes) {
-      WMRL_CUDA_OK(cudaFuncSetAttribute(tc_bptt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+      WMRL_CUDA_OK(cudaFuncSetAttribute(tc_bptt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+      WMRL_CUDA_OK(cudaFuncSetAttribute(tc_bptt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
       s_smem[dev] = pl.smem_bytes;
     }
     if (!s_wg[dev]) {
@@ -919,7 +1084,8 @@ int tc_imagine_bwd(const Dims& d, const void* packed, const float* noise, const 
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_bptt_kernel, p));
+    if (p.trace) WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_bptt_kernel<true>, p));
+    else WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_bptt_kernel<false>, p));
     WMRL_CUDA_OK(cudaGetLastError());
     if (!cs.last_launch) WMRL_CUDA_OK(cudaEventCreateWithFlags(&cs.last_launch, cudaEventDisableTiming));
     WMRL_CUDA_OK(cudaEventRecord(cs.last_launch, st));

@@ -65,6 +65,16 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
   }
 }
 
+// Same without the printf (a real call: every register live across the wait would be spilled around it) - for
+// waiters that hold prefetched operands in registers.  A protocol bug still traps.
+__device__ __forceinline__ void mbar_wait_backoff_quiet(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+
 // ---------------------------------------------------------------- cluster (CTA pair)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
