@@ -41,6 +41,17 @@ FILES = [
     "reflect/components/trainers/value/__init__.py",
     "reflect/components/trainers/value/value_trainer.py",
     "reflect/components/trainers/value/critic.py",
+    # the reference's own tests of this path that need no gymnasium environment, and what their conftest imports
+    # (tests/test_reference_drop_in.py runs them against the drop-in modules on the GPU box)
+    "reflect/components/rssm_world_model/tests/conftest.py",
+    "reflect/components/rssm_world_model/tests/test_rssm.py",
+    "reflect/components/rssm_world_model/tests/test_continuous_states.py",
+    "reflect/components/rssm_world_model/tests/test_discrete_states.py",
+    "reflect/components/trainers/reward/__init__.py",
+    "reflect/components/trainers/reward/reward_trainer.py",
+    "reflect/data/__init__.py",
+    "reflect/data/loader.py",
+    "reflect/data/noise.py",
 ]
 
 

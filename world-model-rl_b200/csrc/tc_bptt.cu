@@ -200,13 +200,29 @@ __device__ __forceinline__ void epi_sync_all() { asm volatile("bar.sync 5, %0;" 
 
 // Gaussian-sample backward (autograd of rssm.py:179-181) for the step that produced state `ts` (1..H):
 //   g_mean = dL/dmean[ts] + g_s,  g_raw = (dL/dstd[ts] + g_s eps[ts-1]) sigmoid(raw),  g_s = carried dL/ds + dL/dstoch[ts]
-// sigmoid(raw) = 1 - exp(-softplus(raw)) = 1 - exp(-(std - 0.1)).  Writes the [g_mean | g_raw] panel.
-__device__ __forceinline__ void sample_bwd(const BCtx& c, int ts, bool use_carry) {
+// sigmoid(raw) = 1 - exp(-softplus(raw)) = 1 - exp(-(std - 0.1)).  Writes the [g_mean | g_raw] panel.  The five
+// per-row inputs are loaded ahead of time (SamplePre) by the 8-column owners: threads sidx < Sp/8.
+struct SamplePre { float gs[8], gmu[8], gsd[8], e[8], sd[8]; };
+__device__ __forceinline__ void sample_load(const BCtx& c, int ts, SamplePre& pf) {
   const BwdParams& p = *c.p;
   if (c.sidx >= p.Sp / 8) return;
   const int col = c.sidx * 8;
   const long long o = (c.b * (p.H + 1) + ts) * p.S + col;
   const float* eps = p.noise + ((long long)(ts - 1) * p.B + c.b) * p.S + col;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool ok = c.valid && col + i < p.S;
+    pf.gs[i] = (ok && p.g_stoch) ? p.g_stoch[o + i] : 0.f;
+    pf.gmu[i] = (ok && p.g_mean) ? p.g_mean[o + i] : 0.f;
+    pf.gsd[i] = (ok && p.g_std) ? p.g_std[o + i] : 0.f;
+    pf.e[i] = ok ? eps[i] : 0.f;
+    pf.sd[i] = ok ? p.std_seq[o + i] : 1.f;
+  }
+}
+__device__ __forceinline__ void sample_bwd(const BCtx& c, bool use_carry, const SamplePre& pf) {
+  const BwdParams& p = *c.p;
+  if (c.sidx >= p.Sp / 8) return;
+  const int col = c.sidx * 8;
   float gm[8], gr[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -214,17 +230,10 @@ __device__ __forceinline__ void sample_bwd(const BCtx& c, int ts, bool use_carry
     float gs = 0.f;
     if (use_carry)
       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gs) : "r"(c.smem_base + p.off_carry + ((col + i) * kRowsB + c.row) * 4));
-    float gmu = 0.f, gsd = 0.f, e = 0.f, sd = 1.f;
-    if (ok) {
-      if (p.g_stoch) gs += p.g_stoch[o + i];
-      if (p.g_mean) gmu = p.g_mean[o + i];
-      if (p.g_std) gsd = p.g_std[o + i];
-      e = eps[i];
-      sd = p.std_seq[o + i];
-    }
-    const float sig = 1.f - __expf(-(sd - 0.1f));
-    gm[i] = ok ? gmu + gs : 0.f;
-    gr[i] = ok ? (gsd + gs * e) * sig : 0.f;
+    gs += pf.gs[i];
+    const float sig = 1.f - __expf(-(pf.sd[i] - 0.1f));
+    gm[i] = ok ? pf.gmu[i] + gs : 0.f;
+    gr[i] = ok ? (pf.gsd[i] + gs * pf.e[i]) * sig : 0.f;
   }
   st_chunk(c.smem_base + p.off_go + c.sidx * kPSB + c.row * 16, gm);
   st_chunk(c.smem_base + p.off_go + (p.Sp / 8 + c.sidx) * kPSB + c.row * 16, gr);
@@ -302,9 +311,33 @@ __device__ __forceinline__ void gru_load(const BCtx& c, int sub, GruPre& pf) {
     for (int i = 0; i < 8; ++i) pf.hp[i] = (c.valid && col + i < p.D) ? hrow[i] : 0.f;
   }
 }
+// L2 prefetch (no register cost) of the fp32 rows the LATER jobs of this step read: the upstream deter gradient of
+// index t (carry job), the sample-backward inputs of index t and the actions (embed job) - issued ~15-30K cycles ahead
+__device__ __forceinline__ void prefetch_step_rows(const BCtx& c) {
+  const BwdParams& p = *c.p;
+  if (!c.valid) return;
+  const long long T1 = p.H + 1;
+  if (p.g_deter) {
+    const int hw = p.Dp / 2;
+    for (int sub = c.q; sub * 8 < hw; sub += kQ) {
+      const int col = c.hf * hw + sub * 8;
+      if (col < p.D) prefetch_l2(p.g_deter + (c.b * T1 + c.t) * p.D + col);
+    }
+  }
+  if (c.sidx < p.Sp / 8 && c.sidx * 8 < p.S && c.t > 0) {
+    const long long o = (c.b * T1 + c.t) * p.S + c.sidx * 8;
+    prefetch_l2(p.std_seq + o);
+    if (p.g_stoch) prefetch_l2(p.g_stoch + o);
+    if (p.g_mean) prefetch_l2(p.g_mean + o);
+    if (p.g_std) prefetch_l2(p.g_std + o);
+    prefetch_l2(p.noise + ((long long)(c.t - 1) * p.B + c.b) * p.S + c.sidx * 8);
+  }
+  if (c.sidx == 0) prefetch_l2(p.actions + (c.b * p.H + c.t) * p.A);
+}
 __device__ __forceinline__ void epib_gru(const BCtx& c, const JobDesc& jb, GruPre& pf) {
   const BwdParams& p = *c.p;
   const int hw = p.Dp / 2;
+  prefetch_step_rows(c);
   const uint32_t gate = c.smem_base + jb.dst_off + c.row * 16;
   const uint32_t gstride = (uint32_t)(p.Dp / 8) * kPSB;
 #pragma unroll 1
@@ -418,7 +451,25 @@ __device__ __forceinline__ void epib_carry(const BCtx& c, const JobDesc& jb, con
 // ---- [dL/ds_t | dL/da_t] = g_x W_e.  dL/ds_t is carried (shared memory) or, at t = 0, the start-state gradient;
 // dL/da_t goes through the tanh squash (actor.py:49-50: a = tanh(mu / scale) bound) into the g_mu panel + stash.
 // Then - all warps - the Gaussian-sample backward of step t-1, which needs the carried dL/ds.
-__device__ __forceinline__ void epib_emb(const BCtx& c, const JobDesc& jb) {
+struct EmbPre { SamplePre sp; float act[8]; };
+__device__ __forceinline__ void emb_prefetch(const BCtx& c, const JobDesc& jb, EmbPre& pf) {
+  const BwdParams& p = *c.p;
+  if (c.t > 0) sample_load(c, c.t, pf.sp);
+  // the (single) sub-group of this thread that holds action columns, if any
+  const int hw = jb.n / 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pf.act[i] = 0.f;
+  for (int sub = c.q; sub * 8 < hw; sub += kQ) {
+    const int col = c.hf * hw + sub * 8;
+    if (col >= p.Sp && c.valid) {
+      const int a0 = col - p.Sp;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (a0 + i < p.A) pf.act[i] = p.actions[(c.b * p.H + c.t) * p.A + a0 + i];
+    }
+  }
+}
+__device__ __forceinline__ void epib_emb(const BCtx& c, const JobDesc& jb, const EmbPre& pf) {
   const BwdParams& p = *c.p;
   const int hw = jb.n / 2;
   for (int sub = c.q; sub * 8 < hw; sub += kQ) {
@@ -450,17 +501,16 @@ __device__ __forceinline__ void epib_emb(const BCtx& c, const JobDesc& jb) {
         gm[i] = 0.f;
         if (ai < p.A && c.valid) {
           const float bd = cb_eparams[p.bound_off + ai];
-          const float act = p.actions[(c.b * p.H + c.t) * p.A + ai];
-          const float th = (bd != 0.f) ? act / bd : 0.f;
+          const float th = (bd != 0.f) ? pf.act[i] / bd : 0.f;
           gm[i] = acc[i] * bd * (1.f - th * th) * p.inv_action_scale;
         }
       }
-      st_chunk_sg(c.smem_base + jb.dst_off + (a0 / 8) * kPSB + c.row * 16, c.gblk + p.sl.gmu + (a0 / 8) * kStashChunk, gm);
+      st_chunk_sg_cs(c.smem_base + jb.dst_off + (a0 / 8) * kPSB + c.row * 16, c.gblk + p.sl.gmu + (a0 / 8) * kStashChunk, gm);
     }
   }
   if (c.t > 0) {
     epi_sync_all();
-    sample_bwd(c, c.t, true);
+    sample_bwd(c, true, pf.sp);
   }
 }
 
@@ -525,7 +575,7 @@ __device__ __forceinline__ void epib_ln(const BCtx& c, const JobDesc& jb, const 
             s2 = fmaf(g_x, xh[i + e], s2);
           }
         }
-        st_chunk_g(gu_g + (f0 / 8 + k) * kStashChunk, gu);
+        st_chunk_g_cs(gu_g + (f0 / 8 + k) * kStashChunk, gu);
       }
     }
   }
@@ -568,8 +618,8 @@ __device__ __forceinline__ void epib_ln(const BCtx& c, const JobDesc& jb, const 
             gp[i + e] = rstd * (g_x - m1 - xh[i + e] * m2);
           }
         }
-        if (jb.aux & 1u) st_chunk_sg(c.smem_base + jb.dst_off + (f0 / 8 + k) * kPSB + c.row * 16, gp_g + (f0 / 8 + k) * kStashChunk, gp);
-        else st_chunk_g(gp_g + (f0 / 8 + k) * kStashChunk, gp);
+        if (jb.aux & 1u) st_chunk_sg_cs(c.smem_base + jb.dst_off + (f0 / 8 + k) * kPSB + c.row * 16, gp_g + (f0 / 8 + k) * kStashChunk, gp);
+        else st_chunk_g_cs(gp_g + (f0 / 8 + k) * kStashChunk, gp);
       }
     }
   }
@@ -635,18 +685,31 @@ __global__ void __launch_bounds__(kThreadsB, 1) tc_bptt_kernel(const BwdParams p
       // the fields the epilogues read (x-hat of every block; x, gates, prior hidden, rstd) are two contiguous ranges
       const uint32_t pf0 = p.sl.xh[0], pf0_bytes = (uint32_t)p.La * (uint32_t)(p.Ha / 8) * kStashChunk;
       const uint32_t pf1 = p.sl.xe, pf1_bytes = p.sl.blk_f - p.sl.xe;
-      auto pull = [&](size_t blk) {
+      auto pull_ln = [&](size_t blk) {
         const uint8_t* b0 = p.stash_f + blk * p.sl.blk_f;
-        for (uint32_t o = 0; o < pf0_bytes; o += 65536u) bulk_prefetch_l2(b0 + pf0 + o, min(65536u, pf0_bytes - o));
-        for (uint32_t o = 0; o < pf1_bytes; o += 65536u) bulk_prefetch_l2(b0 + pf1 + o, min(65536u, pf1_bytes - o));
+        for (uint32_t o = 0; o < pf0_bytes; o += 32768u) bulk_prefetch_l2(b0 + pf0 + o, min(32768u, pf0_bytes - o));
+      };
+      auto pull_dyn = [&](size_t blk) {
+        const uint8_t* b0 = p.stash_f + blk * p.sl.blk_f;
+        for (uint32_t o = 0; o < pf1_bytes; o += 32768u) bulk_prefetch_l2(b0 + pf1 + o, min(32768u, pf1_bytes - o));
       };
       for (int grp = unit; grp < ngroups; grp += nunits)
         for (int ti = 0; ti < p.H; ++ti) {
           const size_t blk0 = ((size_t)grp * 2 + rank) * (size_t)p.H;
-          if (ti == 0) pull(blk0 + p.H - 1);
-          if (ti + 1 < p.H) pull(blk0 + p.H - 2 - ti);      // one step ahead of the epilogues
+          const size_t blk = blk0 + p.H - 1 - ti;
+          if (ti == 0) pull_dyn(blk);                        // tile start: no lead time for the first step
+          int jidx = -1;
           for (int s = 0; s < p.nstages; ++s) {
             const uint4 raw = cb_stages[s];
+            if ((raw.y >> 24) & ST_FIRST_OF_JOB) {
+              // operands are pulled into L2 a few jobs (tens of microseconds) ahead of the epilogue that reads them - a
+              // whole step ahead they would be evicted again by the ~100 MB every step streams through the L2:
+              // x-hat of this step's LayerNorm jobs while the GRU job runs, the dynamics fields of the NEXT step
+              // while the second LayerNorm job runs
+              ++jidx;
+              if (jidx == 1) pull_ln(blk);
+              if (jidx == p.njobs - 2 && ti + 1 < p.H) pull_dyn(blk - 1);
+            }
             const uint32_t bytes = ((raw.y & 0xFFFFu) * 16u) / 2u;
             mbar_wait(empty_bar(slot), phase ^ 1u);
             mbar_arrive_expect_tx(full_bar(slot), bytes);
@@ -774,8 +837,18 @@ __global__ void __launch_bounds__(kThreadsB, 1) tc_bptt_kernel(const BwdParams p
       mbar_wait_backoff_quiet(accf_bar(job), (job >> 1) & 1u);
       c.t = p.H - 1;
       c.first = true;
-      sample_bwd(c, p.H, false);
+      {
+        SamplePre sp;
+        sample_load(c, p.H, sp);
+        sample_bwd(c, false, sp);
+      }
       carry_init(c);
+      // h of the last step for the first GRU backward (later steps: the carry job prefetches it)
+      if (c.valid)
+        for (int sub = c.q; sub * 8 < p.Dp / 2; sub += kQ) {
+          const int col = c.hf * (p.Dp / 2) + sub * 8;
+          if (col < p.D) prefetch_l2(p.deter_seq + (c.b * (p.H + 1) + p.H - 1) * p.D + col);
+        }
       fence_proxy_async_smem();
       WMRL_JOB_DONE_B(job);
       ++job;
@@ -817,10 +890,12 @@ __global__ void __launch_bounds__(kThreadsB, 1) tc_bptt_kernel(const BwdParams p
             if (kTrace && tr) p.trace[((ti * p.njobs) + jb_i) * 4 + 2] = clock64();
             epib_carry(c, jb, pf);
           } else {
+            EmbPre pf;
+            emb_prefetch(c, jb, pf);
             mbar_wait_backoff_quiet(accf_bar(job), (job >> 1) & 1u);
             tc_fence_after();
             if (kTrace && tr) p.trace[((ti * p.njobs) + jb_i) * 4 + 2] = clock64();
-            epib_emb(c, jb);
+            epib_emb(c, jb, pf);
           }
           tc_fence_before();
           fence_proxy_async_smem();

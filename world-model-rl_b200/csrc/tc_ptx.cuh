@@ -341,6 +341,20 @@ __device__ __forceinline__ void st_chunk_g(void* gptr, const float* v) {
   *reinterpret_cast<uint4*>(gptr) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
+// streaming variants (st.global.cs: evict-first) for write-once data that is read back only by a later kernel, so that
+// it does not push the operands the running kernel has prefetched out of L2
+__device__ __forceinline__ void st_g_cs(void* gptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(gptr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_chunk_g_cs(void* gptr, const float* v) {
+  st_g_cs(gptr, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void st_chunk_sg_cs(uint32_t smem_addr, void* gptr, const float* v) {
+  const uint32_t a = pack_bf16x2(v[0], v[1]), b = pack_bf16x2(v[2], v[3]);
+  const uint32_t c = pack_bf16x2(v[4], v[5]), d = pack_bf16x2(v[6], v[7]);
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(smem_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  st_g_cs(gptr, a, b, c, d);
+}
 // 8 bf16 of a stash panel chunk -> fp32
 __device__ __forceinline__ void ld_chunk_g(const void* gptr, float (&v)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(gptr);

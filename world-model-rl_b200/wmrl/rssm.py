@@ -28,6 +28,24 @@ from .state import (InternalStateContinuous, InternalStateContinuousSequence, In
 _PRECISIONS = {"fp32": _lib.FP32, "bf16": _lib.BF16}
 
 
+def _sequence_types(like=None):
+    """(continuous Sequence class, discrete Sequence class) to RETURN.  The drop-in contract is the
+    reference's own dataclasses: when the caller works with the reference package - the state handed in is an
+    instance of ``reflect.components.rssm_world_model.state.*``, or that module is loaded in this process - the
+    sequences come back as the reference's ``InternalState{Continuous,Discrete}Sequence`` (``isinstance`` checks and
+    its methods keep working); otherwise as the mirrors in ``wmrl.state`` (same fields and methods)."""
+    import sys
+    ref = sys.modules.get("reflect.components.rssm_world_model.state")
+    use_ref = ref is not None and (like is None or type(like).__module__.startswith("reflect."))
+    if like is not None and type(like).__module__.startswith("reflect.") and ref is None:   # pragma: no cover
+        import importlib
+        ref = importlib.import_module("reflect.components.rssm_world_model.state")
+        use_ref = True
+    if use_ref:
+        return ref.InternalStateContinuousSequence, ref.InternalStateDiscreteSequence
+    return InternalStateContinuousSequence, InternalStateDiscreteSequence
+
+
 def _actor_tensors(actor: nn.Module):
     """(La, Ha, flat tensor list in functional._actor_layout order) from an
     Actor-shaped module (reference Actor or wmrl.actor.Actor)."""
@@ -198,13 +216,13 @@ class RSSMBase(nn.Module):
             init_da, init_db = initial_states.mean.to(device), initial_states.std.to(device)
         outs = ImagineRollout.apply(cfg, int(n_steps), packed, deter0, stoch0, init_da, init_db, noise, bound,
                                     *actor_p, *rssm_p)
+        cont_cls, disc_cls = _sequence_types(initial_states)
         if self.variant == _lib.DISCRETE:
             deter_seq, stoch_seq, logits, actions, _idx = outs
-            seq = InternalStateDiscreteSequence(deter_states=deter_seq, stoch_states=stoch_seq, logits=logits)
+            seq = disc_cls(deter_states=deter_seq, stoch_states=stoch_seq, logits=logits)
         else:
             deter_seq, stoch_seq, means, stds, actions = outs
-            seq = InternalStateContinuousSequence(deter_states=deter_seq, stoch_states=stoch_seq, means=means,
-                                                  stds=stds)
+            seq = cont_cls(deter_states=deter_seq, stoch_states=stoch_seq, means=means, stds=stds)
         return (seq, actions) if return_actions else seq
 
     def observe_rollout(self, obs_embeds: torch.Tensor, action_embs: torch.Tensor, *,
@@ -232,14 +250,13 @@ class RSSMBase(nn.Module):
             inits = (init_pri.mean, init_pri.std, init_post.mean, init_post.std)
         outs = ObserveRollout.apply(cfg, obs_embeds, action_embs.to(device), n_pri, n_post, *inits,
                                     *self._rssm_tensors())
+        cont_cls, disc_cls = _sequence_types()
         if self.variant == _lib.DISCRETE:
-            pri = InternalStateDiscreteSequence(deter_states=outs[0], stoch_states=outs[1], logits=outs[2])
-            post = InternalStateDiscreteSequence(deter_states=outs[3], stoch_states=outs[4], logits=outs[5])
+            pri = disc_cls(deter_states=outs[0], stoch_states=outs[1], logits=outs[2])
+            post = disc_cls(deter_states=outs[3], stoch_states=outs[4], logits=outs[5])
         else:
-            pri = InternalStateContinuousSequence(deter_states=outs[0], stoch_states=outs[1], means=outs[2],
-                                                  stds=outs[3])
-            post = InternalStateContinuousSequence(deter_states=outs[4], stoch_states=outs[5], means=outs[6],
-                                                   stds=outs[7])
+            pri = cont_cls(deter_states=outs[0], stoch_states=outs[1], means=outs[2], stds=outs[3])
+            post = cont_cls(deter_states=outs[4], stoch_states=outs[5], means=outs[6], stds=outs[7])
         return pri, post
 
 
