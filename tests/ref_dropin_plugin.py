@@ -16,8 +16,15 @@ import torch  # noqa: E402
 if "gymnasium" not in sys.modules:
     gym = types.ModuleType("gymnasium")
 
+    class _StubEnv:
+        """what ``gym.make`` returns here: the reference evaluates it as a DEFAULT ARGUMENT at class-definition time
+        (data/loader.py:74), so creating it must succeed; any use of it fails loudly."""
+
+        def __getattr__(self, name):
+            raise RuntimeError("gymnasium is stubbed: the selected reference tests do not step environments")
+
     def _no_env(*a, **k):
-        raise RuntimeError("gymnasium is stubbed: the selected reference tests do not create environments")
+        return _StubEnv()
 
     gym.make = _no_env
     gym.Env = object
