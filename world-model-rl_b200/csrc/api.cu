@@ -1,5 +1,7 @@
 // C ABI of libwmrl (include/wmrl.h): argument checking and dispatch between the
 // fp32 SIMT path (f32_path.cu) and the bf16 tcgen05 path (tc_imagine.cu).
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -23,6 +25,20 @@ int check_dims(const wmrl_dims* d, int op) {
     WMRL_REQUIRE(d->E > 0, "observe needs E > 0");
   }
   return 0;
+}
+
+// Which bf16 forward serves a shape.  The persistent kernels (tc_imagine.cu) are preferred; the layer-wise
+// chain (tc_layer.cu) covers the discrete variant and everything else.  WMRL_BF16_PATH=layer forces the chain
+// (A/B comparisons, tests).
+int bf16_path(const Dims& d) {
+  static int force_layer = -1;
+  if (force_layer < 0) {
+    const char* e = getenv("WMRL_BF16_PATH");
+    force_layer = (e && e[0] == 'l') ? 1 : 0;
+  }
+  if (!force_layer && tc_supported(d)) return 1;
+  if (tcl_supported(d)) return 2;
+  return (force_layer && tc_supported(d)) ? 1 : 0;
 }
 
 static int require_device() {
@@ -61,13 +77,13 @@ int wmrl_device_supports_bf16(void) {
 int wmrl_bf16_train_supported(const wmrl_dims* d) {
   if (check_dims(d, 0)) return 0;
   Dims dd(*d);
-  return tc_train_supported(dd) ? 1 : 0;
+  return (bf16_path(dd) == 1 && tc_train_supported(dd)) ? 1 : 0;
 }
 
 size_t wmrl_saved_bytes(const wmrl_dims* d, int op) {
   if (check_dims(d, op)) return 0;
   Dims dd(*d);
-  if (op == 0 && d->precision == WMRL_BF16 && tc_train_supported(dd)) return tc_saved_bytes(dd);
+  if (op == 0 && d->precision == WMRL_BF16 && bf16_path(dd) == 1 && tc_train_supported(dd)) return tc_saved_bytes(dd);
   return f32_saved_bytes(dd, op);
 }
 
@@ -76,9 +92,10 @@ size_t wmrl_workspace_bytes(const wmrl_dims* d, int op) {
   Dims dd(*d);
   size_t a = f32_workspace_bytes(dd, op);
   if (d->precision == WMRL_BF16 && op == 0) {
-    size_t b = tc_workspace_bytes(dd);
+    const int path = bf16_path(dd);
+    size_t b = path == 2 ? tcl_workspace_bytes(dd) : tc_workspace_bytes(dd);
     if (b > a) a = b;
-    if ((d->flags & WMRL_FLAG_BACKWARD) && tc_train_supported(dd)) {   // gradient stash of the bf16 BPTT
+    if ((d->flags & WMRL_FLAG_BACKWARD) && path == 1 && tc_train_supported(dd)) {   // gradient stash of the bf16 BPTT
       b = tc_bwd_workspace_bytes(dd);
       if (b > a) a = b;
     }
@@ -89,8 +106,8 @@ size_t wmrl_workspace_bytes(const wmrl_dims* d, int op) {
 size_t wmrl_packed_bytes(const wmrl_dims* d) {
   if (check_dims(d, 0)) return 0;
   Dims dd(*d);
-  if (!tc_supported(dd)) return 0;
-  return tc_packed_bytes(dd);
+  const int path = bf16_path(dd);
+  return path == 1 ? tc_packed_bytes(dd) : (path == 2 ? tcl_packed_bytes(dd) : 0);
 }
 
 int wmrl_pack_weights(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
@@ -98,8 +115,10 @@ int wmrl_pack_weights(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_
   if (int r = check_dims(d, 0)) return r;
   WMRL_REQUIRE(w && aw && packed, "pack_weights: NULL argument");
   Dims dd(*d);
-  WMRL_REQUIRE(tc_supported(dd), "pack_weights: shape not supported by the tcgen05 path");
+  const int path = bf16_path(dd);
+  WMRL_REQUIRE(path != 0, "pack_weights: shape not supported by the tcgen05 path");
   if (int r = require_device()) return r;
+  if (path == 2) return tcl_pack_weights(dd, w, aw, packed, (cudaStream_t)stream);
   return tc_pack_weights(dd, w, aw, packed, (cudaStream_t)stream);
 }
 
@@ -121,9 +140,17 @@ int wmrl_imagine_fwd(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_a
   if (save)
     WMRL_REQUIRE(saved && saved_bytes >= wmrl_saved_bytes(d, 0), "imagine_fwd: saved buffer too small");
   if (d->precision == WMRL_BF16) {
-    WMRL_REQUIRE(tc_supported(dd), "imagine_fwd: shape not supported by the bf16 tcgen05 path");
+    const int path = bf16_path(dd);
+    WMRL_REQUIRE(path != 0, "imagine_fwd: shape not supported by the bf16 tcgen05 path");
     WMRL_REQUIRE(packed, "imagine_fwd: bf16 path needs the packed weight image");
     WMRL_REQUIRE(wmrl_device_supports_bf16(), "imagine_fwd: bf16 path needs an sm_100 device");
+    if (path == 2) {
+      WMRL_REQUIRE(!save, "imagine_fwd: the layer-wise bf16 chain has no training path (activation stash + BPTT); "
+                          "record with the fp32 forward");
+      WMRL_REQUIRE(dd.variant == WMRL_CONTINUOUS || idx, "imagine_fwd: discrete needs idx");
+      return tcl_imagine_fwd(dd, packed, deter0, stoch0, noise, deter_seq, stoch_seq, dist_a, dist_b, actions, idx, ws,
+                             (cudaStream_t)stream);
+    }
     WMRL_REQUIRE(!save || tc_train_supported(dd), "imagine_fwd: this shape has no bf16 training path (activation "
                                                   "stash + BPTT kernel); record with the fp32 forward");
     return tc_imagine_fwd(dd, w, aw, packed, deter0, stoch0, noise, deter_seq, stoch_seq, dist_a,
@@ -151,7 +178,7 @@ int wmrl_imagine_bwd(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_a
   if (int r = require_device()) return r;
   if (d->precision == WMRL_BF16) {
     // `saved` is the bf16 activation stash written by wmrl_imagine_fwd(precision BF16, SAVE_FOR_BWD)
-    WMRL_REQUIRE(tc_train_supported(dd), "imagine_bwd: this shape has no bf16 BPTT kernel");
+    WMRL_REQUIRE(bf16_path(dd) == 1 && tc_train_supported(dd), "imagine_bwd: this shape has no bf16 BPTT kernel");
     WMRL_REQUIRE(packed, "imagine_bwd: bf16 path needs the packed weight image");
     WMRL_REQUIRE(!(d->flags & WMRL_FLAG_WM_WGRAD), "imagine_bwd: the bf16 BPTT produces actor gradients only "
                                                    "(world model frozen, world_model.py:172); use the fp32 path");

@@ -93,4 +93,16 @@ int tc_imagine_bwd(const Dims& d, const void* packed, const float* noise, const 
                    const float* g_dist_a, const float* g_dist_b, const wmrl_actor_grads* gaw, float* g_deter0,
                    float* g_stoch0, void* ws, cudaStream_t st);
 
+// layer-wise bf16 tcgen05 chain (tc_layer.cu): the discrete RSSM and the continuous shapes outside the persistent kernel
+bool tcl_supported(const Dims& d);
+size_t tcl_packed_bytes(const Dims& d);
+size_t tcl_workspace_bytes(const Dims& d);
+int tcl_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw, void* packed,
+                     cudaStream_t st);
+int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, const float* stoch0, const float* noise,
+                    float* deter_seq, float* stoch_seq, float* dist_a, float* dist_b, float* actions, int32_t* idx,
+                    void* ws, cudaStream_t st);
+// which bf16 forward serves this shape: 1 persistent folded-pair / single-CTA kernel, 2 layer-wise chain, 0 none
+int bf16_path(const Dims& d);
+
 }  // namespace wmrl

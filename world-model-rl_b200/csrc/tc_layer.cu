@@ -1,0 +1,864 @@
+// bf16 tensor-core path of RSSMBase.imagine_rollout (rssm.py:123-140) for the shapes whose latent tile does not
+// fit one SM - the discrete-categorical RSSM (deter 600 / 1024, 32x32 one-hot latent: DESIGN.md 4.7) and every
+// continuous shape outside the persistent folded-pair kernel's limits: the LAYER-WISE tcgen05 chain.
+//
+//   * every activation of a step lives in HBM/L2 as a bf16 PANEL per 128-row batch tile,
+//     [tile][k/8][128 rows][8] - exactly the tcgen05 K-major no-swizzle core-matrix layout of an MMA A operand,
+//     so a K-slice of a tile is ONE contiguous bulk copy (TMA engine, no tensor map) and the epilogue that
+//     produces it stores 512 contiguous bytes per warp.  The whole working set (weights 10-25 MB bf16,
+//     activations <= 16 MB per layer at 8 192 rows) stays in the 126 MB L2 across the horizon;
+//   * one kernel, tc_layer_kernel, runs every layer of the step: persistent CTAs walk (row tile, column tile)
+//     work items; warp roles = TMA producer lane (A K-slices + pre-packed weight K-slices through a 4 x 48 KB
+//     ring), one MMA-issuing lane (tcgen05.mma.cta_group::1.kind::f16, M = 128, N <= 256, fp32 accumulators in
+//     TMEM, double-buffered across work items when a tile needs <= 256 columns) and 16 epilogue warps;
+//   * the layer's elementwise tail is fused into the TMEM -> register epilogue: bias + LayerNorm + ELU
+//     (actor.py:23-36), bias + ELU (rssm.py:33-35, 65), tanh-squash action (actor.py:49-50), the GRUCell gates
+//     with the fp32 master copy of h in the output tensor (rssm.py:66; the accumulator tile is
+//     [i_n | r | z | h_n] of 64 state columns: W_ih x fills [i_n | r | z], W_hh h accumulates onto [r | z] and
+//     fills h_n), the Gaussian reparameterised sample (rssm.py:179-181) and the categorical straight-through
+//     sample (rssm.py:222-227, state/discrete.py:20-37): per 32-class group logsumexp-normalise -> softmax ->
+//     first-index argmax(p / q) entirely in one thread's registers (a thread owns a batch row = a TMEM lane),
+//     fp32 logits + one-hot out, uint8-equivalent index out, one-hot bf16 panel for the next step's GEMMs.
+//
+// The step is a chain of launches on the caller's stream (no host sync): actor blocks, mu, embed, GRU, prior
+// hidden, prior head + sample = La + 5 launches per step.
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "tc_plan.cuh"
+#include "tc_ptx.cuh"
+
+namespace wmrl {
+using namespace ptx;
+
+int tc_pack_plan(const Plan& pl, uint8_t* base, cudaStream_t st);
+
+constexpr int kLEpiWarps = 16, kLEpiThreads = kLEpiWarps * 32, kLThreads = kLEpiThreads + 64;
+constexpr int kLProducerWarp = kLEpiWarps, kLMmaWarp = kLEpiWarps + 1;
+constexpr uint32_t kLSlotBytes = 49152;
+constexpr int kLSlots = 4;
+constexpr uint32_t kLTileChunk = 2048;      // bytes of one 8-column chunk of a 128-row panel tile
+constexpr uint32_t kLParamBytes = 8192;     // per work item epilogue parameters (bias / LayerNorm affine / gate biases)
+constexpr uint32_t kLScratchBytes = 4096;   // LayerNorm partial statistics: [q][row] x (sum, sq)
+constexpr uint32_t kLBarBytes = 256;
+constexpr uint32_t kLSmemBytes = kLSlots * kLSlotBytes + kLParamBytes + kLScratchBytes + kLBarBytes;
+constexpr int kGruTile = 64;                // state columns per GRU work item (4 x 64 = 256 TMEM columns)
+
+enum : int { LE_LN_ELU = 1, LE_BIAS_ELU, LE_MU, LE_GRU, LE_SAMPLE_DISC, LE_SAMPLE_CONT };
+
+struct LSeg {
+  const uint8_t* a;        // activation panel, tile 0
+  uint32_t a_tile_bytes;   // bytes between row tiles
+  uint32_t w_off;          // byte offset of this segment's weights inside a column tile's weight block
+  uint16_t k16;            // K = 16 steps
+  uint16_t n;              // weight rows (MMA N, split into <= 256 pieces)
+  uint16_t tmem_col;
+  uint16_t split;          // != 0: in the first K step columns [0,split) accumulate and [split,n) start fresh
+  uint16_t fresh;          // the first K step overwrites the accumulator
+  uint16_t pad;
+};
+
+struct LayerArgs {
+  LSeg seg[3];
+  int nseg;
+  const uint8_t* w;        // packed weights of the layer: column tile j at w + j * w_tile_bytes
+  uint32_t w_tile_bytes;
+  const float* ep;         // epilogue parameters: column tile j at ep + j * ep_floats
+  uint32_t ep_floats;
+  int kc;                  // K = 16 steps per ring stage
+  int dbuf;                // accumulators double-buffered across work items (tile needs <= 256 TMEM columns)
+  int type;                // LE_*
+  int n;                   // accumulator columns of one column tile seen by the epilogue
+  int NT, MT;              // column tiles, row tiles
+  int B, H, t;
+  int D, S, C, A, Sp, Dp;
+  float inv_action_scale;
+  uint8_t* out;            // destination panel (tile 0)
+  uint32_t out_tile_bytes;
+  int out_cols;            // padded width of the destination panel: chunks beyond it are not stored
+  float *deter_seq, *stoch_seq, *dist_a, *dist_b, *actions;
+  int32_t* idx;
+  const float* noise;
+};
+
+// --------------------------------------------------------------------------
+// epilogues.  Thread -> (row = TMEM lane, q = column split among the 4 warps of a lane quarter)
+// --------------------------------------------------------------------------
+struct LCtx {
+  const LayerArgs* p;
+  uint32_t prm;        // smem address of this work item's epilogue parameters
+  uint32_t scratch;    // smem address of the LayerNorm scratch
+  uint32_t tmem_lane;  // accumulator base of this work item with the warp's lane quarter folded in
+  int row, q, quarter, lane;
+  int mt, nt;
+  long long b;         // global row
+  bool valid;
+  uint8_t* out_row;    // destination panel of this row tile, offset by row * 16
+};
+
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void l_quarter_sync(int quarter) {
+  asm volatile("bar.sync %0, %1;" ::"r"(quarter + 1), "r"(4 * 32) : "memory");
+}
+__device__ __forceinline__ void l_epi_sync() { asm volatile("bar.sync 5, %0;" ::"r"(kLEpiThreads) : "memory"); }
+
+// Linear -> LayerNorm(eps 1e-5) -> ELU (actor.py:23-36); parameters [bias | gamma log2e | beta log2e]
+__device__ __forceinline__ void lepi_ln_elu(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  const int W = p.n, ngrp = W / 32;
+  const uint32_t bias = c.prm, gam = bias + W * 4, bet = gam + W * 4;
+  float sum = 0.f, sq = 0.f;
+  for (int g = c.q; g < ngrp; g += 4) {
+    float v[32];
+    tmem_ld32(c.tmem_lane + g * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = lds4(bias + (g * 32 + i) * 4);
+      const float x0 = v[i] + b4.x, x1 = v[i + 1] + b4.y, x2 = v[i + 2] + b4.z, x3 = v[i + 3] + b4.w;
+      sum += (x0 + x1) + (x2 + x3);
+      sq = fmaf(x0, x0, sq); sq = fmaf(x1, x1, sq); sq = fmaf(x2, x2, sq); sq = fmaf(x3, x3, sq);
+    }
+  }
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(c.scratch + (c.q * 128 + c.row) * 8), "f"(sum), "f"(sq) : "memory");
+  l_quarter_sync(c.quarter);
+  sum = 0.f; sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float a, b;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "r"(c.scratch + (k * 128 + c.row) * 8) : "memory");
+    sum += a; sq += b;
+  }
+  const float inv = 1.f / (float)W;
+  const float mean = sum * inv;
+  const float var = fmaxf(sq * inv - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float nmr = -mean * rstd;
+  for (int g = c.q; g < ngrp; g += 4) {
+    float v[32];
+    tmem_ld32(c.tmem_lane + g * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = lds4(bias + (g * 32 + i) * 4);
+      const float4 g4 = lds4(gam + (g * 32 + i) * 4);
+      const float4 e4 = lds4(bet + (g * 32 + i) * 4);
+      v[i] = elu_scaled(fmaf(fmaf(v[i] + b4.x, rstd, nmr), g4.x, e4.x));
+      v[i + 1] = elu_scaled(fmaf(fmaf(v[i + 1] + b4.y, rstd, nmr), g4.y, e4.y));
+      v[i + 2] = elu_scaled(fmaf(fmaf(v[i + 2] + b4.z, rstd, nmr), g4.z, e4.z));
+      v[i + 3] = elu_scaled(fmaf(fmaf(v[i + 3] + b4.w, rstd, nmr), g4.w, e4.w));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) st_chunk_g(c.out_row + (size_t)(g * 4 + k) * kLTileChunk, v + k * 8);
+  }
+}
+
+// bias + ELU -> panel (embed rssm.py:65, prior hidden rssm.py:33-35); column tile nt covers [nt*n, +n)
+__device__ __forceinline__ void lepi_bias_elu(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  for (int g = c.q; g < p.n / 16; g += 4) {
+    const int col = c.nt * p.n + g * 16;
+    if (col >= p.out_cols) break;
+    float v[16];
+    tmem_ld16(c.tmem_lane + g * 16, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 b4 = lds4(c.prm + (g * 16 + i) * 4);
+      v[i] = elu_fast(v[i] + b4.x); v[i + 1] = elu_fast(v[i + 1] + b4.y);
+      v[i + 2] = elu_fast(v[i + 2] + b4.z); v[i + 3] = elu_fast(v[i + 3] + b4.w);
+    }
+    st_chunk_g(c.out_row + (size_t)(col / 8) * kLTileChunk, v);
+    st_chunk_g(c.out_row + (size_t)(col / 8 + 1) * kLTileChunk, v + 8);
+  }
+}
+
+// a = tanh(mu / action_scale) * bound (actor.py:49-50) -> actions[B,H,A] + the 16-column action panel
+__device__ __forceinline__ void lepi_mu(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  if (c.q != 0) return;
+  float v[16];
+  tmem_ld16(c.tmem_lane, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 b4 = lds4(c.prm + i * 4), d4 = lds4(c.prm + (16 + i) * 4);
+    v[i] = tanh_fast((v[i] + b4.x) * p.inv_action_scale) * d4.x;
+    v[i + 1] = tanh_fast((v[i + 1] + b4.y) * p.inv_action_scale) * d4.y;
+    v[i + 2] = tanh_fast((v[i + 2] + b4.z) * p.inv_action_scale) * d4.z;
+    v[i + 3] = tanh_fast((v[i + 3] + b4.w) * p.inv_action_scale) * d4.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (i >= p.A) v[i] = 0.f;
+    else if (c.valid) p.actions[(c.b * p.H + p.t) * p.A + i] = v[i];
+  }
+  st_chunk_g(c.out_row, v);
+  st_chunk_g(c.out_row + kLTileChunk, v + 8);
+}
+
+// GRUCell gates (rssm.py:66) of one 64-column tile: TMEM [i_n | r | z | h_n]; parameters [b_r | b_z | b_in | b_hn]
+// (b_r = b_ir + b_hr, b_z likewise).  h_prev is the fp32 master copy deter_seq[:, t]; h' goes to deter_seq[:, t+1]
+// and, as bf16, to the other h panel.  Warp q owns the 16-column group q.
+struct LGruPre { float hp[16]; };
+__device__ __forceinline__ void lgru_prefetch(const LCtx& c, LGruPre& pf) {
+  const LayerArgs& p = *c.p;
+  const int col = c.nt * kGruTile + c.q * 16;
+  const float* hprev = p.deter_seq + (c.b * (p.H + 1) + p.t) * p.D;
+  if (c.valid && col + 16 <= p.D && (p.D & 3) == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 h4 = *reinterpret_cast<const float4*>(hprev + col + i);
+      pf.hp[i] = h4.x; pf.hp[i + 1] = h4.y; pf.hp[i + 2] = h4.z; pf.hp[i + 3] = h4.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pf.hp[i] = (c.valid && col + i < p.D) ? hprev[col + i] : 0.f;
+  }
+}
+__device__ __forceinline__ void lepi_gru(const LCtx& c, const LGruPre& pf) {
+  const LayerArgs& p = *c.p;
+  constexpr int cw = kGruTile;
+  const int col0 = c.nt * cw + c.q * 16;
+  if (col0 >= p.Dp) return;
+  float* hnext = p.deter_seq + (c.b * (p.H + 1) + p.t + 1) * p.D;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const int lc = c.q * 16 + hf * 8;   // column inside the tile
+    const int col = c.nt * cw + lc;
+    float gi[8], r[8], z[8], gh[8], hn[8];
+    tmem_ld8(c.tmem_lane + lc, gi);
+    tmem_ld8(c.tmem_lane + cw + lc, r);
+    tmem_ld8(c.tmem_lane + 2 * cw + lc, z);
+    tmem_ld8(c.tmem_lane + 3 * cw + lc, gh);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; i += 4) {
+      const float4 br = lds4(c.prm + (lc + i) * 4), bz = lds4(c.prm + (cw + lc + i) * 4);
+      const float4 bi = lds4(c.prm + (2 * cw + lc + i) * 4), bh = lds4(c.prm + (3 * cw + lc + i) * 4);
+      const float brv[4] = {br.x, br.y, br.z, br.w}, bzv[4] = {bz.x, bz.y, bz.z, bz.w};
+      const float biv[4] = {bi.x, bi.y, bi.z, bi.w}, bhv[4] = {bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float rr = sigmoid_fast(r[i + e] + brv[e]);
+        const float zz = sigmoid_fast(z[i + e] + bzv[e]);
+        const float nn = tanh_fast(gi[i + e] + biv[e] + rr * (gh[i + e] + bhv[e]));
+        const float hprev = pf.hp[hf * 8 + i + e];
+        const float h = (col + i + e < p.D) ? fmaf(zz, hprev - nn, nn) : 0.f;   // (1-z) n + z h
+        hn[i + e] = h;
+      }
+    }
+    if (c.valid) {
+      if (col + 8 <= p.D && (p.D & 3) == 0) {
+        *reinterpret_cast<float4*>(hnext + col) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        *reinterpret_cast<float4*>(hnext + col + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (col + i < p.D) hnext[col + i] = hn[i];
+      }
+    }
+    if (col < p.out_cols) st_chunk_g(c.out_row + (size_t)(col / 8) * kLTileChunk, hn);
+  }
+}
+
+// Gaussian head (rssm.py:179-181): TMEM [mean (Sp) | raw (Sp)], parameters [b_mean | b_raw]; 8-column groups
+__device__ __forceinline__ void lepi_sample_cont(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  const long long T1 = p.H + 1;
+  const long long o = (c.b * T1 + p.t + 1) * p.S;
+  for (int g = c.q; g < p.Sp / 8; g += 4) {
+    const int col = g * 8;
+    float m[8], s[8], sd[8], st[8];
+    tmem_ld8(c.tmem_lane + col, m);
+    tmem_ld8(c.tmem_lane + p.Sp + col, s);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; i += 4) {
+      const float4 bm = lds4(c.prm + (col + i) * 4), bs = lds4(c.prm + (p.Sp + col + i) * 4);
+      const float bmv[4] = {bm.x, bm.y, bm.z, bm.w}, bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool in = c.valid && col + i + e < p.S;
+        const float mean = m[i + e] + bmv[e];
+        const float raw = s[i + e] + bsv[e];
+        const float sp = fmaxf(raw, 0.f) + __logf(1.f + ex2_fast(-fabsf(raw) * 1.4426950408889634f));
+        const float ee = in ? p.noise[((long long)p.t * p.B + c.b) * p.S + col + i + e] : 0.f;
+        m[i + e] = mean;
+        sd[i + e] = sp + 0.1f;
+        st[i + e] = in ? fmaf(sd[i + e], ee, mean) : 0.f;
+        if (in) {
+          p.dist_a[o + col + i + e] = mean;
+          p.dist_b[o + col + i + e] = sd[i + e];
+          p.stoch_seq[o + col + i + e] = st[i + e];
+        }
+      }
+    }
+    st_chunk_g(c.out_row + (size_t)g * kLTileChunk, st);
+  }
+}
+
+// Categorical straight-through head (rssm.py:222-227, state/discrete.py:20-37).  A column tile holds n / S groups of
+// S classes; warp q owns the 32-column blocks q, q+4, ...; a thread holds all classes of its groups in registers.
+//   p = Categorical(logits).probs = softmax(logits - logsumexp(logits));  idx = first argmax(p / q), q ~ Exp(1)
+// (torch.multinomial's single-draw rule); forward value of the straight-through sample is exactly one_hot(idx).
+template <int S>
+__device__ __forceinline__ void lepi_sample_disc(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  const long long T1 = p.H + 1;
+  const int P = p.C * p.S;
+  for (int blk = c.q; blk < p.n / 32; blk += 4) {
+    const int col = c.nt * p.n + blk * 32;     // first logit column of this block
+    if (col >= p.out_cols) break;
+    float l[32], qv[32];
+    tmem_ld32(c.tmem_lane + blk * 32, l);
+    const float* qrow = p.noise + ((long long)p.t * p.B + c.b) * P + col;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      if (c.valid && col + i < P) {
+        const float4 q4 = *reinterpret_cast<const float4*>(qrow + i);
+        qv[i] = q4.x; qv[i + 1] = q4.y; qv[i + 2] = q4.z; qv[i + 3] = q4.w;
+      } else {
+        qv[i] = qv[i + 1] = qv[i + 2] = qv[i + 3] = 1.f;
+      }
+    }
+    tmem_ld_wait();
+    const bool store = c.valid && col < P;
+    float* lo = p.dist_a + (c.b * T1 + p.t + 1) * P + col;
+    float* so = p.stoch_seq + (c.b * T1 + p.t + 1) * P + col;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = lds4(c.prm + (blk * 32 + i) * 4);
+      l[i] += b4.x; l[i + 1] += b4.y; l[i + 2] += b4.z; l[i + 3] += b4.w;
+      if (store && col + i < P) *reinterpret_cast<float4*>(lo + i) = make_float4(l[i], l[i + 1], l[i + 2], l[i + 3]);
+    }
+    int bi[32 / S];
+#pragma unroll
+    for (int g = 0; g < 32 / S; ++g) {
+      float mx = l[g * S];
+#pragma unroll
+      for (int j = 1; j < S; ++j) mx = fmaxf(mx, l[g * S + j]);
+      float se = 0.f;
+#pragma unroll
+      for (int j = 0; j < S; ++j) se += __expf(l[g * S + j] - mx);
+      const float lse = mx + __logf(se);
+      const float mx2 = mx - lse;            // max of the normalised logits
+      float se2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < S; ++j) { l[g * S + j] = __expf((l[g * S + j] - lse) - mx2); se2 += l[g * S + j]; }
+      const float inv = 1.f / se2;
+      float best = -1.f;
+      int b = 0;
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        const float v = __fdividef(l[g * S + j] * inv, qv[g * S + j]);
+        if (v > best) { best = v; b = j; }
+      }
+      bi[g] = b;
+      const int grp = (col / S) + g;
+      if (c.valid && grp < p.C && p.idx) p.idx[(c.b * p.H + p.t) * p.C + grp] = b;
+    }
+    // forward value of the straight-through sample: exactly one_hot(idx) -> fp32 sequence + bf16 panel
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float oh[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) oh[e] = (((k * 8 + e) % S) == bi[(k * 8 + e) / S]) ? 1.f : 0.f;
+      if (col + k * 8 < P) {
+        if (store) {
+          *reinterpret_cast<float4*>(so + k * 8) = make_float4(oh[0], oh[1], oh[2], oh[3]);
+          *reinterpret_cast<float4*>(so + k * 8 + 4) = make_float4(oh[4], oh[5], oh[6], oh[7]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) oh[e] = 0.f;
+      }
+      if (col + k * 8 < p.out_cols) st_chunk_g(c.out_row + (size_t)(col / 8 + k) * kLTileChunk, oh);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// the kernel
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_constant__ LayerArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring = smem_base;
+  const uint32_t prm = smem_base + kLSlots * kLSlotBytes;
+  const uint32_t scratch = prm + kLParamBytes;
+  const uint32_t bars = scratch + kLScratchBytes;
+  auto full_bar = [&](uint32_t s) { return bars + 8u * s; };
+  auto empty_bar = [&](uint32_t s) { return bars + 64u + 8u * s; };
+  auto accf_bar = [&](uint32_t j) { return bars + 128u + 8u * j; };
+  auto acce_bar = [&](uint32_t j) { return bars + 144u + 8u * j; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (bars - smem_base) + 160);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int nitems = p.MT * p.NT;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < (uint32_t)kLSlots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (uint32_t j = 0; j < 2; ++j) { mbar_init(accf_bar(j), 1); mbar_init(acce_bar(j), kLEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == kLMmaWarp) { tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t w_in_slot = (uint32_t)p.kc * 4096u;   // the weight K-slice follows the activation K-slice in a slot
+
+  if (warp == kLProducerWarp) {
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int mt = item / p.NT, nt = item % p.NT;
+        const uint8_t* wt = p.w + (size_t)nt * p.w_tile_bytes;
+        for (int sg = 0; sg < p.nseg; ++sg) {
+          const LSeg& s = p.seg[sg];
+          const uint8_t* a = s.a + (size_t)mt * s.a_tile_bytes;
+          const uint8_t* w = wt + s.w_off;
+          for (int k0 = 0; k0 < (int)s.k16; k0 += p.kc) {
+            const uint32_t nk = (uint32_t)min(p.kc, (int)s.k16 - k0);
+            const uint32_t ab = nk * 4096u, wb = nk * (uint32_t)s.n * 32u;
+            mbar_wait(empty_bar(slot), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(slot), ab + wb);
+            bulk_g2s(ring + slot * kLSlotBytes, a + (size_t)k0 * 4096u, ab, full_bar(slot));
+            bulk_g2s(ring + slot * kLSlotBytes + w_in_slot, w + (size_t)k0 * s.n * 32u, wb, full_bar(slot));
+            if (++slot == (uint32_t)kLSlots) { slot = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == kLMmaWarp) {
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0, it = 0;
+      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        const uint32_t ab = p.dbuf ? (it & 1u) : 0u;
+        const uint32_t use = p.dbuf ? (it >> 1) : it;      // how many times this accumulator buffer was used before
+        if (use > 0) { mbar_wait(acce_bar(ab), (use - 1u) & 1u); tc_fence_after(); }
+        const uint32_t tm0 = tmem_base + ab * 256u;
+        for (int sg = 0; sg < p.nseg; ++sg) {
+          const LSeg& s = p.seg[sg];
+          const uint32_t n = s.n;
+          for (int k0 = 0; k0 < (int)s.k16; k0 += p.kc) {
+            const int nk = min(p.kc, (int)s.k16 - k0);
+            mbar_wait(full_bar(slot), phase);
+            tc_fence_after();
+            const uint32_t a_addr = ring + slot * kLSlotBytes, b_addr = a_addr + w_in_slot;
+            for (int i = 0; i < nk; ++i) {
+              const bool first = (k0 == 0 && i == 0);
+              const uint32_t alo = (((a_addr + (uint32_t)i * 4096u) >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);
+              const uint32_t bk = b_addr + (uint32_t)i * n * 32u;
+              if (first && s.split) {
+                const uint32_t b0 = ((bk >> 4) & 0x3FFFu) | (n << 16);
+                mma_bf16_lohi(tm0 + s.tmem_col, alo, kDescHi, b0, kDescHi, make_idesc_bf16(128, s.split), 1u);
+                const uint32_t b1 = (((bk + (uint32_t)s.split * 16u) >> 4) & 0x3FFFu) | (n << 16);
+                mma_bf16_lohi(tm0 + s.tmem_col + s.split, alo, kDescHi, b1, kDescHi,
+                              make_idesc_bf16(128, n - s.split), 0u);
+              } else {
+                const uint32_t acc = (first && s.fresh) ? 0u : 1u;
+                for (uint32_t n0 = 0; n0 < n; n0 += 256u) {
+                  const uint32_t nn = min(256u, n - n0);
+                  const uint32_t b0 = (((bk + n0 * 16u) >> 4) & 0x3FFFu) | (n << 16);   // LBO = n * 16 B
+                  mma_bf16_lohi(tm0 + s.tmem_col + n0, alo, kDescHi, b0, kDescHi, make_idesc_bf16(128, nn), acc);
+                }
+              }
+            }
+            tc_commit(empty_bar(slot));
+            if (++slot == (uint32_t)kLSlots) { slot = 0; phase ^= 1u; }
+          }
+        }
+        tc_commit(accf_bar(ab));
+      }
+    }
+  } else {
+    LCtx c;
+    c.p = &p;
+    c.prm = prm;
+    c.scratch = scratch;
+    c.quarter = warp & 3;
+    c.q = warp >> 2;
+    c.lane = lane;
+    c.row = c.quarter * 32 + lane;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      const uint32_t ab = p.dbuf ? (it & 1u) : 0u;
+      const uint32_t use = p.dbuf ? (it >> 1) : it;
+      c.mt = item / p.NT; c.nt = item % p.NT;
+      c.b = (long long)c.mt * 128 + c.row;
+      c.valid = c.b < p.B;
+      c.tmem_lane = tmem_base + ab * 256u + ((uint32_t)(c.quarter * 32) << 16);
+      c.out_row = p.out + (size_t)c.mt * p.out_tile_bytes + (size_t)c.row * 16;
+      // this work item's epilogue parameters -> shared memory (the previous item's readers are done)
+      l_epi_sync();
+      {
+        const float4* src = reinterpret_cast<const float4*>(p.ep + (size_t)c.nt * p.ep_floats);
+        for (uint32_t i = threadIdx.x; i < p.ep_floats / 4; i += kLEpiThreads) {
+          const float4 v = src[i];
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(prm + i * 16), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        }
+      }
+      l_epi_sync();
+      LGruPre gpf;
+      if (p.type == LE_GRU) lgru_prefetch(c, gpf);
+      mbar_wait_backoff_quiet(accf_bar(ab), use & 1u);
+      tc_fence_after();
+      switch (p.type) {
+        case LE_LN_ELU: lepi_ln_elu(c); break;
+        case LE_BIAS_ELU: lepi_bias_elu(c); break;
+        case LE_MU: lepi_mu(c); break;
+        case LE_GRU: lepi_gru(c, gpf); break;
+        case LE_SAMPLE_CONT: lepi_sample_cont(c); break;
+        case LE_SAMPLE_DISC:
+          if (p.S == 32) lepi_sample_disc<32>(c);
+          else if (p.S == 16) lepi_sample_disc<16>(c);
+          else if (p.S == 8) lepi_sample_disc<8>(c);
+          else lepi_sample_disc<4>(c);
+          break;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce_bar(ab));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kLMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+// start states -> index 0 of the sequence outputs and the bf16 panels (all 128 rows of every tile, zeros past B)
+__global__ void tcl_init_kernel(const float* __restrict__ deter0, const float* __restrict__ stoch0, float* deter_seq,
+                                float* stoch_seq, uint8_t* hpanel, uint8_t* spanel, int B, int H, int D, int S_in,
+                                int Dp, int Sip) {
+  const int mt = blockIdx.y;
+  const int chunks = Dp / 8 + Sip / 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < chunks * 128; i += gridDim.x * blockDim.x) {
+    const int row = i % 128, ch = i / 128;
+    const long long b = (long long)mt * 128 + row;
+    const bool isd = ch < Dp / 8;
+    const int k8 = isd ? ch : ch - Dp / 8;
+    const int W = isd ? D : S_in;
+    const float* src = isd ? deter0 : stoch0;
+    float* seq = isd ? deter_seq : stoch_seq;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = k8 * 8 + e;
+      v[e] = (b < B && col < W) ? src[b * W + col] : 0.f;
+      if (b < B && col < W) seq[(b * (H + 1)) * W + col] = v[e];
+    }
+    uint8_t* panel = isd ? hpanel + (size_t)mt * (Dp / 8) * kLTileChunk : spanel + (size_t)mt * (Sip / 8) * kLTileChunk;
+    st_chunk_g(panel + (size_t)k8 * kLTileChunk + row * 16, v);
+  }
+}
+
+// --------------------------------------------------------------------------
+// host: plan, packing, launch chain
+// --------------------------------------------------------------------------
+enum { BUF_H0 = 0, BUF_H1, BUF_S, BUF_A, BUF_Y0, BUF_Y1, BUF_X, BUF_HID, BUF_COUNT };
+
+struct LSegH { int buf, k16, n, tmem_col, split, fresh; uint32_t w_off; };
+struct LLayerH {
+  int type = 0, NT = 1, n = 0, nseg = 0, kc = 1, dbuf = 0, out = 0;
+  LSegH seg[3];
+  size_t w_off = 0;          // into the data area
+  uint32_t w_tile_bytes = 0;
+  size_t ep_off = 0;         // float offset into eparams
+  uint32_t ep_floats = 0;
+};
+struct LPlan {
+  bool ok = false;
+  Plan pk;                   // pack ops / vec ops / image offsets (stage and job tables stay empty)
+  std::vector<LLayerH> layers;
+  int Dp = 0, Sip = 0, Sp = 0, Hdp = 0, Ha = 0;
+  int width[BUF_COUNT] = {0};
+};
+
+static int ceil_to(int x, int m) { return (x + m - 1) / m * m; }
+
+// one K segment of one column tile: rows `rs` of src[., ld], K range [k0, k0 + kvalid) padded to kpad
+static void l_add_pack(LPlan& lp, const RowSpec& rs, const float* src, int ld, int k0, int kvalid, int kpad) {
+  PackOp op{};
+  op.src = src; op.ld = ld; op.trans = 0;
+  op.nseg = rs.nseg;
+  for (int q = 0; q < rs.nseg; ++q) { op.row0[q] = rs.seg[q].row0; op.valid[q] = rs.seg[q].valid; op.pad[q] = rs.seg[q].pad; }
+  op.k0 = k0; op.kvalid = kvalid; op.nk8 = kpad / 8;
+  op.nks = 0; op.kbegin = 0;
+  op.split = 1;
+  op.dst_off = lp.pk.data_bytes;
+  op.bias = nullptr; op.bias_k = -1;
+  lp.pk.pack_ops.push_back(op);
+  lp.pk.data_bytes += (size_t)kpad * rs.N() * 2;
+}
+
+static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw) {
+  LPlan lp;
+  const bool disc = d.variant == WMRL_DISCRETE;
+  if (d.Ha % 32 != 0 || d.Ha > 512 || d.Ha < 32 || d.A > 16 || d.La < 1) return lp;
+  if (disc && !(d.S == 4 || d.S == 8 || d.S == 16 || d.S == 32)) return lp;
+  const int Dp = ceil16(d.D), Sip = ceil16(d.S_in), Sp = ceil16(d.S), Hdp = ceil16(d.Hd);
+  if (!disc && 2 * Sp > 256) return lp;
+  lp.Dp = Dp; lp.Sip = Sip; lp.Sp = Sp; lp.Hdp = Hdp; lp.Ha = d.Ha;
+  lp.width[BUF_H0] = lp.width[BUF_H1] = Dp; lp.width[BUF_S] = Sip; lp.width[BUF_A] = 16;
+  lp.width[BUF_Y0] = lp.width[BUF_Y1] = d.Ha; lp.width[BUF_X] = Dp; lp.width[BUF_HID] = Hdp;
+  const float* nul = nullptr;
+  Plan& pk = lp.pk;
+  auto kc_for = [&](int nmax) { int kc = (int)(kLSlotBytes / (4096u + (uint32_t)nmax * 32u)); return std::max(1, std::min(kc, 8)); };
+  // even column tiles of at most `cap` columns, multiples of `unit`
+  auto tiles = [&](int total, int cap, int unit, int& nt, int& wt) {
+    nt = (total + cap - 1) / cap;
+    wt = ceil_to((total + nt - 1) / nt, unit);
+  };
+  // ---- actor blocks: [h | s] (block 0) or y_{l-1} -> Linear -> LayerNorm -> ELU
+  for (int l = 0; l < d.La; ++l) {
+    LLayerH L;
+    L.type = LE_LN_ELU; L.NT = 1; L.n = d.Ha; L.dbuf = d.Ha <= 256 ? 1 : 0; L.out = (l & 1) ? BUF_Y1 : BUF_Y0;
+    L.kc = kc_for(d.Ha);
+    L.w_off = pk.data_bytes;
+    const float* lw = aw ? aw->lin_w[l] : nul;
+    RowSpec rs(0, d.Ha, d.Ha);
+    if (l == 0) {
+      L.nseg = 2;
+      L.seg[0] = {BUF_H0, Dp / 16, d.Ha, 0, 0, 1, 0u};
+      l_add_pack(lp, rs, lw, d.F, 0, d.D, Dp);
+      L.seg[1] = {BUF_S, Sip / 16, d.Ha, 0, 0, 0, (uint32_t)(pk.data_bytes - L.w_off)};
+      l_add_pack(lp, rs, lw, d.F, d.D, d.S_in, Sip);
+    } else {
+      L.nseg = 1;
+      L.seg[0] = {((l - 1) & 1) ? BUF_Y1 : BUF_Y0, d.Ha / 16, d.Ha, 0, 0, 1, 0u};
+      l_add_pack(lp, rs, lw, d.Ha, 0, d.Ha, d.Ha);
+    }
+    L.w_tile_bytes = (uint32_t)(pk.data_bytes - L.w_off);
+    L.ep_off = add_vec(pk, aw ? aw->lin_b[l] : nul, nul, 0, d.Ha, d.Ha);
+    add_vec(pk, aw ? aw->ln_g[l] : nul, nul, 0, d.Ha, d.Ha, 1.4426950408889634f);
+    add_vec(pk, aw ? aw->ln_b[l] : nul, nul, 0, d.Ha, d.Ha, 1.4426950408889634f);
+    L.ep_floats = 3u * d.Ha;
+    lp.layers.push_back(L);
+  }
+  const int ylast = ((d.La - 1) & 1) ? BUF_Y1 : BUF_Y0;
+  // ---- mu head
+  {
+    LLayerH L;
+    L.type = LE_MU; L.NT = 1; L.n = 16; L.dbuf = 1; L.out = BUF_A; L.kc = kc_for(16); L.nseg = 1;
+    L.w_off = pk.data_bytes;
+    L.seg[0] = {ylast, d.Ha / 16, 16, 0, 0, 1, 0u};
+    l_add_pack(lp, RowSpec(0, d.A, 16), aw ? aw->mu_w : nul, d.Ha, 0, d.Ha, d.Ha);
+    L.w_tile_bytes = (uint32_t)(pk.data_bytes - L.w_off);
+    L.ep_off = add_vec(pk, aw ? aw->mu_b : nul, nul, 0, d.A, 16);
+    add_vec(pk, aw ? aw->bound : nul, nul, 0, d.A, 16);
+    L.ep_floats = 32;
+    lp.layers.push_back(L);
+  }
+  // ---- state-action embed: [s | a] -> Linear -> ELU
+  {
+    LLayerH L;
+    L.type = LE_BIAS_ELU; L.dbuf = 1; L.out = BUF_X; L.nseg = 2;
+    tiles(Dp, 256, 16, L.NT, L.n);
+    L.kc = kc_for(L.n);
+    L.w_off = pk.data_bytes;
+    const int Ke = d.S_in + d.A;
+    for (int j = 0; j < L.NT; ++j) {
+      const size_t t0 = pk.data_bytes;
+      RowSpec rs(j * L.n, d.D - j * L.n, L.n);
+      L.seg[0] = {BUF_S, Sip / 16, L.n, 0, 0, 1, 0u};
+      l_add_pack(lp, rs, w ? w->embed_w : nul, Ke, 0, d.S_in, Sip);
+      L.seg[1] = {BUF_A, 1, L.n, 0, 0, 0, (uint32_t)(pk.data_bytes - t0)};
+      l_add_pack(lp, rs, w ? w->embed_w : nul, Ke, d.S_in, d.A, 16);
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+      const uint32_t at = add_vec(pk, w ? w->embed_b : nul, nul, j * L.n, std::max(0, std::min(L.n, d.D - j * L.n)), L.n);
+      if (j == 0) L.ep_off = at;
+    }
+    L.ep_floats = (uint32_t)L.n;
+    lp.layers.push_back(L);
+  }
+  // ---- GRU, 64 state columns per work item: TMEM [i_n | r | z | h_n]
+  {
+    LLayerH L;
+    constexpr int cw = kGruTile;
+    L.type = LE_GRU; L.dbuf = 1; L.out = BUF_H1; L.nseg = 2; L.n = 4 * cw;
+    L.NT = (Dp + cw - 1) / cw;
+    L.kc = kc_for(3 * cw);
+    L.w_off = pk.data_bytes;
+    for (int j = 0; j < L.NT; ++j) {
+      const size_t t0 = pk.data_bytes;
+      const int c0 = j * cw, v = std::max(0, std::min(cw, d.D - c0));
+      RowSpec rx;   // W_ih rows [n | r | z] of the tile's state columns
+      rx.add(2 * d.D + c0, v, cw); rx.add(c0, v, cw); rx.add(d.D + c0, v, cw);
+      L.seg[0] = {BUF_X, Dp / 16, 3 * cw, 0, 0, 1, 0u};
+      l_add_pack(lp, rx, w ? w->w_ih : nul, d.D, 0, d.D, Dp);
+      RowSpec rh;   // W_hh rows [r | z | n]
+      rh.add(c0, v, cw); rh.add(d.D + c0, v, cw); rh.add(2 * d.D + c0, v, cw);
+      L.seg[1] = {BUF_H0, Dp / 16, 3 * cw, cw, 2 * cw, 0, (uint32_t)(pk.data_bytes - t0)};
+      l_add_pack(lp, rh, w ? w->w_hh : nul, d.D, 0, d.D, Dp);
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+      const uint32_t at = add_vec(pk, w ? w->b_ih : nul, w ? w->b_hh : nul, c0, v, cw);       // b_r
+      add_vec(pk, w ? w->b_ih : nul, w ? w->b_hh : nul, d.D + c0, v, cw);                    // b_z
+      add_vec(pk, w ? w->b_ih : nul, nul, 2 * d.D + c0, v, cw);                              // b_in
+      add_vec(pk, w ? w->b_hh : nul, nul, 2 * d.D + c0, v, cw);                              // b_hn
+      if (j == 0) L.ep_off = at;
+    }
+    L.ep_floats = 4 * cw;
+    lp.layers.push_back(L);
+  }
+  // ---- prior hidden: h' -> Linear -> ELU
+  {
+    LLayerH L;
+    L.type = LE_BIAS_ELU; L.dbuf = 1; L.out = BUF_HID; L.nseg = 1;
+    tiles(Hdp, 256, 16, L.NT, L.n);
+    L.kc = kc_for(L.n);
+    L.w_off = pk.data_bytes;
+    for (int j = 0; j < L.NT; ++j) {
+      const size_t t0 = pk.data_bytes;
+      L.seg[0] = {BUF_H1, Dp / 16, L.n, 0, 0, 1, 0u};
+      l_add_pack(lp, RowSpec(j * L.n, d.Hd - j * L.n, L.n), w ? w->prior0_w : nul, d.D, 0, d.D, Dp);
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+      const uint32_t at = add_vec(pk, w ? w->prior0_b : nul, nul, j * L.n, std::max(0, std::min(L.n, d.Hd - j * L.n)), L.n);
+      if (j == 0) L.ep_off = at;
+    }
+    L.ep_floats = (uint32_t)L.n;
+    lp.layers.push_back(L);
+  }
+  // ---- prior head + sample
+  {
+    LLayerH L;
+    L.dbuf = 1; L.out = BUF_S; L.nseg = 1;
+    L.w_off = pk.data_bytes;
+    if (disc) {
+      L.type = LE_SAMPLE_DISC;
+      tiles(ceil_to(d.P, 32), 256, 32, L.NT, L.n);
+      for (int j = 0; j < L.NT; ++j) {
+        const size_t t0 = pk.data_bytes;
+        L.seg[0] = {BUF_HID, Hdp / 16, L.n, 0, 0, 1, 0u};
+        l_add_pack(lp, RowSpec(j * L.n, d.P - j * L.n, L.n), w ? w->prior2_w : nul, d.Hd, 0, d.Hd, Hdp);
+        L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+        const uint32_t at = add_vec(pk, w ? w->prior2_b : nul, nul, j * L.n, std::max(0, std::min(L.n, d.P - j * L.n)), L.n);
+        if (j == 0) L.ep_off = at;
+      }
+      L.ep_floats = (uint32_t)L.n;
+    } else {
+      L.type = LE_SAMPLE_CONT; L.NT = 1; L.n = 2 * Sp;
+      RowSpec rs;
+      rs.add(0, d.S, Sp); rs.add(d.S, d.S, Sp);
+      L.seg[0] = {BUF_HID, Hdp / 16, L.n, 0, 0, 1, 0u};
+      l_add_pack(lp, rs, w ? w->prior2_w : nul, d.Hd, 0, d.Hd, Hdp);
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - L.w_off);
+      L.ep_off = add_vec(pk, w ? w->prior2_b : nul, nul, 0, d.S, Sp);
+      add_vec(pk, w ? w->prior2_b : nul, nul, d.S, d.S, Sp);
+      L.ep_floats = 2u * Sp;
+    }
+    L.kc = kc_for(L.n);
+    lp.layers.push_back(L);
+  }
+  for (const LLayerH& L : lp.layers) {
+    if (L.ep_floats * 4 > kLParamBytes || (L.ep_floats & 3)) return lp;
+    for (int s = 0; s < L.nseg; ++s)
+      if ((uint32_t)L.kc * (4096u + (uint32_t)L.seg[s].n * 32u) > kLSlotBytes) return lp;
+  }
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  pk.off_stage_tab = 256;
+  pk.off_job_tab = 512;
+  pk.off_packops = 768;
+  pk.off_eparams = al(pk.off_packops + pk.pack_ops.size() * sizeof(PackOp) + pk.vec_ops.size() * sizeof(VecOp));
+  pk.off_data = al(pk.off_eparams + pk.eparams_floats * sizeof(float));
+  pk.total_bytes = al(pk.off_data + pk.data_bytes);
+  pk.ok = true;
+  lp.ok = true;
+  return lp;
+}
+
+bool tcl_supported(const Dims& d) { return tcl_make_plan(d, nullptr, nullptr).ok; }
+size_t tcl_packed_bytes(const Dims& d) {
+  LPlan lp = tcl_make_plan(d, nullptr, nullptr);
+  return lp.ok ? lp.pk.total_bytes : 0;
+}
+static size_t buf_bytes(const LPlan& lp, int buf, int MT) { return (size_t)MT * (lp.width[buf] / 8) * kLTileChunk; }
+size_t tcl_workspace_bytes(const Dims& d) {
+  LPlan lp = tcl_make_plan(d, nullptr, nullptr);
+  if (!lp.ok) return 0;
+  const int MT = (d.B + 127) / 128;
+  size_t n = 1024;
+  for (int b = 0; b < BUF_COUNT; ++b) n += buf_bytes(lp, b, MT) + 1024;
+  return n;
+}
+int tcl_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw, void* packed,
+                     cudaStream_t st) {
+  LPlan lp = tcl_make_plan(d, w, aw);
+  WMRL_REQUIRE(lp.ok, "pack_weights: shape not supported by the layer-wise tcgen05 path");
+  return tc_pack_plan(lp.pk, (uint8_t*)packed, st);
+}
+
+int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, const float* stoch0, const float* noise,
+                    float* deter_seq, float* stoch_seq, float* dist_a, float* dist_b, float* actions, int32_t* idx,
+                    void* ws, cudaStream_t st) {
+  LPlan lp = tcl_make_plan(d, nullptr, nullptr);
+  WMRL_REQUIRE(lp.ok, "imagine_fwd: shape not supported by the layer-wise tcgen05 path");
+  static std::mutex mu;
+  static bool attr_set[64] = {false};
+  int dev = 0, nsm = 148;
+  WMRL_CUDA_OK(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+      WMRL_CUDA_OK(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmemBytes));
+      attr_set[dev] = true;
+    }
+  }
+  static int sm_cached[64] = {0};
+  if (dev >= 0 && dev < 64) {
+    if (!sm_cached[dev]) WMRL_CUDA_OK(cudaDeviceGetAttribute(&sm_cached[dev], cudaDevAttrMultiProcessorCount, dev));
+    nsm = sm_cached[dev];
+  }
+  const int MT = (d.B + 127) / 128;
+  const uint8_t* img = (const uint8_t*)packed;
+  const uint8_t* data = img + lp.pk.off_data;
+  const float* ep = (const float*)(img + lp.pk.off_eparams);
+  uint8_t* bufs[BUF_COUNT];
+  {
+    uint8_t* p = (uint8_t*)(((uintptr_t)ws + 1023) / 1024 * 1024);
+    for (int b = 0; b < BUF_COUNT; ++b) { bufs[b] = p; p += (buf_bytes(lp, b, MT) + 1023) / 1024 * 1024; }
+  }
+  tcl_init_kernel<<<dim3(8, MT), 256, 0, st>>>(deter0, stoch0, deter_seq, stoch_seq, bufs[BUF_H0], bufs[BUF_S], d.B, d.T,
+                                               d.D, d.S_in, lp.Dp, lp.Sip);
+  WMRL_CUDA_OK(cudaGetLastError());
+  for (int t = 0; t < d.T; ++t) {
+    const int hcur = (t & 1) ? BUF_H1 : BUF_H0, hnext = (t & 1) ? BUF_H0 : BUF_H1;
+    for (const LLayerH& L : lp.layers) {
+      LayerArgs a{};
+      a.nseg = L.nseg;
+      for (int s = 0; s < L.nseg; ++s) {
+        int buf = L.seg[s].buf;
+        if (buf == BUF_H0) buf = hcur; else if (buf == BUF_H1) buf = hnext;
+        a.seg[s].a = bufs[buf];
+        a.seg[s].a_tile_bytes = (uint32_t)(lp.width[buf] / 8) * kLTileChunk;
+        a.seg[s].w_off = L.seg[s].w_off;
+        a.seg[s].k16 = (uint16_t)L.seg[s].k16; a.seg[s].n = (uint16_t)L.seg[s].n;
+        a.seg[s].tmem_col = (uint16_t)L.seg[s].tmem_col; a.seg[s].split = (uint16_t)L.seg[s].split;
+        a.seg[s].fresh = (uint16_t)L.seg[s].fresh;
+      }
+      a.w = data + L.w_off; a.w_tile_bytes = L.w_tile_bytes;
+      a.ep = ep + L.ep_off; a.ep_floats = L.ep_floats;
+      a.kc = L.kc; a.dbuf = L.dbuf; a.type = L.type; a.n = L.n; a.NT = L.NT; a.MT = MT;
+      a.B = d.B; a.H = d.T; a.t = t; a.D = d.D; a.S = d.S; a.C = d.C; a.A = d.A; a.Sp = lp.Sp; a.Dp = lp.Dp;
+      a.inv_action_scale = 1.f / d.action_scale;
+      int ob = L.out;
+      if (ob == BUF_H1) ob = hnext;
+      a.out = bufs[ob]; a.out_tile_bytes = (uint32_t)(lp.width[ob] / 8) * kLTileChunk; a.out_cols = lp.width[ob];
+      a.deter_seq = deter_seq; a.stoch_seq = stoch_seq; a.dist_a = dist_a; a.dist_b = dist_b; a.actions = actions;
+      a.idx = idx; a.noise = noise;
+      const int items = MT * L.NT;
+      tc_layer_kernel<<<std::min(items, nsm), kLThreads, kLSmemBytes, st>>>(a);
+      WMRL_CUDA_OK(cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+}  // namespace wmrl
