@@ -1,0 +1,55 @@
+"""Time the bf16 imagine forward of the layer-wise tcgen05 chain (csrc/tc_layer.cu) at the BASELINE discrete
+configs and print ms / latent-steps/s / TFLOP/s (algorithmic FLOPs of SURVEY 8d).  `python tools/layer_bench.py`."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "world-model-rl_b200"), os.path.join(ROOT, "tests")]
+import helpers_gpu as HG  # noqa: E402
+
+
+def flops_fwd(D, S_in, P, Hd, A, Ha, La):
+    F = D + S_in
+    actor = F * Ha + (La - 1) * Ha * Ha + Ha * A
+    dyn = (S_in + A) * D + 6 * D * D + D * Hd + Hd * P
+    return 2 * (actor + dyn)
+
+
+def run(name, variant, D, S, C, Hd, A, Ha, La, B, H, iters=5, precision="bf16"):
+    rssm, actor = HG.build_modules(variant, D, S, C, Hd, 64, A, Ha, La, precision=precision)
+    d0, s0, nz = HG.synth_inputs(variant, B, H, D, S, C)
+    init = HG.init_state(rssm, d0, s0)
+    nz = nz.cuda()
+    with torch.no_grad():
+        for _ in range(2):
+            rssm.imagine_rollout(init, actor, H, noise=nz)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            rssm.imagine_rollout(init, actor, H, noise=nz)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    S_in = S * C if variant == "discrete" else S
+    P = S_in if variant == "discrete" else 2 * S
+    fl = flops_fwd(D, S_in, P, Hd, A, Ha, La)
+    out = {"case": name, "precision": precision, "ms": round(ms, 3), "latent_steps_per_s": B * H / ms * 1e3,
+           "tflops": fl * B * H / ms / 1e9, "flops_per_latent_step": fl}
+    print(json.dumps(out), flush=True)
+    return out
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c2", "c5", "c2f32"]
+    if "c2" in which:
+        run("configs[1] discrete D600 32x32 2500x15", "discrete", 600, 32, 32, 600, 6, 512, 3, 2500, 15, iters=20)
+    if "c2f32" in which:
+        run("configs[1] discrete D600 32x32 2500x15", "discrete", 600, 32, 32, 600, 6, 512, 3, 2500, 15, iters=10, precision="fp32")
+    if "c5" in which:
+        run("configs[4] discrete D1024 32x32 8192x64 (one GPU's shard)", "discrete", 1024, 32, 32, 1024, 6, 512, 3, 8192, 64, iters=3)
+    if "c4" in which:   # continuous bench shape; WMRL_BF16_PATH=layer forces the chain
+        run("configs[3] continuous 65536x15", "continuous", 200, 30, 1, 200, 6, 512, 3, 65536, 15, iters=5)

@@ -36,14 +36,17 @@ int tc_pack_plan(const Plan& pl, uint8_t* base, cudaStream_t st);
 
 constexpr int kLEpiWarps = 16, kLEpiThreads = kLEpiWarps * 32, kLThreads = kLEpiThreads + 64;
 constexpr int kLProducerWarp = kLEpiWarps, kLMmaWarp = kLEpiWarps + 1;
-constexpr uint32_t kLSlotBytes = 49152;
+constexpr uint32_t kLSlotBytes = 40960;
 constexpr int kLSlots = 4;
+constexpr uint32_t kLStageBytes = 32768;    // per epilogue warp 2 KB (16 rows x 128 B): transposes for coalesced global I/O
 constexpr uint32_t kLTileChunk = 2048;      // bytes of one 8-column chunk of a 128-row panel tile
 constexpr uint32_t kLParamBytes = 8192;     // per work item epilogue parameters (bias / LayerNorm affine / gate biases)
 constexpr uint32_t kLScratchBytes = 4096;   // LayerNorm partial statistics: [q][row] x (sum, sq)
 constexpr uint32_t kLBarBytes = 256;
-constexpr uint32_t kLSmemBytes = kLSlots * kLSlotBytes + kLParamBytes + kLScratchBytes + kLBarBytes;
+constexpr uint32_t kLSmemBytes = kLSlots * kLSlotBytes + kLStageBytes + kLParamBytes + kLScratchBytes + kLBarBytes;
 constexpr int kGruTile = 64;                // state columns per GRU work item (4 x 64 = 256 TMEM columns)
+
+static_assert((kLSlots & (kLSlots - 1)) == 0, "kLSlots must be a power of two");
 
 enum : int { LE_LN_ELU = 1, LE_BIAS_ELU, LE_MU, LE_GRU, LE_SAMPLE_DISC, LE_SAMPLE_CONT };
 
@@ -80,7 +83,16 @@ struct LayerArgs {
   float *deter_seq, *stoch_seq, *dist_a, *dist_b, *actions;
   int32_t* idx;
   const float* noise;
+  long long* trace;        // optional (WMRL_FLAG_TRACE): SM clocks of CTA 0, 16 slots per launch (tools/trace_layer.py)
 };
+
+// tight spin for the single-lane producer / MMA loops (no printf call in the loop body: its argument set-up bloats the
+// issuing lane's instruction stream); a protocol bug still traps
+__device__ __forceinline__ void mbar_wait_backoff_free(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++spins > (1u << 26)) __trap();
+}
 
 // --------------------------------------------------------------------------
 // epilogues.  Thread -> (row = TMEM lane, q = column split among the 4 warps of a lane quarter)
@@ -89,13 +101,16 @@ struct LCtx {
   const LayerArgs* p;
   uint32_t prm;        // smem address of this work item's epilogue parameters
   uint32_t scratch;    // smem address of the LayerNorm scratch
+  uint32_t stage;      // smem address of this warp's 2 KB transpose staging
   uint32_t tmem_lane;  // accumulator base of this work item with the warp's lane quarter folded in
   int row, q, quarter, lane;
   int mt, nt;
   long long b;         // global row
   bool valid;
   uint8_t* out_row;    // destination panel of this row tile, offset by row * 16
+  long long* probe;    // timeline probes of the first work item (thread 0 of CTA 0 when tracing), else null
 };
+#define LPROBE(c, k) do { if ((c).probe) (c).probe[k] = clock64(); } while (0)
 
 __device__ __forceinline__ float4 lds4(uint32_t addr) {
   float4 v;
@@ -307,90 +322,143 @@ __device__ __forceinline__ void lepi_sample_cont(const LCtx& c) {
 // S classes; warp q owns the 32-column blocks q, q+4, ...; a thread holds all classes of its groups in registers.
 //   p = Categorical(logits).probs = softmax(logits - logsumexp(logits));  idx = first argmax(p / q), q ~ Exp(1)
 // (torch.multinomial's single-draw rule); forward value of the straight-through sample is exactly one_hot(idx).
+// Global I/O goes through a per-warp 2 KB staging transpose (16 rows x 128 B, 16-byte chunks XOR-swizzled by the row)
+// so that every warp-level LDG / STG touches 4 rows x 128 contiguous bytes instead of 32 different lines: the
+// row-per-thread pattern cost 39K cycles per work item in LSU wavefronts alone (tools/trace_layer.py).
+__device__ __forceinline__ uint32_t stage_addr(uint32_t base, int r16, int chunk) {
+  return base + (uint32_t)r16 * 128u + (uint32_t)((chunk ^ (r16 & 7)) * 16);
+}
 template <int S>
 __device__ __forceinline__ void lepi_sample_disc(const LCtx& c) {
   const LayerArgs& p = *c.p;
   const long long T1 = p.H + 1;
   const int P = p.C * p.S;
+  const int lane = c.lane;
+  const long long b0 = c.b - lane;             // global row of lane 0 of this warp
+  const int sub = lane >> 3, chunk = lane & 7;  // transposed role: row (4 * i + sub) of a 16-row half, 16-byte chunk
   for (int blk = c.q; blk < p.n / 32; blk += 4) {
     const int col = c.nt * p.n + blk * 32;     // first logit column of this block
     if (col >= p.out_cols) break;
-    float l[32], qv[32];
+    float l[32];
+    LPROBE(c, 0);
     tmem_ld32(c.tmem_lane + blk * 32, l);
-    const float* qrow = p.noise + ((long long)p.t * p.B + c.b) * P + col;
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      if (c.valid && col + i < P) {
-        const float4 q4 = *reinterpret_cast<const float4*>(qrow + i);
-        qv[i] = q4.x; qv[i + 1] = q4.y; qv[i + 2] = q4.z; qv[i + 3] = q4.w;
-      } else {
-        qv[i] = qv[i + 1] = qv[i + 2] = qv[i + 3] = 1.f;
-      }
-    }
     tmem_ld_wait();
-    const bool store = c.valid && col < P;
-    float* lo = p.dist_a + (c.b * T1 + p.t + 1) * P + col;
-    float* so = p.stoch_seq + (c.b * T1 + p.t + 1) * P + col;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 b4 = lds4(c.prm + (blk * 32 + i) * 4);
       l[i] += b4.x; l[i + 1] += b4.y; l[i + 2] += b4.z; l[i + 3] += b4.w;
-      if (store && col + i < P) *reinterpret_cast<float4*>(lo + i) = make_float4(l[i], l[i + 1], l[i + 2], l[i + 3]);
     }
+    LPROBE(c, 1);
+    // ---- raw logits out (state/discrete.py:20-37 stores them un-normalised): staging -> coalesced stores
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if ((lane >> 4) == half) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_addr(c.stage, lane & 15, k)), "f"(l[4 * k]),
+                       "f"(l[4 * k + 1]), "f"(l[4 * k + 2]), "f"(l[4 * k + 3]) : "memory");
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r16 = i * 4 + sub;
+        const long long br = b0 + half * 16 + r16;
+        const float4 v = lds4(stage_addr(c.stage, r16, chunk));
+        if (br < p.B && col + chunk * 4 < P)
+          *reinterpret_cast<float4*>(p.dist_a + (br * T1 + p.t + 1) * P + col + chunk * 4) = v;
+      }
+      __syncwarp();
+    }
+    LPROBE(c, 2);
+    // ---- q ~ Exp(1) of this block: coalesced loads -> staging -> the row's owner
+    float qv[32];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r16 = i * 4 + sub;
+        const long long br = b0 + half * 16 + r16;
+        float4 q4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (br < p.B && col + chunk * 4 < P)
+          q4 = *reinterpret_cast<const float4*>(p.noise + ((long long)p.t * p.B + br) * P + col + chunk * 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_addr(c.stage, r16, chunk)), "f"(q4.x), "f"(q4.y),
+                     "f"(q4.z), "f"(q4.w) : "memory");
+      }
+      __syncwarp();
+      if ((lane >> 4) == half) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 v = lds4(stage_addr(c.stage, lane & 15, k));
+          qv[4 * k] = v.x; qv[4 * k + 1] = v.y; qv[4 * k + 2] = v.z; qv[4 * k + 3] = v.w;
+        }
+      }
+      __syncwarp();
+    }
+    LPROBE(c, 3);
+    // ---- per group: p = softmax(l - logsumexp(l)) = exp(l - max) / sum; idx = first argmax(p / q).  The common
+    // factor 1 / sum does not move the argmax and p_j / q_j > p_b / q_b <=> e_j q_b > e_b q_j (all positive), so the
+    // draw costs one ex2 per class and no divisions.
+    uint32_t packed = 0;   // this row's draws, S bits per group
     int bi[32 / S];
 #pragma unroll
     for (int g = 0; g < 32 / S; ++g) {
       float mx = l[g * S];
 #pragma unroll
       for (int j = 1; j < S; ++j) mx = fmaxf(mx, l[g * S + j]);
-      float se = 0.f;
-#pragma unroll
-      for (int j = 0; j < S; ++j) se += __expf(l[g * S + j] - mx);
-      const float lse = mx + __logf(se);
-      const float mx2 = mx - lse;            // max of the normalised logits
-      float se2 = 0.f;
-#pragma unroll
-      for (int j = 0; j < S; ++j) { l[g * S + j] = __expf((l[g * S + j] - lse) - mx2); se2 += l[g * S + j]; }
-      const float inv = 1.f / se2;
-      float best = -1.f;
+      const float mxs = mx * 1.4426950408889634f;
+      float eb = ex2_fast(fmaf(l[g * S], 1.4426950408889634f, -mxs)), qb = qv[g * S];
       int b = 0;
 #pragma unroll
-      for (int j = 0; j < S; ++j) {
-        const float v = __fdividef(l[g * S + j] * inv, qv[g * S + j]);
-        if (v > best) { best = v; b = j; }
+      for (int j = 1; j < S; ++j) {
+        const float e = ex2_fast(fmaf(l[g * S + j], 1.4426950408889634f, -mxs));
+        const bool better = e * qb > eb * qv[g * S + j];
+        eb = better ? e : eb;
+        qb = better ? qv[g * S + j] : qb;
+        b = better ? j : b;
       }
       bi[g] = b;
+      packed |= (uint32_t)b << ((g * S) & 31);
       const int grp = (col / S) + g;
       if (c.valid && grp < p.C && p.idx) p.idx[(c.b * p.H + p.t) * p.C + grp] = b;
     }
-    // forward value of the straight-through sample: exactly one_hot(idx) -> fp32 sequence + bf16 panel
+    LPROBE(c, 4);
+    // ---- forward value of the straight-through sample, exactly one_hot(idx): fp32 sequence (coalesced, the draws
+    // travel by shuffle) + bf16 panel chunk of the row's owner
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + sub;
+      const uint32_t pk = __shfl_sync(0xffffffffu, packed, r);
+      const int g = (chunk * 4) / S;
+      const int v = (int)((S >= 32) ? pk : ((pk >> ((g * S) & 31)) & ((1u << (S & 31)) - 1u)));
+      const int e0 = (chunk * 4) % S;
+      const long long br = b0 + r;
+      if (br < p.B && col + chunk * 4 < P)
+        *reinterpret_cast<float4*>(p.stoch_seq + (br * T1 + p.t + 1) * P + col + chunk * 4) =
+            make_float4(e0 == v ? 1.f : 0.f, e0 + 1 == v ? 1.f : 0.f, e0 + 2 == v ? 1.f : 0.f, e0 + 3 == v ? 1.f : 0.f);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float oh[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) oh[e] = (((k * 8 + e) % S) == bi[(k * 8 + e) / S]) ? 1.f : 0.f;
-      if (col + k * 8 < P) {
-        if (store) {
-          *reinterpret_cast<float4*>(so + k * 8) = make_float4(oh[0], oh[1], oh[2], oh[3]);
-          *reinterpret_cast<float4*>(so + k * 8 + 4) = make_float4(oh[4], oh[5], oh[6], oh[7]);
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) oh[e] = 0.f;
-      }
+      for (int e = 0; e < 8; ++e) oh[e] = (col + k * 8 < P && ((k * 8 + e) % S) == bi[(k * 8 + e) / S]) ? 1.f : 0.f;
       if (col + k * 8 < p.out_cols) st_chunk_g(c.out_row + (size_t)(col / 8 + k) * kLTileChunk, oh);
     }
+    LPROBE(c, 5);
   }
 }
 
 // --------------------------------------------------------------------------
 // the kernel
 // --------------------------------------------------------------------------
+// kType: the fused epilogue (LE_*), kS: classes per categorical group (LE_SAMPLE_DISC) - one instantiation each, so
+// that no epilogue pays for another's registers (96 per thread at 576 threads)
+template <int kType, int kS>
 __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_constant__ LayerArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t ring = smem_base;
-  const uint32_t prm = smem_base + kLSlots * kLSlotBytes;
+  const uint32_t stage_base = smem_base + kLSlots * kLSlotBytes;
+  const uint32_t prm = stage_base + kLStageBytes;
   const uint32_t scratch = prm + kLParamBytes;
   const uint32_t bars = scratch + kLScratchBytes;
   auto full_bar = [&](uint32_t s) { return bars + 8u * s; };
@@ -411,12 +479,22 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the previous layer's
+  // tail; from here on this grid reads what that layer wrote.  The next layer may start its own set-up right away
+  // (every grid of the chain is a single wave, so no CTA of this grid is still waiting for an SM).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t w_in_slot = (uint32_t)p.kc * 4096u;   // the weight K-slice follows the activation K-slice in a slot
+  const bool tr = p.trace != nullptr && blockIdx.x == 0;
+#define LTRACE(k) do { if (tr) p.trace[k] = clock64(); } while (0)
+  if (tr && threadIdx.x == 0) p.trace[0] = clock64();
 
   if (warp == kLProducerWarp) {
-    if (lane == 0) {
-      uint32_t slot = 0, phase = 0;
+    // kLSlots issuing lanes: lane j owns ring slot j (stage numbers j, j + 4, ...).  One lane sustains only one bulk
+    // copy per ~415 cycles whatever its size; four lanes keep the ring fed.
+    if (lane < kLSlots) {
+      uint32_t sidx = 0, phase = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int mt = item / p.NT, nt = item % p.NT;
         const uint8_t* wt = p.w + (size_t)nt * p.w_tile_bytes;
@@ -424,16 +502,19 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
           const LSeg& s = p.seg[sg];
           const uint8_t* a = s.a + (size_t)mt * s.a_tile_bytes;
           const uint8_t* w = wt + s.w_off;
-          for (int k0 = 0; k0 < (int)s.k16; k0 += p.kc) {
+          for (int k0 = 0; k0 < (int)s.k16; k0 += p.kc, ++sidx) {
+            if ((int)(sidx & (kLSlots - 1)) != lane) continue;
             const uint32_t nk = (uint32_t)min(p.kc, (int)s.k16 - k0);
             const uint32_t ab = nk * 4096u, wb = nk * (uint32_t)s.n * 32u;
-            mbar_wait(empty_bar(slot), phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(slot), ab + wb);
-            bulk_g2s(ring + slot * kLSlotBytes, a + (size_t)k0 * 4096u, ab, full_bar(slot));
-            bulk_g2s(ring + slot * kLSlotBytes + w_in_slot, w + (size_t)k0 * s.n * 32u, wb, full_bar(slot));
-            if (++slot == (uint32_t)kLSlots) { slot = 0; phase ^= 1u; }
+            mbar_wait_backoff_free(empty_bar(lane), phase ^ 1u);
+            if (sidx == 0) LTRACE(1);
+            mbar_arrive_expect_tx(full_bar(lane), ab + wb);
+            bulk_g2s(ring + lane * kLSlotBytes, a + (size_t)k0 * 4096u, ab, full_bar(lane));
+            bulk_g2s(ring + lane * kLSlotBytes + w_in_slot, w + (size_t)k0 * s.n * 32u, wb, full_bar(lane));
+            phase ^= 1u;
           }
         }
+        if (item == (int)blockIdx.x && lane == 0) LTRACE(2);    // lane 0's copies of the first work item issued
       }
     }
   } else if (warp == kLMmaWarp) {
@@ -443,33 +524,52 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
         const uint32_t ab = p.dbuf ? (it & 1u) : 0u;
         const uint32_t use = p.dbuf ? (it >> 1) : it;      // how many times this accumulator buffer was used before
-        if (use > 0) { mbar_wait(acce_bar(ab), (use - 1u) & 1u); tc_fence_after(); }
+        if (use > 0) { mbar_wait_backoff_free(acce_bar(ab), (use - 1u) & 1u); tc_fence_after(); }
         const uint32_t tm0 = tmem_base + ab * 256u;
         for (int sg = 0; sg < p.nseg; ++sg) {
+          // everything that does not change inside the K loop is computed here: the issuing lane's own instruction
+          // stream is the critical path (~4 cycles of issue latency per dependent integer instruction)
           const LSeg& s = p.seg[sg];
           const uint32_t n = s.n;
-          for (int k0 = 0; k0 < (int)s.k16; k0 += p.kc) {
-            const int nk = min(p.kc, (int)s.k16 - k0);
-            mbar_wait(full_bar(slot), phase);
+          const uint32_t n_a = n > 256u ? 256u : n, n_b = n - n_a;          // pieces of <= 256 columns
+          const uint32_t id_a = make_idesc_bf16(128, n_a), id_b = make_idesc_bf16(128, n_b ? n_b : 16u);
+          const uint32_t tm_a = tm0 + s.tmem_col, tm_b = tm_a + 256u;
+          const uint32_t bstep = n * 2u;                                    // n * 32 bytes >> 4
+          const uint32_t blbo = n << 16;                                    // LBO = n * 16 bytes
+          const int k16 = (int)s.k16, kc = p.kc;
+          for (int k0 = 0; k0 < k16; k0 += kc) {
+            const int nk = min(kc, k16 - k0);
+            mbar_wait_backoff_free(full_bar(slot), phase);
             tc_fence_after();
-            const uint32_t a_addr = ring + slot * kLSlotBytes, b_addr = a_addr + w_in_slot;
-            for (int i = 0; i < nk; ++i) {
-              const bool first = (k0 == 0 && i == 0);
-              const uint32_t alo = (((a_addr + (uint32_t)i * 4096u) >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);
-              const uint32_t bk = b_addr + (uint32_t)i * n * 32u;
-              if (first && s.split) {
-                const uint32_t b0 = ((bk >> 4) & 0x3FFFu) | (n << 16);
-                mma_bf16_lohi(tm0 + s.tmem_col, alo, kDescHi, b0, kDescHi, make_idesc_bf16(128, s.split), 1u);
-                const uint32_t b1 = (((bk + (uint32_t)s.split * 16u) >> 4) & 0x3FFFu) | (n << 16);
-                mma_bf16_lohi(tm0 + s.tmem_col + s.split, alo, kDescHi, b1, kDescHi,
+            if (it == 0 && sg == 0 && k0 == 0) LTRACE(3);    // first stage landed
+            const uint32_t a_addr = ring + slot * kLSlotBytes;
+            uint32_t alo = ((a_addr >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);
+            uint32_t blo = (((a_addr + w_in_slot) >> 4) & 0x3FFFu) | blbo;
+            int i = 0;
+            if (k0 == 0) {   // first K step of the segment: fresh / split accumulate rules
+              if (s.split) {
+                mma_bf16_lohi(tm_a, alo, kDescHi, blo, kDescHi, make_idesc_bf16(128, s.split), 1u);
+                mma_bf16_lohi(tm_a + s.split, alo, kDescHi, blo + (uint32_t)s.split, kDescHi,
                               make_idesc_bf16(128, n - s.split), 0u);
               } else {
-                const uint32_t acc = (first && s.fresh) ? 0u : 1u;
-                for (uint32_t n0 = 0; n0 < n; n0 += 256u) {
-                  const uint32_t nn = min(256u, n - n0);
-                  const uint32_t b0 = (((bk + n0 * 16u) >> 4) & 0x3FFFu) | (n << 16);   // LBO = n * 16 B
-                  mma_bf16_lohi(tm0 + s.tmem_col + n0, alo, kDescHi, b0, kDescHi, make_idesc_bf16(128, nn), acc);
-                }
+                const uint32_t acc = s.fresh ? 0u : 1u;
+                mma_bf16_lohi(tm_a, alo, kDescHi, blo, kDescHi, id_a, acc);
+                if (n_b) mma_bf16_lohi(tm_b, alo, kDescHi, blo + 256u, kDescHi, id_b, acc);
+              }
+              alo += 256u; blo += bstep; i = 1;
+            }
+            if (n_b) {
+#pragma unroll 2
+              for (; i < nk; ++i) {
+                mma_bf16_lohi(tm_a, alo, kDescHi, blo, kDescHi, id_a, 1u);
+                mma_bf16_lohi(tm_b, alo, kDescHi, blo + 256u, kDescHi, id_b, 1u);
+                alo += 256u; blo += bstep;
+              }
+            } else {
+#pragma unroll 4
+              for (; i < nk; ++i) {
+                mma_bf16_lohi(tm_a, alo, kDescHi, blo, kDescHi, id_a, 1u);
+                alo += 256u; blo += bstep;
               }
             }
             tc_commit(empty_bar(slot));
@@ -477,13 +577,16 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
           }
         }
         tc_commit(accf_bar(ab));
+        if (it == 0) LTRACE(4);                      // first work item's MMAs issued
       }
+      LTRACE(5);                                     // all MMAs issued
     }
   } else {
     LCtx c;
     c.p = &p;
     c.prm = prm;
     c.scratch = scratch;
+    c.stage = stage_base + (uint32_t)warp * 2048u;
     c.quarter = warp & 3;
     c.q = warp >> 2;
     c.lane = lane;
@@ -497,6 +600,7 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
       c.valid = c.b < p.B;
       c.tmem_lane = tmem_base + ab * 256u + ((uint32_t)(c.quarter * 32) << 16);
       c.out_row = p.out + (size_t)c.mt * p.out_tile_bytes + (size_t)c.row * 16;
+      c.probe = (tr && it == 0 && threadIdx.x == 0) ? p.trace + 16 : nullptr;
       // this work item's epilogue parameters -> shared memory (the previous item's readers are done)
       l_epi_sync();
       {
@@ -508,30 +612,50 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
       }
       l_epi_sync();
       LGruPre gpf;
-      if (p.type == LE_GRU) lgru_prefetch(c, gpf);
+      if (kType == LE_GRU) lgru_prefetch(c, gpf);
+      if (kType == LE_SAMPLE_DISC && c.valid) {
+        // the Exp(1) draws of this row are read once, from HBM: pull them into L2 while the MMAs run
+        const int P = p.C * p.S;
+        const float* qrow = p.noise + ((long long)p.t * p.B + c.b) * P + c.nt * p.n;
+        for (int o = c.q * 32; o < p.n && c.nt * p.n + o < P; o += 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(qrow + o));
+      }
+      if (it == 0 && threadIdx.x == 0) LTRACE(6);    // parameters staged, waiting for the accumulator
       mbar_wait_backoff_quiet(accf_bar(ab), use & 1u);
       tc_fence_after();
-      switch (p.type) {
-        case LE_LN_ELU: lepi_ln_elu(c); break;
-        case LE_BIAS_ELU: lepi_bias_elu(c); break;
-        case LE_MU: lepi_mu(c); break;
-        case LE_GRU: lepi_gru(c, gpf); break;
-        case LE_SAMPLE_CONT: lepi_sample_cont(c); break;
-        case LE_SAMPLE_DISC:
-          if (p.S == 32) lepi_sample_disc<32>(c);
-          else if (p.S == 16) lepi_sample_disc<16>(c);
-          else if (p.S == 8) lepi_sample_disc<8>(c);
-          else lepi_sample_disc<4>(c);
-          break;
-      }
+      if (it == 0 && threadIdx.x == 0) LTRACE(7);    // accumulator complete
+      if (kType == LE_LN_ELU) lepi_ln_elu(c);
+      else if (kType == LE_BIAS_ELU) lepi_bias_elu(c);
+      else if (kType == LE_MU) lepi_mu(c);
+      else if (kType == LE_GRU) lepi_gru(c, gpf);
+      else if (kType == LE_SAMPLE_CONT) lepi_sample_cont(c);
+      else lepi_sample_disc<(kS > 0 ? kS : 4)>(c);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce_bar(ab));
+      if (it == 0 && threadIdx.x == 0) LTRACE(8);    // first epilogue done
     }
+    if (threadIdx.x == 0) { LTRACE(9); if (tr) p.trace[10] = (long long)it; }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == kLMmaWarp) tmem_dealloc(tmem_base, 512);
+  if (tr && threadIdx.x == 0) p.trace[11] = clock64();
+#undef LTRACE
+}
+
+typedef void (*LayerKernel)(const LayerArgs);
+static LayerKernel layer_kernel_for(int type, int S) {
+  switch (type) {
+    case LE_LN_ELU: return tc_layer_kernel<LE_LN_ELU, 0>;
+    case LE_BIAS_ELU: return tc_layer_kernel<LE_BIAS_ELU, 0>;
+    case LE_MU: return tc_layer_kernel<LE_MU, 0>;
+    case LE_GRU: return tc_layer_kernel<LE_GRU, 0>;
+    case LE_SAMPLE_CONT: return tc_layer_kernel<LE_SAMPLE_CONT, 0>;
+    default: break;
+  }
+  return S == 32 ? tc_layer_kernel<LE_SAMPLE_DISC, 32> : S == 16 ? tc_layer_kernel<LE_SAMPLE_DISC, 16>
+       : S == 8 ? tc_layer_kernel<LE_SAMPLE_DISC, 8> : tc_layer_kernel<LE_SAMPLE_DISC, 4>;
 }
 
 // start states -> index 0 of the sequence outputs and the bf16 panels (all 128 rows of every tile, zeros past B)
@@ -784,7 +908,7 @@ size_t tcl_workspace_bytes(const Dims& d) {
   LPlan lp = tcl_make_plan(d, nullptr, nullptr);
   if (!lp.ok) return 0;
   const int MT = (d.B + 127) / 128;
-  size_t n = 1024;
+  size_t n = 8192;
   for (int b = 0; b < BUF_COUNT; ++b) n += buf_bytes(lp, b, MT) + 1024;
   return n;
 }
@@ -807,7 +931,12 @@ int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, cons
   {
     std::lock_guard<std::mutex> lk(mu);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-      WMRL_CUDA_OK(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLSmemBytes));
+      for (int ty = LE_LN_ELU; ty <= LE_SAMPLE_CONT; ++ty)
+        for (int S : {4, 8, 16, 32}) {
+          if (ty != LE_SAMPLE_DISC && S != 4) continue;
+          WMRL_CUDA_OK(cudaFuncSetAttribute(layer_kernel_for(ty, S), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)kLSmemBytes));
+        }
       attr_set[dev] = true;
     }
   }
@@ -822,9 +951,10 @@ int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, cons
   const float* ep = (const float*)(img + lp.pk.off_eparams);
   uint8_t* bufs[BUF_COUNT];
   {
-    uint8_t* p = (uint8_t*)(((uintptr_t)ws + 1023) / 1024 * 1024);
+    uint8_t* p = (uint8_t*)(((uintptr_t)ws + 4096 + 1023) / 1024 * 1024);
     for (int b = 0; b < BUF_COUNT; ++b) { bufs[b] = p; p += (buf_bytes(lp, b, MT) + 1023) / 1024 * 1024; }
   }
+  long long* trace_base = (long long*)ws;   // the first 1 KB of the workspace (the panels start 1 KB-aligned after it)
   tcl_init_kernel<<<dim3(8, MT), 256, 0, st>>>(deter0, stoch0, deter_seq, stoch_seq, bufs[BUF_H0], bufs[BUF_S], d.B, d.T,
                                                d.D, d.S_in, lp.Dp, lp.Sip);
   WMRL_CUDA_OK(cudaGetLastError());
@@ -853,9 +983,20 @@ int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, cons
       a.out = bufs[ob]; a.out_tile_bytes = (uint32_t)(lp.width[ob] / 8) * kLTileChunk; a.out_cols = lp.width[ob];
       a.deter_seq = deter_seq; a.stoch_seq = stoch_seq; a.dist_a = dist_a; a.dist_b = dist_b; a.actions = actions;
       a.idx = idx; a.noise = noise;
+      a.trace = nullptr;
+      if ((d.flags & WMRL_FLAG_TRACE) && t == std::min(1, d.T - 1)) a.trace = trace_base + 32 * (&L - &lp.layers[0]);
       const int items = MT * L.NT;
-      tc_layer_kernel<<<std::min(items, nsm), kLThreads, kLSmemBytes, st>>>(a);
-      WMRL_CUDA_OK(cudaGetLastError());
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)std::min(items, nsm));
+      cfg.blockDim = dim3(kLThreads);
+      cfg.dynamicSmemBytes = kLSmemBytes;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, layer_kernel_for(L.type, d.S), a));
     }
   }
   return 0;
