@@ -77,13 +77,18 @@ int wmrl_device_supports_bf16(void) {
 int wmrl_bf16_train_supported(const wmrl_dims* d) {
   if (check_dims(d, 0)) return 0;
   Dims dd(*d);
-  return (bf16_path(dd) == 1 && tc_train_supported(dd)) ? 1 : 0;
+  const int path = bf16_path(dd);
+  return ((path == 1 && tc_train_supported(dd)) || (path == 2 && tcl_train_supported(dd))) ? 1 : 0;
 }
 
 size_t wmrl_saved_bytes(const wmrl_dims* d, int op) {
   if (check_dims(d, op)) return 0;
   Dims dd(*d);
-  if (op == 0 && d->precision == WMRL_BF16 && bf16_path(dd) == 1 && tc_train_supported(dd)) return tc_saved_bytes(dd);
+  if (op == 0 && d->precision == WMRL_BF16) {
+    const int path = bf16_path(dd);
+    if (path == 1 && tc_train_supported(dd)) return tc_saved_bytes(dd);
+    if (path == 2 && tcl_train_supported(dd)) return tcl_saved_bytes(dd);
+  }
   return f32_saved_bytes(dd, op);
 }
 
@@ -145,11 +150,9 @@ int wmrl_imagine_fwd(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_a
     WMRL_REQUIRE(packed, "imagine_fwd: bf16 path needs the packed weight image");
     WMRL_REQUIRE(wmrl_device_supports_bf16(), "imagine_fwd: bf16 path needs an sm_100 device");
     if (path == 2) {
-      WMRL_REQUIRE(!save, "imagine_fwd: the layer-wise bf16 chain has no training path (activation stash + BPTT); "
-                          "record with the fp32 forward");
       WMRL_REQUIRE(dd.variant == WMRL_CONTINUOUS || idx, "imagine_fwd: discrete needs idx");
-      return tcl_imagine_fwd(dd, packed, deter0, stoch0, noise, deter_seq, stoch_seq, dist_a, dist_b, actions, idx, ws,
-                             (cudaStream_t)stream);
+      return tcl_imagine_fwd(dd, packed, deter0, stoch0, noise, deter_seq, stoch_seq, dist_a, dist_b, actions, idx,
+                             save ? saved : nullptr, ws, (cudaStream_t)stream);
     }
     WMRL_REQUIRE(!save || tc_train_supported(dd), "imagine_fwd: this shape has no bf16 training path (activation "
                                                   "stash + BPTT kernel); record with the fp32 forward");
@@ -178,12 +181,18 @@ int wmrl_imagine_bwd(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_a
   if (int r = require_device()) return r;
   if (d->precision == WMRL_BF16) {
     // `saved` is the bf16 activation stash written by wmrl_imagine_fwd(precision BF16, SAVE_FOR_BWD)
-    WMRL_REQUIRE(bf16_path(dd) == 1 && tc_train_supported(dd), "imagine_bwd: this shape has no bf16 BPTT kernel");
+    const int path = bf16_path(dd);
+    WMRL_REQUIRE((path == 1 && tc_train_supported(dd)) || (path == 2 && tcl_train_supported(dd)),
+                 "imagine_bwd: this shape has no bf16 BPTT kernel");
     WMRL_REQUIRE(packed, "imagine_bwd: bf16 path needs the packed weight image");
     WMRL_REQUIRE(!(d->flags & WMRL_FLAG_WM_WGRAD), "imagine_bwd: the bf16 BPTT produces actor gradients only "
                                                    "(world model frozen, world_model.py:172); use the fp32 path");
-    WMRL_REQUIRE(dist_b && g_deter0 && g_stoch0, "imagine_bwd: NULL tensor");
+    WMRL_REQUIRE(g_deter0 && g_stoch0 && (dd.variant == WMRL_DISCRETE || dist_b), "imagine_bwd: NULL tensor");
     WMRL_REQUIRE(wmrl_device_supports_bf16(), "imagine_bwd: bf16 path needs an sm_100 device");
+    if (path == 2) {
+      return tcl_imagine_bwd(dd, packed, noise, deter_seq, dist_a, dist_b, actions, saved, g_deter_seq, g_stoch_seq,
+                             g_dist_a, g_dist_b, gaw, g_deter0, g_stoch0, ws, (cudaStream_t)stream);
+    }
     return tc_imagine_bwd(dd, packed, noise, deter_seq, dist_b, actions, saved, g_deter_seq, g_stoch_seq, g_dist_a,
                           g_dist_b, gaw, g_deter0, g_stoch0, ws, (cudaStream_t)stream);
   }

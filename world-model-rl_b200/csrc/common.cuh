@@ -101,7 +101,13 @@ int tcl_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_
                      cudaStream_t st);
 int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, const float* stoch0, const float* noise,
                     float* deter_seq, float* stoch_seq, float* dist_a, float* dist_b, float* actions, int32_t* idx,
-                    void* ws, cudaStream_t st);
+                    void* saved, void* ws, cudaStream_t st);
+bool tcl_train_supported(const Dims& d);
+size_t tcl_saved_bytes(const Dims& d);
+int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const float* deter_seq, const float* dist_a,
+                    const float* dist_b, const float* actions, const void* saved, const float* g_deter_seq,
+                    const float* g_stoch_seq, const float* g_dist_a, const float* g_dist_b, const wmrl_actor_grads* gaw,
+                    float* g_deter0, float* g_stoch0, void* ws, cudaStream_t st);
 // which bf16 forward serves this shape: 1 persistent folded-pair / single-CTA kernel, 2 layer-wise chain, 0 none
 int bf16_path(const Dims& d);
 

@@ -48,7 +48,8 @@ constexpr int kGruTile = 64;                // state columns per GRU work item (
 
 static_assert((kLSlots & (kLSlots - 1)) == 0, "kLSlots must be a power of two");
 
-enum : int { LE_LN_ELU = 1, LE_BIAS_ELU, LE_MU, LE_GRU, LE_SAMPLE_DISC, LE_SAMPLE_CONT };
+enum : int { LE_LN_ELU = 1, LE_BIAS_ELU, LE_MU, LE_GRU, LE_SAMPLE_DISC, LE_SAMPLE_CONT,
+              LB_ELU, LB_GRU, LB_CARRY, LB_EMB, LB_LN };   // LB_*: BPTT epilogues
 
 struct LSeg {
   const uint8_t* a;        // activation panel, tile 0
@@ -75,8 +76,12 @@ struct LayerArgs {
   int n;                   // accumulator columns of one column tile seen by the epilogue
   int NT, MT;              // column tiles, row tiles
   int B, H, t;
-  int D, S, C, A, Sp, Dp;
+  int D, S, C, A, Sp, Dp, Sip;
   float inv_action_scale;
+  int save;                // forward: record what the BPTT needs (LayerNorm x-hat + rstd, GRU r / z / n / h_n)
+  uint8_t* aux[4];         // extra panels (tile 0) an epilogue reads or writes: recorded activations, g_u
+  uint32_t aux_tile_bytes;
+  float *f0, *f1, *f2;     // extra fp32 tensors (rstd, carry rows, upstream / start-state gradients; see the epilogues)
   uint8_t* out;            // destination panel (tile 0)
   uint32_t out_tile_bytes;
   int out_cols;            // padded width of the destination panel: chunks beyond it are not stored
@@ -154,22 +159,31 @@ __device__ __forceinline__ void lepi_ln_elu(const LCtx& c) {
   const float var = fmaxf(sq * inv - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
   const float nmr = -mean * rstd;
+  if (p.save && c.q == 0 && p.f0) p.f0[(long long)c.mt * 128 + c.row] = rstd;
+  uint8_t* xrow = p.save ? p.aux[0] + (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16 : nullptr;
   for (int g = c.q; g < ngrp; g += 4) {
     float v[32];
     tmem_ld32(c.tmem_lane + g * 32, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float4 b4 = lds4(bias + (g * 32 + i) * 4);
-      const float4 g4 = lds4(gam + (g * 32 + i) * 4);
-      const float4 e4 = lds4(bet + (g * 32 + i) * 4);
-      v[i] = elu_scaled(fmaf(fmaf(v[i] + b4.x, rstd, nmr), g4.x, e4.x));
-      v[i + 1] = elu_scaled(fmaf(fmaf(v[i + 1] + b4.y, rstd, nmr), g4.y, e4.y));
-      v[i + 2] = elu_scaled(fmaf(fmaf(v[i + 2] + b4.z, rstd, nmr), g4.z, e4.z));
-      v[i + 3] = elu_scaled(fmaf(fmaf(v[i + 3] + b4.w, rstd, nmr), g4.w, e4.w));
-    }
+    for (int k = 0; k < 4; ++k) {
+      float xh[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) st_chunk_g(c.out_row + (size_t)(g * 4 + k) * kLTileChunk, v + k * 8);
+      for (int i = 0; i < 8; i += 4) {
+        const int f = g * 32 + k * 8 + i;
+        const float4 b4 = lds4(bias + f * 4), g4 = lds4(gam + f * 4), e4 = lds4(bet + f * 4);
+        xh[i] = fmaf(v[k * 8 + i] + b4.x, rstd, nmr);
+        xh[i + 1] = fmaf(v[k * 8 + i + 1] + b4.y, rstd, nmr);
+        xh[i + 2] = fmaf(v[k * 8 + i + 2] + b4.z, rstd, nmr);
+        xh[i + 3] = fmaf(v[k * 8 + i + 3] + b4.w, rstd, nmr);
+        v[k * 8 + i] = elu_scaled(fmaf(xh[i], g4.x, e4.x));
+        v[k * 8 + i + 1] = elu_scaled(fmaf(xh[i + 1], g4.y, e4.y));
+        v[k * 8 + i + 2] = elu_scaled(fmaf(xh[i + 2], g4.z, e4.z));
+        v[k * 8 + i + 3] = elu_scaled(fmaf(xh[i + 3], g4.w, e4.w));
+      }
+      if (p.save) st_chunk_g(xrow + (size_t)(g * 4 + k) * kLTileChunk, xh);
+      st_chunk_g(c.out_row + (size_t)(g * 4 + k) * kLTileChunk, v + k * 8);
+    }
   }
 }
 
@@ -247,6 +261,7 @@ __device__ __forceinline__ void lepi_gru(const LCtx& c, const LGruPre& pf) {
     const int lc = c.q * 16 + hf * 8;   // column inside the tile
     const int col = c.nt * cw + lc;
     float gi[8], r[8], z[8], gh[8], hn[8];
+    float sr[8], sz[8], sn[8], sh[8];   // recorded for the BPTT: r, z, n, W_hn h + b_hn
     tmem_ld8(c.tmem_lane + lc, gi);
     tmem_ld8(c.tmem_lane + cw + lc, r);
     tmem_ld8(c.tmem_lane + 2 * cw + lc, z);
@@ -266,6 +281,7 @@ __device__ __forceinline__ void lepi_gru(const LCtx& c, const LGruPre& pf) {
         const float hprev = pf.hp[hf * 8 + i + e];
         const float h = (col + i + e < p.D) ? fmaf(zz, hprev - nn, nn) : 0.f;   // (1-z) n + z h
         hn[i + e] = h;
+        sr[i + e] = rr; sz[i + e] = zz; sn[i + e] = nn; sh[i + e] = gh[i + e] + bhv[e];
       }
     }
     if (c.valid) {
@@ -279,6 +295,10 @@ __device__ __forceinline__ void lepi_gru(const LCtx& c, const LGruPre& pf) {
       }
     }
     if (col < p.out_cols) st_chunk_g(c.out_row + (size_t)(col / 8) * kLTileChunk, hn);
+    if (p.save && col < p.out_cols) {
+      const size_t ao = (size_t)c.mt * p.aux_tile_bytes + (size_t)(col / 8) * kLTileChunk + (size_t)c.row * 16;
+      st_chunk_g(p.aux[0] + ao, sr); st_chunk_g(p.aux[1] + ao, sz); st_chunk_g(p.aux[2] + ao, sn); st_chunk_g(p.aux[3] + ao, sh);
+    }
   }
 }
 
@@ -444,6 +464,234 @@ __device__ __forceinline__ void lepi_sample_disc(const LCtx& c) {
       if (col + k * 8 < p.out_cols) st_chunk_g(c.out_row + (size_t)(col / 8 + k) * kLTileChunk, oh);
     }
     LPROBE(c, 5);
+  }
+}
+
+// ==========================================================================
+// BPTT epilogues.  Recorded activations are panels of the same layout, read 16 B per row and chunk;
+// every output is ZERO for rows past B (the weight-gradient GEMMs contract over all 128 rows of a tile).
+// ==========================================================================
+__device__ __forceinline__ uint4 l_ldg16(const void* ptr) { return *reinterpret_cast<const uint4*>(ptr); }
+__device__ __forceinline__ void l_unpack8(const uint4& u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+
+// g = acc * ELU'(a), a = the recorded post-ELU activation (ELU'(z) = 1 for z > 0, else a + 1) -> panel
+__device__ __forceinline__ void lepib_elu(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  const uint8_t* arow = p.aux[0] + (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16;
+  for (int g = c.q; g < p.n / 8; g += 4) {
+    const int col = c.nt * p.n + g * 8;
+    if (col >= p.out_cols) break;
+    float v[8], a[8];
+    tmem_ld8(c.tmem_lane + g * 8, v);
+    const uint4 au = l_ldg16(arow + (size_t)(col / 8) * kLTileChunk);
+    l_unpack8(au, a);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = c.valid ? v[i] * ((a[i] > 0.f) ? 1.f : (a[i] + 1.f)) : 0.f;
+    st_chunk_g(c.out_row + (size_t)(col / 8) * kLTileChunk, v);
+  }
+}
+
+// GRUCell backward (h' = (1-z) n + z h, n = tanh(i_n + r h_n)): accumulator = g_hid W1; f0 = the fp32 carry rows
+// [MT*128][Dp] holding the rest of dL/dh'.  Writes the gate-gradient panel [g_n | g_r | g_z | g_n r] and leaves the
+// direct term dL/dh' z in the carry row.
+__device__ __forceinline__ void lepib_gru(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  const long long prow = (long long)c.mt * 128 + c.row;
+  const size_t arow = (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16;
+  const size_t fstride = (size_t)(p.Dp / 8) * kLTileChunk;
+  for (int g = c.q; g < p.n / 8; g += 4) {
+    const int col = c.nt * p.n + g * 8;
+    if (col >= p.Dp) break;
+    float acc[8], r[8], z[8], n[8], hn[8], cr[8], hp[8];
+    tmem_ld8(c.tmem_lane + g * 8, acc);
+    const size_t ao = arow + (size_t)(col / 8) * kLTileChunk;
+    const uint4 ur = l_ldg16(p.aux[0] + ao), uz = l_ldg16(p.aux[1] + ao), un = l_ldg16(p.aux[2] + ao), uh = l_ldg16(p.aux[3] + ao);
+    float* scr = p.f0 + prow * p.Dp + col;
+    const float4 c0 = *reinterpret_cast<const float4*>(scr), c1 = *reinterpret_cast<const float4*>(scr + 4);
+    cr[0] = c0.x; cr[1] = c0.y; cr[2] = c0.z; cr[3] = c0.w; cr[4] = c1.x; cr[5] = c1.y; cr[6] = c1.z; cr[7] = c1.w;
+    const float* hrow = p.deter_seq + (c.b * (p.H + 1) + p.t) * p.D + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hp[i] = (c.valid && col + i < p.D) ? hrow[i] : 0.f;
+    l_unpack8(ur, r); l_unpack8(uz, z); l_unpack8(un, n); l_unpack8(uh, hn);
+    tmem_ld_wait();
+    float on[8], orr[8], oz[8], oh[8], od[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gh = c.valid ? acc[i] + cr[i] : 0.f;
+      const float gn = gh * (1.f - z[i]);
+      const float gz = gh * (hp[i] - n[i]);
+      od[i] = gh * z[i];
+      const float gnp = gn * (1.f - n[i] * n[i]);
+      on[i] = gnp;
+      oz[i] = gz * z[i] * (1.f - z[i]);
+      oh[i] = gnp * r[i];
+      orr[i] = gnp * hn[i] * r[i] * (1.f - r[i]);
+    }
+    uint8_t* dst = c.out_row + (size_t)(col / 8) * kLTileChunk;
+    st_chunk_g(dst, on);
+    st_chunk_g(dst + fstride, orr);
+    st_chunk_g(dst + 2 * fstride, oz);
+    st_chunk_g(dst + 3 * fstride, oh);
+    *reinterpret_cast<float4*>(scr) = make_float4(od[0], od[1], od[2], od[3]);
+    *reinterpret_cast<float4*>(scr + 4) = make_float4(od[4], od[5], od[6], od[7]);
+  }
+}
+
+// dL/dh_t = acc + dL/dh' z (carry row) + upstream dL/ddeter[:, t]: carried on, or - at t = 0 - the start-state gradient
+__device__ __forceinline__ void lepib_carry(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  const long long prow = (long long)c.mt * 128 + c.row;
+  for (int g = c.q; g < p.n / 8; g += 4) {
+    const int col = c.nt * p.n + g * 8;
+    if (col >= p.Dp) break;
+    float acc[8];
+    tmem_ld8(c.tmem_lane + g * 8, acc);
+    float* scr = p.f0 + prow * p.Dp + col;
+    const float4 c0 = *reinterpret_cast<const float4*>(scr), c1 = *reinterpret_cast<const float4*>(scr + 4);
+    const float cr[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    float up[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      up[i] = (p.f1 && c.valid && col + i < p.D) ? p.f1[(c.b * (p.H + 1) + p.t) * p.D + col + i] : 0.f;
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = c.valid ? acc[i] + cr[i] + up[i] : 0.f;
+    if (p.t > 0) {
+      *reinterpret_cast<float4*>(scr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(scr + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else if (c.valid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col + i < p.D) p.f2[c.b * p.D + col + i] = acc[i];
+    }
+  }
+}
+
+// [dL/ds_t | dL/da_t] = g_x W_e.  Latent tiles: fp32 carry rows f0 [MT*128][Sip] (read by the previous step's sample
+// backward) or, at t = 0, the start-state gradient f2 (+ upstream f1[:, 0]).  Last tile: the action columns through the
+// tanh squash (actor.py:49-50: a = tanh(mu / scale) bound) -> g_mu panel.
+__device__ __forceinline__ void lepib_emb(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  const int S_in = p.S * p.C;
+  if (c.nt < p.NT - 1) {
+    const long long prow = (long long)c.mt * 128 + c.row;
+    for (int g = c.q; g < p.n / 8; g += 4) {
+      const int col = c.nt * p.n + g * 8;
+      if (col >= p.Sip) break;
+      float acc[8];
+      tmem_ld8(c.tmem_lane + g * 8, acc);
+      tmem_ld_wait();
+      if (p.t > 0) {
+        float* scr = p.f0 + prow * p.Sip + col;
+        *reinterpret_cast<float4*>(scr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(scr + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      } else if (c.valid) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (col + i < S_in) {
+            float gv = acc[i];
+            if (p.f1) gv += p.f1[(c.b * (p.H + 1)) * S_in + col + i];
+            p.f2[c.b * S_in + col + i] = gv;
+          }
+      }
+    }
+  } else if (c.q == 0) {
+    float acc[16], gm[16];
+    tmem_ld16(c.tmem_lane, acc);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      gm[i] = 0.f;
+      if (i < p.A && c.valid) {
+        const float bd = __ldg(p.ep + i);
+        const float a = p.actions[(c.b * p.H + p.t) * p.A + i];
+        const float th = (bd != 0.f) ? a / bd : 0.f;
+        gm[i] = acc[i] * bd * (1.f - th * th) * p.inv_action_scale;
+      }
+    }
+    st_chunk_g(c.out_row, gm);
+    st_chunk_g(c.out_row + kLTileChunk, gm + 8);
+  }
+}
+
+// LayerNorm(eps 1e-5, affine) + ELU backward of one actor block (actor.py:23-36) from the recorded x-hat / rstd:
+//   u = gamma xh + beta, g_u = g_y ELU'(u), g_xh = g_u gamma, g_pre = rstd (g_xh - mean(g_xh) - xh mean(g_xh xh)).
+// parameters [gamma log2e | beta log2e | gamma]; aux[0] = x-hat (read), aux[1] = g_u panel (written), out = g_pre.
+__device__ __forceinline__ void lepib_ln(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  const int W = p.n, ngrp = W / 32;
+  const uint32_t gsc = c.prm, bsc = gsc + W * 4, gam = bsc + W * 4;
+  const uint8_t* xrow = p.aux[0] + (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16;
+  uint8_t* gurow = p.aux[1] + (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16;
+  const float rstd = c.valid ? p.f0[(long long)c.mt * 128 + c.row] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  for (int g = c.q; g < ngrp; g += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8], xh[8], gu[8];
+      tmem_ld8(c.tmem_lane + g * 32 + k * 8, v);
+      const uint4 xu = l_ldg16(xrow + (size_t)(g * 4 + k) * kLTileChunk);
+      l_unpack8(xu, xh);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; i += 4) {
+        const int f = g * 32 + k * 8 + i;
+        const float4 g4 = lds4(gsc + f * 4), b4 = lds4(bsc + f * 4), w4 = lds4(gam + f * 4);
+        const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w}, gw[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float us = fmaf(gs[e], xh[i + e], bs[e]);                                  // u * log2(e)
+          const float g_u = c.valid ? v[i + e] * ex2_fast(fminf(us, 0.f)) : 0.f;           // ELU'(u) = 1 (u > 0) | exp(u)
+          const float g_x = g_u * gw[e];
+          gu[i + e] = g_u;
+          s1 += g_x;
+          s2 = fmaf(g_x, xh[i + e], s2);
+        }
+      }
+      st_chunk_g(gurow + (size_t)(g * 4 + k) * kLTileChunk, gu);
+    }
+  }
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(c.scratch + (c.q * 128 + c.row) * 8), "f"(s1), "f"(s2) : "memory");
+  l_quarter_sync(c.quarter);
+  s1 = 0.f; s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float a, b;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "r"(c.scratch + (k * 128 + c.row) * 8) : "memory");
+    s1 += a; s2 += b;
+  }
+  const float inv = 1.f / (float)W;
+  const float m1 = s1 * inv, m2 = s2 * inv;
+  for (int g = c.q; g < ngrp; g += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8], xh[8], gp[8];
+      tmem_ld8(c.tmem_lane + g * 32 + k * 8, v);
+      const uint4 xu = l_ldg16(xrow + (size_t)(g * 4 + k) * kLTileChunk);
+      l_unpack8(xu, xh);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; i += 4) {
+        const int f = g * 32 + k * 8 + i;
+        const float4 g4 = lds4(gsc + f * 4), b4 = lds4(bsc + f * 4), w4 = lds4(gam + f * 4);
+        const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w}, gw[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float us = fmaf(gs[e], xh[i + e], bs[e]);
+          const float g_x = v[i + e] * ex2_fast(fminf(us, 0.f)) * gw[e];
+          gp[i + e] = c.valid ? rstd * (g_x - m1 - xh[i + e] * m2) : 0.f;
+        }
+      }
+      st_chunk_g(c.out_row + (size_t)(g * 4 + k) * kLTileChunk, gp);
+    }
   }
 }
 
@@ -629,6 +877,11 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
       else if (kType == LE_MU) lepi_mu(c);
       else if (kType == LE_GRU) lepi_gru(c, gpf);
       else if (kType == LE_SAMPLE_CONT) lepi_sample_cont(c);
+      else if (kType == LB_ELU) lepib_elu(c);
+      else if (kType == LB_GRU) lepib_gru(c);
+      else if (kType == LB_CARRY) lepib_carry(c);
+      else if (kType == LB_EMB) lepib_emb(c);
+      else if (kType == LB_LN) lepib_ln(c);
       else lepi_sample_disc<(kS > 0 ? kS : 4)>(c);
       tc_fence_before();
       __syncwarp();
@@ -652,6 +905,11 @@ static LayerKernel layer_kernel_for(int type, int S) {
     case LE_MU: return tc_layer_kernel<LE_MU, 0>;
     case LE_GRU: return tc_layer_kernel<LE_GRU, 0>;
     case LE_SAMPLE_CONT: return tc_layer_kernel<LE_SAMPLE_CONT, 0>;
+    case LB_ELU: return tc_layer_kernel<LB_ELU, 0>;
+    case LB_GRU: return tc_layer_kernel<LB_GRU, 0>;
+    case LB_CARRY: return tc_layer_kernel<LB_CARRY, 0>;
+    case LB_EMB: return tc_layer_kernel<LB_EMB, 0>;
+    case LB_LN: return tc_layer_kernel<LB_LN, 0>;
     default: break;
   }
   return S == 32 ? tc_layer_kernel<LE_SAMPLE_DISC, 32> : S == 16 ? tc_layer_kernel<LE_SAMPLE_DISC, 16>
@@ -685,13 +943,254 @@ __global__ void tcl_init_kernel(const float* __restrict__ deter0, const float* _
 }
 
 // --------------------------------------------------------------------------
-// host: plan, packing, launch chain
+// BPTT helpers outside the GEMM chain
 // --------------------------------------------------------------------------
-enum { BUF_H0 = 0, BUF_H1, BUF_S, BUF_A, BUF_Y0, BUF_Y1, BUF_X, BUF_HID, BUF_COUNT };
+// carry rows of dL/dh: the upstream gradient of the LAST deter state (zero where absent / padding)
+__global__ void tcl_carry_init_kernel(float* carry_h, const float* g_deter, int B, int H, int D, int Dp, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long b = i / Dp;
+  const int col = (int)(i % Dp);
+  carry_h[i] = (g_deter && b < B && col < D) ? g_deter[(b * (H + 1) + H) * D + col] : 0.f;
+}
+
+struct SbArgs {
+  const float *carry_s, *g_stoch, *g_da, *g_db, *dist_a, *dist_b, *noise;
+  uint8_t* out;   // g_out panel [MT][Pp/8][128][8] bf16
+  int B, H, t, S, C, Sp, Sip, Pp, MT;
+};
+__device__ __forceinline__ void panel_store_bf16(uint8_t* panel, int Pp, long long prow, int col, float v) {
+  const long long mt = prow >> 7;
+  const int row = (int)(prow & 127);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(panel + (size_t)mt * (Pp / 8) * kLTileChunk + (size_t)(col / 8) * kLTileChunk +
+                                                        (size_t)row * 16) + (col & 7);
+  *dst = __float2bfloat16_rn(v);
+}
+// straight-through categorical backward (state/discrete.py:27-30): for the state produced by step t,
+//   G = carried dL/ds + dL/dstoch[:, t+1];  dlogits = p (G - sum_k p_k G_k) + dL/dlogits[:, t+1],  p = softmax(logits[:, t+1])
+// one warp per (padded row, group), lane = class
+__global__ void tcl_sample_bwd_disc_kernel(const SbArgs a) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (long long)a.MT * 128 * a.C) return;
+  const long long prow = warp / a.C;
+  const int c = (int)(warp % a.C);
+  const int P = a.C * a.S;
+  const bool valid = prow < a.B;
+  const long long o = (prow * (a.H + 1) + a.t + 1) * P + (long long)c * a.S;
+  float l = -INFINITY, G = 0.f, gl = 0.f;
+  if (valid && lane < a.S) {
+    l = a.dist_a[o + lane];
+    if (a.carry_s) G = a.carry_s[prow * a.Sip + c * a.S + lane];
+    if (a.g_stoch) G += a.g_stoch[o + lane];
+    if (a.g_da) gl = a.g_da[o + lane];
+  }
+  float mx = l;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  const float e = (valid && lane < a.S) ? expf(l - mx) : 0.f;
+  float se = e, sg = e * G;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, s); sg += __shfl_xor_sync(0xffffffffu, sg, s); }
+  if (lane < a.S) {
+    const float v = valid ? (e / se) * (G - sg / se) + gl : 0.f;
+    panel_store_bf16(a.out, a.Pp, prow, c * a.S + lane, v);
+  }
+  // zero the padding columns [P, Pp) once per row
+  if (c == 0 && P + lane < a.Pp) panel_store_bf16(a.out, a.Pp, prow, P + lane, 0.f);
+}
+// Gaussian reparameterised sample backward (rssm.py:179-181): panel [g_mean (Sp) | g_raw (Sp)],
+//   g_mean = dL/dmean + G,  g_raw = (dL/dstd + G eps) sigmoid(raw),  sigmoid(raw) = 1 - exp(-(std - 0.1))
+// one thread per (padded row, 8-column chunk)
+__global__ void tcl_sample_bwd_cont_kernel(const SbArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nch = a.Sp / 8;
+  if (i >= (long long)a.MT * 128 * nch) return;
+  const long long prow = i / nch;
+  const int col = (int)(i % nch) * 8;
+  const bool valid = prow < a.B;
+  const long long o = (prow * (a.H + 1) + a.t + 1) * a.S + col;
+  float gm[8], gr[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    gm[k] = gr[k] = 0.f;
+    if (valid && col + k < a.S) {
+      float G = a.carry_s ? a.carry_s[prow * a.Sip + col + k] : 0.f;
+      if (a.g_stoch) G += a.g_stoch[o + k];
+      const float eps = a.noise[((long long)a.t * a.B + prow) * a.S + col + k];
+      const float sig = 1.f - __expf(-(a.dist_b[o + k] - 0.1f));
+      gm[k] = (a.g_da ? a.g_da[o + k] : 0.f) + G;
+      gr[k] = ((a.g_db ? a.g_db[o + k] : 0.f) + G * eps) * sig;
+    }
+  }
+  const long long mt = prow >> 7;
+  const int row = (int)(prow & 127);
+  uint8_t* base = a.out + (size_t)mt * (a.Pp / 8) * kLTileChunk + (size_t)row * 16;
+  st_chunk_g(base + (size_t)(col / 8) * kLTileChunk, gm);
+  st_chunk_g(base + (size_t)((a.Sp + col) / 8) * kLTileChunk, gr);
+}
+
+// weight gradients: dW[n][m] += sum over 128-row blocks of A_blk[m][rows] . B_blk[n][rows]
+//   A = in-feature panel (actor block input), 128 in-features per CTA tile (TMEM lanes)
+//   B = out-feature panel (g_pre / g_mu), up to 256 out-features per CTA tile (TMEM columns)
+// For a contraction over ROWS a panel tile [feature/8][128 rows][8] is exactly the canonical no-swizzle MN-major
+// operand: 8 features contiguous, 8-row groups 128 B apart, feature chunks 2 KB apart.  Split-K over the SMs, fp32 atomics.
+struct Wg2Params {
+  const uint8_t* a_base; size_t a_blk;
+  const uint8_t* b_base; size_t b_blk;
+  int nblocks, m_cols, m_valid, n_cols, n_valid;
+  float* dW; int ldw;
+  int mtiles, ntiles, splits;
+};
+constexpr int kWg2Stages = 2, kWg2Threads = 192;
+constexpr uint32_t kWg2A = 32768, kWg2B = 65536, kWg2Stage = kWg2A + kWg2B;
+constexpr uint32_t kWg2Smem = kWg2Stages * kWg2Stage + 1024;
+__global__ void __launch_bounds__(kWg2Threads, 1) tcl_wgrad_kernel(const Wg2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bars = smem_base + kWg2Stages * kWg2Stage;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };
+  const uint32_t acc_bar = bars + 128u;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kWg2Stages * kWg2Stage + 136);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, split = blockIdx.y;
+  const int mt = tile / p.ntiles, nt = tile % p.ntiles;
+  const int m0 = mt * 128, n0 = nt * 256;
+  const int mc = min(128, p.m_cols - m0), nc = min(256, p.n_cols - n0);
+  const uint32_t a_bytes = (uint32_t)(mc / 8) * kLTileChunk, b_bytes = (uint32_t)(nc / 8) * kLTileChunk;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWg2Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) { tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nmine = (p.nblocks > split) ? (p.nblocks - split + p.splits - 1) / p.splits : 0;
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int i = 0; i < nmine; ++i) {
+        const size_t blk = (size_t)split + (size_t)i * p.splits;
+        mbar_wait(empty_bar(slot), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(slot), a_bytes + b_bytes);
+        bulk_g2s(smem_base + slot * kWg2Stage, p.a_base + blk * p.a_blk + (size_t)(m0 / 8) * kLTileChunk, a_bytes, full_bar(slot));
+        bulk_g2s(smem_base + slot * kWg2Stage + kWg2A, p.b_base + blk * p.b_blk + (size_t)(n0 / 8) * kLTileChunk, b_bytes,
+                 full_bar(slot));
+        if (++slot == kWg2Stages) { slot = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)nc) | (1u << 15) | (1u << 16);   // A and B MN-major
+      uint32_t slot = 0, phase = 0;
+      for (int i = 0; i < nmine; ++i) {
+        mbar_wait(full_bar(slot), phase);
+        tc_fence_after();
+        const uint32_t a0 = smem_base + slot * kWg2Stage, b0 = a0 + kWg2A;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // 16 rows (K) per MMA: two 8-row groups = 256 B further on
+          const uint64_t da = make_smem_desc(a0 + k * 256, 128u, kLTileChunk);
+          const uint64_t db = make_smem_desc(b0 + k * 256, 128u, kLTileChunk);
+          mma_bf16_ss(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(empty_bar(slot));
+        if (++slot == kWg2Stages) { slot = 0; phase ^= 1u; }
+      }
+      tc_commit(acc_bar);
+    }
+  } else {
+    // epilogue: thread = TMEM lane = in-feature m; consecutive lanes -> consecutive dW columns (coalesced atomics)
+    mbar_wait_backoff(acc_bar, 0);
+    tc_fence_after();
+    if (nmine > 0) {
+      const int m = m0 + warp * 32 + lane;
+      const bool ok = m < p.m_valid;
+      const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+      for (int j0 = 0; j0 < nc; j0 += 16) {
+        float v[16];
+        tmem_ld16(tl + j0, v);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + j0 + j;
+            if (n < p.n_valid) atomicAdd(p.dW + (size_t)n * p.ldw + m, v[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 256);
+}
+
+// column sums over panel tiles: out[c] += sum over blocks and their 128 rows of X[c] (* Y[c])
+struct Cs2Params {
+  const uint8_t* x_base; size_t x_blk;
+  const uint8_t* y_base; size_t y_blk;   // null: plain column sum
+  int nblocks, valid;
+  float* out;
+};
+constexpr int kCs2Warps = 8;
+__global__ void __launch_bounds__(kCs2Warps * 32) tcl_colsum_kernel(const Cs2Params p) {
+  const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const size_t off = (size_t)chunk * kLTileChunk + (size_t)lane * 16;
+  for (size_t blk = (size_t)blockIdx.y * kCs2Warps + warp; blk < (size_t)p.nblocks; blk += (size_t)gridDim.y * kCs2Warps) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float x[8];
+      ld_chunk_g(p.x_base + blk * p.x_blk + off + r * 512, x);
+      if (p.y_base) {
+        float y[8];
+        ld_chunk_g(p.y_base + blk * p.y_blk + off + r * 512, y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[i], y[i], acc[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += x[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], s);
+  __shared__ float part[kCs2Warps][8];
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[warp][i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+    for (int w2 = 0; w2 < kCs2Warps; ++w2) s += part[w2][threadIdx.x];
+    const int col = chunk * 8 + threadIdx.x;
+    if (col < p.valid) atomicAdd(p.out + col, s);
+  }
+}
+
+// --------------------------------------------------------------------------
+// host: plan, packing, memory layout, launch chains
+// --------------------------------------------------------------------------
+// logical panel buffers.  Forward fields first (activations; recorded per step when training), then the BPTT's
+// gradient panels.  F_Y / F_XH / F_RSTD / G_GP / G_GU take one slot per actor block.
+enum {
+  F_H = 0, F_HN, F_S, F_SN, F_A, F_X, F_HID, F_GR, F_GZ, F_GN, F_GHN,
+  F_Y0, F_XH0 = F_Y0 + WMRL_MAX_ACTOR_LAYERS, F_RSTD0 = F_XH0 + WMRL_MAX_ACTOR_LAYERS,
+  G_GO = F_RSTD0 + WMRL_MAX_ACTOR_LAYERS, G_GHID, G_GATES_I, G_GATES_H, G_GX, G_GMU,
+  G_GP0, G_GU0 = G_GP0 + WMRL_MAX_ACTOR_LAYERS, BUF_COUNT = G_GU0 + WMRL_MAX_ACTOR_LAYERS
+};
 
 struct LSegH { int buf, k16, n, tmem_col, split, fresh; uint32_t w_off; };
 struct LLayerH {
-  int type = 0, NT = 1, n = 0, nseg = 0, kc = 1, dbuf = 0, out = 0;
+  int type = 0, NT = 1, n = 0, nseg = 0, kc = 1, dbuf = 0, out = 0, layer = 0;
   LSegH seg[3];
   size_t w_off = 0;          // into the data area
   uint32_t w_tile_bytes = 0;
@@ -701,9 +1200,9 @@ struct LLayerH {
 struct LPlan {
   bool ok = false;
   Plan pk;                   // pack ops / vec ops / image offsets (stage and job tables stay empty)
-  std::vector<LLayerH> layers;
-  int Dp = 0, Sip = 0, Sp = 0, Hdp = 0, Ha = 0;
-  int width[BUF_COUNT] = {0};
+  std::vector<LLayerH> layers;    // forward chain of one step
+  std::vector<LLayerH> blayers;   // backward chain of one step (after the sample backward)
+  int Dp = 0, Sip = 0, Sp = 0, Hdp = 0, Ha = 0, Pp = 0;
 };
 
 static int ceil_to(int x, int m) { return (x + m - 1) / m * m; }
@@ -722,6 +1221,34 @@ static void l_add_pack(LPlan& lp, const RowSpec& rs, const float* src, int ld, i
   lp.pk.pack_ops.push_back(op);
   lp.pk.data_bytes += (size_t)kpad * rs.N() * 2;
 }
+// dgrad operand: B rows are IN-features `rs` of the torch weight src[out][in] (ld = in-features), the K index runs over
+// OUT-features, given as up to 4 ranges {first, valid, padded}
+struct KRange { int k0, valid, pad; };
+static void l_add_pack_t(LPlan& lp, const RowSpec& rs, const float* src, int ld, std::initializer_list<KRange> ks) {
+  PackOp op{};
+  op.src = src; op.ld = ld; op.trans = 1;
+  op.nseg = rs.nseg;
+  for (int q = 0; q < rs.nseg; ++q) { op.row0[q] = rs.seg[q].row0; op.valid[q] = rs.seg[q].valid; op.pad[q] = rs.seg[q].pad; }
+  int kpad = 0, i = 0;
+  for (const KRange& k : ks) { op.kk0[i] = k.k0; op.kkvalid[i] = k.valid; op.kkpad[i] = k.pad; kpad += k.pad; ++i; }
+  op.nks = i; op.kbegin = 0;
+  op.k0 = 0; op.kvalid = kpad; op.nk8 = kpad / 8;
+  op.split = 1;
+  op.dst_off = lp.pk.data_bytes;
+  op.bias = nullptr; op.bias_k = -1;
+  lp.pk.pack_ops.push_back(op);
+  lp.pk.data_bytes += (size_t)kpad * rs.N() * 2;
+}
+
+static int buf_width(const LPlan& lp, int buf) {
+  if (buf == F_H || buf == F_HN || buf == F_X || buf == F_GR || buf == F_GZ || buf == F_GN || buf == F_GHN || buf == G_GX) return lp.Dp;
+  if (buf == F_S || buf == F_SN) return lp.Sip;
+  if (buf == F_A || buf == G_GMU) return 16;
+  if (buf == F_HID || buf == G_GHID) return lp.Hdp;
+  if (buf == G_GO) return lp.Pp;
+  if (buf == G_GATES_I || buf == G_GATES_H) return 4 * lp.Dp;
+  return lp.Ha;   // F_Y, F_XH, G_GP, G_GU
+}
 
 static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw) {
   LPlan lp;
@@ -730,9 +1257,8 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
   if (disc && !(d.S == 4 || d.S == 8 || d.S == 16 || d.S == 32)) return lp;
   const int Dp = ceil16(d.D), Sip = ceil16(d.S_in), Sp = ceil16(d.S), Hdp = ceil16(d.Hd);
   if (!disc && 2 * Sp > 256) return lp;
-  lp.Dp = Dp; lp.Sip = Sip; lp.Sp = Sp; lp.Hdp = Hdp; lp.Ha = d.Ha;
-  lp.width[BUF_H0] = lp.width[BUF_H1] = Dp; lp.width[BUF_S] = Sip; lp.width[BUF_A] = 16;
-  lp.width[BUF_Y0] = lp.width[BUF_Y1] = d.Ha; lp.width[BUF_X] = Dp; lp.width[BUF_HID] = Hdp;
+  const int Pp = disc ? Sip : 2 * Sp;
+  lp.Dp = Dp; lp.Sip = Sip; lp.Sp = Sp; lp.Hdp = Hdp; lp.Ha = d.Ha; lp.Pp = Pp;
   const float* nul = nullptr;
   Plan& pk = lp.pk;
   auto kc_for = [&](int nmax) { int kc = (int)(kLSlotBytes / (4096u + (uint32_t)nmax * 32u)); return std::max(1, std::min(kc, 8)); };
@@ -741,23 +1267,24 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
     nt = (total + cap - 1) / cap;
     wt = ceil_to((total + nt - 1) / nt, unit);
   };
+  // ====================================================================== forward chain
   // ---- actor blocks: [h | s] (block 0) or y_{l-1} -> Linear -> LayerNorm -> ELU
   for (int l = 0; l < d.La; ++l) {
     LLayerH L;
-    L.type = LE_LN_ELU; L.NT = 1; L.n = d.Ha; L.dbuf = d.Ha <= 256 ? 1 : 0; L.out = (l & 1) ? BUF_Y1 : BUF_Y0;
+    L.type = LE_LN_ELU; L.NT = 1; L.n = d.Ha; L.dbuf = d.Ha <= 256 ? 1 : 0; L.out = F_Y0 + l; L.layer = l;
     L.kc = kc_for(d.Ha);
     L.w_off = pk.data_bytes;
     const float* lw = aw ? aw->lin_w[l] : nul;
     RowSpec rs(0, d.Ha, d.Ha);
     if (l == 0) {
       L.nseg = 2;
-      L.seg[0] = {BUF_H0, Dp / 16, d.Ha, 0, 0, 1, 0u};
+      L.seg[0] = {F_H, Dp / 16, d.Ha, 0, 0, 1, 0u};
       l_add_pack(lp, rs, lw, d.F, 0, d.D, Dp);
-      L.seg[1] = {BUF_S, Sip / 16, d.Ha, 0, 0, 0, (uint32_t)(pk.data_bytes - L.w_off)};
+      L.seg[1] = {F_S, Sip / 16, d.Ha, 0, 0, 0, (uint32_t)(pk.data_bytes - L.w_off)};
       l_add_pack(lp, rs, lw, d.F, d.D, d.S_in, Sip);
     } else {
       L.nseg = 1;
-      L.seg[0] = {((l - 1) & 1) ? BUF_Y1 : BUF_Y0, d.Ha / 16, d.Ha, 0, 0, 1, 0u};
+      L.seg[0] = {F_Y0 + l - 1, d.Ha / 16, d.Ha, 0, 0, 1, 0u};
       l_add_pack(lp, rs, lw, d.Ha, 0, d.Ha, d.Ha);
     }
     L.w_tile_bytes = (uint32_t)(pk.data_bytes - L.w_off);
@@ -767,11 +1294,11 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
     L.ep_floats = 3u * d.Ha;
     lp.layers.push_back(L);
   }
-  const int ylast = ((d.La - 1) & 1) ? BUF_Y1 : BUF_Y0;
+  const int ylast = F_Y0 + d.La - 1;
   // ---- mu head
   {
     LLayerH L;
-    L.type = LE_MU; L.NT = 1; L.n = 16; L.dbuf = 1; L.out = BUF_A; L.kc = kc_for(16); L.nseg = 1;
+    L.type = LE_MU; L.NT = 1; L.n = 16; L.dbuf = 1; L.out = F_A; L.kc = kc_for(16); L.nseg = 1;
     L.w_off = pk.data_bytes;
     L.seg[0] = {ylast, d.Ha / 16, 16, 0, 0, 1, 0u};
     l_add_pack(lp, RowSpec(0, d.A, 16), aw ? aw->mu_w : nul, d.Ha, 0, d.Ha, d.Ha);
@@ -784,7 +1311,7 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
   // ---- state-action embed: [s | a] -> Linear -> ELU
   {
     LLayerH L;
-    L.type = LE_BIAS_ELU; L.dbuf = 1; L.out = BUF_X; L.nseg = 2;
+    L.type = LE_BIAS_ELU; L.dbuf = 1; L.out = F_X; L.nseg = 2;
     tiles(Dp, 256, 16, L.NT, L.n);
     L.kc = kc_for(L.n);
     L.w_off = pk.data_bytes;
@@ -792,9 +1319,9 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
     for (int j = 0; j < L.NT; ++j) {
       const size_t t0 = pk.data_bytes;
       RowSpec rs(j * L.n, d.D - j * L.n, L.n);
-      L.seg[0] = {BUF_S, Sip / 16, L.n, 0, 0, 1, 0u};
+      L.seg[0] = {F_S, Sip / 16, L.n, 0, 0, 1, 0u};
       l_add_pack(lp, rs, w ? w->embed_w : nul, Ke, 0, d.S_in, Sip);
-      L.seg[1] = {BUF_A, 1, L.n, 0, 0, 0, (uint32_t)(pk.data_bytes - t0)};
+      L.seg[1] = {F_A, 1, L.n, 0, 0, 0, (uint32_t)(pk.data_bytes - t0)};
       l_add_pack(lp, rs, w ? w->embed_w : nul, Ke, d.S_in, d.A, 16);
       L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
       const uint32_t at = add_vec(pk, w ? w->embed_b : nul, nul, j * L.n, std::max(0, std::min(L.n, d.D - j * L.n)), L.n);
@@ -807,7 +1334,7 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
   {
     LLayerH L;
     constexpr int cw = kGruTile;
-    L.type = LE_GRU; L.dbuf = 1; L.out = BUF_H1; L.nseg = 2; L.n = 4 * cw;
+    L.type = LE_GRU; L.dbuf = 1; L.out = F_HN; L.nseg = 2; L.n = 4 * cw;
     L.NT = (Dp + cw - 1) / cw;
     L.kc = kc_for(3 * cw);
     L.w_off = pk.data_bytes;
@@ -816,11 +1343,11 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
       const int c0 = j * cw, v = std::max(0, std::min(cw, d.D - c0));
       RowSpec rx;   // W_ih rows [n | r | z] of the tile's state columns
       rx.add(2 * d.D + c0, v, cw); rx.add(c0, v, cw); rx.add(d.D + c0, v, cw);
-      L.seg[0] = {BUF_X, Dp / 16, 3 * cw, 0, 0, 1, 0u};
+      L.seg[0] = {F_X, Dp / 16, 3 * cw, 0, 0, 1, 0u};
       l_add_pack(lp, rx, w ? w->w_ih : nul, d.D, 0, d.D, Dp);
       RowSpec rh;   // W_hh rows [r | z | n]
       rh.add(c0, v, cw); rh.add(d.D + c0, v, cw); rh.add(2 * d.D + c0, v, cw);
-      L.seg[1] = {BUF_H0, Dp / 16, 3 * cw, cw, 2 * cw, 0, (uint32_t)(pk.data_bytes - t0)};
+      L.seg[1] = {F_H, Dp / 16, 3 * cw, cw, 2 * cw, 0, (uint32_t)(pk.data_bytes - t0)};
       l_add_pack(lp, rh, w ? w->w_hh : nul, d.D, 0, d.D, Dp);
       L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
       const uint32_t at = add_vec(pk, w ? w->b_ih : nul, w ? w->b_hh : nul, c0, v, cw);       // b_r
@@ -835,13 +1362,13 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
   // ---- prior hidden: h' -> Linear -> ELU
   {
     LLayerH L;
-    L.type = LE_BIAS_ELU; L.dbuf = 1; L.out = BUF_HID; L.nseg = 1;
+    L.type = LE_BIAS_ELU; L.dbuf = 1; L.out = F_HID; L.nseg = 1;
     tiles(Hdp, 256, 16, L.NT, L.n);
     L.kc = kc_for(L.n);
     L.w_off = pk.data_bytes;
     for (int j = 0; j < L.NT; ++j) {
       const size_t t0 = pk.data_bytes;
-      L.seg[0] = {BUF_H1, Dp / 16, L.n, 0, 0, 1, 0u};
+      L.seg[0] = {F_HN, Dp / 16, L.n, 0, 0, 1, 0u};
       l_add_pack(lp, RowSpec(j * L.n, d.Hd - j * L.n, L.n), w ? w->prior0_w : nul, d.D, 0, d.D, Dp);
       L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
       const uint32_t at = add_vec(pk, w ? w->prior0_b : nul, nul, j * L.n, std::max(0, std::min(L.n, d.Hd - j * L.n)), L.n);
@@ -853,14 +1380,14 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
   // ---- prior head + sample
   {
     LLayerH L;
-    L.dbuf = 1; L.out = BUF_S; L.nseg = 1;
+    L.dbuf = 1; L.out = F_SN; L.nseg = 1;
     L.w_off = pk.data_bytes;
     if (disc) {
       L.type = LE_SAMPLE_DISC;
       tiles(ceil_to(d.P, 32), 256, 32, L.NT, L.n);
       for (int j = 0; j < L.NT; ++j) {
         const size_t t0 = pk.data_bytes;
-        L.seg[0] = {BUF_HID, Hdp / 16, L.n, 0, 0, 1, 0u};
+        L.seg[0] = {F_HID, Hdp / 16, L.n, 0, 0, 1, 0u};
         l_add_pack(lp, RowSpec(j * L.n, d.P - j * L.n, L.n), w ? w->prior2_w : nul, d.Hd, 0, d.Hd, Hdp);
         L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
         const uint32_t at = add_vec(pk, w ? w->prior2_b : nul, nul, j * L.n, std::max(0, std::min(L.n, d.P - j * L.n)), L.n);
@@ -871,7 +1398,7 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
       L.type = LE_SAMPLE_CONT; L.NT = 1; L.n = 2 * Sp;
       RowSpec rs;
       rs.add(0, d.S, Sp); rs.add(d.S, d.S, Sp);
-      L.seg[0] = {BUF_HID, Hdp / 16, L.n, 0, 0, 1, 0u};
+      L.seg[0] = {F_HID, Hdp / 16, L.n, 0, 0, 1, 0u};
       l_add_pack(lp, rs, w ? w->prior2_w : nul, d.Hd, 0, d.Hd, Hdp);
       L.w_tile_bytes = (uint32_t)(pk.data_bytes - L.w_off);
       L.ep_off = add_vec(pk, w ? w->prior2_b : nul, nul, 0, d.S, Sp);
@@ -881,11 +1408,123 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
     L.kc = kc_for(L.n);
     lp.layers.push_back(L);
   }
-  for (const LLayerH& L : lp.layers) {
-    if (L.ep_floats * 4 > kLParamBytes || (L.ep_floats & 3)) return lp;
-    for (int s = 0; s < L.nseg; ++s)
-      if ((uint32_t)L.kc * (4096u + (uint32_t)L.seg[s].n * 32u) > kLSlotBytes) return lp;
+  // ====================================================================== backward chain (dgrad through the frozen
+  // world model and the actor; transposed weights; world_model.py:172, rssm.py:135)
+  const uint32_t zero16 = add_vec(pk, nul, nul, 0, 0, 16);   // epilogues without parameters still load 16 floats
+  // ---- dL/d(prior hidden) = g_out W2 (x ELU'(hid))
+  {
+    LLayerH L;
+    L.type = LB_ELU; L.dbuf = 1; L.out = G_GHID; L.nseg = 1; L.layer = F_HID;
+    tiles(Hdp, 256, 16, L.NT, L.n);
+    L.kc = kc_for(L.n);
+    L.w_off = pk.data_bytes;
+    for (int j = 0; j < L.NT; ++j) {
+      const size_t t0 = pk.data_bytes;
+      L.seg[0] = {G_GO, Pp / 16, L.n, 0, 0, 1, 0u};
+      RowSpec rs(j * L.n, d.Hd - j * L.n, L.n);
+      if (disc) l_add_pack_t(lp, rs, w ? w->prior2_w : nul, d.Hd, {{0, d.P, Pp}});
+      else l_add_pack_t(lp, rs, w ? w->prior2_w : nul, d.Hd, {{0, d.S, Sp}, {d.S, d.S, Sp}});
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+    }
+    L.ep_off = zero16; L.ep_floats = 0;
+    lp.blayers.push_back(L);
   }
+  // ---- dL/dh' = g_hid W1 + carried; GRU gate backward -> [g_n | g_r | g_z | g_n r]
+  {
+    LLayerH L;
+    L.type = LB_GRU; L.dbuf = 1; L.out = G_GATES_I; L.nseg = 1;
+    tiles(Dp, 128, 16, L.NT, L.n);
+    L.kc = kc_for(L.n);
+    L.w_off = pk.data_bytes;
+    for (int j = 0; j < L.NT; ++j) {
+      const size_t t0 = pk.data_bytes;
+      L.seg[0] = {G_GHID, Hdp / 16, L.n, 0, 0, 1, 0u};
+      l_add_pack_t(lp, RowSpec(j * L.n, d.D - j * L.n, L.n), w ? w->prior0_w : nul, d.D, {{0, d.Hd, Hdp}});
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+    }
+    L.ep_off = zero16; L.ep_floats = 0;
+    lp.blayers.push_back(L);
+  }
+  // ---- dL/dx = [g_n | g_r | g_z] W_ih (x ELU'(x))
+  {
+    LLayerH L;
+    L.type = LB_ELU; L.dbuf = 1; L.out = G_GX; L.nseg = 1; L.layer = F_X;
+    tiles(Dp, 256, 16, L.NT, L.n);
+    L.kc = kc_for(L.n);
+    L.w_off = pk.data_bytes;
+    for (int j = 0; j < L.NT; ++j) {
+      const size_t t0 = pk.data_bytes;
+      L.seg[0] = {G_GATES_I, 3 * Dp / 16, L.n, 0, 0, 1, 0u};
+      l_add_pack_t(lp, RowSpec(j * L.n, d.D - j * L.n, L.n), w ? w->w_ih : nul, d.D,
+                   {{2 * d.D, d.D, Dp}, {0, d.D, Dp}, {d.D, d.D, Dp}});
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+    }
+    L.ep_off = zero16; L.ep_floats = 0;
+    lp.blayers.push_back(L);
+  }
+  // ---- dL/dh_t = [g_r | g_z | g_n r] W_hh + dL/dh' z (+ upstream)
+  {
+    LLayerH L;
+    L.type = LB_CARRY; L.dbuf = 1; L.out = G_GX; L.nseg = 1;
+    tiles(Dp, 256, 16, L.NT, L.n);
+    L.kc = kc_for(L.n);
+    L.w_off = pk.data_bytes;
+    for (int j = 0; j < L.NT; ++j) {
+      const size_t t0 = pk.data_bytes;
+      L.seg[0] = {G_GATES_H, 3 * Dp / 16, L.n, 0, 0, 1, 0u};
+      l_add_pack_t(lp, RowSpec(j * L.n, d.D - j * L.n, L.n), w ? w->w_hh : nul, d.D,
+                   {{0, d.D, Dp}, {d.D, d.D, Dp}, {2 * d.D, d.D, Dp}});
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+    }
+    L.ep_off = zero16; L.ep_floats = 0;
+    lp.blayers.push_back(L);
+  }
+  // ---- [dL/ds_t | dL/da_t] = g_x W_e: latent column tiles, then ONE action tile (tanh-squash backward -> g_mu)
+  {
+    LLayerH L;
+    L.type = LB_EMB; L.dbuf = 1; L.out = G_GMU; L.nseg = 1;
+    int nts;
+    tiles(Sip, 256, 16, nts, L.n);
+    L.NT = nts + 1;
+    L.kc = kc_for(L.n);
+    L.w_off = pk.data_bytes;
+    const int Ke = d.S_in + d.A;
+    for (int j = 0; j < L.NT; ++j) {
+      const size_t t0 = pk.data_bytes;
+      L.seg[0] = {G_GX, Dp / 16, L.n, 0, 0, 1, 0u};
+      RowSpec rs = (j < nts) ? RowSpec(j * L.n, d.S_in - j * L.n, L.n) : RowSpec(d.S_in, d.A, L.n);
+      l_add_pack_t(lp, rs, w ? w->embed_w : nul, Ke, {{0, d.D, Dp}});
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+    }
+    L.ep_off = add_vec(pk, aw ? aw->bound : nul, nul, 0, d.A, 16); L.ep_floats = 0;   // ep_floats 0: same block for every tile
+    lp.blayers.push_back(L);
+  }
+  // ---- actor: dL/dy_{L-1} = g_mu W_mu, then per block LayerNorm+ELU backward and dL/dy_{l-1} = g_pre_l W_l
+  for (int l = d.La - 1; l >= 0; --l) {
+    LLayerH L;
+    L.type = LB_LN; L.NT = 1; L.n = d.Ha; L.dbuf = d.Ha <= 256 ? 1 : 0; L.out = G_GP0 + l; L.layer = l; L.nseg = 1;
+    L.kc = kc_for(d.Ha);
+    L.w_off = pk.data_bytes;
+    if (l == d.La - 1) {
+      L.seg[0] = {G_GMU, 1, d.Ha, 0, 0, 1, 0u};
+      l_add_pack_t(lp, RowSpec(0, d.Ha, d.Ha), aw ? aw->mu_w : nul, d.Ha, {{0, d.A, 16}});
+    } else {
+      L.seg[0] = {G_GP0 + l + 1, d.Ha / 16, d.Ha, 0, 0, 1, 0u};
+      l_add_pack_t(lp, RowSpec(0, d.Ha, d.Ha), aw ? aw->lin_w[l + 1] : nul, d.Ha, {{0, d.Ha, d.Ha}});
+    }
+    L.w_tile_bytes = (uint32_t)(pk.data_bytes - L.w_off);
+    L.ep_off = add_vec(pk, aw ? aw->ln_g[l] : nul, nul, 0, d.Ha, d.Ha, 1.4426950408889634f);
+    add_vec(pk, aw ? aw->ln_b[l] : nul, nul, 0, d.Ha, d.Ha, 1.4426950408889634f);
+    add_vec(pk, aw ? aw->ln_g[l] : nul, nul, 0, d.Ha, d.Ha);
+    L.ep_floats = 3u * d.Ha;
+    lp.blayers.push_back(L);
+  }
+  for (const std::vector<LLayerH>* v : {&lp.layers, &lp.blayers})
+    for (const LLayerH& L : *v) {
+      if (L.ep_floats * 4 > kLParamBytes || (L.ep_floats & 3)) return lp;
+      for (int s = 0; s < L.nseg; ++s)
+        if ((uint32_t)L.kc * (4096u + (uint32_t)L.seg[s].n * 32u) > kLSlotBytes) return lp;
+    }
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   pk.off_stage_tab = 256;
   pk.off_job_tab = 512;
@@ -898,19 +1537,70 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
   return lp;
 }
 
+// ---- memory layout.  Every panel buffer is [steps][MT][cols/8][2 KB]; the forward fields live in the workspace
+// (one step, the h / s panels two) or, when recording for the BPTT, in `saved` with one entry per step.
+struct Region { size_t off = 0; uint32_t tile_bytes = 0; size_t step_bytes = 0; int steps = 0; int where = 0; };   // where: 0 ws, 1 saved
+struct LMem {
+  Region r[BUF_COUNT];
+  size_t carry_h = 0, carry_s = 0;   // fp32 [MT*128][Dp] / [MT*128][Sip] in the backward workspace
+  size_t ws_bytes = 0, saved_bytes = 0;
+};
+constexpr size_t kLTraceBytes = 8192;
+// mode 0: forward, nothing recorded; 1: forward, recording; 2: backward (forward fields resolve into `saved`)
+static LMem tcl_layout(const LPlan& lp, const Dims& d, int mode) {
+  LMem m;
+  const int MT = (d.B + 127) / 128, T = d.T;
+  size_t off[2] = {kLTraceBytes, 0};
+  auto place = [&](int buf, int steps, int where, size_t row_bytes = 0) {
+    Region& r = m.r[buf];
+    r.tile_bytes = row_bytes ? (uint32_t)(128 * row_bytes) : (uint32_t)(buf_width(lp, buf) / 8) * kLTileChunk;
+    r.step_bytes = (size_t)MT * r.tile_bytes;
+    r.steps = steps; r.where = where;
+    r.off = off[where];
+    off[where] += ((size_t)steps * r.step_bytes + 1023) / 1024 * 1024;
+  };
+  const bool rec = mode != 0;
+  const int sv = rec ? 1 : 0;
+  place(F_H, rec ? T + 1 : 2, sv);
+  place(F_S, rec ? T + 1 : 1, sv);
+  if (mode != 2) place(F_A, 1, 0);
+  place(F_X, rec ? T : 1, sv);
+  place(F_HID, rec ? T : 1, sv);
+  for (int l = 0; l < d.La; ++l) place(F_Y0 + l, rec ? T : 1, sv);
+  if (rec) {
+    for (int f : {F_GR, F_GZ, F_GN, F_GHN}) place(f, T, 1);
+    for (int l = 0; l < d.La; ++l) { place(F_XH0 + l, T, 1); place(F_RSTD0 + l, T, 1, sizeof(float)); }
+  }
+  if (mode == 2) {
+    place(G_GO, 1, 0); place(G_GHID, 1, 0); place(G_GATES_I, 1, 0); place(G_GX, 1, 0);
+    m.r[G_GATES_H] = m.r[G_GATES_I];
+    m.r[G_GATES_H].off += (size_t)(lp.Dp / 8) * kLTileChunk;
+    place(G_GMU, T, 0);
+    for (int l = 0; l < d.La; ++l) { place(G_GP0 + l, T, 0); place(G_GU0 + l, T, 0); }
+    m.carry_h = off[0]; off[0] += ((size_t)MT * 128 * lp.Dp * 4 + 1023) / 1024 * 1024;
+    m.carry_s = off[0]; off[0] += ((size_t)MT * 128 * lp.Sip * 4 + 1023) / 1024 * 1024;
+  }
+  m.r[F_HN] = m.r[F_H]; m.r[F_SN] = m.r[F_S];
+  m.ws_bytes = off[0] + 1024;
+  m.saved_bytes = off[1] + 1024;
+  return m;
+}
+
 bool tcl_supported(const Dims& d) { return tcl_make_plan(d, nullptr, nullptr).ok; }
+bool tcl_train_supported(const Dims& d) { return tcl_supported(d); }
 size_t tcl_packed_bytes(const Dims& d) {
   LPlan lp = tcl_make_plan(d, nullptr, nullptr);
   return lp.ok ? lp.pk.total_bytes : 0;
 }
-static size_t buf_bytes(const LPlan& lp, int buf, int MT) { return (size_t)MT * (lp.width[buf] / 8) * kLTileChunk; }
 size_t tcl_workspace_bytes(const Dims& d) {
   LPlan lp = tcl_make_plan(d, nullptr, nullptr);
   if (!lp.ok) return 0;
-  const int MT = (d.B + 127) / 128;
-  size_t n = 8192;
-  for (int b = 0; b < BUF_COUNT; ++b) n += buf_bytes(lp, b, MT) + 1024;
-  return n;
+  const int mode = (d.flags & WMRL_FLAG_BACKWARD) ? 2 : ((d.flags & WMRL_FLAG_SAVE_FOR_BWD) ? 1 : 0);
+  return tcl_layout(lp, d, mode).ws_bytes;
+}
+size_t tcl_saved_bytes(const Dims& d) {
+  LPlan lp = tcl_make_plan(d, nullptr, nullptr);
+  return lp.ok ? tcl_layout(lp, d, 1).saved_bytes : 0;
 }
 int tcl_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_params* aw, void* packed,
                      cudaStream_t st) {
@@ -919,86 +1609,237 @@ int tcl_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_
   return tc_pack_plan(lp.pk, (uint8_t*)packed, st);
 }
 
-int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, const float* stoch0, const float* noise,
-                    float* deter_seq, float* stoch_seq, float* dist_a, float* dist_b, float* actions, int32_t* idx,
-                    void* ws, cudaStream_t st) {
-  LPlan lp = tcl_make_plan(d, nullptr, nullptr);
-  WMRL_REQUIRE(lp.ok, "imagine_fwd: shape not supported by the layer-wise tcgen05 path");
+static int tcl_device_setup(int& nsm) {
   static std::mutex mu;
   static bool attr_set[64] = {false};
-  int dev = 0, nsm = 148;
-  WMRL_CUDA_OK(cudaGetDevice(&dev));
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-      for (int ty = LE_LN_ELU; ty <= LE_SAMPLE_CONT; ++ty)
-        for (int S : {4, 8, 16, 32}) {
-          if (ty != LE_SAMPLE_DISC && S != 4) continue;
-          WMRL_CUDA_OK(cudaFuncSetAttribute(layer_kernel_for(ty, S), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)kLSmemBytes));
-        }
-      attr_set[dev] = true;
-    }
-  }
   static int sm_cached[64] = {0};
-  if (dev >= 0 && dev < 64) {
-    if (!sm_cached[dev]) WMRL_CUDA_OK(cudaDeviceGetAttribute(&sm_cached[dev], cudaDevAttrMultiProcessorCount, dev));
-    nsm = sm_cached[dev];
+  int dev = 0;
+  WMRL_CUDA_OK(cudaGetDevice(&dev));
+  WMRL_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
+  std::lock_guard<std::mutex> lk(mu);
+  if (!attr_set[dev]) {
+    for (int ty = LE_LN_ELU; ty <= LB_LN; ++ty)
+      for (int S : {4, 8, 16, 32}) {
+        if (ty != LE_SAMPLE_DISC && S != 4) continue;
+        WMRL_CUDA_OK(cudaFuncSetAttribute(layer_kernel_for(ty, S), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kLSmemBytes));
+      }
+    WMRL_CUDA_OK(cudaFuncSetAttribute(tcl_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWg2Smem));
+    WMRL_CUDA_OK(cudaDeviceGetAttribute(&sm_cached[dev], cudaDevAttrMultiProcessorCount, dev));
+    attr_set[dev] = true;
   }
-  const int MT = (d.B + 127) / 128;
+  nsm = sm_cached[dev];
+  return 0;
+}
+
+struct LCall {            // what the launch helper needs to resolve a layer description into kernel arguments
+  const LPlan* lp; const LMem* m; const Dims* d;
+  uint8_t* ws; uint8_t* saved;
+  const uint8_t* data; const float* ep;
+  int MT, nsm;
+  cudaStream_t st;
+  uint8_t* at(int buf, int step) const {
+    const Region& r = m->r[buf];
+    return (r.where ? saved : ws) + r.off + (size_t)step * r.step_bytes;
+  }
+};
+static int tcl_launch(const LCall& c, const LLayerH& L, LayerArgs& a, const int* seg_step, int out_step) {
+  const LPlan& lp = *c.lp;
+  const Dims& d = *c.d;
+  a.nseg = L.nseg;
+  for (int s = 0; s < L.nseg; ++s) {
+    const int buf = L.seg[s].buf;
+    a.seg[s].a = c.at(buf, seg_step[s]);
+    a.seg[s].a_tile_bytes = c.m->r[buf].tile_bytes;
+    a.seg[s].w_off = L.seg[s].w_off;
+    a.seg[s].k16 = (uint16_t)L.seg[s].k16; a.seg[s].n = (uint16_t)L.seg[s].n;
+    a.seg[s].tmem_col = (uint16_t)L.seg[s].tmem_col; a.seg[s].split = (uint16_t)L.seg[s].split;
+    a.seg[s].fresh = (uint16_t)L.seg[s].fresh;
+  }
+  a.w = c.data + L.w_off; a.w_tile_bytes = L.w_tile_bytes;
+  a.ep = c.ep + L.ep_off; a.ep_floats = L.ep_floats;
+  a.kc = L.kc; a.dbuf = L.dbuf; a.type = L.type; a.n = L.n; a.NT = L.NT; a.MT = c.MT;
+  a.B = d.B; a.H = d.T; a.D = d.D; a.S = d.S; a.C = d.C; a.A = d.A; a.Sp = lp.Sp; a.Dp = lp.Dp; a.Sip = lp.Sip;
+  a.inv_action_scale = 1.f / d.action_scale;
+  a.out = c.at(L.out, out_step); a.out_tile_bytes = c.m->r[L.out].tile_bytes; a.out_cols = buf_width(lp, L.out);
+  const int items = c.MT * L.NT;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)std::min(items, c.nsm));
+  cfg.blockDim = dim3(kLThreads);
+  cfg.dynamicSmemBytes = kLSmemBytes;
+  cfg.stream = c.st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, layer_kernel_for(L.type, d.S), a));
+  return 0;
+}
+
+int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, const float* stoch0, const float* noise,
+                    float* deter_seq, float* stoch_seq, float* dist_a, float* dist_b, float* actions, int32_t* idx,
+                    void* saved, void* ws, cudaStream_t st) {
+  LPlan lp = tcl_make_plan(d, nullptr, nullptr);
+  WMRL_REQUIRE(lp.ok, "imagine_fwd: shape not supported by the layer-wise tcgen05 path");
+  const bool rec = saved != nullptr;
+  const LMem m = tcl_layout(lp, d, rec ? 1 : 0);
+  LCall c{&lp, &m, &d, (uint8_t*)ws, (uint8_t*)saved, nullptr, nullptr, (d.B + 127) / 128, 148, st};
+  if (int r = tcl_device_setup(c.nsm)) return r;
   const uint8_t* img = (const uint8_t*)packed;
-  const uint8_t* data = img + lp.pk.off_data;
-  const float* ep = (const float*)(img + lp.pk.off_eparams);
-  uint8_t* bufs[BUF_COUNT];
-  {
-    uint8_t* p = (uint8_t*)(((uintptr_t)ws + 4096 + 1023) / 1024 * 1024);
-    for (int b = 0; b < BUF_COUNT; ++b) { bufs[b] = p; p += (buf_bytes(lp, b, MT) + 1023) / 1024 * 1024; }
-  }
-  long long* trace_base = (long long*)ws;   // the first 1 KB of the workspace (the panels start 1 KB-aligned after it)
-  tcl_init_kernel<<<dim3(8, MT), 256, 0, st>>>(deter0, stoch0, deter_seq, stoch_seq, bufs[BUF_H0], bufs[BUF_S], d.B, d.T,
-                                               d.D, d.S_in, lp.Dp, lp.Sip);
+  c.data = img + lp.pk.off_data;
+  c.ep = (const float*)(img + lp.pk.off_eparams);
+  long long* trace_base = (long long*)ws;   // the first 8 KB of the workspace
+  tcl_init_kernel<<<dim3(8, c.MT), 256, 0, st>>>(deter0, stoch0, deter_seq, stoch_seq, c.at(F_H, 0), c.at(F_S, 0), d.B, d.T,
+                                                 d.D, d.S_in, lp.Dp, lp.Sip);
   WMRL_CUDA_OK(cudaGetLastError());
   for (int t = 0; t < d.T; ++t) {
-    const int hcur = (t & 1) ? BUF_H1 : BUF_H0, hnext = (t & 1) ? BUF_H0 : BUF_H1;
+    // step index of each field: recorded fields are indexed by t (h, s: t -> t + 1); otherwise one entry (h: parity)
+    auto step_of = [&](int buf) {
+      if (buf == F_H) return rec ? t : (t & 1);
+      if (buf == F_HN) return rec ? t + 1 : ((t + 1) & 1);
+      if (buf == F_S) return rec ? t : 0;
+      if (buf == F_SN) return rec ? t + 1 : 0;
+      if (buf == F_A) return 0;
+      return rec ? t : 0;
+    };
     for (const LLayerH& L : lp.layers) {
       LayerArgs a{};
-      a.nseg = L.nseg;
-      for (int s = 0; s < L.nseg; ++s) {
-        int buf = L.seg[s].buf;
-        if (buf == BUF_H0) buf = hcur; else if (buf == BUF_H1) buf = hnext;
-        a.seg[s].a = bufs[buf];
-        a.seg[s].a_tile_bytes = (uint32_t)(lp.width[buf] / 8) * kLTileChunk;
-        a.seg[s].w_off = L.seg[s].w_off;
-        a.seg[s].k16 = (uint16_t)L.seg[s].k16; a.seg[s].n = (uint16_t)L.seg[s].n;
-        a.seg[s].tmem_col = (uint16_t)L.seg[s].tmem_col; a.seg[s].split = (uint16_t)L.seg[s].split;
-        a.seg[s].fresh = (uint16_t)L.seg[s].fresh;
-      }
-      a.w = data + L.w_off; a.w_tile_bytes = L.w_tile_bytes;
-      a.ep = ep + L.ep_off; a.ep_floats = L.ep_floats;
-      a.kc = L.kc; a.dbuf = L.dbuf; a.type = L.type; a.n = L.n; a.NT = L.NT; a.MT = MT;
-      a.B = d.B; a.H = d.T; a.t = t; a.D = d.D; a.S = d.S; a.C = d.C; a.A = d.A; a.Sp = lp.Sp; a.Dp = lp.Dp;
-      a.inv_action_scale = 1.f / d.action_scale;
-      int ob = L.out;
-      if (ob == BUF_H1) ob = hnext;
-      a.out = bufs[ob]; a.out_tile_bytes = (uint32_t)(lp.width[ob] / 8) * kLTileChunk; a.out_cols = lp.width[ob];
+      a.t = t;
       a.deter_seq = deter_seq; a.stoch_seq = stoch_seq; a.dist_a = dist_a; a.dist_b = dist_b; a.actions = actions;
       a.idx = idx; a.noise = noise;
+      a.save = rec ? 1 : 0;
+      if (rec && L.type == LE_LN_ELU) {
+        a.aux[0] = c.at(F_XH0 + L.layer, t); a.aux_tile_bytes = m.r[F_XH0 + L.layer].tile_bytes;
+        a.f0 = (float*)c.at(F_RSTD0 + L.layer, t);
+      }
+      if (rec && L.type == LE_GRU) {
+        a.aux[0] = c.at(F_GR, t); a.aux[1] = c.at(F_GZ, t); a.aux[2] = c.at(F_GN, t); a.aux[3] = c.at(F_GHN, t);
+        a.aux_tile_bytes = m.r[F_GR].tile_bytes;
+      }
       a.trace = nullptr;
       if ((d.flags & WMRL_FLAG_TRACE) && t == std::min(1, d.T - 1)) a.trace = trace_base + 32 * (&L - &lp.layers[0]);
-      const int items = MT * L.NT;
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((unsigned)std::min(items, nsm));
-      cfg.blockDim = dim3(kLThreads);
-      cfg.dynamicSmemBytes = kLSmemBytes;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, layer_kernel_for(L.type, d.S), a));
+      int ss[3];
+      for (int s = 0; s < L.nseg; ++s) ss[s] = step_of(L.seg[s].buf);
+      if (int r = tcl_launch(c, L, a, ss, step_of(L.out))) return r;
     }
   }
+  return 0;
+}
+
+// BPTT over the recorded rollout (autograd of rssm.py:123-140 with the world model frozen and the actor input
+// detached).  Per step, backwards in time: sample backward (SIMT) -> 5 dgrad GEMMs through the dynamics with fused
+// ELU' / GRU-gate / tanh-squash backward -> La dgrad GEMMs through the actor with fused LayerNorm+ELU backward; then the
+// actor weight gradients as big-K tcgen05 GEMMs over the recorded panels and column sums for the bias / affine terms.
+int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const float* deter_seq, const float* dist_a,
+                    const float* dist_b, const float* actions, const void* saved, const float* g_deter_seq,
+                    const float* g_stoch_seq, const float* g_dist_a, const float* g_dist_b, const wmrl_actor_grads* gaw,
+                    float* g_deter0, float* g_stoch0, void* ws, cudaStream_t st) {
+  LPlan lp = tcl_make_plan(d, nullptr, nullptr);
+  WMRL_REQUIRE(lp.ok, "imagine_bwd: shape not supported by the layer-wise tcgen05 path");
+  const LMem m = tcl_layout(lp, d, 2);
+  LCall c{&lp, &m, &d, (uint8_t*)ws, (uint8_t*)const_cast<void*>(saved), nullptr, nullptr, (d.B + 127) / 128, 148, st};
+  if (int r = tcl_device_setup(c.nsm)) return r;
+  const uint8_t* img = (const uint8_t*)packed;
+  c.data = img + lp.pk.off_data;
+  c.ep = (const float*)(img + lp.pk.off_eparams);
+  const int T = d.T, MT = c.MT;
+  const bool disc = d.variant == WMRL_DISCRETE;
+  float* carry_h = (float*)((uint8_t*)ws + m.carry_h);
+  float* carry_s = (float*)((uint8_t*)ws + m.carry_s);
+  {
+    const long long n = (long long)MT * 128 * lp.Dp;
+    tcl_carry_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(carry_h, g_deter_seq, d.B, T, d.D, lp.Dp, n);
+    WMRL_CUDA_OK(cudaGetLastError());
+  }
+  for (int t = T - 1; t >= 0; --t) {
+    // dL/d(head output) of the step that produced state t+1
+    {
+      SbArgs s{};
+      s.carry_s = (t < T - 1) ? carry_s : nullptr; s.g_stoch = g_stoch_seq; s.g_da = g_dist_a; s.g_db = g_dist_b;
+      s.dist_a = dist_a; s.dist_b = dist_b; s.noise = noise; s.out = c.at(G_GO, 0);
+      s.B = d.B; s.H = T; s.t = t; s.S = d.S; s.C = d.C; s.Sp = lp.Sp; s.Sip = lp.Sip; s.Pp = lp.Pp; s.MT = MT;
+      if (disc) {
+        const long long nw = (long long)MT * 128 * d.C;
+        tcl_sample_bwd_disc_kernel<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, st>>>(s);
+      } else {
+        const long long n = (long long)MT * 128 * (lp.Sp / 8);
+        tcl_sample_bwd_cont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s);
+      }
+      WMRL_CUDA_OK(cudaGetLastError());
+    }
+    for (const LLayerH& L : lp.blayers) {
+      LayerArgs a{};
+      a.t = t;
+      a.deter_seq = const_cast<float*>(deter_seq); a.actions = const_cast<float*>(actions);
+      int out_step = 0;
+      switch (L.type) {
+        case LB_ELU:
+          a.aux[0] = c.at(L.layer, t); a.aux_tile_bytes = m.r[L.layer].tile_bytes;
+          break;
+        case LB_GRU:
+          a.aux[0] = c.at(F_GR, t); a.aux[1] = c.at(F_GZ, t); a.aux[2] = c.at(F_GN, t); a.aux[3] = c.at(F_GHN, t);
+          a.aux_tile_bytes = m.r[F_GR].tile_bytes;
+          a.f0 = carry_h;
+          break;
+        case LB_CARRY:
+          a.f0 = carry_h; a.f1 = const_cast<float*>(g_deter_seq); a.f2 = g_deter0;
+          break;
+        case LB_EMB:
+          a.f0 = carry_s; a.f1 = const_cast<float*>(g_stoch_seq); a.f2 = g_stoch0;
+          out_step = t;
+          break;
+        case LB_LN:
+          a.aux[0] = c.at(F_XH0 + L.layer, t); a.aux[1] = c.at(G_GU0 + L.layer, t); a.aux_tile_bytes = m.r[F_XH0 + L.layer].tile_bytes;
+          a.f0 = (float*)c.at(F_RSTD0 + L.layer, t);
+          out_step = t;
+          break;
+      }
+      int ss[3] = {0, 0, 0};
+      if (L.seg[0].buf == G_GMU || L.seg[0].buf >= G_GP0) ss[0] = t;
+      if (int r = tcl_launch(c, L, a, ss, out_step)) return r;
+    }
+  }
+  // ---- weight gradients: dW[out][in] += sum over (step, row tile) of G^T X, both operands straight from the panels
+  const int nblk = T * MT;
+  auto wgrad = [&](int abuf, int m_cols, int m_valid, int bbuf, int n_cols, int n_valid, float* dW, int ldw) -> int {
+    if (!dW) return 0;
+    Wg2Params q{};
+    q.a_base = c.at(abuf, 0); q.a_blk = m.r[abuf].tile_bytes; q.b_base = c.at(bbuf, 0); q.b_blk = m.r[bbuf].tile_bytes;
+    q.nblocks = nblk; q.m_cols = m_cols; q.m_valid = m_valid; q.n_cols = n_cols; q.n_valid = n_valid;
+    q.dW = dW; q.ldw = ldw;
+    q.mtiles = (m_cols + 127) / 128; q.ntiles = (n_cols + 255) / 256;
+    const int tl = q.mtiles * q.ntiles;
+    q.splits = std::max(1, std::min(nblk, c.nsm / tl));
+    tcl_wgrad_kernel<<<dim3(tl, q.splits), kWg2Threads, kWg2Smem, st>>>(q);
+    WMRL_CUDA_OK(cudaGetLastError());
+    return 0;
+  };
+  auto colsum = [&](int xbuf, int ybuf, int cols, int valid, float* out) -> int {
+    if (!out) return 0;
+    Cs2Params q{};
+    q.x_base = c.at(xbuf, 0); q.x_blk = m.r[xbuf].tile_bytes;
+    q.y_base = ybuf >= 0 ? c.at(ybuf, 0) : nullptr; q.y_blk = ybuf >= 0 ? m.r[ybuf].tile_bytes : 0;
+    q.nblocks = nblk; q.valid = valid; q.out = out;
+    const int chunks = cols / 8;
+    const int ysplit = std::max(1, std::min((nblk + kCs2Warps - 1) / kCs2Warps, (8 * c.nsm + chunks - 1) / chunks));
+    tcl_colsum_kernel<<<dim3(chunks, ysplit), kCs2Warps * 32, 0, st>>>(q);
+    WMRL_CUDA_OK(cudaGetLastError());
+    return 0;
+  };
+  for (int l = 0; l < d.La; ++l) {
+    if (l == 0) {
+      if (int r = wgrad(F_H, lp.Dp, d.D, G_GP0, d.Ha, d.Ha, gaw->lin_w[0], d.F)) return r;
+      if (int r = wgrad(F_S, lp.Sip, d.S_in, G_GP0, d.Ha, d.Ha, gaw->lin_w[0] ? gaw->lin_w[0] + d.D : nullptr, d.F)) return r;
+    } else {
+      if (int r = wgrad(F_Y0 + l - 1, d.Ha, d.Ha, G_GP0 + l, d.Ha, d.Ha, gaw->lin_w[l], d.Ha)) return r;
+    }
+    if (int r = colsum(G_GP0 + l, -1, d.Ha, d.Ha, gaw->lin_b[l])) return r;
+    if (int r = colsum(G_GU0 + l, -1, d.Ha, d.Ha, gaw->ln_b[l])) return r;
+    if (int r = colsum(G_GU0 + l, F_XH0 + l, d.Ha, d.Ha, gaw->ln_g[l])) return r;
+  }
+  if (int r = wgrad(F_Y0 + d.La - 1, d.Ha, d.Ha, G_GMU, 16, d.A, gaw->mu_w, d.Ha)) return r;
+  if (int r = colsum(G_GMU, -1, 16, d.A, gaw->mu_b)) return r;
   return 0;
 }
 
