@@ -425,40 +425,114 @@ def aux_all_ranks(c, rssm, actor, dev, world, rank, barrier):
     return out
 
 
-def aux_configs(dev):
-    """Informational, outside the timed region: BASELINE configs[1] (discrete D600/32x32, 2500 start states,
-    H=15) forward + hand-written actor-BPTT backward through the fp32 CUDA path, as latent-steps/s."""
+def _discrete_problem(dev, B, H, D, S, C, A, precision, seed=0):
     import wmrl
-    torch.manual_seed(0)
-    B, H, D, S, C, A = 2500, 15, 600, 32, 32, 6
-    rssm = wmrl.DiscreteRSSM(D, D, S, C, 1024, A).to(dev)
+    torch.manual_seed(seed)
+    rssm = wmrl.DiscreteRSSM(D, D, S, C, 1024, A, precision=precision).to(dev)
     actor = wmrl.Actor(D + S * C, A, 1.0, 3, 512).to(dev)
     for p_ in rssm.parameters():
         p_.requires_grad_(False)
-    g = torch.Generator().manual_seed(1)
+    g = torch.Generator().manual_seed(1 + seed)
     d0 = torch.tanh(torch.randn(B, D, generator=g)).to(dev)
     s0 = torch.nn.functional.one_hot(torch.randint(0, S, (B, C), generator=g), S).float().reshape(B, C * S).to(dev)
     init = wmrl.InternalStateDiscrete(d0, s0, torch.randn(B, C, S, generator=g).to(dev))
-    q = torch.empty(H, B, C, S).exponential_(1.0, generator=g).to(dev)
-    gf = torch.randn(B, H, D + S * C, generator=g).to(dev) / B
+    gf = torch.randn(B, 1, D + S * C, generator=g).to(dev) / B
+    return rssm, actor, init, gf
 
-    def step():
-        actor.zero_grad(set_to_none=True)
-        seq = rssm.imagine_rollout(init, actor, H, noise=q)
-        (seq.get_features() * gf).sum().backward()
 
-    for _ in range(2):
-        step()
+def _event_ms(fn, n, warm=2):
+    for _ in range(warm):
+        fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(3):
-        step()
+    for _ in range(n):
+        fn()
     b.record()
     torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / 3
-    return {"configs[1] discrete D600 32x32, 2500x15, fwd + actor-BPTT bwd, fp32 CUDA path":
-            {"ms": ms, "latent_steps_per_s": B * H / ms * 1e3, "flops_per_latent_step_fwd_bwd": 21499712}}
+    return a.elapsed_time(b) / n
+
+
+def aux_configs(dev):
+    """Informational, outside the timed region: BASELINE configs[1] (discrete D600/32x32, 2500 start states, H=15),
+    forward and forward + actor-BPTT backward, on the bf16 layer-wise tcgen05 chain and on the fp32 validation chain
+    (same module, same call; noise drawn inside as the reference does)."""
+    B, H, D, S, C, A = 2500, 15, 600, 32, 32, 6
+    FL_F, FL_FB = 10222496, 21499712          # SURVEY 8d, algorithmic FLOPs per latent step
+    peaks, _ = measured_peaks()
+    burst = float(peaks.get("bf16_tflops", 1628.3))
+    out = {}
+    for prec in ("bf16", "fp32"):
+        rssm, actor, init, gf = _discrete_problem(dev, B, H, D, S, C, A, prec)
+
+        def fwd():
+            with torch.no_grad():
+                rssm.imagine_rollout(init, actor, H)
+
+        def step():
+            actor.zero_grad(set_to_none=True)
+            seq = rssm.imagine_rollout(init, actor, H)
+            (seq.get_features() * gf).sum().backward()
+
+        f_ms, t_ms = _event_ms(fwd, 10), _event_ms(step, 5)
+        out[f"configs[1] discrete D600 32x32, 2500x15, {prec}"] = {
+            "fwd_ms": f_ms, "fwd_latent_steps_per_s": B * H / f_ms * 1e3, "fwd_tflops": FL_F * B * H / f_ms / 1e9,
+            "fwd_bwd_ms": t_ms, "fwd_bwd_latent_steps_per_s": B * H / t_ms * 1e3,
+            "fwd_bwd_tflops": FL_FB * B * H / t_ms / 1e9, "fwd_bwd_frac_of_bf16_burst": FL_FB * B * H / t_ms / 1e9 / burst,
+            "flops_per_latent_step_fwd": FL_F, "flops_per_latent_step_fwd_bwd": FL_FB}
+        del rssm, actor, init, gf
+    return out
+
+
+def aux_configs4_shard(dev, world, rank, barrier):
+    """BASELINE configs[4] (discrete D1024 / hidden 1024 / 32x32, horizon 64, 65 536 start states over 8 GPUs): every
+    rank runs ITS 8 192-row shard - forward (recording) + bf16 BPTT + flat NCCL all-reduce of the actor gradients.
+    At --gpus 8 this is the named configuration; at fewer GPUs it is the same per-GPU shard (weak scaling)."""
+    import torch.distributed as dist
+    from wmrl.parallel import allreduce_gradients
+    B, H, D, S, C, A = 8192, 64, 1024, 32, 32, 6
+    FL_FB = 45131776
+    try:
+        rssm, actor, init, gf = _discrete_problem(dev, B, H, D, S, C, A, "bf16", seed=10 + rank)
+        gf = gf / world
+        ar = []
+
+        def step():
+            actor.zero_grad(set_to_none=True)
+            seq = rssm.imagine_rollout(init, actor, H)
+            (seq.get_features() * gf).sum().backward()
+            if world > 1:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                allreduce_gradients(actor.parameters(), average=False)
+                e1.record()
+                ar.append((e0, e1))
+
+        for _ in range(2):
+            step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            step()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b) / 3
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        peaks, _ = measured_peaks()
+        tf = FL_FB * B * H / ms / 1e9
+        arm = [x.elapsed_time(y) for x, y in ar[2:]]
+        return {"what": "discrete D1024/Hd1024/32x32, 8192 start states per GPU x H 64, forward (recording) + bf16 BPTT + "
+                        "weight-gradient GEMMs + flat NCCL all-reduce of the actor gradients (layer-wise tcgen05 chain)",
+                "global_start_states": B * world, "ms_per_step": ms, "latent_steps_per_s": world * B * H / ms * 1e3,
+                "tflops_per_gpu": tf, "frac_of_bf16_burst": tf / float(peaks.get("bf16_tflops", 1628.3)),
+                "flops_per_latent_step_fwd_bwd": FL_FB, "allreduce_ms_mean": (sum(arm) / len(arm)) if arm else 0.0,
+                "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    except RuntimeError as e:   # pragma: no cover
+        return {"error": str(e)[:300]}
 
 
 def workload_config(c, n_gpus):
@@ -616,6 +690,9 @@ def run_ours(args):
     aux_all = None
     if not args.no_aux:
         aux_all = aux_all_ranks(c, rssm, actor, dev, world, rank, barrier)
+        torch.cuda.empty_cache()
+        aux_all["configs[4] per-GPU shard, fwd+bwd+allreduce"] = aux_configs4_shard(dev, world, rank, barrier)
+        torch.cuda.empty_cache()
     if rank == 0:
         peaks, peaks_src = measured_peaks()
         fl = flops_per_latent_step(c)

@@ -43,6 +43,48 @@ def run(name, variant, D, S, C, Hd, A, Ha, La, B, H, iters=5, precision="bf16"):
     return out
 
 
+def flops_bwd(D, S_in, P, Hd, A, Ha, La):
+    F = D + S_in
+    actor = F * Ha + (La - 1) * Ha * Ha + Ha * A
+    dyn = (S_in + A) * D + 6 * D * D + D * Hd + Hd * P
+    return 2 * (dyn + 2 * actor - F * Ha)
+
+
+def run_train(name, variant, D, S, C, Hd, A, Ha, La, B, H, iters=5, precision="bf16"):
+    """forward (recording) + actor BPTT: d/d(actor params) of sum(features * g) with the world model frozen."""
+    rssm, actor = HG.build_modules(variant, D, S, C, Hd, 64, A, Ha, La, precision=precision)
+    for p in rssm.parameters():
+        p.requires_grad_(False)
+    d0, s0, nz = HG.synth_inputs(variant, B, H, D, S, C)
+    init = HG.init_state(rssm, d0, s0)
+    nz = nz.cuda()
+    S_in = S * C if variant == "discrete" else S
+    gfeat = torch.randn(B, 1, D + S_in, device="cuda") / B
+
+    def step():
+        actor.zero_grad(set_to_none=True)
+        seq = rssm.imagine_rollout(init, actor, H, noise=nz)
+        (seq.get_features() * gfeat).sum().backward()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    P = S_in if variant == "discrete" else 2 * S
+    fl = flops_fwd(D, S_in, P, Hd, A, Ha, La) + flops_bwd(D, S_in, P, Hd, A, Ha, La)
+    out = {"case": name + " fwd+bwd", "precision": precision, "ms": round(ms, 3), "latent_steps_per_s": B * H / ms * 1e3,
+           "tflops": fl * B * H / ms / 1e9, "flops_per_latent_step_fwd_bwd": fl,
+           "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2)}
+    print(json.dumps(out), flush=True)
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c5", "c2f32"]
     if "c2" in which:
@@ -51,5 +93,11 @@ if __name__ == "__main__":
         run("configs[1] discrete D600 32x32 2500x15", "discrete", 600, 32, 32, 600, 6, 512, 3, 2500, 15, iters=10, precision="fp32")
     if "c5" in which:
         run("configs[4] discrete D1024 32x32 8192x64 (one GPU's shard)", "discrete", 1024, 32, 32, 1024, 6, 512, 3, 8192, 64, iters=3)
+    if "c2t" in which:
+        run_train("configs[1] discrete D600 32x32 2500x15", "discrete", 600, 32, 32, 600, 6, 512, 3, 2500, 15, iters=10)
+    if "c2tf32" in which:
+        run_train("configs[1] discrete D600 32x32 2500x15", "discrete", 600, 32, 32, 600, 6, 512, 3, 2500, 15, iters=5, precision="fp32")
+    if "c5t" in which:
+        run_train("configs[4] discrete D1024 32x32 8192x64 (one GPU's shard)", "discrete", 1024, 32, 32, 1024, 6, 512, 3, 8192, 64, iters=2)
     if "c4" in which:   # continuous bench shape; WMRL_BF16_PATH=layer forces the chain
         run("configs[3] continuous 65536x15", "continuous", 200, 30, 1, 200, 6, 512, 3, 65536, 15, iters=5)
