@@ -38,6 +38,8 @@ def _setup(variant, D, S, C, Hd, A, Ha, La, seed=3):
 
 def _agree(name, got, ref, cos_min=COS_MIN, rel_max=REL_MAX):
     got, ref = got.detach().float().cpu().flatten(), ref.detach().float().cpu().flatten()
+    if got.numel() < 8:      # a lone scalar (mu.bias at A = 1) is one cancelling sum over B*H rows: no averaging
+        rel_max = max(rel_max, 6e-2)
     cos = float(got @ ref / (got.norm() * ref.norm() + 1e-30))
     rel = float((got - ref).norm() / (ref.norm() + 1e-30))
     assert cos >= cos_min and rel <= rel_max, f"{name}: cosine {cos:.6f}, relative error {rel:.3e}"

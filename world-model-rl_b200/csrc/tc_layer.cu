@@ -79,7 +79,7 @@ struct LayerArgs {
   int D, S, C, A, Sp, Dp, Sip;
   float inv_action_scale;
   int save;                // forward: record what the BPTT needs (LayerNorm x-hat + rstd, GRU r / z / n / h_n)
-  uint8_t* aux[4];         // extra panels (tile 0) an epilogue reads or writes: recorded activations, g_u
+  uint8_t* aux[5];         // extra panels (tile 0) an epilogue reads or writes: recorded activations, g_u
   uint32_t aux_tile_bytes;
   float *f0, *f1, *f2;     // extra fp32 tensors (rstd, carry rows, upstream / start-state gradients; see the epilogues)
   uint8_t* out;            // destination panel (tile 0)
@@ -481,122 +481,200 @@ __device__ __forceinline__ void l_unpack8(const uint4& u, float (&v)[8]) {
   }
 }
 
-// g = acc * ELU'(a), a = the recorded post-ELU activation (ELU'(z) = 1 for z > 0, else a + 1) -> panel
+// fp32 carry rows live in a panel layout of their own, [tile][col/4][128 rows][4 floats]: a warp's access to four
+// columns of its 32 rows is 512 contiguous bytes (the row-major form cost 32 LSU wavefronts per instruction)
+__device__ __forceinline__ float* fpanel(float* base, int mt, int Wp, int col, int row) {
+  return base + ((size_t)mt * (Wp / 4) + (col >> 2)) * 512 + row * 4;
+}
+// a 32-row x 32-column block of a row-major fp32 tensor (row r of this warp at row0 + r * ld) -> every thread gets
+// its own row's 32 values.  Coalesced: each LDG.128 covers 4 rows x 128 B; transposed through the warp's staging area.
+__device__ __forceinline__ void load_rows32(const LCtx& c, const float* row0, long long ld, int nrows_valid, int ncols_valid,
+                                            float (&out)[32]) {
+  const int sub = c.lane >> 3, chunk = c.lane & 7;
+  float4 t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + sub;
+    t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nrows_valid && chunk * 4 < ncols_valid) {
+      const float* src = row0 + (long long)r * ld + chunk * 4;
+      if (chunk * 4 + 4 <= ncols_valid && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) t[i] = *reinterpret_cast<const float4*>(src);
+      else {
+        t[i].x = src[0];
+        if (chunk * 4 + 1 < ncols_valid) t[i].y = src[1];
+        if (chunk * 4 + 2 < ncols_valid) t[i].z = src[2];
+        if (chunk * 4 + 3 < ncols_valid) t[i].w = src[3];
+      }
+    }
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = t[half * 4 + i];
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_addr(c.stage, i * 4 + sub, chunk)), "f"(v.x), "f"(v.y),
+                   "f"(v.z), "f"(v.w) : "memory");
+    }
+    __syncwarp();
+    if ((c.lane >> 4) == half) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 v = lds4(stage_addr(c.stage, c.lane & 15, k));
+        out[4 * k] = v.x; out[4 * k + 1] = v.y; out[4 * k + 2] = v.z; out[4 * k + 3] = v.w;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// g = acc * ELU'(a), a = the recorded post-ELU activation (ELU'(z) = 1 for z > 0, else a + 1) -> panel.
+// 32 columns per iteration with every global load in flight before the first use.
 __device__ __forceinline__ void lepib_elu(const LCtx& c) {
   const LayerArgs& p = *c.p;
   const uint8_t* arow = p.aux[0] + (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16;
-  for (int g = c.q; g < p.n / 8; g += 4) {
-    const int col = c.nt * p.n + g * 8;
+  for (int blk = c.q; blk * 32 < p.n; blk += 4) {
+    const int col = c.nt * p.n + blk * 32;
     if (col >= p.out_cols) break;
-    float v[8], a[8];
-    tmem_ld8(c.tmem_lane + g * 8, v);
-    const uint4 au = l_ldg16(arow + (size_t)(col / 8) * kLTileChunk);
-    l_unpack8(au, a);
+    float v[32];
+    tmem_ld32(c.tmem_lane + blk * 32, v);
+    uint4 au[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool in = blk * 32 + k * 8 < p.n && col + k * 8 < p.out_cols;
+      au[k] = in ? l_ldg16(arow + (size_t)(col / 8 + k) * kLTileChunk) : make_uint4(0, 0, 0, 0);
+    }
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = c.valid ? v[i] * ((a[i] > 0.f) ? 1.f : (a[i] + 1.f)) : 0.f;
-    st_chunk_g(c.out_row + (size_t)(col / 8) * kLTileChunk, v);
+    for (int k = 0; k < 4; ++k) {
+      if (blk * 32 + k * 8 < p.n && col + k * 8 < p.out_cols) {
+        float a[8], o[8];
+        l_unpack8(au[k], a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = c.valid ? v[k * 8 + i] * ((a[i] > 0.f) ? 1.f : (a[i] + 1.f)) : 0.f;
+        st_chunk_g(c.out_row + (size_t)(col / 8 + k) * kLTileChunk, o);
+      }
+    }
   }
 }
 
-// GRUCell backward (h' = (1-z) n + z h, n = tanh(i_n + r h_n)): accumulator = g_hid W1; f0 = the fp32 carry rows
-// [MT*128][Dp] holding the rest of dL/dh'.  Writes the gate-gradient panel [g_n | g_r | g_z | g_n r] and leaves the
-// direct term dL/dh' z in the carry row.
+// GRUCell backward (h' = (1-z) n + z h, n = tanh(i_n + r h_n)): accumulator = g_hid W1; f0 = the fp32 carry panel
+// holding the rest of dL/dh'.  aux[0..3] = recorded r, z, n, h_n; aux[4] = the recorded h_t panel.  Writes the
+// gate-gradient panel [g_n | g_r | g_z | g_n r] and leaves the direct term dL/dh' z in the carry panel.
 __device__ __forceinline__ void lepib_gru(const LCtx& c) {
   const LayerArgs& p = *c.p;
-  const long long prow = (long long)c.mt * 128 + c.row;
   const size_t arow = (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16;
   const size_t fstride = (size_t)(p.Dp / 8) * kLTileChunk;
-  for (int g = c.q; g < p.n / 8; g += 4) {
-    const int col = c.nt * p.n + g * 8;
+  for (int g = c.q; g * 16 < p.n; g += 4) {
+    const int col = c.nt * p.n + g * 16;
     if (col >= p.Dp) break;
-    float acc[8], r[8], z[8], n[8], hn[8], cr[8], hp[8];
-    tmem_ld8(c.tmem_lane + g * 8, acc);
-    const size_t ao = arow + (size_t)(col / 8) * kLTileChunk;
-    const uint4 ur = l_ldg16(p.aux[0] + ao), uz = l_ldg16(p.aux[1] + ao), un = l_ldg16(p.aux[2] + ao), uh = l_ldg16(p.aux[3] + ao);
-    float* scr = p.f0 + prow * p.Dp + col;
-    const float4 c0 = *reinterpret_cast<const float4*>(scr), c1 = *reinterpret_cast<const float4*>(scr + 4);
-    cr[0] = c0.x; cr[1] = c0.y; cr[2] = c0.z; cr[3] = c0.w; cr[4] = c1.x; cr[5] = c1.y; cr[6] = c1.z; cr[7] = c1.w;
-    const float* hrow = p.deter_seq + (c.b * (p.H + 1) + p.t) * p.D + col;
+    float acc[16];
+    tmem_ld16(c.tmem_lane + g * 16, acc);
+    uint4 ur[2], uz[2], un[2], uh[2], up[2];
+    float4 cr[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) hp[i] = (c.valid && col + i < p.D) ? hrow[i] : 0.f;
-    l_unpack8(ur, r); l_unpack8(uz, z); l_unpack8(un, n); l_unpack8(uh, hn);
-    tmem_ld_wait();
-    float on[8], orr[8], oz[8], oh[8], od[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float gh = c.valid ? acc[i] + cr[i] : 0.f;
-      const float gn = gh * (1.f - z[i]);
-      const float gz = gh * (hp[i] - n[i]);
-      od[i] = gh * z[i];
-      const float gnp = gn * (1.f - n[i] * n[i]);
-      on[i] = gnp;
-      oz[i] = gz * z[i] * (1.f - z[i]);
-      oh[i] = gnp * r[i];
-      orr[i] = gnp * hn[i] * r[i] * (1.f - r[i]);
+    for (int k = 0; k < 2; ++k) {
+      const size_t ao = arow + (size_t)(col / 8 + k) * kLTileChunk;
+      ur[k] = l_ldg16(p.aux[0] + ao); uz[k] = l_ldg16(p.aux[1] + ao); un[k] = l_ldg16(p.aux[2] + ao); uh[k] = l_ldg16(p.aux[3] + ao);
+      up[k] = l_ldg16(p.aux[4] + ao);
     }
-    uint8_t* dst = c.out_row + (size_t)(col / 8) * kLTileChunk;
-    st_chunk_g(dst, on);
-    st_chunk_g(dst + fstride, orr);
-    st_chunk_g(dst + 2 * fstride, oz);
-    st_chunk_g(dst + 3 * fstride, oh);
-    *reinterpret_cast<float4*>(scr) = make_float4(od[0], od[1], od[2], od[3]);
-    *reinterpret_cast<float4*>(scr + 4) = make_float4(od[4], od[5], od[6], od[7]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cr[k] = *reinterpret_cast<const float4*>(fpanel(p.f0, c.mt, p.Dp, col + 4 * k, c.row));
+    tmem_ld_wait();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float r[8], z[8], n[8], hn[8], hp[8];
+      l_unpack8(ur[k], r); l_unpack8(uz[k], z); l_unpack8(un[k], n); l_unpack8(uh[k], hn); l_unpack8(up[k], hp);
+      const float crv[8] = {cr[2 * k].x, cr[2 * k].y, cr[2 * k].z, cr[2 * k].w, cr[2 * k + 1].x, cr[2 * k + 1].y, cr[2 * k + 1].z, cr[2 * k + 1].w};
+      float on[8], orr[8], oz[8], oh[8], od[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float gh = c.valid ? acc[k * 8 + i] + crv[i] : 0.f;
+        const float gn = gh * (1.f - z[i]);
+        const float gz = gh * (hp[i] - n[i]);
+        od[i] = gh * z[i];
+        const float gnp = gn * (1.f - n[i] * n[i]);
+        on[i] = gnp;
+        oz[i] = gz * z[i] * (1.f - z[i]);
+        oh[i] = gnp * r[i];
+        orr[i] = gnp * hn[i] * r[i] * (1.f - r[i]);
+      }
+      uint8_t* dst = c.out_row + (size_t)(col / 8 + k) * kLTileChunk;
+      st_chunk_g(dst, on);
+      st_chunk_g(dst + fstride, orr);
+      st_chunk_g(dst + 2 * fstride, oz);
+      st_chunk_g(dst + 3 * fstride, oh);
+      *reinterpret_cast<float4*>(fpanel(p.f0, c.mt, p.Dp, col + 8 * k, c.row)) = make_float4(od[0], od[1], od[2], od[3]);
+      *reinterpret_cast<float4*>(fpanel(p.f0, c.mt, p.Dp, col + 8 * k + 4, c.row)) = make_float4(od[4], od[5], od[6], od[7]);
+    }
   }
 }
 
-// dL/dh_t = acc + dL/dh' z (carry row) + upstream dL/ddeter[:, t]: carried on, or - at t = 0 - the start-state gradient
+// dL/dh_t = acc + dL/dh' z (carry panel) + upstream dL/ddeter[:, t]: carried on, or - at t = 0 - the start-state gradient
 __device__ __forceinline__ void lepib_carry(const LCtx& c) {
   const LayerArgs& p = *c.p;
-  const long long prow = (long long)c.mt * 128 + c.row;
-  for (int g = c.q; g < p.n / 8; g += 4) {
-    const int col = c.nt * p.n + g * 8;
+  const long long b0 = c.b - c.lane;
+  for (int blk = c.q; blk * 32 < p.n; blk += 4) {
+    const int col = c.nt * p.n + blk * 32;
     if (col >= p.Dp) break;
-    float acc[8];
-    tmem_ld8(c.tmem_lane + g * 8, acc);
-    float* scr = p.f0 + prow * p.Dp + col;
-    const float4 c0 = *reinterpret_cast<const float4*>(scr), c1 = *reinterpret_cast<const float4*>(scr + 4);
-    const float cr[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-    float up[8];
+    float acc[32], up[32];
+    tmem_ld32(c.tmem_lane + blk * 32, acc);
+    float4 cr[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      up[i] = (p.f1 && c.valid && col + i < p.D) ? p.f1[(c.b * (p.H + 1) + p.t) * p.D + col + i] : 0.f;
+    for (int k = 0; k < 8; ++k)
+      cr[k] = (col + 4 * k < p.Dp) ? *reinterpret_cast<const float4*>(fpanel(p.f0, c.mt, p.Dp, col + 4 * k, c.row))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.f1) {
+      const int nr = (int)max(0LL, min(32LL, (long long)p.B - b0));
+      load_rows32(c, p.f1 + (b0 * (p.H + 1) + p.t) * p.D + col, (long long)(p.H + 1) * p.D, nr, min(32, p.D - col), up);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) up[i] = 0.f;
+    }
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = c.valid ? acc[i] + cr[i] + up[i] : 0.f;
+    for (int k = 0; k < 8; ++k) {
+      acc[4 * k] = c.valid ? acc[4 * k] + cr[k].x + up[4 * k] : 0.f;
+      acc[4 * k + 1] = c.valid ? acc[4 * k + 1] + cr[k].y + up[4 * k + 1] : 0.f;
+      acc[4 * k + 2] = c.valid ? acc[4 * k + 2] + cr[k].z + up[4 * k + 2] : 0.f;
+      acc[4 * k + 3] = c.valid ? acc[4 * k + 3] + cr[k].w + up[4 * k + 3] : 0.f;
+    }
     if (p.t > 0) {
-      *reinterpret_cast<float4*>(scr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(scr + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (col + 4 * k < p.Dp && blk * 32 + 4 * k < p.n)
+          *reinterpret_cast<float4*>(fpanel(p.f0, c.mt, p.Dp, col + 4 * k, c.row)) =
+              make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
     } else if (c.valid) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (col + i < p.D) p.f2[c.b * p.D + col + i] = acc[i];
+      for (int i = 0; i < 32; ++i)
+        if (col + i < p.D && blk * 32 + i < p.n) p.f2[c.b * p.D + col + i] = acc[i];
     }
   }
 }
 
-// [dL/ds_t | dL/da_t] = g_x W_e.  Latent tiles: fp32 carry rows f0 [MT*128][Sip] (read by the previous step's sample
-// backward) or, at t = 0, the start-state gradient f2 (+ upstream f1[:, 0]).  Last tile: the action columns through the
-// tanh squash (actor.py:49-50: a = tanh(mu / scale) bound) -> g_mu panel.
+// [dL/ds_t | dL/da_t] = g_x W_e.  Latent tiles: fp32 carry panel f0 (read by the previous step's sample backward)
+// or, at t = 0, the start-state gradient f2 (+ upstream f1[:, 0]).  Last tile: the action columns through the tanh
+// squash (actor.py:49-50: a = tanh(mu / scale) bound) -> g_mu panel.
 __device__ __forceinline__ void lepib_emb(const LCtx& c) {
   const LayerArgs& p = *c.p;
   const int S_in = p.S * p.C;
   if (c.nt < p.NT - 1) {
-    const long long prow = (long long)c.mt * 128 + c.row;
-    for (int g = c.q; g < p.n / 8; g += 4) {
-      const int col = c.nt * p.n + g * 8;
+    for (int blk = c.q; blk * 32 < p.n; blk += 4) {
+      const int col = c.nt * p.n + blk * 32;
       if (col >= p.Sip) break;
-      float acc[8];
-      tmem_ld8(c.tmem_lane + g * 8, acc);
+      float acc[32];
+      tmem_ld32(c.tmem_lane + blk * 32, acc);
       tmem_ld_wait();
       if (p.t > 0) {
-        float* scr = p.f0 + prow * p.Sip + col;
-        *reinterpret_cast<float4*>(scr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(scr + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (col + 4 * k < p.Sip && blk * 32 + 4 * k < p.n)
+            *reinterpret_cast<float4*>(fpanel(p.f0, c.mt, p.Sip, col + 4 * k, c.row)) =
+                make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
       } else if (c.valid) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (col + i < S_in) {
+        for (int i = 0; i < 32; ++i)
+          if (col + i < S_in && blk * 32 + i < p.n) {
             float gv = acc[i];
             if (p.f1) gv += p.f1[(c.b * (p.H + 1)) * S_in + col + i];
             p.f2[c.b * S_in + col + i] = gv;
@@ -625,6 +703,7 @@ __device__ __forceinline__ void lepib_emb(const LCtx& c) {
 // LayerNorm(eps 1e-5, affine) + ELU backward of one actor block (actor.py:23-36) from the recorded x-hat / rstd:
 //   u = gamma xh + beta, g_u = g_y ELU'(u), g_xh = g_u gamma, g_pre = rstd (g_xh - mean(g_xh) - xh mean(g_xh xh)).
 // parameters [gamma log2e | beta log2e | gamma]; aux[0] = x-hat (read), aux[1] = g_u panel (written), out = g_pre.
+// 32 columns per iteration, the four x-hat chunks and the accumulator load in flight together.
 __device__ __forceinline__ void lepib_ln(const LCtx& c) {
   const LayerArgs& p = *c.p;
   const int W = p.n, ngrp = W / 32;
@@ -634,13 +713,16 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
   const float rstd = c.valid ? p.f0[(long long)c.mt * 128 + c.row] : 0.f;
   float s1 = 0.f, s2 = 0.f;
   for (int g = c.q; g < ngrp; g += 4) {
+    float v[32];
+    tmem_ld32(c.tmem_lane + g * 32, v);
+    uint4 xu[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xu[k] = l_ldg16(xrow + (size_t)(g * 4 + k) * kLTileChunk);
+    tmem_ld_wait();
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float v[8], xh[8], gu[8];
-      tmem_ld8(c.tmem_lane + g * 32 + k * 8, v);
-      const uint4 xu = l_ldg16(xrow + (size_t)(g * 4 + k) * kLTileChunk);
-      l_unpack8(xu, xh);
-      tmem_ld_wait();
+      float xh[8], gu[8];
+      l_unpack8(xu[k], xh);
 #pragma unroll
       for (int i = 0; i < 8; i += 4) {
         const int f = g * 32 + k * 8 + i;
@@ -649,7 +731,7 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float us = fmaf(gs[e], xh[i + e], bs[e]);                                  // u * log2(e)
-          const float g_u = c.valid ? v[i + e] * ex2_fast(fminf(us, 0.f)) : 0.f;           // ELU'(u) = 1 (u > 0) | exp(u)
+          const float g_u = c.valid ? v[k * 8 + i + e] * ex2_fast(fminf(us, 0.f)) : 0.f;   // ELU'(u) = 1 (u > 0) | exp(u)
           const float g_x = g_u * gw[e];
           gu[i + e] = g_u;
           s1 += g_x;
@@ -671,13 +753,16 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
   const float inv = 1.f / (float)W;
   const float m1 = s1 * inv, m2 = s2 * inv;
   for (int g = c.q; g < ngrp; g += 4) {
+    float v[32];
+    tmem_ld32(c.tmem_lane + g * 32, v);
+    uint4 xu[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xu[k] = l_ldg16(xrow + (size_t)(g * 4 + k) * kLTileChunk);
+    tmem_ld_wait();
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float v[8], xh[8], gp[8];
-      tmem_ld8(c.tmem_lane + g * 32 + k * 8, v);
-      const uint4 xu = l_ldg16(xrow + (size_t)(g * 4 + k) * kLTileChunk);
-      l_unpack8(xu, xh);
-      tmem_ld_wait();
+      float xh[8], gp[8];
+      l_unpack8(xu[k], xh);
 #pragma unroll
       for (int i = 0; i < 8; i += 4) {
         const int f = g * 32 + k * 8 + i;
@@ -686,7 +771,7 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float us = fmaf(gs[e], xh[i + e], bs[e]);
-          const float g_x = v[i + e] * ex2_fast(fminf(us, 0.f)) * gw[e];
+          const float g_x = v[k * 8 + i + e] * ex2_fast(fminf(us, 0.f)) * gw[e];
           gp[i + e] = c.valid ? rstd * (g_x - m1 - xh[i + e] * m2) : 0.f;
         }
       }
@@ -947,10 +1032,13 @@ __global__ void tcl_init_kernel(const float* __restrict__ deter0, const float* _
 // --------------------------------------------------------------------------
 // carry rows of dL/dh: the upstream gradient of the LAST deter state (zero where absent / padding)
 __global__ void tcl_carry_init_kernel(float* carry_h, const float* g_deter, int B, int H, int D, int Dp, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // panel order: [tile][col/4][row][4]
   if (i >= n) return;
-  const long long b = i / Dp;
-  const int col = (int)(i % Dp);
+  const int e = (int)(i & 3), row = (int)((i >> 2) & 127);
+  const long long ch = i >> 9;
+  const long long mt = ch / (Dp / 4);
+  const int col = (int)(ch % (Dp / 4)) * 4 + e;
+  const long long b = mt * 128 + row;
   carry_h[i] = (g_deter && b < B && col < D) ? g_deter[(b * (H + 1) + H) * D + col] : 0.f;
 }
 
@@ -981,7 +1069,7 @@ __global__ void tcl_sample_bwd_disc_kernel(const SbArgs a) {
   float l = -INFINITY, G = 0.f, gl = 0.f;
   if (valid && lane < a.S) {
     l = a.dist_a[o + lane];
-    if (a.carry_s) G = a.carry_s[prow * a.Sip + c * a.S + lane];
+    if (a.carry_s) { const int cc = c * a.S + lane; G = a.carry_s[((prow >> 7) * (a.Sip / 4) + (cc >> 2)) * 512 + (prow & 127) * 4 + (cc & 3)]; }
     if (a.g_stoch) G += a.g_stoch[o + lane];
     if (a.g_da) gl = a.g_da[o + lane];
   }
@@ -1015,7 +1103,7 @@ __global__ void tcl_sample_bwd_cont_kernel(const SbArgs a) {
   for (int k = 0; k < 8; ++k) {
     gm[k] = gr[k] = 0.f;
     if (valid && col + k < a.S) {
-      float G = a.carry_s ? a.carry_s[prow * a.Sip + col + k] : 0.f;
+      float G = a.carry_s ? a.carry_s[((prow >> 7) * (a.Sip / 4) + ((col + k) >> 2)) * 512 + (prow & 127) * 4 + ((col + k) & 3)] : 0.f;
       if (a.g_stoch) G += a.g_stoch[o + k];
       const float eps = a.noise[((long long)a.t * a.B + prow) * a.S + col + k];
       const float sig = 1.f - __expf(-(a.dist_b[o + k] - 0.1f));
@@ -1779,6 +1867,7 @@ int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const
           break;
         case LB_GRU:
           a.aux[0] = c.at(F_GR, t); a.aux[1] = c.at(F_GZ, t); a.aux[2] = c.at(F_GN, t); a.aux[3] = c.at(F_GHN, t);
+          a.aux[4] = c.at(F_H, t);
           a.aux_tile_bytes = m.r[F_GR].tile_bytes;
           a.f0 = carry_h;
           break;
@@ -1797,6 +1886,8 @@ int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const
       }
       int ss[3] = {0, 0, 0};
       if (L.seg[0].buf == G_GMU || L.seg[0].buf >= G_GP0) ss[0] = t;
+      a.trace = nullptr;
+      if ((d.flags & WMRL_FLAG_TRACE) && t == std::max(0, T - 2)) a.trace = (long long*)ws + 32 * (&L - &lp.blayers[0]);
       if (int r = tcl_launch(c, L, a, ss, out_step)) return r;
     }
   }
