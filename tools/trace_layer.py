@@ -88,6 +88,10 @@ if "bwd" in sys.argv:
     trb = ws2[:nb * 32 * 8].view(torch.int64).cpu().reshape(nb, 32)
     print(f"{case} backward (step T-2): cycles relative to kernel start (CTA 0)")
     show(trb, ["prior2^T", "prior1^T+GRUb", "W_ih^T", "W_hh^T", "embed^T"] + [f"LNb{l}" for l in range(La - 1, -1, -1)])
+    pc = [int(x) for x in trb[3][16:20]]
+    print("W_hh^T carry epilogue probes (thread 0, last block): loads issued+staged", pc[1] - pc[0], " tmem wait", pc[2] - pc[1], " math+stores", pc[3] - pc[2])
+    pl = [int(x) for x in trb[nb - 1][16:21]]
+    print("LNb0 probes: first block loads", pl[1] - pl[0], " pass1", pl[2] - pl[0], " exchange", pl[3] - pl[2], " pass2", pl[4] - pl[3])
 
 pr = [int(x) for x in tr[nl - 1][16:22]]
 if pr[5]:

@@ -617,6 +617,7 @@ __device__ __forceinline__ void lepib_carry(const LCtx& c) {
     const int col = c.nt * p.n + blk * 32;
     if (col >= p.Dp) break;
     float acc[32], up[32];
+    LPROBE(c, 0);
     tmem_ld32(c.tmem_lane + blk * 32, acc);
     float4 cr[8];
 #pragma unroll
@@ -630,7 +631,9 @@ __device__ __forceinline__ void lepib_carry(const LCtx& c) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) up[i] = 0.f;
     }
+    LPROBE(c, 1);
     tmem_ld_wait();
+    LPROBE(c, 2);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       acc[4 * k] = c.valid ? acc[4 * k] + cr[k].x + up[4 * k] : 0.f;
@@ -649,6 +652,7 @@ __device__ __forceinline__ void lepib_carry(const LCtx& c) {
       for (int i = 0; i < 32; ++i)
         if (col + i < p.D && blk * 32 + i < p.n) p.f2[c.b * p.D + col + i] = acc[i];
     }
+    LPROBE(c, 3);
   }
 }
 
@@ -700,38 +704,45 @@ __device__ __forceinline__ void lepib_emb(const LCtx& c) {
   }
 }
 
-// LayerNorm(eps 1e-5, affine) + ELU backward of one actor block (actor.py:23-36) from the recorded x-hat / rstd:
-//   u = gamma xh + beta, g_u = g_y ELU'(u), g_xh = g_u gamma, g_pre = rstd (g_xh - mean(g_xh) - xh mean(g_xh xh)).
-// parameters [gamma log2e | beta log2e | gamma]; aux[0] = x-hat (read), aux[1] = g_u panel (written), out = g_pre.
-// 32 columns per iteration, the four x-hat chunks and the accumulator load in flight together.
+// LayerNorm(eps 1e-5, affine) + ELU backward of one actor block (actor.py:23-36) from the recorded x-hat / rstd / y:
+//   g_u = g_y ELU'(u) with ELU'(u) = 1 (y > 0) | y + 1 from the recorded post-ELU y (no transcendental op: the exp form
+//   was MUFU-bound, 2 x 64K ex2 per work item), g_xh = g_u gamma, g_pre = rstd (g_xh - mean(g_xh) - xh mean(g_xh xh)).
+// parameters [gamma log2e | beta log2e | gamma] (only gamma is read); aux[0] = x-hat, aux[2] = y (read), aux[1] = g_u
+// panel (written), out = g_pre.  32 columns per iteration, all loads of a block in flight together.
 __device__ __forceinline__ void lepib_ln(const LCtx& c) {
   const LayerArgs& p = *c.p;
   const int W = p.n, ngrp = W / 32;
-  const uint32_t gsc = c.prm, bsc = gsc + W * 4, gam = bsc + W * 4;
-  const uint8_t* xrow = p.aux[0] + (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16;
-  uint8_t* gurow = p.aux[1] + (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16;
+  const uint32_t gam = c.prm + 2 * W * 4;
+  const size_t ro = (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16;
+  const uint8_t* xrow = p.aux[0] + ro;
+  const uint8_t* yrow = p.aux[2] + ro;
+  uint8_t* gurow = p.aux[1] + ro;
   const float rstd = c.valid ? p.f0[(long long)c.mt * 128 + c.row] : 0.f;
   float s1 = 0.f, s2 = 0.f;
+  LPROBE(c, 0);
   for (int g = c.q; g < ngrp; g += 4) {
     float v[32];
     tmem_ld32(c.tmem_lane + g * 32, v);
-    uint4 xu[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) xu[k] = l_ldg16(xrow + (size_t)(g * 4 + k) * kLTileChunk);
-    tmem_ld_wait();
+    uint4 xu[4], yu[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float xh[8], gu[8];
+      xu[k] = l_ldg16(xrow + (size_t)(g * 4 + k) * kLTileChunk);
+      yu[k] = l_ldg16(yrow + (size_t)(g * 4 + k) * kLTileChunk);
+    }
+    tmem_ld_wait();
+    if (g == c.q) LPROBE(c, 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float xh[8], y[8], gu[8];
       l_unpack8(xu[k], xh);
+      l_unpack8(yu[k], y);
 #pragma unroll
       for (int i = 0; i < 8; i += 4) {
-        const int f = g * 32 + k * 8 + i;
-        const float4 g4 = lds4(gsc + f * 4), b4 = lds4(bsc + f * 4), w4 = lds4(gam + f * 4);
-        const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w}, gw[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float4 w4 = lds4(gam + (g * 32 + k * 8 + i) * 4);
+        const float gw[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float us = fmaf(gs[e], xh[i + e], bs[e]);                                  // u * log2(e)
-          const float g_u = c.valid ? v[k * 8 + i + e] * ex2_fast(fminf(us, 0.f)) : 0.f;   // ELU'(u) = 1 (u > 0) | exp(u)
+          const float g_u = c.valid ? v[k * 8 + i + e] * fminf(y[i + e] + 1.f, 1.f) : 0.f;   // ELU' = min(y + 1, 1)
           const float g_x = g_u * gw[e];
           gu[i + e] = g_u;
           s1 += g_x;
@@ -741,8 +752,10 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
       st_chunk_g(gurow + (size_t)(g * 4 + k) * kLTileChunk, gu);
     }
   }
+  LPROBE(c, 2);
   asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(c.scratch + (c.q * 128 + c.row) * 8), "f"(s1), "f"(s2) : "memory");
   l_quarter_sync(c.quarter);
+  LPROBE(c, 3);
   s1 = 0.f; s2 = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -755,28 +768,73 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
   for (int g = c.q; g < ngrp; g += 4) {
     float v[32];
     tmem_ld32(c.tmem_lane + g * 32, v);
-    uint4 xu[4];
+    uint4 xu[4], yu[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) xu[k] = l_ldg16(xrow + (size_t)(g * 4 + k) * kLTileChunk);
+    for (int k = 0; k < 4; ++k) {
+      xu[k] = l_ldg16(xrow + (size_t)(g * 4 + k) * kLTileChunk);
+      yu[k] = l_ldg16(yrow + (size_t)(g * 4 + k) * kLTileChunk);
+    }
     tmem_ld_wait();
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float xh[8], gp[8];
+      float xh[8], y[8], gp[8];
       l_unpack8(xu[k], xh);
+      l_unpack8(yu[k], y);
 #pragma unroll
       for (int i = 0; i < 8; i += 4) {
-        const int f = g * 32 + k * 8 + i;
-        const float4 g4 = lds4(gsc + f * 4), b4 = lds4(bsc + f * 4), w4 = lds4(gam + f * 4);
-        const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w}, gw[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float4 w4 = lds4(gam + (g * 32 + k * 8 + i) * 4);
+        const float gw[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float us = fmaf(gs[e], xh[i + e], bs[e]);
-          const float g_x = v[k * 8 + i + e] * ex2_fast(fminf(us, 0.f)) * gw[e];
+          const float g_x = v[k * 8 + i + e] * fminf(y[i + e] + 1.f, 1.f) * gw[e];
           gp[i + e] = c.valid ? rstd * (g_x - m1 - xh[i + e] * m2) : 0.f;
         }
       }
       st_chunk_g(c.out_row + (size_t)(g * 4 + k) * kLTileChunk, gp);
     }
+  }
+  LPROBE(c, 4);
+}
+
+// What the backward epilogues read from HBM (recorded panels written a whole forward ago, upstream gradients read
+// once) is pulled into L2 while the work item's MMAs run: issued before the accumulator wait, no registers held.
+__device__ __forceinline__ void l_prefetch(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+__device__ __forceinline__ void lepib_prefetch(const LCtx& c, int type) {
+  const LayerArgs& p = *c.p;
+  const bool lead = (c.lane & 7) == 0;   // 8 rows x 16 B share a 128-byte line of a panel chunk
+  const size_t ro = (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16;
+  if (type == LB_ELU) {
+    if (lead)
+      for (int ch = c.q * 4; ch * 8 < p.n; ch += 16)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int col = c.nt * p.n + (ch + k) * 8;
+          if ((ch + k) * 8 < p.n && col < p.out_cols) l_prefetch(p.aux[0] + ro + (size_t)(col / 8) * kLTileChunk);
+        }
+  } else if (type == LB_GRU) {
+    if (lead)
+      for (int g = c.q; g * 16 < p.n; g += 4) {
+        const int col = c.nt * p.n + g * 16;
+        if (col >= p.Dp) break;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int f = 0; f < 5; ++f) l_prefetch(p.aux[f] + ro + (size_t)(col / 8 + k) * kLTileChunk);
+      }
+  } else if (type == LB_CARRY) {
+    if (p.f1 && c.valid)
+      for (int blk = c.q; blk * 32 < p.n; blk += 4) {
+        const int col = c.nt * p.n + blk * 32;
+        if (col < p.D) l_prefetch(p.f1 + (c.b * (p.H + 1) + p.t) * p.D + col);
+      }
+  } else if (type == LB_LN) {
+    if (lead)
+      for (int g = c.q; g < p.n / 32; g += 4)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          l_prefetch(p.aux[0] + ro + (size_t)(g * 4 + k) * kLTileChunk);
+          l_prefetch(p.aux[2] + ro + (size_t)(g * 4 + k) * kLTileChunk);
+        }
   }
 }
 
@@ -953,6 +1011,7 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
         for (int o = c.q * 32; o < p.n && c.nt * p.n + o < P; o += 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(qrow + o));
       }
+      if (kType >= LB_ELU) lepib_prefetch(c, kType);
       if (it == 0 && threadIdx.x == 0) LTRACE(6);    // parameters staged, waiting for the accumulator
       mbar_wait_backoff_quiet(accf_bar(ab), use & 1u);
       tc_fence_after();
@@ -1879,7 +1938,8 @@ int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const
           out_step = t;
           break;
         case LB_LN:
-          a.aux[0] = c.at(F_XH0 + L.layer, t); a.aux[1] = c.at(G_GU0 + L.layer, t); a.aux_tile_bytes = m.r[F_XH0 + L.layer].tile_bytes;
+          a.aux[0] = c.at(F_XH0 + L.layer, t); a.aux[1] = c.at(G_GU0 + L.layer, t); a.aux[2] = c.at(F_Y0 + L.layer, t);
+          a.aux_tile_bytes = m.r[F_XH0 + L.layer].tile_bytes;
           a.f0 = (float*)c.at(F_RSTD0 + L.layer, t);
           out_step = t;
           break;
