@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define WMRL_ABI_VERSION 1
+#define WMRL_ABI_VERSION 2
 #if defined(__GNUC__)
 #define WMRL_API __attribute__((visibility("default")))
 #else
@@ -185,6 +185,20 @@ WMRL_API int wmrl_observe_fwd(const wmrl_dims* d, const wmrl_rssm_params* w, con
                      float* pri_deter, float* pri_stoch, float* pri_dist_a, float* pri_dist_b,
                      float* post_deter, float* post_stoch, float* post_dist_a, float* post_dist_b,
                      void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * The same forward on the bf16 layer-wise tcgen05 chain (no gradient record: filtering for evaluation, acting and
+ * for the start states of imagination, which the reference detaches - state/discrete.py:81-89).  The RSSM weights
+ * (prior AND posterior heads) are packed once per version with wmrl_pack_observe_weights into a buffer of
+ * wmrl_observe_packed_bytes (0: shape not supported); workspace from wmrl_workspace_bytes(d with WMRL_BF16, 1).
+ * Same tensors and index conventions as wmrl_observe_fwd.
+ */
+WMRL_API size_t wmrl_observe_packed_bytes(const wmrl_dims* d);
+WMRL_API int wmrl_pack_observe_weights(const wmrl_dims* d, const wmrl_rssm_params* w, void* packed, void* stream);
+WMRL_API int wmrl_observe_fwd_bf16(const wmrl_dims* d, const void* packed, const float* obs_embeds, const float* actions,
+                          const float* noise_prior, const float* noise_post, float* pri_deter, float* pri_stoch,
+                          float* pri_dist_a, float* pri_dist_b, float* post_deter, float* post_stoch, float* post_dist_a,
+                          float* post_dist_b, void* ws, size_t ws_bytes, void* stream);
 
 /* Full backward (weight grads + d obs_embeds + d actions) of observe_fwd, as
  * needed by WorldModel.update (world_model.py:120-163). */

@@ -160,11 +160,11 @@ def prior_deter(w: Weights, stoch: torch.Tensor, action: torch.Tensor, deter: to
     return h, out
 
 
-def posterior_out(w: Weights, deter: torch.Tensor, obs_embed: torch.Tensor) -> torch.Tensor:
+def posterior_out(w: Weights, deter: torch.Tensor, obs_embed: torch.Tensor, emu: bool = False) -> torch.Tensor:
     """cat(deter, obs_embed) -> Linear -> ELU -> Linear (rssm.py:80-81)."""
     hcat = torch.cat([deter, obs_embed], dim=-1)
-    hid = F.elu(F.linear(hcat, w["state_posterior.0.weight"], w["state_posterior.0.bias"]))
-    return F.linear(hid, w["state_posterior.2.weight"], w["state_posterior.2.bias"])
+    hid = F.elu(_lin(hcat, w["state_posterior.0.weight"], w["state_posterior.0.bias"], emu))
+    return _lin(hid, w["state_posterior.2.weight"], w["state_posterior.2.bias"], emu)
 
 
 # --------------------------------------------------------------------------
@@ -247,12 +247,18 @@ def observe_rollout(
     noise_post: torch.Tensor,
     S: int,
     C: int = 1,
+    emulate_bf16: bool = False,
+    forced_post_idx: Optional[torch.Tensor] = None,
 ):
     """RSSMBase.observe_rollout (rssm.py:93-121) from the zero initial state
     (rssm.py:166-172 / 215-220).  For t in 0..T-2: prior_{t+1} = prior(a_t, post_t);
     post_{t+1} = posterior(e_{t+1}, prior_{t+1}).  Two draws per step (prior
     first, then posterior).  Returns dicts for the prior and posterior
-    sequences WITHOUT the index-0 slot, fields [B,T-1,...]."""
+    sequences WITHOUT the index-0 slot, fields [B,T-1,...].
+
+    ``emulate_bf16`` / ``forced_post_idx`` [B,T-1,C]: checker modes for the bf16 tcgen05 chain, as in
+    ``imagine_rollout`` (GEMM operands rounded to bf16; the posterior sample that is fed forward replays
+    recorded indices while ``idx`` still reports the oracle's own draw)."""
     Bn, T = obs_embeds.shape[:2]
     D = w["rnn.weight_hh"].shape[1]
     S_in = S if variant == "continuous" else C * S
@@ -261,8 +267,8 @@ def observe_rollout(
     pri: Dict[str, List[torch.Tensor]] = {k: [] for k in ("deter", "stoch", "d1", "d2", "idx")}
     pos: Dict[str, List[torch.Tensor]] = {k: [] for k in ("deter", "stoch", "d1", "d2", "idx")}
     for t in range(T - 1):
-        h, out = prior_deter(w, stoch, actions[:, t], deter)       # rssm.py:90 via :112
-        pout = posterior_out(w, h, obs_embeds[:, t + 1])           # rssm.py:91
+        h, out = prior_deter(w, stoch, actions[:, t], deter, emulate_bf16)       # rssm.py:90 via :112
+        pout = posterior_out(w, h, obs_embeds[:, t + 1], emulate_bf16)           # rssm.py:91
         if variant == "continuous":
             ps, pm, pstd = gen_stoch_continuous(out, S, noise_prior[t])
             qs, qm, qstd = gen_stoch_continuous(pout, S, noise_post[t])
@@ -270,7 +276,8 @@ def observe_rollout(
             pos["d1"].append(qm); pos["d2"].append(qstd)
         else:
             ps, pl, pi = gen_stoch_discrete(out, C, S, noise_prior[t])
-            qs, ql, qi = gen_stoch_discrete(pout, C, S, noise_post[t])
+            qs, ql, qi = gen_stoch_discrete(pout, C, S, noise_post[t],
+                                            None if forced_post_idx is None else forced_post_idx[:, t])
             pri["d1"].append(pl); pri["idx"].append(pi)
             pos["d1"].append(ql); pos["idx"].append(qi)
         pri["deter"].append(h); pri["stoch"].append(ps)

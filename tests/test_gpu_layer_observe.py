@@ -1,0 +1,90 @@
+"""GPU parity of posterior filtering (RSSMBase.observe_rollout forward, rssm.py:93-121) on the bf16 layer-wise
+tcgen05 chain: `precision="bf16"` modules called without a gradient record.  Checker: the bf16-emulating oracle;
+the discrete variant replays the kernel's posterior indices (they are what is fed forward), compares deter / both
+logits sequences at an absolute 6e-3 and requires both index streams to agree with the oracle's own draws except
+at near-ties (rate <= 1e-3)."""
+import pytest
+import torch
+
+from oracle import rssm_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 6e-3
+
+
+def _setup(variant, D, S, C, Hd, E, A, seed=5):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import helpers_gpu as HG
+    from wmrl import _lib
+    if not _lib.load().wmrl_device_supports_bf16():
+        pytest.skip("not an sm_100 device")
+    rssm, _ = HG.build_modules(variant, D, S, C, Hd, E, A, 64, 1, seed=seed, precision="bf16")
+    return HG, rssm
+
+
+def _inputs(variant, B, T, E, A, S, C, seed=2):
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.relu(torch.randn(B, T, E, generator=g))          # the encoder ends in ReLU
+    act = torch.rand(B, T, A, generator=g) * 2 - 1
+    if variant == "continuous":
+        n1, n2 = torch.randn(T - 1, B, S, generator=g), torch.randn(T - 1, B, S, generator=g)
+    else:
+        n1 = torch.empty(T - 1, B, C, S).exponential_(1.0, generator=g)
+        n2 = torch.empty(T - 1, B, C, S).exponential_(1.0, generator=g)
+    return obs, act, n1, n2
+
+
+def _close(name, got, want, tol=TOL):
+    err = float((got.detach().cpu().float() - want).abs().max())
+    assert err <= tol, f"{name}: max |err| {err:.3e} > {tol}"
+    return err
+
+
+@pytest.mark.parametrize("shape", [(32, 8, 4, 32, 16, 2, 40, 9), (600, 32, 32, 600, 1024, 6, 50, 12), (200, 16, 8, 96, 64, 3, 150, 5)])
+def test_discrete_filtering_replay_vs_bf16_oracle(shape):
+    D, S, C, Hd, E, A, B, T = shape
+    HG, rssm = _setup("discrete", D, S, C, Hd, E, A)
+    obs, act, n1, n2 = _inputs("discrete", B, T, E, A, S, C)
+    with torch.no_grad():
+        pri, post = rssm.observe_rollout(obs.cuda(), act.cuda(), noise=(n1.cuda(), n2.cuda()))
+    assert float(pri.deter_states[:, 0].abs().max()) == 0.0 and float(post.stoch_states[:, 0].abs().max()) == 0.0
+    assert torch.equal(pri.deter_states, post.deter_states)
+    st = post.stoch_states[:, 1:].reshape(B, T - 1, C, S).cpu()
+    assert torch.all((st == 0) | (st == 1)) and torch.all(st.sum(-1) == 1)
+    qi = st.argmax(-1)
+    pi = pri.stoch_states[:, 1:].reshape(B, T - 1, C, S).cpu().argmax(-1)
+    with torch.no_grad():
+        rp, rq = O.observe_rollout("discrete", HG.cpu_weights(rssm), obs, act, n1, n2, S, C, emulate_bf16=True,
+                                   forced_post_idx=qi)
+    e = [_close("deter", post.deter_states[:, 1:], rq["deter"]), _close("prior logits", pri.logits[:, 1:], rp["logits"]),
+         _close("posterior logits", post.logits[:, 1:], rq["logits"])]
+    for name, mine, ref in (("prior", pi, rp["idx"]), ("posterior", qi, rq["idx"])):
+        rate = float((mine != ref).float().mean())
+        assert rate <= 1e-3, f"{name} index mismatch rate {rate:.2e}"
+    print(shape, e)
+
+
+@pytest.mark.parametrize("shape", [(200, 30, 200, 1024, 6, 50, 10), (32, 8, 32, 16, 1, 33, 6)])
+def test_continuous_filtering_vs_bf16_oracle(shape):
+    D, S, Hd, E, A, B, T = shape
+    HG, rssm = _setup("continuous", D, S, 1, Hd, E, A)
+    obs, act, n1, n2 = _inputs("continuous", B, T, E, A, S, 1)
+    with torch.no_grad():
+        pri, post = rssm.observe_rollout(obs.cuda(), act.cuda(), noise=(n1.cuda(), n2.cuda()))
+        rp, rq = O.observe_rollout("continuous", HG.cpu_weights(rssm), obs, act, n1, n2, S, emulate_bf16=True)
+    e = [_close("deter", post.deter_states[:, 1:], rq["deter"]), _close("prior mean", pri.means[:, 1:], rp["mean"]),
+         _close("prior std", pri.stds[:, 1:], rp["std"]), _close("posterior mean", post.means[:, 1:], rq["mean"]),
+         _close("posterior stoch", post.stoch_states[:, 1:], rq["stoch"]), _close("prior stoch", pri.stoch_states[:, 1:], rp["stoch"])]
+    print(shape, e)
+
+
+def test_filtering_with_grad_record_still_takes_the_fp32_path():
+    """training the world model (RSSM parameters require grad, autograd on) records with the fp32 chain."""
+    HG, rssm = _setup("continuous", 32, 8, 1, 32, 16, 1)
+    obs, act, n1, n2 = _inputs("continuous", 20, 5, 16, 1, 8, 1)
+    pri, post = rssm.observe_rollout(obs.cuda(), act.cuda(), noise=(n1.cuda(), n2.cuda()))
+    post.get_features().sum().backward()
+    assert rssm.rnn.weight_hh.grad is not None
+    rp, rq = O.observe_rollout("continuous", HG.cpu_weights(rssm), obs, act, n1, n2, 8)
+    torch.testing.assert_close(post.deter_states[:, 1:].detach().cpu(), rq["deter"], rtol=1e-5, atol=2e-5)

@@ -85,6 +85,31 @@ def run_train(name, variant, D, S, C, Hd, A, Ha, La, B, H, iters=5, precision="b
     return out
 
 
+def run_observe(name, B, T, precision, iters=10):
+    """configs[2]: discrete posterior filtering over B sequences of T frames (conv-encoder output E = 1024), no grad."""
+    D, S, C, Hd, E, A = 600, 32, 32, 600, 1024, 6
+    rssm, _ = HG.build_modules("discrete", D, S, C, Hd, E, A, 64, 1, precision=precision)
+    g = torch.Generator().manual_seed(3)
+    obs = torch.relu(torch.randn(B, T, E, generator=g)).cuda()
+    act = (torch.rand(B, T, A, generator=g) * 2 - 1).cuda()
+    with torch.no_grad():
+        for _ in range(2):
+            rssm.observe_rollout(obs, act)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            rssm.observe_rollout(obs, act)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    fl = 10682400       # SURVEY 8d: observe fwd FLOPs per sample-step at C2/C3 dims
+    out = {"case": name, "precision": precision, "ms": round(ms, 3), "sample_steps_per_s": B * (T - 1) / ms * 1e3,
+           "tflops": fl * B * (T - 1) / ms / 1e9}
+    print(json.dumps(out), flush=True)
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c5", "c2f32"]
     if "c2" in which:
@@ -99,5 +124,8 @@ if __name__ == "__main__":
         run_train("configs[1] discrete D600 32x32 2500x15", "discrete", 600, 32, 32, 600, 6, 512, 3, 2500, 15, iters=5, precision="fp32")
     if "c5t" in which:
         run_train("configs[4] discrete D1024 32x32 8192x64 (one GPU's shard)", "discrete", 1024, 32, 32, 1024, 6, 512, 3, 8192, 64, iters=2)
+    if "c3" in which:
+        run_observe("configs[2] discrete observe 50x51 (E 1024) fwd", 50, 51, "bf16")
+        run_observe("configs[2] discrete observe 50x51 (E 1024) fwd", 50, 51, "fp32")
     if "c4" in which:   # continuous bench shape; WMRL_BF16_PATH=layer forces the chain
         run("configs[3] continuous 65536x15", "continuous", 200, 30, 1, 200, 6, 512, 3, 65536, 15, iters=5)

@@ -105,7 +105,45 @@ size_t wmrl_workspace_bytes(const wmrl_dims* d, int op) {
       if (b > a) a = b;
     }
   }
+  if (d->precision == WMRL_BF16 && op == 1) {
+    const size_t b = tcl_observe_workspace_bytes(dd);
+    if (b > a) a = b;
+  }
   return a;
+}
+
+size_t wmrl_observe_packed_bytes(const wmrl_dims* d) {
+  if (check_dims(d, 1)) return 0;
+  Dims dd(*d);
+  return tcl_observe_packed_bytes(dd);
+}
+
+int wmrl_pack_observe_weights(const wmrl_dims* d, const wmrl_rssm_params* w, void* packed, void* stream) {
+  if (int r = check_dims(d, 1)) return r;
+  WMRL_REQUIRE(w && packed, "pack_observe_weights: NULL argument");
+  Dims dd(*d);
+  WMRL_REQUIRE(tcl_observe_supported(dd), "pack_observe_weights: shape not supported by the tcgen05 path");
+  if (int r = require_device()) return r;
+  return tcl_pack_observe_weights(dd, w, packed, (cudaStream_t)stream);
+}
+
+int wmrl_observe_fwd_bf16(const wmrl_dims* d, const void* packed, const float* obs_embeds, const float* actions,
+                          const float* noise_prior, const float* noise_post, float* pri_deter, float* pri_stoch,
+                          float* pri_dist_a, float* pri_dist_b, float* post_deter, float* post_stoch, float* post_dist_a,
+                          float* post_dist_b, void* ws, size_t ws_bytes, void* stream) {
+  if (int r = check_dims(d, 1)) return r;
+  Dims dd(*d);
+  if (dd.B == 0 || dd.T == 0) return 0;
+  WMRL_REQUIRE(packed, "observe_fwd_bf16: needs the packed weight image (wmrl_pack_observe_weights)");
+  WMRL_REQUIRE(tcl_observe_supported(dd), "observe_fwd_bf16: shape not supported by the tcgen05 path");
+  WMRL_REQUIRE(pri_deter && pri_stoch && pri_dist_a && post_deter && post_stoch && post_dist_a, "observe_fwd_bf16: NULL output");
+  WMRL_REQUIRE(dd.T == 1 || (obs_embeds && actions && noise_prior && noise_post), "observe_fwd_bf16: NULL input");
+  WMRL_REQUIRE(dd.variant == WMRL_DISCRETE || (pri_dist_b && post_dist_b), "observe_fwd_bf16: continuous needs stds");
+  WMRL_REQUIRE(ws && ws_bytes >= tcl_observe_workspace_bytes(dd), "observe_fwd_bf16: workspace too small");
+  WMRL_REQUIRE(wmrl_device_supports_bf16(), "observe_fwd_bf16: needs an sm_100 device");
+  if (int r = require_device()) return r;
+  return tcl_observe_fwd(dd, packed, obs_embeds, actions, noise_prior, noise_post, pri_deter, pri_stoch, pri_dist_a,
+                         pri_dist_b, post_deter, post_stoch, post_dist_a, post_dist_b, ws, (cudaStream_t)stream);
 }
 
 size_t wmrl_packed_bytes(const wmrl_dims* d) {

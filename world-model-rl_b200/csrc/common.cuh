@@ -108,6 +108,14 @@ int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const
                     const float* dist_b, const float* actions, const void* saved, const float* g_deter_seq,
                     const float* g_stoch_seq, const float* g_dist_a, const float* g_dist_b, const wmrl_actor_grads* gaw,
                     float* g_deter0, float* g_stoch0, void* ws, cudaStream_t st);
+// posterior filtering (observe_rollout forward) on the layer-wise chain
+bool tcl_observe_supported(const Dims& d);
+size_t tcl_observe_packed_bytes(const Dims& d);
+size_t tcl_observe_workspace_bytes(const Dims& d);
+int tcl_pack_observe_weights(const Dims& d, const wmrl_rssm_params* w, void* packed, cudaStream_t st);
+int tcl_observe_fwd(const Dims& d, const void* packed, const float* obs, const float* act, const float* noise_pri,
+                    const float* noise_post, float* pri_deter, float* pri_stoch, float* pri_da, float* pri_db,
+                    float* post_deter, float* post_stoch, float* post_da, float* post_db, void* ws, cudaStream_t st);
 // which bf16 forward serves this shape: 1 persistent folded-pair / single-CTA kernel, 2 layer-wise chain, 0 none
 int bf16_path(const Dims& d);
 

@@ -1078,7 +1078,7 @@ __global__ void tcl_init_kernel(const float* __restrict__ deter0, const float* _
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int col = k8 * 8 + e;
-      v[e] = (b < B && col < W) ? src[b * W + col] : 0.f;
+      v[e] = (src && b < B && col < W) ? src[b * W + col] : 0.f;
       if (b < B && col < W) seq[(b * (H + 1)) * W + col] = v[e];
     }
     uint8_t* panel = isd ? hpanel + (size_t)mt * (Dp / 8) * kLTileChunk : spanel + (size_t)mt * (Sip / 8) * kLTileChunk;
@@ -1330,6 +1330,7 @@ __global__ void __launch_bounds__(kCs2Warps * 32) tcl_colsum_kernel(const Cs2Par
 // gradient panels.  F_Y / F_XH / F_RSTD / G_GP / G_GU take one slot per actor block.
 enum {
   F_H = 0, F_HN, F_S, F_SN, F_A, F_X, F_HID, F_GR, F_GZ, F_GN, F_GHN,
+  F_OBS, F_ACT, F_HIDQ, F_SPRI,   // posterior filtering: observation-embedding / action panels per step, posterior hidden, prior-sample sink
   F_Y0, F_XH0 = F_Y0 + WMRL_MAX_ACTOR_LAYERS, F_RSTD0 = F_XH0 + WMRL_MAX_ACTOR_LAYERS,
   G_GO = F_RSTD0 + WMRL_MAX_ACTOR_LAYERS, G_GHID, G_GATES_I, G_GATES_H, G_GX, G_GMU,
   G_GP0, G_GU0 = G_GP0 + WMRL_MAX_ACTOR_LAYERS, BUF_COUNT = G_GU0 + WMRL_MAX_ACTOR_LAYERS
@@ -1349,7 +1350,7 @@ struct LPlan {
   Plan pk;                   // pack ops / vec ops / image offsets (stage and job tables stay empty)
   std::vector<LLayerH> layers;    // forward chain of one step
   std::vector<LLayerH> blayers;   // backward chain of one step (after the sample backward)
-  int Dp = 0, Sip = 0, Sp = 0, Hdp = 0, Ha = 0, Pp = 0;
+  int Dp = 0, Sip = 0, Sp = 0, Hdp = 0, Ha = 0, Pp = 0, Ep = 0;
 };
 
 static int ceil_to(int x, int m) { return (x + m - 1) / m * m; }
@@ -1389,9 +1390,10 @@ static void l_add_pack_t(LPlan& lp, const RowSpec& rs, const float* src, int ld,
 
 static int buf_width(const LPlan& lp, int buf) {
   if (buf == F_H || buf == F_HN || buf == F_X || buf == F_GR || buf == F_GZ || buf == F_GN || buf == F_GHN || buf == G_GX) return lp.Dp;
-  if (buf == F_S || buf == F_SN) return lp.Sip;
-  if (buf == F_A || buf == G_GMU) return 16;
-  if (buf == F_HID || buf == G_GHID) return lp.Hdp;
+  if (buf == F_S || buf == F_SN || buf == F_SPRI) return lp.Sip;
+  if (buf == F_A || buf == G_GMU || buf == F_ACT) return 16;
+  if (buf == F_HID || buf == G_GHID || buf == F_HIDQ) return lp.Hdp;
+  if (buf == F_OBS) return lp.Ep;
   if (buf == G_GO) return lp.Pp;
   if (buf == G_GATES_I || buf == G_GATES_H) return 4 * lp.Dp;
   return lp.Ha;   // F_Y, F_XH, G_GP, G_GU
@@ -1991,6 +1993,259 @@ int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const
   }
   if (int r = wgrad(F_Y0 + d.La - 1, d.Ha, d.Ha, G_GMU, 16, d.A, gaw->mu_w, d.Ha)) return r;
   if (int r = colsum(G_GMU, -1, 16, d.A, gaw->mu_b)) return r;
+  return 0;
+}
+
+// ==========================================================================
+// Posterior filtering on the chain (RSSMBase.observe_rollout, rssm.py:93-121), forward: per step
+//   prior_{t+1} = prior(a_t, post_t)  (embed -> GRU -> prior hidden -> prior head + sample)
+//   post_{t+1}  = posterior(e_{t+1}, prior_{t+1})  ([h' | e] -> hidden -> head + sample; its sample feeds step t+1)
+// obs_embeds / actions are converted once into per-step bf16 panels.
+// ==========================================================================
+static LPlan tcl_make_observe_plan(const Dims& d, const wmrl_rssm_params* w) {
+  LPlan lp;
+  const bool disc = d.variant == WMRL_DISCRETE;
+  if (d.A > 16) return lp;
+  if (disc && !(d.S == 4 || d.S == 8 || d.S == 16 || d.S == 32)) return lp;
+  const int Dp = ceil16(d.D), Sip = ceil16(d.S_in), Sp = ceil16(d.S), Hdp = ceil16(d.Hd), Ep = ceil16(d.E);
+  if (!disc && 2 * Sp > 256) return lp;
+  lp.Dp = Dp; lp.Sip = Sip; lp.Sp = Sp; lp.Hdp = Hdp; lp.Ha = 32; lp.Pp = disc ? Sip : 2 * Sp; lp.Ep = Ep;
+  const float* nul = nullptr;
+  Plan& pk = lp.pk;
+  auto kc_for = [&](int nmax) { int kc = (int)(kLSlotBytes / (4096u + (uint32_t)nmax * 32u)); return std::max(1, std::min(kc, 8)); };
+  auto tiles = [&](int total, int cap, int unit, int& nt, int& wt) {
+    nt = (total + cap - 1) / cap;
+    wt = ceil_to((total + nt - 1) / nt, unit);
+  };
+  // ---- state-action embed: [post s_t | a_t] -> Linear -> ELU
+  {
+    LLayerH L;
+    L.type = LE_BIAS_ELU; L.dbuf = 1; L.out = F_X; L.nseg = 2;
+    tiles(Dp, 256, 16, L.NT, L.n);
+    L.kc = kc_for(L.n);
+    L.w_off = pk.data_bytes;
+    const int Ke = d.S_in + d.A;
+    for (int j = 0; j < L.NT; ++j) {
+      const size_t t0 = pk.data_bytes;
+      RowSpec rs(j * L.n, d.D - j * L.n, L.n);
+      L.seg[0] = {F_S, Sip / 16, L.n, 0, 0, 1, 0u};
+      l_add_pack(lp, rs, w ? w->embed_w : nul, Ke, 0, d.S_in, Sip);
+      L.seg[1] = {F_ACT, 1, L.n, 0, 0, 0, (uint32_t)(pk.data_bytes - t0)};
+      l_add_pack(lp, rs, w ? w->embed_w : nul, Ke, d.S_in, d.A, 16);
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+      const uint32_t at = add_vec(pk, w ? w->embed_b : nul, nul, j * L.n, std::max(0, std::min(L.n, d.D - j * L.n)), L.n);
+      if (j == 0) L.ep_off = at;
+    }
+    L.ep_floats = (uint32_t)L.n;
+    lp.layers.push_back(L);
+  }
+  // ---- GRU
+  {
+    LLayerH L;
+    constexpr int cw = kGruTile;
+    L.type = LE_GRU; L.dbuf = 1; L.out = F_HN; L.nseg = 2; L.n = 4 * cw;
+    L.NT = (Dp + cw - 1) / cw;
+    L.kc = kc_for(3 * cw);
+    L.w_off = pk.data_bytes;
+    for (int j = 0; j < L.NT; ++j) {
+      const size_t t0 = pk.data_bytes;
+      const int c0 = j * cw, v = std::max(0, std::min(cw, d.D - c0));
+      RowSpec rx;
+      rx.add(2 * d.D + c0, v, cw); rx.add(c0, v, cw); rx.add(d.D + c0, v, cw);
+      L.seg[0] = {F_X, Dp / 16, 3 * cw, 0, 0, 1, 0u};
+      l_add_pack(lp, rx, w ? w->w_ih : nul, d.D, 0, d.D, Dp);
+      RowSpec rh;
+      rh.add(c0, v, cw); rh.add(d.D + c0, v, cw); rh.add(2 * d.D + c0, v, cw);
+      L.seg[1] = {F_H, Dp / 16, 3 * cw, cw, 2 * cw, 0, (uint32_t)(pk.data_bytes - t0)};
+      l_add_pack(lp, rh, w ? w->w_hh : nul, d.D, 0, d.D, Dp);
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+      const uint32_t at = add_vec(pk, w ? w->b_ih : nul, w ? w->b_hh : nul, c0, v, cw);
+      add_vec(pk, w ? w->b_ih : nul, w ? w->b_hh : nul, d.D + c0, v, cw);
+      add_vec(pk, w ? w->b_ih : nul, nul, 2 * d.D + c0, v, cw);
+      add_vec(pk, w ? w->b_hh : nul, nul, 2 * d.D + c0, v, cw);
+      if (j == 0) L.ep_off = at;
+    }
+    L.ep_floats = 4 * cw;
+    lp.layers.push_back(L);
+  }
+  // ---- hidden layers of the two heads: prior h' -> ELU; posterior [h' | e_{t+1}] -> ELU
+  for (int post = 0; post < 2; ++post) {
+    LLayerH L;
+    L.type = LE_BIAS_ELU; L.dbuf = 1; L.out = post ? F_HIDQ : F_HID; L.nseg = post ? 2 : 1;
+    tiles(Hdp, 256, 16, L.NT, L.n);
+    L.kc = kc_for(L.n);
+    L.w_off = pk.data_bytes;
+    const float* W0 = w ? (post ? w->post0_w : w->prior0_w) : nul;
+    const float* b0 = w ? (post ? w->post0_b : w->prior0_b) : nul;
+    const int ld = post ? d.D + d.E : d.D;
+    for (int j = 0; j < L.NT; ++j) {
+      const size_t t0 = pk.data_bytes;
+      RowSpec rs(j * L.n, d.Hd - j * L.n, L.n);
+      L.seg[0] = {F_HN, Dp / 16, L.n, 0, 0, 1, 0u};
+      l_add_pack(lp, rs, W0, ld, 0, d.D, Dp);
+      if (post) {
+        L.seg[1] = {F_OBS, Ep / 16, L.n, 0, 0, 0, (uint32_t)(pk.data_bytes - t0)};
+        l_add_pack(lp, rs, W0, ld, d.D, d.E, Ep);
+      }
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+      const uint32_t at = add_vec(pk, b0, nul, j * L.n, std::max(0, std::min(L.n, d.Hd - j * L.n)), L.n);
+      if (j == 0) L.ep_off = at;
+    }
+    L.ep_floats = (uint32_t)L.n;
+    lp.layers.push_back(L);
+  }
+  // ---- heads + samples (layer = 0 prior, 1 posterior)
+  for (int post = 0; post < 2; ++post) {
+    LLayerH L;
+    L.dbuf = 1; L.out = post ? F_SN : F_SPRI; L.nseg = 1; L.layer = post;
+    L.w_off = pk.data_bytes;
+    const float* W2 = w ? (post ? w->post2_w : w->prior2_w) : nul;
+    const float* b2 = w ? (post ? w->post2_b : w->prior2_b) : nul;
+    const int in = post ? F_HIDQ : F_HID;
+    if (disc) {
+      L.type = LE_SAMPLE_DISC;
+      tiles(ceil_to(d.P, 32), 256, 32, L.NT, L.n);
+      for (int j = 0; j < L.NT; ++j) {
+        const size_t t0 = pk.data_bytes;
+        L.seg[0] = {in, Hdp / 16, L.n, 0, 0, 1, 0u};
+        l_add_pack(lp, RowSpec(j * L.n, d.P - j * L.n, L.n), W2, d.Hd, 0, d.Hd, Hdp);
+        L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+        const uint32_t at = add_vec(pk, b2, nul, j * L.n, std::max(0, std::min(L.n, d.P - j * L.n)), L.n);
+        if (j == 0) L.ep_off = at;
+      }
+      L.ep_floats = (uint32_t)L.n;
+    } else {
+      L.type = LE_SAMPLE_CONT; L.NT = 1; L.n = 2 * Sp;
+      RowSpec rs;
+      rs.add(0, d.S, Sp); rs.add(d.S, d.S, Sp);
+      L.seg[0] = {in, Hdp / 16, L.n, 0, 0, 1, 0u};
+      l_add_pack(lp, rs, W2, d.Hd, 0, d.Hd, Hdp);
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - L.w_off);
+      L.ep_off = add_vec(pk, b2, nul, 0, d.S, Sp);
+      add_vec(pk, b2, nul, d.S, d.S, Sp);
+      L.ep_floats = 2u * Sp;
+    }
+    L.kc = kc_for(L.n);
+    lp.layers.push_back(L);
+  }
+  // execution order of a step: embed, GRU, prior hidden, prior head, posterior hidden, posterior head
+  std::swap(lp.layers[3], lp.layers[4]);
+  for (const LLayerH& L : lp.layers) {
+    if (L.ep_floats * 4 > kLParamBytes || (L.ep_floats & 3)) return lp;
+    for (int s = 0; s < L.nseg; ++s)
+      if ((uint32_t)L.kc * (4096u + (uint32_t)L.seg[s].n * 32u) > kLSlotBytes) return lp;
+  }
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  pk.off_stage_tab = 256;
+  pk.off_job_tab = 512;
+  pk.off_packops = 768;
+  pk.off_eparams = al(pk.off_packops + pk.pack_ops.size() * sizeof(PackOp) + pk.vec_ops.size() * sizeof(VecOp));
+  pk.off_data = al(pk.off_eparams + pk.eparams_floats * sizeof(float));
+  pk.total_bytes = al(pk.off_data + pk.data_bytes);
+  pk.ok = true;
+  lp.ok = true;
+  return lp;
+}
+
+static LMem tcl_observe_layout(const LPlan& lp, const Dims& d) {
+  LMem m;
+  const int MT = (d.B + 127) / 128;
+  size_t off = kLTraceBytes;
+  auto place = [&](int buf, int steps) {
+    Region& r = m.r[buf];
+    r.tile_bytes = (uint32_t)(buf_width(lp, buf) / 8) * kLTileChunk;
+    r.step_bytes = (size_t)MT * r.tile_bytes;
+    r.steps = steps; r.where = 0; r.off = off;
+    off += ((size_t)steps * r.step_bytes + 1023) / 1024 * 1024;
+  };
+  place(F_H, 2); place(F_S, 1); place(F_SPRI, 1); place(F_X, 1); place(F_HID, 1); place(F_HIDQ, 1);
+  place(F_OBS, std::max(1, d.T)); place(F_ACT, std::max(1, d.T));
+  m.r[F_HN] = m.r[F_H]; m.r[F_SN] = m.r[F_S];
+  m.ws_bytes = off + 1024;
+  return m;
+}
+
+// fp32 [B][T][W] row-major -> bf16 panels [T][MT][Wp/8][128][8] (zeros past B / W)
+__global__ void tcl_to_panel_kernel(const float* __restrict__ src, uint8_t* dst, int B, int T, int W, int Wp, int MT) {
+  const int t = blockIdx.z, mt = blockIdx.y;
+  const int chunks = Wp / 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < chunks * 128; i += gridDim.x * blockDim.x) {
+    const int row = i & 127, k8 = i >> 7;
+    const long long b = (long long)mt * 128 + row;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = k8 * 8 + e;
+      v[e] = (b < B && col < W) ? src[(b * T + t) * W + col] : 0.f;
+    }
+    st_chunk_g(dst + (((size_t)t * MT + mt) * chunks + k8) * kLTileChunk + row * 16, v);
+  }
+}
+
+bool tcl_observe_supported(const Dims& d) { return tcl_make_observe_plan(d, nullptr).ok; }
+size_t tcl_observe_packed_bytes(const Dims& d) {
+  LPlan lp = tcl_make_observe_plan(d, nullptr);
+  return lp.ok ? lp.pk.total_bytes : 0;
+}
+size_t tcl_observe_workspace_bytes(const Dims& d) {
+  LPlan lp = tcl_make_observe_plan(d, nullptr);
+  return lp.ok ? tcl_observe_layout(lp, d).ws_bytes : 0;
+}
+int tcl_pack_observe_weights(const Dims& d, const wmrl_rssm_params* w, void* packed, cudaStream_t st) {
+  LPlan lp = tcl_make_observe_plan(d, w);
+  WMRL_REQUIRE(lp.ok, "pack_observe_weights: shape not supported by the layer-wise tcgen05 path");
+  return tc_pack_plan(lp.pk, (uint8_t*)packed, st);
+}
+
+int tcl_observe_fwd(const Dims& d, const void* packed, const float* obs, const float* act, const float* noise_pri,
+                    const float* noise_post, float* pri_deter, float* pri_stoch, float* pri_da, float* pri_db,
+                    float* post_deter, float* post_stoch, float* post_da, float* post_db, void* ws, cudaStream_t st) {
+  LPlan lp = tcl_make_observe_plan(d, nullptr);
+  WMRL_REQUIRE(lp.ok, "observe_fwd: shape not supported by the layer-wise tcgen05 path");
+  const LMem m = tcl_observe_layout(lp, d);
+  LCall c{&lp, &m, &d, (uint8_t*)ws, nullptr, nullptr, nullptr, (d.B + 127) / 128, 148, st};
+  if (int r = tcl_device_setup(c.nsm)) return r;
+  const uint8_t* img = (const uint8_t*)packed;
+  c.data = img + lp.pk.off_data;
+  c.ep = (const float*)(img + lp.pk.off_eparams);
+  const int T = d.T, MT = c.MT, H = T - 1;
+  // index 0 of both sequences = the zero initial state (rssm.py:166-172 / 215-220); h / s panels start at zero
+  tcl_init_kernel<<<dim3(8, MT), 256, 0, st>>>(nullptr, nullptr, pri_deter, pri_stoch, c.at(F_H, 0), c.at(F_S, 0), d.B, H, d.D,
+                                               d.S_in, lp.Dp, lp.Sip);
+  tcl_init_kernel<<<dim3(8, MT), 256, 0, st>>>(nullptr, nullptr, post_deter, post_stoch, c.at(F_H, 0), c.at(F_S, 0), d.B, H,
+                                               d.D, d.S_in, lp.Dp, lp.Sip);
+  WMRL_CUDA_OK(cudaGetLastError());
+  if (H < 1) return 0;
+  tcl_to_panel_kernel<<<dim3(8, MT, T), 256, 0, st>>>(obs, c.at(F_OBS, 0), d.B, T, d.E, lp.Ep, MT);
+  tcl_to_panel_kernel<<<dim3(1, MT, T), 256, 0, st>>>(act, c.at(F_ACT, 0), d.B, T, d.A, 16, MT);
+  WMRL_CUDA_OK(cudaGetLastError());
+  Dims dstep = d;
+  dstep.T = H;   // the sequence tensors hold H + 1 = T entries
+  LCall cs = c;
+  cs.d = &dstep;
+  for (int t = 0; t < H; ++t) {
+    auto step_of = [&](int buf) {
+      if (buf == F_H) return t & 1;
+      if (buf == F_HN) return (t + 1) & 1;
+      if (buf == F_OBS) return t + 1;
+      if (buf == F_ACT) return t;
+      return 0;
+    };
+    for (const LLayerH& L : lp.layers) {
+      LayerArgs a{};
+      a.t = t;
+      const bool post = L.layer == 1 && (L.type == LE_SAMPLE_DISC || L.type == LE_SAMPLE_CONT);
+      a.deter_seq = pri_deter;
+      a.stoch_seq = post ? post_stoch : pri_stoch; a.dist_a = post ? post_da : pri_da; a.dist_b = post ? post_db : pri_db;
+      a.actions = nullptr; a.idx = nullptr; a.noise = post ? noise_post : noise_pri;
+      a.trace = nullptr;
+      int ss[3];
+      for (int s = 0; s < L.nseg; ++s) ss[s] = step_of(L.seg[s].buf);
+      if (int r = tcl_launch(cs, L, a, ss, step_of(L.out))) return r;
+    }
+  }
+  // both sequences carry the same deterministic states (rssm.py:84-91)
+  WMRL_CUDA_OK(cudaMemcpyAsync(post_deter, pri_deter, (size_t)d.B * T * d.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

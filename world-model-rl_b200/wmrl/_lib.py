@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwmrl.so")
 MAX_ACTOR_LAYERS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 CONTINUOUS, DISCRETE = 0, 1
 FP32, BF16 = 0, 1
@@ -75,6 +75,9 @@ _SIGNATURES = {
                          [C.POINTER(ActorGradPtrs), C.POINTER(RssmPtrs), _P, _P, _P, C.c_size_t, _P]),
     "wmrl_observe_fwd": (C.c_int, [C.POINTER(Dims), C.POINTER(RssmPtrs)] + [_P] * 13 +
                          [C.c_size_t, _P, C.c_size_t, _P]),
+    "wmrl_observe_packed_bytes": (C.c_size_t, [C.POINTER(Dims)]),
+    "wmrl_pack_observe_weights": (C.c_int, [C.POINTER(Dims), C.POINTER(RssmPtrs), _P, _P]),
+    "wmrl_observe_fwd_bf16": (C.c_int, [C.POINTER(Dims)] + [_P] * 14 + [C.c_size_t, _P]),
     "wmrl_observe_bwd": (C.c_int, [C.POINTER(Dims), C.POINTER(RssmPtrs)] + [_P] * 21 +
                          [C.POINTER(RssmPtrs), _P, _P, _P, C.c_size_t, _P]),
     "wmrl_lambda_return_fwd": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P]),

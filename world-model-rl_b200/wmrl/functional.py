@@ -169,6 +169,66 @@ class PackedWeights:
         return buf
 
 
+class PackedObserveWeights:
+    """bf16 image of the RSSM weights (prior and posterior heads) for the filtering forward on the tcgen05 chain."""
+
+    def __init__(self):
+        self.key = None
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, cfg: PathConfig, rssm_p: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
+        lib = _lib.load()
+        key = (dataclasses.replace(cfg, record=True), tuple((p.data_ptr(), p._version) for p in rssm_p))
+        if self.key == key and self.buf is not None:
+            return self.buf
+        dev = rssm_p[0].device
+        d = cfg.dims(0, 0, precision=_lib.BF16)
+        n = lib.wmrl_observe_packed_bytes(C.byref(d))
+        if n == 0:
+            return None
+        buf = _bytes(n, dev)
+        r32 = [_f32c(p) for p in rssm_p]
+        w = _rssm_ptrs(r32)
+        _native(dev, lib.wmrl_pack_observe_weights, C.byref(d), C.byref(w), buf.data_ptr(), _stream_ptr(dev))
+        self.key, self.buf = key, buf
+        return buf
+
+
+def observe_rollout_bf16(cfg: PathConfig, packed: torch.Tensor, obs, act, noise_pri, noise_post, inits):
+    """no-grad posterior filtering on the bf16 layer-wise tcgen05 chain (wmrl_observe_fwd_bf16); same outputs as
+    ``ObserveRollout`` without a gradient record."""
+    lib = _lib.load()
+    dev = _require_cuda(obs, act, noise_pri, noise_post)
+    B, T = obs.shape[0], obs.shape[1]
+    disc = cfg.variant == _lib.DISCRETE
+    ob, ac, n1, n2 = _f32c(obs), _f32c(act), _f32c(noise_pri), _f32c(noise_post)
+
+    def seq_bufs():
+        de = torch.empty(B, T, cfg.D, device=dev)
+        st = torch.empty(B, T, cfg.S_in, device=dev)
+        if disc:
+            return de, st, torch.empty(B, T, cfg.C, cfg.S, device=dev), None
+        return de, st, torch.empty(B, T, cfg.S, device=dev), torch.empty(B, T, cfg.S, device=dev)
+
+    pri, post = seq_bufs(), seq_bufs()
+    d = cfg.dims(B, T, 0, _lib.BF16)
+    ws_n = lib.wmrl_workspace_bytes(C.byref(d), _lib.OP_OBSERVE)
+    ws = _bytes(ws_n, dev)
+    if B > 0 and T > 0:
+        _native(dev, lib.wmrl_observe_fwd_bf16, C.byref(d), packed.data_ptr(), ob.data_ptr(), ac.data_ptr(), n1.data_ptr(),
+                n2.data_ptr(), pri[0].data_ptr(), pri[1].data_ptr(), pri[2].data_ptr(), _lib.ptr(pri[3]), post[0].data_ptr(),
+                post[1].data_ptr(), post[2].data_ptr(), _lib.ptr(post[3]), ws.data_ptr(), ws_n, _stream_ptr(dev))
+    if T > 0:
+        pri[2][:, 0] = inits[0]
+        post[2][:, 0] = inits[2]
+        if not disc:
+            pri[3][:, 0] = inits[1]
+            post[3][:, 0] = inits[3]
+    if disc:
+        return pri[0], pri[1], pri[2], post[0], post[1], post[2]
+    return pri + post
+
+
 # ----------------------------------------------------------------------------
 # imagine
 # ----------------------------------------------------------------------------

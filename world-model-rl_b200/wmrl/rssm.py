@@ -21,7 +21,8 @@ import torch
 from torch import nn
 
 from . import _lib
-from .functional import ImagineRollout, ObserveRollout, PackedWeights, PathConfig
+from .functional import (ImagineRollout, ObserveRollout, PackedObserveWeights, PackedWeights, PathConfig,
+                         observe_rollout_bf16)
 from .state import (InternalStateContinuous, InternalStateContinuousSequence, InternalStateDiscrete,
                     InternalStateDiscreteSequence)
 
@@ -120,6 +121,7 @@ class RSSMBase(nn.Module):
             nn.Linear(hidden_size, parameterized_stoch_size))
         self.set_precision(precision)
         self._packed = PackedWeights()
+        self._packed_obs = PackedObserveWeights()
 
     # ------------------------------------------------------------------ config
     def set_precision(self, precision: str) -> "RSSMBase":
@@ -248,8 +250,18 @@ class RSSMBase(nn.Module):
             inits = (init_pri.logits, None, init_post.logits, None)
         else:
             inits = (init_pri.mean, init_pri.std, init_post.mean, init_post.std)
-        outs = ObserveRollout.apply(cfg, obs_embeds, action_embs.to(device), n_pri, n_post, *inits,
-                                    *self._rssm_tensors())
+        rssm_p = self._rssm_tensors()
+        packed = None
+        if (cfg.precision == _lib.BF16 and T > 1 and obs_embeds.is_cuda
+                and not (torch.is_grad_enabled() and (obs_embeds.requires_grad or action_embs.requires_grad
+                                                      or any(p.requires_grad for p in rssm_p)))):
+            # filtering without a gradient record (evaluation, acting, start states of imagination): bf16 tcgen05 chain
+            packed = self._packed_obs.get(cfg, rssm_p)
+        if packed is not None:
+            outs = observe_rollout_bf16(cfg, packed, obs_embeds, action_embs.to(device), n_pri, n_post,
+                                        tuple(None if t is None else t.to(device) for t in inits))
+        else:
+            outs = ObserveRollout.apply(cfg, obs_embeds, action_embs.to(device), n_pri, n_post, *inits, *rssm_p)
         cont_cls, disc_cls = _sequence_types()
         if self.variant == _lib.DISCRETE:
             pri = disc_cls(deter_states=outs[0], stoch_states=outs[1], logits=outs[2])
