@@ -348,6 +348,8 @@ __device__ __forceinline__ void lepi_sample_cont(const LCtx& c) {
 __device__ __forceinline__ uint32_t stage_addr(uint32_t base, int r16, int chunk) {
   return base + (uint32_t)r16 * 128u + (uint32_t)((chunk ^ (r16 & 7)) * 16);
 }
+__device__ __forceinline__ void load_rows32(const LCtx& c, const float* row0, long long ld, int nrows_valid, int ncols_valid,
+                                            float (&out)[32]);
 template <int S>
 __device__ __forceinline__ void lepi_sample_disc(const LCtx& c) {
   const LayerArgs& p = *c.p;
@@ -390,35 +392,14 @@ __device__ __forceinline__ void lepi_sample_disc(const LCtx& c) {
       __syncwarp();
     }
     LPROBE(c, 2);
-    // ---- q ~ Exp(1) of this block: coalesced loads -> staging -> the row's owner
+    // ---- q ~ Exp(1) of this block: coalesced loads (all eight in flight) -> staging -> the row's owner
     float qv[32];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r16 = i * 4 + sub;
-        const long long br = b0 + half * 16 + r16;
-        float4 q4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (br < p.B && col + chunk * 4 < P)
-          q4 = *reinterpret_cast<const float4*>(p.noise + ((long long)p.t * p.B + br) * P + col + chunk * 4);
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_addr(c.stage, r16, chunk)), "f"(q4.x), "f"(q4.y),
-                     "f"(q4.z), "f"(q4.w) : "memory");
-      }
-      __syncwarp();
-      if ((lane >> 4) == half) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float4 v = lds4(stage_addr(c.stage, lane & 15, k));
-          qv[4 * k] = v.x; qv[4 * k + 1] = v.y; qv[4 * k + 2] = v.z; qv[4 * k + 3] = v.w;
-        }
-      }
-      __syncwarp();
-    }
+    load_rows32(c, p.noise + ((long long)p.t * p.B + b0) * P + col, P, (int)max(0LL, min(32LL, (long long)p.B - b0)),
+                min(32, P - col), qv);
     LPROBE(c, 3);
     // ---- per group: p = softmax(l - logsumexp(l)) = exp(l - max) / sum; idx = first argmax(p / q).  The common
     // factor 1 / sum does not move the argmax and p_j / q_j > p_b / q_b <=> e_j q_b > e_b q_j (all positive), so the
     // draw costs one ex2 per class and no divisions.
-    uint32_t packed = 0;   // this row's draws, S bits per group
     int bi[32 / S];
 #pragma unroll
     for (int g = 0; g < 32 / S; ++g) {
@@ -437,25 +418,13 @@ __device__ __forceinline__ void lepi_sample_disc(const LCtx& c) {
         b = better ? j : b;
       }
       bi[g] = b;
-      packed |= (uint32_t)b << ((g * S) & 31);
       const int grp = (col / S) + g;
       if (c.valid && grp < p.C && p.idx) p.idx[(c.b * p.H + p.t) * p.C + grp] = b;
     }
     LPROBE(c, 4);
-    // ---- forward value of the straight-through sample, exactly one_hot(idx): fp32 sequence (coalesced, the draws
-    // travel by shuffle) + bf16 panel chunk of the row's owner
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = i * 4 + sub;
-      const uint32_t pk = __shfl_sync(0xffffffffu, packed, r);
-      const int g = (chunk * 4) / S;
-      const int v = (int)((S >= 32) ? pk : ((pk >> ((g * S) & 31)) & ((1u << (S & 31)) - 1u)));
-      const int e0 = (chunk * 4) % S;
-      const long long br = b0 + r;
-      if (br < p.B && col + chunk * 4 < P)
-        *reinterpret_cast<float4*>(p.stoch_seq + (br * T1 + p.t + 1) * P + col + chunk * 4) =
-            make_float4(e0 == v ? 1.f : 0.f, e0 + 1 == v ? 1.f : 0.f, e0 + 2 == v ? 1.f : 0.f, e0 + 3 == v ? 1.f : 0.f);
-    }
+    // ---- forward value of the straight-through sample, exactly one_hot(idx): the bf16 panel chunk of the row's
+    // owner feeds the next step; the fp32 `stoch` sequence the reference returns is expanded from the indices by
+    // tcl_onehot_kernel after the scan (a streaming kernel on all SMs instead of 8 KB per row on this critical path)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float oh[8];
@@ -1089,6 +1058,21 @@ __global__ void tcl_init_kernel(const float* __restrict__ deter0, const float* _
 // --------------------------------------------------------------------------
 // BPTT helpers outside the GEMM chain
 // --------------------------------------------------------------------------
+// stoch[b][t+1][c*S + j] = (j == idx[b][t][c]) for every step of a discrete rollout (state/discrete.py:27-32 forward value)
+__global__ void tcl_onehot_kernel(const int32_t* __restrict__ idx, float* __restrict__ stoch, long long B, int H, int C, int S) {
+  const long long n4 = B * H * (long long)(C * S / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int per = C * S / 4;
+    const long long bt = i / per;
+    const int e0 = (int)(i % per) * 4;
+    const long long b = bt / H;
+    const int t = (int)(bt % H);
+    const int v = idx[bt * C + e0 / S], j0 = e0 % S;
+    *reinterpret_cast<float4*>(stoch + (b * (H + 1) + t + 1) * (long long)(C * S) + e0) =
+        make_float4(j0 == v ? 1.f : 0.f, j0 + 1 == v ? 1.f : 0.f, j0 + 2 == v ? 1.f : 0.f, j0 + 3 == v ? 1.f : 0.f);
+  }
+}
+
 // carry rows of dL/dh: the upstream gradient of the LAST deter state (zero where absent / padding)
 __global__ void tcl_carry_init_kernel(float* carry_h, const float* g_deter, int B, int H, int D, int Dp, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // panel order: [tile][col/4][row][4]
@@ -1691,7 +1675,8 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
 struct Region { size_t off = 0; uint32_t tile_bytes = 0; size_t step_bytes = 0; int steps = 0; int where = 0; };   // where: 0 ws, 1 saved
 struct LMem {
   Region r[BUF_COUNT];
-  size_t carry_h = 0, carry_s = 0;   // fp32 [MT*128][Dp] / [MT*128][Sip] in the backward workspace
+  size_t carry_h = 0, carry_s = 0;   // fp32 carry panels in the backward workspace
+  size_t idx_pri = 0, idx_post = 0;  // filtering: int32 [B][T-1][C] draws of the two heads (discrete)
   size_t ws_bytes = 0, saved_bytes = 0;
 };
 constexpr size_t kLTraceBytes = 8192;
@@ -1872,6 +1857,10 @@ int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, cons
       for (int s = 0; s < L.nseg; ++s) ss[s] = step_of(L.seg[s].buf);
       if (int r = tcl_launch(c, L, a, ss, step_of(L.out))) return r;
     }
+  }
+  if (d.variant == WMRL_DISCRETE) {
+    tcl_onehot_kernel<<<4 * c.nsm, 256, 0, st>>>(idx, stoch_seq, d.B, d.T, d.C, d.S);
+    WMRL_CUDA_OK(cudaGetLastError());
   }
   return 0;
 }
@@ -2161,6 +2150,9 @@ static LMem tcl_observe_layout(const LPlan& lp, const Dims& d) {
   place(F_H, 2); place(F_S, 1); place(F_SPRI, 1); place(F_X, 1); place(F_HID, 1); place(F_HIDQ, 1);
   place(F_OBS, std::max(1, d.T)); place(F_ACT, std::max(1, d.T));
   m.r[F_HN] = m.r[F_H]; m.r[F_SN] = m.r[F_S];
+  const size_t ib = ((size_t)d.B * std::max(1, d.T) * d.C * sizeof(int32_t) + 1023) / 1024 * 1024;
+  m.idx_pri = off; off += ib;
+  m.idx_post = off; off += ib;
   m.ws_bytes = off + 1024;
   return m;
 }
@@ -2237,12 +2229,18 @@ int tcl_observe_fwd(const Dims& d, const void* packed, const float* obs, const f
       const bool post = L.layer == 1 && (L.type == LE_SAMPLE_DISC || L.type == LE_SAMPLE_CONT);
       a.deter_seq = pri_deter;
       a.stoch_seq = post ? post_stoch : pri_stoch; a.dist_a = post ? post_da : pri_da; a.dist_b = post ? post_db : pri_db;
-      a.actions = nullptr; a.idx = nullptr; a.noise = post ? noise_post : noise_pri;
+      a.actions = nullptr; a.noise = post ? noise_post : noise_pri;
+      a.idx = (int32_t*)((uint8_t*)ws + (post ? m.idx_post : m.idx_pri));
       a.trace = nullptr;
       int ss[3];
       for (int s = 0; s < L.nseg; ++s) ss[s] = step_of(L.seg[s].buf);
       if (int r = tcl_launch(cs, L, a, ss, step_of(L.out))) return r;
     }
+  }
+  if (d.variant == WMRL_DISCRETE) {
+    tcl_onehot_kernel<<<4 * c.nsm, 256, 0, st>>>((const int32_t*)((uint8_t*)ws + m.idx_pri), pri_stoch, d.B, H, d.C, d.S);
+    tcl_onehot_kernel<<<4 * c.nsm, 256, 0, st>>>((const int32_t*)((uint8_t*)ws + m.idx_post), post_stoch, d.B, H, d.C, d.S);
+    WMRL_CUDA_OK(cudaGetLastError());
   }
   // both sequences carry the same deterministic states (rssm.py:84-91)
   WMRL_CUDA_OK(cudaMemcpyAsync(post_deter, pri_deter, (size_t)d.B * T * d.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
