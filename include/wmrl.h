@@ -214,6 +214,21 @@ WMRL_API int wmrl_observe_bwd(const wmrl_dims* d, const wmrl_rssm_params* w, con
                      size_t ws_bytes, void* stream);
 
 /*
+ * KL(prior || posterior) of the two sequences wmrl_observe_fwd returns, with the free-nats clamp of WorldModel.update
+ * (world_model.py:131-141): kl[B][T-1] per (row, t >= 1) summed over the latent (Independent(Normal, 1) /
+ * Independent(OneHotCategoricalStraightThrough, 1), state/continuous.py:79-84, state/discrete.py:77-79);
+ * sums[0] += sum max(kl, rho), sums[1] += sum kl (the caller zero-fills sums and divides by B (T-1)).
+ * *_a = means | logits, *_b = stds | NULL, all [B][T][.] as produced by the observe calls (index 0 is skipped).
+ * bwd: gradients of  scale * sum_rows max(kl_row, rho)  w.r.t. the four parameter tensors (index 0 untouched: the
+ * caller zero-fills); scale = upstream gradient / (B (T-1)).
+ */
+WMRL_API int wmrl_kl_loss_fwd(const wmrl_dims* d, const float* pri_a, const float* pri_b, const float* post_a,
+                     const float* post_b, float rho, float* kl, float* sums, void* stream);
+WMRL_API int wmrl_kl_loss_bwd(const wmrl_dims* d, const float* pri_a, const float* pri_b, const float* post_a,
+                     const float* post_b, float rho, float scale, float* g_pri_a, float* g_pri_b, float* g_post_a,
+                     float* g_post_b, void* stream);
+
+/*
  * lambda-return targets of ValueGradTrainer.value_loss (value_trainer.py:126-134
  * over :62-113) as one O(H) scan per row; V, r, d, out: [B][H] (the trailing
  * singleton of the reference's [B,H,1] dropped).  d is the pre-processed 0/1

@@ -1,0 +1,137 @@
+// World-model loss side of posterior filtering (WorldModel.update, world_model.py:128-141): the KL term between the
+// prior and posterior sequences that observe_rollout returns, with the free-nats clamp, as ONE fused pass over the
+// distribution parameters (the reference builds two torch.distributions objects, D.kl_divergence, torch.max, two
+// means: ~20 elementwise launches over [B,T,.] tensors).  HBM-bound: each parameter is read once forward, once
+// backward.
+//   continuous: KL(N(m1,s1) || N(m2,s2)) summed over the S latent dims (D.Independent(Normal, 1), state/continuous.py:79-84)
+//   discrete:   KL(Cat(l1) || Cat(l2)) summed over the C groups (Independent(OneHotCategoricalStraightThrough, 1),
+//               state/discrete.py:77-79; the KL of one-hot categoricals is the categorical KL)
+// Index 0 of the sequences (the initial state) is excluded, as get_dist() does.
+#include "common.cuh"
+
+namespace wmrl {
+
+__device__ __forceinline__ float kl_warp_sum(float v) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+__device__ __forceinline__ float kl_warp_max(float v) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, s));
+  return v;
+}
+
+// one warp per (b, t >= 1).  kBwd: write the parameter gradients of  scale * sum_rows max(kl_row, rho)
+template <bool kDisc, bool kBwd>
+__global__ void kl_kernel(const float* __restrict__ pa, const float* __restrict__ pb, const float* __restrict__ qa,
+                          const float* __restrict__ qb, long long B, int T, int S, int C, float rho, float scale,
+                          float* __restrict__ kl_out, float* __restrict__ sums, float* g_pa, float* g_pb, float* g_qa,
+                          float* g_qb) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * (T - 1)) return;
+  const long long b = warp / (T - 1);
+  const int t = (int)(warp % (T - 1)) + 1;
+  const int W = kDisc ? C * S : S;
+  const long long o = (b * T + t) * W;
+  float kl = 0.f;
+  if (!kDisc) {
+    for (int j = lane; j < S; j += 32) {
+      const float m1 = pa[o + j], s1 = pb[o + j], m2 = qa[o + j], s2 = qb[o + j];
+      const float dm = m1 - m2, r = s1 / s2;
+      // torch's kl_normal_normal: 0.5 * (var_ratio + t1 - 1 - log(var_ratio)), var_ratio = (s1/s2)^2, t1 = ((m1-m2)/s2)^2
+      const float vr = r * r, t1 = (dm / s2) * (dm / s2);
+      kl += 0.5f * (vr + t1 - 1.f - logf(vr));
+    }
+    kl = kl_warp_sum(kl);
+  } else {
+    for (int c = 0; c < C; ++c) {
+      float part = 0.f;
+      for (int j0 = 0; j0 < S; j0 += 32) {   // S <= 32 in every config; the loop keeps larger S correct when one chunk
+        const int j = j0 + lane;             // holds a whole group (S <= 32) - asserted on the host
+        const float l1 = j < S ? pa[o + c * S + j] : -INFINITY, l2 = j < S ? qa[o + c * S + j] : -INFINITY;
+        const float mx1 = kl_warp_max(l1), mx2 = kl_warp_max(l2);
+        const float e1 = j < S ? expf(l1 - mx1) : 0.f, e2 = j < S ? expf(l2 - mx2) : 0.f;
+        const float z1 = kl_warp_sum(e1), z2 = kl_warp_sum(e2);
+        const float lp1 = l1 - mx1 - logf(z1), lp2 = l2 - mx2 - logf(z2);
+        part += j < S ? (e1 / z1) * (lp1 - lp2) : 0.f;
+      }
+      kl += kl_warp_sum(part);
+    }
+  }
+  if (!kBwd) {
+    if (lane == 0) {
+      kl_out[b * (T - 1) + t - 1] = kl;
+      atomicAdd(sums, fmaxf(kl, rho));
+      atomicAdd(sums + 1, kl);
+    }
+    return;
+  }
+  const float g = (kl > rho) ? scale : 0.f;   // d max(kl, rho) / d kl
+  if (!kDisc) {
+    for (int j = lane; j < S; j += 32) {
+      const float m1 = pa[o + j], s1 = pb[o + j], m2 = qa[o + j], s2 = qb[o + j];
+      const float dm = m1 - m2, i2 = 1.f / (s2 * s2);
+      g_pa[o + j] = g * dm * i2;
+      g_qa[o + j] = -g * dm * i2;
+      g_pb[o + j] = g * (s1 * i2 - 1.f / s1);
+      g_qb[o + j] = g * (1.f / s2 - (s1 * s1 + dm * dm) * i2 / s2);
+    }
+  } else {
+    for (int c = 0; c < C; ++c) {
+      const int j = lane;
+      const float l1 = j < S ? pa[o + c * S + j] : -INFINITY, l2 = j < S ? qa[o + c * S + j] : -INFINITY;
+      const float mx1 = kl_warp_max(l1), mx2 = kl_warp_max(l2);
+      const float e1 = j < S ? expf(l1 - mx1) : 0.f, e2 = j < S ? expf(l2 - mx2) : 0.f;
+      const float z1 = kl_warp_sum(e1), z2 = kl_warp_sum(e2);
+      const float p1 = e1 / z1, p2 = e2 / z2;
+      const float d = (l1 - mx1 - logf(z1)) - (l2 - mx2 - logf(z2));
+      const float klc = kl_warp_sum(j < S ? p1 * d : 0.f);
+      if (j < S) {
+        g_pa[o + c * S + j] = g * p1 * (d - klc);     // d KL / d l1_j = p_j (log p_j - log q_j - KL)
+        g_qa[o + c * S + j] = g * (p2 - p1);          // d KL / d l2_j = q_j - p_j
+      }
+    }
+  }
+}
+
+}  // namespace wmrl
+
+using namespace wmrl;
+
+extern "C" {
+
+int wmrl_kl_loss_fwd(const wmrl_dims* d, const float* pri_a, const float* pri_b, const float* post_a, const float* post_b,
+                     float rho, float* kl, float* sums, void* stream) {
+  if (int r = check_dims(d, 1)) return r;
+  Dims dd(*d);
+  if (dd.B == 0 || dd.T <= 1) return 0;
+  const bool disc = dd.variant == WMRL_DISCRETE;
+  WMRL_REQUIRE(pri_a && post_a && kl && sums && (disc || (pri_b && post_b)), "kl_loss_fwd: NULL tensor");
+  WMRL_REQUIRE(!disc || dd.S <= 32, "kl_loss: more than 32 classes per categorical group is not supported");
+  const long long rows = (long long)dd.B * (dd.T - 1);
+  const unsigned blocks = (unsigned)((rows * 32 + 255) / 256);
+  if (disc) kl_kernel<true, false><<<blocks, 256, 0, (cudaStream_t)stream>>>(pri_a, nullptr, post_a, nullptr, dd.B, dd.T, dd.S, dd.C, rho, 0.f, kl, sums, nullptr, nullptr, nullptr, nullptr);
+  else kl_kernel<false, false><<<blocks, 256, 0, (cudaStream_t)stream>>>(pri_a, pri_b, post_a, post_b, dd.B, dd.T, dd.S, 1, rho, 0.f, kl, sums, nullptr, nullptr, nullptr, nullptr);
+  WMRL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int wmrl_kl_loss_bwd(const wmrl_dims* d, const float* pri_a, const float* pri_b, const float* post_a, const float* post_b,
+                     float rho, float scale, float* g_pri_a, float* g_pri_b, float* g_post_a, float* g_post_b, void* stream) {
+  if (int r = check_dims(d, 1)) return r;
+  Dims dd(*d);
+  if (dd.B == 0 || dd.T <= 1) return 0;
+  const bool disc = dd.variant == WMRL_DISCRETE;
+  WMRL_REQUIRE(pri_a && post_a && g_pri_a && g_post_a && (disc || (pri_b && post_b && g_pri_b && g_post_b)), "kl_loss_bwd: NULL tensor");
+  WMRL_REQUIRE(!disc || dd.S <= 32, "kl_loss: more than 32 classes per categorical group is not supported");
+  const long long rows = (long long)dd.B * (dd.T - 1);
+  const unsigned blocks = (unsigned)((rows * 32 + 255) / 256);
+  if (disc) kl_kernel<true, true><<<blocks, 256, 0, (cudaStream_t)stream>>>(pri_a, nullptr, post_a, nullptr, dd.B, dd.T, dd.S, dd.C, rho, scale, nullptr, nullptr, g_pri_a, nullptr, g_post_a, nullptr);
+  else kl_kernel<false, true><<<blocks, 256, 0, (cudaStream_t)stream>>>(pri_a, pri_b, post_a, post_b, dd.B, dd.T, dd.S, 1, rho, scale, nullptr, nullptr, g_pri_a, g_pri_b, g_post_a, g_post_b);
+  WMRL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

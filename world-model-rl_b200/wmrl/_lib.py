@@ -80,6 +80,8 @@ _SIGNATURES = {
     "wmrl_observe_fwd_bf16": (C.c_int, [C.POINTER(Dims)] + [_P] * 14 + [C.c_size_t, _P]),
     "wmrl_observe_bwd": (C.c_int, [C.POINTER(Dims), C.POINTER(RssmPtrs)] + [_P] * 21 +
                          [C.POINTER(RssmPtrs), _P, _P, _P, C.c_size_t, _P]),
+    "wmrl_kl_loss_fwd": (C.c_int, [C.POINTER(Dims), _P, _P, _P, _P, C.c_float, _P, _P, _P]),
+    "wmrl_kl_loss_bwd": (C.c_int, [C.POINTER(Dims), _P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
     "wmrl_lambda_return_fwd": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P]),
     "wmrl_lambda_return_bwd": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),
     "wmrl_done_mask": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),

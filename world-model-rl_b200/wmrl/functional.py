@@ -517,6 +517,56 @@ def lambda_return(V: torch.Tensor, r: torch.Tensor, d: torch.Tensor, gamma: floa
     return LambdaReturn.apply(V, r, d, float(gamma), float(lam)).reshape(shape)
 
 
+class KLLoss(torch.autograd.Function):
+    """(mean max(KL, rho), mean KL) of prior || posterior over [B, T-1] (world_model.py:131-141) in one fused pass
+    each way.  Inputs are the sequences' distribution tensors [B,T,.]; b tensors are None for the discrete variant."""
+
+    @staticmethod
+    def forward(ctx, cfg: PathConfig, rho: float, pa, pb, qa, qb):
+        lib = _lib.load()
+        dev = _require_cuda(pa, qa)
+        B, T = pa.shape[0], pa.shape[1]
+        pa32, qa32 = _f32c(pa), _f32c(qa)
+        pb32 = None if pb is None else _f32c(pb)
+        qb32 = None if qb is None else _f32c(qb)
+        kl = torch.empty(B, max(T - 1, 0), device=dev)
+        sums = torch.zeros(2, device=dev)
+        d = cfg.dims(B, T, 0, _lib.FP32)
+        if B > 0 and T > 1:
+            _native(dev, lib.wmrl_kl_loss_fwd, C.byref(d), pa32.data_ptr(), _lib.ptr(pb32), qa32.data_ptr(), _lib.ptr(qb32),
+                    float(rho), kl.data_ptr(), sums.data_ptr(), _stream_ptr(dev))
+        ctx.cfg, ctx.rho, ctx.has_b = cfg, float(rho), pb is not None
+        empty = torch.empty(0, device=dev)
+        ctx.save_for_backward(pa32, pb32 if pb32 is not None else empty, qa32, qb32 if qb32 is not None else empty)
+        n = max(B * (T - 1), 1)
+        ctx.mark_non_differentiable(kl)
+        return sums[0] / n, sums[1] / n, kl
+
+    @staticmethod
+    def backward(ctx, g_clamped, g_mean, _g_kl):
+        lib = _lib.load()
+        pa, pb, qa, qb = ctx.saved_tensors
+        if g_mean is not None and bool((g_mean != 0).any()):
+            raise RuntimeError("wmrl: KLLoss differentiates the clamped mean only (the reference reports the plain mean as a float)")
+        B, T = pa.shape[0], pa.shape[1]
+        dev = pa.device
+        d = ctx.cfg.dims(B, T, 0, _lib.FP32)
+        g_pa, g_qa = torch.zeros_like(pa), torch.zeros_like(qa)
+        g_pb = torch.zeros_like(pb) if ctx.has_b else None
+        g_qb = torch.zeros_like(qb) if ctx.has_b else None
+        if B > 0 and T > 1:
+            scale = float(g_clamped) / (B * (T - 1))
+            _native(dev, lib.wmrl_kl_loss_bwd, C.byref(d), pa.data_ptr(), _lib.ptr(pb if ctx.has_b else None), qa.data_ptr(),
+                    _lib.ptr(qb if ctx.has_b else None), ctx.rho, scale, g_pa.data_ptr(), _lib.ptr(g_pb), g_qa.data_ptr(),
+                    _lib.ptr(g_qb), _stream_ptr(dev))
+        return None, None, g_pa, g_pb, g_qa, g_qb
+
+
+def kl_loss(cfg: PathConfig, rho: float, prior_a, prior_b, post_a, post_b):
+    """-> (mean over [B,T-1] of max(KL, rho), mean KL, kl[B,T-1])."""
+    return KLLoss.apply(cfg, float(rho), prior_a, prior_b, post_a, post_b)
+
+
 def done_mask(dones: torch.Tensor) -> torch.Tensor:
     """shift right, threshold at 0.5, running max (value_trainer.py:148-149)."""
     lib = _lib.load()

@@ -88,12 +88,32 @@ class WorldModel(nn.Module):
             observations = self.decoder(features) if with_observations else None
         return ImaginedRollouts(rewards=rewards, dones=dones, features=features, observations=observations)
 
+    def _kl_terms(self, prior_seq, post_seq, rho: float):
+        """(mean max(KL(prior || posterior), rho), mean KL) over [B, T-1] (world_model.py:131-141): one fused libwmrl
+        pass over the distribution parameters on CUDA, the torch.distributions expression otherwise."""
+        from . import _lib
+        from .functional import PathConfig, kl_loss
+        disc = hasattr(prior_seq, "logits")
+        a1 = prior_seq.logits if disc else prior_seq.means
+        if a1.is_cuda and a1.dtype == torch.float32 and a1.shape[1] > 1:
+            if disc:
+                C_, S_ = a1.shape[2], a1.shape[3]
+                if S_ <= 32:
+                    cfg = PathConfig(variant=_lib.DISCRETE, D=1, S=S_, C=C_, A=1, Hd=1, E=1)
+                    kc, km, _ = kl_loss(cfg, rho, a1, None, post_seq.logits, None)
+                    return kc, km
+            else:
+                cfg = PathConfig(variant=_lib.CONTINUOUS, D=1, S=a1.shape[2], C=1, A=1, Hd=1, E=1)
+                kc, km, _ = kl_loss(cfg, rho, a1, prior_seq.stds, post_seq.means, post_seq.stds)
+                return kc, km
+        kl = D.kl_divergence(prior_seq.get_dist(), post_seq.get_dist())
+        return torch.clamp_min(kl, rho).mean(), kl.mean()
+
     # ---- loss side (torch glue) ---------------------------------------------
     def update(self, prior_state_sequence, posterior_state_sequence, obs, reward, done) -> WorldModelLosses:
         p = self.params
         feats = posterior_state_sequence.get_features()
-        kl = D.kl_divergence(prior_state_sequence.get_dist(), posterior_state_sequence.get_dist())
-        kl_clamped = torch.clamp_min(kl, p.rho).mean()
+        kl_clamped, kl_mean = self._kl_terms(prior_state_sequence, posterior_state_sequence, p.rho)
         reward_loss = _unit_normal_nll(self.reward_model(feats), reward[:, 1:], 1)
         done_loss = F.binary_cross_entropy_with_logits(self.done_model(feats), done[:, 1:].float())
         decoded = self.decoder(feats)
@@ -107,7 +127,7 @@ class WorldModel(nn.Module):
                 + p.done_coeff * done_loss)
         grad_norm = self.opt.backward(loss)
         self.opt.update_parameters()
-        return WorldModelLosses(recon_loss=recon_loss.item(), dynamic_model_loss=kl.mean().item(),
+        return WorldModelLosses(recon_loss=recon_loss.item(), dynamic_model_loss=kl_mean.item(),
                                 dynamic_model_loss_clamped=kl_clamped.item(), reward_loss=reward_loss.item(),
                                 done_loss=done_loss.item(), loss=loss.item(), grad_norm=grad_norm.item())
 
