@@ -187,18 +187,33 @@ WMRL_API int wmrl_observe_fwd(const wmrl_dims* d, const wmrl_rssm_params* w, con
                      void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, void* stream);
 
 /*
- * The same forward on the bf16 layer-wise tcgen05 chain (no gradient record: filtering for evaluation, acting and
- * for the start states of imagination, which the reference detaches - state/discrete.py:81-89).  The RSSM weights
- * (prior AND posterior heads) are packed once per version with wmrl_pack_observe_weights into a buffer of
- * wmrl_observe_packed_bytes (0: shape not supported); workspace from wmrl_workspace_bytes(d with WMRL_BF16, 1).
- * Same tensors and index conventions as wmrl_observe_fwd.
+ * The same forward on the bf16 layer-wise tcgen05 chain.  The RSSM weights (prior AND posterior heads, plus their
+ * transposes for the backward) are packed once per version with wmrl_pack_observe_weights into a buffer of
+ * wmrl_observe_packed_bytes (0: shape not supported); d->precision = WMRL_BF16; buffer sizes from
+ * wmrl_workspace_bytes(d, 1) / wmrl_saved_bytes(d, 1) with the flags of the call.  With WMRL_FLAG_SAVE_FOR_BWD the
+ * per-step activation panels are kept in `saved` for wmrl_observe_bwd_bf16.  Same tensors and index conventions as
+ * wmrl_observe_fwd.
  */
 WMRL_API size_t wmrl_observe_packed_bytes(const wmrl_dims* d);
 WMRL_API int wmrl_pack_observe_weights(const wmrl_dims* d, const wmrl_rssm_params* w, void* packed, void* stream);
 WMRL_API int wmrl_observe_fwd_bf16(const wmrl_dims* d, const void* packed, const float* obs_embeds, const float* actions,
                           const float* noise_prior, const float* noise_post, float* pri_deter, float* pri_stoch,
                           float* pri_dist_a, float* pri_dist_b, float* post_deter, float* post_stoch, float* post_dist_a,
-                          float* post_dist_b, void* ws, size_t ws_bytes, void* stream);
+                          float* post_dist_b, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, void* stream);
+/*
+ * Full backward of the above (world-model training, world_model.py:120-163) on the same chain: dgrad GEMMs with fused
+ * epilogues backwards in time, RSSM weight gradients as big-K tcgen05 GEMMs over the recorded panels, d obs_embeds and
+ * d actions.  d->flags must carry WMRL_FLAG_BACKWARD (workspace sizing).  g_deter = dL/d pri_deter + dL/d post_deter
+ * (both sequences hold the same deterministic states); any other g_* may be NULL.  Gradients are ACCUMULATED into gw
+ * (caller zero-fills); g_obs_embeds [B][T][E] / g_actions [B][T][A] are written for the entries the scan reads
+ * (obs 1..T-1, actions 0..T-2; the caller zero-fills the rest); either may be NULL.
+ */
+WMRL_API int wmrl_observe_bwd_bf16(const wmrl_dims* d, const void* packed, const float* noise_prior, const float* noise_post,
+                          const float* pri_deter, const float* pri_dist_a, const float* pri_dist_b, const float* post_dist_a,
+                          const float* post_dist_b, const void* saved, const float* g_deter, const float* g_pri_stoch,
+                          const float* g_pri_dist_a, const float* g_pri_dist_b, const float* g_post_stoch,
+                          const float* g_post_dist_a, const float* g_post_dist_b, const wmrl_rssm_grads* gw,
+                          float* g_obs_embeds, float* g_actions, void* ws, size_t ws_bytes, void* stream);
 
 /* Full backward (weight grads + d obs_embeds + d actions) of observe_fwd, as
  * needed by WorldModel.update (world_model.py:120-163). */

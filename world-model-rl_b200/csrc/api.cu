@@ -89,6 +89,7 @@ size_t wmrl_saved_bytes(const wmrl_dims* d, int op) {
     if (path == 1 && tc_train_supported(dd)) return tc_saved_bytes(dd);
     if (path == 2 && tcl_train_supported(dd)) return tcl_saved_bytes(dd);
   }
+  if (op == 1 && d->precision == WMRL_BF16 && tcl_observe_supported(dd)) return tcl_observe_saved_bytes(dd);
   return f32_saved_bytes(dd, op);
 }
 
@@ -130,20 +131,46 @@ int wmrl_pack_observe_weights(const wmrl_dims* d, const wmrl_rssm_params* w, voi
 int wmrl_observe_fwd_bf16(const wmrl_dims* d, const void* packed, const float* obs_embeds, const float* actions,
                           const float* noise_prior, const float* noise_post, float* pri_deter, float* pri_stoch,
                           float* pri_dist_a, float* pri_dist_b, float* post_deter, float* post_stoch, float* post_dist_a,
-                          float* post_dist_b, void* ws, size_t ws_bytes, void* stream) {
+                          float* post_dist_b, void* saved, size_t saved_bytes, void* ws, size_t ws_bytes, void* stream) {
   if (int r = check_dims(d, 1)) return r;
   Dims dd(*d);
   if (dd.B == 0 || dd.T == 0) return 0;
+  WMRL_REQUIRE(d->precision == WMRL_BF16, "observe_fwd_bf16: dims.precision must be WMRL_BF16");
   WMRL_REQUIRE(packed, "observe_fwd_bf16: needs the packed weight image (wmrl_pack_observe_weights)");
   WMRL_REQUIRE(tcl_observe_supported(dd), "observe_fwd_bf16: shape not supported by the tcgen05 path");
   WMRL_REQUIRE(pri_deter && pri_stoch && pri_dist_a && post_deter && post_stoch && post_dist_a, "observe_fwd_bf16: NULL output");
   WMRL_REQUIRE(dd.T == 1 || (obs_embeds && actions && noise_prior && noise_post), "observe_fwd_bf16: NULL input");
   WMRL_REQUIRE(dd.variant == WMRL_DISCRETE || (pri_dist_b && post_dist_b), "observe_fwd_bf16: continuous needs stds");
   WMRL_REQUIRE(ws && ws_bytes >= tcl_observe_workspace_bytes(dd), "observe_fwd_bf16: workspace too small");
+  const bool save = (d->flags & WMRL_FLAG_SAVE_FOR_BWD) != 0;
+  if (save) WMRL_REQUIRE(saved && saved_bytes >= tcl_observe_saved_bytes(dd), "observe_fwd_bf16: saved buffer too small");
   WMRL_REQUIRE(wmrl_device_supports_bf16(), "observe_fwd_bf16: needs an sm_100 device");
   if (int r = require_device()) return r;
   return tcl_observe_fwd(dd, packed, obs_embeds, actions, noise_prior, noise_post, pri_deter, pri_stoch, pri_dist_a,
-                         pri_dist_b, post_deter, post_stoch, post_dist_a, post_dist_b, ws, (cudaStream_t)stream);
+                         pri_dist_b, post_deter, post_stoch, post_dist_a, post_dist_b, save ? saved : nullptr, ws,
+                         (cudaStream_t)stream);
+}
+
+int wmrl_observe_bwd_bf16(const wmrl_dims* d, const void* packed, const float* noise_prior, const float* noise_post,
+                          const float* pri_deter, const float* pri_dist_a, const float* pri_dist_b, const float* post_dist_a,
+                          const float* post_dist_b, const void* saved, const float* g_deter, const float* g_pri_stoch,
+                          const float* g_pri_dist_a, const float* g_pri_dist_b, const float* g_post_stoch,
+                          const float* g_post_dist_a, const float* g_post_dist_b, const wmrl_rssm_grads* gw,
+                          float* g_obs_embeds, float* g_actions, void* ws, size_t ws_bytes, void* stream) {
+  if (int r = check_dims(d, 1)) return r;
+  Dims dd(*d);
+  if (dd.B == 0 || dd.T <= 1) return 0;
+  WMRL_REQUIRE(d->precision == WMRL_BF16 && (d->flags & WMRL_FLAG_BACKWARD), "observe_bwd_bf16: dims need WMRL_BF16 and WMRL_FLAG_BACKWARD");
+  WMRL_REQUIRE(packed && saved && gw, "observe_bwd_bf16: NULL packed / saved / grads");
+  WMRL_REQUIRE(tcl_observe_supported(dd), "observe_bwd_bf16: shape not supported by the tcgen05 path");
+  WMRL_REQUIRE(noise_prior && noise_post && pri_deter && pri_dist_a && post_dist_a, "observe_bwd_bf16: NULL tensor");
+  WMRL_REQUIRE(dd.variant == WMRL_DISCRETE || (pri_dist_b && post_dist_b), "observe_bwd_bf16: continuous needs stds");
+  WMRL_REQUIRE(ws && ws_bytes >= tcl_observe_workspace_bytes(dd), "observe_bwd_bf16: workspace too small");
+  WMRL_REQUIRE(wmrl_device_supports_bf16(), "observe_bwd_bf16: needs an sm_100 device");
+  if (int r = require_device()) return r;
+  return tcl_observe_bwd(dd, packed, noise_prior, noise_post, pri_deter, pri_dist_a, pri_dist_b, post_dist_a, post_dist_b,
+                         saved, g_deter, g_pri_stoch, g_pri_dist_a, g_pri_dist_b, g_post_stoch, g_post_dist_a, g_post_dist_b,
+                         gw, g_obs_embeds, g_actions, ws, (cudaStream_t)stream);
 }
 
 size_t wmrl_packed_bytes(const wmrl_dims* d) {

@@ -115,7 +115,14 @@ size_t tcl_observe_workspace_bytes(const Dims& d);
 int tcl_pack_observe_weights(const Dims& d, const wmrl_rssm_params* w, void* packed, cudaStream_t st);
 int tcl_observe_fwd(const Dims& d, const void* packed, const float* obs, const float* act, const float* noise_pri,
                     const float* noise_post, float* pri_deter, float* pri_stoch, float* pri_da, float* pri_db,
-                    float* post_deter, float* post_stoch, float* post_da, float* post_db, void* ws, cudaStream_t st);
+                    float* post_deter, float* post_stoch, float* post_da, float* post_db, void* saved, void* ws,
+                    cudaStream_t st);
+size_t tcl_observe_saved_bytes(const Dims& d);
+int tcl_observe_bwd(const Dims& d, const void* packed, const float* noise_pri, const float* noise_post, const float* pri_deter,
+                    const float* pri_da, const float* pri_db, const float* post_da, const float* post_db, const void* saved,
+                    const float* g_deter, const float* g_pri_stoch, const float* g_pri_da, const float* g_pri_db,
+                    const float* g_post_stoch, const float* g_post_da, const float* g_post_db, const wmrl_rssm_grads* gw,
+                    float* g_obs, float* g_act, void* ws, cudaStream_t st);
 // which bf16 forward serves this shape: 1 persistent folded-pair / single-CTA kernel, 2 layer-wise chain, 0 none
 int bf16_path(const Dims& d);
 

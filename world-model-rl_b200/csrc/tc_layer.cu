@@ -49,7 +49,7 @@ constexpr int kGruTile = 64;                // state columns per GRU work item (
 static_assert((kLSlots & (kLSlots - 1)) == 0, "kLSlots must be a power of two");
 
 enum : int { LE_LN_ELU = 1, LE_BIAS_ELU, LE_MU, LE_GRU, LE_SAMPLE_DISC, LE_SAMPLE_CONT,
-              LB_ELU, LB_GRU, LB_CARRY, LB_EMB, LB_LN };   // LB_*: BPTT epilogues
+              LB_ELU, LB_GRU, LB_CARRY, LB_EMB, LB_LN, LB_POST };   // LB_*: backward epilogues
 
 struct LSeg {
   const uint8_t* a;        // activation panel, tile 0
@@ -76,12 +76,13 @@ struct LayerArgs {
   int n;                   // accumulator columns of one column tile seen by the epilogue
   int NT, MT;              // column tiles, row tiles
   int B, H, t;
-  int D, S, C, A, Sp, Dp, Sip;
+  int D, S, C, A, Sp, Dp, Sip, E;
   float inv_action_scale;
   int save;                // forward: record what the BPTT needs (LayerNorm x-hat + rstd, GRU r / z / n / h_n)
   uint8_t* aux[5];         // extra panels (tile 0) an epilogue reads or writes: recorded activations, g_u
   uint32_t aux_tile_bytes;
-  float *f0, *f1, *f2;     // extra fp32 tensors (rstd, carry rows, upstream / start-state gradients; see the epilogues)
+  float *f0, *f1, *f2, *f3; // extra fp32 tensors (rstd, carry panels, upstream / start-state / input gradients; see the epilogues)
+  int mode, nt_split;      // epilogue variants (LB_EMB: 1 = raw action gradients out; LB_POST: first column tile of the obs part)
   uint8_t* out;            // destination panel (tile 0)
   uint32_t out_tile_bytes;
   int out_cols;            // padded width of the destination panel: chunks beyond it are not stored
@@ -616,7 +617,7 @@ __device__ __forceinline__ void lepib_carry(const LCtx& c) {
         if (col + 4 * k < p.Dp && blk * 32 + 4 * k < p.n)
           *reinterpret_cast<float4*>(fpanel(p.f0, c.mt, p.Dp, col + 4 * k, c.row)) =
               make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
-    } else if (c.valid) {
+    } else if (c.valid && p.f2) {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (col + i < p.D && blk * 32 + i < p.n) p.f2[c.b * p.D + col + i] = acc[i];
@@ -644,7 +645,7 @@ __device__ __forceinline__ void lepib_emb(const LCtx& c) {
           if (col + 4 * k < p.Sip && blk * 32 + 4 * k < p.n)
             *reinterpret_cast<float4*>(fpanel(p.f0, c.mt, p.Sip, col + 4 * k, c.row)) =
                 make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
-      } else if (c.valid) {
+      } else if (c.valid && p.f2) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (col + i < S_in && blk * 32 + i < p.n) {
@@ -654,6 +655,15 @@ __device__ __forceinline__ void lepib_emb(const LCtx& c) {
           }
       }
     }
+  } else if (c.q == 0 && p.mode == 1) {
+    // filtering: the actions are inputs - their gradient goes out as is (f3 = dL/d actions[B][T][A], index t)
+    float acc[16];
+    tmem_ld16(c.tmem_lane, acc);
+    tmem_ld_wait();
+    if (p.f3 && c.valid)
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < p.A) p.f3[(c.b * (p.H + 1) + p.t) * p.A + i] = acc[i];
   } else if (c.q == 0) {
     float acc[16], gm[16];
     tmem_ld16(c.tmem_lane, acc);
@@ -670,6 +680,76 @@ __device__ __forceinline__ void lepib_emb(const LCtx& c) {
     }
     st_chunk_g(c.out_row, gm);
     st_chunk_g(c.out_row + kLTileChunk, gm + 8);
+  }
+}
+
+// the inverse of load_rows32: every thread hands over its row's 32 values, the warp stores them coalesced
+__device__ __forceinline__ void store_rows32(const LCtx& c, float* row0, long long ld, int nrows_valid, int ncols_valid,
+                                             const float (&v)[32]) {
+  const int sub = c.lane >> 3, chunk = c.lane & 7;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    if ((c.lane >> 4) == half) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_addr(c.stage, c.lane & 15, k)), "f"(v[4 * k]),
+                     "f"(v[4 * k + 1]), "f"(v[4 * k + 2]), "f"(v[4 * k + 3]) : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r16 = i * 4 + sub, r = half * 16 + r16;
+      const float4 t = lds4(stage_addr(c.stage, r16, chunk));
+      if (r < nrows_valid && chunk * 4 < ncols_valid) {
+        float* dst = row0 + (long long)r * ld + chunk * 4;
+        if (chunk * 4 + 4 <= ncols_valid && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) *reinterpret_cast<float4*>(dst) = t;
+        else {
+          dst[0] = t.x;
+          if (chunk * 4 + 1 < ncols_valid) dst[1] = t.y;
+          if (chunk * 4 + 2 < ncols_valid) dst[2] = t.z;
+          if (chunk * 4 + 3 < ncols_valid) dst[3] = t.w;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// posterior hidden layer dgrad (rssm.py:80): [dL/dh' | dL/de_{t+1}] = g_hidq W_post0.  Column tiles below nt_split
+// cover h' and ADD into the fp32 carry panel f0 (the prior path and the carried gradient are already there); the
+// tiles from nt_split on cover the observation embedding and go to f3 = dL/d obs_embeds[:, t+1] (row-major fp32).
+__device__ __forceinline__ void lepib_post(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  const long long b0 = c.b - c.lane;
+  const int E = p.E;
+  for (int blk = c.q; blk * 32 < p.n; blk += 4) {
+    float acc[32];
+    if (c.nt < p.nt_split) {
+      const int col = c.nt * p.n + blk * 32;
+      if (col >= p.Dp) break;
+      tmem_ld32(c.tmem_lane + blk * 32, acc);
+      float4 cr[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        cr[k] = (col + 4 * k < p.Dp && blk * 32 + 4 * k < p.n) ? *reinterpret_cast<const float4*>(fpanel(p.f0, c.mt, p.Dp, col + 4 * k, c.row))
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (col + 4 * k < p.Dp && blk * 32 + 4 * k < p.n)
+          *reinterpret_cast<float4*>(fpanel(p.f0, c.mt, p.Dp, col + 4 * k, c.row)) =
+              c.valid ? make_float4(cr[k].x + acc[4 * k], cr[k].y + acc[4 * k + 1], cr[k].z + acc[4 * k + 2], cr[k].w + acc[4 * k + 3])
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const int col = (c.nt - p.nt_split) * p.n + blk * 32;
+      if (col >= E) break;
+      tmem_ld32(c.tmem_lane + blk * 32, acc);
+      tmem_ld_wait();
+      if (p.f3) {
+        const int nr = (int)max(0LL, min(32LL, (long long)p.B - b0));
+        store_rows32(c, p.f3 + (b0 * (p.H + 1) + p.t + 1) * E + col, (long long)(p.H + 1) * E, nr, min(min(32, E - col), p.n - blk * 32), acc);
+      }
+    }
   }
 }
 
@@ -995,6 +1075,7 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
       else if (kType == LB_CARRY) lepib_carry(c);
       else if (kType == LB_EMB) lepib_emb(c);
       else if (kType == LB_LN) lepib_ln(c);
+      else if (kType == LB_POST) lepib_post(c);
       else lepi_sample_disc<(kS > 0 ? kS : 4)>(c);
       tc_fence_before();
       __syncwarp();
@@ -1023,6 +1104,7 @@ static LayerKernel layer_kernel_for(int type, int S) {
     case LB_CARRY: return tc_layer_kernel<LB_CARRY, 0>;
     case LB_EMB: return tc_layer_kernel<LB_EMB, 0>;
     case LB_LN: return tc_layer_kernel<LB_LN, 0>;
+    case LB_POST: return tc_layer_kernel<LB_POST, 0>;
     default: break;
   }
   return S == 32 ? tc_layer_kernel<LE_SAMPLE_DISC, 32> : S == 16 ? tc_layer_kernel<LE_SAMPLE_DISC, 16>
@@ -1316,7 +1398,7 @@ enum {
   F_H = 0, F_HN, F_S, F_SN, F_A, F_X, F_HID, F_GR, F_GZ, F_GN, F_GHN,
   F_OBS, F_ACT, F_HIDQ, F_SPRI,   // posterior filtering: observation-embedding / action panels per step, posterior hidden, prior-sample sink
   F_Y0, F_XH0 = F_Y0 + WMRL_MAX_ACTOR_LAYERS, F_RSTD0 = F_XH0 + WMRL_MAX_ACTOR_LAYERS,
-  G_GO = F_RSTD0 + WMRL_MAX_ACTOR_LAYERS, G_GHID, G_GATES_I, G_GATES_H, G_GX, G_GMU,
+  G_GO = F_RSTD0 + WMRL_MAX_ACTOR_LAYERS, G_GHID, G_GATES_I, G_GATES_H, G_GX, G_GMU, G_OQ, G_HIDQ,
   G_GP0, G_GU0 = G_GP0 + WMRL_MAX_ACTOR_LAYERS, BUF_COUNT = G_GU0 + WMRL_MAX_ACTOR_LAYERS
 };
 
@@ -1376,9 +1458,9 @@ static int buf_width(const LPlan& lp, int buf) {
   if (buf == F_H || buf == F_HN || buf == F_X || buf == F_GR || buf == F_GZ || buf == F_GN || buf == F_GHN || buf == G_GX) return lp.Dp;
   if (buf == F_S || buf == F_SN || buf == F_SPRI) return lp.Sip;
   if (buf == F_A || buf == G_GMU || buf == F_ACT) return 16;
-  if (buf == F_HID || buf == G_GHID || buf == F_HIDQ) return lp.Hdp;
+  if (buf == F_HID || buf == G_GHID || buf == F_HIDQ || buf == G_HIDQ) return lp.Hdp;
   if (buf == F_OBS) return lp.Ep;
-  if (buf == G_GO) return lp.Pp;
+  if (buf == G_GO || buf == G_OQ) return lp.Pp;
   if (buf == G_GATES_I || buf == G_GATES_H) return 4 * lp.Dp;
   return lp.Ha;   // F_Y, F_XH, G_GP, G_GU
 }
@@ -1752,7 +1834,7 @@ static int tcl_device_setup(int& nsm) {
   WMRL_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
   std::lock_guard<std::mutex> lk(mu);
   if (!attr_set[dev]) {
-    for (int ty = LE_LN_ELU; ty <= LB_LN; ++ty)
+    for (int ty = LE_LN_ELU; ty <= LB_POST; ++ty)
       for (int S : {4, 8, 16, 32}) {
         if (ty != LE_SAMPLE_DISC && S != 4) continue;
         WMRL_CUDA_OK(cudaFuncSetAttribute(layer_kernel_for(ty, S), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1793,7 +1875,7 @@ static int tcl_launch(const LCall& c, const LLayerH& L, LayerArgs& a, const int*
   a.w = c.data + L.w_off; a.w_tile_bytes = L.w_tile_bytes;
   a.ep = c.ep + L.ep_off; a.ep_floats = L.ep_floats;
   a.kc = L.kc; a.dbuf = L.dbuf; a.type = L.type; a.n = L.n; a.NT = L.NT; a.MT = c.MT;
-  a.B = d.B; a.H = d.T; a.D = d.D; a.S = d.S; a.C = d.C; a.A = d.A; a.Sp = lp.Sp; a.Dp = lp.Dp; a.Sip = lp.Sip;
+  a.B = d.B; a.H = d.T; a.D = d.D; a.S = d.S; a.C = d.C; a.A = d.A; a.Sp = lp.Sp; a.Dp = lp.Dp; a.Sip = lp.Sip; a.E = d.E;
   a.inv_action_scale = 1.f / d.action_scale;
   a.out = c.at(L.out, out_step); a.out_tile_bytes = c.m->r[L.out].tile_bytes; a.out_cols = buf_width(lp, L.out);
   const int items = c.MT * L.NT;
@@ -2119,11 +2201,110 @@ static LPlan tcl_make_observe_plan(const Dims& d, const wmrl_rssm_params* w) {
   }
   // execution order of a step: embed, GRU, prior hidden, prior head, posterior hidden, posterior head
   std::swap(lp.layers[3], lp.layers[4]);
-  for (const LLayerH& L : lp.layers) {
-    if (L.ep_floats * 4 > kLParamBytes || (L.ep_floats & 3)) return lp;
-    for (int s = 0; s < L.nseg; ++s)
-      if ((uint32_t)L.kc * (4096u + (uint32_t)L.seg[s].n * 32u) > kLSlotBytes) return lp;
+  // ====================================================================== backward chain (full backward of filtering:
+  // dgrad through both heads, the GRU and the embed; weight gradients after the scan, world_model.py:120-163)
+  {
+    const int Pp = lp.Pp;
+    const uint32_t zero16 = add_vec(pk, nul, nul, 0, 0, 16);
+    auto head_dgrad = [&](int in_buf, const float* W2, int out_buf, int stash) {   // g_hid = g_out W2 (x ELU'(hid))
+      LLayerH L;
+      L.type = LB_ELU; L.dbuf = 1; L.out = out_buf; L.nseg = 1; L.layer = stash;
+      tiles(Hdp, 256, 16, L.NT, L.n);
+      L.kc = kc_for(L.n);
+      L.w_off = pk.data_bytes;
+      for (int j = 0; j < L.NT; ++j) {
+        const size_t t0 = pk.data_bytes;
+        L.seg[0] = {in_buf, Pp / 16, L.n, 0, 0, 1, 0u};
+        RowSpec rs(j * L.n, d.Hd - j * L.n, L.n);
+        if (disc) l_add_pack_t(lp, rs, W2, d.Hd, {{0, d.P, Pp}});
+        else l_add_pack_t(lp, rs, W2, d.Hd, {{0, d.S, Sp}, {d.S, d.S, Sp}});
+        L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+      }
+      L.ep_off = zero16; L.ep_floats = 0;
+      lp.blayers.push_back(L);
+    };
+    // ---- posterior head, then the posterior hidden layer: [dL/dh' += | dL/de =] g_hidq W_post0
+    head_dgrad(G_OQ, w ? w->post2_w : nul, G_HIDQ, F_HIDQ);
+    {
+      LLayerH L;
+      L.type = LB_POST; L.dbuf = 1; L.out = G_GX; L.nseg = 1;
+      int nth;
+      tiles(Dp, 256, 16, nth, L.n);
+      const int nte = (Ep + L.n - 1) / L.n;
+      L.NT = nth + nte; L.layer = nth;
+      L.kc = kc_for(L.n);
+      L.w_off = pk.data_bytes;
+      for (int j = 0; j < L.NT; ++j) {
+        const size_t t0 = pk.data_bytes;
+        L.seg[0] = {G_HIDQ, Hdp / 16, L.n, 0, 0, 1, 0u};
+        RowSpec rs = (j < nth) ? RowSpec(j * L.n, d.D - j * L.n, L.n) : RowSpec(d.D + (j - nth) * L.n, d.E - (j - nth) * L.n, L.n);
+        l_add_pack_t(lp, rs, w ? w->post0_w : nul, d.D + d.E, {{0, d.Hd, Hdp}});
+        L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+      }
+      L.ep_off = zero16; L.ep_floats = 0;
+      lp.blayers.push_back(L);
+    }
+    // ---- prior head, prior hidden + GRU gate backward
+    head_dgrad(G_GO, w ? w->prior2_w : nul, G_GHID, F_HID);
+    {
+      LLayerH L;
+      L.type = LB_GRU; L.dbuf = 1; L.out = G_GATES_I; L.nseg = 1;
+      tiles(Dp, 128, 16, L.NT, L.n);
+      L.kc = kc_for(L.n);
+      L.w_off = pk.data_bytes;
+      for (int j = 0; j < L.NT; ++j) {
+        const size_t t0 = pk.data_bytes;
+        L.seg[0] = {G_GHID, Hdp / 16, L.n, 0, 0, 1, 0u};
+        l_add_pack_t(lp, RowSpec(j * L.n, d.D - j * L.n, L.n), w ? w->prior0_w : nul, d.D, {{0, d.Hd, Hdp}});
+        L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+      }
+      L.ep_off = zero16; L.ep_floats = 0;
+      lp.blayers.push_back(L);
+    }
+    // ---- dL/dx = [g_n | g_r | g_z] W_ih (x ELU'(x));  dL/dh_t = [g_r | g_z | g_n r] W_hh + dL/dh' z
+    for (int hh = 0; hh < 2; ++hh) {
+      LLayerH L;
+      L.type = hh ? LB_CARRY : LB_ELU; L.dbuf = 1; L.out = G_GX; L.nseg = 1; L.layer = F_X;
+      tiles(Dp, 256, 16, L.NT, L.n);
+      L.kc = kc_for(L.n);
+      L.w_off = pk.data_bytes;
+      for (int j = 0; j < L.NT; ++j) {
+        const size_t t0 = pk.data_bytes;
+        L.seg[0] = {hh ? G_GATES_H : G_GATES_I, 3 * Dp / 16, L.n, 0, 0, 1, 0u};
+        if (hh) l_add_pack_t(lp, RowSpec(j * L.n, d.D - j * L.n, L.n), w ? w->w_hh : nul, d.D, {{0, d.D, Dp}, {d.D, d.D, Dp}, {2 * d.D, d.D, Dp}});
+        else l_add_pack_t(lp, RowSpec(j * L.n, d.D - j * L.n, L.n), w ? w->w_ih : nul, d.D, {{2 * d.D, d.D, Dp}, {0, d.D, Dp}, {d.D, d.D, Dp}});
+        L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+      }
+      L.ep_off = zero16; L.ep_floats = 0;
+      lp.blayers.push_back(L);
+    }
+    // ---- [dL/d post_s_t | dL/da_t] = g_x W_e
+    {
+      LLayerH L;
+      L.type = LB_EMB; L.dbuf = 1; L.out = G_GMU; L.nseg = 1;
+      int nts;
+      tiles(Sip, 256, 16, nts, L.n);
+      L.NT = nts + 1;
+      L.kc = kc_for(L.n);
+      L.w_off = pk.data_bytes;
+      const int Ke = d.S_in + d.A;
+      for (int j = 0; j < L.NT; ++j) {
+        const size_t t0 = pk.data_bytes;
+        L.seg[0] = {G_GX, Dp / 16, L.n, 0, 0, 1, 0u};
+        RowSpec rs = (j < nts) ? RowSpec(j * L.n, d.S_in - j * L.n, L.n) : RowSpec(d.S_in, d.A, L.n);
+        l_add_pack_t(lp, rs, w ? w->embed_w : nul, Ke, {{0, d.D, Dp}});
+        L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+      }
+      L.ep_off = zero16; L.ep_floats = 0;
+      lp.blayers.push_back(L);
+    }
   }
+  for (const std::vector<LLayerH>* v : {&lp.layers, &lp.blayers})
+    for (const LLayerH& L : *v) {
+      if (L.ep_floats * 4 > kLParamBytes || (L.ep_floats & 3)) return lp;
+      for (int s = 0; s < L.nseg; ++s)
+        if ((uint32_t)L.kc * (4096u + (uint32_t)L.seg[s].n * 32u) > kLSlotBytes) return lp;
+    }
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   pk.off_stage_tab = 256;
   pk.off_job_tab = 512;
@@ -2136,24 +2317,41 @@ static LPlan tcl_make_observe_plan(const Dims& d, const wmrl_rssm_params* w) {
   return lp;
 }
 
-static LMem tcl_observe_layout(const LPlan& lp, const Dims& d) {
+// mode 0: forward, nothing recorded; 1: forward, recording (world-model training); 2: backward
+static LMem tcl_observe_layout(const LPlan& lp, const Dims& d, int mode) {
   LMem m;
-  const int MT = (d.B + 127) / 128;
-  size_t off = kLTraceBytes;
-  auto place = [&](int buf, int steps) {
+  const int MT = (d.B + 127) / 128, T = std::max(1, d.T), H = std::max(1, d.T - 1);
+  size_t off[2] = {kLTraceBytes, 0};
+  auto place = [&](int buf, int steps, int where) {
     Region& r = m.r[buf];
     r.tile_bytes = (uint32_t)(buf_width(lp, buf) / 8) * kLTileChunk;
     r.step_bytes = (size_t)MT * r.tile_bytes;
-    r.steps = steps; r.where = 0; r.off = off;
-    off += ((size_t)steps * r.step_bytes + 1023) / 1024 * 1024;
+    r.steps = steps; r.where = where; r.off = off[where];
+    off[where] += ((size_t)steps * r.step_bytes + 1023) / 1024 * 1024;
   };
-  place(F_H, 2); place(F_S, 1); place(F_SPRI, 1); place(F_X, 1); place(F_HID, 1); place(F_HIDQ, 1);
-  place(F_OBS, std::max(1, d.T)); place(F_ACT, std::max(1, d.T));
+  const bool rec = mode != 0;
+  const int sv = rec ? 1 : 0;
+  place(F_H, rec ? T : 2, sv); place(F_S, rec ? T : 1, sv);
+  place(F_X, rec ? H : 1, sv); place(F_HID, rec ? H : 1, sv); place(F_HIDQ, rec ? H : 1, sv);
+  place(F_OBS, T, sv); place(F_ACT, T, sv);
+  if (rec) for (int f : {F_GR, F_GZ, F_GN, F_GHN}) place(f, H, 1);
+  if (mode != 2) place(F_SPRI, 1, 0);
+  if (mode == 2) {
+    place(G_OQ, H, 0); place(G_HIDQ, H, 0); place(G_GO, H, 0); place(G_GHID, H, 0); place(G_GATES_I, H, 0); place(G_GX, H, 0);
+    m.r[G_GATES_H] = m.r[G_GATES_I];
+    m.r[G_GATES_H].off += (size_t)(lp.Dp / 8) * kLTileChunk;
+    place(G_GMU, 1, 0);
+    m.carry_h = off[0]; off[0] += ((size_t)MT * 128 * lp.Dp * 4 + 1023) / 1024 * 1024;
+    m.carry_s = off[0]; off[0] += ((size_t)MT * 128 * lp.Sip * 4 + 1023) / 1024 * 1024;
+  }
   m.r[F_HN] = m.r[F_H]; m.r[F_SN] = m.r[F_S];
-  const size_t ib = ((size_t)d.B * std::max(1, d.T) * d.C * sizeof(int32_t) + 1023) / 1024 * 1024;
-  m.idx_pri = off; off += ib;
-  m.idx_post = off; off += ib;
-  m.ws_bytes = off + 1024;
+  if (mode != 2) {
+    const size_t ib = ((size_t)d.B * T * d.C * sizeof(int32_t) + 1023) / 1024 * 1024;
+    m.idx_pri = off[0]; off[0] += ib;
+    m.idx_post = off[0]; off[0] += ib;
+  }
+  m.ws_bytes = off[0] + 1024;
+  m.saved_bytes = off[1] + 1024;
   return m;
 }
 
@@ -2181,7 +2379,13 @@ size_t tcl_observe_packed_bytes(const Dims& d) {
 }
 size_t tcl_observe_workspace_bytes(const Dims& d) {
   LPlan lp = tcl_make_observe_plan(d, nullptr);
-  return lp.ok ? tcl_observe_layout(lp, d).ws_bytes : 0;
+  if (!lp.ok) return 0;
+  const int mode = (d.flags & WMRL_FLAG_BACKWARD) ? 2 : ((d.flags & WMRL_FLAG_SAVE_FOR_BWD) ? 1 : 0);
+  return tcl_observe_layout(lp, d, mode).ws_bytes;
+}
+size_t tcl_observe_saved_bytes(const Dims& d) {
+  LPlan lp = tcl_make_observe_plan(d, nullptr);
+  return lp.ok ? tcl_observe_layout(lp, d, 1).saved_bytes : 0;
 }
 int tcl_pack_observe_weights(const Dims& d, const wmrl_rssm_params* w, void* packed, cudaStream_t st) {
   LPlan lp = tcl_make_observe_plan(d, w);
@@ -2191,11 +2395,13 @@ int tcl_pack_observe_weights(const Dims& d, const wmrl_rssm_params* w, void* pac
 
 int tcl_observe_fwd(const Dims& d, const void* packed, const float* obs, const float* act, const float* noise_pri,
                     const float* noise_post, float* pri_deter, float* pri_stoch, float* pri_da, float* pri_db,
-                    float* post_deter, float* post_stoch, float* post_da, float* post_db, void* ws, cudaStream_t st) {
+                    float* post_deter, float* post_stoch, float* post_da, float* post_db, void* saved, void* ws,
+                    cudaStream_t st) {
   LPlan lp = tcl_make_observe_plan(d, nullptr);
   WMRL_REQUIRE(lp.ok, "observe_fwd: shape not supported by the layer-wise tcgen05 path");
-  const LMem m = tcl_observe_layout(lp, d);
-  LCall c{&lp, &m, &d, (uint8_t*)ws, nullptr, nullptr, nullptr, (d.B + 127) / 128, 148, st};
+  const bool rec = saved != nullptr;
+  const LMem m = tcl_observe_layout(lp, d, rec ? 1 : 0);
+  LCall c{&lp, &m, &d, (uint8_t*)ws, (uint8_t*)saved, nullptr, nullptr, (d.B + 127) / 128, 148, st};
   if (int r = tcl_device_setup(c.nsm)) return r;
   const uint8_t* img = (const uint8_t*)packed;
   c.data = img + lp.pk.off_data;
@@ -2217,15 +2423,23 @@ int tcl_observe_fwd(const Dims& d, const void* packed, const float* obs, const f
   cs.d = &dstep;
   for (int t = 0; t < H; ++t) {
     auto step_of = [&](int buf) {
-      if (buf == F_H) return t & 1;
-      if (buf == F_HN) return (t + 1) & 1;
+      if (buf == F_H) return rec ? t : (t & 1);
+      if (buf == F_HN) return rec ? t + 1 : ((t + 1) & 1);
+      if (buf == F_S) return rec ? t : 0;
+      if (buf == F_SN) return rec ? t + 1 : 0;
       if (buf == F_OBS) return t + 1;
       if (buf == F_ACT) return t;
-      return 0;
+      if (buf == F_SPRI) return 0;
+      return rec ? t : 0;
     };
     for (const LLayerH& L : lp.layers) {
       LayerArgs a{};
       a.t = t;
+      a.save = rec ? 1 : 0;
+      if (rec && L.type == LE_GRU) {
+        a.aux[0] = c.at(F_GR, t); a.aux[1] = c.at(F_GZ, t); a.aux[2] = c.at(F_GN, t); a.aux[3] = c.at(F_GHN, t);
+        a.aux_tile_bytes = m.r[F_GR].tile_bytes;
+      }
       const bool post = L.layer == 1 && (L.type == LE_SAMPLE_DISC || L.type == LE_SAMPLE_CONT);
       a.deter_seq = pri_deter;
       a.stoch_seq = post ? post_stoch : pri_stoch; a.dist_a = post ? post_da : pri_da; a.dist_b = post ? post_db : pri_db;
@@ -2244,6 +2458,155 @@ int tcl_observe_fwd(const Dims& d, const void* packed, const float* obs, const f
   }
   // both sequences carry the same deterministic states (rssm.py:84-91)
   WMRL_CUDA_OK(cudaMemcpyAsync(post_deter, pri_deter, (size_t)d.B * T * d.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// Full backward of filtering on the chain (world-model training, world_model.py:120-163): per step, backwards in
+// time, the two sample backwards (SIMT) and 7 dgrad GEMMs with fused epilogues; every gradient panel is kept per step
+// and the RSSM weight gradients are MN-major big-K tcgen05 GEMMs over (recorded activation, gradient) panel pairs after
+// the scan, the bias gradients column sums.  g_deter = dL/d pri_deter + dL/d post_deter (both sequences hold the same h).
+int tcl_observe_bwd(const Dims& d, const void* packed, const float* noise_pri, const float* noise_post, const float* pri_deter,
+                    const float* pri_da, const float* pri_db, const float* post_da, const float* post_db, const void* saved,
+                    const float* g_deter, const float* g_pri_stoch, const float* g_pri_da, const float* g_pri_db,
+                    const float* g_post_stoch, const float* g_post_da, const float* g_post_db, const wmrl_rssm_grads* gw,
+                    float* g_obs, float* g_act, void* ws, cudaStream_t st) {
+  LPlan lp = tcl_make_observe_plan(d, nullptr);
+  WMRL_REQUIRE(lp.ok, "observe_bwd: shape not supported by the layer-wise tcgen05 path");
+  const LMem m = tcl_observe_layout(lp, d, 2);
+  LCall c{&lp, &m, &d, (uint8_t*)ws, (uint8_t*)const_cast<void*>(saved), nullptr, nullptr, (d.B + 127) / 128, 148, st};
+  if (int r = tcl_device_setup(c.nsm)) return r;
+  const uint8_t* img = (const uint8_t*)packed;
+  c.data = img + lp.pk.off_data;
+  c.ep = (const float*)(img + lp.pk.off_eparams);
+  const int T = d.T, MT = c.MT, H = T - 1;
+  if (H < 1) return 0;
+  const bool disc = d.variant == WMRL_DISCRETE;
+  Dims dstep = d;
+  dstep.T = H;
+  LCall cs = c;
+  cs.d = &dstep;
+  float* carry_h = (float*)((uint8_t*)ws + m.carry_h);
+  float* carry_s = (float*)((uint8_t*)ws + m.carry_s);
+  {
+    const long long n = (long long)MT * 128 * lp.Dp;
+    tcl_carry_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(carry_h, g_deter, d.B, H, d.D, lp.Dp, n);
+    WMRL_CUDA_OK(cudaGetLastError());
+  }
+  for (int t = H - 1; t >= 0; --t) {
+    for (int post = 1; post >= 0; --post) {   // dL/d(head outputs) of the state produced by step t
+      SbArgs s{};
+      s.carry_s = (post && t < H - 1) ? carry_s : nullptr;
+      s.g_stoch = post ? g_post_stoch : g_pri_stoch; s.g_da = post ? g_post_da : g_pri_da; s.g_db = post ? g_post_db : g_pri_db;
+      s.dist_a = post ? post_da : pri_da; s.dist_b = post ? post_db : pri_db; s.noise = post ? noise_post : noise_pri;
+      s.out = c.at(post ? G_OQ : G_GO, t);
+      s.B = d.B; s.H = H; s.t = t; s.S = d.S; s.C = d.C; s.Sp = lp.Sp; s.Sip = lp.Sip; s.Pp = lp.Pp; s.MT = MT;
+      if (disc) {
+        const long long nw = (long long)MT * 128 * d.C;
+        tcl_sample_bwd_disc_kernel<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, st>>>(s);
+      } else {
+        const long long n = (long long)MT * 128 * (lp.Sp / 8);
+        tcl_sample_bwd_cont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s);
+      }
+      WMRL_CUDA_OK(cudaGetLastError());
+    }
+    for (const LLayerH& L : lp.blayers) {
+      LayerArgs a{};
+      a.t = t;
+      a.deter_seq = const_cast<float*>(pri_deter);
+      switch (L.type) {
+        case LB_ELU:
+          a.aux[0] = c.at(L.layer, t); a.aux_tile_bytes = m.r[L.layer].tile_bytes;
+          break;
+        case LB_POST:
+          a.f0 = carry_h; a.f3 = g_obs; a.nt_split = L.layer;
+          break;
+        case LB_GRU:
+          a.aux[0] = c.at(F_GR, t); a.aux[1] = c.at(F_GZ, t); a.aux[2] = c.at(F_GN, t); a.aux[3] = c.at(F_GHN, t);
+          a.aux[4] = c.at(F_H, t);
+          a.aux_tile_bytes = m.r[F_GR].tile_bytes;
+          a.f0 = carry_h;
+          break;
+        case LB_CARRY:
+          a.f0 = carry_h; a.f1 = const_cast<float*>(g_deter); a.f2 = nullptr;
+          break;
+        case LB_EMB:
+          a.f0 = carry_s; a.f1 = nullptr; a.f2 = nullptr; a.f3 = g_act; a.mode = 1;
+          break;
+      }
+      int ss[3] = {t, t, t};
+      if (int r = tcl_launch(cs, L, a, ss, L.out == G_GMU ? 0 : t)) return r;
+    }
+  }
+  // ---- weight gradients over (recorded activation, gradient) panel pairs, blocks = (step, row tile)
+  const int nblk = H * MT;
+  auto wgrad = [&](uint8_t* a_base, size_t a_blk, int m_cols, int m_valid, uint8_t* b_base, size_t b_blk, int n_cols, int n_valid,
+                   float* dW, int ldw) -> int {
+    if (!dW) return 0;
+    Wg2Params q{};
+    q.a_base = a_base; q.a_blk = a_blk; q.b_base = b_base; q.b_blk = b_blk;
+    q.nblocks = nblk; q.m_cols = m_cols; q.m_valid = m_valid; q.n_cols = n_cols; q.n_valid = n_valid;
+    q.dW = dW; q.ldw = ldw;
+    q.mtiles = (m_cols + 127) / 128; q.ntiles = (n_cols + 255) / 256;
+    const int tl = q.mtiles * q.ntiles;
+    q.splits = std::max(1, std::min(nblk, c.nsm / tl));
+    tcl_wgrad_kernel<<<dim3(tl, q.splits), kWg2Threads, kWg2Smem, st>>>(q);
+    WMRL_CUDA_OK(cudaGetLastError());
+    return 0;
+  };
+  auto colsum = [&](uint8_t* x_base, size_t x_blk, int cols, int valid, float* out) -> int {
+    if (!out) return 0;
+    Cs2Params q{};
+    q.x_base = x_base; q.x_blk = x_blk; q.y_base = nullptr; q.y_blk = 0; q.nblocks = nblk; q.valid = valid; q.out = out;
+    const int chunks = cols / 8;
+    const int ysplit = std::max(1, std::min((nblk + kCs2Warps - 1) / kCs2Warps, (8 * c.nsm + chunks - 1) / chunks));
+    tcl_colsum_kernel<<<dim3(chunks, ysplit), kCs2Warps * 32, 0, st>>>(q);
+    WMRL_CUDA_OK(cudaGetLastError());
+    return 0;
+  };
+  auto tb = [&](int buf) { return (size_t)m.r[buf].tile_bytes; };
+  const int D = d.D, Dp = lp.Dp, Hdp = lp.Hdp, Sp = lp.Sp;
+  const size_t fchunk = (size_t)(Dp / 8) * kLTileChunk;   // one Dp-wide field of the gate panel
+  // heads: W2 [P, Hd] (continuous: rows [mean | raw] sit in two Sp-wide halves of the gradient panel), W0
+  for (int post = 0; post < 2; ++post) {
+    const int gout = post ? G_OQ : G_GO, ghid = post ? G_HIDQ : G_GHID, hid = post ? F_HIDQ : F_HID;
+    float* dW2 = post ? gw->post2_w : gw->prior2_w;
+    float* db2 = post ? gw->post2_b : gw->prior2_b;
+    if (disc) {
+      if (int r = wgrad(c.at(hid, 0), tb(hid), Hdp, d.Hd, c.at(gout, 0), tb(gout), lp.Pp, d.P, dW2, d.Hd)) return r;
+      if (int r = colsum(c.at(gout, 0), tb(gout), lp.Pp, d.P, db2)) return r;
+    } else {
+      for (int half = 0; half < 2; ++half) {
+        uint8_t* gb = c.at(gout, 0) + (size_t)half * (Sp / 8) * kLTileChunk;
+        if (int r = wgrad(c.at(hid, 0), tb(hid), Hdp, d.Hd, gb, tb(gout), Sp, d.S, dW2 ? dW2 + (size_t)half * d.S * d.Hd : nullptr, d.Hd)) return r;
+        if (int r = colsum(gb, tb(gout), Sp, d.S, db2 ? db2 + half * d.S : nullptr)) return r;
+      }
+    }
+    float* dW0 = post ? gw->post0_w : gw->prior0_w;
+    const int ld0 = post ? D + d.E : D;
+    if (int r = wgrad(c.at(F_H, 1), tb(F_H), Dp, D, c.at(ghid, 0), tb(ghid), Hdp, d.Hd, dW0, ld0)) return r;
+    if (post)
+      if (int r = wgrad(c.at(F_OBS, 1), tb(F_OBS), lp.Ep, d.E, c.at(ghid, 0), tb(ghid), Hdp, d.Hd, dW0 ? dW0 + D : nullptr, ld0)) return r;
+    if (int r = colsum(c.at(ghid, 0), tb(ghid), Hdp, d.Hd, post ? gw->post0_b : gw->prior0_b)) return r;
+  }
+  // GRU: gate panel fields [g_n | g_r | g_z | g_n r]; torch rows [r | z | n]
+  {
+    uint8_t* gates = c.at(G_GATES_I, 0);
+    const size_t gblk = tb(G_GATES_I);
+    const int f_ih[3] = {1, 2, 0}, f_hh[3] = {1, 2, 3};   // panel field of torch gate block r, z, n
+    for (int g = 0; g < 3; ++g) {
+      if (int r = wgrad(c.at(F_X, 0), tb(F_X), Dp, D, gates + f_ih[g] * fchunk, gblk, Dp, D, gw->w_ih ? gw->w_ih + (size_t)g * D * D : nullptr, D)) return r;
+      if (int r = wgrad(c.at(F_H, 0), tb(F_H), Dp, D, gates + f_hh[g] * fchunk, gblk, Dp, D, gw->w_hh ? gw->w_hh + (size_t)g * D * D : nullptr, D)) return r;
+      if (int r = colsum(gates + f_ih[g] * fchunk, gblk, Dp, D, gw->b_ih ? gw->b_ih + g * D : nullptr)) return r;
+      if (int r = colsum(gates + f_hh[g] * fchunk, gblk, Dp, D, gw->b_hh ? gw->b_hh + g * D : nullptr)) return r;
+    }
+  }
+  // embed: W_e [D, S_in + A] over [post s_t | a_t]
+  {
+    const int Ke = d.S_in + d.A;
+    if (int r = wgrad(c.at(F_S, 0), tb(F_S), lp.Sip, d.S_in, c.at(G_GX, 0), tb(G_GX), Dp, D, gw->embed_w, Ke)) return r;
+    if (int r = wgrad(c.at(F_ACT, 0), tb(F_ACT), 16, d.A, c.at(G_GX, 0), tb(G_GX), Dp, D, gw->embed_w ? gw->embed_w + d.S_in : nullptr, Ke)) return r;
+    if (int r = colsum(c.at(G_GX, 0), tb(G_GX), Dp, D, gw->embed_b)) return r;
+  }
   return 0;
 }
 

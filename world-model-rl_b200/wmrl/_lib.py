@@ -77,7 +77,8 @@ _SIGNATURES = {
                          [C.c_size_t, _P, C.c_size_t, _P]),
     "wmrl_observe_packed_bytes": (C.c_size_t, [C.POINTER(Dims)]),
     "wmrl_pack_observe_weights": (C.c_int, [C.POINTER(Dims), C.POINTER(RssmPtrs), _P, _P]),
-    "wmrl_observe_fwd_bf16": (C.c_int, [C.POINTER(Dims)] + [_P] * 14 + [C.c_size_t, _P]),
+    "wmrl_observe_fwd_bf16": (C.c_int, [C.POINTER(Dims)] + [_P] * 14 + [C.c_size_t, _P, C.c_size_t, _P]),
+    "wmrl_observe_bwd_bf16": (C.c_int, [C.POINTER(Dims)] + [_P] * 16 + [C.POINTER(RssmPtrs), _P, _P, _P, C.c_size_t, _P]),
     "wmrl_observe_bwd": (C.c_int, [C.POINTER(Dims), C.POINTER(RssmPtrs)] + [_P] * 21 +
                          [C.POINTER(RssmPtrs), _P, _P, _P, C.c_size_t, _P]),
     "wmrl_kl_loss_fwd": (C.c_int, [C.POINTER(Dims), _P, _P, _P, _P, C.c_float, _P, _P, _P]),

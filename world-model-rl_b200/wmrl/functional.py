@@ -194,39 +194,98 @@ class PackedObserveWeights:
         return buf
 
 
-def observe_rollout_bf16(cfg: PathConfig, packed: torch.Tensor, obs, act, noise_pri, noise_post, inits):
-    """no-grad posterior filtering on the bf16 layer-wise tcgen05 chain (wmrl_observe_fwd_bf16); same outputs as
-    ``ObserveRollout`` without a gradient record."""
-    lib = _lib.load()
-    dev = _require_cuda(obs, act, noise_pri, noise_post)
-    B, T = obs.shape[0], obs.shape[1]
-    disc = cfg.variant == _lib.DISCRETE
-    ob, ac, n1, n2 = _f32c(obs), _f32c(act), _f32c(noise_pri), _f32c(noise_post)
+class ObserveRolloutBF16(torch.autograd.Function):
+    """RSSMBase.observe_rollout on the bf16 layer-wise tcgen05 chain, forward (wmrl_observe_fwd_bf16) and full backward
+    (wmrl_observe_bwd_bf16: RSSM weight gradients, d obs_embeds, d actions).  Same inputs / outputs as
+    ``ObserveRollout`` plus the packed weight image."""
 
-    def seq_bufs():
-        de = torch.empty(B, T, cfg.D, device=dev)
-        st = torch.empty(B, T, cfg.S_in, device=dev)
+    @staticmethod
+    def forward(ctx, cfg: PathConfig, packed, obs, act, noise_pri, noise_post, init_pri_da, init_pri_db, init_post_da,
+                init_post_db, *rssm_p):
+        lib = _lib.load()
+        dev = _require_cuda(obs, act, noise_pri, noise_post, *rssm_p)
+        B, T = obs.shape[0], obs.shape[1]
+        disc = cfg.variant == _lib.DISCRETE
+        need_bwd = cfg.record and any(ctx.needs_input_grad)
+        ob, ac, n1, n2 = _f32c(obs), _f32c(act), _f32c(noise_pri), _f32c(noise_post)
+
+        def seq_bufs():
+            de = torch.empty(B, T, cfg.D, device=dev)
+            st = torch.empty(B, T, cfg.S_in, device=dev)
+            if disc:
+                return de, st, torch.empty(B, T, cfg.C, cfg.S, device=dev), None
+            return de, st, torch.empty(B, T, cfg.S, device=dev), torch.empty(B, T, cfg.S, device=dev)
+
+        pri, post = seq_bufs(), seq_bufs()
+        flags = _lib.FLAG_SAVE_FOR_BWD if need_bwd else 0
+        d = cfg.dims(B, T, flags, _lib.BF16)
+        saved_n = lib.wmrl_saved_bytes(C.byref(d), _lib.OP_OBSERVE) if need_bwd else 0
+        saved = _bytes(saved_n, dev) if need_bwd else None
+        ws_n = lib.wmrl_workspace_bytes(C.byref(d), _lib.OP_OBSERVE)
+        ws = _bytes(ws_n, dev)
+        if B > 0 and T > 0:
+            _native(dev, lib.wmrl_observe_fwd_bf16, C.byref(d), packed.data_ptr(), ob.data_ptr(), ac.data_ptr(), n1.data_ptr(),
+                    n2.data_ptr(), pri[0].data_ptr(), pri[1].data_ptr(), pri[2].data_ptr(), _lib.ptr(pri[3]),
+                    post[0].data_ptr(), post[1].data_ptr(), post[2].data_ptr(), _lib.ptr(post[3]), _lib.ptr(saved), saved_n,
+                    ws.data_ptr(), ws_n, _stream_ptr(dev))
+        if T > 0:
+            pri[2][:, 0] = init_pri_da.detach()
+            post[2][:, 0] = init_post_da.detach()
+            if not disc:
+                pri[3][:, 0] = init_pri_db.detach()
+                post[3][:, 0] = init_post_db.detach()
+        ctx.cfg, ctx.disc, ctx.packed = cfg, disc, packed
+        ctx.shape = (B, T, obs.shape[2], act.shape[2])
+        ctx.n_params = len(rssm_p)
+        if need_bwd:
+            empty = torch.empty(0, device=dev)
+            ctx.save_for_backward(n1, n2, pri[0], pri[2], pri[3] if pri[3] is not None else empty, post[2],
+                                  post[3] if post[3] is not None else empty, saved, *[p.detach() for p in rssm_p])
         if disc:
-            return de, st, torch.empty(B, T, cfg.C, cfg.S, device=dev), None
-        return de, st, torch.empty(B, T, cfg.S, device=dev), torch.empty(B, T, cfg.S, device=dev)
+            return pri[0], pri[1], pri[2], post[0], post[1], post[2]
+        return pri + post
 
-    pri, post = seq_bufs(), seq_bufs()
-    d = cfg.dims(B, T, 0, _lib.BF16)
-    ws_n = lib.wmrl_workspace_bytes(C.byref(d), _lib.OP_OBSERVE)
-    ws = _bytes(ws_n, dev)
-    if B > 0 and T > 0:
-        _native(dev, lib.wmrl_observe_fwd_bf16, C.byref(d), packed.data_ptr(), ob.data_ptr(), ac.data_ptr(), n1.data_ptr(),
-                n2.data_ptr(), pri[0].data_ptr(), pri[1].data_ptr(), pri[2].data_ptr(), _lib.ptr(pri[3]), post[0].data_ptr(),
-                post[1].data_ptr(), post[2].data_ptr(), _lib.ptr(post[3]), ws.data_ptr(), ws_n, _stream_ptr(dev))
-    if T > 0:
-        pri[2][:, 0] = inits[0]
-        post[2][:, 0] = inits[2]
-        if not disc:
-            pri[3][:, 0] = inits[1]
-            post[3][:, 0] = inits[3]
-    if disc:
-        return pri[0], pri[1], pri[2], post[0], post[1], post[2]
-    return pri + post
+    @staticmethod
+    def backward(ctx, *gouts):
+        lib = _lib.load()
+        cfg, disc = ctx.cfg, ctx.disc
+        n1, n2, p_de, p_da, p_db, q_da, q_db, saved, *params = ctx.saved_tensors
+        dev = p_de.device
+        B, T, E, A = ctx.shape
+
+        def prep(g):
+            return None if g is None else g.to(torch.float32).contiguous()
+
+        g = [prep(x) for x in gouts]
+        if disc:
+            gp_de, gp_st, gp_da, gp_db, gq_de, gq_st, gq_da, gq_db = g[0], g[1], g[2], None, g[3], g[4], g[5], None
+        else:
+            gp_de, gp_st, gp_da, gp_db, gq_de, gq_st, gq_da, gq_db = g
+        g_de = gp_de if gq_de is None else (gq_de if gp_de is None else gp_de + gq_de)
+        d = cfg.dims(B, T, _lib.FLAG_SAVE_FOR_BWD | _lib.FLAG_BACKWARD, _lib.BF16)
+        gr = [torch.zeros(p.shape, device=dev, dtype=torch.float32) for p in params]
+        g_obs = torch.zeros(B, T, E, device=dev)
+        g_act = torch.zeros(B, T, A, device=dev)
+        ws_n = lib.wmrl_workspace_bytes(C.byref(d), _lib.OP_OBSERVE)
+        ws = _bytes(ws_n, dev)
+        gw = _rssm_ptrs(gr)
+        if B > 0 and T > 1:
+            _native(dev, lib.wmrl_observe_bwd_bf16, C.byref(d), ctx.packed.data_ptr(), n1.data_ptr(), n2.data_ptr(),
+                    p_de.data_ptr(), p_da.data_ptr(), None if disc else p_db.data_ptr(), q_da.data_ptr(),
+                    None if disc else q_db.data_ptr(), saved.data_ptr(), _lib.ptr(g_de), _lib.ptr(gp_st), _lib.ptr(gp_da),
+                    _lib.ptr(gp_db), _lib.ptr(gq_st), _lib.ptr(gq_da), _lib.ptr(gq_db), C.byref(gw), g_obs.data_ptr(),
+                    g_act.data_ptr(), ws.data_ptr(), ws_n, _stream_ptr(dev))
+        need = ctx.needs_input_grad
+
+        def first(gseq):
+            return None if gseq is None else gseq[:, 0]
+
+        grads = [None, None, g_obs if need[2] else None, g_act if need[3] else None, None, None,
+                 first(gp_da) if need[6] else None, first(gp_db) if need[7] else None,
+                 first(gq_da) if need[8] else None, first(gq_db) if need[9] else None]
+        for i, gt in enumerate(gr):
+            grads.append(gt if need[10 + i] else None)
+        return tuple(grads)
 
 
 # ----------------------------------------------------------------------------

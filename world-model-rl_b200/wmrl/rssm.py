@@ -21,8 +21,8 @@ import torch
 from torch import nn
 
 from . import _lib
-from .functional import (ImagineRollout, ObserveRollout, PackedObserveWeights, PackedWeights, PathConfig,
-                         observe_rollout_bf16)
+from .functional import (ImagineRollout, ObserveRollout, ObserveRolloutBF16, PackedObserveWeights, PackedWeights,
+                         PathConfig)
 from .state import (InternalStateContinuous, InternalStateContinuousSequence, InternalStateDiscrete,
                     InternalStateDiscreteSequence)
 
@@ -252,14 +252,11 @@ class RSSMBase(nn.Module):
             inits = (init_pri.mean, init_pri.std, init_post.mean, init_post.std)
         rssm_p = self._rssm_tensors()
         packed = None
-        if (cfg.precision == _lib.BF16 and T > 1 and obs_embeds.is_cuda
-                and not (torch.is_grad_enabled() and (obs_embeds.requires_grad or action_embs.requires_grad
-                                                      or any(p.requires_grad for p in rssm_p)))):
-            # filtering without a gradient record (evaluation, acting, start states of imagination): bf16 tcgen05 chain
+        if cfg.precision == _lib.BF16 and T > 1 and obs_embeds.is_cuda:
+            # filtering AND its full backward (world-model training) on the bf16 layer-wise tcgen05 chain
             packed = self._packed_obs.get(cfg, rssm_p)
         if packed is not None:
-            outs = observe_rollout_bf16(cfg, packed, obs_embeds, action_embs.to(device), n_pri, n_post,
-                                        tuple(None if t is None else t.to(device) for t in inits))
+            outs = ObserveRolloutBF16.apply(cfg, packed, obs_embeds, action_embs.to(device), n_pri, n_post, *inits, *rssm_p)
         else:
             outs = ObserveRollout.apply(cfg, obs_embeds, action_embs.to(device), n_pri, n_post, *inits, *rssm_p)
         cont_cls, disc_cls = _sequence_types()
