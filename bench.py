@@ -481,6 +481,39 @@ def aux_configs(dev):
             "fwd_bwd_tflops": FL_FB * B * H / t_ms / 1e9, "fwd_bwd_frac_of_bf16_burst": FL_FB * B * H / t_ms / 1e9 / burst,
             "flops_per_latent_step_fwd": FL_F, "flops_per_latent_step_fwd_bwd": FL_FB}
         del rssm, actor, init, gf
+    out.update(aux_config2_filtering(dev))
+    return out
+
+
+def aux_config2_filtering(dev):
+    """BASELINE configs[2], world-model side: discrete posterior filtering over 50 sequences x 51 frames (conv-encoder
+    embedding E = 1024), forward without a gradient record and forward + full backward (RSSM weight gradients), on the
+    bf16 layer-wise chain and on the fp32 chain."""
+    import wmrl
+    B, T, D, S, C, E, A = 50, 51, 600, 32, 32, 1024, 6
+    out = {}
+    g = torch.Generator().manual_seed(3)
+    obs = torch.relu(torch.randn(B, T, E, generator=g)).to(dev)
+    act = (torch.rand(B, T, A, generator=g) * 2 - 1).to(dev)
+    gf = torch.randn(B, T - 1, D + S * C, generator=g).to(dev) / B
+    for prec in ("bf16", "fp32"):
+        torch.manual_seed(0)
+        rssm = wmrl.DiscreteRSSM(D, D, S, C, E, A, precision=prec).to(dev)
+
+        def fwd():
+            with torch.no_grad():
+                rssm.observe_rollout(obs, act)
+
+        def step():
+            rssm.zero_grad(set_to_none=True)
+            _, post = rssm.observe_rollout(obs, act)
+            (post.get_features() * gf).sum().backward()
+
+        f_ms, t_ms = _event_ms(fwd, 10), _event_ms(step, 5)
+        out[f"configs[2] discrete observe 50x51 (E 1024), {prec}"] = {
+            "fwd_ms": f_ms, "fwd_bwd_ms": t_ms, "fwd_bwd_sample_steps_per_s": B * (T - 1) / t_ms * 1e3,
+            "flops_per_sample_step_fwd_bwd": 32047200}
+        del rssm
     return out
 
 

@@ -110,6 +110,38 @@ def run_observe(name, B, T, precision, iters=10):
     return out
 
 
+def run_observe_train(name, B, T, precision, iters=5):
+    """configs[2] world-model side: observe_rollout forward (recording) + full backward (RSSM weight gradients)."""
+    D, S, C, Hd, E, A = 600, 32, 32, 600, 1024, 6
+    rssm, _ = HG.build_modules("discrete", D, S, C, Hd, E, A, 64, 1, precision=precision)
+    g = torch.Generator().manual_seed(3)
+    obs = torch.relu(torch.randn(B, T, E, generator=g)).cuda()
+    act = (torch.rand(B, T, A, generator=g) * 2 - 1).cuda()
+    gf = torch.randn(B, T - 1, D + S * C, device="cuda") / B
+    gl = torch.randn(B, T - 1, C, S, device="cuda") / B
+
+    def step():
+        rssm.zero_grad(set_to_none=True)
+        pri, post = rssm.observe_rollout(obs, act)
+        ((post.get_features() * gf).sum() + (pri.logits[:, 1:] * gl).sum() + (post.logits[:, 1:] * gl).sum()).backward()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    fl = 32047200       # SURVEY 8d: observe fwd+bwd (wgrad + dgrad) FLOPs per sample-step
+    out = {"case": name + " fwd+bwd", "precision": precision, "ms": round(ms, 3), "sample_steps_per_s": B * (T - 1) / ms * 1e3,
+           "tflops": fl * B * (T - 1) / ms / 1e9}
+    print(json.dumps(out), flush=True)
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c5", "c2f32"]
     if "c2" in which:
@@ -127,5 +159,10 @@ if __name__ == "__main__":
     if "c3" in which:
         run_observe("configs[2] discrete observe 50x51 (E 1024) fwd", 50, 51, "bf16")
         run_observe("configs[2] discrete observe 50x51 (E 1024) fwd", 50, 51, "fp32")
+    if "c3t" in which:
+        run_observe_train("configs[2] discrete observe 50x51 (E 1024)", 50, 51, "bf16")
+        run_observe_train("configs[2] discrete observe 50x51 (E 1024)", 50, 51, "fp32")
+        run_observe_train("discrete observe 1024x51 (E 1024)", 1024, 51, "bf16")
+        run_observe_train("discrete observe 1024x51 (E 1024)", 1024, 51, "fp32", iters=2)
     if "c4" in which:   # continuous bench shape; WMRL_BF16_PATH=layer forces the chain
         run("configs[3] continuous 65536x15", "continuous", 200, 30, 1, 200, 6, 512, 3, 65536, 15, iters=5)
