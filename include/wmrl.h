@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define WMRL_ABI_VERSION 2
+#define WMRL_ABI_VERSION 3
 #if defined(__GNUC__)
 #define WMRL_API __attribute__((visibility("default")))
 #else
@@ -284,6 +284,56 @@ WMRL_API int wmrl_ln_act_fwd(int32_t M, int32_t W, const float* x, const float* 
 WMRL_API int wmrl_ln_act_bwd(int32_t M, int32_t W, const float* dy, const float* xhat, const float* rstd,
                     const float* gamma, const float* beta, int32_t act, float* dx, float* dgamma, float* dbeta,
                     void* stream);
+
+/*
+ * The MLP heads either side of the path on the bf16 tcgen05 chain: the reward / done models
+ * (rssm_world_model/models.py:3-37, [Linear, LayerNorm, SiLU] x depth -> Linear, called on the imagined features at
+ * world_model.py:178-180) and the value critic / target critic (trainers/value/critic.py:4-29, ReLU; called at
+ * value_trainer.py:121-123).  rows = B * H feature rows; hidden % 32 == 0, hidden <= 512, out_dim <= 16.
+ *   wmrl_mlp_to_panel   fp32 x[rows][in_dim] -> the bf16 MMA panel every head over the same features reads
+ *   wmrl_mlp_fwd_bf16   out[rows][out_dim] (pre-output-activation); with WMRL_MLP_SAVE records y / x-hat / rstd of
+ *                       every block into `saved` for the backward
+ *   wmrl_mlp_bwd_bf16   g_x[rows][in_dim] (NULL: skipped; WMRL_MLP_XGRAD_ACCUMULATE adds onto it) and, with
+ *                       WMRL_MLP_WGRAD, the parameter gradients (ADDED into gw's tensors: zero them first; NULL
+ *                       members are skipped).  dims.flags must carry the same WMRL_MLP_WGRAD bit in
+ *                       wmrl_mlp_workspace_bytes(d, 1) and in the call.
+ * Weights travel as a packed bf16 image (wmrl_mlp_pack) holding the forward and the transposed backward operands.
+ */
+#define WMRL_MAX_MLP_LAYERS 8
+enum { WMRL_ACT_ELU = 0, WMRL_ACT_SILU = 1, WMRL_ACT_RELU = 2 };
+enum { WMRL_MLP_SAVE = 1, WMRL_MLP_WGRAD = 2, WMRL_MLP_XGRAD_ACCUMULATE = 4 };
+typedef struct wmrl_mlp_dims {
+  int64_t rows;
+  int32_t in_dim, hidden, depth, out_dim;
+  int32_t act;     /* WMRL_ACT_*  */
+  int32_t flags;   /* WMRL_MLP_*  */
+} wmrl_mlp_dims;
+typedef struct wmrl_mlp_params {
+  const float* lin_w[WMRL_MAX_MLP_LAYERS];   /* [hidden][in_dim] (block 0) or [hidden][hidden] */
+  const float* lin_b[WMRL_MAX_MLP_LAYERS];
+  const float* ln_g[WMRL_MAX_MLP_LAYERS];
+  const float* ln_b[WMRL_MAX_MLP_LAYERS];
+  const float* out_w;                        /* [out_dim][hidden] */
+  const float* out_b;
+} wmrl_mlp_params;
+typedef struct wmrl_mlp_grads {
+  float* lin_w[WMRL_MAX_MLP_LAYERS];
+  float* lin_b[WMRL_MAX_MLP_LAYERS];
+  float* ln_g[WMRL_MAX_MLP_LAYERS];
+  float* ln_b[WMRL_MAX_MLP_LAYERS];
+  float* out_w;
+  float* out_b;
+} wmrl_mlp_grads;
+WMRL_API size_t wmrl_mlp_packed_bytes(const wmrl_mlp_dims* d);      /* 0: shape not supported */
+WMRL_API size_t wmrl_mlp_panel_bytes(const wmrl_mlp_dims* d);
+WMRL_API size_t wmrl_mlp_saved_bytes(const wmrl_mlp_dims* d);
+WMRL_API size_t wmrl_mlp_workspace_bytes(const wmrl_mlp_dims* d, int32_t backward);
+WMRL_API int wmrl_mlp_pack(const wmrl_mlp_dims* d, const wmrl_mlp_params* w, void* packed, void* stream);
+WMRL_API int wmrl_mlp_to_panel(const wmrl_mlp_dims* d, const float* x, void* panel, void* stream);
+WMRL_API int wmrl_mlp_fwd_bf16(const wmrl_mlp_dims* d, const void* packed, const void* x_panel, float* out, void* saved,
+                      size_t saved_bytes, void* ws, size_t ws_bytes, void* stream);
+WMRL_API int wmrl_mlp_bwd_bf16(const wmrl_mlp_dims* d, const void* packed, const void* x_panel, const void* saved,
+                      const float* g_out, const wmrl_mlp_grads* gw, float* g_x, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -60,6 +60,24 @@ def _lin(x, w, b, emu: bool):
 
 
 # --------------------------------------------------------------------------
+# MLP heads next to the path (rssm_world_model/models.py:3-37, trainers/value/critic.py:4-29)
+# --------------------------------------------------------------------------
+def mlp_head(sd: Weights, x: torch.Tensor, act: str = "silu", emu: bool = False) -> torch.Tensor:
+    """[Linear, LayerNorm(eps 1e-5), act] x depth -> Linear over the last dim, from an ``nn.Sequential`` state dict
+    ("0.weight", "1.weight", ... as DenseModel.fc / ValueCritic.layers hold them; models.py:10-22, critic.py:12-27).
+    ``emu``: bf16 MMA operands (activations and weights), fp32 accumulation - the tcgen05 chain's arithmetic."""
+    fn = {"elu": F.elu, "silu": F.silu, "relu": F.relu}[act]
+    l = 0
+    while f"{3 * l + 1}.weight" in sd:
+        w, b = sd[f"{3 * l}.weight"], sd[f"{3 * l}.bias"]
+        x = _lin(x, w, b, emu)
+        x = F.layer_norm(x, (w.shape[0],), sd[f"{3 * l + 1}.weight"], sd[f"{3 * l + 1}.bias"], 1e-5)
+        x = fn(x)
+        l += 1
+    return _lin(x, sd[f"{3 * l}.weight"], sd[f"{3 * l}.bias"], emu)
+
+
+# --------------------------------------------------------------------------
 # Actor  (components/models/actor.py)
 # --------------------------------------------------------------------------
 def actor_num_layers(aw: Weights) -> int:

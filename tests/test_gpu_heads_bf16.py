@@ -1,0 +1,145 @@
+"""The MLP heads (DenseModel reward / done, ValueCritic) on the bf16 tcgen05 chain (wmrl_mlp_fwd_bf16 /
+wmrl_mlp_bwd_bf16) against the oracle: forward against the bf16-emulating restatement (tight) and the fp32 modules
+(north_star tolerance rtol 1e-2 of the output scale); every gradient - d features, all Linear / LayerNorm parameters
+- against torch autograd through the bf16-emulating oracle (cosine >= 0.9995, relative Frobenius error <= 2e-2) and
+against fp32 autograd of the module itself.  SiLU / ELU heads meet the same bound in fp32; the ReLU critic only a
+looser one (cosine >= 0.99, relative error <= 0.12): a pre-activation within bf16 rounding of zero falls on the
+other side of the kink, each flip changes a full-sized gradient element, and ~0.1 % flips per block are ~3 % of
+gradient norm - a property of bf16 operands, reproduced exactly by the emulating oracle."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _make(kind, F_):
+    import wmrl
+    if kind == "critic":
+        return wmrl.ValueCritic(F_, num_layers=3, hidden_dim=512, precision="bf16"), "relu", "layers"
+    if kind == "done":
+        return wmrl.DenseModel(depth=3, input_dim=F_, hidden_dim=256, output_dim=1, output_act=torch.nn.Sigmoid,
+                               precision="bf16"), "silu", "fc"
+    if kind == "elu2":
+        return wmrl.DenseModel(depth=2, input_dim=F_, hidden_dim=96, output_dim=5, hidden_act=torch.nn.ELU,
+                               precision="bf16"), "elu", "fc"
+    return wmrl.DenseModel(depth=3, input_dim=F_, hidden_dim=256, output_dim=1, precision="bf16"), "silu", "fc"
+
+
+def _perturb(m, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() == 1:   # biases / LayerNorm affine away from their trivial init
+                p.add_(torch.randn(p.shape, generator=g) * 0.2)
+
+
+@pytest.mark.parametrize("kind,F_,B,H", [("reward", 230, 300, 5), ("done", 230, 129, 3), ("critic", 230, 300, 5),
+                                         ("critic", 1624, 64, 4), ("elu2", 40, 7, 1)])
+def test_forward_and_gradients(kind, F_, B, H):
+    from oracle import rssm_oracle as O
+    torch.manual_seed(11)
+    m, act, attr = _make(kind, F_)
+    _perturb(m, 5)
+    ref = copy.deepcopy(m)
+    ref.precision = "fp32"
+    x = torch.randn(B, H, F_)
+    # oracle, fp32 on the CPU (the torch module itself is the reference's implementation)
+    xr = x.clone().requires_grad_(True)
+    seq_r = getattr(ref, attr)
+    yr_pre = seq_r(xr)
+    yr = ref.output_act(yr_pre) if hasattr(ref, "output_act") else yr_pre
+    gy = torch.randn_like(yr)
+    yr.backward(gy)
+    sd = {k: v.detach() for k, v in seq_r.state_dict().items()}
+    y_emu = O.mlp_head(sd, x, act, emu=True)
+    torch.testing.assert_close(O.mlp_head(sd, x, act, emu=False), yr_pre.detach(), rtol=1e-5, atol=1e-5)
+    # chain
+    mc = m.cuda()
+    xc = x.cuda().requires_grad_(True)
+    yc = mc(xc)
+    assert yc.shape == yr.shape
+    yc.backward(gy.cuda())
+    pre_c = getattr(mc, attr)
+    with torch.no_grad():
+        import wmrl.functional as Fn
+        yc_pre = Fn.mlp_forward_bf16(pre_c, xc.detach())
+    scale = float(yr_pre.detach().abs().max())
+    assert float((yc_pre.cpu() - y_emu).abs().max()) <= 2e-3 * max(scale, 1.0)
+    assert float((yc_pre.cpu() - yr_pre.detach()).abs().max()) <= 1e-2 * max(scale, 1.0)
+
+    def close(a, b, what, cos_min=0.9995, rel_max=2e-2):
+        a, b = a.detach().cpu().double().flatten(), b.detach().double().flatten()
+        nb = float(b.norm())
+        if nb == 0:
+            assert float(a.norm()) == 0, what
+            return
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+        rel = float((a - b).norm() / nb)
+        assert cos >= cos_min and rel <= rel_max, (what, cos, rel)
+
+    # autograd through the bf16-emulating oracle (same kink decisions as the chain)
+    xe = x.clone().requires_grad_(True)
+    sde = {k: v.detach().clone().requires_grad_(True) for k, v in seq_r.state_dict().items()}
+    ye_pre = O.mlp_head(sde, xe, act, emu=True)
+    ye = ref.output_act(ye_pre) if hasattr(ref, "output_act") else ye_pre
+    ye.backward(gy)
+    close(xc.grad, xe.grad, "d x (emu)")
+    for n, pc in pre_c.named_parameters():
+        close(pc.grad, sde[n].grad, n + " (emu)")
+    loose = dict(cos_min=0.99, rel_max=0.12) if act == "relu" else {}
+    close(xc.grad, xr.grad, "d x", **loose)
+    for (n, pc), (_, pr) in zip(mc.named_parameters(), ref.named_parameters()):
+        close(pc.grad, pr.grad, n, **loose)
+
+
+def test_feature_gradient_only_and_shared_panel():
+    """frozen head (target critic, reward model inside FreezeParameters): only d features; two heads over the SAME
+    feature tensor share one converted panel and their input gradients add up."""
+    import wmrl
+    import wmrl.functional as Fn
+    torch.manual_seed(2)
+    F_ = 230
+    a = wmrl.ValueCritic(F_, precision="bf16").cuda()
+    b = wmrl.DenseModel(input_dim=F_, precision="bf16").cuda()
+    for p in list(a.parameters()) + list(b.parameters()):
+        p.requires_grad_(False)
+    x = torch.randn(260, 4, F_, device="cuda", requires_grad=True)
+    ya = a(x)
+    panel = Fn._PANELS.panel
+    yb = b(x)
+    assert Fn._PANELS.panel is panel          # converted once
+    (ya.sum() + 2.0 * yb.sum()).backward()
+    ar, br = copy.deepcopy(a).cpu(), copy.deepcopy(b).cpu()
+    ar.precision = br.precision = "fp32"
+    xr = x.detach().cpu().requires_grad_(True)
+    (ar.layers(xr).sum() + 2.0 * br.fc(xr).sum()).backward()
+    g, gr = x.grad.cpu().flatten().double(), xr.grad.flatten().double()
+    assert float(torch.dot(g, gr) / (g.norm() * gr.norm())) >= 0.99     # ReLU critic vs fp32: the kink bound (see header)
+    assert float((g - gr).norm() / gr.norm()) <= 0.12
+    assert all(p.grad is None for p in a.parameters())
+    # a new tensor object is converted afresh even if the allocator hands back the same address
+    x2 = torch.randn(260, 4, F_, device="cuda")
+    y2 = a(x2)
+    torch.testing.assert_close(y2, a(x2.clone()), rtol=0, atol=0)
+
+
+def test_large_rows_property():
+    """983 040 feature rows (configs[3]: 65 536 x 15): the chain is row-wise - a slice of the big batch equals the same
+    rows run alone, bit for bit."""
+    import wmrl
+    torch.manual_seed(4)
+    m = wmrl.ValueCritic(230, precision="bf16").cuda()
+    x = torch.randn(65536, 15, 230, device="cuda")
+    with torch.no_grad():
+        y = m(x)
+        assert y.shape == (65536, 15, 1) and bool(torch.isfinite(y).all())
+        sub = x[40000:40003].clone()
+        torch.testing.assert_close(m(sub), y[40000:40003], rtol=0, atol=0)

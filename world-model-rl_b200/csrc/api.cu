@@ -315,4 +315,51 @@ int wmrl_observe_bwd(const wmrl_dims* d, const wmrl_rssm_params* w, const float*
                          g_actions, (float*)ws, (cudaStream_t)stream);
 }
 
+size_t wmrl_mlp_packed_bytes(const wmrl_mlp_dims* d) { return tcm_packed_bytes(d); }
+size_t wmrl_mlp_panel_bytes(const wmrl_mlp_dims* d) { return tcm_panel_bytes(d); }
+size_t wmrl_mlp_saved_bytes(const wmrl_mlp_dims* d) { return tcm_saved_bytes(d); }
+size_t wmrl_mlp_workspace_bytes(const wmrl_mlp_dims* d, int32_t backward) { return tcm_workspace_bytes(d, backward); }
+
+int wmrl_mlp_pack(const wmrl_mlp_dims* d, const wmrl_mlp_params* w, void* packed, void* stream) {
+  WMRL_REQUIRE(d && w && packed, "mlp_pack: NULL argument");
+  WMRL_REQUIRE(tcm_supported(d), "mlp_pack: shape not supported (hidden % 32 == 0, hidden <= 512, out_dim <= 16)");
+  for (int l = 0; l < d->depth; ++l)
+    WMRL_REQUIRE(w->lin_w[l] && w->lin_b[l] && w->ln_g[l] && w->ln_b[l], "mlp_pack: NULL block parameter");
+  WMRL_REQUIRE(w->out_w && w->out_b, "mlp_pack: NULL output Linear");
+  if (int r = require_device()) return r;
+  return tcm_pack(d, w, packed, (cudaStream_t)stream);
+}
+
+int wmrl_mlp_to_panel(const wmrl_mlp_dims* d, const float* x, void* panel, void* stream) {
+  WMRL_REQUIRE(d && tcm_supported(d), "mlp_to_panel: shape not supported");
+  if (d->rows == 0) return 0;
+  WMRL_REQUIRE(x && panel, "mlp_to_panel: NULL tensor");
+  if (int r = require_device()) return r;
+  return tcm_to_panel(d, x, panel, (cudaStream_t)stream);
+}
+
+int wmrl_mlp_fwd_bf16(const wmrl_mlp_dims* d, const void* packed, const void* x_panel, float* out, void* saved,
+                      size_t saved_bytes, void* ws, size_t ws_bytes, void* stream) {
+  WMRL_REQUIRE(d && tcm_supported(d), "mlp_fwd: shape not supported");
+  if (d->rows == 0) return 0;
+  WMRL_REQUIRE(packed && x_panel && out, "mlp_fwd: NULL tensor");
+  WMRL_REQUIRE(wmrl_device_supports_bf16(), "mlp_fwd: needs an sm_100 device");
+  const bool save = (d->flags & WMRL_MLP_SAVE) != 0;
+  WMRL_REQUIRE(!save || (saved && saved_bytes >= tcm_saved_bytes(d)), "mlp_fwd: saved buffer too small");
+  WMRL_REQUIRE(ws && ws_bytes >= tcm_workspace_bytes(d, 0), "mlp_fwd: workspace too small");
+  if (int r = require_device()) return r;
+  return tcm_fwd(d, packed, x_panel, out, save ? saved : nullptr, ws, (cudaStream_t)stream);
+}
+
+int wmrl_mlp_bwd_bf16(const wmrl_mlp_dims* d, const void* packed, const void* x_panel, const void* saved,
+                      const float* g_out, const wmrl_mlp_grads* gw, float* g_x, void* ws, size_t ws_bytes, void* stream) {
+  WMRL_REQUIRE(d && tcm_supported(d), "mlp_bwd: shape not supported");
+  if (d->rows == 0) return 0;
+  WMRL_REQUIRE(packed && x_panel && saved && g_out, "mlp_bwd: NULL tensor");
+  WMRL_REQUIRE(wmrl_device_supports_bf16(), "mlp_bwd: needs an sm_100 device");
+  WMRL_REQUIRE(ws && ws_bytes >= tcm_workspace_bytes(d, 1), "mlp_bwd: workspace too small");
+  if (int r = require_device()) return r;
+  return tcm_bwd(d, packed, x_panel, saved, g_out, gw, g_x, ws, (cudaStream_t)stream);
+}
+
 }  // extern "C"

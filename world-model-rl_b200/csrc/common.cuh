@@ -123,6 +123,18 @@ int tcl_observe_bwd(const Dims& d, const void* packed, const float* noise_pri, c
                     const float* g_deter, const float* g_pri_stoch, const float* g_pri_da, const float* g_pri_db,
                     const float* g_post_stoch, const float* g_post_da, const float* g_post_db, const wmrl_rssm_grads* gw,
                     float* g_obs, float* g_act, void* ws, cudaStream_t st);
+// MLP heads (reward / done models, critic) on the layer-wise chain
+bool tcm_supported(const wmrl_mlp_dims* d);
+size_t tcm_packed_bytes(const wmrl_mlp_dims* d);
+size_t tcm_panel_bytes(const wmrl_mlp_dims* d);
+size_t tcm_saved_bytes(const wmrl_mlp_dims* d);
+size_t tcm_workspace_bytes(const wmrl_mlp_dims* d, int backward);
+int tcm_pack(const wmrl_mlp_dims* d, const wmrl_mlp_params* w, void* packed, cudaStream_t st);
+int tcm_to_panel(const wmrl_mlp_dims* d, const float* x, void* panel, cudaStream_t st);
+int tcm_fwd(const wmrl_mlp_dims* d, const void* packed, const void* x_panel, float* out, void* saved, void* ws,
+            cudaStream_t st);
+int tcm_bwd(const wmrl_mlp_dims* d, const void* packed, const void* x_panel, const void* saved, const float* g_out,
+            const wmrl_mlp_grads* gw, float* g_x, void* ws, cudaStream_t st);
 // which bf16 forward serves this shape: 1 persistent folded-pair / single-CTA kernel, 2 layer-wise chain, 0 none
 int bf16_path(const Dims& d);
 

@@ -49,7 +49,14 @@ constexpr int kGruTile = 64;                // state columns per GRU work item (
 static_assert((kLSlots & (kLSlots - 1)) == 0, "kLSlots must be a power of two");
 
 enum : int { LE_LN_ELU = 1, LE_BIAS_ELU, LE_MU, LE_GRU, LE_SAMPLE_DISC, LE_SAMPLE_CONT,
-              LB_ELU, LB_GRU, LB_CARRY, LB_EMB, LB_LN, LB_POST };   // LB_*: backward epilogues
+              LB_ELU, LB_GRU, LB_CARRY, LB_EMB, LB_LN, LB_POST,     // LB_*: backward epilogues
+              // the MLP heads on the chain (reward / done models, critic): LayerNorm + SiLU / ReLU blocks, the output
+              // Linear, their backward forms and the input-gradient layer
+              LE_LN_SILU, LE_LN_RELU, LE_OUT, LB_LN_SILU, LB_LN_RELU, LB_XGRAD, kLTypeLast = LB_XGRAD };
+enum : int { kActElu = 0, kActSilu = 1, kActRelu = 2 };
+__host__ __device__ constexpr bool l_is_bwd(int type) {
+  return (type >= LB_ELU && type <= LB_POST) || type == LB_LN_SILU || type == LB_LN_RELU || type == LB_XGRAD;
+}
 
 struct LSeg {
   const uint8_t* a;        // activation panel, tile 0
@@ -128,8 +135,18 @@ __device__ __forceinline__ void l_quarter_sync(int quarter) {
 }
 __device__ __forceinline__ void l_epi_sync() { asm volatile("bar.sync 5, %0;" ::"r"(kLEpiThreads) : "memory"); }
 
-// Linear -> LayerNorm(eps 1e-5) -> ELU (actor.py:23-36); parameters [bias | gamma log2e | beta log2e]
-__device__ __forceinline__ void lepi_ln_elu(const LCtx& c) {
+// activation on zs = z * log2(e) (the LayerNorm affine is pre-scaled): ELU (actor.py:33), SiLU (models.py:12),
+// ReLU (trainers/value/critic.py:19)
+template <int kAct>
+__device__ __forceinline__ float act_scaled(float zs) {
+  if (kAct == kActElu) return elu_scaled(zs);
+  if (kAct == kActRelu) return fmaxf(zs, 0.f) * 0.6931471805599453f;
+  return __fdividef(zs * 0.6931471805599453f, 1.f + ex2_fast(-zs));   // z sigmoid(z)
+}
+// Linear -> LayerNorm(eps 1e-5) -> ELU | SiLU | ReLU (actor.py:23-36, models.py:3-37, critic.py:4-29); parameters
+// [bias | gamma log2e | beta log2e]
+template <int kAct>
+__device__ __forceinline__ void lepi_ln_act(const LCtx& c) {
   const LayerArgs& p = *c.p;
   const int W = p.n, ngrp = W / 32;
   const uint32_t bias = c.prm, gam = bias + W * 4, bet = gam + W * 4;
@@ -177,10 +194,10 @@ __device__ __forceinline__ void lepi_ln_elu(const LCtx& c) {
         xh[i + 1] = fmaf(v[k * 8 + i + 1] + b4.y, rstd, nmr);
         xh[i + 2] = fmaf(v[k * 8 + i + 2] + b4.z, rstd, nmr);
         xh[i + 3] = fmaf(v[k * 8 + i + 3] + b4.w, rstd, nmr);
-        v[k * 8 + i] = elu_scaled(fmaf(xh[i], g4.x, e4.x));
-        v[k * 8 + i + 1] = elu_scaled(fmaf(xh[i + 1], g4.y, e4.y));
-        v[k * 8 + i + 2] = elu_scaled(fmaf(xh[i + 2], g4.z, e4.z));
-        v[k * 8 + i + 3] = elu_scaled(fmaf(xh[i + 3], g4.w, e4.w));
+        v[k * 8 + i] = act_scaled<kAct>(fmaf(xh[i], g4.x, e4.x));
+        v[k * 8 + i + 1] = act_scaled<kAct>(fmaf(xh[i + 1], g4.y, e4.y));
+        v[k * 8 + i + 2] = act_scaled<kAct>(fmaf(xh[i + 2], g4.z, e4.z));
+        v[k * 8 + i + 3] = act_scaled<kAct>(fmaf(xh[i + 3], g4.w, e4.w));
       }
       if (p.save) st_chunk_g(xrow + (size_t)(g * 4 + k) * kLTileChunk, xh);
       st_chunk_g(c.out_row + (size_t)(g * 4 + k) * kLTileChunk, v + k * 8);
@@ -230,6 +247,24 @@ __device__ __forceinline__ void lepi_mu(const LCtx& c) {
   }
   st_chunk_g(c.out_row, v);
   st_chunk_g(c.out_row + kLTileChunk, v + 8);
+}
+
+// output Linear of an MLP head (models.py:22, critic.py:26): out[row][0..O) = acc + bias, fp32, O = p.A <= 16
+__device__ __forceinline__ void lepi_out(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  if (c.q != 0) return;
+  float v[16];
+  tmem_ld16(c.tmem_lane, v);
+  tmem_ld_wait();
+  if (!c.valid) return;
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 b4 = lds4(c.prm + i * 4);
+    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (i < p.A) p.f0[c.b * p.A + i] = v[i];
 }
 
 // GRUCell gates (rssm.py:66) of one 64-column tile: TMEM [i_n | r | z | h_n]; parameters [b_r | b_z | b_in | b_hn]
@@ -753,14 +788,50 @@ __device__ __forceinline__ void lepib_post(const LCtx& c) {
   }
 }
 
+// input gradient of an MLP head: accumulator = g_pre_0 W_0 -> fp32 rows of g_x[R][F] (p.D = F), coalesced through the
+// staging transpose; p.mode != 0 adds onto what g_x holds (several heads sharing one feature tensor)
+__device__ __forceinline__ void lepib_xgrad(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  const long long b0 = (long long)c.mt * 128 + c.quarter * 32;
+  const int nr = (int)max(0LL, min(32LL, (long long)p.B - b0));
+  for (int blk = c.q; blk * 32 < p.n; blk += 4) {
+    const int col = c.nt * p.n + blk * 32;
+    if (col >= p.D) break;
+    float acc[32];
+    tmem_ld32(c.tmem_lane + blk * 32, acc);
+    tmem_ld_wait();
+    const int nc = min(32, p.D - col);
+    float* dst = p.f0 + b0 * p.D + col;
+    if (p.mode) {
+      float old[32];
+      load_rows32(c, dst, p.D, nr, nc, old);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] += old[i];
+    }
+    store_rows32(c, dst, p.D, nr, nc, acc);
+  }
+}
+
 // LayerNorm(eps 1e-5, affine) + ELU backward of one actor block (actor.py:23-36) from the recorded x-hat / rstd / y:
 //   g_u = g_y ELU'(u) with ELU'(u) = 1 (y > 0) | y + 1 from the recorded post-ELU y (no transcendental op: the exp form
 //   was MUFU-bound, 2 x 64K ex2 per work item), g_xh = g_u gamma, g_pre = rstd (g_xh - mean(g_xh) - xh mean(g_xh xh)).
 // parameters [gamma log2e | beta log2e | gamma] (only gamma is read); aux[0] = x-hat, aux[2] = y (read), aux[1] = g_u
 // panel (written), out = g_pre.  32 columns per iteration, all loads of a block in flight together.
+// activation derivative from the recorded tensors: ELU / ReLU from the post-activation y, SiLU from u = x-hat gamma +
+// beta (recomputed in the log2e-scaled domain the forward used): sigma (1 + u (1 - sigma))
+template <int kAct>
+__device__ __forceinline__ float act_grad(float y, float xh, float gs, float bs) {
+  if (kAct == kActElu) return fminf(y + 1.f, 1.f);
+  if (kAct == kActRelu) return y > 0.f ? 1.f : 0.f;
+  const float us = fmaf(xh, gs, bs);
+  const float sg = __fdividef(1.f, 1.f + ex2_fast(-us));
+  return sg * fmaf(us * 0.6931471805599453f, 1.f - sg, 1.f);
+}
+template <int kAct>
 __device__ __forceinline__ void lepib_ln(const LCtx& c) {
   const LayerArgs& p = *c.p;
   const int W = p.n, ngrp = W / 32;
+  const uint32_t gsc = c.prm, bsc = c.prm + W * 4;
   const uint32_t gam = c.prm + 2 * W * 4;
   const size_t ro = (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16;
   const uint8_t* xrow = p.aux[0] + ro;
@@ -776,7 +847,7 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       xu[k] = l_ldg16(xrow + (size_t)(g * 4 + k) * kLTileChunk);
-      yu[k] = l_ldg16(yrow + (size_t)(g * 4 + k) * kLTileChunk);
+      yu[k] = (kAct == kActSilu) ? make_uint4(0, 0, 0, 0) : l_ldg16(yrow + (size_t)(g * 4 + k) * kLTileChunk);
     }
     tmem_ld_wait();
     if (g == c.q) LPROBE(c, 1);
@@ -789,16 +860,22 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
       for (int i = 0; i < 8; i += 4) {
         const float4 w4 = lds4(gam + (g * 32 + k * 8 + i) * 4);
         const float gw[4] = {w4.x, w4.y, w4.z, w4.w};
+        float gs[4] = {0.f, 0.f, 0.f, 0.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
+        if (kAct == kActSilu) {
+          const float4 a4 = lds4(gsc + (g * 32 + k * 8 + i) * 4), b4 = lds4(bsc + (g * 32 + k * 8 + i) * 4);
+          gs[0] = a4.x; gs[1] = a4.y; gs[2] = a4.z; gs[3] = a4.w;
+          bs[0] = b4.x; bs[1] = b4.y; bs[2] = b4.z; bs[3] = b4.w;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float g_u = c.valid ? v[k * 8 + i + e] * fminf(y[i + e] + 1.f, 1.f) : 0.f;   // ELU' = min(y + 1, 1)
+          const float g_u = c.valid ? v[k * 8 + i + e] * act_grad<kAct>(y[i + e], xh[i + e], gs[e], bs[e]) : 0.f;
           const float g_x = g_u * gw[e];
           gu[i + e] = g_u;
           s1 += g_x;
           s2 = fmaf(g_x, xh[i + e], s2);
         }
       }
-      st_chunk_g(gurow + (size_t)(g * 4 + k) * kLTileChunk, gu);
+      if (p.aux[1]) st_chunk_g(gurow + (size_t)(g * 4 + k) * kLTileChunk, gu);
     }
   }
   LPROBE(c, 2);
@@ -821,7 +898,7 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       xu[k] = l_ldg16(xrow + (size_t)(g * 4 + k) * kLTileChunk);
-      yu[k] = l_ldg16(yrow + (size_t)(g * 4 + k) * kLTileChunk);
+      yu[k] = (kAct == kActSilu) ? make_uint4(0, 0, 0, 0) : l_ldg16(yrow + (size_t)(g * 4 + k) * kLTileChunk);
     }
     tmem_ld_wait();
 #pragma unroll
@@ -833,9 +910,15 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
       for (int i = 0; i < 8; i += 4) {
         const float4 w4 = lds4(gam + (g * 32 + k * 8 + i) * 4);
         const float gw[4] = {w4.x, w4.y, w4.z, w4.w};
+        float gs[4] = {0.f, 0.f, 0.f, 0.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
+        if (kAct == kActSilu) {
+          const float4 a4 = lds4(gsc + (g * 32 + k * 8 + i) * 4), b4 = lds4(bsc + (g * 32 + k * 8 + i) * 4);
+          gs[0] = a4.x; gs[1] = a4.y; gs[2] = a4.z; gs[3] = a4.w;
+          bs[0] = b4.x; bs[1] = b4.y; bs[2] = b4.z; bs[3] = b4.w;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float g_x = v[k * 8 + i + e] * fminf(y[i + e] + 1.f, 1.f) * gw[e];
+          const float g_x = v[k * 8 + i + e] * act_grad<kAct>(y[i + e], xh[i + e], gs[e], bs[e]) * gw[e];
           gp[i + e] = c.valid ? rstd * (g_x - m1 - xh[i + e] * m2) : 0.f;
         }
       }
@@ -876,13 +959,13 @@ __device__ __forceinline__ void lepib_prefetch(const LCtx& c, int type) {
         const int col = c.nt * p.n + blk * 32;
         if (col < p.D) l_prefetch(p.f1 + (c.b * (p.H + 1) + p.t) * p.D + col);
       }
-  } else if (type == LB_LN) {
+  } else if (type == LB_LN || type == LB_LN_SILU || type == LB_LN_RELU) {
     if (lead)
       for (int g = c.q; g < p.n / 32; g += 4)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           l_prefetch(p.aux[0] + ro + (size_t)(g * 4 + k) * kLTileChunk);
-          l_prefetch(p.aux[2] + ro + (size_t)(g * 4 + k) * kLTileChunk);
+          if (type != LB_LN_SILU) l_prefetch(p.aux[2] + ro + (size_t)(g * 4 + k) * kLTileChunk);
         }
   }
 }
@@ -1060,12 +1143,18 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
         for (int o = c.q * 32; o < p.n && c.nt * p.n + o < P; o += 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(qrow + o));
       }
-      if (kType >= LB_ELU) lepib_prefetch(c, kType);
+      if (l_is_bwd(kType)) lepib_prefetch(c, kType);
       if (it == 0 && threadIdx.x == 0) LTRACE(6);    // parameters staged, waiting for the accumulator
       mbar_wait_backoff_quiet(accf_bar(ab), use & 1u);
       tc_fence_after();
       if (it == 0 && threadIdx.x == 0) LTRACE(7);    // accumulator complete
-      if (kType == LE_LN_ELU) lepi_ln_elu(c);
+      if (kType == LE_LN_ELU) lepi_ln_act<kActElu>(c);
+      else if (kType == LE_LN_SILU) lepi_ln_act<kActSilu>(c);
+      else if (kType == LE_LN_RELU) lepi_ln_act<kActRelu>(c);
+      else if (kType == LE_OUT) lepi_out(c);
+      else if (kType == LB_LN_SILU) lepib_ln<kActSilu>(c);
+      else if (kType == LB_LN_RELU) lepib_ln<kActRelu>(c);
+      else if (kType == LB_XGRAD) lepib_xgrad(c);
       else if (kType == LE_BIAS_ELU) lepi_bias_elu(c);
       else if (kType == LE_MU) lepi_mu(c);
       else if (kType == LE_GRU) lepi_gru(c, gpf);
@@ -1074,7 +1163,7 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
       else if (kType == LB_GRU) lepib_gru(c);
       else if (kType == LB_CARRY) lepib_carry(c);
       else if (kType == LB_EMB) lepib_emb(c);
-      else if (kType == LB_LN) lepib_ln(c);
+      else if (kType == LB_LN) lepib_ln<kActElu>(c);
       else if (kType == LB_POST) lepib_post(c);
       else lepi_sample_disc<(kS > 0 ? kS : 4)>(c);
       tc_fence_before();
@@ -1105,6 +1194,12 @@ static LayerKernel layer_kernel_for(int type, int S) {
     case LB_EMB: return tc_layer_kernel<LB_EMB, 0>;
     case LB_LN: return tc_layer_kernel<LB_LN, 0>;
     case LB_POST: return tc_layer_kernel<LB_POST, 0>;
+    case LE_LN_SILU: return tc_layer_kernel<LE_LN_SILU, 0>;
+    case LE_LN_RELU: return tc_layer_kernel<LE_LN_RELU, 0>;
+    case LE_OUT: return tc_layer_kernel<LE_OUT, 0>;
+    case LB_LN_SILU: return tc_layer_kernel<LB_LN_SILU, 0>;
+    case LB_LN_RELU: return tc_layer_kernel<LB_LN_RELU, 0>;
+    case LB_XGRAD: return tc_layer_kernel<LB_XGRAD, 0>;
     default: break;
   }
   return S == 32 ? tc_layer_kernel<LE_SAMPLE_DISC, 32> : S == 16 ? tc_layer_kernel<LE_SAMPLE_DISC, 16>
@@ -1834,7 +1929,7 @@ static int tcl_device_setup(int& nsm) {
   WMRL_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
   std::lock_guard<std::mutex> lk(mu);
   if (!attr_set[dev]) {
-    for (int ty = LE_LN_ELU; ty <= LB_POST; ++ty)
+    for (int ty = LE_LN_ELU; ty <= kLTypeLast; ++ty)
       for (int S : {4, 8, 16, 32}) {
         if (ty != LE_SAMPLE_DISC && S != 4) continue;
         WMRL_CUDA_OK(cudaFuncSetAttribute(layer_kernel_for(ty, S), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2607,6 +2702,328 @@ int tcl_observe_bwd(const Dims& d, const void* packed, const float* noise_pri, c
     if (int r = wgrad(c.at(F_ACT, 0), tb(F_ACT), 16, d.A, c.at(G_GX, 0), tb(G_GX), Dp, D, gw->embed_w ? gw->embed_w + d.S_in : nullptr, Ke)) return r;
     if (int r = colsum(c.at(G_GX, 0), tb(G_GX), Dp, D, gw->embed_b)) return r;
   }
+  return 0;
+}
+
+// ==========================================================================
+// MLP heads on the chain: the reward / done models (rssm_world_model/models.py:3-37: [Linear, LayerNorm, SiLU] x depth,
+// Linear) and the value critic (trainers/value/critic.py:4-29: ReLU) over the features the rollout returns
+// (world_model.py:178-180, value_trainer.py:121-123).  R = B * H rows are row tiles of the same tc_layer_kernel:
+//   forward   x panel -> depth x (GEMM + fused LayerNorm + activation, recording y / x-hat / rstd when training) ->
+//             output Linear as a 16-column GEMM tile -> fp32 out[R][O]
+//   backward  g_out -> panel; per block, from the last: dgrad GEMM over the TRANSPOSED next weight with the fused
+//             LayerNorm + activation backward; the input gradient g_x[R][F] in fp32 (coalesced); weight gradients as
+//             MN-major big-K GEMMs over (recorded activation, gradient) panels, biases / affine as column sums.
+// One feature panel (wmrl_mlp_to_panel) feeds every head that consumes the same features.
+// ==========================================================================
+struct MlpShape {
+  long long R; int F, Hh, L, O, act, flags;
+  int Fp, MT;
+};
+static bool mlp_shape(const wmrl_mlp_dims* d, MlpShape& m) {
+  if (!d) return false;
+  m.R = d->rows; m.F = d->in_dim; m.Hh = d->hidden; m.L = d->depth; m.O = d->out_dim; m.act = d->act; m.flags = d->flags;
+  if (m.R < 0 || m.R > 65535ll * 128 || m.F < 1 || m.F > 4096 || m.Hh < 32 || m.Hh > 512 || m.Hh % 32 != 0) return false;
+  if (m.L < 1 || m.L > WMRL_MAX_MLP_LAYERS || m.O < 1 || m.O > 16 || m.act < 0 || m.act > 2) return false;
+  m.Fp = ceil16(m.F);
+  m.MT = (int)((m.R + 127) / 128);
+  return true;
+}
+enum { M_X = 0, M_GOUT, M_Y0, M_XH0 = M_Y0 + WMRL_MAX_MLP_LAYERS, M_RSTD0 = M_XH0 + WMRL_MAX_MLP_LAYERS,
+       M_GP0 = M_RSTD0 + WMRL_MAX_MLP_LAYERS, M_GU0 = M_GP0 + WMRL_MAX_MLP_LAYERS, M_COUNT = M_GU0 + WMRL_MAX_MLP_LAYERS };
+
+static LPlan tcm_make_plan(const MlpShape& m, const wmrl_mlp_params* w) {
+  LPlan lp;
+  Plan& pk = lp.pk;
+  const float* nul = nullptr;
+  constexpr float kLog2e = 1.4426950408889634f;
+  auto kc_for = [&](int nmax) { int kc = (int)(kLSlotBytes / (4096u + (uint32_t)nmax * 32u)); return std::max(1, std::min(kc, 8)); };
+  const int fwd_type = m.act == kActElu ? LE_LN_ELU : (m.act == kActSilu ? LE_LN_SILU : LE_LN_RELU);
+  const int bwd_type = m.act == kActElu ? LB_LN : (m.act == kActSilu ? LB_LN_SILU : LB_LN_RELU);
+  // ---- forward blocks
+  for (int l = 0; l < m.L; ++l) {
+    LLayerH L;
+    L.type = fwd_type; L.NT = 1; L.n = m.Hh; L.dbuf = m.Hh <= 256 ? 1 : 0; L.out = M_Y0 + l; L.layer = l; L.nseg = 1;
+    L.kc = kc_for(m.Hh);
+    L.w_off = pk.data_bytes;
+    const int K = l == 0 ? m.F : m.Hh, Kp = l == 0 ? m.Fp : m.Hh;
+    L.seg[0] = {l == 0 ? M_X : M_Y0 + l - 1, Kp / 16, m.Hh, 0, 0, 1, 0u};
+    l_add_pack(lp, RowSpec(0, m.Hh, m.Hh), w ? w->lin_w[l] : nul, K, 0, K, Kp);
+    L.w_tile_bytes = (uint32_t)(pk.data_bytes - L.w_off);
+    L.ep_off = add_vec(pk, w ? w->lin_b[l] : nul, nul, 0, m.Hh, m.Hh);
+    add_vec(pk, w ? w->ln_g[l] : nul, nul, 0, m.Hh, m.Hh, kLog2e);
+    add_vec(pk, w ? w->ln_b[l] : nul, nul, 0, m.Hh, m.Hh, kLog2e);
+    L.ep_floats = 3u * m.Hh;
+    lp.layers.push_back(L);
+  }
+  // ---- output Linear
+  {
+    LLayerH L;
+    L.type = LE_OUT; L.NT = 1; L.n = 16; L.dbuf = 1; L.out = -1; L.kc = kc_for(16); L.nseg = 1;
+    L.w_off = pk.data_bytes;
+    L.seg[0] = {M_Y0 + m.L - 1, m.Hh / 16, 16, 0, 0, 1, 0u};
+    l_add_pack(lp, RowSpec(0, m.O, 16), w ? w->out_w : nul, m.Hh, 0, m.Hh, m.Hh);
+    L.w_tile_bytes = (uint32_t)(pk.data_bytes - L.w_off);
+    L.ep_off = add_vec(pk, w ? w->out_b : nul, nul, 0, m.O, 16);
+    L.ep_floats = 16;
+    lp.layers.push_back(L);
+  }
+  // ---- backward blocks, last first: g_y_l = g_next W_next -> LayerNorm + activation backward -> g_pre_l
+  for (int l = m.L - 1; l >= 0; --l) {
+    LLayerH L;
+    L.type = bwd_type; L.NT = 1; L.n = m.Hh; L.dbuf = m.Hh <= 256 ? 1 : 0; L.out = M_GP0 + l; L.layer = l; L.nseg = 1;
+    L.kc = kc_for(m.Hh);
+    L.w_off = pk.data_bytes;
+    if (l == m.L - 1) {
+      L.seg[0] = {M_GOUT, 1, m.Hh, 0, 0, 1, 0u};
+      l_add_pack_t(lp, RowSpec(0, m.Hh, m.Hh), w ? w->out_w : nul, m.Hh, {{0, m.O, 16}});
+    } else {
+      L.seg[0] = {M_GP0 + l + 1, m.Hh / 16, m.Hh, 0, 0, 1, 0u};
+      l_add_pack_t(lp, RowSpec(0, m.Hh, m.Hh), w ? w->lin_w[l + 1] : nul, m.Hh, {{0, m.Hh, m.Hh}});
+    }
+    L.w_tile_bytes = (uint32_t)(pk.data_bytes - L.w_off);
+    L.ep_off = add_vec(pk, w ? w->ln_g[l] : nul, nul, 0, m.Hh, m.Hh, kLog2e);
+    add_vec(pk, w ? w->ln_b[l] : nul, nul, 0, m.Hh, m.Hh, kLog2e);
+    add_vec(pk, w ? w->ln_g[l] : nul, nul, 0, m.Hh, m.Hh);
+    L.ep_floats = 3u * m.Hh;
+    lp.blayers.push_back(L);
+  }
+  // ---- input gradient: g_x = g_pre_0 W_0, column tiles of <= 256 input features
+  {
+    LLayerH L;
+    L.type = LB_XGRAD; L.dbuf = 1; L.out = -1; L.nseg = 1;
+    const int total = ceil_to(m.F, 32);
+    L.NT = (total + 255) / 256;
+    L.n = ceil_to((total + L.NT - 1) / L.NT, 32);
+    L.kc = kc_for(L.n);
+    L.w_off = pk.data_bytes;
+    for (int j = 0; j < L.NT; ++j) {
+      const size_t t0 = pk.data_bytes;
+      L.seg[0] = {M_GP0, m.Hh / 16, L.n, 0, 0, 1, 0u};
+      l_add_pack_t(lp, RowSpec(j * L.n, m.F - j * L.n, L.n), w ? w->lin_w[0] : nul, m.F, {{0, m.Hh, m.Hh}});
+      L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+    }
+    L.ep_off = add_vec(pk, nul, nul, 0, 0, 16); L.ep_floats = 0;
+    lp.blayers.push_back(L);
+  }
+  for (const std::vector<LLayerH>* v : {&lp.layers, &lp.blayers})
+    for (const LLayerH& L : *v) {
+      if (L.ep_floats * 4 > kLParamBytes || (L.ep_floats & 3)) return lp;
+      for (int s = 0; s < L.nseg; ++s)
+        if ((uint32_t)L.kc * (4096u + (uint32_t)L.seg[s].n * 32u) > kLSlotBytes) return lp;
+    }
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  pk.off_stage_tab = 256;
+  pk.off_job_tab = 512;
+  pk.off_packops = 768;
+  pk.off_eparams = al(pk.off_packops + pk.pack_ops.size() * sizeof(PackOp) + pk.vec_ops.size() * sizeof(VecOp));
+  pk.off_data = al(pk.off_eparams + pk.eparams_floats * sizeof(float));
+  pk.total_bytes = al(pk.off_data + pk.data_bytes);
+  pk.ok = true;
+  lp.ok = true;
+  return lp;
+}
+
+// panel buffers of one MLP call: [MT][cols/8][2 KB] each.  `saved` holds what the backward reads (y, x-hat, rstd per
+// block); the forward workspace the y panels when nothing is recorded; the backward workspace g_out, g_pre, g_u.
+struct MlpMem {
+  size_t off[M_COUNT]; uint32_t tile[M_COUNT]; int where[M_COUNT];   // where: 0 ws, 1 saved, 2 caller's x panel
+  size_t ws_bytes = 0, saved_bytes = 0;
+};
+static MlpMem tcm_layout(const MlpShape& m, int mode) {   // mode 0 forward, 1 forward recording, 2 backward
+  MlpMem mm{};
+  size_t o[2] = {0, 0};
+  auto place = [&](int buf, int cols, int where, size_t row_bytes = 0) {
+    mm.tile[buf] = row_bytes ? (uint32_t)(128 * row_bytes) : (uint32_t)(cols / 8) * kLTileChunk;
+    mm.where[buf] = where;
+    mm.off[buf] = o[where];
+    o[where] += ((size_t)m.MT * mm.tile[buf] + 1023) / 1024 * 1024;
+  };
+  mm.tile[M_X] = (uint32_t)(m.Fp / 8) * kLTileChunk; mm.where[M_X] = 2; mm.off[M_X] = 0;
+  const int sv = mode == 0 ? 0 : 1;
+  for (int l = 0; l < m.L; ++l) {
+    if (mode == 0 && l >= 2) { mm.tile[M_Y0 + l] = mm.tile[M_Y0 + (l & 1)]; mm.where[M_Y0 + l] = 0; mm.off[M_Y0 + l] = mm.off[M_Y0 + (l & 1)]; }
+    else place(M_Y0 + l, m.Hh, sv);
+    if (mode != 0) { place(M_XH0 + l, m.Hh, 1); place(M_RSTD0 + l, 0, 1, sizeof(float)); }
+  }
+  if (mode == 2) {
+    place(M_GOUT, 16, 0);
+    const bool wg = (m.flags & WMRL_MLP_WGRAD) != 0;
+    for (int l = 0; l < m.L; ++l) {
+      // without weight gradients a block's g_pre is read once, by the next dgrad: two panels ping-pong
+      if (!wg && l >= 2) { mm.tile[M_GP0 + l] = mm.tile[M_GP0 + (l & 1)]; mm.where[M_GP0 + l] = 0; mm.off[M_GP0 + l] = mm.off[M_GP0 + (l & 1)]; }
+      else place(M_GP0 + l, m.Hh, 0);
+      if (wg) place(M_GU0 + l, m.Hh, 0);
+    }
+  }
+  mm.ws_bytes = o[0] + 1024;
+  mm.saved_bytes = o[1] + 1024;
+  return mm;
+}
+
+bool tcm_supported(const wmrl_mlp_dims* d) { MlpShape m; return mlp_shape(d, m) && tcm_make_plan(m, nullptr).ok; }
+size_t tcm_packed_bytes(const wmrl_mlp_dims* d) {
+  MlpShape m;
+  if (!mlp_shape(d, m)) return 0;
+  LPlan lp = tcm_make_plan(m, nullptr);
+  return lp.ok ? lp.pk.total_bytes : 0;
+}
+size_t tcm_panel_bytes(const wmrl_mlp_dims* d) {
+  MlpShape m;
+  return mlp_shape(d, m) ? (size_t)m.MT * (m.Fp / 8) * kLTileChunk + 1024 : 0;
+}
+size_t tcm_saved_bytes(const wmrl_mlp_dims* d) { MlpShape m; return mlp_shape(d, m) ? tcm_layout(m, 1).saved_bytes : 0; }
+size_t tcm_workspace_bytes(const wmrl_mlp_dims* d, int backward) {
+  MlpShape m;
+  return mlp_shape(d, m) ? tcm_layout(m, backward ? 2 : ((m.flags & WMRL_MLP_SAVE) ? 1 : 0)).ws_bytes : 0;
+}
+int tcm_pack(const wmrl_mlp_dims* d, const wmrl_mlp_params* w, void* packed, cudaStream_t st) {
+  MlpShape m;
+  WMRL_REQUIRE(mlp_shape(d, m), "mlp_pack: shape not supported (hidden % 32, hidden <= 512, out_dim <= 16)");
+  LPlan lp = tcm_make_plan(m, w);
+  WMRL_REQUIRE(lp.ok, "mlp_pack: shape not supported by the layer-wise tcgen05 path");
+  return tc_pack_plan(lp.pk, (uint8_t*)packed, st);
+}
+int tcm_to_panel(const wmrl_mlp_dims* d, const float* x, void* panel, cudaStream_t st) {
+  MlpShape m;
+  WMRL_REQUIRE(mlp_shape(d, m), "mlp_to_panel: bad dims");
+  if (m.MT == 0) return 0;
+  tcl_to_panel_kernel<<<dim3(4, (unsigned)m.MT, 1), 256, 0, st>>>(x, (uint8_t*)panel, (int)m.R, 1, m.F, m.Fp, m.MT);
+  WMRL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+struct MlpCall {
+  const MlpShape* m; const MlpMem* mm;
+  uint8_t* ws; uint8_t* saved; const uint8_t* xpanel;
+  const uint8_t* data; const float* ep;
+  int nsm; cudaStream_t st;
+  uint8_t* at(int buf) const {
+    const int w = mm->where[buf];
+    return (w == 2 ? const_cast<uint8_t*>(xpanel) : (w == 1 ? saved : ws)) + mm->off[buf];
+  }
+};
+static int tcm_launch(const MlpCall& c, const LLayerH& L, LayerArgs& a) {
+  const MlpShape& m = *c.m;
+  a.nseg = 1;
+  const int buf = L.seg[0].buf;
+  a.seg[0].a = c.at(buf);
+  a.seg[0].a_tile_bytes = c.mm->tile[buf];
+  a.seg[0].w_off = L.seg[0].w_off;
+  a.seg[0].k16 = (uint16_t)L.seg[0].k16; a.seg[0].n = (uint16_t)L.seg[0].n;
+  a.seg[0].tmem_col = 0; a.seg[0].split = 0; a.seg[0].fresh = 1;
+  a.w = c.data + L.w_off; a.w_tile_bytes = L.w_tile_bytes;
+  a.ep = c.ep + L.ep_off; a.ep_floats = L.ep_floats;
+  a.kc = L.kc; a.dbuf = L.dbuf; a.type = L.type; a.n = L.n; a.NT = L.NT; a.MT = m.MT;
+  a.B = (int)m.R; a.H = 1; a.t = 0; a.D = m.F; a.A = m.O;
+  if (L.out >= 0) { a.out = c.at(L.out); a.out_tile_bytes = c.mm->tile[L.out]; a.out_cols = m.Hh; }
+  const int items = m.MT * L.NT;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)std::min(items, c.nsm));
+  cfg.blockDim = dim3(kLThreads);
+  cfg.dynamicSmemBytes = kLSmemBytes;
+  cfg.stream = c.st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, layer_kernel_for(L.type, 4), a));
+  return 0;
+}
+
+int tcm_fwd(const wmrl_mlp_dims* d, const void* packed, const void* x_panel, float* out, void* saved, void* ws,
+            cudaStream_t st) {
+  MlpShape m;
+  WMRL_REQUIRE(mlp_shape(d, m), "mlp_fwd: shape not supported");
+  if (m.MT == 0) return 0;
+  LPlan lp = tcm_make_plan(m, nullptr);
+  WMRL_REQUIRE(lp.ok, "mlp_fwd: shape not supported by the layer-wise tcgen05 path");
+  const bool rec = saved != nullptr;
+  const MlpMem mm = tcm_layout(m, rec ? 1 : 0);
+  MlpCall c{&m, &mm, (uint8_t*)ws, (uint8_t*)saved, (const uint8_t*)x_panel, nullptr, nullptr, 148, st};
+  if (int r = tcl_device_setup(c.nsm)) return r;
+  const uint8_t* img = (const uint8_t*)packed;
+  c.data = img + lp.pk.off_data;
+  c.ep = (const float*)(img + lp.pk.off_eparams);
+  for (const LLayerH& L : lp.layers) {
+    LayerArgs a{};
+    a.save = rec ? 1 : 0;
+    if (L.type == LE_OUT) a.f0 = out;
+    else if (rec) {
+      a.aux[0] = c.at(M_XH0 + L.layer); a.aux_tile_bytes = mm.tile[M_XH0 + L.layer];
+      a.f0 = (float*)c.at(M_RSTD0 + L.layer);
+    }
+    if (int r = tcm_launch(c, L, a)) return r;
+  }
+  return 0;
+}
+
+int tcm_bwd(const wmrl_mlp_dims* d, const void* packed, const void* x_panel, const void* saved, const float* g_out,
+            const wmrl_mlp_grads* gw, float* g_x, void* ws, cudaStream_t st) {
+  MlpShape m;
+  WMRL_REQUIRE(mlp_shape(d, m), "mlp_bwd: shape not supported");
+  if (m.MT == 0) return 0;
+  LPlan lp = tcm_make_plan(m, nullptr);
+  WMRL_REQUIRE(lp.ok, "mlp_bwd: shape not supported by the layer-wise tcgen05 path");
+  const bool wg = (m.flags & WMRL_MLP_WGRAD) != 0;
+  WMRL_REQUIRE(!wg || gw, "mlp_bwd: WMRL_MLP_WGRAD needs the gradient struct");
+  const MlpMem mm = tcm_layout(m, 2);
+  MlpCall c{&m, &mm, (uint8_t*)ws, (uint8_t*)const_cast<void*>(saved), (const uint8_t*)x_panel, nullptr, nullptr, 148, st};
+  if (int r = tcl_device_setup(c.nsm)) return r;
+  const uint8_t* img = (const uint8_t*)packed;
+  c.data = img + lp.pk.off_data;
+  c.ep = (const float*)(img + lp.pk.off_eparams);
+  tcl_to_panel_kernel<<<dim3(1, (unsigned)m.MT, 1), 256, 0, st>>>(g_out, c.at(M_GOUT), (int)m.R, 1, m.O, 16, m.MT);
+  WMRL_CUDA_OK(cudaGetLastError());
+  for (const LLayerH& L : lp.blayers) {
+    LayerArgs a{};
+    if (L.type == LB_XGRAD) {
+      if (!g_x) continue;
+      a.f0 = g_x;
+      a.mode = (m.flags & WMRL_MLP_XGRAD_ACCUMULATE) ? 1 : 0;
+    } else {
+      a.aux[0] = c.at(M_XH0 + L.layer); a.aux[1] = wg ? c.at(M_GU0 + L.layer) : nullptr; a.aux[2] = c.at(M_Y0 + L.layer);
+      a.aux_tile_bytes = mm.tile[M_XH0 + L.layer];
+      a.f0 = (float*)c.at(M_RSTD0 + L.layer);
+    }
+    if (int r = tcm_launch(c, L, a)) return r;
+  }
+  if (!wg) return 0;
+  auto wgrad = [&](int abuf, int m_cols, int m_valid, int bbuf, int n_cols, int n_valid, float* dW, int ldw) -> int {
+    if (!dW) return 0;
+    Wg2Params q{};
+    q.a_base = c.at(abuf); q.a_blk = mm.tile[abuf]; q.b_base = c.at(bbuf); q.b_blk = mm.tile[bbuf];
+    q.nblocks = m.MT; q.m_cols = m_cols; q.m_valid = m_valid; q.n_cols = n_cols; q.n_valid = n_valid;
+    q.dW = dW; q.ldw = ldw;
+    q.mtiles = (m_cols + 127) / 128; q.ntiles = (n_cols + 255) / 256;
+    const int tl = q.mtiles * q.ntiles;
+    q.splits = std::max(1, std::min(m.MT, c.nsm / tl));
+    tcl_wgrad_kernel<<<dim3(tl, q.splits), kWg2Threads, kWg2Smem, st>>>(q);
+    WMRL_CUDA_OK(cudaGetLastError());
+    return 0;
+  };
+  auto colsum = [&](int xbuf, int ybuf, int cols, int valid, float* out) -> int {
+    if (!out) return 0;
+    Cs2Params q{};
+    q.x_base = c.at(xbuf); q.x_blk = mm.tile[xbuf];
+    q.y_base = ybuf >= 0 ? c.at(ybuf) : nullptr; q.y_blk = ybuf >= 0 ? mm.tile[ybuf] : 0;
+    q.nblocks = m.MT; q.valid = valid; q.out = out;
+    const int chunks = cols / 8;
+    const int ysplit = std::max(1, std::min((m.MT + kCs2Warps - 1) / kCs2Warps, (8 * c.nsm + chunks - 1) / chunks));
+    tcl_colsum_kernel<<<dim3(chunks, ysplit), kCs2Warps * 32, 0, st>>>(q);
+    WMRL_CUDA_OK(cudaGetLastError());
+    return 0;
+  };
+  for (int l = 0; l < m.L; ++l) {
+    if (l == 0) { if (int r = wgrad(M_X, m.Fp, m.F, M_GP0, m.Hh, m.Hh, gw->lin_w[0], m.F)) return r; }
+    else if (int r = wgrad(M_Y0 + l - 1, m.Hh, m.Hh, M_GP0 + l, m.Hh, m.Hh, gw->lin_w[l], m.Hh)) return r;
+    if (int r = colsum(M_GP0 + l, -1, m.Hh, m.Hh, gw->lin_b[l])) return r;
+    if (int r = colsum(M_GU0 + l, -1, m.Hh, m.Hh, gw->ln_b[l])) return r;
+    if (int r = colsum(M_GU0 + l, M_XH0 + l, m.Hh, m.Hh, gw->ln_g[l])) return r;
+  }
+  if (int r = wgrad(M_Y0 + m.L - 1, m.Hh, m.Hh, M_GOUT, 16, m.O, gw->out_w, m.Hh)) return r;
+  if (int r = colsum(M_GOUT, -1, 16, m.O, gw->out_b)) return r;
   return 0;
 }
 

@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwmrl.so")
 MAX_ACTOR_LAYERS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 CONTINUOUS, DISCRETE = 0, 1
 FP32, BF16 = 0, 1
@@ -58,6 +58,22 @@ class ActorGradPtrs(C.Structure):
                 ("mu_w", _f32p), ("mu_b", _f32p)]
 
 
+MAX_MLP_LAYERS = 8
+MLP_SAVE, MLP_WGRAD, MLP_XGRAD_ACCUMULATE = 1, 2, 4
+
+
+class MlpDims(C.Structure):
+    """wmrl_mlp_dims"""
+    _fields_ = [("rows", C.c_int64)] + [(n, C.c_int32) for n in ("in_dim", "hidden", "depth", "out_dim", "act", "flags")]
+
+
+class MlpPtrs(C.Structure):
+    """wmrl_mlp_params and wmrl_mlp_grads share this layout."""
+    _fields_ = [("lin_w", _f32p * MAX_MLP_LAYERS), ("lin_b", _f32p * MAX_MLP_LAYERS),
+                ("ln_g", _f32p * MAX_MLP_LAYERS), ("ln_b", _f32p * MAX_MLP_LAYERS),
+                ("out_w", _f32p), ("out_b", _f32p)]
+
+
 # every symbol include/wmrl.h declares, with its ctypes signature
 _P = C.c_void_p
 _SIGNATURES = {
@@ -91,6 +107,14 @@ _SIGNATURES = {
     "wmrl_linear_wgrad": (C.c_int, [C.c_int32] * 3 + [_P, C.c_int64, _P, C.c_int64, _P, _P]),
     "wmrl_ln_act_fwd": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "wmrl_ln_act_bwd": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    "wmrl_mlp_packed_bytes": (C.c_size_t, [C.POINTER(MlpDims)]),
+    "wmrl_mlp_panel_bytes": (C.c_size_t, [C.POINTER(MlpDims)]),
+    "wmrl_mlp_saved_bytes": (C.c_size_t, [C.POINTER(MlpDims)]),
+    "wmrl_mlp_workspace_bytes": (C.c_size_t, [C.POINTER(MlpDims), C.c_int32]),
+    "wmrl_mlp_pack": (C.c_int, [C.POINTER(MlpDims), C.POINTER(MlpPtrs), _P, _P]),
+    "wmrl_mlp_to_panel": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P]),
+    "wmrl_mlp_fwd_bf16": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
+    "wmrl_mlp_bwd_bf16": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, C.POINTER(MlpPtrs), _P, _P, C.c_size_t, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -746,6 +746,184 @@ def layer_norm_act(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, act
     return LayerNormAct.apply(x, gamma, beta, act)
 
 
+# ----------------------------------------------------------------------------
+# MLP heads on the bf16 tcgen05 chain (wmrl_mlp_*): reward / done models, critic, target critic
+# ----------------------------------------------------------------------------
+def _mlp_pattern(seq: "torch.nn.Sequential"):
+    """(blocks [(Linear, LayerNorm)], act id, output Linear) when ``seq`` is [Linear, LayerNorm, act] x depth -> Linear
+    with one activation type, else None."""
+    nn = torch.nn
+    acts = {nn.ELU: ACT_ELU, nn.SiLU: ACT_SILU, nn.ReLU: ACT_RELU}
+    mods = list(seq)
+    if len(mods) < 4 or (len(mods) - 1) % 3 != 0 or not isinstance(mods[-1], nn.Linear):
+        return None
+    blocks, act = [], None
+    for i in range(0, len(mods) - 1, 3):
+        lin, ln, a = mods[i], mods[i + 1], mods[i + 2]
+        if not (isinstance(lin, nn.Linear) and lin.bias is not None and isinstance(ln, nn.LayerNorm)
+                and ln.elementwise_affine and ln.bias is not None and abs(ln.eps - 1e-5) < 1e-12
+                and len(ln.normalized_shape) == 1 and type(a) in acts):
+            return None
+        if isinstance(a, nn.ELU) and a.alpha != 1.0:
+            return None
+        if act is not None and acts[type(a)] != act:
+            return None
+        act = acts[type(a)]
+        blocks.append((lin, ln))
+    if mods[-1].bias is None:
+        return None
+    hidden = blocks[0][0].out_features
+    if any(b[0].out_features != hidden for b in blocks) or mods[-1].in_features != hidden:
+        return None
+    return blocks, act, mods[-1]
+
+
+def _mlp_dims(rows: int, in_dim: int, hidden: int, depth: int, out_dim: int, act: int, flags: int = 0) -> _lib.MlpDims:
+    return _lib.MlpDims(rows=rows, in_dim=in_dim, hidden=hidden, depth=depth, out_dim=out_dim, act=act, flags=flags)
+
+
+def _mlp_ptrs(params: Sequence[Optional[torch.Tensor]], depth: int) -> _lib.MlpPtrs:
+    """flat order: per block (lin_w, lin_b, ln_g, ln_b), then out_w, out_b (the actor's layout)."""
+    s = _lib.MlpPtrs()
+    for l in range(depth):
+        s.lin_w[l] = _lib.ptr(params[4 * l + 0])
+        s.lin_b[l] = _lib.ptr(params[4 * l + 1])
+        s.ln_g[l] = _lib.ptr(params[4 * l + 2])
+        s.ln_b[l] = _lib.ptr(params[4 * l + 3])
+    s.out_w = _lib.ptr(params[4 * depth])
+    s.out_b = _lib.ptr(params[4 * depth + 1])
+    return s
+
+
+class _PanelCache:
+    """The bf16 MMA panel of the most recent feature tensor: reward model, done model, critic and target critic all
+    read the same ``features`` object (world_model.py:178-180, value_trainer.py:121-123), which is converted once."""
+
+    def __init__(self):
+        self.ref = None
+        self.version = -1
+        self.panel: Optional[torch.Tensor] = None
+
+    def get(self, x: torch.Tensor, x2: torch.Tensor, d: _lib.MlpDims) -> torch.Tensor:
+        import weakref
+        if self.ref is not None and self.ref() is x and self.version == x._version and self.panel is not None:
+            return self.panel
+        lib = _lib.load()
+        dev = x2.device
+        panel = _bytes(lib.wmrl_mlp_panel_bytes(C.byref(d)), dev)
+        _native(dev, lib.wmrl_mlp_to_panel, C.byref(d), x2.data_ptr(), panel.data_ptr(), _stream_ptr(dev))
+        self.ref, self.version, self.panel = weakref.ref(x), x._version, panel
+        return panel
+
+
+_PANELS = _PanelCache()
+_MLP_PACKED: "dict" = {}
+
+
+def _mlp_packed(seq, params, d0: _lib.MlpDims) -> torch.Tensor:
+    """packed bf16 image of one head's weights, refreshed when a parameter's version changes (an optimiser step)."""
+    import weakref
+    lib = _lib.load()
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    ent = _MLP_PACKED.get(id(seq))
+    if ent is not None and ent[0]() is seq and ent[1] == key:
+        return ent[2]
+    dev = params[0].device
+    buf = _bytes(lib.wmrl_mlp_packed_bytes(C.byref(d0)), dev)
+    p32 = [_f32c(p) for p in params]
+    ptrs = _mlp_ptrs(p32, d0.depth)
+    _native(dev, lib.wmrl_mlp_pack, C.byref(d0), C.byref(ptrs), buf.data_ptr(), _stream_ptr(dev))
+    if len(_MLP_PACKED) > 64:
+        for k in [k for k, v in _MLP_PACKED.items() if v[0]() is None]:
+            del _MLP_PACKED[k]
+    _MLP_PACKED[id(seq)] = (weakref.ref(seq), key, buf)
+    return buf
+
+
+class MlpBF16(torch.autograd.Function):
+    """[Linear, LayerNorm, act] x depth -> Linear on the layer-wise tcgen05 chain (wmrl_mlp_fwd_bf16 /
+    wmrl_mlp_bwd_bf16): bf16 operands, fp32 accumulation, fp32 in / out.  Gradients: d x, and the parameters'
+    when any of them requires grad."""
+
+    @staticmethod
+    def forward(ctx, spec, packed, panel, x, *params):
+        lib = _lib.load()
+        in_dim, hidden, depth, out_dim, act = spec
+        dev = x.device
+        rows = x.numel() // in_dim
+        need = x.requires_grad or any(p.requires_grad for p in params)
+        d = _mlp_dims(rows, in_dim, hidden, depth, out_dim, act, _lib.MLP_SAVE if need else 0)
+        out = torch.empty(rows, out_dim, device=dev)
+        saved = _bytes(lib.wmrl_mlp_saved_bytes(C.byref(d)), dev) if need else None
+        ws_n = lib.wmrl_mlp_workspace_bytes(C.byref(d), 0)
+        ws = _bytes(ws_n, dev)
+        if rows > 0:
+            _native(dev, lib.wmrl_mlp_fwd_bf16, C.byref(d), packed.data_ptr(), panel.data_ptr(), out.data_ptr(),
+                    _lib.ptr(saved), 0 if saved is None else saved.numel(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        ctx.spec, ctx.rows, ctx.x_shape = spec, rows, x.shape
+        ctx.packed, ctx.panel, ctx.saved_buf = packed, panel, saved
+        ctx.param_shapes = [p.shape for p in params]
+        return out.reshape(*x.shape[:-1], out_dim)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        in_dim, hidden, depth, out_dim, act = ctx.spec
+        rows = ctx.rows
+        dev = g_out.device
+        need_x = ctx.needs_input_grad[3]
+        need_w = any(ctx.needs_input_grad[4:])
+        g = _f32c(g_out.reshape(rows, out_dim))
+        g_x = torch.empty(rows, in_dim, device=dev) if need_x else None
+        grads = [torch.zeros(s, device=dev) for s in ctx.param_shapes] if need_w else None
+        if rows > 0:
+            d = _mlp_dims(rows, in_dim, hidden, depth, out_dim, act, _lib.MLP_WGRAD if need_w else 0)
+            ws = _bytes(lib.wmrl_mlp_workspace_bytes(C.byref(d), 1), dev)
+            gp = _mlp_ptrs(grads, depth) if need_w else _lib.MlpPtrs()
+            _native(dev, lib.wmrl_mlp_bwd_bf16, C.byref(d), ctx.packed.data_ptr(), ctx.panel.data_ptr(),
+                    ctx.saved_buf.data_ptr(), g.data_ptr(), C.byref(gp), _lib.ptr(g_x), ws.data_ptr(), ws.numel(),
+                    _stream_ptr(dev))
+        elif need_x:
+            g_x.zero_()
+        out = [None, None, None, g_x.reshape(ctx.x_shape) if need_x else None]
+        for i in range(len(ctx.param_shapes)):
+            out.append(grads[i] if need_w and ctx.needs_input_grad[4 + i] else None)
+        return tuple(out)
+
+
+def mlp_bf16_supported(seq: "torch.nn.Sequential") -> bool:
+    pat = _mlp_pattern(seq)
+    if pat is None:
+        return False
+    blocks, act, out = pat
+    d = _mlp_dims(0, blocks[0][0].in_features, blocks[0][0].out_features, len(blocks), out.out_features, act)
+    return _lib.load().wmrl_mlp_packed_bytes(C.byref(d)) > 0
+
+
+def mlp_forward_bf16(seq: "torch.nn.Sequential", x: torch.Tensor) -> torch.Tensor:
+    """The head ``seq`` applied to ``x[..., in_dim]`` on the bf16 tcgen05 chain.  Raises for module patterns or
+    widths the chain does not cover (``mlp_bf16_supported``); the fp32 route is ``mlp_forward``."""
+    pat = _mlp_pattern(seq)
+    if pat is None or not mlp_bf16_supported(seq):
+        raise RuntimeError("wmrl: this module is not a [Linear, LayerNorm, ELU|SiLU|ReLU] x depth -> Linear head with "
+                           "hidden % 32 == 0, hidden <= 512, out_dim <= 16; use precision='fp32'")
+    blocks, act, out = pat
+    params = []
+    for lin, ln in blocks:
+        params += [lin.weight, lin.bias, ln.weight, ln.bias]
+    params += [out.weight, out.bias]
+    dev = _require_cuda(x, *params)
+    in_dim, hidden = blocks[0][0].in_features, blocks[0][0].out_features
+    if x.shape[-1] != in_dim:
+        raise ValueError(f"mlp: input has {x.shape[-1]} features, the head expects {in_dim}")
+    spec = (in_dim, hidden, len(blocks), out.out_features, act)
+    d0 = _mlp_dims(x.numel() // in_dim, *spec)
+    packed = _mlp_packed(seq, params, d0)
+    x2 = _f32c(x.reshape(-1, in_dim))
+    panel = _PANELS.get(x, x2, d0)
+    return MlpBF16.apply(spec, packed, panel, x, *params)
+
+
 def mlp_forward(seq: "torch.nn.Sequential", x: torch.Tensor) -> torch.Tensor:
     """Run an ``nn.Sequential`` of the reference's head pattern - [Linear, LayerNorm, act] x depth, Linear -
     on libwmrl's kernels (3xTF32 tensor-core GEMM + fused LayerNorm/activation) when ``x`` is a CUDA fp32

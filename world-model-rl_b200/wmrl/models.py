@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .functional import mlp_forward
+from .functional import mlp_forward, mlp_forward_bf16
 
 
 def _mlp(in_dim, hidden, depth, out_dim, act, layernorm=True):
@@ -26,20 +26,23 @@ def _mlp(in_dim, hidden, depth, out_dim, act, layernorm=True):
 
 class DenseModel(nn.Module):
     def __init__(self, depth: int = 3, input_dim: int = 230, hidden_dim: int = 256, output_dim: int = 1,
-                 hidden_act=nn.SiLU, output_act=nn.Identity, use_layernorm: bool = True):
+                 hidden_act=nn.SiLU, output_act=nn.Identity, use_layernorm: bool = True, precision: str = "fp32"):
         super().__init__()
         self.fc = _mlp(input_dim, hidden_dim, depth, output_dim, hidden_act, use_layernorm)
         self.output_act = output_act()
+        self.precision = precision   # "bf16": the layer-wise tcgen05 chain (wmrl_mlp_*), fp32 in / out
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
-        return self.output_act(mlp_forward(self.fc, z))
+        run = mlp_forward_bf16 if self.precision == "bf16" else mlp_forward
+        return self.output_act(run(self.fc, z))
 
 
 class ValueCritic(nn.Module):
-    def __init__(self, state_dim, num_layers=3, hidden_dim=512):
+    def __init__(self, state_dim, num_layers=3, hidden_dim=512, precision: str = "fp32"):
         super().__init__()
         self.state_dim, self.num_layers, self.hidden_dim = state_dim, num_layers, hidden_dim
         self.layers = _mlp(state_dim, hidden_dim, num_layers, 1, nn.ReLU, True)
+        self.precision = precision
 
     def forward(self, x):
-        return mlp_forward(self.layers, x)
+        return (mlp_forward_bf16 if self.precision == "bf16" else mlp_forward)(self.layers, x)
