@@ -425,6 +425,54 @@ def aux_all_ranks(c, rssm, actor, dev, world, rank, barrier):
     return out
 
 
+def aux_actor_critic_update(c, rssm, actor, dev):
+    """The real consumer of the rollout (world_model.py:165-189 -> value_trainer.py:138-182) at the bench shape, one GPU:
+    WorldModel.imagine_rollout (rollout -> features -> reward / done models) -> ValueGradTrainer (critic, target critic,
+    lambda-return, value loss; critic step, actor BPTT, actor step), with the heads on the bf16 tcgen05 chain and on
+    the fp32 kernels.  `targets_*`: no-grad evaluation of the lambda-return targets; `update_*`: one full update."""
+    import wmrl
+    B, H, F_ = c["B"], c["H"], c["D"] + c["S"]
+    g = torch.Generator().manual_seed(77)
+    d0 = torch.tanh(torch.randn(B, c["D"], generator=g)).to(dev)
+    s0 = torch.randn(B, c["S"], generator=g).to(dev)
+    init = wmrl.InternalStateContinuous(d0, s0, s0.clone(), torch.ones_like(s0))
+    out = {"what": "WorldModel.imagine_rollout -> reward / done models -> ValueGradTrainer (critic + target critic 3x512 ReLU, "
+                   "reward / done 3x256 SiLU, lambda-return); 65536 start states x H 15; rollout bf16"}
+    mac_c = F_ * 512 + 2 * 512 * 512 + 512
+    mac_d = F_ * 256 + 2 * 256 * 256 + 256
+    out["head_flops_per_latent_step_fwd"] = 2 * (2 * mac_c + 2 * mac_d)
+    for prec in ("bf16", "fp32"):
+        torch.manual_seed(5)
+        wm = wmrl.WorldModel(torch.nn.Identity(), torch.nn.Identity(),
+                             wmrl.DenseModel(input_dim=F_, output_act=torch.nn.Sigmoid, precision=prec),
+                             wmrl.DenseModel(input_dim=F_, precision=prec), rssm).to(dev)
+        trainer = wmrl.ValueGradTrainer(actor, wmrl.ValueCritic(F_, precision=prec).to(dev))
+        trainer.target_critic.to(dev)
+
+        def targets():
+            with torch.no_grad():
+                roll = wm.imagine_rollout(init, actor, H)
+                d = wmrl.functional.done_mask(roll.dones)
+                return trainer.value_targets(trainer.target_critic(roll.features), roll.rewards, d)
+
+        def update():
+            roll = wm.imagine_rollout(init, actor, H)
+            return trainer.update(roll.features, roll.rewards, roll.dones)
+
+        try:
+            out[f"targets_{prec}_heads_ms"] = _event_ms(targets, 5)
+            out[f"update_{prec}_heads_ms"] = _event_ms(update, 3)
+        except RuntimeError as e:   # pragma: no cover
+            out[f"error_{prec}"] = str(e)[:300]
+        del wm, trainer
+        wmrl.functional.clear_panel_cache()
+        torch.cuda.empty_cache()
+    for p_ in rssm.parameters():
+        p_.requires_grad_(False)
+    actor.zero_grad(set_to_none=True)
+    return out
+
+
 def _discrete_problem(dev, B, H, D, S, C, A, precision, seed=0):
     import wmrl
     torch.manual_seed(seed)
@@ -766,6 +814,8 @@ def run_ours(args):
             line["aux"] = aux_all
         if world == 1 and not args.no_aux:
             line.setdefault("aux", {}).update(aux_configs(dev))
+            line["aux"]["actor_critic_update"] = aux_actor_critic_update(c, rssm, actor, dev)
+            torch.cuda.empty_cache()
             line["gpu_eager_baseline"] = gpu_eager_baseline(c, dev, avg_launch_s * 1e3)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -143,3 +143,67 @@ def test_large_rows_property():
         assert y.shape == (65536, 15, 1) and bool(torch.isfinite(y).all())
         sub = x[40000:40003].clone()
         torch.testing.assert_close(m(sub), y[40000:40003], rtol=0, atol=0)
+
+
+def _trainer_problem(prec, B=192, H=6):
+    import wmrl
+    torch.manual_seed(21)
+    D, S, A = 200, 30, 6
+    rssm = wmrl.ContinuousRSSM(D, D, S, 64, A, precision="bf16" if prec == "bf16" else "fp32").cuda()
+    actor = wmrl.Actor(D + S, A, num_layers=3, hidden_dim=512).cuda()
+    wm = wmrl.WorldModel(torch.nn.Identity(), torch.nn.Identity(),
+                         wmrl.DenseModel(input_dim=D + S, output_act=torch.nn.Sigmoid, precision=prec),
+                         wmrl.DenseModel(input_dim=D + S, precision=prec), rssm).cuda()
+    trainer = wmrl.ValueGradTrainer(actor, wmrl.ValueCritic(D + S, precision=prec).cuda())
+    g = torch.Generator().manual_seed(3)
+    d0 = torch.tanh(torch.randn(B, D, generator=g)).cuda()
+    s0 = torch.randn(B, S, generator=g).cuda()
+    init = wmrl.InternalStateContinuous(d0, s0, s0.clone(), torch.ones_like(s0))
+    noise = torch.randn(H, B, S, generator=g).cuda()
+    return wm, trainer, actor, init, noise, H
+
+
+def test_update_with_detached_critic_input_matches_reference_flow():
+    """wmrl.ValueGradTrainer feeds the critic detached states (skips a BPTT whose actor gradients the reference zeroes
+    unused, value_trainer.py:153-156 + utils.py:19-21): after one update every actor and critic parameter equals the
+    reference flow's (critic on the attached states), fp32 kernels."""
+    import wmrl
+    results = []
+    for attached in (False, True):
+        wm, trainer, actor, init, noise, H = _trainer_problem("fp32")
+        if attached:
+            def value_loss(state_samples, reward_samples, done_samples, tr=trainer):
+                values = tr.critic(state_samples)
+                with wmrl.FreezeParameters([tr.target_critic]):
+                    tv = tr.value_targets(tr.target_critic(state_samples), reward_samples, done_samples)
+                return (0.5 * (tv.detach() - values) ** 2).mean(), tv
+            trainer.value_loss = value_loss
+        roll = wm.imagine_rollout(init, actor, H, noise=noise)
+        losses = trainer.update(roll.features, roll.rewards, roll.dones)
+        results.append((losses, [p.detach().clone() for p in list(actor.parameters()) + list(trainer.critic.parameters())]))
+    (la, pa), (lb, pb) = results
+    assert abs(la.value_loss - lb.value_loss) <= 1e-6 * max(1.0, abs(lb.value_loss))
+    assert abs(la.actor_loss - lb.actor_loss) <= 1e-6 * max(1.0, abs(lb.actor_loss))
+    for x, y in zip(pa, pb):
+        torch.testing.assert_close(x, y, rtol=1e-4, atol=1e-6)
+
+
+def test_value_targets_bf16_heads_vs_fp32():
+    """lambda-return targets through the bf16 heads vs the fp32 heads on the same rollout (north_star: rtol 1e-2)."""
+    import wmrl
+    import wmrl.functional as Fn
+    wm, trainer, actor, init, noise, H = _trainer_problem("bf16")
+    with torch.no_grad():
+        roll = wm.imagine_rollout(init, actor, H, noise=noise)
+        d = Fn.done_mask(roll.dones)
+        t16 = trainer.value_targets(trainer.target_critic(roll.features), roll.rewards, d)
+        wmrl.set_precision(wm.reward_model, "fp32"); wmrl.set_precision(wm.done_model, "fp32")
+        wmrl.set_precision(trainer.target_critic, "fp32")
+        r32, dn32 = wm.reward_model(roll.features), wm.done_model(roll.features)
+        t32 = trainer.value_targets(trainer.target_critic(roll.features), r32, Fn.done_mask(dn32))
+    scale = float(t32.abs().max())
+    assert float((t16 - t32).abs().max()) <= 1e-2 * max(scale, 1.0)
+    wmrl.set_precision(wm, "bf16")
+    assert wm.reward_model.precision == "bf16" and wm.dynamic_model.precision == "bf16"
+    losses = trainer.update(roll.features, roll.rewards, roll.dones, critic_only=True)
+    assert losses.value_loss == losses.value_loss

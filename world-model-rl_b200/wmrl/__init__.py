@@ -2,7 +2,7 @@
 mauicv/world-model-rl (package ``reflect``).  See DESIGN.md / INTEGRATION.md."""
 from .actor import Actor
 from .memory_actor import WorldModelActor
-from .models import DenseModel, ValueCritic
+from .models import DenseModel, ValueCritic, set_precision
 from .rssm import ContinuousRSSM, DiscreteRSSM, RSSMBase
 from .state import (InternalStateContinuous, InternalStateContinuousSequence, InternalStateDiscrete,
                     InternalStateDiscreteSequence)
@@ -14,5 +14,5 @@ __all__ = [
     "Actor", "WorldModelActor", "DenseModel", "ValueCritic", "ContinuousRSSM", "DiscreteRSSM", "RSSMBase",
     "InternalStateContinuous", "InternalStateContinuousSequence", "InternalStateDiscrete",
     "InternalStateDiscreteSequence", "AdamOptim", "FreezeParameters", "ValueGradTrainer",
-    "ValueGradTrainerLosses", "ImaginedRollouts", "WorldModel", "WorldModelTrainingParams",
+    "ValueGradTrainerLosses", "ImaginedRollouts", "WorldModel", "WorldModelTrainingParams", "set_precision",
 ]

@@ -797,26 +797,38 @@ def _mlp_ptrs(params: Sequence[Optional[torch.Tensor]], depth: int) -> _lib.MlpP
 
 class _PanelCache:
     """The bf16 MMA panel of the most recent feature tensor: reward model, done model, critic and target critic all
-    read the same ``features`` object (world_model.py:178-180, value_trainer.py:121-123), which is converted once."""
+    read the same ``features`` memory (world_model.py:178-180, value_trainer.py:121-123), which is converted once.
+    The cache keeps a (detached) view of the source alive, so its address cannot be handed to another tensor while
+    the entry exists; (address, shape, version counter) then identifies the contents - ``x.detach()`` and views of
+    ``x`` hit, an in-place write misses."""
 
     def __init__(self):
-        self.ref = None
-        self.version = -1
+        self.key = None
+        self.src: Optional[torch.Tensor] = None
         self.panel: Optional[torch.Tensor] = None
 
-    def get(self, x: torch.Tensor, x2: torch.Tensor, d: _lib.MlpDims) -> torch.Tensor:
-        import weakref
-        if self.ref is not None and self.ref() is x and self.version == x._version and self.panel is not None:
+    def clear(self) -> None:
+        self.key = self.src = self.panel = None
+
+    def get(self, x2: torch.Tensor, d: _lib.MlpDims) -> torch.Tensor:
+        key = (x2.data_ptr(), tuple(x2.shape), x2._version, x2.device)
+        if self.key == key and self.panel is not None:
             return self.panel
         lib = _lib.load()
         dev = x2.device
         panel = _bytes(lib.wmrl_mlp_panel_bytes(C.byref(d)), dev)
         _native(dev, lib.wmrl_mlp_to_panel, C.byref(d), x2.data_ptr(), panel.data_ptr(), _stream_ptr(dev))
-        self.ref, self.version, self.panel = weakref.ref(x), x._version, panel
+        self.key, self.src, self.panel = key, x2, panel
         return panel
 
 
 _PANELS = _PanelCache()
+
+
+def clear_panel_cache() -> None:
+    """Drop the cached feature panel (and the reference that keeps its source tensor alive)."""
+    _PANELS.clear()
+
 _MLP_PACKED: "dict" = {}
 
 
@@ -920,7 +932,7 @@ def mlp_forward_bf16(seq: "torch.nn.Sequential", x: torch.Tensor) -> torch.Tenso
     d0 = _mlp_dims(x.numel() // in_dim, *spec)
     packed = _mlp_packed(seq, params, d0)
     x2 = _f32c(x.reshape(-1, in_dim))
-    panel = _PANELS.get(x, x2, d0)
+    panel = _PANELS.get(x2, d0)
     return MlpBF16.apply(spec, packed, panel, x, *params)
 
 

@@ -24,6 +24,24 @@ def _mlp(in_dim, hidden, depth, out_dim, act, layernorm=True):
     return nn.Sequential(*layers)
 
 
+_PRECISIONS = ("fp32", "bf16")
+
+
+def set_precision(module: nn.Module, precision: str) -> nn.Module:
+    """Switch every wmrl module under ``module`` (RSSM, DenseModel heads, ValueCritic) to ``precision``:
+    "fp32" = the reference-accurate kernels, "bf16" = the tcgen05 paths (fp32 in / out, bf16 MMA operands)."""
+    if precision not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {_PRECISIONS}")
+    for m in module.modules():
+        if hasattr(m, "set_precision") and m is not module:
+            m.set_precision(precision)
+        elif isinstance(m, (DenseModel, ValueCritic)):
+            m.precision = precision
+    if hasattr(module, "set_precision") and not isinstance(module, (DenseModel, ValueCritic)):
+        module.set_precision(precision)
+    return module
+
+
 class DenseModel(nn.Module):
     def __init__(self, depth: int = 3, input_dim: int = 230, hidden_dim: int = 256, output_dim: int = 1,
                  hidden_act=nn.SiLU, output_act=nn.Identity, use_layernorm: bool = True, precision: str = "fp32"):

@@ -64,7 +64,10 @@ class ValueGradTrainer:
         return lambda_return(target_state_values, rewards, dones, self.gamma, self.lam)
 
     def value_loss(self, state_samples, reward_samples, done_samples):
-        values = self.critic(state_samples)
+        # the critic reads DETACHED states: the reference lets the value loss back-propagate into the rollout
+        # (value_trainer.py:121, 153-156), but the actor gradients that produces are zeroed by actor_optim.backward
+        # before they are ever used (utils.py:19-21) - detaching skips a whole BPTT with identical updates
+        values = self.critic(state_samples.detach())
         with FreezeParameters([self.target_critic]):
             target_values = self.value_targets(self.target_critic(state_samples), reward_samples, done_samples)
         loss = 0.5 * (target_values.detach() - values) ** 2
