@@ -150,7 +150,7 @@ def _trainer_problem(prec, B=192, H=6):
     torch.manual_seed(21)
     D, S, A = 200, 30, 6
     rssm = wmrl.ContinuousRSSM(D, D, S, 64, A, precision="bf16" if prec == "bf16" else "fp32").cuda()
-    actor = wmrl.Actor(D + S, A, num_layers=3, hidden_dim=512).cuda()
+    actor = wmrl.Actor(D + S, A, 1.0, num_layers=3, hidden_dim=512).cuda()
     wm = wmrl.WorldModel(torch.nn.Identity(), torch.nn.Identity(),
                          wmrl.DenseModel(input_dim=D + S, output_act=torch.nn.Sigmoid, precision=prec),
                          wmrl.DenseModel(input_dim=D + S, precision=prec), rssm).cuda()
@@ -195,12 +195,16 @@ def test_value_targets_bf16_heads_vs_fp32():
     wm, trainer, actor, init, noise, H = _trainer_problem("bf16")
     with torch.no_grad():
         roll = wm.imagine_rollout(init, actor, H, noise=noise)
-        d = Fn.done_mask(roll.dones)
-        t16 = trainer.value_targets(trainer.target_critic(roll.features), roll.rewards, d)
+        v16 = trainer.target_critic(roll.features)
         wmrl.set_precision(wm.reward_model, "fp32"); wmrl.set_precision(wm.done_model, "fp32")
         wmrl.set_precision(trainer.target_critic, "fp32")
         r32, dn32 = wm.reward_model(roll.features), wm.done_model(roll.features)
-        t32 = trainer.value_targets(trainer.target_critic(roll.features), r32, Fn.done_mask(dn32))
+        # the done mask is a 0.5 threshold (value_trainer.py:148-149): both target sets use the fp32 heads' mask, the
+        # done probabilities themselves are compared directly
+        d = Fn.done_mask(dn32)
+        t16 = trainer.value_targets(v16, roll.rewards, d)
+        t32 = trainer.value_targets(trainer.target_critic(roll.features), r32, d)
+    assert float((roll.dones - dn32).abs().max()) <= 1e-2
     scale = float(t32.abs().max())
     assert float((t16 - t32).abs().max()) <= 1e-2 * max(scale, 1.0)
     wmrl.set_precision(wm, "bf16")
