@@ -244,6 +244,16 @@ WMRL_API int wmrl_kl_loss_bwd(const wmrl_dims* d, const float* pri_a, const floa
                      float* g_post_b, void* stream);
 
 /*
+ * Reward and done losses of WorldModel.update (world_model.py:130, 143-144) in one pass over the two heads' outputs:
+ * sums[0] += sum_i 0.5 (tgt_r - pred_r)^2 + 0.5 log(2 pi)  (unit-variance Normal NLL, get_norm_dist),
+ * sums[1] += sum_i binary_cross_entropy_with_logits(logit_d, tgt_d); the caller zero-fills sums and divides by the
+ * row counts.  g_pred_r / g_logit_d (either may be NULL) receive the UNSCALED gradients pred_r - tgt_r and
+ * sigmoid(logit_d) - tgt_d in the same pass.
+ */
+WMRL_API int wmrl_head_losses(const float* pred_r, const float* tgt_r, int64_t n_reward, const float* logit_d,
+                     const float* tgt_d, int64_t n_done, float* sums, float* g_pred_r, float* g_logit_d, void* stream);
+
+/*
  * lambda-return targets of ValueGradTrainer.value_loss (value_trainer.py:126-134
  * over :62-113) as one O(H) scan per row; V, r, d, out: [B][H] (the trailing
  * singleton of the reference's [B,H,1] dropped).  d is the pre-processed 0/1

@@ -53,3 +53,27 @@ def test_kl_loss_matches_torch_distributions(variant, B, T, S, C):
     for m, t in zip(mine, [t for t in (pa, pb, qa, qb) if t is not None]):
         torch.testing.assert_close(m, t.grad, rtol=2e-4, atol=1e-7)
         assert float(m[:, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,T", [(50, 50), (3, 2), (1, 7)])
+def test_head_losses_vs_torch(B, T):
+    """reward NLL + done BCE of WorldModel.update (world_model.py:130, 143-144): the fused pass vs torch.distributions /
+    F.binary_cross_entropy_with_logits, values and gradients."""
+    import torch.distributions as D
+    import torch.nn.functional as F
+    import wmrl.functional as Fn
+    g = torch.Generator().manual_seed(B * 100 + T)
+    pr = (torch.randn(B, T, 1, generator=g) * 2).cuda().requires_grad_(True)
+    tr = torch.randn(B, T, 1, generator=g).cuda()
+    ld = (torch.randn(B, T, 1, generator=g) * 4).cuda().requires_grad_(True)
+    td = (torch.rand(B, T, 1, generator=g) > 0.7).float().cuda()
+    rl, dl = Fn.head_losses(pr, tr, ld, td)
+    (10.0 * rl + 0.5 * dl).backward()
+    pr2, ld2 = pr.detach().clone().requires_grad_(True), ld.detach().clone().requires_grad_(True)
+    rl2 = -D.Independent(D.Normal(pr2, 1.0), 1).log_prob(tr).mean()
+    dl2 = F.binary_cross_entropy_with_logits(ld2, td)
+    (10.0 * rl2 + 0.5 * dl2).backward()
+    torch.testing.assert_close(rl, rl2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(dl, dl2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(pr.grad, pr2.grad, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(ld.grad, ld2.grad, rtol=1e-5, atol=1e-7)

@@ -7,6 +7,8 @@
 //   discrete:   KL(Cat(l1) || Cat(l2)) summed over the C groups (Independent(OneHotCategoricalStraightThrough, 1),
 //               state/discrete.py:77-79; the KL of one-hot categoricals is the categorical KL)
 // Index 0 of the sequences (the initial state) is excluded, as get_dist() does.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace wmrl {
@@ -96,6 +98,40 @@ __global__ void kl_kernel(const float* __restrict__ pa, const float* __restrict_
   }
 }
 
+// Reward and done losses of WorldModel.update (world_model.py:130, 143-144) in one pass over the two heads' outputs:
+//   reward: -log N(r; p, 1) = 0.5 (r - p)^2 + 0.5 log(2 pi)   (get_norm_dist: Independent(Normal(p, 1), 1))
+//   done:   binary_cross_entropy_with_logits(l, y) = max(l, 0) - l y + log(1 + exp(-|l|))
+// sums[0] += sum of reward terms, sums[1] += sum of done terms; the unscaled gradients d/dp = p - r and
+// d/dl = sigmoid(l) - y are written in the same pass (the caller scales them by the upstream gradient / count).
+__global__ void head_losses_kernel(const float* __restrict__ pr, const float* __restrict__ tr, long long nr,
+                                   const float* __restrict__ ld, const float* __restrict__ td, long long nd,
+                                   float* __restrict__ sums, float* __restrict__ g_pr, float* __restrict__ g_ld) {
+  float a = 0.f, b = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += stride) {
+    const float d = pr[i] - tr[i];
+    a += 0.5f * d * d + 0.9189385332046727f;
+    if (g_pr) g_pr[i] = d;
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += stride) {
+    const float l = ld[i], y = td[i];
+    const float e = expf(-fabsf(l));
+    b += fmaxf(l, 0.f) - l * y + log1pf(e);
+    if (g_ld) g_ld[i] = (l >= 0.f ? 1.f / (1.f + e) : e / (1.f + e)) - y;
+  }
+  a = kl_warp_sum(a); b = kl_warp_sum(b);
+  __shared__ float sa[32], sb[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sa[warp] = a; sb[warp] = b; }
+  __syncthreads();
+  if (warp == 0) {
+    a = lane < (int)(blockDim.x >> 5) ? sa[lane] : 0.f;
+    b = lane < (int)(blockDim.x >> 5) ? sb[lane] : 0.f;
+    a = kl_warp_sum(a); b = kl_warp_sum(b);
+    if (lane == 0) { atomicAdd(sums, a); atomicAdd(sums + 1, b); }
+  }
+}
+
 }  // namespace wmrl
 
 using namespace wmrl;
@@ -130,6 +166,19 @@ int wmrl_kl_loss_bwd(const wmrl_dims* d, const float* pri_a, const float* pri_b,
   const unsigned blocks = (unsigned)((rows * 32 + 255) / 256);
   if (disc) kl_kernel<true, true><<<blocks, 256, 0, (cudaStream_t)stream>>>(pri_a, nullptr, post_a, nullptr, dd.B, dd.T, dd.S, dd.C, rho, scale, nullptr, nullptr, g_pri_a, nullptr, g_post_a, nullptr);
   else kl_kernel<false, true><<<blocks, 256, 0, (cudaStream_t)stream>>>(pri_a, pri_b, post_a, post_b, dd.B, dd.T, dd.S, 1, rho, scale, nullptr, nullptr, g_pri_a, g_pri_b, g_post_a, g_post_b);
+  WMRL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int wmrl_head_losses(const float* pred_r, const float* tgt_r, int64_t n_reward, const float* logit_d, const float* tgt_d,
+                     int64_t n_done, float* sums, float* g_pred_r, float* g_logit_d, void* stream) {
+  WMRL_REQUIRE(n_reward >= 0 && n_done >= 0 && sums, "head_losses: bad arguments");
+  WMRL_REQUIRE((n_reward == 0 || (pred_r && tgt_r)) && (n_done == 0 || (logit_d && tgt_d)), "head_losses: NULL tensor");
+  const long long n = n_reward > n_done ? n_reward : n_done;
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 148 * 8);
+  head_losses_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred_r, tgt_r, n_reward, logit_d, tgt_d, n_done, sums, g_pred_r,
+                                                                g_logit_d);
   WMRL_CUDA_OK(cudaGetLastError());
   return 0;
 }

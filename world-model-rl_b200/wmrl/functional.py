@@ -626,6 +626,44 @@ def kl_loss(cfg: PathConfig, rho: float, prior_a, prior_b, post_a, post_b):
     return KLLoss.apply(cfg, float(rho), prior_a, prior_b, post_a, post_b)
 
 
+class HeadLosses(torch.autograd.Function):
+    """(reward NLL, done BCE-with-logits) of WorldModel.update (world_model.py:130, 143-144), values and both
+    gradients in ONE pass (wmrl_head_losses).  reward loss = mean over rows of the summed unit-variance Normal NLL
+    over the last dim; done loss = mean over all elements."""
+
+    @staticmethod
+    def forward(ctx, pred_r, tgt_r, logit_d, tgt_d):
+        lib = _lib.load()
+        dev = _require_cuda(pred_r, logit_d)
+        pr, tr = _f32c(pred_r), _f32c(tgt_r.expand_as(pred_r))
+        ld, td = _f32c(logit_d), _f32c(tgt_d.expand_as(logit_d))
+        sums = torch.zeros(2, device=dev)
+        need = pred_r.requires_grad or logit_d.requires_grad
+        g_pr = torch.empty_like(pr) if need else None
+        g_ld = torch.empty_like(ld) if need else None
+        _native(dev, lib.wmrl_head_losses, pr.data_ptr(), tr.data_ptr(), pr.numel(), ld.data_ptr(), td.data_ptr(),
+                ld.numel(), sums.data_ptr(), _lib.ptr(g_pr), _lib.ptr(g_ld), _stream_ptr(dev))
+        rows_r = max(pr.numel() // max(pr.shape[-1], 1), 1)
+        n_d = max(ld.numel(), 1)
+        ctx.rows_r, ctx.n_d = rows_r, n_d
+        ctx.shapes = (pred_r.shape, logit_d.shape)
+        if need:
+            ctx.save_for_backward(g_pr, g_ld)
+        return sums[0] / rows_r, sums[1] / n_d
+
+    @staticmethod
+    def backward(ctx, g_r, g_d):
+        g_pr, g_ld = ctx.saved_tensors
+        out_r = (g_pr * (g_r / ctx.rows_r)).reshape(ctx.shapes[0]) if ctx.needs_input_grad[0] else None
+        out_d = (g_ld * (g_d / ctx.n_d)).reshape(ctx.shapes[1]) if ctx.needs_input_grad[2] else None
+        return out_r, None, out_d, None
+
+
+def head_losses(pred_reward, reward, done_logits, done):
+    """-> (reward_loss, done_loss) as WorldModel.update computes them (world_model.py:143-144)."""
+    return HeadLosses.apply(pred_reward, reward, done_logits, done)
+
+
 def done_mask(dones: torch.Tensor) -> torch.Tensor:
     """shift right, threshold at 0.5, running max (value_trainer.py:148-149)."""
     lib = _lib.load()

@@ -114,8 +114,14 @@ class WorldModel(nn.Module):
         p = self.params
         feats = posterior_state_sequence.get_features()
         kl_clamped, kl_mean = self._kl_terms(prior_state_sequence, posterior_state_sequence, p.rho)
-        reward_loss = _unit_normal_nll(self.reward_model(feats), reward[:, 1:], 1)
-        done_loss = F.binary_cross_entropy_with_logits(self.done_model(feats), done[:, 1:].float())
+        pred_r, pred_d = self.reward_model(feats), self.done_model(feats)
+        if pred_r.is_cuda and pred_r.dtype == torch.float32 and pred_r.shape == reward[:, 1:].shape \
+                and pred_d.shape == done[:, 1:].shape:
+            from .functional import head_losses      # both losses and their gradients in one fused pass
+            reward_loss, done_loss = head_losses(pred_r, reward[:, 1:], pred_d, done[:, 1:].float())
+        else:
+            reward_loss = _unit_normal_nll(pred_r, reward[:, 1:], 1)
+            done_loss = F.binary_cross_entropy_with_logits(pred_d, done[:, 1:].float())
         decoded = self.decoder(feats)
         tgt = obs[:, 1:]
         # the reference flattens [B,T] and treats the remaining dims beyond the first as the event
