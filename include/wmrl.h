@@ -244,6 +244,22 @@ WMRL_API int wmrl_kl_loss_bwd(const wmrl_dims* d, const float* pri_a, const floa
                      float* g_post_b, void* stream);
 
 /*
+ * One online acting step of the stateful policy (rssm_world_model/memory_actor.py:34-57) as ONE kernel, fp32:
+ *   post = posterior(obs_embed, state) (rssm.py:70-82), action = actor([h | s_post], deterministic) (actor.py:47-52),
+ *   state' = prior(action, post) (rssm.py:53-68).
+ * d.B rows (B = 1 in the reference; one 8-CTA cluster per row), d.T ignored.  obs_embed [B][E], deter [B][D] (the
+ * carried state's deterministic part: its stochastic part is not read by the posterior), noise_post / noise_prior
+ * [B][S] N(0,1) draws (continuous) or [B][C][S] Exp(1) draws (discrete).  Outputs: action [B][A]; the posterior
+ * state's sample [B][S_in] and distribution (dist_a = mean | logits, dist_b = std | NULL); the next carried state:
+ * deter_next [B][D], prior sample and distribution.  Every output is read as rows of stride ld_out floats (>= its
+ * width), so a caller may hand slices of ONE allocation.
+ */
+WMRL_API int wmrl_act_step(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
+                  const float* obs_embed, const float* deter, const float* noise_post, const float* noise_prior,
+                  float* action, float* post_stoch, float* post_dist_a, float* post_dist_b, float* deter_next,
+                  float* prior_stoch, float* prior_dist_a, float* prior_dist_b, int64_t ld_out, void* stream);
+
+/*
  * Reward and done losses of WorldModel.update (world_model.py:130, 143-144) in one pass over the two heads' outputs:
  * sums[0] += sum_i 0.5 (tgt_r - pred_r)^2 + 0.5 log(2 pi)  (unit-variance Normal NLL, get_norm_dist),
  * sums[1] += sum_i binary_cross_entropy_with_logits(logit_d, tgt_d); the caller zero-fills sums and divides by the

@@ -185,6 +185,23 @@ def posterior_out(w: Weights, deter: torch.Tensor, obs_embed: torch.Tensor, emu:
     return _lin(hid, w["state_posterior.2.weight"], w["state_posterior.2.bias"], emu)
 
 
+def act_step(variant: str, w: Weights, aw: Weights, obs_embed: torch.Tensor, deter: torch.Tensor, noise_post: torch.Tensor,
+             noise_prior: torch.Tensor, S: int, C: int = 1, action_scale: float = 5.0, bound=None):
+    """One online acting step of WorldModelActor.__call__ (memory_actor.py:51-56) with the two latent draws passed
+    in: post = posterior(e, state) (rssm.py:70-82), a = actor(post.features, deterministic) (actor.py:47-52),
+    next = prior(a, post) (rssm.py:53-68).  -> dict of action, post_* and next-state tensors."""
+    bound = torch.ones(1) if bound is None else bound
+    gen = (lambda o, n: gen_stoch_continuous(o, S, n)) if variant == "continuous" \
+        else (lambda o, n: gen_stoch_discrete(o, C, S, n))
+    out_q = posterior_out(w, deter, obs_embed)
+    post_s, post_a, post_b = gen(out_q, noise_post)
+    action = actor_mu(aw, torch.cat([deter, post_s], dim=-1), action_scale, bound)
+    h, out_p = prior_deter(w, post_s, action, deter)
+    pri_s, pri_a, pri_b = gen(out_p, noise_prior)
+    return {"action": action, "post_stoch": post_s, "post_a": post_a, "post_b": post_b, "deter_next": h,
+            "prior_stoch": pri_s, "prior_a": pri_a, "prior_b": pri_b}
+
+
 # --------------------------------------------------------------------------
 # Rollouts
 # --------------------------------------------------------------------------

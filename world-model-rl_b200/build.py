@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "wmrl", "libwmrl.so")
 STAMP = OUT + ".stamp"
-SOURCES = ["api.cu", "f32_path.cu", "tf32_gemm.cu", "tc_imagine.cu", "tc_bptt.cu", "tc_layer.cu", "losses.cu"]
+SOURCES = ["api.cu", "f32_path.cu", "tf32_gemm.cu", "tc_imagine.cu", "tc_bptt.cu", "tc_layer.cu", "losses.cu", "act_step.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared",

@@ -626,6 +626,56 @@ def kl_loss(cfg: PathConfig, rho: float, prior_a, prior_b, post_a, post_b):
     return KLLoss.apply(cfg, float(rho), prior_a, prior_b, post_a, post_b)
 
 
+_ACT_PTRS: "dict" = {}
+
+
+def act_step(cfg: PathConfig, rssm_p: Sequence[torch.Tensor], actor_p: Sequence[torch.Tensor], bound: torch.Tensor,
+             obs_embed: torch.Tensor, deter: torch.Tensor, noise_post: torch.Tensor, noise_prior: torch.Tensor):
+    """One online acting step (memory_actor.py:34-57: posterior -> deterministic actor -> prior) as ONE cluster kernel
+    (wmrl_act_step), fp32, no gradients.  -> (action, post_stoch, post_a, post_b, deter_next, prior_stoch, prior_a,
+    prior_b); the *_b tensors are None for the discrete variant."""
+    lib = _lib.load()
+    dev = deter.device
+    if not (deter.is_cuda and obs_embed.is_cuda and rssm_p[0].is_cuda and actor_p[0].is_cuda):
+        _require_cuda(obs_embed, deter, *rssm_p, *actor_p)
+    B = deter.shape[0]
+    disc = cfg.variant == _lib.DISCRETE
+    S_in, W = cfg.S_in, cfg.dist_width
+    fast = lambda t: t if (t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad) else _f32c(t)  # noqa: E731
+    e, h = fast(obs_embed), fast(deter)
+    if e.shape != (B, cfg.E) or h.shape != (B, cfg.D):
+        raise ValueError(f"act_step: obs_embed {tuple(e.shape)} / deter {tuple(h.shape)} do not match E={cfg.E}, D={cfg.D}")
+    n1, n2 = fast(noise_post), fast(noise_prior)
+    nlat = S_in if disc else cfg.S
+    if n1.numel() != B * nlat or n2.numel() != B * nlat:
+        raise ValueError("act_step: noise tensors must hold one draw per latent element")
+    # one allocation for all outputs (the step is host-latency-bound at B = 1)
+    widths = [cfg.A, S_in, W, cfg.D, S_in, W] + ([] if disc else [W, W])
+    flat = torch.empty(B, sum(widths), device=dev)
+    parts, o = [], 0
+    for wd in widths:
+        parts.append(flat[:, o:o + wd])
+        o += wd
+    action, post_s, post_a, deter_n, pri_s, pri_a = parts[:6]
+    post_b, pri_b = (None, None) if disc else (parts[6], parts[7])
+    d = cfg.dims(B, 1, 0, _lib.FP32)
+    # the pointer structs are cached per parameter set
+    key = (cfg.La, bound.data_ptr()) + tuple(p.data_ptr() for p in rssm_p) + tuple(p.data_ptr() for p in actor_p)
+    ent = _ACT_PTRS.get(key)
+    if ent is None:
+        keep = [_f32c(p) for p in rssm_p], [_f32c(p) for p in actor_p]
+        if len(_ACT_PTRS) > 16:
+            _ACT_PTRS.clear()
+        ent = _ACT_PTRS[key] = (_rssm_ptrs(keep[0]), _actor_ptrs(keep[1], cfg.La, bound), keep)
+    w, aw = ent[0], ent[1]
+    if B > 0:
+        ld = flat.shape[1]
+        _native(dev, lib.wmrl_act_step, C.byref(d), C.byref(w), C.byref(aw), e.data_ptr(), h.data_ptr(), n1.data_ptr(),
+                n2.data_ptr(), action.data_ptr(), post_s.data_ptr(), post_a.data_ptr(), _lib.ptr(post_b),
+                deter_n.data_ptr(), pri_s.data_ptr(), pri_a.data_ptr(), _lib.ptr(pri_b), ld, _stream_ptr(dev))
+    return action, post_s, post_a, post_b, deter_n, pri_s, pri_a, pri_b
+
+
 class HeadLosses(torch.autograd.Function):
     """(reward NLL, done BCE-with-logits) of WorldModel.update (world_model.py:130, 143-144), values and both
     gradients in ONE pass (wmrl_head_losses).  reward loss = mean over rows of the summed unit-variance Normal NLL

@@ -1,5 +1,6 @@
 """Stateful online policy (rssm_world_model/memory_actor.py:8-57): encoder ->
-posterior -> actor -> prior at B=1, through the eager single-step RSSM API."""
+posterior -> actor -> prior at B=1.  On CUDA the three RSSM / actor stages are one native cluster kernel
+(``RSSMBase.act_step`` -> wmrl_act_step); CPU modules use the eager single-step API."""
 from __future__ import annotations
 
 import copy
@@ -37,7 +38,11 @@ class WorldModelActor:
         rssm = self.world_model.dynamic_model
         with FreezeParameters([self.world_model, self.actor, self.actor_copy]):
             embed = self.world_model.encoder(obs.to(device))
-            post = rssm.posterior(embed[:, 0], self.state)
-            self.action = self.actor(post.get_features(), deterministic=True)
-            self.state = rssm.prior(self.action, post)
+            if embed.is_cuda and embed.dtype == torch.float32 and hasattr(rssm, "act_step"):
+                # posterior -> actor -> prior as ONE cluster kernel (wmrl_act_step) instead of ~45 launches
+                self.action, self.state, _ = rssm.act_step(embed[:, 0], self.state, self.actor)
+            else:
+                post = rssm.posterior(embed[:, 0], self.state)
+                self.action = self.actor(post.get_features(), deterministic=True)
+                self.state = rssm.prior(self.action, post)
         return self.action

@@ -98,6 +98,11 @@ def _actor_bound(actor: nn.Module, A: int, device) -> torch.Tensor:
     return b
 
 
+import operator as _operator
+
+_RSSM_GETTER = _operator.attrgetter(*[_lib.RSSM_KEYS[f] for f in _lib.RSSM_FIELDS])
+
+
 class RSSMBase(nn.Module):
     """Owns the weights of rssm.py:14-42 under identical names."""
 
@@ -140,8 +145,7 @@ class RSSMBase(nn.Module):
         return self.stoch_size * (self.num_groups if self.variant == _lib.DISCRETE else 1)
 
     def _rssm_tensors(self):
-        sd = dict(self.named_parameters())
-        return [sd[_lib.RSSM_KEYS[f]] for f in _lib.RSSM_FIELDS]
+        return list(_RSSM_GETTER(self))
 
     def _config(self, action_size: int, Ha: int = 0, La: int = 0, action_scale: float = 5.0) -> PathConfig:
         return PathConfig(variant=self.variant, D=self.deter_size, S=self.stoch_size, C=self.num_groups,
@@ -173,6 +177,37 @@ class RSSMBase(nn.Module):
     def observe_step(self, obs_embed, action_emb, state):
         prior_state = self.prior(action_emb, state)
         return prior_state, self.posterior(obs_embed, prior_state)
+
+    def act_step(self, obs_embed: torch.Tensor, state, actor: nn.Module, *, noise_post: Optional[torch.Tensor] = None,
+                 noise_prior: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None):
+        """The online acting step of WorldModelActor.__call__ (memory_actor.py:51-56) as ONE native kernel:
+        ``post = posterior(obs_embed, state)``, ``action = actor(post.get_features(), deterministic=True)``,
+        ``next_state = prior(action, post)``  ->  (action, next_state, post).  fp32, no gradients; the two latent draws
+        are made here (N(0,1) / Exp(1), as generate_stoch_state does) unless passed in."""
+        from .functional import act_step as _act_step
+        device = next(actor.parameters()).device
+        La, Ha, actor_p = _actor_tensors(actor)
+        A = actor.mu.weight.shape[0]
+        cfg = self._config(A, Ha, La, getattr(actor, "action_scale", 5.0))
+        deter = state.deter_state.to(device)
+        B = deter.shape[0]
+        if noise_post is None or noise_prior is None:
+            both = self.draw_imagine_noise(2, B, device, generator)     # one launch for both draws
+            noise_post = both[0] if noise_post is None else noise_post
+            noise_prior = both[1] if noise_prior is None else noise_prior
+        bound = _actor_bound(actor, A, device)
+        with torch.no_grad():
+            out = _act_step(cfg, self._rssm_tensors(), actor_p, bound, obs_embed if obs_embed.device == device else obs_embed.to(device),
+                            deter, noise_post, noise_prior)
+        action, post_s, post_a, post_b, deter_n, pri_s, pri_a, pri_b = out
+        if self.variant == _lib.DISCRETE:
+            shp = (B, self.num_groups, self.stoch_size)
+            post = InternalStateDiscrete(deter_state=deter, stoch_state=post_s, logits=post_a.reshape(shp))
+            nxt = InternalStateDiscrete(deter_state=deter_n, stoch_state=pri_s, logits=pri_a.reshape(shp))
+        else:
+            post = InternalStateContinuous(deter_state=deter, stoch_state=post_s, mean=post_a, std=post_b)
+            nxt = InternalStateContinuous(deter_state=deter_n, stoch_state=pri_s, mean=pri_a, std=pri_b)
+        return action, nxt, post
 
     # ------------------------------------------------------------ noise helpers
     def draw_imagine_noise(self, n_steps: int, batch: int, device, generator: Optional[torch.Generator] = None):
