@@ -252,12 +252,25 @@ WMRL_API int wmrl_kl_loss_bwd(const wmrl_dims* d, const float* pri_a, const floa
  * [B][S] N(0,1) draws (continuous) or [B][C][S] Exp(1) draws (discrete).  Outputs: action [B][A]; the posterior
  * state's sample [B][S_in] and distribution (dist_a = mean | logits, dist_b = std | NULL); the next carried state:
  * deter_next [B][D], prior sample and distribution.  Every output is read as rows of stride ld_out floats (>= its
- * width), so a caller may hand slices of ONE allocation.
+ * width), so a caller may hand slices of ONE allocation.  The posterior sample is drawn before the action, the
+ * prior sample after it, as in the reference.
  */
+/* Optional action sampling of the step (the Normal head, actor.py:54-59, with the rsample / clamp / entropy of its
+ * use-site): std = sigmoid(stddev(hid)) + 0.01, action = clamp(mean + std * noise_action, -bound, bound),
+ * entropy = sum_j 0.5 + 0.5 log(2 pi) + log std_j.  sampling == NULL or std_w == NULL: deterministic action. */
+typedef struct wmrl_act_sampling {
+  const float* std_w;          /* stddev.weight [A][Ha] */
+  const float* std_b;          /* stddev.bias   [A]     */
+  const float* noise_action;   /* [B][A] N(0,1) draws   */
+  float* act_mean;             /* [B][A] (row stride ld_out): tanh-squashed mean */
+  float* act_std;              /* [B][A] (row stride ld_out) */
+  float* entropy;              /* [B], may be NULL */
+} wmrl_act_sampling;
 WMRL_API int wmrl_act_step(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
                   const float* obs_embed, const float* deter, const float* noise_post, const float* noise_prior,
                   float* action, float* post_stoch, float* post_dist_a, float* post_dist_b, float* deter_next,
-                  float* prior_stoch, float* prior_dist_a, float* prior_dist_b, int64_t ld_out, void* stream);
+                  float* prior_stoch, float* prior_dist_a, float* prior_dist_b, int64_t ld_out,
+                  const wmrl_act_sampling* sampling, void* stream);
 
 /*
  * Reward and done losses of WorldModel.update (world_model.py:130, 143-144) in one pass over the two heads' outputs:

@@ -83,3 +83,37 @@ def test_world_model_actor_uses_the_kernel():
     a1, n1, _ = rssm.act_step(e, st, actor, generator=g1)
     a2, n2, _ = rssm.act_step(e, st, actor, generator=g2)
     assert torch.equal(a1, a2) and torch.equal(n1.stoch_state, n2.stoch_state)
+
+
+@pytest.mark.parametrize("variant,D,S,C,Hd,E,A,Ha,La,B", [CASES[1], CASES[3]])
+def test_act_step_sampled_action(variant, D, S, C, Hd, E, A, Ha, La, B):
+    """in-kernel action sampling (actor.py:54-59 + rsample / clamp / entropy): mean, std, entropy and the clamped
+    sample against torch.distributions on the oracle's actor_dist; the sampled action feeds the prior."""
+    import torch.distributions as TD
+    import helpers_gpu as HG
+    from oracle import rssm_oracle as O
+    bound = [0.3 + 0.1 * i for i in range(A)]
+    rssm, actor = HG.build_modules(variant, D, S, C, Hd, E, A, Ha, La, bound=bound, seed=8)
+    w, aw = HG.cpu_weights(rssm), HG.cpu_weights(actor)
+    g = torch.Generator().manual_seed(12)
+    deter = torch.tanh(torch.randn(B, D, generator=g))
+    state = HG.init_state(rssm, deter, torch.zeros(B, S * (C if variant == "discrete" else 1)))
+    e = torch.randn(B, E, generator=g)
+    if variant == "continuous":
+        n1, n2 = torch.randn(B, S, generator=g), torch.randn(B, S, generator=g)
+    else:
+        n1, n2 = (torch.empty(B, C, S).exponential_(1.0, generator=g) for _ in range(2))
+    na = torch.randn(B, A, generator=g) * 2.0
+    action, nxt, post, (mean, std, ent) = rssm.act_step(e.cuda(), state, actor, noise_post=n1.cuda(), noise_prior=n2.cuda(),
+                                                         deterministic=False, noise_action=na.cuda())
+    bt = torch.tensor(bound)
+    ref = O.act_step(variant, w, aw, e, deter, n1, n2, S, C, actor.action_scale, bt)
+    mu_r, std_r = O.actor_dist(aw, torch.cat([deter, ref["post_stoch"].detach()], -1), actor.action_scale, bt)
+    torch.testing.assert_close(mean.cpu(), mu_r, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(std.cpu(), std_r, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(ent.cpu(), TD.Independent(TD.Normal(mu_r, std_r), 1).entropy(), rtol=1e-4, atol=1e-5)
+    a_ref = torch.max(torch.min(mu_r + std_r * na, bt), -bt)
+    torch.testing.assert_close(action.cpu(), a_ref, rtol=1e-4, atol=1e-5)
+    assert bool((action.cpu().abs() <= bt + 1e-6).all()) and bool((action.cpu().abs() == bt).any())   # the clamp is active
+    h_ref, _ = O.prior_deter(w, ref["post_stoch"].detach(), a_ref, deter)
+    torch.testing.assert_close(nxt.deter_state.cpu(), h_ref, rtol=1e-4, atol=1e-5)

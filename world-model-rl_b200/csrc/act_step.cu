@@ -27,6 +27,7 @@ struct ActArgs {
   const float* obs_embed; const float* deter; const float* noise_post; const float* noise_pri;
   float* action; float* post_stoch; float* post_a; float* post_b;
   float* deter_next; float* pri_stoch; float* pri_a; float* pri_b;
+  wmrl_act_sampling smp;   // std_w == NULL: deterministic action
   int variant, B, D, S, C, A, Hd, E, Ha, La, S_in, P, F;
   float inv_action_scale;
   long long ldo;   // row stride (floats) of every output tensor
@@ -234,17 +235,48 @@ __global__ void __launch_bounds__(kActThreads, 1) act_step_kernel(const __grid_c
     cur = (cur == p.o_y0) ? p.o_y1 : p.o_y0;
   }
   {
-    // mu head + tanh squash -> action (every CTA's [s | a] buffer; global by rank 0)
+    // mu head + tanh squash -> action (every CTA's [s | a] buffer; global by the computing warp).  With the sampling
+    // block (actor.py:54-59 and its use-site: rsample, clamp to the bound, entropy) warps A..2A-1 evaluate the stddev
+    // head; the pair (mu_j, std_j) meets in the warp that owns mu_j through this CTA's own scratch copy.
     const float* x = c.smem + in_off;
-    for (int j = c.gwarp; j < p.A; j += kActCluster * kActWarps) {
+    const bool smp = p.smp.std_w != nullptr;
+    const int nwarp = kActCluster * kActWarps;
+    if (smp) {
+      // std_j first, broadcast into every CTA's scratch (o_out is free here), then one barrier
+      for (int j = c.gwarp; j < p.A; j += nwarp) {
+        const float* rows[1] = {p.smp.std_w + (size_t)j * p.Ha};
+        float acc[1];
+        warp_dots<1>(rows, x, p.Ha, acc);
+        if (c.lane == 0) {
+          const float z = acc[0] + __ldg(p.smp.std_b + j);
+          bcast_store(c, p.o_out + j, 1.f / (1.f + expf(-z)) + 0.01f);
+        }
+      }
+      c.cluster.sync();
+    }
+    for (int j = c.gwarp; j < p.A; j += nwarp) {
       const float* rows[1] = {aw.mu_w + (size_t)j * p.Ha};
       float acc[1];
       warp_dots<1>(rows, x, p.Ha, acc);
       if (c.lane == 0) {
-        const float a = tanhf((acc[0] + __ldg(aw.mu_b + j)) * p.inv_action_scale) * __ldg(aw.bound + j);
+        const float bd = __ldg(aw.bound + j);
+        float a = tanhf((acc[0] + __ldg(aw.mu_b + j)) * p.inv_action_scale) * bd;
+        if (smp) {
+          const float sd = c.smem[p.o_out + j];
+          p.smp.act_mean[row * p.ldo + j] = a;
+          p.smp.act_std[row * p.ldo + j] = sd;
+          a = fmaxf(fminf(a + sd * __ldg(p.smp.noise_action + (size_t)row * p.A + j), bd), -bd);
+        }
         bcast_store(c, p.o_sa + p.S_in + j, a);
         p.action[row * p.ldo + j] = a;
       }
+    }
+    if (smp && c.gwarp == 0 && p.smp.entropy) {
+      // H = sum_j 0.5 + 0.5 log(2 pi) + log std_j  (Independent(Normal, 1).entropy())
+      float h = 0.f;
+      for (int j = c.lane; j < p.A; j += 32) h += 1.4189385332046727f + logf(c.smem[p.o_out + j]);
+      h = act_warp_sum(h);
+      if (c.lane == 0) p.smp.entropy[row] = h;
     }
   }
   c.cluster.sync();
@@ -290,7 +322,7 @@ extern "C" {
 int wmrl_act_step(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_actor_params* aw, const float* obs_embed,
                   const float* deter, const float* noise_post, const float* noise_prior, float* action,
                   float* post_stoch, float* post_dist_a, float* post_dist_b, float* deter_next, float* prior_stoch,
-                  float* prior_dist_a, float* prior_dist_b, int64_t ld_out, void* stream) {
+                  float* prior_dist_a, float* prior_dist_b, int64_t ld_out, const wmrl_act_sampling* sampling, void* stream) {
   if (int r = check_dims(d, 0)) return r;
   WMRL_REQUIRE(w && aw, "act_step: NULL weights");
   Dims dd(*d);
@@ -311,6 +343,11 @@ int wmrl_act_step(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_acto
   a.Ha = dd.Ha; a.La = dd.La; a.S_in = dd.S_in; a.P = dd.P; a.F = dd.F;
   a.inv_action_scale = 1.f / dd.action_scale;
   a.ldo = ld_out;
+  if (sampling && sampling->std_w) {
+    WMRL_REQUIRE(sampling->std_b && sampling->noise_action && sampling->act_mean && sampling->act_std, "act_step: incomplete sampling block");
+    WMRL_REQUIRE(dd.A <= dd.P, "act_step: sampling needs A <= P (scratch)");
+    a.smp = *sampling;
+  }
   auto al4 = [](int x) { return (x + 3) / 4 * 4; };
   int o = 0;
   a.o_he = o; o += al4(dd.D + dd.E);

@@ -74,6 +74,11 @@ class MlpPtrs(C.Structure):
                 ("out_w", _f32p), ("out_b", _f32p)]
 
 
+class ActSampling(C.Structure):
+    """wmrl_act_sampling"""
+    _fields_ = [(n, _f32p) for n in ("std_w", "std_b", "noise_action", "act_mean", "act_std", "entropy")]
+
+
 # every symbol include/wmrl.h declares, with its ctypes signature
 _P = C.c_void_p
 _SIGNATURES = {
@@ -99,7 +104,7 @@ _SIGNATURES = {
                          [C.POINTER(RssmPtrs), _P, _P, _P, C.c_size_t, _P]),
     "wmrl_kl_loss_fwd": (C.c_int, [C.POINTER(Dims), _P, _P, _P, _P, C.c_float, _P, _P, _P]),
     "wmrl_kl_loss_bwd": (C.c_int, [C.POINTER(Dims), _P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
-    "wmrl_act_step": (C.c_int, [C.POINTER(Dims), C.POINTER(RssmPtrs), C.POINTER(ActorPtrs)] + [_P] * 12 + [C.c_int64, _P]),
+    "wmrl_act_step": (C.c_int, [C.POINTER(Dims), C.POINTER(RssmPtrs), C.POINTER(ActorPtrs)] + [_P] * 12 + [C.c_int64, C.POINTER(ActSampling), _P]),
     "wmrl_head_losses": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "wmrl_lambda_return_fwd": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P]),
     "wmrl_lambda_return_bwd": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),

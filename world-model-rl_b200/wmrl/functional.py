@@ -630,10 +630,13 @@ _ACT_PTRS: "dict" = {}
 
 
 def act_step(cfg: PathConfig, rssm_p: Sequence[torch.Tensor], actor_p: Sequence[torch.Tensor], bound: torch.Tensor,
-             obs_embed: torch.Tensor, deter: torch.Tensor, noise_post: torch.Tensor, noise_prior: torch.Tensor):
+             obs_embed: torch.Tensor, deter: torch.Tensor, noise_post: torch.Tensor, noise_prior: torch.Tensor,
+             sampling: Optional[tuple] = None):
     """One online acting step (memory_actor.py:34-57: posterior -> deterministic actor -> prior) as ONE cluster kernel
     (wmrl_act_step), fp32, no gradients.  -> (action, post_stoch, post_a, post_b, deter_next, prior_stoch, prior_a,
-    prior_b); the *_b tensors are None for the discrete variant."""
+    prior_b); the *_b tensors are None for the discrete variant.  ``sampling`` = (stddev.weight, stddev.bias,
+    noise_action[B,A]) switches the action to clamp(mean + std * noise, +-bound) (actor.py:54-59) and appends
+    (act_mean, act_std, entropy) to the result."""
     lib = _lib.load()
     dev = deter.device
     if not (deter.is_cuda and obs_embed.is_cuda and rssm_p[0].is_cuda and actor_p[0].is_cuda):
@@ -650,7 +653,7 @@ def act_step(cfg: PathConfig, rssm_p: Sequence[torch.Tensor], actor_p: Sequence[
     if n1.numel() != B * nlat or n2.numel() != B * nlat:
         raise ValueError("act_step: noise tensors must hold one draw per latent element")
     # one allocation for all outputs (the step is host-latency-bound at B = 1)
-    widths = [cfg.A, S_in, W, cfg.D, S_in, W] + ([] if disc else [W, W])
+    widths = [cfg.A, S_in, W, cfg.D, S_in, W] + ([] if disc else [W, W]) + ([cfg.A, cfg.A, 1] if sampling else [])
     flat = torch.empty(B, sum(widths), device=dev)
     parts, o = [], 0
     for wd in widths:
@@ -668,11 +671,22 @@ def act_step(cfg: PathConfig, rssm_p: Sequence[torch.Tensor], actor_p: Sequence[
             _ACT_PTRS.clear()
         ent = _ACT_PTRS[key] = (_rssm_ptrs(keep[0]), _actor_ptrs(keep[1], cfg.La, bound), keep)
     w, aw = ent[0], ent[1]
+    smp = ent = None
+    if sampling:
+        sw, sb, na = (fast(t) for t in sampling)
+        if sw.shape != (cfg.A, cfg.Ha) or na.numel() != B * cfg.A:
+            raise ValueError("act_step: sampling = (stddev.weight [A,Ha], stddev.bias [A], noise_action [B,A])")
+        ent = torch.empty(B, device=dev)
+        smp = _lib.ActSampling(std_w=sw.data_ptr(), std_b=sb.data_ptr(), noise_action=na.data_ptr(),
+                               act_mean=parts[-3].data_ptr(), act_std=parts[-2].data_ptr(), entropy=ent.data_ptr())
     if B > 0:
         ld = flat.shape[1]
         _native(dev, lib.wmrl_act_step, C.byref(d), C.byref(w), C.byref(aw), e.data_ptr(), h.data_ptr(), n1.data_ptr(),
                 n2.data_ptr(), action.data_ptr(), post_s.data_ptr(), post_a.data_ptr(), _lib.ptr(post_b),
-                deter_n.data_ptr(), pri_s.data_ptr(), pri_a.data_ptr(), _lib.ptr(pri_b), ld, _stream_ptr(dev))
+                deter_n.data_ptr(), pri_s.data_ptr(), pri_a.data_ptr(), _lib.ptr(pri_b), ld,
+                C.byref(smp) if smp is not None else None, _stream_ptr(dev))
+    if sampling:
+        return action, post_s, post_a, post_b, deter_n, pri_s, pri_a, pri_b, parts[-3], parts[-2], ent
     return action, post_s, post_a, post_b, deter_n, pri_s, pri_a, pri_b
 
 

@@ -179,11 +179,14 @@ class RSSMBase(nn.Module):
         return prior_state, self.posterior(obs_embed, prior_state)
 
     def act_step(self, obs_embed: torch.Tensor, state, actor: nn.Module, *, noise_post: Optional[torch.Tensor] = None,
-                 noise_prior: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None):
+                 noise_prior: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None,
+                 deterministic: bool = True, noise_action: Optional[torch.Tensor] = None):
         """The online acting step of WorldModelActor.__call__ (memory_actor.py:51-56) as ONE native kernel:
         ``post = posterior(obs_embed, state)``, ``action = actor(post.get_features(), deterministic=True)``,
         ``next_state = prior(action, post)``  ->  (action, next_state, post).  fp32, no gradients; the two latent draws
-        are made here (N(0,1) / Exp(1), as generate_stoch_state does) unless passed in."""
+        are made here (N(0,1) / Exp(1), as generate_stoch_state does) unless passed in.  ``deterministic=False`` samples
+        the action in the kernel from the actor's Normal head (actor.py:54-59: clamp(mean + std * eps, +-bound)) and
+        returns (action, next_state, post, (act_mean, act_std, entropy))."""
         from .functional import act_step as _act_step
         device = next(actor.parameters()).device
         La, Ha, actor_p = _actor_tensors(actor)
@@ -196,10 +199,15 @@ class RSSMBase(nn.Module):
             noise_post = both[0] if noise_post is None else noise_post
             noise_prior = both[1] if noise_prior is None else noise_prior
         bound = _actor_bound(actor, A, device)
+        sampling = None
+        if not deterministic:
+            if noise_action is None:
+                noise_action = torch.randn(B, A, device=device, generator=generator)
+            sampling = (actor.stddev.weight, actor.stddev.bias, noise_action)
         with torch.no_grad():
             out = _act_step(cfg, self._rssm_tensors(), actor_p, bound, obs_embed if obs_embed.device == device else obs_embed.to(device),
-                            deter, noise_post, noise_prior)
-        action, post_s, post_a, post_b, deter_n, pri_s, pri_a, pri_b = out
+                            deter, noise_post, noise_prior, sampling)
+        action, post_s, post_a, post_b, deter_n, pri_s, pri_a, pri_b = out[:8]
         if self.variant == _lib.DISCRETE:
             shp = (B, self.num_groups, self.stoch_size)
             post = InternalStateDiscrete(deter_state=deter, stoch_state=post_s, logits=post_a.reshape(shp))
@@ -207,6 +215,8 @@ class RSSMBase(nn.Module):
         else:
             post = InternalStateContinuous(deter_state=deter, stoch_state=post_s, mean=post_a, std=post_b)
             nxt = InternalStateContinuous(deter_state=deter_n, stoch_state=pri_s, mean=pri_a, std=pri_b)
+        if not deterministic:
+            return action, nxt, post, tuple(out[8:])
         return action, nxt, post
 
     # ------------------------------------------------------------ noise helpers
