@@ -65,4 +65,4 @@ if f[4]:
 
 raw = ws[:1024 * 8].view(torch.int64).cpu()
 print("dependency wait per job (step 1):", [int(raw[760 + j]) for j in range(njobs)])
-print("gru1 stages (wait-weights, issue+commit):", [(int(raw[730 + 2 * i]), int(raw[731 + 2 * i])) for i in range(6)])
+print("traced job's stages (wait-weights, issue+commit):", [(int(raw[730 + 2 * i]), int(raw[731 + 2 * i])) for i in range(10)])

@@ -1741,7 +1741,11 @@ __global__ void __launch_bounds__(kThreadsFold, 1) tc_imagine_fold_kernel(const 
               if (tr && t < 4) p.trace[((t * p.njobs) + jidx) * 4 + 0] = clock64();
 #ifdef WMRL_TC_STAGE_TRACE
               if (tr && t == 1) p.trace[760 + jidx] = clock64() - d0;          // dependency wait of each job
+              #ifdef WMRL_TC_STAGE_TRACE_JOB
+              stage_trace = (tr && t == 1 && jidx == WMRL_TC_STAGE_TRACE_JOB) ? p.trace + 730 : nullptr;
+#else
               stage_trace = (tr && t == 1 && jidx == p.njobs - 3) ? p.trace + 730 : nullptr;   // gru1's stages
+#endif
 #endif
             }
             run_stage(rec, flags);

@@ -51,12 +51,40 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Long waits (epilogue warps): WMRL_WAIT_HINT > 0 passes a suspend-time hint (ns) to try_wait so the hardware parks the
+// warp until the phase completes instead of polling; WMRL_WAIT_SLEEP (ns) is the back-off between polls (0: none).
+#ifndef WMRL_WAIT_HINT
+#define WMRL_WAIT_HINT 0
+#endif
+#ifndef WMRL_WAIT_SLEEP
+#define WMRL_WAIT_SLEEP 64
+#endif
+__device__ __forceinline__ bool mbar_try_wait_long(uint32_t bar, uint32_t parity) {
+#if WMRL_WAIT_HINT > 0
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"((uint32_t)WMRL_WAIT_HINT)
+      : "memory");
+  return ok != 0;
+#else
+  return mbar_try_wait(bar, parity);
+#endif
+}
+__device__ __forceinline__ void mbar_long_backoff() {
+#if WMRL_WAIT_SLEEP > 0
+  __nanosleep(WMRL_WAIT_SLEEP);
+#endif
+}
 // Same, for waiters that expect to wait long (epilogue warps): sleep between polls so the
 // polling does not steal issue slots from the producer / MMA warps.
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
+  while (!mbar_try_wait_long(bar, parity)) {
+    mbar_long_backoff();
     if (++spins > (1u << 24)) {
       printf("wmrl: mbarrier watchdog (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
              threadIdx.x, bar, parity);
@@ -69,8 +97,8 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
 // waiters that hold prefetched operands in registers.  A protocol bug still traps.
 __device__ __forceinline__ void mbar_wait_backoff_quiet(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
+  while (!mbar_try_wait_long(bar, parity)) {
+    mbar_long_backoff();
     if (++spins > (1u << 24)) __trap();
   }
 }
