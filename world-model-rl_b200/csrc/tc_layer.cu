@@ -43,7 +43,9 @@ constexpr uint32_t kLTileChunk = 2048;      // bytes of one 8-column chunk of a 
 constexpr uint32_t kLParamBytes = 8192;     // per work item epilogue parameters (bias / LayerNorm affine / gate biases)
 constexpr uint32_t kLScratchBytes = 4096;   // LayerNorm partial statistics: [q][row] x (sum, sq)
 constexpr uint32_t kLBarBytes = 256;
-constexpr uint32_t kLSmemBytes = kLSlots * kLSlotBytes + kLStageBytes + kLParamBytes + kLScratchBytes + kLBarBytes;
+constexpr int kLMaxSplit = 4;               // LayerNorm layers of few row tiles: N split over a cluster of <= 4 CTAs
+constexpr uint32_t kLXchgBytes = 2 * kLMaxSplit * 128 * 8;   // [item parity][source CTA][row] x (two row statistics)
+constexpr uint32_t kLSmemBytes = kLSlots * kLSlotBytes + kLStageBytes + kLParamBytes + kLScratchBytes + kLXchgBytes + kLBarBytes;
 constexpr int kGruTile = 64;                // state columns per GRU work item (4 x 64 = 256 TMEM columns)
 
 static_assert((kLSlots & (kLSlots - 1)) == 0, "kLSlots must be a power of two");
@@ -89,6 +91,9 @@ struct LayerArgs {
   uint8_t* aux[5];         // extra panels (tile 0) an epilogue reads or writes: recorded activations, g_u
   uint32_t aux_tile_bytes;
   float *f0, *f1, *f2, *f3; // extra fp32 tensors (rstd, carry panels, upstream / start-state / input gradients; see the epilogues)
+  int csplit;              // > 1: LayerNorm layer whose NT = csplit column tiles run on the CTAs of one cluster and
+                           // exchange their row statistics through distributed shared memory (few row tiles)
+  int ln_width;            // full LayerNorm width (= n unless csplit > 1)
   int mode, nt_split;      // epilogue variants (LB_EMB: 1 = raw action gradients out; LB_POST: first column tile of the obs part)
   uint8_t* out;            // destination panel (tile 0)
   uint32_t out_tile_bytes;
@@ -114,6 +119,8 @@ struct LCtx {
   const LayerArgs* p;
   uint32_t prm;        // smem address of this work item's epilogue parameters
   uint32_t scratch;    // smem address of the LayerNorm scratch
+  uint32_t xchg, xbar; // cluster exchange area / its mbarrier (csplit > 1)
+  uint32_t xphase;     // parity of this CTA's LayerNorm item count
   uint32_t stage;      // smem address of this warp's 2 KB transpose staging
   uint32_t tmem_lane;  // accumulator base of this work item with the warp's lane quarter folded in
   int row, q, quarter, lane;
@@ -135,6 +142,30 @@ __device__ __forceinline__ void l_quarter_sync(int quarter) {
 }
 __device__ __forceinline__ void l_epi_sync() { asm volatile("bar.sync 5, %0;" ::"r"(kLEpiThreads) : "memory"); }
 
+// Row statistics of a LayerNorm whose columns are split over the CTAs of a cluster: every CTA publishes its (a, b) of
+// each row into all CTAs' exchange areas (DSMEM), signals their barriers, and sums what the others published.  Called by
+// all epilogue threads after the per-quarter combine (a, b identical in the 4 warps of a quarter).
+__device__ __forceinline__ void l_cluster_stats(const LCtx& c, float& a, float& b) {
+  const int n = c.p->csplit;
+  const uint32_t me = cluster_ctarank();
+  const uint32_t slot = c.xchg + ((c.xphase * kLMaxSplit + me) * 128u + (uint32_t)c.row) * 8u;
+  if (c.q == 0) {
+    for (int r = 0; r < n; ++r) st_cluster_f32x2(mapa(slot, (uint32_t)r), a, b);
+    fence_acq_rel_cluster();
+    __syncwarp();
+    if (c.lane == 0)
+      for (int r = 0; r < n; ++r) mbar_arrive_remote_release(mapa(c.xbar, (uint32_t)r));
+  }
+  mbar_wait_cluster_quiet(c.xbar, c.xphase);
+  a = 0.f; b = 0.f;
+  for (int r = 0; r < n; ++r) {
+    float x, y;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(x), "=f"(y)
+                 : "r"(c.xchg + ((c.xphase * kLMaxSplit + (uint32_t)r) * 128u + (uint32_t)c.row) * 8u) : "memory");
+    a += x; b += y;
+  }
+}
+
 // activation on zs = z * log2(e) (the LayerNorm affine is pre-scaled): ELU (actor.py:33), SiLU (models.py:12),
 // ReLU (trainers/value/critic.py:19)
 template <int kAct>
@@ -148,7 +179,7 @@ __device__ __forceinline__ float act_scaled(float zs) {
 template <int kAct>
 __device__ __forceinline__ void lepi_ln_act(const LCtx& c) {
   const LayerArgs& p = *c.p;
-  const int W = p.n, ngrp = W / 32;
+  const int W = p.n, ngrp = W / 32;   // this column tile (the whole layer unless csplit > 1)
   const uint32_t bias = c.prm, gam = bias + W * 4, bet = gam + W * 4;
   float sum = 0.f, sq = 0.f;
   for (int g = c.q; g < ngrp; g += 4) {
@@ -172,13 +203,16 @@ __device__ __forceinline__ void lepi_ln_act(const LCtx& c) {
     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "r"(c.scratch + (k * 128 + c.row) * 8) : "memory");
     sum += a; sq += b;
   }
-  const float inv = 1.f / (float)W;
+  if (p.csplit > 1) l_cluster_stats(c, sum, sq);
+  const float inv = 1.f / (float)p.ln_width;
   const float mean = sum * inv;
   const float var = fmaxf(sq * inv - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
   const float nmr = -mean * rstd;
-  if (p.save && c.q == 0 && p.f0) p.f0[(long long)c.mt * 128 + c.row] = rstd;
-  uint8_t* xrow = p.save ? p.aux[0] + (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16 : nullptr;
+  if (p.save && c.q == 0 && c.nt == 0 && p.f0) p.f0[(long long)c.mt * 128 + c.row] = rstd;
+  const size_t ch0 = (size_t)c.nt * (W / 8) * kLTileChunk;   // this tile's first chunk in the row tile's panels
+  uint8_t* xrow = p.save ? p.aux[0] + (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16 + ch0 : nullptr;
+  uint8_t* const orow = c.out_row + ch0;
   for (int g = c.q; g < ngrp; g += 4) {
     float v[32];
     tmem_ld32(c.tmem_lane + g * 32, v);
@@ -200,7 +234,7 @@ __device__ __forceinline__ void lepi_ln_act(const LCtx& c) {
         v[k * 8 + i + 3] = act_scaled<kAct>(fmaf(xh[i + 3], g4.w, e4.w));
       }
       if (p.save) st_chunk_g(xrow + (size_t)(g * 4 + k) * kLTileChunk, xh);
-      st_chunk_g(c.out_row + (size_t)(g * 4 + k) * kLTileChunk, v + k * 8);
+      st_chunk_g(orow + (size_t)(g * 4 + k) * kLTileChunk, v + k * 8);
     }
   }
 }
@@ -833,10 +867,12 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
   const int W = p.n, ngrp = W / 32;
   const uint32_t gsc = c.prm, bsc = c.prm + W * 4;
   const uint32_t gam = c.prm + 2 * W * 4;
-  const size_t ro = (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16;
+  const size_t ch0 = (size_t)c.nt * (W / 8) * kLTileChunk;   // this column tile's first chunk (csplit > 1: nt > 0)
+  const size_t ro = (size_t)c.mt * p.aux_tile_bytes + (size_t)c.row * 16 + ch0;
   const uint8_t* xrow = p.aux[0] + ro;
   const uint8_t* yrow = p.aux[2] + ro;
   uint8_t* gurow = p.aux[1] + ro;
+  uint8_t* const orow = c.out_row + ch0;
   const float rstd = c.valid ? p.f0[(long long)c.mt * 128 + c.row] : 0.f;
   float s1 = 0.f, s2 = 0.f;
   LPROBE(c, 0);
@@ -889,7 +925,8 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "r"(c.scratch + (k * 128 + c.row) * 8) : "memory");
     s1 += a; s2 += b;
   }
-  const float inv = 1.f / (float)W;
+  if (p.csplit > 1) l_cluster_stats(c, s1, s2);
+  const float inv = 1.f / (float)p.ln_width;
   const float m1 = s1 * inv, m2 = s2 * inv;
   for (int g = c.q; g < ngrp; g += 4) {
     float v[32];
@@ -922,7 +959,7 @@ __device__ __forceinline__ void lepib_ln(const LCtx& c) {
           gp[i + e] = c.valid ? rstd * (g_x - m1 - xh[i + e] * m2) : 0.f;
         }
       }
-      st_chunk_g(c.out_row + (size_t)(g * 4 + k) * kLTileChunk, gp);
+      st_chunk_g(orow + (size_t)(g * 4 + k) * kLTileChunk, gp);
     }
   }
   LPROBE(c, 4);
@@ -964,8 +1001,9 @@ __device__ __forceinline__ void lepib_prefetch(const LCtx& c, int type) {
       for (int g = c.q; g < p.n / 32; g += 4)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          l_prefetch(p.aux[0] + ro + (size_t)(g * 4 + k) * kLTileChunk);
-          if (type != LB_LN_SILU) l_prefetch(p.aux[2] + ro + (size_t)(g * 4 + k) * kLTileChunk);
+          const size_t ch = (size_t)c.nt * (p.n / 8) + (size_t)(g * 4 + k);
+          l_prefetch(p.aux[0] + ro + ch * kLTileChunk);
+          if (type != LB_LN_SILU) l_prefetch(p.aux[2] + ro + ch * kLTileChunk);
         }
   }
 }
@@ -983,12 +1021,14 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
   const uint32_t stage_base = smem_base + kLSlots * kLSlotBytes;
   const uint32_t prm = stage_base + kLStageBytes;
   const uint32_t scratch = prm + kLParamBytes;
-  const uint32_t bars = scratch + kLScratchBytes;
+  const uint32_t xchg = scratch + kLScratchBytes;
+  const uint32_t bars = xchg + kLXchgBytes;
   auto full_bar = [&](uint32_t s) { return bars + 8u * s; };
   auto empty_bar = [&](uint32_t s) { return bars + 64u + 8u * s; };
   auto accf_bar = [&](uint32_t j) { return bars + 128u + 8u * j; };
   auto acce_bar = [&](uint32_t j) { return bars + 144u + 8u * j; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (bars - smem_base) + 160);
+  const uint32_t xbar = bars + 176u;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int nitems = p.MT * p.NT;
@@ -996,11 +1036,13 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < (uint32_t)kLSlots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (uint32_t j = 0; j < 2; ++j) { mbar_init(accf_bar(j), 1); mbar_init(acce_bar(j), kLEpiWarps); }
+    if (p.csplit > 1) mbar_init(xbar, 4u * (uint32_t)p.csplit);   // lane 0 of the q == 0 warp of every quarter of every CTA
     fence_barrier_init();
   }
   if (warp == kLMmaWarp) { tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
+  if (p.csplit > 1) cluster_sync_all();   // the peers' exchange barriers exist before anybody signals them
   tc_fence_after();
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the previous layer's
   // tail; from here on this grid reads what that layer wrote.  The next layer may start its own set-up right away
@@ -1110,6 +1152,7 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
     c.prm = prm;
     c.scratch = scratch;
     c.stage = stage_base + (uint32_t)warp * 2048u;
+    c.xchg = xchg; c.xbar = xbar;
     c.quarter = warp & 3;
     c.q = warp >> 2;
     c.lane = lane;
@@ -1119,6 +1162,7 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
       const uint32_t ab = p.dbuf ? (it & 1u) : 0u;
       const uint32_t use = p.dbuf ? (it >> 1) : it;
       c.mt = item / p.NT; c.nt = item % p.NT;
+      c.xphase = it & 1u;
       c.b = (long long)c.mt * 128 + c.row;
       c.valid = c.b < p.B;
       c.tmem_lane = tmem_base + ab * 256u + ((uint32_t)(c.quarter * 32) << 16);
@@ -1175,6 +1219,7 @@ __global__ void __launch_bounds__(kLThreads, 1) tc_layer_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (p.csplit > 1) cluster_sync_all();   // no CTA leaves while a peer may still write into its exchange area
   if (warp == kLMmaWarp) tmem_dealloc(tmem_base, 512);
   if (tr && threadIdx.x == 0) p.trace[11] = clock64();
 #undef LTRACE
@@ -1500,6 +1545,7 @@ enum {
 struct LSegH { int buf, k16, n, tmem_col, split, fresh; uint32_t w_off; };
 struct LLayerH {
   int type = 0, NT = 1, n = 0, nseg = 0, kc = 1, dbuf = 0, out = 0, layer = 0;
+  int csplit = 0;            // > 1: the NT = csplit column tiles of a LayerNorm layer run as one cluster
   LSegH seg[3];
   size_t w_off = 0;          // into the data area
   uint32_t w_tile_bytes = 0;
@@ -1511,6 +1557,10 @@ struct LPlan {
   Plan pk;                   // pack ops / vec ops / image offsets (stage and job tables stay empty)
   std::vector<LLayerH> layers;    // forward chain of one step
   std::vector<LLayerH> blayers;   // backward chain of one step (after the sample backward)
+  // the same chains with every LayerNorm layer split into `csplit` column tiles (one cluster per row tile, statistics
+  // exchanged through DSMEM): used when a call has so few row tiles that one CTA per row tile leaves most SMs idle
+  std::vector<LLayerH> layers_s, blayers_s;
+  int csplit = 0;
   int Dp = 0, Sip = 0, Sp = 0, Hdp = 0, Ha = 0, Pp = 0, Ep = 0;
 };
 
@@ -1829,7 +1879,64 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
     L.ep_floats = 3u * d.Ha;
     lp.blayers.push_back(L);
   }
-  for (const std::vector<LLayerH>* v : {&lp.layers, &lp.blayers})
+  // ====================================================================== LayerNorm layers split over a cluster
+  if (d.Ha % (32 * kLMaxSplit) == 0) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    const int ns = d.Ha / kLMaxSplit;
+    lp.csplit = kLMaxSplit;
+    lp.layers_s = lp.layers;
+    lp.blayers_s = lp.blayers;
+    for (LLayerH& L : lp.layers_s) {
+      if (L.type != LE_LN_ELU) continue;
+      const int l = L.layer;
+      const float* lw = aw ? aw->lin_w[l] : nul;
+      L.NT = kLMaxSplit; L.n = ns; L.dbuf = 1; L.kc = kc_for(ns); L.csplit = kLMaxSplit;
+      L.w_off = pk.data_bytes;
+      for (int j = 0; j < L.NT; ++j) {
+        const size_t t0 = pk.data_bytes;
+        RowSpec rs(j * ns, ns, ns);
+        if (l == 0) {
+          L.seg[0] = {F_H, Dp / 16, ns, 0, 0, 1, 0u};
+          l_add_pack(lp, rs, lw, d.F, 0, d.D, Dp);
+          L.seg[1] = {F_S, Sip / 16, ns, 0, 0, 0, (uint32_t)(pk.data_bytes - t0)};
+          l_add_pack(lp, rs, lw, d.F, d.D, d.S_in, Sip);
+        } else {
+          L.seg[0] = {F_Y0 + l - 1, d.Ha / 16, ns, 0, 0, 1, 0u};
+          l_add_pack(lp, rs, lw, d.Ha, 0, d.Ha, d.Ha);
+        }
+        L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+        const uint32_t at = add_vec(pk, aw ? aw->lin_b[l] : nul, nul, j * ns, ns, ns);
+        add_vec(pk, aw ? aw->ln_g[l] : nul, nul, j * ns, ns, ns, kLog2e);
+        add_vec(pk, aw ? aw->ln_b[l] : nul, nul, j * ns, ns, ns, kLog2e);
+        if (j == 0) L.ep_off = at;
+      }
+      L.ep_floats = 3u * ns;
+    }
+    for (LLayerH& L : lp.blayers_s) {
+      if (L.type != LB_LN) continue;
+      const int l = L.layer;
+      L.NT = kLMaxSplit; L.n = ns; L.dbuf = 1; L.kc = kc_for(ns); L.csplit = kLMaxSplit;
+      L.w_off = pk.data_bytes;
+      for (int j = 0; j < L.NT; ++j) {
+        const size_t t0 = pk.data_bytes;
+        RowSpec rs(j * ns, ns, ns);
+        if (l == d.La - 1) {
+          L.seg[0] = {G_GMU, 1, ns, 0, 0, 1, 0u};
+          l_add_pack_t(lp, rs, aw ? aw->mu_w : nul, d.Ha, {{0, d.A, 16}});
+        } else {
+          L.seg[0] = {G_GP0 + l + 1, d.Ha / 16, ns, 0, 0, 1, 0u};
+          l_add_pack_t(lp, rs, aw ? aw->lin_w[l + 1] : nul, d.Ha, {{0, d.Ha, d.Ha}});
+        }
+        L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+        const uint32_t at = add_vec(pk, aw ? aw->ln_g[l] : nul, nul, j * ns, ns, ns, kLog2e);
+        add_vec(pk, aw ? aw->ln_b[l] : nul, nul, j * ns, ns, ns, kLog2e);
+        add_vec(pk, aw ? aw->ln_g[l] : nul, nul, j * ns, ns, ns);
+        if (j == 0) L.ep_off = at;
+      }
+      L.ep_floats = 3u * ns;
+    }
+  }
+  for (const std::vector<LLayerH>* v : {&lp.layers, &lp.blayers, &lp.layers_s, &lp.blayers_s})
     for (const LLayerH& L : *v) {
       if (L.ep_floats * 4 > kLParamBytes || (L.ep_floats & 3)) return lp;
       for (int s = 0; s < L.nseg; ++s)
@@ -1920,6 +2027,7 @@ int tcl_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_
   return tc_pack_plan(lp.pk, (uint8_t*)packed, st);
 }
 
+static int g_max_clusters[64] = {0};   // co-resident clusters of kLMaxSplit layer-kernel CTAs (set by tcl_device_setup)
 static int tcl_device_setup(int& nsm) {
   static std::mutex mu;
   static bool attr_set[64] = {false};
@@ -1937,6 +2045,20 @@ static int tcl_device_setup(int& nsm) {
       }
     WMRL_CUDA_OK(cudaFuncSetAttribute(tcl_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWg2Smem));
     WMRL_CUDA_OK(cudaDeviceGetAttribute(&sm_cached[dev], cudaDevAttrMultiProcessorCount, dev));
+    {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(sm_cached[dev] / kLMaxSplit * kLMaxSplit));
+      cfg.blockDim = dim3(kLThreads);
+      cfg.dynamicSmemBytes = kLSmemBytes;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kLMaxSplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, layer_kernel_for(LE_LN_ELU, 4), &cfg) != cudaSuccess) { nc = 0; cudaGetLastError(); }
+      g_max_clusters[dev] = nc;
+    }
     attr_set[dev] = true;
   }
   nsm = sm_cached[dev];
@@ -1970,6 +2092,7 @@ static int tcl_launch(const LCall& c, const LLayerH& L, LayerArgs& a, const int*
   a.w = c.data + L.w_off; a.w_tile_bytes = L.w_tile_bytes;
   a.ep = c.ep + L.ep_off; a.ep_floats = L.ep_floats;
   a.kc = L.kc; a.dbuf = L.dbuf; a.type = L.type; a.n = L.n; a.NT = L.NT; a.MT = c.MT;
+  a.csplit = L.csplit; a.ln_width = L.csplit > 1 ? L.n * L.NT : L.n;
   a.B = d.B; a.H = d.T; a.D = d.D; a.S = d.S; a.C = d.C; a.A = d.A; a.Sp = lp.Sp; a.Dp = lp.Dp; a.Sip = lp.Sip; a.E = d.E;
   a.inv_action_scale = 1.f / d.action_scale;
   a.out = c.at(L.out, out_step); a.out_tile_bytes = c.m->r[L.out].tile_bytes; a.out_cols = buf_width(lp, L.out);
@@ -1979,13 +2102,27 @@ static int tcl_launch(const LCall& c, const LLayerH& L, LayerArgs& a, const int*
   cfg.blockDim = dim3(kLThreads);
   cfg.dynamicSmemBytes = kLSmemBytes;
   cfg.stream = c.st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (L.csplit > 1) {   // one cluster per row tile; the caller checked that all of them are co-resident
+    cfg.gridDim = dim3((unsigned)items);
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)L.csplit; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, layer_kernel_for(L.type, d.S), a));
   return 0;
+}
+// few row tiles: the LayerNorm layers run split over clusters when every row tile's cluster is co-resident (single wave)
+static bool tcl_use_split(const LPlan& lp, int MT) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("WMRL_LN_SPLIT"); off = (e && e[0] == '0') ? 1 : 0; }
+  return !off && lp.csplit > 1 && MT <= g_max_clusters[dev];
 }
 
 int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, const float* stoch0, const float* noise,
@@ -2004,6 +2141,7 @@ int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, cons
   tcl_init_kernel<<<dim3(8, c.MT), 256, 0, st>>>(deter0, stoch0, deter_seq, stoch_seq, c.at(F_H, 0), c.at(F_S, 0), d.B, d.T,
                                                  d.D, d.S_in, lp.Dp, lp.Sip);
   WMRL_CUDA_OK(cudaGetLastError());
+  const std::vector<LLayerH>& fl = tcl_use_split(lp, c.MT) ? lp.layers_s : lp.layers;
   for (int t = 0; t < d.T; ++t) {
     // step index of each field: recorded fields are indexed by t (h, s: t -> t + 1); otherwise one entry (h: parity)
     auto step_of = [&](int buf) {
@@ -2014,7 +2152,7 @@ int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, cons
       if (buf == F_A) return 0;
       return rec ? t : 0;
     };
-    for (const LLayerH& L : lp.layers) {
+    for (const LLayerH& L : fl) {
       LayerArgs a{};
       a.t = t;
       a.deter_seq = deter_seq; a.stoch_seq = stoch_seq; a.dist_a = dist_a; a.dist_b = dist_b; a.actions = actions;
@@ -2029,7 +2167,7 @@ int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, cons
         a.aux_tile_bytes = m.r[F_GR].tile_bytes;
       }
       a.trace = nullptr;
-      if ((d.flags & WMRL_FLAG_TRACE) && t == std::min(1, d.T - 1)) a.trace = trace_base + 32 * (&L - &lp.layers[0]);
+      if ((d.flags & WMRL_FLAG_TRACE) && t == std::min(1, d.T - 1)) a.trace = trace_base + 32 * (&L - &fl[0]);
       int ss[3];
       for (int s = 0; s < L.nseg; ++s) ss[s] = step_of(L.seg[s].buf);
       if (int r = tcl_launch(c, L, a, ss, step_of(L.out))) return r;
@@ -2067,6 +2205,7 @@ int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const
     tcl_carry_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(carry_h, g_deter_seq, d.B, T, d.D, lp.Dp, n);
     WMRL_CUDA_OK(cudaGetLastError());
   }
+  const std::vector<LLayerH>& bl = tcl_use_split(lp, MT) ? lp.blayers_s : lp.blayers;
   for (int t = T - 1; t >= 0; --t) {
     // dL/d(head output) of the step that produced state t+1
     {
@@ -2083,7 +2222,7 @@ int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const
       }
       WMRL_CUDA_OK(cudaGetLastError());
     }
-    for (const LLayerH& L : lp.blayers) {
+    for (const LLayerH& L : bl) {
       LayerArgs a{};
       a.t = t;
       a.deter_seq = const_cast<float*>(deter_seq); a.actions = const_cast<float*>(actions);
@@ -2115,7 +2254,7 @@ int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const
       int ss[3] = {0, 0, 0};
       if (L.seg[0].buf == G_GMU || L.seg[0].buf >= G_GP0) ss[0] = t;
       a.trace = nullptr;
-      if ((d.flags & WMRL_FLAG_TRACE) && t == std::max(0, T - 2)) a.trace = (long long*)ws + 32 * (&L - &lp.blayers[0]);
+      if ((d.flags & WMRL_FLAG_TRACE) && t == std::max(0, T - 2)) a.trace = (long long*)ws + 32 * (&L - &bl[0]);
       if (int r = tcl_launch(c, L, a, ss, out_step)) return r;
     }
   }
@@ -2915,6 +3054,7 @@ static int tcm_launch(const MlpCall& c, const LLayerH& L, LayerArgs& a) {
   a.w = c.data + L.w_off; a.w_tile_bytes = L.w_tile_bytes;
   a.ep = c.ep + L.ep_off; a.ep_floats = L.ep_floats;
   a.kc = L.kc; a.dbuf = L.dbuf; a.type = L.type; a.n = L.n; a.NT = L.NT; a.MT = m.MT;
+  a.csplit = 0; a.ln_width = L.n;
   a.B = (int)m.R; a.H = 1; a.t = 0; a.D = m.F; a.A = m.O;
   if (L.out >= 0) { a.out = c.at(L.out); a.out_tile_bytes = c.mm->tile[L.out]; a.out_cols = m.Hh; }
   const int items = m.MT * L.NT;

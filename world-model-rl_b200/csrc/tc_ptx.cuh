@@ -123,6 +123,15 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// same with cluster-scope release: generic-proxy stores made (here or, ordered by __syncwarp, by the other lanes) before
+// the arrive are visible to a cluster-scope acquire wait on that barrier
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1,%2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 // wait on a local mbarrier whose arrivals may come from the peer CTA (cluster-scope acquire)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -144,6 +153,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       __trap();
     }
   }
+}
+
+// same without the printf (see mbar_wait_backoff_quiet): a protocol bug still traps
+__device__ __forceinline__ void mbar_wait_cluster_quiet(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity))
+    if (++spins > (1u << 26)) __trap();
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA)
