@@ -227,3 +227,54 @@ def test_oracle_bf16_emulation_is_a_small_perturbation():
         assert float((a[k] - b[k]).norm() / a[k].norm()) < 1e-2, k
     x = torch.tensor([1.0, 0.5, -2.0, 3.140625])
     assert torch.equal(O.bf16_round(x), x)
+
+
+def test_mlp_abi_size_queries_and_struct_layout():
+    """wmrl_mlp_* size queries need no device; struct mirrors follow the header's field order."""
+    import ctypes as C
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "wmrl.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", header.split("typedef struct wmrl_mlp_dims {")[1].split("} wmrl_mlp_dims;")[0], flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        if decl.strip():
+            names += [n.strip() for n in decl.strip().split(None, 1)[1].split(",")]
+    assert names == [f[0] for f in _lib.MlpDims._fields_]
+    d = _lib.MlpDims(rows=1000, in_dim=230, hidden=512, depth=3, out_dim=1, act=2, flags=0)
+    assert lib.wmrl_mlp_packed_bytes(C.byref(d)) > 2 * 2 * (230 * 512 + 2 * 512 * 512)   # forward + transposed operands
+    assert lib.wmrl_mlp_panel_bytes(C.byref(d)) >= 8 * 128 * 240 * 2                        # 8 row tiles, in_dim padded to 240
+    assert lib.wmrl_mlp_saved_bytes(C.byref(d)) >= 3 * 2 * 8 * 128 * 512 * 2                # y + x-hat per block
+    ws0, ws1 = lib.wmrl_mlp_workspace_bytes(C.byref(d), 0), lib.wmrl_mlp_workspace_bytes(C.byref(d), 1)
+    d.flags = _lib.MLP_WGRAD
+    assert lib.wmrl_mlp_workspace_bytes(C.byref(d), 1) > ws1 > 0 and ws0 > 0                # g_u panels only with WGRAD
+    for bad in (dict(hidden=500), dict(hidden=1024), dict(out_dim=17), dict(depth=0), dict(act=3)):
+        kw = dict(rows=10, in_dim=230, hidden=512, depth=3, out_dim=1, act=2, flags=0)
+        kw.update(bad)
+        assert lib.wmrl_mlp_packed_bytes(C.byref(_lib.MlpDims(**kw))) == 0, bad
+    rc = lib.wmrl_mlp_fwd_bf16(C.byref(_lib.MlpDims(rows=10, in_dim=8, hidden=500, depth=1, out_dim=1, act=0, flags=0)),
+                               None, None, None, None, 0, None, 0, None)
+    assert rc != 0 and b"not supported" in lib.wmrl_last_error()
+
+
+def test_heads_precision_switch_on_cpu():
+    """fp32 heads on CPU tensors run the torch modules (reference behaviour); the bf16 chain refuses CPU tensors;
+    set_precision reaches every wmrl module under a container."""
+    m = wmrl.DenseModel(input_dim=24, hidden_dim=32, depth=2)
+    c = wmrl.ValueCritic(24, num_layers=2, hidden_dim=64)
+    x = torch.randn(5, 3, 24)
+    torch.testing.assert_close(m(x), m.fc(x))
+    torch.testing.assert_close(c(x), c.layers(x))
+    box = torch.nn.ModuleDict({"r": m, "c": c, "rssm": wmrl.ContinuousRSSM(16, 16, 4, 8, 2)})
+    wmrl.set_precision(box, "bf16")
+    assert m.precision == c.precision == box["rssm"].precision == "bf16"
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(x)
+    wmrl.set_precision(box, "fp32")
+    assert m.precision == "fp32" and box["rssm"].precision == "fp32"
+    with pytest.raises(ValueError):
+        wmrl.set_precision(box, "fp8")
+    from wmrl.functional import mlp_bf16_supported
+    assert mlp_bf16_supported(m.fc) and mlp_bf16_supported(c.layers)
+    assert not mlp_bf16_supported(torch.nn.Sequential(torch.nn.Linear(8, 40), torch.nn.LayerNorm(40), torch.nn.ReLU(),
+                                                      torch.nn.Linear(40, 1)))          # hidden % 32 != 0
+    assert not mlp_bf16_supported(torch.nn.Sequential(torch.nn.Linear(8, 32), torch.nn.Tanh(), torch.nn.Linear(32, 1)))
