@@ -236,6 +236,92 @@ def make_lambda_case(ref, name, *, B, H, seed, gamma=0.99, lam=0.95):
     return path
 
 
+def make_heads_case(ref, name, *, B, H, F_, seed):
+    """The MLP heads the rollout's callers run over the features: reference DenseModel (reward: SiLU, identity out;
+    done: SiLU, sigmoid out; models.py:3-37) and ValueCritic (critic.py:4-29): outputs and every gradient."""
+    from reflect.components.rssm_world_model.models import DenseModel
+    torch.manual_seed(seed)
+    heads = {"reward": DenseModel(depth=2, input_dim=F_, hidden_dim=64, output_dim=1),
+             "done": DenseModel(depth=3, input_dim=F_, hidden_dim=32, output_dim=1, output_act=torch.nn.Sigmoid),
+             "critic": ref["ValueCritic"](F_, 3, 96)}
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for m in heads.values():
+            for p_ in m.parameters():
+                if p_.dim() == 1:
+                    p_.add_(0.2 * torch.randn(p_.shape, generator=g))
+    out = {"dims": np.asarray([B, H, F_], dtype=np.int64)}
+    x = torch.randn(B, H, F_, generator=g)
+    out["x"] = x.numpy()
+    for k, m in heads.items():
+        out.update(_np(m.state_dict(), k + "."))
+        xi = x.clone().requires_grad_(True)
+        y = m(xi)
+        gy = torch.randn(y.shape, generator=g)
+        y.backward(gy)
+        out[k + "_y"], out[k + "_gy"], out[k + "_gx"] = y.detach().numpy(), gy.numpy(), xi.grad.numpy()
+        for n_, p_ in m.named_parameters():
+            out[k + "_grad." + n_] = p_.grad.numpy().copy()
+    path = os.path.join(OUT, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    return path
+
+
+def make_act_case(ref, variant, name, *, B, steps, D, S, C, Hd, E, A, Ha, La, seed):
+    """WorldModelActor.__call__'s RSSM / actor stages (memory_actor.py:51-56) on the unmodified reference, `steps`
+    chained environment steps: post = posterior(e, state); a = actor(post.features, deterministic=True);
+    state = prior(a, post).  The latent draws come from the tape (posterior first, then prior, per step)."""
+    torch.manual_seed(seed)
+    if variant == "continuous":
+        rssm = ref["ContinuousRSSM"](Hd, D, S, E, A)
+    else:
+        rssm = ref["DiscreteRSSM"](Hd, D, S, C, E, A)
+    S_in = S if variant == "continuous" else C * S
+    bound = [0.5 + 0.25 * i for i in range(A)] if A > 1 else 1.0
+    actor = ref["Actor"](D + S_in, A, bound, La, Ha)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for p_ in actor.parameters():
+            if p_.dim() == 1:
+                p_.add_(0.1 * torch.randn(p_.shape, generator=g))
+    deter0 = torch.tanh(torch.randn(B, D, generator=g))
+    if variant == "continuous":
+        state = ref["InternalStateContinuous"](deter_state=deter0, stoch_state=torch.zeros(B, S),
+                                               mean=torch.zeros(B, S), std=torch.ones(B, S))
+        noise = torch.randn(2 * steps, B, S, generator=g)
+        tape = dict(eps_list=list(noise))
+    else:
+        state = ref["InternalStateDiscrete"](deter_state=deter0, stoch_state=torch.zeros(B, C * S),
+                                             logits=torch.zeros(B, C, S))
+        noise = torch.empty(2 * steps, B, C, S).exponential_(1, generator=g)
+        tape = dict(q_list=list(noise))
+    embeds = torch.randn(steps, B, E, generator=g)
+    out = {"dims": np.asarray([B, steps, D, S, C, Hd, E, A, Ha, La], dtype=np.int64), "deter0": deter0.numpy(),
+           "noise": noise.numpy(), "embeds": embeds.numpy(), "bound": np.asarray(bound, dtype=np.float32)}
+    out.update(_np(rssm.state_dict(), "rssm."))
+    out.update(_np(actor.state_dict(), "actor."))
+    rec = {k: [] for k in ("action", "post_stoch", "post_a", "post_b", "deter", "pri_stoch", "pri_a", "pri_b")}
+    with torch.no_grad(), noise_tape(**tape):
+        for t in range(steps):
+            post = rssm.posterior(embeds[t], state)
+            a = actor(post.get_features(), deterministic=True)
+            state = rssm.prior(a, post)
+            rec["action"].append(a)
+            rec["post_stoch"].append(post.stoch_state); rec["pri_stoch"].append(state.stoch_state)
+            rec["deter"].append(state.deter_state)
+            if variant == "continuous":
+                rec["post_a"].append(post.mean); rec["post_b"].append(post.std)
+                rec["pri_a"].append(state.mean); rec["pri_b"].append(state.std)
+            else:
+                rec["post_a"].append(post.logits); rec["pri_a"].append(state.logits)
+    for k, v in rec.items():
+        if v:
+            out["step_" + k] = torch.stack(v).numpy()
+    path = os.path.join(OUT, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    return path
+
+
 def main():
     ref = _import_reference()
     torch.set_num_threads(1)   # fixed summation order in the CPU GEMMs
@@ -254,6 +340,9 @@ def main():
     print(make_lambda_case(ref, "lambda_h3", B=4, H=3, seed=51))
     print(make_lambda_case(ref, "lambda_h1", B=4, H=1, seed=52))
     print(make_lambda_case(ref, "lambda_h64", B=3, H=64, seed=53))
+    print(make_heads_case(ref, "heads", B=7, H=5, F_=24, seed=60))
+    print(make_act_case(ref, "continuous", "act_cont", B=3, steps=4, D=32, S=32, C=1, Hd=32, E=48, A=2, Ha=64, La=3, seed=70))
+    print(make_act_case(ref, "discrete", "act_disc", B=3, steps=4, D=27, S=6, C=3, Hd=19, E=21, A=3, Ha=64, La=2, seed=71))
 
 
 if __name__ == "__main__":

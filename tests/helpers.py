@@ -14,7 +14,7 @@ class Golden:
     def __init__(self, name):
         self.name = name
         self.z = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
-        if "dims" in self.z:
+        if "dims" in self.z and len(self.z["dims"]) == 11:
             (self.B, self.H, self.T, self.D, self.S, self.C, self.Hd, self.E, self.A, self.Ha,
              self.La) = [int(v) for v in self.z["dims"]]
             self.variant = "continuous" if name.startswith("cont") else "discrete"

@@ -99,3 +99,45 @@ def test_lambda_weights_quirk():
     t = O.lambda_return_scan(V, r, d, 0.9, 0.5)
     assert torch.allclose(t[0, 0], torch.tensor([0.5 * (1.0 + 0.9 * 3.0)]))
     assert torch.allclose(t[0, 1], torch.tensor([3.0]))
+
+
+# ---- heads and the online acting step: oracle restatements vs the unmodified reference's vectors ------------------
+HEAD_ACTS = {"reward": "silu", "done": "silu", "critic": "relu"}
+HEAD_SEQ = {"reward": "fc.", "done": "fc.", "critic": "layers."}
+
+
+@pytest.mark.parametrize("head", ["reward", "done", "critic"])
+def test_mlp_head_matches_reference(head):
+    g = Golden("heads")
+    sd = {k: v.clone().requires_grad_(True) for k, v in g.weights(head + "." + HEAD_SEQ[head]).items()}
+    x = g.t("x").requires_grad_(True)
+    y = O.mlp_head(sd, x, HEAD_ACTS[head])
+    if head == "done":
+        y = torch.sigmoid(y)          # DenseModel.output_act (models.py:37)
+    torch.testing.assert_close(y, g.t(head + "_y"), rtol=1e-6, atol=1e-6)
+    y.backward(g.t(head + "_gy"))
+    torch.testing.assert_close(x.grad, g.t(head + "_gx"), rtol=1e-5, atol=1e-6)
+    for k, v in sd.items():
+        torch.testing.assert_close(v.grad, g.t(f"{head}_grad.{HEAD_SEQ[head]}{k}"), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["act_cont", "act_disc"])
+def test_act_step_matches_reference(name):
+    g = Golden(name)
+    B, steps, D, S, C, Hd, E, A, Ha, La = [int(v) for v in g.z["dims"]]
+    variant = "continuous" if name == "act_cont" else "discrete"
+    w, aw = g.weights("rssm."), g.weights("actor.")
+    deter = g.t("deter0")
+    noise, embeds = g.t("noise"), g.t("embeds")
+    for t in range(steps):
+        r = O.act_step(variant, w, aw, embeds[t], deter, noise[2 * t], noise[2 * t + 1], S, C, 5.0, g.t("bound"))
+        torch.testing.assert_close(r["action"], g.t("step_action")[t], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(r["deter_next"], g.t("step_deter")[t], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(r["post_stoch"].detach(), g.t("step_post_stoch")[t], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(r["prior_stoch"].detach(), g.t("step_pri_stoch")[t], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(r["post_a"], g.t("step_post_a")[t], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(r["prior_a"], g.t("step_pri_a")[t], rtol=1e-6, atol=1e-6)
+        if variant == "continuous":
+            torch.testing.assert_close(r["post_b"], g.t("step_post_b")[t], rtol=1e-6, atol=1e-6)
+            torch.testing.assert_close(r["prior_b"], g.t("step_pri_b")[t], rtol=1e-6, atol=1e-6)
+        deter = r["deter_next"]
