@@ -264,7 +264,7 @@ typedef struct wmrl_act_sampling {
   const float* noise_action;   /* [B][A] N(0,1) draws   */
   float* act_mean;             /* [B][A] (row stride ld_out): tanh-squashed mean */
   float* act_std;              /* [B][A] (row stride ld_out) */
-  float* entropy;              /* [B], may be NULL */
+  float* entropy;              /* [B] (row stride ld_out, like every output), may be NULL */
 } wmrl_act_sampling;
 WMRL_API int wmrl_act_step(const wmrl_dims* d, const wmrl_rssm_params* w, const wmrl_actor_params* aw,
                   const float* obs_embed, const float* deter, const float* noise_post, const float* noise_prior,

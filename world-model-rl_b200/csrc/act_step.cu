@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kActThreads, 1) act_step_kernel(const __grid_c
       float h = 0.f;
       for (int j = c.lane; j < p.A; j += 32) h += 1.4189385332046727f + logf(c.smem[p.o_out + j]);
       h = act_warp_sum(h);
-      if (c.lane == 0) p.smp.entropy[row] = h;
+      if (c.lane == 0) p.smp.entropy[row * p.ldo] = h;
     }
   }
   c.cluster.sync();

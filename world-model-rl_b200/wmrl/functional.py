@@ -626,7 +626,81 @@ def kl_loss(cfg: PathConfig, rho: float, prior_a, prior_b, post_a, post_b):
     return KLLoss.apply(cfg, float(rho), prior_a, prior_b, post_a, post_b)
 
 
-_ACT_PTRS: "dict" = {}
+class ActStepPlan:
+    """Everything of an online acting step that does not change between environment steps: the validated parameter
+    lists, the pointer structs and the dims struct per batch size.  At B = 1 the step is host-latency-bound (the kernel
+    takes ~30 us), so the per-call Python work is kept to pointer comparisons, one allocation and the ctypes call.
+    ``valid()`` is false once any parameter moved (``.to()``, ``param.data = ...`` as WorldModelActor.perturb_actor does)."""
+
+    def __init__(self, cfg: PathConfig, rssm_p: Sequence[torch.Tensor], actor_p: Sequence[torch.Tensor], bound: torch.Tensor):
+        self.cfg = cfg
+        self.dev = _require_cuda(*rssm_p, *actor_p, bound)
+        self.tensors = list(rssm_p) + list(actor_p) + [bound]
+        self.ptrs = [t.data_ptr() for t in self.tensors]
+        # fp32 contiguous parameters are passed by reference (optimiser steps are seen); anything else would need a
+        # converted copy, which must not be cached
+        self.cacheable = all(t.dtype == torch.float32 and t.is_contiguous() for t in self.tensors)
+        self.keep = [_f32c(p) for p in rssm_p], [_f32c(p) for p in actor_p]
+        self.w = _rssm_ptrs(self.keep[0])
+        self.aw = _actor_ptrs(self.keep[1], cfg.La, bound)
+        self.dims = {}
+        disc = cfg.variant == _lib.DISCRETE
+        W = cfg.dist_width
+        self.widths = [cfg.A, cfg.S_in, W, cfg.D, cfg.S_in, W] + ([] if disc else [W, W])
+        self.nlat = cfg.S_in if disc else cfg.S
+
+    def valid(self) -> bool:
+        return self.cacheable and [t.data_ptr() for t in self.tensors] == self.ptrs
+
+    def run(self, obs_embed, deter, noise_post, noise_prior, sampling=None):
+        lib = _lib.load()
+        cfg, dev = self.cfg, self.dev
+        if deter.device != dev or obs_embed.device != dev:
+            raise RuntimeError(f"wmrl: act_step inputs must live on {dev} (no CPU fallback)")
+        B = deter.shape[0]
+        fast = lambda t: t if (t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad) else _f32c(t)  # noqa: E731
+        e, h = fast(obs_embed), fast(deter)
+        if e.shape != (B, cfg.E) or h.shape != (B, cfg.D):
+            raise ValueError(f"act_step: obs_embed {tuple(e.shape)} / deter {tuple(h.shape)} do not match E={cfg.E}, D={cfg.D}")
+        n1, n2 = fast(noise_post), fast(noise_prior)
+        if n1.numel() != B * self.nlat or n2.numel() != B * self.nlat:
+            raise ValueError("act_step: noise tensors must hold one draw per latent element")
+        disc = cfg.variant == _lib.DISCRETE
+        widths = self.widths + ([cfg.A, cfg.A, 1] if sampling else [])
+        flat = torch.empty(B, sum(widths), device=dev)      # one allocation for all outputs
+        parts, o = [], 0
+        for wd in widths:
+            parts.append(flat[:, o:o + wd])
+            o += wd
+        action, post_s, post_a, deter_n, pri_s, pri_a = parts[:6]
+        post_b, pri_b = (None, None) if disc else (parts[6], parts[7])
+        d = self.dims.get(B)
+        if d is None:
+            d = self.dims[B] = cfg.dims(B, 1, 0, _lib.FP32)
+        smp = None
+        if sampling:
+            sw, sb, na = (fast(t) for t in sampling)
+            if sw.shape != (cfg.A, cfg.Ha) or na.numel() != B * cfg.A:
+                raise ValueError("act_step: sampling = (stddev.weight [A,Ha], stddev.bias [A], noise_action [B,A])")
+            smp = _lib.ActSampling(std_w=sw.data_ptr(), std_b=sb.data_ptr(), noise_action=na.data_ptr(),
+                                   act_mean=parts[-3].data_ptr(), act_std=parts[-2].data_ptr(), entropy=parts[-1].data_ptr())
+        if B > 0:
+            base, ld = flat.data_ptr(), flat.shape[1]
+            offs, o = [], 0
+            for wd in widths:
+                offs.append(base + 4 * o)
+                o += wd
+            with torch.cuda.device(dev):
+                rc = lib.wmrl_act_step(C.byref(d), C.byref(self.w), C.byref(self.aw), e.data_ptr(), h.data_ptr(), n1.data_ptr(),
+                                       n2.data_ptr(), offs[0], offs[1], offs[2], None if disc else offs[6], offs[3], offs[4],
+                                       offs[5], None if disc else offs[7], ld, C.byref(smp) if smp is not None else None,
+                                       torch.cuda.current_stream(dev).cuda_stream)
+            if rc:
+                _lib.check(rc, "wmrl_act_step")
+        out = (action, post_s, post_a, post_b, deter_n, pri_s, pri_a, pri_b)
+        if sampling:
+            out += (parts[-3], parts[-2], parts[-1].reshape(B))
+        return out
 
 
 def act_step(cfg: PathConfig, rssm_p: Sequence[torch.Tensor], actor_p: Sequence[torch.Tensor], bound: torch.Tensor,
@@ -636,58 +710,8 @@ def act_step(cfg: PathConfig, rssm_p: Sequence[torch.Tensor], actor_p: Sequence[
     (wmrl_act_step), fp32, no gradients.  -> (action, post_stoch, post_a, post_b, deter_next, prior_stoch, prior_a,
     prior_b); the *_b tensors are None for the discrete variant.  ``sampling`` = (stddev.weight, stddev.bias,
     noise_action[B,A]) switches the action to clamp(mean + std * noise, +-bound) (actor.py:54-59) and appends
-    (act_mean, act_std, entropy) to the result."""
-    lib = _lib.load()
-    dev = deter.device
-    if not (deter.is_cuda and obs_embed.is_cuda and rssm_p[0].is_cuda and actor_p[0].is_cuda):
-        _require_cuda(obs_embed, deter, *rssm_p, *actor_p)
-    B = deter.shape[0]
-    disc = cfg.variant == _lib.DISCRETE
-    S_in, W = cfg.S_in, cfg.dist_width
-    fast = lambda t: t if (t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad) else _f32c(t)  # noqa: E731
-    e, h = fast(obs_embed), fast(deter)
-    if e.shape != (B, cfg.E) or h.shape != (B, cfg.D):
-        raise ValueError(f"act_step: obs_embed {tuple(e.shape)} / deter {tuple(h.shape)} do not match E={cfg.E}, D={cfg.D}")
-    n1, n2 = fast(noise_post), fast(noise_prior)
-    nlat = S_in if disc else cfg.S
-    if n1.numel() != B * nlat or n2.numel() != B * nlat:
-        raise ValueError("act_step: noise tensors must hold one draw per latent element")
-    # one allocation for all outputs (the step is host-latency-bound at B = 1)
-    widths = [cfg.A, S_in, W, cfg.D, S_in, W] + ([] if disc else [W, W]) + ([cfg.A, cfg.A, 1] if sampling else [])
-    flat = torch.empty(B, sum(widths), device=dev)
-    parts, o = [], 0
-    for wd in widths:
-        parts.append(flat[:, o:o + wd])
-        o += wd
-    action, post_s, post_a, deter_n, pri_s, pri_a = parts[:6]
-    post_b, pri_b = (None, None) if disc else (parts[6], parts[7])
-    d = cfg.dims(B, 1, 0, _lib.FP32)
-    # the pointer structs are cached per parameter set
-    key = (cfg.La, bound.data_ptr()) + tuple(p.data_ptr() for p in rssm_p) + tuple(p.data_ptr() for p in actor_p)
-    ent = _ACT_PTRS.get(key)
-    if ent is None:
-        keep = [_f32c(p) for p in rssm_p], [_f32c(p) for p in actor_p]
-        if len(_ACT_PTRS) > 16:
-            _ACT_PTRS.clear()
-        ent = _ACT_PTRS[key] = (_rssm_ptrs(keep[0]), _actor_ptrs(keep[1], cfg.La, bound), keep)
-    w, aw = ent[0], ent[1]
-    smp = ent = None
-    if sampling:
-        sw, sb, na = (fast(t) for t in sampling)
-        if sw.shape != (cfg.A, cfg.Ha) or na.numel() != B * cfg.A:
-            raise ValueError("act_step: sampling = (stddev.weight [A,Ha], stddev.bias [A], noise_action [B,A])")
-        ent = torch.empty(B, device=dev)
-        smp = _lib.ActSampling(std_w=sw.data_ptr(), std_b=sb.data_ptr(), noise_action=na.data_ptr(),
-                               act_mean=parts[-3].data_ptr(), act_std=parts[-2].data_ptr(), entropy=ent.data_ptr())
-    if B > 0:
-        ld = flat.shape[1]
-        _native(dev, lib.wmrl_act_step, C.byref(d), C.byref(w), C.byref(aw), e.data_ptr(), h.data_ptr(), n1.data_ptr(),
-                n2.data_ptr(), action.data_ptr(), post_s.data_ptr(), post_a.data_ptr(), _lib.ptr(post_b),
-                deter_n.data_ptr(), pri_s.data_ptr(), pri_a.data_ptr(), _lib.ptr(pri_b), ld,
-                C.byref(smp) if smp is not None else None, _stream_ptr(dev))
-    if sampling:
-        return action, post_s, post_a, post_b, deter_n, pri_s, pri_a, pri_b, parts[-3], parts[-2], ent
-    return action, post_s, post_a, post_b, deter_n, pri_s, pri_a, pri_b
+    (act_mean, act_std, entropy) to the result.  (``RSSM.act_step`` keeps an ``ActStepPlan`` across calls instead.)"""
+    return ActStepPlan(cfg, rssm_p, actor_p, bound).run(obs_embed, deter, noise_post, noise_prior, sampling)
 
 
 class HeadLosses(torch.autograd.Function):

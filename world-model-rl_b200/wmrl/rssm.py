@@ -99,6 +99,9 @@ def _actor_bound(actor: nn.Module, A: int, device) -> torch.Tensor:
 
 
 import operator as _operator
+import weakref
+
+_ACT_PLANS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()   # RSSM module -> (actor ref, ActStepPlan, bound)
 
 _RSSM_GETTER = _operator.attrgetter(*[_lib.RSSM_KEYS[f] for f in _lib.RSSM_FIELDS])
 
@@ -187,26 +190,34 @@ class RSSMBase(nn.Module):
         are made here (N(0,1) / Exp(1), as generate_stoch_state does) unless passed in.  ``deterministic=False`` samples
         the action in the kernel from the actor's Normal head (actor.py:54-59: clamp(mean + std * eps, +-bound)) and
         returns (action, next_state, post, (act_mean, act_std, entropy))."""
-        from .functional import act_step as _act_step
-        device = next(actor.parameters()).device
-        La, Ha, actor_p = _actor_tensors(actor)
-        A = actor.mu.weight.shape[0]
-        cfg = self._config(A, Ha, La, getattr(actor, "action_scale", 5.0))
-        deter = state.deter_state.to(device)
+        from .functional import ActStepPlan
+        ent = _ACT_PLANS.get(self)
+        plan = ent[1] if (ent is not None and ent[0]() is actor and ent[2] is actor.bound) else None
+        if plan is None or not plan.valid():
+            device = next(actor.parameters()).device
+            La, Ha, actor_p = _actor_tensors(actor)
+            A = actor.mu.weight.shape[0]
+            cfg = self._config(A, Ha, La, getattr(actor, "action_scale", 5.0))
+            plan = ActStepPlan(cfg, self._rssm_tensors(), actor_p, _actor_bound(actor, A, device))
+            _ACT_PLANS[self] = (weakref.ref(actor), plan, actor.bound)
+        device, A = plan.dev, plan.cfg.A
+        deter = state.deter_state
+        if deter.device != device:
+            deter = deter.to(device)
+        if obs_embed.device != device:
+            obs_embed = obs_embed.to(device)
         B = deter.shape[0]
         if noise_post is None or noise_prior is None:
             both = self.draw_imagine_noise(2, B, device, generator)     # one launch for both draws
             noise_post = both[0] if noise_post is None else noise_post
             noise_prior = both[1] if noise_prior is None else noise_prior
-        bound = _actor_bound(actor, A, device)
         sampling = None
         if not deterministic:
             if noise_action is None:
                 noise_action = torch.randn(B, A, device=device, generator=generator)
             sampling = (actor.stddev.weight, actor.stddev.bias, noise_action)
         with torch.no_grad():
-            out = _act_step(cfg, self._rssm_tensors(), actor_p, bound, obs_embed if obs_embed.device == device else obs_embed.to(device),
-                            deter, noise_post, noise_prior, sampling)
+            out = plan.run(obs_embed, deter, noise_post, noise_prior, sampling)
         action, post_s, post_a, post_b, deter_n, pri_s, pri_a, pri_b = out[:8]
         if self.variant == _lib.DISCRETE:
             shp = (B, self.num_groups, self.stoch_size)
