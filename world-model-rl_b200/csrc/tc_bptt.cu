@@ -44,7 +44,9 @@ struct BwdParams {
   const uint8_t* stage_data;
   const uint8_t* stash_f;
   uint8_t* stash_g;
-  float* gh_scratch;        // [ntiles*128][Dp] fp32: carried dL/dh (and the GRU's direct z-path term in between)
+  float* gh_scratch;        // fp32 carried dL/dh (and the GRU's direct z-path term in between), one PANEL per (tile, CTA):
+                            // [Dp/4][64 rows][4] - a warp's float4 access to 4 columns of its 32 rows is 512 contiguous
+                            // bytes (the row-major form cost 32 LSU wavefronts per instruction)
   const float *deter_seq, *std_seq, *actions, *noise;
   const float *g_deter, *g_stoch, *g_mean, *g_std;   // upstream gradients of the sequence outputs (any may be null)
   float *g_deter0, *g_stoch0;
@@ -192,6 +194,11 @@ struct BCtx {
   uint8_t* gblk;        // gradient stash block of (tile, CTA, t), offset by row*16
 };
 
+// this thread's 4 floats of columns [col, col + 4) (col % 4 == 0) of its row in the fp32 scratch panel of its (tile, CTA)
+__device__ __forceinline__ float* scr4(const BCtx& c, int col) {
+  const BwdParams& p = *c.p;
+  return p.gh_scratch + (((size_t)(c.prow >> 6) * (size_t)(p.Dp >> 2) + (size_t)(col >> 2)) * kRowsB + (size_t)c.row) * 4;
+}
 __device__ __forceinline__ float4 ldcb4(uint32_t off) { return reinterpret_cast<const float4*>(cb_eparams)[off >> 2]; }
 __device__ __forceinline__ void rowpair_sync_b(int quarter) {
   asm volatile("bar.sync %0, %1;" ::"r"((quarter & 1) + 1), "r"(2 * kQ * 32) : "memory");
@@ -237,6 +244,39 @@ __device__ __forceinline__ void sample_bwd(const BCtx& c, bool use_carry, const 
   }
   st_chunk(c.smem_base + p.off_go + c.sidx * kPSB + c.row * 16, gm);
   st_chunk(c.smem_base + p.off_go + (p.Sp / 8 + c.sidx) * kPSB + c.row * 16, gr);
+}
+
+// same arithmetic with the five per-row inputs read in place (two columns at a time, packed at once): used by the embed
+// job, where the carried dL/ds is in shared memory and the rows are L2-resident
+__device__ __forceinline__ void sample_bwd_direct(const BCtx& c, int ts) {
+  const BwdParams& p = *c.p;
+  if (c.sidx >= p.Sp / 8) return;
+  const int col = c.sidx * 8;
+  const long long o = (c.b * (p.H + 1) + ts) * p.S + col;
+  const float* eps = p.noise + ((long long)(ts - 1) * p.B + c.b) * p.S + col;
+  uint32_t pm[4], pr[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float gm2[2], gr2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * j + e;
+      const bool ok = c.valid && col + i < p.S;
+      float gs;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gs) : "r"(c.smem_base + p.off_carry + ((col + i) * kRowsB + c.row) * 4));
+      gs += (ok && p.g_stoch) ? p.g_stoch[o + i] : 0.f;
+      const float sd = ok ? p.std_seq[o + i] : 1.f;
+      const float sig = 1.f - __expf(-(sd - 0.1f));
+      gm2[e] = ok ? ((p.g_mean ? p.g_mean[o + i] : 0.f) + gs) : 0.f;
+      gr2[e] = ok ? ((p.g_std ? p.g_std[o + i] : 0.f) + gs * eps[i]) * sig : 0.f;
+    }
+    pm[j] = pack_bf16x2(gm2[0], gm2[1]);
+    pr[j] = pack_bf16x2(gr2[0], gr2[1]);
+  }
+  const uint32_t d0 = c.smem_base + p.off_go + c.sidx * kPSB + c.row * 16;
+  const uint32_t d1 = c.smem_base + p.off_go + (p.Sp / 8 + c.sidx) * kPSB + c.row * 16;
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d0), "r"(pm[0]), "r"(pm[1]), "r"(pm[2]), "r"(pm[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d1), "r"(pr[0]), "r"(pr[1]), "r"(pr[2]), "r"(pr[3]) : "memory");
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
@@ -290,27 +330,6 @@ __device__ __forceinline__ void epib_elu(const BCtx& c, const JobDesc& jb, const
 // accumulator = g_hid W1 (prior-head path of dL/dh'); the scratch row holds the rest of dL/dh' (carried gradient +
 // upstream dL/ddeter[t+1], put there by the previous backward step / the tile initialisation).  Writes the gate
 // gradient panels [g_n | g_r | g_z | g_n r] and parks the direct term dL/dh' z in the scratch row.
-struct GruPre { uint4 g[4]; float hp[8], cr[8]; };
-__device__ __forceinline__ void gru_load(const BCtx& c, int sub, GruPre& pf) {
-  const BwdParams& p = *c.p;
-  const int col = c.hf * (p.Dp / 2) + sub * 8;
-  const uint8_t* f = c.fblk + (col / 8) * kStashChunk;
-  pf.g[0] = ldg16(f + p.sl.gr);
-  pf.g[1] = ldg16(f + p.sl.gz);
-  pf.g[2] = ldg16(f + p.sl.gn);
-  pf.g[3] = ldg16(f + p.sl.ghn);
-  const float* scr = p.gh_scratch + c.prow * p.Dp + col;
-  const float4 a = *reinterpret_cast<const float4*>(scr), b4 = *reinterpret_cast<const float4*>(scr + 4);
-  pf.cr[0] = a.x; pf.cr[1] = a.y; pf.cr[2] = a.z; pf.cr[3] = a.w; pf.cr[4] = b4.x; pf.cr[5] = b4.y; pf.cr[6] = b4.z; pf.cr[7] = b4.w;
-  const float* hrow = p.deter_seq + (c.b * (p.H + 1) + c.t) * p.D + col;
-  if (c.valid && col + 8 <= p.D && (p.D & 3) == 0) {
-    const float4 h0 = *reinterpret_cast<const float4*>(hrow), h1 = *reinterpret_cast<const float4*>(hrow + 4);
-    pf.hp[0] = h0.x; pf.hp[1] = h0.y; pf.hp[2] = h0.z; pf.hp[3] = h0.w; pf.hp[4] = h1.x; pf.hp[5] = h1.y; pf.hp[6] = h1.z; pf.hp[7] = h1.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) pf.hp[i] = (c.valid && col + i < p.D) ? hrow[i] : 0.f;
-  }
-}
 // L2 prefetch (no register cost) of the fp32 rows the LATER jobs of this step read: the upstream deter gradient of
 // index t (carry job), the sample-backward inputs of index t and the actions (embed job) - issued ~15-30K cycles ahead
 __device__ __forceinline__ void prefetch_step_rows(const BCtx& c) {
@@ -334,7 +353,14 @@ __device__ __forceinline__ void prefetch_step_rows(const BCtx& c) {
   }
   if (c.sidx == 0) prefetch_l2(p.actions + (c.b * p.H + c.t) * p.A);
 }
-__device__ __forceinline__ void epib_gru(const BCtx& c, const JobDesc& jb, GruPre& pf) {
+__device__ __forceinline__ uint32_t u4c(const uint4& u, int j) { return j == 0 ? u.x : (j == 1 ? u.y : (j == 2 ? u.z : u.w)); }
+__device__ __forceinline__ float f4c(const float4& u, int j) { return j == 0 ? u.x : (j == 1 ? u.y : (j == 2 ? u.z : u.w)); }
+// Register-lean form: nothing is held across the accumulator wait (everything this epilogue reads is L2-resident: the
+// stash block was bulk-prefetched a step ahead, the scratch row was written by this thread one step earlier, the h row
+// prefetched by the previous carry epilogue), the recorded gates stay PACKED (bf16 pairs) until the column pair that
+// needs them (h_t comes from the recorded bf16 [h | s] panel), and every output pair is packed as soon as it exists - the previous form kept 56 unpacked inputs and 40
+// outputs live and spilled ~100 registers per sub-group to local memory (L2 round trips: the L1D is ~1 KB here).
+__device__ __forceinline__ void epib_gru(const BCtx& c, const JobDesc& jb) {
   const BwdParams& p = *c.p;
   const int hw = p.Dp / 2;
   prefetch_step_rows(c);
@@ -343,32 +369,48 @@ __device__ __forceinline__ void epib_gru(const BCtx& c, const JobDesc& jb, GruPr
 #pragma unroll 1
   for (int sub = c.q; sub * 8 < hw; sub += kQ) {
     const int col = c.hf * hw + sub * 8;
-    float acc[8], r[8], z[8], n[8], hn[8];
+    float acc[8];
     tmem_ld8(c.tmem_lane + jb.tmem_col + sub * 8, acc);
-    if (sub != c.q) gru_load(c, sub, pf);      // the first sub-group was fetched before the accumulator wait
-    unpack8(pf.g[0], r); unpack8(pf.g[1], z); unpack8(pf.g[2], n); unpack8(pf.g[3], hn);
+    const uint8_t* f = c.fblk + (col / 8) * kStashChunk;
+    const uint4 ur = ldg16(f + p.sl.gr), uz = ldg16(f + p.sl.gz), un = ldg16(f + p.sl.gn), uh = ldg16(f + p.sl.ghn);
+    float* const scr_a = scr4(c, col);
+    float* const scr_b = scr4(c, col + 4);
+    const float4 cr0 = *reinterpret_cast<const float4*>(scr_a), cr1 = *reinterpret_cast<const float4*>(scr_b);
+    const uint4 up = ldg16(f + p.sl.feat);   // h_t of these columns from the recorded [h | s] panel (bf16), not the fp32 rows
     tmem_ld_wait();
-    float on[8], orr[8], oz[8], oh[8], od[8];
+    uint32_t pn[4], pr[4], pz[4], ph[4];
+    float od[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float gh = acc[i] + pf.cr[i];
-      const float gn = gh * (1.f - z[i]);
-      const float gz = gh * (pf.hp[i] - n[i]);
-      od[i] = gh * z[i];
-      const float gnp = gn * (1.f - n[i] * n[i]);
-      on[i] = gnp;
-      oz[i] = gz * z[i] * (1.f - z[i]);
-      oh[i] = gnp * r[i];
-      orr[i] = gnp * hn[i] * r[i] * (1.f - r[i]);
+    for (int j = 0; j < 4; ++j) {     // columns 2j, 2j + 1
+      const uint32_t wr = u4c(ur, j), wz = u4c(uz, j), wn = u4c(un, j), wh = u4c(uh, j), wp = u4c(up, j);
+      float o_n[2], o_r[2], o_z[2], o_h[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = 2 * j + e;
+        const float r = __uint_as_float(e ? (wr & 0xFFFF0000u) : (wr << 16));
+        const float z = __uint_as_float(e ? (wz & 0xFFFF0000u) : (wz << 16));
+        const float n = __uint_as_float(e ? (wn & 0xFFFF0000u) : (wn << 16));
+        const float hn = __uint_as_float(e ? (wh & 0xFFFF0000u) : (wh << 16));
+        const float cr = i < 4 ? f4c(cr0, i) : f4c(cr1, i - 4);
+        const float hp = __uint_as_float(e ? (wp & 0xFFFF0000u) : (wp << 16));
+        const float gh = acc[i] + cr;
+        const float gnp = gh * (1.f - z) * (1.f - n * n);
+        od[i] = gh * z;
+        o_n[e] = gnp;
+        o_z[e] = gh * (hp - n) * z * (1.f - z);
+        o_h[e] = gnp * r;
+        o_r[e] = gnp * hn * r * (1.f - r);
+      }
+      pn[j] = pack_bf16x2(o_n[0], o_n[1]); pr[j] = pack_bf16x2(o_r[0], o_r[1]);
+      pz[j] = pack_bf16x2(o_z[0], o_z[1]); ph[j] = pack_bf16x2(o_h[0], o_h[1]);
     }
     const uint32_t dst = gate + (col / 8) * kPSB;
-    st_chunk(dst, on);
-    st_chunk(dst + gstride, orr);
-    st_chunk(dst + 2 * gstride, oz);
-    st_chunk(dst + 3 * gstride, oh);
-    float* scr = p.gh_scratch + c.prow * p.Dp + col;
-    *reinterpret_cast<float4*>(scr) = make_float4(od[0], od[1], od[2], od[3]);
-    *reinterpret_cast<float4*>(scr + 4) = make_float4(od[4], od[5], od[6], od[7]);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pn[0]), "r"(pn[1]), "r"(pn[2]), "r"(pn[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + gstride), "r"(pr[0]), "r"(pr[1]), "r"(pr[2]), "r"(pr[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 2 * gstride), "r"(pz[0]), "r"(pz[1]), "r"(pz[2]), "r"(pz[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 3 * gstride), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+    *reinterpret_cast<float4*>(scr_a) = make_float4(od[0], od[1], od[2], od[3]);
+    *reinterpret_cast<float4*>(scr_b) = make_float4(od[4], od[5], od[6], od[7]);
   }
 }
 
@@ -397,9 +439,8 @@ __device__ __forceinline__ void carry_init(const BCtx& c) {
     const int col = c.hf * hw + sub * 8;
     float up[8];
     load_g_deter(c, p.H, col, up);
-    float* scr = p.gh_scratch + c.prow * p.Dp + col;
-    *reinterpret_cast<float4*>(scr) = make_float4(up[0], up[1], up[2], up[3]);
-    *reinterpret_cast<float4*>(scr + 4) = make_float4(up[4], up[5], up[6], up[7]);
+    *reinterpret_cast<float4*>(scr4(c, col)) = make_float4(up[0], up[1], up[2], up[3]);
+    *reinterpret_cast<float4*>(scr4(c, col + 4)) = make_float4(up[4], up[5], up[6], up[7]);
   }
 }
 
@@ -413,9 +454,8 @@ __device__ __forceinline__ void carry_prefetch(const BCtx& c, CarryPre& pf) {
   for (int o = 0; o < kSubMax; ++o) {
     const int sub = c.q + o * kQ;
     if (sub * 8 < hw) {
-      const float* scr = p.gh_scratch + c.prow * p.Dp + c.hf * hw + sub * 8;
-      pf.s[o][0] = *reinterpret_cast<const float4*>(scr);
-      pf.s[o][1] = *reinterpret_cast<const float4*>(scr + 4);
+      pf.s[o][0] = *reinterpret_cast<const float4*>(scr4(c, c.hf * hw + sub * 8));
+      pf.s[o][1] = *reinterpret_cast<const float4*>(scr4(c, c.hf * hw + sub * 8 + 4));
     }
   }
 }
@@ -434,11 +474,8 @@ __device__ __forceinline__ void epib_carry(const BCtx& c, const JobDesc& jb, con
       acc[0] += pf.s[o][0].x + up[0]; acc[1] += pf.s[o][0].y + up[1]; acc[2] += pf.s[o][0].z + up[2]; acc[3] += pf.s[o][0].w + up[3];
       acc[4] += pf.s[o][1].x + up[4]; acc[5] += pf.s[o][1].y + up[5]; acc[6] += pf.s[o][1].z + up[6]; acc[7] += pf.s[o][1].w + up[7];
       if (c.t > 0) {
-        float* scr = p.gh_scratch + c.prow * p.Dp + col;
-        *reinterpret_cast<float4*>(scr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(scr + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        // the previous step's GRU backward reads h_{t-1} of these columns: pull the sector into L2 now
-        if (c.valid && col < p.D) prefetch_l2(p.deter_seq + (c.b * (p.H + 1) + c.t - 1) * p.D + col);
+        *reinterpret_cast<float4*>(scr4(c, col)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(scr4(c, col + 4)) = make_float4(acc[4], acc[5], acc[6], acc[7]);
       } else if (c.valid) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -451,10 +488,9 @@ __device__ __forceinline__ void epib_carry(const BCtx& c, const JobDesc& jb, con
 // ---- [dL/ds_t | dL/da_t] = g_x W_e.  dL/ds_t is carried (shared memory) or, at t = 0, the start-state gradient;
 // dL/da_t goes through the tanh squash (actor.py:49-50: a = tanh(mu / scale) bound) into the g_mu panel + stash.
 // Then - all warps - the Gaussian-sample backward of step t-1, which needs the carried dL/ds.
-struct EmbPre { SamplePre sp; float act[8]; };
+struct EmbPre { float act[8]; };
 __device__ __forceinline__ void emb_prefetch(const BCtx& c, const JobDesc& jb, EmbPre& pf) {
   const BwdParams& p = *c.p;
-  if (c.t > 0) sample_load(c, c.t, pf.sp);
   // the (single) sub-group of this thread that holds action columns, if any
   const int hw = jb.n / 2;
 #pragma unroll
@@ -472,6 +508,12 @@ __device__ __forceinline__ void emb_prefetch(const BCtx& c, const JobDesc& jb, E
 __device__ __forceinline__ void epib_emb(const BCtx& c, const JobDesc& jb, const EmbPre& pf) {
   const BwdParams& p = *c.p;
   const int hw = jb.n / 2;
+  // the sample-backward inputs of step t-1 (five 8-column rows, L2-resident since the GRU job's prefetch) are requested
+  // first, so that their round trip overlaps the accumulator read-out below
+  SamplePre sp;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sp.gs[i] = 0.f; sp.gmu[i] = 0.f; sp.gsd[i] = 0.f; sp.e[i] = 0.f; sp.sd[i] = 1.f; }
+  if (c.t > 0) sample_load(c, c.t, sp);
   for (int sub = c.q; sub * 8 < hw; sub += kQ) {
     const int col = c.hf * hw + sub * 8;
     float acc[8];
@@ -509,8 +551,10 @@ __device__ __forceinline__ void epib_emb(const BCtx& c, const JobDesc& jb, const
     }
   }
   if (c.t > 0) {
+    // the sample-backward inputs are loaded HERE, not before the accumulator wait: holding their 40 registers across the
+    // embed epilogue spilled them to local memory; the rows were pulled into L2 by prefetch_step_rows during the GRU job
     epi_sync_all();
-    sample_bwd(c, true, pf.sp);
+    sample_bwd(c, true, sp);
   }
 }
 
@@ -843,12 +887,6 @@ __global__ void __launch_bounds__(kThreadsB, 1) tc_bptt_kernel(const BwdParams p
         sample_bwd(c, false, sp);
       }
       carry_init(c);
-      // h of the last step for the first GRU backward (later steps: the carry job prefetches it)
-      if (c.valid)
-        for (int sub = c.q; sub * 8 < p.Dp / 2; sub += kQ) {
-          const int col = c.hf * (p.Dp / 2) + sub * 8;
-          if (col < p.D) prefetch_l2(p.deter_seq + (c.b * (p.H + 1) + p.H - 1) * p.D + col);
-        }
       fence_proxy_async_smem();
       WMRL_JOB_DONE_B(job);
       ++job;
@@ -875,12 +913,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) tc_bptt_kernel(const BwdParams p
             if (kTrace && tr) p.trace[((ti * p.njobs) + jb_i) * 4 + 2] = clock64();
             epib_elu(c, jb, pf);
           } else if (jb.type == JB_GRUB) {
-            GruPre pf;
-            if (c.q * 8 < p.Dp / 2) gru_load(c, c.q, pf);
             mbar_wait_backoff_quiet(accf_bar(job), (job >> 1) & 1u);
             tc_fence_after();
             if (kTrace && tr) p.trace[((ti * p.njobs) + jb_i) * 4 + 2] = clock64();
-            epib_gru(c, jb, pf);
+            epib_gru(c, jb);
           } else if (jb.type == JB_CARRY) {
             // (its scratch rows were written by this thread in the GRU epilogue of this step: program order)
             CarryPre pf;
