@@ -372,42 +372,6 @@ __device__ __forceinline__ void lepi_gru(const LCtx& c, const LGruPre& pf) {
   }
 }
 
-// Gaussian head (rssm.py:179-181): TMEM [mean (Sp) | raw (Sp)], parameters [b_mean | b_raw]; 8-column groups
-__device__ __forceinline__ void lepi_sample_cont(const LCtx& c) {
-  const LayerArgs& p = *c.p;
-  const long long T1 = p.H + 1;
-  const long long o = (c.b * T1 + p.t + 1) * p.S;
-  for (int g = c.q; g < p.Sp / 8; g += 4) {
-    const int col = g * 8;
-    float m[8], s[8], sd[8], st[8];
-    tmem_ld8(c.tmem_lane + col, m);
-    tmem_ld8(c.tmem_lane + p.Sp + col, s);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 8; i += 4) {
-      const float4 bm = lds4(c.prm + (col + i) * 4), bs = lds4(c.prm + (p.Sp + col + i) * 4);
-      const float bmv[4] = {bm.x, bm.y, bm.z, bm.w}, bsv[4] = {bs.x, bs.y, bs.z, bs.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool in = c.valid && col + i + e < p.S;
-        const float mean = m[i + e] + bmv[e];
-        const float raw = s[i + e] + bsv[e];
-        const float sp = fmaxf(raw, 0.f) + __logf(1.f + ex2_fast(-fabsf(raw) * 1.4426950408889634f));
-        const float ee = in ? p.noise[((long long)p.t * p.B + c.b) * p.S + col + i + e] : 0.f;
-        m[i + e] = mean;
-        sd[i + e] = sp + 0.1f;
-        st[i + e] = in ? fmaf(sd[i + e], ee, mean) : 0.f;
-        if (in) {
-          p.dist_a[o + col + i + e] = mean;
-          p.dist_b[o + col + i + e] = sd[i + e];
-          p.stoch_seq[o + col + i + e] = st[i + e];
-        }
-      }
-    }
-    st_chunk_g(c.out_row + (size_t)g * kLTileChunk, st);
-  }
-}
-
 // Categorical straight-through head (rssm.py:222-227, state/discrete.py:20-37).  A column tile holds n / S groups of
 // S classes; warp q owns the 32-column blocks q, q+4, ...; a thread holds all classes of its groups in registers.
 //   p = Categorical(logits).probs = softmax(logits - logsumexp(logits));  idx = first argmax(p / q), q ~ Exp(1)
@@ -819,6 +783,62 @@ __device__ __forceinline__ void lepib_post(const LCtx& c) {
         store_rows32(c, p.f3 + (b0 * (p.H + 1) + p.t + 1) * E + col, (long long)(p.H + 1) * E, nr, min(min(32, E - col), p.n - blk * 32), acc);
       }
     }
+  }
+}
+
+// Gaussian head (rssm.py:179-181): TMEM [mean (Sp) | raw (Sp)], parameters [b_mean | b_raw].  Warp q owns the 32-column
+// blocks q, q + 4, ...; the noise rows come in and mean / std / sample rows go out through the staging transpose (4 rows x
+// 128 contiguous bytes per warp-level access; the row-per-thread scalar form cost ~50 us per step at 65 536 rows).
+__device__ __forceinline__ void lepi_sample_cont(const LCtx& c) {
+  const LayerArgs& p = *c.p;
+  const long long T1 = p.H + 1;
+  const long long b0 = c.b - c.lane;
+  const int nr = (int)max(0LL, min(32LL, (long long)p.B - b0));
+  for (int blk = c.q; blk * 32 < p.Sp; blk += 4) {
+    const int col = blk * 32;
+    const int nc = min(32, p.S - col);
+    const long long row0 = (b0 * T1 + p.t + 1) * p.S + col;
+    float ee[32];
+    load_rows32(c, p.noise + ((long long)p.t * p.B + b0) * p.S + col, p.S, nr, nc, ee);
+    {   // std = softplus(raw) + 0.1 -> out; ee <- std * eps   (two 32-float arrays live at a time: 96-register cap)
+      float sd[32];
+      tmem_ld32(c.tmem_lane + p.Sp + col, sd);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col + i < p.Sp) bs = lds4(c.prm + (p.Sp + col + i) * 4);
+        const float bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float raw = sd[i + e] + bsv[e];
+          sd[i + e] = fmaxf(raw, 0.f) + __logf(1.f + ex2_fast(-fabsf(raw) * 1.4426950408889634f)) + 0.1f;
+          ee[i + e] *= sd[i + e];
+        }
+      }
+      store_rows32(c, p.dist_b + row0, T1 * p.S, nr, nc, sd);
+    }
+    {   // mean -> out; sample = mean + std * eps -> out and the next step's panel (zeros past S / past B)
+      float m[32];
+      tmem_ld32(c.tmem_lane + col, m);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 bm = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col + i < p.Sp) bm = lds4(c.prm + (col + i) * 4);
+        const float bmv[4] = {bm.x, bm.y, bm.z, bm.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          m[i + e] += bmv[e];
+          ee[i + e] = (c.valid && col + i + e < p.S) ? ee[i + e] + m[i + e] : 0.f;
+        }
+      }
+      store_rows32(c, p.dist_a + row0, T1 * p.S, nr, nc, m);
+    }
+    store_rows32(c, p.stoch_seq + row0, T1 * p.S, nr, nc, ee);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (col + k * 8 < p.Sp) st_chunk_g(c.out_row + (size_t)(col / 8 + k) * kLTileChunk, ee + k * 8);
   }
 }
 
