@@ -1579,8 +1579,11 @@ struct LPlan {
   std::vector<LLayerH> blayers;   // backward chain of one step (after the sample backward)
   // the same chains with every LayerNorm layer split into `csplit` column tiles (one cluster per row tile, statistics
   // exchanged through DSMEM): used when a call has so few row tiles that one CTA per row tile leaves most SMs idle
-  std::vector<LLayerH> layers_s, blayers_s;
-  int csplit = 0;
+  std::vector<LLayerH> layers_s, blayers_s;   // split over kLMaxSplit CTAs: few row tiles
+  // split over CTA PAIRS for wide blocks (Ha > 256) at ANY row count: a 512-column block fills TMEM, so its epilogue was
+  // exposed; two 256-column halves double-buffer their accumulators and the next item's MMAs run under the epilogue
+  std::vector<LLayerH> layers_p, blayers_p;
+  int csplit = 0, cpair = 0;
   int Dp = 0, Sip = 0, Sp = 0, Hdp = 0, Ha = 0, Pp = 0, Ep = 0;
 };
 
@@ -1900,17 +1903,16 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
     lp.blayers.push_back(L);
   }
   // ====================================================================== LayerNorm layers split over a cluster
-  if (d.Ha % (32 * kLMaxSplit) == 0) {
+  auto make_split = [&](int f, std::vector<LLayerH>& fl, std::vector<LLayerH>& bl) {
     constexpr float kLog2e = 1.4426950408889634f;
-    const int ns = d.Ha / kLMaxSplit;
-    lp.csplit = kLMaxSplit;
-    lp.layers_s = lp.layers;
-    lp.blayers_s = lp.blayers;
-    for (LLayerH& L : lp.layers_s) {
+    const int ns = d.Ha / f;
+    fl = lp.layers;
+    bl = lp.blayers;
+    for (LLayerH& L : fl) {
       if (L.type != LE_LN_ELU) continue;
       const int l = L.layer;
       const float* lw = aw ? aw->lin_w[l] : nul;
-      L.NT = kLMaxSplit; L.n = ns; L.dbuf = 1; L.kc = kc_for(ns); L.csplit = kLMaxSplit;
+      L.NT = f; L.n = ns; L.dbuf = 1; L.kc = kc_for(ns); L.csplit = f;
       L.w_off = pk.data_bytes;
       for (int j = 0; j < L.NT; ++j) {
         const size_t t0 = pk.data_bytes;
@@ -1932,10 +1934,10 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
       }
       L.ep_floats = 3u * ns;
     }
-    for (LLayerH& L : lp.blayers_s) {
+    for (LLayerH& L : bl) {
       if (L.type != LB_LN) continue;
       const int l = L.layer;
-      L.NT = kLMaxSplit; L.n = ns; L.dbuf = 1; L.kc = kc_for(ns); L.csplit = kLMaxSplit;
+      L.NT = f; L.n = ns; L.dbuf = 1; L.kc = kc_for(ns); L.csplit = f;
       L.w_off = pk.data_bytes;
       for (int j = 0; j < L.NT; ++j) {
         const size_t t0 = pk.data_bytes;
@@ -1955,8 +1957,10 @@ static LPlan tcl_make_plan(const Dims& d, const wmrl_rssm_params* w, const wmrl_
       }
       L.ep_floats = 3u * ns;
     }
-  }
-  for (const std::vector<LLayerH>* v : {&lp.layers, &lp.blayers, &lp.layers_s, &lp.blayers_s})
+  };
+  if (d.Ha % (32 * kLMaxSplit) == 0) { lp.csplit = kLMaxSplit; make_split(kLMaxSplit, lp.layers_s, lp.blayers_s); }
+  if (d.Ha > 256 && d.Ha % 64 == 0) { lp.cpair = 2; make_split(2, lp.layers_p, lp.blayers_p); }
+  for (const std::vector<LLayerH>* v : {&lp.layers, &lp.blayers, &lp.layers_s, &lp.blayers_s, &lp.layers_p, &lp.blayers_p})
     for (const LLayerH& L : *v) {
       if (L.ep_floats * 4 > kLParamBytes || (L.ep_floats & 3)) return lp;
       for (int s = 0; s < L.nseg; ++s)
@@ -2047,7 +2051,7 @@ int tcl_pack_weights(const Dims& d, const wmrl_rssm_params* w, const wmrl_actor_
   return tc_pack_plan(lp.pk, (uint8_t*)packed, st);
 }
 
-static int g_max_clusters[64] = {0};   // co-resident clusters of kLMaxSplit layer-kernel CTAs (set by tcl_device_setup)
+static int g_max_clusters[64][kLMaxSplit + 1] = {};   // [device][f]: co-resident clusters of f layer-kernel CTAs (tcl_device_setup)
 static int tcl_device_setup(int& nsm) {
   static std::mutex mu;
   static bool attr_set[64] = {false};
@@ -2065,19 +2069,19 @@ static int tcl_device_setup(int& nsm) {
       }
     WMRL_CUDA_OK(cudaFuncSetAttribute(tcl_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWg2Smem));
     WMRL_CUDA_OK(cudaDeviceGetAttribute(&sm_cached[dev], cudaDevAttrMultiProcessorCount, dev));
-    {
+    for (int f : {2, kLMaxSplit}) {
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((unsigned)(sm_cached[dev] / kLMaxSplit * kLMaxSplit));
+      cfg.gridDim = dim3((unsigned)(sm_cached[dev] / f * f));
       cfg.blockDim = dim3(kLThreads);
       cfg.dynamicSmemBytes = kLSmemBytes;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = kLMaxSplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      attr[0].val.clusterDim.x = (unsigned)f; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       int nc = 0;
       if (cudaOccupancyMaxActiveClusters(&nc, layer_kernel_for(LE_LN_ELU, 4), &cfg) != cudaSuccess) { nc = 0; cudaGetLastError(); }
-      g_max_clusters[dev] = nc;
+      g_max_clusters[dev][f] = nc;
     }
     attr_set[dev] = true;
   }
@@ -2085,6 +2089,24 @@ static int tcl_device_setup(int& nsm) {
   return 0;
 }
 
+static int tcl_max_clusters(int f) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || f < 2 || f > kLMaxSplit) return 0;
+  return g_max_clusters[dev][f];
+}
+// which tiling of the LayerNorm layers a call with MT row tiles uses: kLMaxSplit-CTA clusters when every row tile's
+// cluster is co-resident (few row tiles), CTA pairs for wide blocks otherwise, 0 = one CTA per row tile
+static int tcl_split_choice(int csplit, int cpair, int MT) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("WMRL_LN_SPLIT"); off = (e && e[0] == '0') ? 1 : 0; }
+  if (off) return 0;
+  if (csplit > 1 && MT <= tcl_max_clusters(csplit)) return csplit;
+  // pairs re-read the block's input panel from both CTAs: a win while that panel is L2-resident (<= 256 row tiles =
+  // 32 MB at 512 columns; measured: configs[4] shard 20.2 -> 19.1 ms forward), a loss once it streams from HBM
+  // (983 040-row heads: 5.9 -> 6.3 ms)
+  if (cpair > 1 && MT <= 256 && tcl_max_clusters(cpair) > 0) return cpair;
+  return 0;
+}
 struct LCall {            // what the launch helper needs to resolve a layer description into kernel arguments
   const LPlan* lp; const LMem* m; const Dims* d;
   uint8_t* ws; uint8_t* saved;
@@ -2127,8 +2149,8 @@ static int tcl_launch(const LCall& c, const LLayerH& L, LayerArgs& a, const int*
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (L.csplit > 1) {   // one cluster per row tile; the caller checked that all of them are co-resident
-    cfg.gridDim = dim3((unsigned)items);
+  if (L.csplit > 1) {   // clusters of csplit CTAs, all co-resident (single wave): persistent over the row tiles
+    cfg.gridDim = dim3((unsigned)(std::min(c.MT, tcl_max_clusters(L.csplit)) * L.csplit));
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = (unsigned)L.csplit; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.numAttrs = 2;
@@ -2136,15 +2158,6 @@ static int tcl_launch(const LCall& c, const LLayerH& L, LayerArgs& a, const int*
   WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, layer_kernel_for(L.type, d.S), a));
   return 0;
 }
-// few row tiles: the LayerNorm layers run split over clusters when every row tile's cluster is co-resident (single wave)
-static bool tcl_use_split(const LPlan& lp, int MT) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
-  static int off = -1;
-  if (off < 0) { const char* e = getenv("WMRL_LN_SPLIT"); off = (e && e[0] == '0') ? 1 : 0; }
-  return !off && lp.csplit > 1 && MT <= g_max_clusters[dev];
-}
-
 int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, const float* stoch0, const float* noise,
                     float* deter_seq, float* stoch_seq, float* dist_a, float* dist_b, float* actions, int32_t* idx,
                     void* saved, void* ws, cudaStream_t st) {
@@ -2161,7 +2174,8 @@ int tcl_imagine_fwd(const Dims& d, const void* packed, const float* deter0, cons
   tcl_init_kernel<<<dim3(8, c.MT), 256, 0, st>>>(deter0, stoch0, deter_seq, stoch_seq, c.at(F_H, 0), c.at(F_S, 0), d.B, d.T,
                                                  d.D, d.S_in, lp.Dp, lp.Sip);
   WMRL_CUDA_OK(cudaGetLastError());
-  const std::vector<LLayerH>& fl = tcl_use_split(lp, c.MT) ? lp.layers_s : lp.layers;
+  const int sc = tcl_split_choice(lp.csplit, lp.cpair, c.MT);
+  const std::vector<LLayerH>& fl = sc == 0 ? lp.layers : (sc == 2 ? lp.layers_p : lp.layers_s);
   for (int t = 0; t < d.T; ++t) {
     // step index of each field: recorded fields are indexed by t (h, s: t -> t + 1); otherwise one entry (h: parity)
     auto step_of = [&](int buf) {
@@ -2225,7 +2239,8 @@ int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const
     tcl_carry_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(carry_h, g_deter_seq, d.B, T, d.D, lp.Dp, n);
     WMRL_CUDA_OK(cudaGetLastError());
   }
-  const std::vector<LLayerH>& bl = tcl_use_split(lp, MT) ? lp.blayers_s : lp.blayers;
+  const int sc = tcl_split_choice(lp.csplit, lp.cpair, MT);
+  const std::vector<LLayerH>& bl = sc == 0 ? lp.blayers : (sc == 2 ? lp.blayers_p : lp.blayers_s);
   for (int t = T - 1; t >= 0; --t) {
     // dL/d(head output) of the step that produced state t+1
     {
@@ -2965,7 +2980,55 @@ static LPlan tcm_make_plan(const MlpShape& m, const wmrl_mlp_params* w) {
     L.ep_off = add_vec(pk, nul, nul, 0, 0, 16); L.ep_floats = 0;
     lp.blayers.push_back(L);
   }
-  for (const std::vector<LLayerH>* v : {&lp.layers, &lp.blayers})
+  // ---- wide blocks (hidden > 256): the same layers as CTA pairs of hidden / 2 columns each (see LPlan::layers_p)
+  if (m.Hh > 256 && m.Hh % 64 == 0) {
+    const int ns = m.Hh / 2;
+    lp.cpair = 2;
+    lp.layers_p = lp.layers;
+    lp.blayers_p = lp.blayers;
+    for (LLayerH& L : lp.layers_p) {
+      if (L.type != fwd_type) continue;
+      const int l = L.layer;
+      const int K = l == 0 ? m.F : m.Hh, Kp = l == 0 ? m.Fp : m.Hh;
+      L.NT = 2; L.n = ns; L.dbuf = 1; L.kc = kc_for(ns); L.csplit = 2;
+      L.w_off = pk.data_bytes;
+      for (int j = 0; j < 2; ++j) {
+        const size_t t0 = pk.data_bytes;
+        L.seg[0] = {l == 0 ? M_X : M_Y0 + l - 1, Kp / 16, ns, 0, 0, 1, 0u};
+        l_add_pack(lp, RowSpec(j * ns, ns, ns), w ? w->lin_w[l] : nul, K, 0, K, Kp);
+        L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+        const uint32_t at = add_vec(pk, w ? w->lin_b[l] : nul, nul, j * ns, ns, ns);
+        add_vec(pk, w ? w->ln_g[l] : nul, nul, j * ns, ns, ns, kLog2e);
+        add_vec(pk, w ? w->ln_b[l] : nul, nul, j * ns, ns, ns, kLog2e);
+        if (j == 0) L.ep_off = at;
+      }
+      L.ep_floats = 3u * ns;
+    }
+    for (LLayerH& L : lp.blayers_p) {
+      if (L.type != bwd_type) continue;
+      const int l = L.layer;
+      L.NT = 2; L.n = ns; L.dbuf = 1; L.kc = kc_for(ns); L.csplit = 2;
+      L.w_off = pk.data_bytes;
+      for (int j = 0; j < 2; ++j) {
+        const size_t t0 = pk.data_bytes;
+        RowSpec rs(j * ns, ns, ns);
+        if (l == m.L - 1) {
+          L.seg[0] = {M_GOUT, 1, ns, 0, 0, 1, 0u};
+          l_add_pack_t(lp, rs, w ? w->out_w : nul, m.Hh, {{0, m.O, 16}});
+        } else {
+          L.seg[0] = {M_GP0 + l + 1, m.Hh / 16, ns, 0, 0, 1, 0u};
+          l_add_pack_t(lp, rs, w ? w->lin_w[l + 1] : nul, m.Hh, {{0, m.Hh, m.Hh}});
+        }
+        L.w_tile_bytes = (uint32_t)(pk.data_bytes - t0);
+        const uint32_t at = add_vec(pk, w ? w->ln_g[l] : nul, nul, j * ns, ns, ns, kLog2e);
+        add_vec(pk, w ? w->ln_b[l] : nul, nul, j * ns, ns, ns, kLog2e);
+        add_vec(pk, w ? w->ln_g[l] : nul, nul, j * ns, ns, ns);
+        if (j == 0) L.ep_off = at;
+      }
+      L.ep_floats = 3u * ns;
+    }
+  }
+  for (const std::vector<LLayerH>* v : {&lp.layers, &lp.blayers, &lp.layers_p, &lp.blayers_p})
     for (const LLayerH& L : *v) {
       if (L.ep_floats * 4 > kLParamBytes || (L.ep_floats & 3)) return lp;
       for (int s = 0; s < L.nseg; ++s)
@@ -3074,7 +3137,7 @@ static int tcm_launch(const MlpCall& c, const LLayerH& L, LayerArgs& a) {
   a.w = c.data + L.w_off; a.w_tile_bytes = L.w_tile_bytes;
   a.ep = c.ep + L.ep_off; a.ep_floats = L.ep_floats;
   a.kc = L.kc; a.dbuf = L.dbuf; a.type = L.type; a.n = L.n; a.NT = L.NT; a.MT = m.MT;
-  a.csplit = 0; a.ln_width = L.n;
+  a.csplit = L.csplit; a.ln_width = L.csplit > 1 ? L.n * L.NT : L.n;
   a.B = (int)m.R; a.H = 1; a.t = 0; a.D = m.F; a.A = m.O;
   if (L.out >= 0) { a.out = c.at(L.out); a.out_tile_bytes = c.mm->tile[L.out]; a.out_cols = m.Hh; }
   const int items = m.MT * L.NT;
@@ -3083,11 +3146,17 @@ static int tcm_launch(const MlpCall& c, const LLayerH& L, LayerArgs& a) {
   cfg.blockDim = dim3(kLThreads);
   cfg.dynamicSmemBytes = kLSmemBytes;
   cfg.stream = c.st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (L.csplit > 1) {
+    cfg.gridDim = dim3((unsigned)(std::min(m.MT, tcl_max_clusters(L.csplit)) * L.csplit));
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)L.csplit; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   WMRL_CUDA_OK(cudaLaunchKernelEx(&cfg, layer_kernel_for(L.type, 4), a));
   return 0;
 }
@@ -3106,7 +3175,8 @@ int tcm_fwd(const wmrl_mlp_dims* d, const void* packed, const void* x_panel, flo
   const uint8_t* img = (const uint8_t*)packed;
   c.data = img + lp.pk.off_data;
   c.ep = (const float*)(img + lp.pk.off_eparams);
-  for (const LLayerH& L : lp.layers) {
+  const std::vector<LLayerH>& fl = tcl_split_choice(0, lp.cpair, m.MT) == 2 ? lp.layers_p : lp.layers;
+  for (const LLayerH& L : fl) {
     LayerArgs a{};
     a.save = rec ? 1 : 0;
     if (L.type == LE_OUT) a.f0 = out;
@@ -3136,7 +3206,8 @@ int tcm_bwd(const wmrl_mlp_dims* d, const void* packed, const void* x_panel, con
   c.ep = (const float*)(img + lp.pk.off_eparams);
   tcl_to_panel_kernel<<<dim3(1, (unsigned)m.MT, 1), 256, 0, st>>>(g_out, c.at(M_GOUT), (int)m.R, 1, m.O, 16, m.MT);
   WMRL_CUDA_OK(cudaGetLastError());
-  for (const LLayerH& L : lp.blayers) {
+  const std::vector<LLayerH>& bl = tcl_split_choice(0, lp.cpair, m.MT) == 2 ? lp.blayers_p : lp.blayers;
+  for (const LLayerH& L : bl) {
     LayerArgs a{};
     if (L.type == LB_XGRAD) {
       if (!g_x) continue;
