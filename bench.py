@@ -41,6 +41,13 @@ UNIT = "latent-steps/s"
 CFG = dict(variant="continuous", B=65536, H=15, D=200, S=30, C=1, Hd=200, E=1024, A=6, Ha=512, La=3)
 
 
+
+def _feed_gradient(features, g):
+    """back-propagate with dL/d features = g (the gradient a consumer - heads, losses - would hand back): identical to
+    (features * g).sum().backward() without the harness's own product and reduction over the feature tensor."""
+    features.backward(g.expand_as(features))
+
+
 def flops_per_latent_step(c) -> int:
     """ALGORITHMIC forward FLOPs per latent step: 2 x MACs of every
     nn.Linear on the path, padding excluded."""
@@ -375,7 +382,7 @@ def aux_all_ranks(c, rssm, actor, dev, world, rank, barrier):
     def train_step():
         actor.zero_grad(set_to_none=True)
         seq = rssm.imagine_rollout(init, actor, H)          # noise drawn inside, as the reference does
-        (seq.get_features() * gfeat).sum().backward()
+        _feed_gradient(seq.get_features(), gfeat)
         if world > 1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -520,7 +527,7 @@ def aux_configs(dev):
         def step():
             actor.zero_grad(set_to_none=True)
             seq = rssm.imagine_rollout(init, actor, H)
-            (seq.get_features() * gf).sum().backward()
+            _feed_gradient(seq.get_features(), gf)
 
         f_ms, t_ms = _event_ms(fwd, 10), _event_ms(step, 5)
         out[f"configs[1] discrete D600 32x32, 2500x15, {prec}"] = {
@@ -555,7 +562,7 @@ def aux_config2_filtering(dev):
         def step():
             rssm.zero_grad(set_to_none=True)
             _, post = rssm.observe_rollout(obs, act)
-            (post.get_features() * gf).sum().backward()
+            _feed_gradient(post.get_features(), gf)
 
         f_ms, t_ms = _event_ms(fwd, 10), _event_ms(step, 5)
         out[f"configs[2] discrete observe 50x51 (E 1024), {prec}"] = {
@@ -581,7 +588,7 @@ def aux_configs4_shard(dev, world, rank, barrier):
         def step():
             actor.zero_grad(set_to_none=True)
             seq = rssm.imagine_rollout(init, actor, H)
-            (seq.get_features() * gf).sum().backward()
+            _feed_gradient(seq.get_features(), gf)
             if world > 1:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()

@@ -11,6 +11,13 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "world-model-rl_b200"), os.path.join(RO
 import helpers_gpu as HG  # noqa: E402
 
 
+
+def _feed_gradient(features, g):
+    """back-propagate with dL/d features = g (the gradient a consumer - heads, losses - would hand back): identical to
+    (features * g).sum().backward() without the harness's own product and reduction over the feature tensor."""
+    features.backward(g.expand_as(features))
+
+
 def flops_fwd(D, S_in, P, Hd, A, Ha, La):
     F = D + S_in
     actor = F * Ha + (La - 1) * Ha * Ha + Ha * A
@@ -64,7 +71,7 @@ def run_train(name, variant, D, S, C, Hd, A, Ha, La, B, H, iters=5, precision="b
     def step():
         actor.zero_grad(set_to_none=True)
         seq = rssm.imagine_rollout(init, actor, H, noise=nz)
-        (seq.get_features() * gfeat).sum().backward()
+        _feed_gradient(seq.get_features(), gfeat)
 
     for _ in range(2):
         step()

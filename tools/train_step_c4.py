@@ -16,6 +16,13 @@ for p in (ROOT, os.path.join(ROOT, "world-model-rl_b200"), os.path.join(ROOT, "t
 import torch  # noqa: E402
 
 
+
+def _feed_gradient(features, g):
+    """back-propagate with dL/d features = g (the gradient a consumer - heads, losses - would hand back): identical to
+    (features * g).sum().backward() without the harness's own product and reduction over the feature tensor."""
+    features.backward(g.expand_as(features))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--B", type=int, default=65536)
@@ -55,7 +62,7 @@ def main():
     def fwd_bwd():
         actor.zero_grad(set_to_none=True)
         seq = rssm.imagine_rollout(init, actor, a.H, noise=nz)
-        (seq.get_features() * gf).sum().backward()
+        _feed_gradient(seq.get_features(), gf)
 
     t0, t1, t2 = timed(fwd_plain, a.iters), timed(fwd_rec, a.iters), timed(fwd_bwd, a.iters)
     steps = a.B * a.H
