@@ -192,14 +192,15 @@ class RSSMBase(nn.Module):
         returns (action, next_state, post, (act_mean, act_std, entropy))."""
         from .functional import ActStepPlan
         ent = _ACT_PLANS.get(self)
-        plan = ent[1] if (ent is not None and ent[0]() is actor and ent[2] is actor.bound) else None
+        bver = getattr(actor.bound, "_version", 0)
+        plan = ent[1] if (ent is not None and ent[0]() is actor and ent[2] is actor.bound and ent[3] == bver) else None
         if plan is None or not plan.valid():
             device = next(actor.parameters()).device
             La, Ha, actor_p = _actor_tensors(actor)
             A = actor.mu.weight.shape[0]
             cfg = self._config(A, Ha, La, getattr(actor, "action_scale", 5.0))
             plan = ActStepPlan(cfg, self._rssm_tensors(), actor_p, _actor_bound(actor, A, device))
-            _ACT_PLANS[self] = (weakref.ref(actor), plan, actor.bound)
+            _ACT_PLANS[self] = (weakref.ref(actor), plan, actor.bound, bver)
         device, A = plan.dev, plan.cfg.A
         deter = state.deter_state
         if deter.device != device:

@@ -12,7 +12,7 @@ from typing import Optional
 
 import torch
 
-from .functional import done_mask, lambda_return
+from .functional import clear_panel_cache, done_mask, lambda_return
 from .utils import AdamOptim, FreezeParameters
 
 
@@ -90,6 +90,7 @@ class ValueGradTrainer:
             actor_gn = self.actor_optim.backward(actor_loss)
             self.actor_optim.update_parameters()
         update_target_network(self.target_critic, self.critic)
+        clear_panel_cache()      # the bf16 heads' feature panel (and the view that keeps its source alive) is per update
         return ValueGradTrainerLosses(
             value_loss=value_loss.item(), value_grad_norm=value_gn.item(),
             actor_loss=None if actor_loss is None else actor_loss.item(),

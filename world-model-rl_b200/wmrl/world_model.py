@@ -133,6 +133,8 @@ class WorldModel(nn.Module):
                 + p.done_coeff * done_loss)
         grad_norm = self.opt.backward(loss)
         self.opt.update_parameters()
+        from .functional import clear_panel_cache
+        clear_panel_cache()
         return WorldModelLosses(recon_loss=recon_loss.item(), dynamic_model_loss=kl_mean.item(),
                                 dynamic_model_loss_clamped=kl_clamped.item(), reward_loss=reward_loss.item(),
                                 done_loss=done_loss.item(), loss=loss.item(), grad_norm=grad_norm.item())
