@@ -133,7 +133,8 @@ def test_feature_gradient_only_and_shared_panel():
 
 def test_large_rows_property():
     """983 040 feature rows (configs[3]: 65 536 x 15): the chain is row-wise - a slice of the big batch equals the same
-    rows run alone, bit for bit."""
+    rows run alone.  Bit for bit when both calls use the same tiling of the 512-wide blocks (a second large call); to
+    bf16 rounding (the LayerNorm statistics are summed in a different order) when the small call runs them as CTA pairs."""
     import wmrl
     torch.manual_seed(4)
     m = wmrl.ValueCritic(230, precision="bf16").cuda()
@@ -142,7 +143,10 @@ def test_large_rows_property():
         y = m(x)
         assert y.shape == (65536, 15, 1) and bool(torch.isfinite(y).all())
         sub = x[40000:40003].clone()
-        torch.testing.assert_close(m(sub), y[40000:40003], rtol=0, atol=0)
+        scale = float(y.abs().max())
+        assert float((m(sub) - y[40000:40003]).abs().max()) <= 2e-3 * max(scale, 1.0)
+        big2 = x[20000:60000].clone()                 # 4 688 row tiles: same (unsplit) tiling as the full call
+        torch.testing.assert_close(m(big2)[20000:20003], y[40000:40003], rtol=0, atol=0)
 
 
 def _trainer_problem(prec, B=192, H=6):
