@@ -1067,36 +1067,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const WgParams 
 struct CsParams {
   const uint8_t* x_base; size_t x_blk;
   const uint8_t* y_base; size_t y_blk;   // null: plain column sum
+  // fused form (one pass over the three panels of an actor block instead of three passes reading four):
+  // out += sum X (ln_b), out2 += sum X Y (ln_g), out3 += sum Z (lin_b); X = g_u, Y = x-hat, Z = g_pre
+  const uint8_t* z_base; size_t z_blk;
   int nblocks, valid;
-  float* out;
+  float* out; float* out2; float* out3;
 };
 constexpr int kCsWarps = 8;
-__global__ void __launch_bounds__(kCsWarps * 32) colsum_kernel(const CsParams p) {
-  const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  const size_t off = (size_t)chunk * kStashChunk + (size_t)lane * 16;
-  for (size_t blk = (size_t)blockIdx.y * kCsWarps + warp; blk < (size_t)p.nblocks; blk += (size_t)gridDim.y * kCsWarps) {
-    float x0[8], x1[8];
-    ld_chunk_g(p.x_base + blk * p.x_blk + off, x0);
-    ld_chunk_g(p.x_base + blk * p.x_blk + off + 512, x1);
-    if (p.y_base) {
-      float y0[8], y1[8];
-      ld_chunk_g(p.y_base + blk * p.y_blk + off, y0);
-      ld_chunk_g(p.y_base + blk * p.y_blk + off + 512, y1);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += x0[i] * y0[i] + x1[i] * y1[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += x0[i] + x1[i];
-    }
-  }
+__device__ __forceinline__ void cs_reduce_store(float (&acc)[8], float* out, int chunk, int valid, float (*part)[8]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], s);
-  __shared__ float part[kCsWarps][8];
+  __syncthreads();
   if (lane == 0)
 #pragma unroll
     for (int i = 0; i < 8; ++i) part[warp][i] = acc[i];
@@ -1105,7 +1089,48 @@ __global__ void __launch_bounds__(kCsWarps * 32) colsum_kernel(const CsParams p)
     float s = 0.f;
     for (int w2 = 0; w2 < kCsWarps; ++w2) s += part[w2][threadIdx.x];
     const int col = chunk * 8 + threadIdx.x;
-    if (col < p.valid) atomicAdd(p.out + col, s);
+    if (col < valid) atomicAdd(out + col, s);
+  }
+}
+__global__ void __launch_bounds__(kCsWarps * 32) colsum_kernel(const CsParams p) {
+  const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[8], acc2[8], acc3[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i] = 0.f; acc2[i] = 0.f; acc3[i] = 0.f; }
+  const size_t off = (size_t)chunk * kStashChunk + (size_t)lane * 16;
+  const bool fused = p.z_base != nullptr;
+  for (size_t blk = (size_t)blockIdx.y * kCsWarps + warp; blk < (size_t)p.nblocks; blk += (size_t)gridDim.y * kCsWarps) {
+    float x0[8], x1[8];
+    ld_chunk_g(p.x_base + blk * p.x_blk + off, x0);
+    ld_chunk_g(p.x_base + blk * p.x_blk + off + 512, x1);
+    if (p.y_base) {
+      float y0[8], y1[8];
+      ld_chunk_g(p.y_base + blk * p.y_blk + off, y0);
+      ld_chunk_g(p.y_base + blk * p.y_blk + off + 512, y1);
+      if (fused) {
+        float z0[8], z1[8];
+        ld_chunk_g(p.z_base + blk * p.z_blk + off, z0);
+        ld_chunk_g(p.z_base + blk * p.z_blk + off + 512, z1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i] += x0[i] + x1[i];
+          acc2[i] += x0[i] * y0[i] + x1[i] * y1[i];
+          acc3[i] += z0[i] + z1[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += x0[i] * y0[i] + x1[i] * y1[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += x0[i] + x1[i];
+    }
+  }
+  __shared__ float part[kCsWarps][8];
+  cs_reduce_store(acc, p.out, chunk, p.valid, part);
+  if (fused) {
+    cs_reduce_store(acc2, p.out2, chunk, p.valid, part);
+    cs_reduce_store(acc3, p.out3, chunk, p.valid, part);
   }
 }
 
@@ -1238,9 +1263,20 @@ int tc_imagine_bwd(const Dims& d, const void* packed, const float* noise, const 
     if (l == 0) rc = wgrad(sf + sl.feat, pl.Dp + pl.Sp, pl.Dp, d.D, d.S, sg + sl.gp[0], d.Ha, d.Ha, gaw->lin_w[0], d.F);
     else rc = wgrad(sf + sl.y[l - 1], d.Ha, d.Ha, d.Ha, 0, sg + sl.gp[l], d.Ha, d.Ha, gaw->lin_w[l], d.Ha);
     WMRL_REQUIRE(rc == 0, "tc_imagine_bwd: weight-gradient launch failed");
-    WMRL_REQUIRE(colsum(sg + sl.gp[l], sl.blk_g, nullptr, 0, d.Ha, d.Ha, gaw->lin_b[l]) == 0, "colsum launch failed");
-    WMRL_REQUIRE(colsum(sg + sl.gu[l], sl.blk_g, nullptr, 0, d.Ha, d.Ha, gaw->ln_b[l]) == 0, "colsum launch failed");
-    WMRL_REQUIRE(colsum(sg + sl.gu[l], sl.blk_g, sf + sl.xh[l], sl.blk_f, d.Ha, d.Ha, gaw->ln_g[l]) == 0, "colsum launch failed");
+    if (gaw->lin_b[l] && gaw->ln_b[l] && gaw->ln_g[l]) {   // one pass over g_u, x-hat, g_pre
+      CsParams q{};
+      q.x_base = sg + sl.gu[l]; q.x_blk = sl.blk_g; q.y_base = sf + sl.xh[l]; q.y_blk = sl.blk_f;
+      q.z_base = sg + sl.gp[l]; q.z_blk = sl.blk_g; q.nblocks = (int)nblk; q.valid = d.Ha;
+      q.out = gaw->ln_b[l]; q.out2 = gaw->ln_g[l]; q.out3 = gaw->lin_b[l];
+      const int chunks = d.Ha / 8;
+      const int ysplit = std::max(1, std::min(((int)nblk + kCsWarps - 1) / kCsWarps, (8 * sms + chunks - 1) / chunks));
+      colsum_kernel<<<dim3(chunks, ysplit), kCsWarps * 32, 0, st>>>(q);
+      WMRL_REQUIRE(cudaGetLastError() == cudaSuccess, "colsum launch failed");
+    } else {
+      WMRL_REQUIRE(colsum(sg + sl.gp[l], sl.blk_g, nullptr, 0, d.Ha, d.Ha, gaw->lin_b[l]) == 0, "colsum launch failed");
+      WMRL_REQUIRE(colsum(sg + sl.gu[l], sl.blk_g, nullptr, 0, d.Ha, d.Ha, gaw->ln_b[l]) == 0, "colsum launch failed");
+      WMRL_REQUIRE(colsum(sg + sl.gu[l], sl.blk_g, sf + sl.xh[l], sl.blk_f, d.Ha, d.Ha, gaw->ln_g[l]) == 0, "colsum launch failed");
+    }
   }
   WMRL_REQUIRE(wgrad(sf + sl.y[d.La - 1], d.Ha, d.Ha, d.Ha, 0, sg + sl.gmu, 16, d.A, gaw->mu_w, d.Ha) == 0,
                "tc_imagine_bwd: weight-gradient launch failed");

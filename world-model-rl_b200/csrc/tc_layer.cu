@@ -1506,37 +1506,20 @@ __global__ void __launch_bounds__(kWg2Threads, 1) tcl_wgrad_kernel(const Wg2Para
 struct Cs2Params {
   const uint8_t* x_base; size_t x_blk;
   const uint8_t* y_base; size_t y_blk;   // null: plain column sum
+  // fused form (z_base != null): out += sum X (ln_b), out2 += sum X Y (ln_g), out3 += sum Z (lin_b) in ONE pass over the
+  // g_u, x-hat and g_pre panels of a block (three separate passes read four panels)
+  const uint8_t* z_base; size_t z_blk;
   int nblocks, valid;
-  float* out;
+  float* out; float* out2; float* out3;
 };
 constexpr int kCs2Warps = 8;
-__global__ void __launch_bounds__(kCs2Warps * 32) tcl_colsum_kernel(const Cs2Params p) {
-  const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  const size_t off = (size_t)chunk * kLTileChunk + (size_t)lane * 16;
-  for (size_t blk = (size_t)blockIdx.y * kCs2Warps + warp; blk < (size_t)p.nblocks; blk += (size_t)gridDim.y * kCs2Warps) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      float x[8];
-      ld_chunk_g(p.x_base + blk * p.x_blk + off + r * 512, x);
-      if (p.y_base) {
-        float y[8];
-        ld_chunk_g(p.y_base + blk * p.y_blk + off + r * 512, y);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[i], y[i], acc[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += x[i];
-      }
-    }
-  }
+__device__ __forceinline__ void cs2_reduce_store(float (&acc)[8], float* out, int chunk, int valid, float (*part)[8]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], s);
-  __shared__ float part[kCs2Warps][8];
+  __syncthreads();
   if (lane == 0)
 #pragma unroll
     for (int i = 0; i < 8; ++i) part[warp][i] = acc[i];
@@ -1545,7 +1528,44 @@ __global__ void __launch_bounds__(kCs2Warps * 32) tcl_colsum_kernel(const Cs2Par
     float s = 0.f;
     for (int w2 = 0; w2 < kCs2Warps; ++w2) s += part[w2][threadIdx.x];
     const int col = chunk * 8 + threadIdx.x;
-    if (col < p.valid) atomicAdd(p.out + col, s);
+    if (col < valid) atomicAdd(out + col, s);
+  }
+}
+__global__ void __launch_bounds__(kCs2Warps * 32) tcl_colsum_kernel(const Cs2Params p) {
+  const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[8], acc2[8], acc3[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i] = 0.f; acc2[i] = 0.f; acc3[i] = 0.f; }
+  const size_t off = (size_t)chunk * kLTileChunk + (size_t)lane * 16;
+  const bool fused = p.z_base != nullptr;
+  for (size_t blk = (size_t)blockIdx.y * kCs2Warps + warp; blk < (size_t)p.nblocks; blk += (size_t)gridDim.y * kCs2Warps) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float x[8];
+      ld_chunk_g(p.x_base + blk * p.x_blk + off + r * 512, x);
+      if (p.y_base) {
+        float y[8];
+        ld_chunk_g(p.y_base + blk * p.y_blk + off + r * 512, y);
+        if (fused) {
+          float z[8];
+          ld_chunk_g(p.z_base + blk * p.z_blk + off + r * 512, z);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { acc[i] += x[i]; acc2[i] = fmaf(x[i], y[i], acc2[i]); acc3[i] += z[i]; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[i], y[i], acc[i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += x[i];
+      }
+    }
+  }
+  __shared__ float part[kCs2Warps][8];
+  cs2_reduce_store(acc, p.out, chunk, p.valid, part);
+  if (fused) {
+    cs2_reduce_store(acc2, p.out2, chunk, p.valid, part);
+    cs2_reduce_store(acc3, p.out3, chunk, p.valid, part);
   }
 }
 
@@ -2320,6 +2340,17 @@ int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const
     WMRL_CUDA_OK(cudaGetLastError());
     return 0;
   };
+  auto colsum3 = [&](int xbuf, int ybuf, int zbuf, int cols, float* o_x, float* o_xy, float* o_z) -> int {
+    Cs2Params q{};
+    q.x_base = c.at(xbuf, 0); q.x_blk = m.r[xbuf].tile_bytes; q.y_base = c.at(ybuf, 0); q.y_blk = m.r[ybuf].tile_bytes;
+    q.z_base = c.at(zbuf, 0); q.z_blk = m.r[zbuf].tile_bytes;
+    q.nblocks = nblk; q.valid = cols; q.out = o_x; q.out2 = o_xy; q.out3 = o_z;
+    const int chunks = cols / 8;
+    const int ysplit = std::max(1, std::min((nblk + kCs2Warps - 1) / kCs2Warps, (8 * c.nsm + chunks - 1) / chunks));
+    tcl_colsum_kernel<<<dim3(chunks, ysplit), kCs2Warps * 32, 0, st>>>(q);
+    WMRL_CUDA_OK(cudaGetLastError());
+    return 0;
+  };
   for (int l = 0; l < d.La; ++l) {
     if (l == 0) {
       if (int r = wgrad(F_H, lp.Dp, d.D, G_GP0, d.Ha, d.Ha, gaw->lin_w[0], d.F)) return r;
@@ -2327,9 +2358,13 @@ int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const
     } else {
       if (int r = wgrad(F_Y0 + l - 1, d.Ha, d.Ha, G_GP0 + l, d.Ha, d.Ha, gaw->lin_w[l], d.Ha)) return r;
     }
-    if (int r = colsum(G_GP0 + l, -1, d.Ha, d.Ha, gaw->lin_b[l])) return r;
-    if (int r = colsum(G_GU0 + l, -1, d.Ha, d.Ha, gaw->ln_b[l])) return r;
-    if (int r = colsum(G_GU0 + l, F_XH0 + l, d.Ha, d.Ha, gaw->ln_g[l])) return r;
+    if (gaw->lin_b[l] && gaw->ln_b[l] && gaw->ln_g[l]) {
+      if (int r = colsum3(G_GU0 + l, F_XH0 + l, G_GP0 + l, d.Ha, gaw->ln_b[l], gaw->ln_g[l], gaw->lin_b[l])) return r;
+    } else {
+      if (int r = colsum(G_GP0 + l, -1, d.Ha, d.Ha, gaw->lin_b[l])) return r;
+      if (int r = colsum(G_GU0 + l, -1, d.Ha, d.Ha, gaw->ln_b[l])) return r;
+      if (int r = colsum(G_GU0 + l, F_XH0 + l, d.Ha, d.Ha, gaw->ln_g[l])) return r;
+    }
   }
   if (int r = wgrad(F_Y0 + d.La - 1, d.Ha, d.Ha, G_GMU, 16, d.A, gaw->mu_w, d.Ha)) return r;
   if (int r = colsum(G_GMU, -1, 16, d.A, gaw->mu_b)) return r;
@@ -3249,9 +3284,20 @@ int tcm_bwd(const wmrl_mlp_dims* d, const void* packed, const void* x_panel, con
   for (int l = 0; l < m.L; ++l) {
     if (l == 0) { if (int r = wgrad(M_X, m.Fp, m.F, M_GP0, m.Hh, m.Hh, gw->lin_w[0], m.F)) return r; }
     else if (int r = wgrad(M_Y0 + l - 1, m.Hh, m.Hh, M_GP0 + l, m.Hh, m.Hh, gw->lin_w[l], m.Hh)) return r;
-    if (int r = colsum(M_GP0 + l, -1, m.Hh, m.Hh, gw->lin_b[l])) return r;
-    if (int r = colsum(M_GU0 + l, -1, m.Hh, m.Hh, gw->ln_b[l])) return r;
-    if (int r = colsum(M_GU0 + l, M_XH0 + l, m.Hh, m.Hh, gw->ln_g[l])) return r;
+    if (gw->lin_b[l] && gw->ln_b[l] && gw->ln_g[l]) {   // one pass over g_u, x-hat, g_pre
+      Cs2Params q{};
+      q.x_base = c.at(M_GU0 + l); q.x_blk = mm.tile[M_GU0 + l]; q.y_base = c.at(M_XH0 + l); q.y_blk = mm.tile[M_XH0 + l];
+      q.z_base = c.at(M_GP0 + l); q.z_blk = mm.tile[M_GP0 + l];
+      q.nblocks = m.MT; q.valid = m.Hh; q.out = gw->ln_b[l]; q.out2 = gw->ln_g[l]; q.out3 = gw->lin_b[l];
+      const int chunks = m.Hh / 8;
+      const int ysplit = std::max(1, std::min((m.MT + kCs2Warps - 1) / kCs2Warps, (8 * c.nsm + chunks - 1) / chunks));
+      tcl_colsum_kernel<<<dim3(chunks, ysplit), kCs2Warps * 32, 0, st>>>(q);
+      WMRL_CUDA_OK(cudaGetLastError());
+    } else {
+      if (int r = colsum(M_GP0 + l, -1, m.Hh, m.Hh, gw->lin_b[l])) return r;
+      if (int r = colsum(M_GU0 + l, -1, m.Hh, m.Hh, gw->ln_b[l])) return r;
+      if (int r = colsum(M_GU0 + l, M_XH0 + l, m.Hh, m.Hh, gw->ln_g[l])) return r;
+    }
   }
   if (int r = wgrad(M_Y0 + m.L - 1, m.Hh, m.Hh, M_GOUT, 16, m.O, gw->out_w, m.Hh)) return r;
   if (int r = colsum(M_GOUT, -1, 16, m.O, gw->out_b)) return r;
