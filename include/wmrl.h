@@ -273,6 +273,16 @@ WMRL_API int wmrl_act_step(const wmrl_dims* d, const wmrl_rssm_params* w, const 
                   const wmrl_act_sampling* sampling, void* stream);
 
 /*
+ * get_features() of a state sequence (state/continuous.py:73-77, state/discrete.py get_features): features[B][T-1][D + S_in] =
+ * cat(deter_seq[:, 1:], stoch_seq[:, 1:], -1) as one streaming pass, and its backward (g_deter_seq [B][T][D] / g_stoch_seq
+ * [B][T][S_in] are fully written: index 0 is zero).
+ */
+WMRL_API int wmrl_features_fwd(const float* deter_seq, const float* stoch_seq, int64_t B, int32_t T, int32_t D, int32_t S_in,
+                      float* features, void* stream);
+WMRL_API int wmrl_features_bwd(const float* g_features, int64_t B, int32_t T, int32_t D, int32_t S_in, float* g_deter_seq,
+                      float* g_stoch_seq, void* stream);
+
+/*
  * Reward and done losses of WorldModel.update (world_model.py:130, 143-144) in one pass over the two heads' outputs:
  * sums[0] += sum_i 0.5 (tgt_r - pred_r)^2 + 0.5 log(2 pi)  (unit-variance Normal NLL, get_norm_dist),
  * sums[1] += sum_i binary_cross_entropy_with_logits(logit_d, tgt_d); the caller zero-fills sums and divides by the

@@ -132,6 +132,36 @@ __global__ void head_losses_kernel(const float* __restrict__ pr, const float* __
   }
 }
 
+// get_features() of a state sequence (state/continuous.py:73-77, state/discrete.py): cat(deter[:, 1:], stoch[:, 1:], -1) as ONE
+// streaming pass (torch.cat runs this strided gather at about a third of HBM bandwidth), and its backward: the gradient of the
+// feature tensor scattered back into [B][T][D] / [B][T][S_in] gradients whose index 0 is zero.
+template <int V, bool kBwd>
+__global__ void features_kernel(float* __restrict__ deter, float* __restrict__ stoch, float* __restrict__ feats, long long B,
+                                int T, int D, int S) {
+  const int F = D + S;
+  const long long nv = B * (long long)(T - 1) * (F / V);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    const long long row = i / (F / V);
+    const int col = (int)(i % (F / V)) * V;
+    const long long b = row / (T - 1);
+    const int t = (int)(row % (T - 1)) + 1;
+    float* src = col < D ? deter + (b * T + t) * D + col : stoch + (b * T + t) * S + (col - D);
+    float* dst = feats + row * F + col;
+    if (V == 4) { if (kBwd) *reinterpret_cast<float4*>(src) = *reinterpret_cast<const float4*>(dst); else *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src); }
+    else if (V == 2) { if (kBwd) *reinterpret_cast<float2*>(src) = *reinterpret_cast<const float2*>(dst); else *reinterpret_cast<float2*>(dst) = *reinterpret_cast<const float2*>(src); }
+    else { if (kBwd) *src = *dst; else *dst = *src; }
+  }
+  if (kBwd) {   // index 0 of both gradients
+    const long long n0 = B * (long long)F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n0; i += stride) {
+      const long long b = i / F;
+      const int col = (int)(i % F);
+      if (col < D) deter[(b * T) * D + col] = 0.f; else stoch[(b * T) * S + (col - D)] = 0.f;
+    }
+  }
+}
+
 }  // namespace wmrl
 
 using namespace wmrl;
@@ -181,6 +211,34 @@ int wmrl_head_losses(const float* pred_r, const float* tgt_r, int64_t n_reward, 
                                                                 g_logit_d);
   WMRL_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+static int features_launch(float* deter, float* stoch, float* feats, int64_t B, int32_t T, int32_t D, int32_t S, bool bwd,
+                           cudaStream_t st) {
+  WMRL_REQUIRE(B >= 0 && T >= 1 && D >= 1 && S >= 1, "features: bad dims");
+  if (B == 0 || T == 1) return 0;
+  WMRL_REQUIRE(deter && stoch && feats, "features: NULL tensor");
+  const int V = (D % 4 == 0 && S % 4 == 0) ? 4 : ((D % 2 == 0 && S % 2 == 0) ? 2 : 1);
+  const long long nv = (long long)B * (T - 1) * ((D + S) / V);
+  const unsigned blocks = (unsigned)std::min<long long>((nv + 255) / 256, 148 * 16);
+#define WMRL_FEAT(VV)                                                                                   \
+  do {                                                                                                  \
+    if (bwd) features_kernel<VV, true><<<blocks, 256, 0, st>>>(deter, stoch, feats, B, T, D, S);        \
+    else features_kernel<VV, false><<<blocks, 256, 0, st>>>(deter, stoch, feats, B, T, D, S);           \
+  } while (0)
+  if (V == 4) WMRL_FEAT(4); else if (V == 2) WMRL_FEAT(2); else WMRL_FEAT(1);
+#undef WMRL_FEAT
+  WMRL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int wmrl_features_fwd(const float* deter_seq, const float* stoch_seq, int64_t B, int32_t T, int32_t D, int32_t S_in,
+                      float* features, void* stream) {
+  return features_launch(const_cast<float*>(deter_seq), const_cast<float*>(stoch_seq), features, B, T, D, S_in, false,
+                         (cudaStream_t)stream);
+}
+int wmrl_features_bwd(const float* g_features, int64_t B, int32_t T, int32_t D, int32_t S_in, float* g_deter_seq,
+                      float* g_stoch_seq, void* stream) {
+  return features_launch(g_deter_seq, g_stoch_seq, const_cast<float*>(g_features), B, T, D, S_in, true, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -105,6 +105,8 @@ _SIGNATURES = {
     "wmrl_kl_loss_fwd": (C.c_int, [C.POINTER(Dims), _P, _P, _P, _P, C.c_float, _P, _P, _P]),
     "wmrl_kl_loss_bwd": (C.c_int, [C.POINTER(Dims), _P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
     "wmrl_act_step": (C.c_int, [C.POINTER(Dims), C.POINTER(RssmPtrs), C.POINTER(ActorPtrs)] + [_P] * 12 + [C.c_int64, C.POINTER(ActSampling), _P]),
+    "wmrl_features_fwd": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "wmrl_features_bwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "wmrl_head_losses": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "wmrl_lambda_return_fwd": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P]),
     "wmrl_lambda_return_bwd": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P, _P]),

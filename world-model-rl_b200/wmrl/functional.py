@@ -714,6 +714,42 @@ def act_step(cfg: PathConfig, rssm_p: Sequence[torch.Tensor], actor_p: Sequence[
     return ActStepPlan(cfg, rssm_p, actor_p, bound).run(obs_embed, deter, noise_post, noise_prior, sampling)
 
 
+class SequenceFeatures(torch.autograd.Function):
+    """``cat(deter_states[:, 1:], stoch_states[:, 1:], -1)`` (state/continuous.py:73-77) as one streaming pass each way
+    (wmrl_features_fwd / _bwd) - torch.cat and its backward's two gathers run at about a third of HBM bandwidth."""
+
+    @staticmethod
+    def forward(ctx, deter_seq, stoch_seq):
+        lib = _lib.load()
+        dev = _require_cuda(deter_seq, stoch_seq)
+        d32, s32 = _f32c(deter_seq), _f32c(stoch_seq)
+        B, T, D = d32.shape
+        S = s32.shape[2]
+        out = torch.empty(B, max(T - 1, 0), D + S, device=dev)
+        if B > 0 and T > 1:
+            _native(dev, lib.wmrl_features_fwd, d32.data_ptr(), s32.data_ptr(), B, T, D, S, out.data_ptr(), _stream_ptr(dev))
+        ctx.dims = (B, T, D, S)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        B, T, D, S = ctx.dims
+        g32 = _f32c(g)
+        dev = g32.device
+        gd, gs = torch.empty(B, T, D, device=dev), torch.empty(B, T, S, device=dev)
+        if B > 0 and T > 1:
+            _native(dev, lib.wmrl_features_bwd, g32.data_ptr(), B, T, D, S, gd.data_ptr(), gs.data_ptr(), _stream_ptr(dev))
+        else:
+            gd.zero_(); gs.zero_()
+        return gd, gs
+
+
+def sequence_features(deter_seq: torch.Tensor, stoch_seq: torch.Tensor) -> torch.Tensor:
+    """features[B, T-1, D + S_in] of a [B, T, .] state sequence (index 0, the initial state, excluded)."""
+    return SequenceFeatures.apply(deter_seq, stoch_seq)
+
+
 class HeadLosses(torch.autograd.Function):
     """(reward NLL, done BCE-with-logits) of WorldModel.update (world_model.py:130, 143-144), values and both
     gradients in ONE pass (wmrl_head_losses).  reward loss = mean over rows of the summed unit-variance Normal NLL

@@ -77,7 +77,12 @@ class _SequenceOps:
         return self[-1]
 
     def get_features(self) -> torch.Tensor:
-        return torch.cat((self.deter_states[:, 1:], self.stoch_states[:, 1:]), dim=-1)
+        d, s = self.deter_states, self.stoch_states
+        if (d.is_cuda and d.dtype == torch.float32 and s.dtype == torch.float32 and d.dim() == 3 and s.dim() == 3
+                and d.device == s.device):
+            from .functional import sequence_features       # one streaming pass each way instead of torch.cat
+            return sequence_features(d, s)
+        return torch.cat((d[:, 1:], s[:, 1:]), dim=-1)
 
     def flatten_batch_time(self):
         flat = {}
