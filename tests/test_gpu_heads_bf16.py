@@ -215,3 +215,67 @@ def test_value_targets_bf16_heads_vs_fp32():
     assert wm.reward_model.precision == "bf16" and wm.dynamic_model.precision == "bf16"
     losses = trainer.update(roll.features, roll.rewards, roll.dones, critic_only=True)
     assert losses.value_loss == losses.value_loss
+
+
+@pytest.mark.parametrize("rows,F_,Hh,L,O,act", [(300, 230, 512, 3, 1, 2), (129, 40, 96, 2, 5, 0), (5000, 230, 256, 3, 1, 1)])
+def test_mlp_c_abi_guard_bands(rows, F_, Hh, L, O, act):
+    """Straight through the C ABI with every caller-owned buffer sized EXACTLY as the size queries say and followed by a
+    canary region: packed image, feature panel, saved activations, both workspaces, out, g_x - nothing may be written
+    past what was asked for; out / g_x agree with the Python-level path."""
+    import ctypes as C
+    import wmrl.functional as Fn
+    from wmrl import _lib
+    lib = _lib.load()
+    torch.manual_seed(rows + Hh)
+    dev = torch.device("cuda")
+    acts = [torch.nn.ELU, torch.nn.SiLU, torch.nn.ReLU]
+    layers, w = [], F_
+    for _ in range(L):
+        layers += [torch.nn.Linear(w, Hh), torch.nn.LayerNorm(Hh), acts[act]()]
+        w = Hh
+    seq = torch.nn.Sequential(*layers, torch.nn.Linear(Hh, O)).to(dev)
+    x = torch.randn(rows, F_, device=dev)
+    g_out = torch.randn(rows, O, device=dev)
+    params = []
+    for i in range(L):
+        params += [seq[3 * i].weight, seq[3 * i].bias, seq[3 * i + 1].weight, seq[3 * i + 1].bias]
+    params += [seq[-1].weight, seq[-1].bias]
+    p32 = [p.detach().contiguous() for p in params]
+    CAN = 4096
+
+    def guarded(nbytes):
+        buf = torch.full((int(nbytes) + CAN,), 0x5A, dtype=torch.uint8, device=dev)
+        return buf
+
+    def intact(buf, nbytes):
+        return bool((buf[int(nbytes):] == 0x5A).all())
+
+    st = torch.cuda.current_stream().cuda_stream
+    d = _lib.MlpDims(rows=rows, in_dim=F_, hidden=Hh, depth=L, out_dim=O, act=act, flags=_lib.MLP_SAVE)
+    n_pack, n_panel = lib.wmrl_mlp_packed_bytes(C.byref(d)), lib.wmrl_mlp_panel_bytes(C.byref(d))
+    n_saved, n_ws = lib.wmrl_mlp_saved_bytes(C.byref(d)), lib.wmrl_mlp_workspace_bytes(C.byref(d), 0)
+    packed, panel, saved, ws = guarded(n_pack), guarded(n_panel), guarded(n_saved), guarded(n_ws)
+    out = guarded(rows * O * 4)
+    _lib.check(lib.wmrl_mlp_pack(C.byref(d), C.byref(Fn._mlp_ptrs(p32, L)), packed.data_ptr(), st), "pack")
+    _lib.check(lib.wmrl_mlp_to_panel(C.byref(d), x.data_ptr(), panel.data_ptr(), st), "to_panel")
+    _lib.check(lib.wmrl_mlp_fwd_bf16(C.byref(d), packed.data_ptr(), panel.data_ptr(), out.data_ptr(), saved.data_ptr(), n_saved,
+                                     ws.data_ptr(), n_ws, st), "fwd")
+    db = _lib.MlpDims(rows=rows, in_dim=F_, hidden=Hh, depth=L, out_dim=O, act=act, flags=_lib.MLP_WGRAD)
+    n_wsb = lib.wmrl_mlp_workspace_bytes(C.byref(db), 1)
+    wsb, g_x = guarded(n_wsb), guarded(rows * F_ * 4)
+    grads = [torch.zeros_like(p) for p in p32]
+    _lib.check(lib.wmrl_mlp_bwd_bf16(C.byref(db), packed.data_ptr(), panel.data_ptr(), saved.data_ptr(), g_out.data_ptr(),
+                                     C.byref(Fn._mlp_ptrs(grads, L)), g_x.data_ptr(), wsb.data_ptr(), n_wsb, st), "bwd")
+    torch.cuda.synchronize()
+    for name, buf, n in (("packed", packed, n_pack), ("panel", panel, n_panel), ("saved", saved, n_saved), ("ws", ws, n_ws),
+                         ("out", out, rows * O * 4), ("ws_bwd", wsb, n_wsb), ("g_x", g_x, rows * F_ * 4)):
+        assert intact(buf, n), f"{name}: written past its {n} bytes"
+    y_abi = out[:rows * O * 4].view(torch.float32).reshape(rows, O)
+    gx_abi = g_x[:rows * F_ * 4].view(torch.float32).reshape(rows, F_)
+    xr = x.clone().requires_grad_(True)
+    y_py = Fn.mlp_forward_bf16(seq, xr)
+    y_py.backward(g_out)
+    torch.testing.assert_close(y_abi, y_py.detach(), rtol=0, atol=0)
+    torch.testing.assert_close(gx_abi, xr.grad, rtol=0, atol=0)
+    for gnat, p in zip(grads, params):
+        torch.testing.assert_close(gnat, p.grad, rtol=2e-3, atol=2e-3 * float(p.grad.abs().max()))   # fp32 atomics: order
