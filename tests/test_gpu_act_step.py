@@ -117,3 +117,67 @@ def test_act_step_sampled_action(variant, D, S, C, Hd, E, A, Ha, La, B):
     assert bool((action.cpu().abs() <= bt + 1e-6).all()) and bool((action.cpu().abs() == bt).any())   # the clamp is active
     h_ref, _ = O.prior_deter(w, ref["post_stoch"].detach(), a_ref, deter)
     torch.testing.assert_close(nxt.deter_state.cpu(), h_ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("variant,D,S,C,Hd,E,A,Ha,La,B", [CASES[1], CASES[3]])
+def test_act_step_c_abi_guard_bands(variant, D, S, C, Hd, E, A, Ha, La, B):
+    """wmrl_act_step straight through the C ABI: every output is its own allocation of exactly (B-1) * ld_out + width
+    floats followed by a canary; nothing past the last valid element may be written, and the results equal the module
+    path's."""
+    import ctypes as C_
+    import helpers_gpu as HG
+    import wmrl.functional as Fn
+    from wmrl import _lib
+    from wmrl.rssm import _actor_tensors, _actor_bound
+    lib = _lib.load()
+    rssm, actor = HG.build_modules(variant, D, S, C, Hd, E, A, Ha, La, bound=[0.5 + 0.25 * i for i in range(A)], seed=4)
+    disc = variant == "discrete"
+    S_in, W = (S * C, S * C) if disc else (S, S)
+    g = torch.Generator().manual_seed(3)
+    deter = torch.tanh(torch.randn(B, D, generator=g)).cuda()
+    e = torch.randn(B, E, generator=g).cuda()
+    if disc:
+        n1, n2 = (torch.empty(B, C, S).exponential_(1.0, generator=g).cuda() for _ in range(2))
+    else:
+        n1, n2 = torch.randn(B, S, generator=g).cuda(), torch.randn(B, S, generator=g).cuda()
+    state = HG.init_state(rssm, deter.cpu(), torch.zeros(B, S_in))
+    a_ref, nxt, post = rssm.act_step(e, state, actor, noise_post=n1, noise_prior=n2)
+    La_, Ha_, actor_p = _actor_tensors(actor)
+    cfg = rssm._config(A, Ha_, La_, actor.action_scale)
+    bound = _actor_bound(actor, A, deter.device)
+    w = Fn._rssm_ptrs([p.detach() for p in rssm._rssm_tensors()])
+    aw = Fn._actor_ptrs([p.detach() for p in actor_p], La_, bound)
+    ld = max(D, S_in, W, A)
+    CAN = 256
+
+    def guarded(width):
+        n = (B - 1) * ld + width
+        return torch.full((n + CAN,), 12345.0, device="cuda"), n
+
+    bufs = {k: guarded(wd) for k, wd in (("action", A), ("post_s", S_in), ("post_a", W), ("post_b", W), ("deter", D),
+                                          ("pri_s", S_in), ("pri_a", W), ("pri_b", W))}
+    d = cfg.dims(B, 1, 0, _lib.FP32)
+    ptr = lambda k: bufs[k][0].data_ptr()
+    rc = lib.wmrl_act_step(C_.byref(d), C_.byref(w), C_.byref(aw), e.data_ptr(), deter.data_ptr(), n1.data_ptr(), n2.data_ptr(),
+                           ptr("action"), ptr("post_s"), ptr("post_a"), None if disc else ptr("post_b"), ptr("deter"),
+                           ptr("pri_s"), ptr("pri_a"), None if disc else ptr("pri_b"), ld, None,
+                           torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "wmrl_act_step")
+    torch.cuda.synchronize()
+    for k, (buf, n) in bufs.items():
+        assert bool((buf[n:] == 12345.0).all()), f"{k}: written past its {n} floats"
+
+    def rows(k, width):
+        buf = bufs[k][0]
+        return torch.stack([buf[r * ld:r * ld + width] for r in range(B)])
+
+    assert torch.equal(rows("action", A), a_ref)
+    assert torch.equal(rows("deter", D), nxt.deter_state)
+    assert torch.equal(rows("pri_s", S_in), nxt.stoch_state)
+    assert torch.equal(rows("post_s", S_in), post.stoch_state)
+    # argument errors are loud
+    rc = lib.wmrl_act_step(C_.byref(d), C_.byref(w), C_.byref(aw), e.data_ptr(), deter.data_ptr(), n1.data_ptr(), n2.data_ptr(),
+                           ptr("action"), ptr("post_s"), ptr("post_a"), None if disc else ptr("post_b"), ptr("deter"),
+                           ptr("pri_s"), ptr("pri_a"), None if disc else ptr("pri_b"), 1, None,
+                           torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and b"ld_out" in lib.wmrl_last_error()
