@@ -1341,36 +1341,50 @@ __device__ __forceinline__ void panel_store_bf16(uint8_t* panel, int Pp, long lo
 }
 // straight-through categorical backward (state/discrete.py:27-30): for the state produced by step t,
 //   G = carried dL/ds + dL/dstoch[:, t+1];  dlogits = p (G - sum_k p_k G_k) + dL/dlogits[:, t+1],  p = softmax(logits[:, t+1])
-// one warp per (padded row, group), lane = class
+// one warp per (padded row, kSbGroups consecutive groups), lane = class: the loads of all its groups are in flight together
+// (one group per warp left the kernel latency-bound at ~2.3 TB/s)
+constexpr int kSbGroups = 4;
 __global__ void tcl_sample_bwd_disc_kernel(const SbArgs a) {
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= (long long)a.MT * 128 * a.C) return;
-  const long long prow = warp / a.C;
-  const int c = (int)(warp % a.C);
+  const int gpr = (a.C + kSbGroups - 1) / kSbGroups;      // warps per row
+  if (warp >= (long long)a.MT * 128 * gpr) return;
+  const long long prow = warp / gpr;
+  const int c0 = (int)(warp % gpr) * kSbGroups;
   const int P = a.C * a.S;
   const bool valid = prow < a.B;
-  const long long o = (prow * (a.H + 1) + a.t + 1) * P + (long long)c * a.S;
-  float l = -INFINITY, G = 0.f, gl = 0.f;
-  if (valid && lane < a.S) {
-    l = a.dist_a[o + lane];
-    if (a.carry_s) { const int cc = c * a.S + lane; G = a.carry_s[((prow >> 7) * (a.Sip / 4) + (cc >> 2)) * 512 + (prow & 127) * 4 + (cc & 3)]; }
-    if (a.g_stoch) G += a.g_stoch[o + lane];
-    if (a.g_da) gl = a.g_da[o + lane];
+  const long long o0 = (prow * (a.H + 1) + a.t + 1) * P;
+  float l[kSbGroups], G[kSbGroups], gl[kSbGroups];
+#pragma unroll
+  for (int k = 0; k < kSbGroups; ++k) {
+    const int c = c0 + k;
+    l[k] = -INFINITY; G[k] = 0.f; gl[k] = 0.f;
+    if (valid && c < a.C && lane < a.S) {
+      const long long o = o0 + (long long)c * a.S + lane;
+      l[k] = a.dist_a[o];
+      if (a.carry_s) { const int cc = c * a.S + lane; G[k] = a.carry_s[((prow >> 7) * (a.Sip / 4) + (cc >> 2)) * 512 + (prow & 127) * 4 + (cc & 3)]; }
+      if (a.g_stoch) G[k] += a.g_stoch[o];
+      if (a.g_da) gl[k] = a.g_da[o];
+    }
   }
-  float mx = l;
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-  const float e = (valid && lane < a.S) ? expf(l - mx) : 0.f;
-  float se = e, sg = e * G;
+  for (int k = 0; k < kSbGroups; ++k) {
+    const int c = c0 + k;
+    if (c >= a.C) break;
+    float mx = l[k];
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, s); sg += __shfl_xor_sync(0xffffffffu, sg, s); }
-  if (lane < a.S) {
-    const float v = valid ? (e / se) * (G - sg / se) + gl : 0.f;
-    panel_store_bf16(a.out, a.Pp, prow, c * a.S + lane, v);
+    for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    const float e = (valid && lane < a.S) ? expf(l[k] - mx) : 0.f;
+    float se = e, sg = e * G[k];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, s); sg += __shfl_xor_sync(0xffffffffu, sg, s); }
+    if (lane < a.S) {
+      const float v = valid ? (e / se) * (G[k] - sg / se) + gl[k] : 0.f;
+      panel_store_bf16(a.out, a.Pp, prow, c * a.S + lane, v);
+    }
   }
   // zero the padding columns [P, Pp) once per row
-  if (c == 0 && P + lane < a.Pp) panel_store_bf16(a.out, a.Pp, prow, P + lane, 0.f);
+  if (c0 == 0 && P + lane < a.Pp) panel_store_bf16(a.out, a.Pp, prow, P + lane, 0.f);
 }
 // Gaussian reparameterised sample backward (rssm.py:179-181): panel [g_mean (Sp) | g_raw (Sp)],
 //   g_mean = dL/dmean + G,  g_raw = (dL/dstd + G eps) sigmoid(raw),  sigmoid(raw) = 1 - exp(-(std - 0.1))
@@ -2269,7 +2283,7 @@ int tcl_imagine_bwd(const Dims& d, const void* packed, const float* noise, const
       s.dist_a = dist_a; s.dist_b = dist_b; s.noise = noise; s.out = c.at(G_GO, 0);
       s.B = d.B; s.H = T; s.t = t; s.S = d.S; s.C = d.C; s.Sp = lp.Sp; s.Sip = lp.Sip; s.Pp = lp.Pp; s.MT = MT;
       if (disc) {
-        const long long nw = (long long)MT * 128 * d.C;
+        const long long nw = (long long)MT * 128 * ((d.C + kSbGroups - 1) / kSbGroups);
         tcl_sample_bwd_disc_kernel<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, st>>>(s);
       } else {
         const long long n = (long long)MT * 128 * (lp.Sp / 8);
@@ -2805,7 +2819,7 @@ int tcl_observe_bwd(const Dims& d, const void* packed, const float* noise_pri, c
       s.out = c.at(post ? G_OQ : G_GO, t);
       s.B = d.B; s.H = H; s.t = t; s.S = d.S; s.C = d.C; s.Sp = lp.Sp; s.Sip = lp.Sip; s.Pp = lp.Pp; s.MT = MT;
       if (disc) {
-        const long long nw = (long long)MT * 128 * d.C;
+        const long long nw = (long long)MT * 128 * ((d.C + kSbGroups - 1) / kSbGroups);
         tcl_sample_bwd_disc_kernel<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, st>>>(s);
       } else {
         const long long n = (long long)MT * 128 * (lp.Sp / 8);
