@@ -147,3 +147,37 @@ def test_discrete_recording_forward_is_bit_identical_and_gradients_add_over_shar
     full, a, b = grads(0, B), grads(0, 193), grads(193, B)
     for k in full:
         _agree(k, a[k] + b[k], full[k], cos_min=0.99999, rel_max=1e-3)
+
+
+def test_layernorm_cluster_forms_agree(monkeypatch):
+    """The three tilings of the 512-wide LayerNorm blocks - one CTA per row tile, CTA pairs, 4-CTA clusters (DSMEM
+    statistics exchange) - on the same rollout and BPTT: outputs within bf16 rounding of each other (the statistics are
+    summed in a different order), gradients cosine >= 0.9999, and each form within the oracle bounds."""
+    shape = (600, 32, 600, 6, 512, 3, 300, 6)          # continuous, layer-wise chain (D = 600 is outside the persistent kernel)
+    D, S, Hd, A, Ha, La, B, H = shape
+    HG, rssm, actor = _setup("continuous", D, S, 1, Hd, A, Ha, La)
+    d0, s0, nz = HG.synth_inputs("continuous", B, H, D, S, 1)
+    init = HG.init_state(rssm, d0, s0)
+    nz = nz.cuda()
+    gf = (torch.randn(B, H, D + S, generator=torch.Generator().manual_seed(5)) / B).cuda()
+    res = {}
+    for form in ("0", "2", "4"):
+        monkeypatch.setenv("WMRL_LN_SPLIT", form)
+        actor.zero_grad(set_to_none=True)
+        seq = rssm.imagine_rollout(init, actor, H, noise=nz)
+        feats = seq.get_features()
+        feats.backward(gf)
+        res[form] = (feats.detach().clone(), {n: p.grad.detach().clone() for n, p in actor.named_parameters() if p.grad is not None})
+    monkeypatch.delenv("WMRL_LN_SPLIT")
+    scale = float(res["0"][0].abs().max())
+    for form in ("2", "4"):
+        assert float((res[form][0] - res["0"][0]).abs().max()) <= 4e-3 * max(scale, 1.0), form
+        assert not torch.equal(res[form][0], res["0"][0]) or form == "2"      # a different tiling really ran
+        assert res[form][1].keys() == res["0"][1].keys() and len(res[form][1]) >= 4 * La + 2
+        for n, ga in res[form][1].items():
+            _agree(f"{n} (form {form} vs unsplit)", ga, res["0"][1][n], cos_min=0.9999, rel_max=1.5e-2)
+    w, aw = HG.cpu_weights(rssm), HG.cpu_weights(actor)
+    ref = O.imagine_rollout("continuous", w, aw, d0, s0, nz.cpu(), H, S, 1, 5.0, torch.ones(A), emulate_bf16=True, bias0_bf16=False)
+    ref_feats = torch.cat([ref["deter"], ref["stoch"]], -1)
+    for form in ("0", "2", "4"):
+        assert float((res[form][0].cpu() - ref_feats).abs().max()) <= 6e-3, form

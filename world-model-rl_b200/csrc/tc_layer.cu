@@ -2131,9 +2131,11 @@ static int tcl_max_clusters(int f) {
 // which tiling of the LayerNorm layers a call with MT row tiles uses: kLMaxSplit-CTA clusters when every row tile's
 // cluster is co-resident (few row tiles), CTA pairs for wide blocks otherwise, 0 = one CTA per row tile
 static int tcl_split_choice(int csplit, int cpair, int MT) {
-  static int off = -1;
-  if (off < 0) { const char* e = getenv("WMRL_LN_SPLIT"); off = (e && e[0] == '0') ? 1 : 0; }
-  if (off) return 0;
+  // WMRL_LN_SPLIT = 0: one CTA per row tile; 2 / 4: force that cluster form wherever it is possible (tests); unset: automatic
+  const char* e = getenv("WMRL_LN_SPLIT");
+  if (e && e[0] == '0') return 0;
+  if (e && e[0] == '2') return (cpair > 1 && tcl_max_clusters(cpair) > 0) ? cpair : 0;
+  if (e && e[0] == '4') return (csplit > 1 && MT <= tcl_max_clusters(csplit)) ? csplit : 0;
   if (csplit > 1 && MT <= tcl_max_clusters(csplit)) return csplit;
   // pairs re-read the block's input panel from both CTAs: a win while that panel is L2-resident (<= 256 row tiles =
   // 32 MB at 512 columns; measured: configs[4] shard 20.2 -> 19.1 ms forward), a loss once it streams from HBM
