@@ -619,30 +619,35 @@ __device__ __forceinline__ void lepib_carry(const LCtx& c) {
   for (int blk = c.q; blk * 32 < p.n; blk += 4) {
     const int col = c.nt * p.n + blk * 32;
     if (col >= p.Dp) break;
-    float acc[32], up[32];
+    // two 32-float arrays live at a time (96-register cap: acc + carry + upstream together spilled 260 B): the carried
+    // rows are folded into the accumulator before the upstream rows arrive
+    float acc[32];
     LPROBE(c, 0);
     tmem_ld32(c.tmem_lane + blk * 32, acc);
-    float4 cr[8];
+    {
+      float4 cr[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      cr[k] = (col + 4 * k < p.Dp) ? *reinterpret_cast<const float4*>(fpanel(p.f0, c.mt, p.Dp, col + 4 * k, c.row))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < 8; ++k)
+        cr[k] = (col + 4 * k < p.Dp) ? *reinterpret_cast<const float4*>(fpanel(p.f0, c.mt, p.Dp, col + 4 * k, c.row))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      LPROBE(c, 1);
+      tmem_ld_wait();
+      LPROBE(c, 2);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc[4 * k] += cr[k].x; acc[4 * k + 1] += cr[k].y; acc[4 * k + 2] += cr[k].z; acc[4 * k + 3] += cr[k].w;
+      }
+    }
     if (p.f1) {
+      float up[32];
       const int nr = (int)max(0LL, min(32LL, (long long)p.B - b0));
       load_rows32(c, p.f1 + (b0 * (p.H + 1) + p.t) * p.D + col, (long long)(p.H + 1) * p.D, nr, min(32, p.D - col), up);
-    } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) up[i] = 0.f;
+      for (int i = 0; i < 32; ++i) acc[i] += up[i];
     }
-    LPROBE(c, 1);
-    tmem_ld_wait();
-    LPROBE(c, 2);
+    if (!c.valid) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      acc[4 * k] = c.valid ? acc[4 * k] + cr[k].x + up[4 * k] : 0.f;
-      acc[4 * k + 1] = c.valid ? acc[4 * k + 1] + cr[k].y + up[4 * k + 1] : 0.f;
-      acc[4 * k + 2] = c.valid ? acc[4 * k + 2] + cr[k].z + up[4 * k + 2] : 0.f;
-      acc[4 * k + 3] = c.valid ? acc[4 * k + 3] + cr[k].w + up[4 * k + 3] : 0.f;
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
     }
     if (p.t > 0) {
 #pragma unroll
