@@ -8,6 +8,12 @@
  *   - Actor.forward(det.)        src/reflect/components/models/actor.py:47-52
  *   - ValueGradTrainer lambda-return loops
  *                                src/reflect/components/trainers/value/value_trainer.py:62-134
+ * and, either side of the path,
+ *   - the MLP heads over the features src/reflect/components/rssm_world_model/models.py:3-37,
+ *                                src/reflect/components/trainers/value/critic.py:4-29
+ *   - WorldModel.update's losses src/reflect/components/rssm_world_model/world_model.py:128-150
+ *   - get_features()             src/reflect/components/rssm_world_model/state/continuous.py:73-77
+ *   - WorldModelActor.__call__   src/reflect/components/rssm_world_model/memory_actor.py:34-57
  * The reference has no FFI of its own (pure Python over torch); the binding a
  * maintainer adds is the ctypes stub shown in INTEGRATION.md.
  *
