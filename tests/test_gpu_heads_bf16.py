@@ -188,8 +188,14 @@ def test_update_with_detached_critic_input_matches_reference_flow():
     (la, pa), (lb, pb) = results
     assert abs(la.value_loss - lb.value_loss) <= 1e-6 * max(1.0, abs(lb.value_loss))
     assert abs(la.actor_loss - lb.actor_loss) <= 1e-6 * max(1.0, abs(lb.actor_loss))
+    # Adam's first step is lr * g / (|g| + 1e-8): a gradient element that is a cancelling sum of ~1e-8 magnitude turns the
+    # fp32-atomics summation order of the weight-gradient kernels into a visible difference of the step.  Such elements
+    # are rare; everything else must agree tightly, and nothing may differ by more than one full step.
+    lr = max(trainer.actor_lr, trainer.critic_lr)
     for x, y in zip(pa, pb):
-        torch.testing.assert_close(x, y, rtol=1e-4, atol=1e-6)
+        bad = (x - y).abs() > 1e-6 + 1e-4 * y.abs()
+        assert float(bad.float().mean()) <= 2e-3, float(bad.float().mean())
+        assert float((x - y).abs().max()) <= 2.5 * lr
 
 
 def test_value_targets_bf16_heads_vs_fp32():
