@@ -11,7 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 import torch
 

@@ -15,7 +15,7 @@ tensors, see ``draw_imagine_noise``), ``generator=``, ``return_actions=``.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple, Union
+from typing import Optional, Tuple
 
 import torch
 from torch import nn
