@@ -223,7 +223,8 @@ def test_value_targets_bf16_heads_vs_fp32():
     assert losses.value_loss == losses.value_loss
 
 
-@pytest.mark.parametrize("rows,F_,Hh,L,O,act", [(300, 230, 512, 3, 1, 2), (129, 40, 96, 2, 5, 0), (5000, 230, 256, 3, 1, 1)])
+@pytest.mark.parametrize("rows,F_,Hh,L,O,act", [(300, 230, 512, 3, 1, 2), (129, 40, 96, 2, 5, 0), (5000, 230, 256, 3, 1, 1),
+                                                   (1, 1, 32, 1, 16, 0), (257, 17, 64, 8, 1, 1), (40, 2048, 448, 2, 3, 2)])
 def test_mlp_c_abi_guard_bands(rows, F_, Hh, L, O, act):
     """Straight through the C ABI with every caller-owned buffer sized EXACTLY as the size queries say and followed by a
     canary region: packed image, feature panel, saved activations, both workspaces, out, g_x - nothing may be written
