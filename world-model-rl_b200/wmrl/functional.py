@@ -103,7 +103,14 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream_ptr(dev) -> int:
+    """cudaStream_t of torch's current stream on ``dev`` (the raw accessor is ~10x cheaper than building a Stream
+    object; the acting step is host-latency-bound)."""
+    if _raw_stream is not None and dev.index is not None:
+        return _raw_stream(dev.index)
     return torch.cuda.current_stream(dev).cuda_stream
 
 
@@ -690,11 +697,14 @@ class ActStepPlan:
             for wd in widths:
                 offs.append(base + 4 * o)
                 o += wd
-            with torch.cuda.device(dev):
-                rc = lib.wmrl_act_step(C.byref(d), C.byref(self.w), C.byref(self.aw), e.data_ptr(), h.data_ptr(), n1.data_ptr(),
-                                       n2.data_ptr(), offs[0], offs[1], offs[2], None if disc else offs[6], offs[3], offs[4],
-                                       offs[5], None if disc else offs[7], ld, C.byref(smp) if smp is not None else None,
-                                       torch.cuda.current_stream(dev).cuda_stream)
+            args = (C.byref(d), C.byref(self.w), C.byref(self.aw), e.data_ptr(), h.data_ptr(), n1.data_ptr(), n2.data_ptr(),
+                    offs[0], offs[1], offs[2], None if disc else offs[6], offs[3], offs[4], offs[5], None if disc else offs[7],
+                    ld, C.byref(smp) if smp is not None else None, _stream_ptr(dev))
+            if torch.cuda.current_device() == dev.index:
+                rc = lib.wmrl_act_step(*args)
+            else:
+                with torch.cuda.device(dev):
+                    rc = lib.wmrl_act_step(*args)
             if rc:
                 _lib.check(rc, "wmrl_act_step")
         out = (action, post_s, post_a, post_b, deter_n, pri_s, pri_a, pri_b)
