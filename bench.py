@@ -721,7 +721,26 @@ def run_ours(args):
                 dst.copy_(src, non_blocking=True)
             ready[slot].record(copy_stream)
 
-    def e2e_run(n, host_noise=True):
+    consumer = {}
+
+    def value_loss_of(st):
+        """the rollout's real consumer (world_model.py:165-189 -> value_trainer.py:115-136): reward / done models over
+        the features, critic and target critic, lambda-return targets, value loss - the scalar the reference returns"""
+        if not consumer:
+            torch.manual_seed(9)
+            F_ = c["D"] + c["S"]
+            consumer["wm"] = wmrl.WorldModel(torch.nn.Identity(), torch.nn.Identity(),
+                                             wmrl.DenseModel(input_dim=F_, output_act=torch.nn.Sigmoid, precision="bf16"),
+                                             wmrl.DenseModel(input_dim=F_, precision="bf16"), rssm).to(dev)
+            consumer["trainer"] = wmrl.ValueGradTrainer(actor, wmrl.ValueCritic(F_, precision="bf16").to(dev))
+            consumer["trainer"].target_critic.to(dev)
+        roll = consumer["wm"].imagine_rollout(st, actor, H)
+        d = wmrl.functional.done_mask(roll.dones)
+        loss, _ = consumer["trainer"].value_loss(roll.features, roll.rewards, d)
+        wmrl.functional.clear_panel_cache()
+        return loss
+
+    def e2e_run(n, host_noise=True, with_consumer=False):
         for e in consumed:
             e.record()
         upload(0, host_noise)
@@ -735,8 +754,11 @@ def run_ours(args):
             with torch.no_grad():
                 # host_noise=False is the reference's own call shape: only the start states come from the
                 # caller, the noise is drawn on the device inside imagine_rollout (rssm.py:181 randn_like)
-                sq = rssm.imagine_rollout(st, actor, H, noise=nz if host_noise else None)
-                res = sq.deter_states[:, -1].mean() + sq.stoch_states[:, -1].mean()
+                if with_consumer:
+                    res = value_loss_of(st)
+                else:
+                    sq = rssm.imagine_rollout(st, actor, H, noise=nz if host_noise else None)
+                    res = sq.deter_states[:, -1].mean() + sq.stoch_states[:, -1].mean()
             consumed[slot].record()
             results_h[slot].copy_(res.reshape(1), non_blocking=True)
             result_ready[slot].record()
@@ -775,6 +797,26 @@ def run_ours(args):
     e2e2_value = world * B * H * args.steps / e2e2_s
     h2d2_bytes = sum(t.numel() * 4 for t in (deter0_h, stoch0_h))
 
+    # same call shape, feeding the rollout's real consumer: heads -> lambda-return -> value loss (scalar D2H)
+    e2e3_value = None
+    if not args.no_aux:
+        e2e_run(2, host_noise=False, with_consumer=True)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(args.steps, host_noise=False, with_consumer=True)
+        barrier()
+        e2e3_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e3_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e3_s = float(t.item())
+        e2e3_value = world * B * H * args.steps / e2e3_s
+        consumer.clear()
+        wmrl.functional.clear_panel_cache()
+        for p_ in rssm.parameters():
+            p_.requires_grad_(False)
+        torch.cuda.empty_cache()
+
     aux_all = None
     if not args.no_aux:
         aux_all = aux_all_ranks(c, rssm, actor, dev, world, rank, barrier)
@@ -809,6 +851,11 @@ def run_ours(args):
             "e2e_host_noise": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                                "note": "same, with the pre-drawn noise tensor also fed from pinned host memory every step "
                                        "(the parity-test call shape: 178 MB of H2D per 4 ms step)"},
+            "e2e_value_loss": None if e2e3_value is None else {
+                "value": e2e3_value, "unit": UNIT, "h2d_bytes_per_step": h2d2_bytes, "d2h_bytes_per_step": 4,
+                "note": "same call shape, the rollout feeding its real consumer through the public API: WorldModel.imagine_rollout "
+                        "(rollout -> reward / done models) -> ValueGradTrainer.value_loss (critic, target critic, lambda-return) "
+                        "-> the value-loss scalar D2H (value_trainer.py:115-136); heads on the bf16 tcgen05 chain"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": traffic, "kernel": "tc_imagine_fold_kernel",
